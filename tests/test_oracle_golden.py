@@ -1,0 +1,119 @@
+"""The oracle (oracle/uorf_oracle.py) against golden vectors produced by the live reference
+(tests/golden/make_golden.py).  CPU only."""
+import torch
+import pytest
+
+from oracle import uorf_oracle as O
+from conftest import load_golden
+
+
+def close(a, b, tol):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    assert err <= tol, f"max abs err {err} > {tol}"
+
+
+def test_posenc():
+    g = load_golden("sin_emb")
+    assert torch.equal(O.posenc(g["x"], 5), g["out"])
+
+
+@pytest.mark.parametrize("name", ["proj_8x8x6_rs4", "proj_16x16x8_rs16"])
+def test_sampling_coords(name):
+    g = load_golden(name)
+    spec = O.FrustumSpec(g["frustum"].tolist(), near=6, far=20, nss_scale=7, render_size=int(g["render_size"]))
+    c, z, r = O.sampling_coords(spec, g["cam2world"])
+    assert torch.equal(c, g["coords"]) and torch.equal(z, g["z_vals"]) and torch.equal(r, g["ray_dir"])
+    c, z, r = O.sampling_coords(spec, g["cam2world"], partitioned=True)
+    assert torch.equal(c, g["coords_p"]) and torch.equal(z, g["z_vals_p"]) and torch.equal(r, g["ray_dir_p"])
+
+
+def test_composite():
+    g = load_golden("raw2outputs")
+    rgb, dep, wn, mm = O.composite(g["raw"], g["z_vals"], g["rays_d"], render_mask=True)
+    close(rgb, g["rgb_map"], 1e-6)
+    close(dep, g["depth_map"], 1e-6)
+    close(wn, g["weights_norm"], 1e-6)
+    close(mm, g["mask_map"], 1e-6)
+
+
+@pytest.mark.parametrize("Z", [64, 40])
+@pytest.mark.parametrize("fixed", [0, 1])
+def test_decoder(Z, fixed):
+    g = load_golden(f"decoder_z{Z}_fixed{fixed}")
+    for loc in (1, 0):
+        raws, masked, unmasked, masks = O.decoder_forward(
+            g["dec"], g["coor_bg"], g["coor_fg"], g["z_slots"], g["fg_transform"], locality=bool(loc),
+            locality_ratio=float(g["locality_ratio"]), fixed_locality=bool(fixed),
+            dens_noise=float(g["dens_noise"]), noise=g["noise"])
+        close(raws, g[f"raws_loc{loc}"], 2e-6)
+        close(masked, g[f"masked_loc{loc}"], 2e-6)
+        close(unmasked, g[f"unmasked_loc{loc}"], 2e-6)
+        close(masks, g[f"masks_loc{loc}"], 2e-6)
+
+
+@pytest.mark.parametrize("Z", [64, 40])
+def test_decoder_grads(Z):
+    g = load_golden(f"decoder_z{Z}_fixed0")
+    p = {k: v.clone().requires_grad_(True) for k, v in g["dec"].items()}
+    zs = g["z_slots"].clone().requires_grad_(True)
+    raws, *_ = O.decoder_forward(p, g["coor_bg"], g["coor_fg"], zs, g["fg_transform"], locality=True,
+                                 locality_ratio=float(g["locality_ratio"]), dens_noise=0.0,
+                                 noise=torch.zeros_like(g["noise"]))
+    close(raws.detach(), g["raws_nonoise"], 2e-6)
+    (raws * g["probe"]).sum().backward()
+    close(zs.grad, g["grad_z_slots"], 1e-4)
+    for k, v in g["grad"].items():
+        scale = max(1.0, v.abs().max().item())
+        close(p[k].grad / scale, v / scale, 1e-5)
+
+
+@pytest.mark.parametrize("Z", [64, 40])
+def test_slot_attention(Z):
+    g = load_golden(f"slot_attention_z{Z}")
+    slots, attn = O.slot_attention_forward(g["sa"], g["feat"], int(g["K"]), 3, g["noise_fg"], g["noise_bg"])
+    close(slots, g["slots"], 2e-6)
+    close(attn, g["attn"], 2e-6)
+
+
+@pytest.mark.parametrize("bottom", [0, 1])
+def test_encoder(bottom):
+    g = load_golden(f"encoder_bottom{bottom}")
+    close(O.encoder_forward(g["enc"], g["x"], bool(bottom)), g["out"], 1e-6)
+
+
+def test_eval_driver():
+    g = load_golden("eval_driver")
+    spec = O.FrustumSpec([16, 16, 8], render_size=8)
+    out = O.eval_render(g["enc"], g["sa"], g["dec"], g["img"], g["cam2world"], g["azi_rot"], spec, num_slots=4,
+                        input_size=32, noise_fg=g["noise_fg"], noise_bg=g["noise_bg"])
+    close(out["x_recon"], g["x_recon"], 5e-6)
+    # sigma is unbounded (relu of a linear head): compare relative to the tensor's scale
+    for key in ("masked_raws", "unmasked_raws"):
+        s = max(1.0, g[key].abs().max().item())
+        close(out[key] / s, g[key] / s, 5e-6)
+    _, zv, rd = O.sampling_coords(spec, g["cam2world"])
+    _, maps, idx = O.slot_mask_maps(out["masked_raws"], zv, rd)
+    close(maps, g["mask_maps"], 5e-6)
+    assert (idx != g["mask_idx"]).float().mean().item() < 0.01
+
+
+@pytest.mark.parametrize("stage", ["coarse", "fine"])
+def test_train_driver(stage):
+    g = load_golden(f"train_driver_{stage}")
+    fine = stage == "fine"
+    spec = O.FrustumSpec([16, 16, 8] if fine else [8, 8, 8], render_size=8)
+    P = {pre: {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g[pre].items()} for pre in ("enc", "sa", "dec")}
+    loss, x_recon, *_ = O.train_forward(P["enc"], P["sa"], P["dec"], g["img"], g["cam2world"], g["azi_rot"], spec,
+                                        num_slots=3, stage=stage, input_size=32, supervision_size=8, bottom=fine,
+                                        noise_fg=g["noise_fg"], noise_bg=g["noise_bg"],
+                                        crop=tuple(int(c) for c in g["crop"]))
+    close(loss.detach(), g["loss_recon"], 1e-6)
+    close(x_recon.detach(), g["x_recon"], 5e-6)
+    loss.backward()
+    for pre in ("enc", "sa", "dec"):
+        for k, v in g["grad"][pre].items():
+            got = P[pre][k].grad
+            got = torch.zeros_like(v) if got is None else got
+            scale = max(1e-3, v.abs().max().item())
+            close(got / scale, v / scale, 2e-4)
