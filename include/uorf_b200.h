@@ -1,0 +1,177 @@
+/* uorf_b200.h — C ABI of libuorf_b200.so: the uORF per-scene render hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (KovenYu/uORF) has no FFI of its own: the path sits behind Python nn.Module calls.
+ * Each entry point below names the reference interface it replaces (paths relative to the reference
+ * repository root).  The host-side mirror of those interfaces (same class / function names and
+ * argument meaning) lives in uorf_b200/modules.py and binds these symbols with ctypes; INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 data unless stated; tensors are contiguous, row-major;
+ *   - the caller allocates all outputs and workspaces (no ownership crosses the ABI);
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work, they never synchronise;
+ *   - return value 0 = ok, negative = error (see UORF_ERR_*); uorf_last_error() gives the text of the
+ *     last error on the calling thread; nothing throws across the boundary;
+ *   - there is no CPU fallback: on a device that is not sm_100 every call returns UORF_ERR_DEVICE.
+ */
+#ifndef UORF_B200_H_
+#define UORF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UORF_ABI_VERSION 1
+
+#define UORF_OK 0
+#define UORF_ERR_ARG (-1)
+#define UORF_ERR_UNSUPPORTED (-2)
+#define UORF_ERR_DEVICE (-3)
+#define UORF_ERR_WORKSPACE (-4)
+
+int uorf_abi_version(void);
+const char* uorf_last_error(void);
+/* Checks that `device` is an sm_100 part and configures the kernels (max dynamic shared memory).
+ * Idempotent; every other call does it implicitly for the current device. */
+int uorf_init(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 1 — frustum sample generation.
+ * Replaces Projection.construct_sampling_coor (models/projection.py:51-113, grid built by
+ * construct_frus_coor :33-49).
+ *   z_cam       [D] camera-space depths, torch.linspace(near, far, D) of projection.py:42
+ *   cam2world   [N][4][4]
+ *   coords      [n_chunks][N*D*Hc*Wc][3]   reference order ((n*D+d)*Hc+h)*Wc+w   (ray_major = 0)
+ *                                          or ray-major   ((n*Hc+h)*Wc+w)*D+d   (ray_major = 1)
+ *   z_vals      [n_chunks][N*Hc*Wc][D]     (may be NULL)
+ *   ray_dir     [n_chunks][N*Hc*Wc][3]     (may be NULL)
+ * scale = 1 gives the unpartitioned output; scale > 1 the reference's strided partition into scale^2
+ * chunks (chunk j <-> (h0,w0) = divmod(j, scale), Hc = H/scale, Wc = W/scale).
+ * With crop_h/crop_w >= 0 (scale must be 1) only the window [crop_h, crop_h+Hc) x [crop_w, crop_w+Wc)
+ * is produced (fine-stage training crop, models/uorf_nogan_model.py:153-165); pass Hc = Wc = render size.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct uorf_frustum {
+  int32_t W, H, D;          /* frustum_size */
+  float near_plane, far_plane;
+  float spixel2cam[16];     /* inverse intrinsics, row-major 4x4 (projection.py:24-31) */
+  float nss_scale;          /* world2nss = diag(1/nss_scale) (projection.py:17-20) */
+} uorf_frustum;
+
+int uorf_sample_coords(const uorf_frustum* f, const float* z_cam, const float* cam2world, int32_t n_views, int32_t scale,
+                       int32_t crop_h, int32_t crop_w, int32_t Hc, int32_t Wc, int32_t ray_major,
+                       float* coords, float* z_vals, float* ray_dir, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 2 — fused K-slot decoder.
+ * Replaces Decoder.forward (models/model.py:106-161) including sin_emb (:261-277).
+ * Weights are the reference's state-dict tensors (fp32, [out][in] row-major).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct uorf_decoder_weights {
+  /* foreground MLP */
+  const float *f_before_w[3], *f_before_b[3]; /* f_before.{0,2,4}: [Z][33+Z], [Z][Z], [Z][Z] */
+  const float *f_after_w[3], *f_after_b[3];   /* f_after.{0,2,4}:  [Z][33+2Z], [Z][Z], [Z][Z] */
+  const float *f_after_latent_w, *f_after_latent_b; /* [Z][Z] */
+  const float *f_after_shape_w, *f_after_shape_b;   /* [1][Z] */
+  const float *f_color0_w, *f_color0_b;             /* f_color.0 [Z/4][Z] */
+  const float *f_color2_w, *f_color2_b;             /* f_color.2 [3][Z/4] */
+  /* background MLP */
+  const float *b_before_w[3], *b_before_b[3]; /* b_before.{0,2,4} */
+  const float *b_after_w[4], *b_after_b[4];   /* b_after.{0,2,4,6}; .6 is [4][Z] */
+} uorf_decoder_weights;
+
+/* precision of the width-Z layers on the tensor cores:
+ *   1 = one bf16 pass (fast mode), 3 = three-term bf16 split with fp32 accumulation (fp32-parity mode) */
+#define UORF_PASSES_BF16 1
+#define UORF_PASSES_BF16X3 3
+
+/* Bytes of the prepared weight image for (K slots, passes). */
+size_t uorf_decoder_image_bytes(int32_t K, int32_t passes);
+
+/* Packs the weights into the tensor-core image and hoists the slot-latent columns of the two wide
+ * layers into per-slot biases.  Must be re-run when weights or z_slots change (once per scene).
+ *   z_slots [K][Z] (slot 0 = background), image: uorf_decoder_image_bytes(K, passes) bytes, 1024-aligned. */
+int uorf_decoder_prepare(const uorf_decoder_weights* w, const float* z_slots, int32_t K, int32_t Z,
+                         int32_t n_freq, int32_t n_layers, int32_t passes, void* image, void* stream);
+
+typedef struct uorf_decoder_args {
+  const float* coor_bg;     /* [P][3] */
+  const float* coor_fg;     /* slot s (0..K-2), point p at coor_fg + s*fg_slot_stride + 3*p */
+  int64_t fg_slot_stride;   /* in floats; 0 for the reference's expand() view of coor_bg */
+  const float* fg_transform;/* device: 9 floats (3x3) or, with fixed_locality, 16 floats (4x4) */
+  const float* noise;       /* [K][P] standard normals (model.py:155) or NULL when dens_noise == 0 */
+  float dens_noise;
+  float locality_ratio;
+  int32_t locality;         /* Decoder.locality */
+  int32_t fixed_locality;   /* Decoder.fixed_locality */
+  int64_t P;
+  int32_t K;
+  int32_t passes;
+  const void* image;        /* from uorf_decoder_prepare (same K, passes) */
+  float* workspace;         /* [P][4] floats scratch */
+  /* outputs; any may be NULL to skip the write */
+  float* raws;              /* [P][4] */
+  float* masked_raws;       /* [K][P][4] */
+  float* unmasked_raws;     /* [K][P][4] */
+  float* masks;             /* [K][P] */
+  uint8_t* outside;         /* [K-1][P] locality flags (outsider_idx, model.py:121/128) */
+} uorf_decoder_args;
+
+int uorf_decoder_forward(const uorf_decoder_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 3 — alpha compositing.  Replaces raw2outputs (models/model.py:279-313).
+ *   raw [R][D][4] (rgb, sigma), z_vals [R][D], rays_d [R][3]
+ *   rgb_map [R][3], depth_map [R], weights_norm [R][D] (may be NULL), mask_map [R] (NULL unless render_mask)
+ * ------------------------------------------------------------------------------------------- */
+int uorf_composite_forward(const float* raw, const float* z_vals, const float* rays_d, int64_t R, int32_t D,
+                           float* rgb_map, float* depth_map, float* weights_norm, float* mask_map,
+                           void* stream);
+/* Backward of rgb_map w.r.t. raw (weights_norm is detached in the reference, model.py:304, so depth
+ * carries no gradient).  grad_rgb [R][3] -> grad_raw [R][D][4]. */
+int uorf_composite_backward(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb,
+                            int64_t R, int32_t D, float* grad_raw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Kernel 4 — slot attention.  Replaces SlotAttention.forward (models/model.py:205-258), batch 1.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct uorf_slot_attention_weights {
+  const float *slots_mu, *slots_logsigma, *slots_mu_bg, *slots_logsigma_bg; /* [C] */
+  const float *norm_feat_w, *norm_feat_b;                                     /* LayerNorm [C] */
+  const float *to_k_w, *to_v_w;                                               /* [C][C], no bias */
+  const float *to_q_ln_w, *to_q_ln_b, *to_q_w;                                /* to_q.0 / to_q.1 */
+  const float *to_q_bg_ln_w, *to_q_bg_ln_b, *to_q_bg_w;
+  const float *gru_w_ih, *gru_w_hh, *gru_b_ih, *gru_b_hh;                     /* [3C][C], [3C] */
+  const float *gru_bg_w_ih, *gru_bg_w_hh, *gru_bg_b_ih, *gru_bg_b_hh;
+  const float *to_res_ln_w, *to_res_ln_b, *to_res_w1, *to_res_b1, *to_res_w2, *to_res_b2; /* [Hd][C], [C][Hd] */
+  const float *to_res_bg_ln_w, *to_res_bg_ln_b, *to_res_bg_w1, *to_res_bg_b1, *to_res_bg_w2, *to_res_bg_b2;
+} uorf_slot_attention_weights;
+
+/* Floats of workspace uorf_slot_attention_forward needs. */
+size_t uorf_slot_attention_workspace_floats(int32_t n_tokens, int32_t C, int32_t K);
+
+/*   feat: element (token t, channel c) at feat + t*feat_token_stride + c*feat_chan_stride (floats), so the
+ *         Encoder's NCHW feature map is consumed in place (token stride 1, channel stride n_tokens);
+ *   noise_fg [K-1][C], noise_bg [C] (the randn draws of model.py:216,219)
+ *   slots [K][C] (slot 0 = background), attn [K][n_tokens] (last iteration, includes +eps) */
+int uorf_slot_attention_forward(const uorf_slot_attention_weights* w, const float* feat, int64_t feat_token_stride,
+                                int64_t feat_chan_stride, const float* noise_fg, const float* noise_bg,
+                                int32_t n_tokens, int32_t C, int32_t K, int32_t hidden, int32_t iters, float eps,
+                                float* workspace, float* slots, float* attn, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Test hook: one 128 x N x (16*ksteps) bf16 GEMM on the tcgen05 path the decoder uses
+ * (A rows written to TMEM by threads, B a swizzled shared-memory tile).  a [128][64], b [N][64] fp32
+ * (rounded to bf16 inside), d [128][N].  Used by tests/ to pin the tensor-core data layouts.
+ * ------------------------------------------------------------------------------------------- */
+int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, int32_t passes, float* d,
+                    void* stream);
+/* Test hook: site code written by a kernel whose mbarrier wait timed out (0 = none). */
+int uorf_debug_flag(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UORF_B200_H_ */

@@ -1,0 +1,234 @@
+// extern "C" surface of libuorf_b200.so (declared in include/uorf_b200.h): argument validation, the
+// per-device context, error strings.  Kernels live in the sibling .cu files.
+#include <cuda_runtime.h>
+#include <mutex>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/uorf_b200.h"
+#include "common.cuh"
+#include "decoder_layout.h"
+
+namespace uorf {
+int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float* cam2world, int n_views, int scale, int crop_h,
+                         int crop_w, int Hc, int Wc, int ray_major, float* coords, float* z_vals, float* ray_dir,
+                         cudaStream_t stream);
+int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int K, int Z, int passes, void* image,
+                        cudaStream_t stream);
+int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, cudaStream_t stream);
+int launch_composite_fwd(const float* raw, const float* z_vals, const float* rays_d, long long R, int D, float* rgb_map,
+                         float* depth_map, float* weights_norm, float* mask_map, int num_sms, cudaStream_t stream);
+int launch_composite_bwd(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb, long long R, int D,
+                         float* grad_raw, int num_sms, cudaStream_t stream);
+size_t slot_attention_ws_floats(int ntok, int C, int K);
+int launch_slot_attention(const uorf_slot_attention_weights* w, const float* feat, long long feat_ts, long long feat_cs,
+                          const float* noise_fg, const float* noise_bg, int ntok, int C, int K, int hidden, int iters, float eps,
+                          float* workspace, float* slots, float* attn, cudaStream_t stream);
+int launch_probe_gemm(const float* a, const float* b, int N, int ksteps, int passes, float* d, int* err_flag, cudaStream_t stream);
+}  // namespace uorf
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+
+struct DeviceCtx {
+  std::once_flag once;
+  int status = UORF_ERR_DEVICE;
+  int num_sms = 0;
+  int* err_flag_host = nullptr;  // pinned + mapped: still readable by the host after a device trap
+  int* err_flag_dev = nullptr;
+  char why[256] = "";
+};
+constexpr int kMaxDevices = 64;
+DeviceCtx g_ctx[kMaxDevices];
+
+void init_device(DeviceCtx* c, int device) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    snprintf(c->why, sizeof(c->why), "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return;
+  }
+  if (prop.major != 10) {
+    snprintf(c->why, sizeof(c->why), "device %d is sm_%d%d; libuorf_b200 runs on sm_100 (B200) only and has no fallback", device,
+             prop.major, prop.minor);
+    return;
+  }
+  c->num_sms = prop.multiProcessorCount;
+  e = cudaHostAlloc(reinterpret_cast<void**>(&c->err_flag_host), sizeof(int), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *c->err_flag_host = 0;
+    e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->err_flag_dev), c->err_flag_host, 0);
+  }
+  if (e != cudaSuccess) {
+    snprintf(c->why, sizeof(c->why), "pinned flag allocation: %s", cudaGetErrorString(e));
+    return;
+  }
+  c->status = UORF_OK;
+}
+
+// context of the CURRENT device (or error)
+DeviceCtx* ctx() {
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= kMaxDevices) {
+    fail(UORF_ERR_DEVICE, "no current CUDA device%s");
+    return nullptr;
+  }
+  DeviceCtx* c = &g_ctx[device];
+  std::call_once(c->once, init_device, c, device);
+  if (c->status != UORF_OK) {
+    fail(c->status, "%s", c->why);
+    return nullptr;
+  }
+  return c;
+}
+
+int check_launch(int rc, const char* what) {
+  if (rc == UORF_OK) return rc;
+  if (rc == UORF_ERR_DEVICE) {
+    cudaError_t e = cudaGetLastError();
+    static thread_local char buf[256];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    return fail(rc, "%s", buf);
+  }
+  return fail(rc, "%s: unsupported shape", what);
+}
+
+}  // namespace
+
+extern "C" {
+
+int uorf_abi_version(void) { return UORF_ABI_VERSION; }
+const char* uorf_last_error(void) { return g_err; }
+
+int uorf_init(int device) {
+  if (device < 0 || device >= kMaxDevices) return fail(UORF_ERR_ARG, "device index out of range%s");
+  DeviceCtx* c = &g_ctx[device];
+  std::call_once(c->once, init_device, c, device);
+  if (c->status != UORF_OK) return fail(c->status, "%s", c->why);
+  return UORF_OK;
+}
+
+int uorf_debug_flag(void) {
+  DeviceCtx* c = ctx();
+  return c && c->err_flag_host ? *c->err_flag_host : -1;
+}
+
+int uorf_sample_coords(const uorf_frustum* f, const float* z_cam, const float* cam2world, int32_t n_views, int32_t scale,
+                       int32_t crop_h, int32_t crop_w, int32_t Hc, int32_t Wc, int32_t ray_major, float* coords, float* z_vals,
+                       float* ray_dir, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  if (!f || !z_cam || !cam2world || !coords) return fail(UORF_ERR_ARG, "uorf_sample_coords: null pointer%s");
+  if (f->W <= 0 || f->H <= 0 || f->D <= 0 || n_views < 0 || scale < 1 || Hc <= 0 || Wc <= 0)
+    return fail(UORF_ERR_ARG, "uorf_sample_coords: bad sizes%s");
+  if (f->W != f->H) return fail(UORF_ERR_UNSUPPORTED, "uorf_sample_coords: W != H (the reference's ray_dir view needs a square frustum)%s");
+  const bool crop = crop_h >= 0 || crop_w >= 0;
+  if (crop) {
+    if (scale != 1 || crop_h < 0 || crop_w < 0 || crop_h + Hc > f->H || crop_w + Wc > f->W)
+      return fail(UORF_ERR_ARG, "uorf_sample_coords: bad crop window%s");
+  } else if (Hc * scale != f->H || Wc * scale != f->W) {
+    return fail(UORF_ERR_ARG, "uorf_sample_coords: Hc*scale != H or Wc*scale != W%s");
+  }
+  return check_launch(uorf::launch_sample_coords(f, z_cam, cam2world, n_views, scale, crop ? crop_h : -1, crop ? crop_w : -1, Hc, Wc,
+                                                 ray_major, coords, z_vals, ray_dir, static_cast<cudaStream_t>(stream)),
+                      "uorf_sample_coords");
+}
+
+size_t uorf_decoder_image_bytes(int32_t K, int32_t passes) {
+  if (K < 2 || (passes != 1 && passes != 3)) return 0;
+  return (size_t)uorf::blob_bytes_total(passes, K);
+}
+
+int uorf_decoder_prepare(const uorf_decoder_weights* w, const float* z_slots, int32_t K, int32_t Z, int32_t n_freq,
+                         int32_t n_layers, int32_t passes, void* image, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  if (!w || !z_slots || !image) return fail(UORF_ERR_ARG, "uorf_decoder_prepare: null pointer%s");
+  if ((reinterpret_cast<uintptr_t>(image) & 1023) != 0) return fail(UORF_ERR_ARG, "uorf_decoder_prepare: image must be 1024-byte aligned%s");
+  if (passes != 1 && passes != 3) return fail(UORF_ERR_ARG, "uorf_decoder_prepare: passes must be 1 or 3%s");
+  if (K < 2 || K > 16) return fail(UORF_ERR_UNSUPPORTED, "uorf_decoder_prepare: K must be in [2,16]%s");
+  if (Z < 4 || Z > uorf::kZPad || (Z % 4) != 0) return fail(UORF_ERR_UNSUPPORTED, "uorf_decoder_prepare: z_dim must be a multiple of 4, <= 64%s");
+  if (n_freq != 5 || n_layers != 3) return fail(UORF_ERR_UNSUPPORTED, "uorf_decoder_prepare: only n_freq=5, n_layers=3 (all shipped configs)%s");
+  return check_launch(uorf::launch_decoder_prep(w, z_slots, K, Z, passes, image, static_cast<cudaStream_t>(stream)),
+                      "uorf_decoder_prepare");
+}
+
+int uorf_decoder_forward(const uorf_decoder_args* a, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  if (!a || !a->coor_bg || !a->coor_fg || !a->fg_transform || !a->image || !a->workspace)
+    return fail(UORF_ERR_ARG, "uorf_decoder_forward: null pointer%s");
+  if (a->passes != 1 && a->passes != 3) return fail(UORF_ERR_ARG, "uorf_decoder_forward: passes must be 1 or 3%s");
+  if (a->K < 2 || a->K > 16) return fail(UORF_ERR_UNSUPPORTED, "uorf_decoder_forward: K must be in [2,16]%s");
+  if (a->P < 0 || a->P > (1LL << 37)) return fail(UORF_ERR_ARG, "uorf_decoder_forward: bad P%s");
+  if (a->dens_noise != 0.f && !a->noise) return fail(UORF_ERR_ARG, "uorf_decoder_forward: dens_noise != 0 needs a noise tensor%s");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a->workspace) | reinterpret_cast<uintptr_t>(a->raws) |
+                       reinterpret_cast<uintptr_t>(a->masked_raws) | reinterpret_cast<uintptr_t>(a->unmasked_raws) |
+                       reinterpret_cast<uintptr_t>(a->image);
+  if (al & 15) return fail(UORF_ERR_ARG, "uorf_decoder_forward: buffers must be 16-byte aligned%s");
+  return check_launch(uorf::launch_decoder_fwd(a, c->num_sms, c->err_flag_dev, static_cast<cudaStream_t>(stream)),
+                      "uorf_decoder_forward");
+}
+
+int uorf_composite_forward(const float* raw, const float* z_vals, const float* rays_d, int64_t R, int32_t D, float* rgb_map,
+                           float* depth_map, float* weights_norm, float* mask_map, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  if (!raw || !z_vals || !rays_d || !rgb_map || !depth_map) return fail(UORF_ERR_ARG, "uorf_composite_forward: null pointer%s");
+  if (R < 0 || D < 1) return fail(UORF_ERR_ARG, "uorf_composite_forward: bad sizes%s");
+  if (D > 256) return fail(UORF_ERR_UNSUPPORTED, "uorf_composite_forward: D > 256%s");
+  if (reinterpret_cast<uintptr_t>(raw) & 15) return fail(UORF_ERR_ARG, "uorf_composite_forward: raw must be 16-byte aligned%s");
+  return check_launch(uorf::launch_composite_fwd(raw, z_vals, rays_d, R, D, rgb_map, depth_map, weights_norm, mask_map, c->num_sms,
+                                                 static_cast<cudaStream_t>(stream)),
+                      "uorf_composite_forward");
+}
+
+int uorf_composite_backward(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb, int64_t R, int32_t D,
+                            float* grad_raw, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  if (!raw || !z_vals || !rays_d || !grad_rgb || !grad_raw) return fail(UORF_ERR_ARG, "uorf_composite_backward: null pointer%s");
+  if (R < 0 || D < 1) return fail(UORF_ERR_ARG, "uorf_composite_backward: bad sizes%s");
+  if (D > 256) return fail(UORF_ERR_UNSUPPORTED, "uorf_composite_backward: D > 256%s");
+  if ((reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(grad_raw)) & 15)
+    return fail(UORF_ERR_ARG, "uorf_composite_backward: raw/grad_raw must be 16-byte aligned%s");
+  return check_launch(uorf::launch_composite_bwd(raw, z_vals, rays_d, grad_rgb, R, D, grad_raw, c->num_sms,
+                                                 static_cast<cudaStream_t>(stream)),
+                      "uorf_composite_backward");
+}
+
+size_t uorf_slot_attention_workspace_floats(int32_t n_tokens, int32_t C, int32_t K) {
+  return uorf::slot_attention_ws_floats(n_tokens, C, K);
+}
+
+int uorf_slot_attention_forward(const uorf_slot_attention_weights* w, const float* feat, int64_t feat_token_stride,
+                                int64_t feat_chan_stride, const float* noise_fg, const float* noise_bg, int32_t n_tokens,
+                                int32_t C, int32_t K, int32_t hidden, int32_t iters, float eps, float* workspace, float* slots,
+                                float* attn, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  if (!w || !feat || !noise_fg || !noise_bg || !workspace || !slots || !attn)
+    return fail(UORF_ERR_ARG, "uorf_slot_attention_forward: null pointer%s");
+  if (n_tokens < 1 || iters < 1) return fail(UORF_ERR_ARG, "uorf_slot_attention_forward: bad sizes%s");
+  return check_launch(uorf::launch_slot_attention(w, feat, feat_token_stride, feat_chan_stride, noise_fg, noise_bg, n_tokens, C, K,
+                                                  hidden, iters, eps, workspace, slots, attn, static_cast<cudaStream_t>(stream)),
+                      "uorf_slot_attention_forward");
+}
+
+int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, int32_t passes, float* d, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  if (!a || !b || !d) return fail(UORF_ERR_ARG, "uorf_probe_gemm: null pointer%s");
+  if (N < 16 || N > 64 || (N % 16) || ksteps < 1 || ksteps > 4 || (passes != 1 && passes != 3))
+    return fail(UORF_ERR_ARG, "uorf_probe_gemm: bad shape%s");
+  return check_launch(uorf::launch_probe_gemm(a, b, N, ksteps, passes, d, c->err_flag_dev, static_cast<cudaStream_t>(stream)),
+                      "uorf_probe_gemm");
+}
+
+}  // extern "C"

@@ -1,0 +1,448 @@
+"""Host-side mirror of the reference's hot-path module API (reference models/model.py, models/projection.py).
+
+Same class / function names, constructor arguments, forward signatures, return shapes and state-dict keys as
+the reference, so a reference driver can swap its imports for these.  All arithmetic below the module
+boundary runs in libuorf_b200.so (hand-written sm_100a kernels, C ABI in include/uorf_b200.h); PyTorch is used
+for device memory, streams and autograd plumbing only.  There is no CPU / eager fallback: tensors must live on
+a CUDA device and the shared object must be loadable, otherwise the call raises.
+
+    Encoder            models/model.py:11-61     (cuDNN convolutions through torch; no custom kernel)
+    SlotAttention      models/model.py:164-258   -> uorf_slot_attention_forward
+    Decoder            models/model.py:64-161    -> uorf_decoder_prepare + uorf_decoder_forward
+    sin_emb            models/model.py:261-277   (fused into the decoder kernel; standalone version for callers)
+    raw2outputs        models/model.py:279-313   -> uorf_composite_forward / _backward
+    Projection         models/projection.py:6-113 -> uorf_sample_coords
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+from torch.nn import init
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _stream(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.UorfError("uorf_b200 modules run on CUDA tensors only (there is no CPU fallback)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ======================================================================================================
+# Encoder — stays on cuDNN (north_star lists no encoder kernel); identical structure and state-dict keys.
+# ======================================================================================================
+class Encoder(nn.Module):
+    """reference models/model.py:11-61"""
+
+    def __init__(self, input_nc=3, z_dim=64, bottom=False):
+        super().__init__()
+        self.bottom = bottom
+        if self.bottom:
+            self.enc_down_0 = nn.Sequential(nn.Conv2d(input_nc + 4, z_dim, 3, stride=1, padding=1), nn.ReLU(True))
+        self.enc_down_1 = nn.Sequential(nn.Conv2d(z_dim if bottom else input_nc + 4, z_dim, 3,
+                                                  stride=2 if bottom else 1, padding=1), nn.ReLU(True))
+        self.enc_down_2 = nn.Sequential(nn.Conv2d(z_dim, z_dim, 3, stride=2, padding=1), nn.ReLU(True))
+        self.enc_down_3 = nn.Sequential(nn.Conv2d(z_dim, z_dim, 3, stride=2, padding=1), nn.ReLU(True))
+        self.enc_up_3 = nn.Sequential(nn.Conv2d(z_dim, z_dim, 3, stride=1, padding=1), nn.ReLU(True),
+                                      nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False))
+        self.enc_up_2 = nn.Sequential(nn.Conv2d(z_dim * 2, z_dim, 3, stride=1, padding=1), nn.ReLU(True),
+                                      nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False))
+        self.enc_up_1 = nn.Sequential(nn.Conv2d(z_dim * 2, z_dim, 3, stride=1, padding=1), nn.ReLU(True))
+        self._planes = {}
+
+    def _pixel_planes(self, H, W, device):
+        key = (H, W, str(device))
+        if key not in self._planes:
+            # built on the CPU exactly like the reference (model.py:43-48), then moved: bit-identical planes
+            X = torch.linspace(-1, 1, W)
+            Y = torch.linspace(-1, 1, H)
+            y1, x1 = torch.meshgrid([Y, X], indexing="ij")
+            self._planes[key] = torch.stack([x1, 2 - x1, y1, 2 - y1]).unsqueeze(0).to(device)
+        return self._planes[key]
+
+    def forward(self, x):
+        W, H = x.shape[3], x.shape[2]
+        x_ = torch.cat([x, self._pixel_planes(H, W, x.device).expand(x.shape[0], -1, -1, -1)], dim=1)
+        if self.bottom:
+            x_down_1 = self.enc_down_1(self.enc_down_0(x_))
+        else:
+            x_down_1 = self.enc_down_1(x_)
+        x_down_2 = self.enc_down_2(x_down_1)
+        x_down_3 = self.enc_down_3(x_down_2)
+        x_up_3 = self.enc_up_3(x_down_3)
+        x_up_2 = self.enc_up_2(torch.cat([x_up_3, x_down_2], dim=1))
+        return self.enc_up_1(torch.cat([x_up_2, x_down_1], dim=1))
+
+
+# ======================================================================================================
+# sin_emb (standalone; the decoder kernel computes it on chip)
+# ======================================================================================================
+def sin_emb(x, n_freq=5, keep_ori=True):
+    """reference models/model.py:261-277.  Px3 -> Px(3+6*n_freq)."""
+    embedded = [x] if keep_ori else []
+    for i in range(n_freq):
+        f = float(2 ** i)
+        embedded += [torch.sin(f * x), torch.cos(f * x)]
+    return torch.cat(embedded, dim=1)
+
+
+# ======================================================================================================
+# raw2outputs
+# ======================================================================================================
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, z_vals, rays_d, render_mask):
+        _require_cuda(raw, z_vals, rays_d)
+        raw_c, z_c, d_c = _f32c(raw), _f32c(z_vals), _f32c(rays_d)
+        R, D = raw_c.shape[0], raw_c.shape[1]
+        rgb = torch.empty(R, 3, device=raw.device, dtype=torch.float32)
+        depth = torch.empty(R, device=raw.device, dtype=torch.float32)
+        wn = torch.empty(R, D, device=raw.device, dtype=torch.float32)
+        mm = torch.empty(R, device=raw.device, dtype=torch.float32) if render_mask else None
+        check(lib().uorf_composite_forward(raw_c.data_ptr(), z_c.data_ptr(), d_c.data_ptr(), R, D, rgb.data_ptr(),
+                                           depth.data_ptr(), wn.data_ptr(), _ptr(mm), _stream(raw)),
+              "uorf_composite_forward")
+        ctx.save_for_backward(raw_c, z_c, d_c)
+        ctx.mark_non_differentiable(depth, wn)
+        if render_mask:
+            ctx.mark_non_differentiable(mm)
+            return rgb, depth, wn, mm
+        return rgb, depth, wn
+
+    @staticmethod
+    def backward(ctx, g_rgb, *unused):
+        raw_c, z_c, d_c = ctx.saved_tensors
+        R, D = raw_c.shape[0], raw_c.shape[1]
+        g = _f32c(g_rgb)
+        g_raw = torch.empty_like(raw_c)
+        check(lib().uorf_composite_backward(raw_c.data_ptr(), z_c.data_ptr(), d_c.data_ptr(), g.data_ptr(), R, D,
+                                            g_raw.data_ptr(), _stream(raw_c)), "uorf_composite_backward")
+        return g_raw, None, None, None
+
+
+def raw2outputs(raw, z_vals, rays_d, render_mask=False):
+    """reference models/model.py:279-313.  raw RxDx4, z_vals RxD, rays_d Rx3 ->
+    rgb_map Rx3, depth_map R, weights_norm RxD [, mask_map R].
+    Gradients flow from rgb_map to raw (depth uses detached weights in the reference; mask_map is only used
+    under no_grad by the reference's drivers)."""
+    return _Composite.apply(raw, z_vals, rays_d, bool(render_mask))
+
+
+# ======================================================================================================
+# Projection
+# ======================================================================================================
+class Projection(object):
+    """reference models/projection.py:6-113 (same constructor and construct_sampling_coor signature)."""
+
+    def __init__(self, focal_ratio=(350. / 320., 350. / 240.), near=5, far=16, frustum_size=[128, 128, 128],
+                 device='cpu', nss_scale=7, render_size=(64, 64)):
+        self.render_size = render_size
+        self.device = torch.device(device)
+        self.focal_ratio = focal_ratio
+        self.near = near
+        self.far = far
+        self.frustum_size = frustum_size
+        self.nss_scale = nss_scale
+        # host-side constants computed exactly as the reference does (projection.py:17-31,42)
+        self.world2nss = torch.tensor([[1 / nss_scale, 0, 0, 0], [0, 1 / nss_scale, 0, 0],
+                                       [0, 0, 1 / nss_scale, 0], [0, 0, 0, 1]]).unsqueeze(0).to(self.device)
+        focal_x = self.focal_ratio[0] * self.frustum_size[0]
+        focal_y = self.focal_ratio[1] * self.frustum_size[1]
+        bias_x = (self.frustum_size[0] - 1.) / 2.
+        bias_y = (self.frustum_size[1] - 1.) / 2.
+        intrinsic_mat = torch.tensor([[focal_x, 0, bias_x, 0], [0, focal_y, bias_y, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+        self.cam2spixel = intrinsic_mat.to(self.device)
+        spixel2cam = intrinsic_mat.inverse()
+        self.spixel2cam = spixel2cam.to(self.device)
+        W, H, D = self.frustum_size
+        self._z_cam = torch.linspace(self.near, self.far, D).to(self.device)
+        f = _lib.Frustum()
+        f.W, f.H, f.D = int(W), int(H), int(D)
+        f.near_plane, f.far_plane = float(near), float(far)
+        for i, v in enumerate(spixel2cam.flatten().tolist()):
+            f.spixel2cam[i] = v
+        f.nss_scale = float(nss_scale)
+        self._frustum = f
+
+    def construct_sampling_coor(self, cam2world, partitioned=False, ray_major=False, crop=None):
+        """cam2world Nx4x4 -> frus_nss_coor (N*D*H*W)x3, z_vals (N*H*W)xD, ray_dir (N*H*W)x3
+        (leading scale^2 chunk dim when partitioned), reference projection.py:51-113.
+
+        Extensions used by the B200 drivers (default off, so the reference call is unchanged):
+          ray_major=True  points ordered (n, h, w, d): the decoder output is then directly the RxDx4 tensor
+                          raw2outputs wants (no permute copy, reference uorf_eval_model.py:147);
+          crop=(h0, w0)   only the render_size window at (h0, w0) (fine-stage training crop,
+                          reference uorf_nogan_model.py:153-165), never materialising the full frustum.
+        """
+        _require_cuda(cam2world)
+        cam2world = _f32c(cam2world)
+        N = cam2world.shape[0]
+        W, H, D = self.frustum_size
+        dev = cam2world.device
+        if self._z_cam.device != dev:
+            self._z_cam = self._z_cam.to(dev)
+        if crop is not None:
+            if partitioned:
+                raise ValueError("crop and partitioned are mutually exclusive")
+            scale, Hc, Wc = 1, int(self.render_size[0]), int(self.render_size[1])
+            ch, cw = int(crop[0]), int(crop[1])
+        else:
+            scale = H // self.render_size[0] if partitioned else 1
+            Hc, Wc = H // scale, W // scale
+            ch = cw = -1
+        nchunk = scale * scale
+        P, R = N * D * Hc * Wc, N * Hc * Wc
+        coords = torch.empty(nchunk, P, 3, device=dev, dtype=torch.float32)
+        z_vals = torch.empty(nchunk, R, D, device=dev, dtype=torch.float32)
+        ray_dir = torch.empty(nchunk, R, 3, device=dev, dtype=torch.float32)
+        check(lib().uorf_sample_coords(C.byref(self._frustum), self._z_cam.data_ptr(), cam2world.data_ptr(), N, scale, ch, cw,
+                                       Hc, Wc, 1 if ray_major else 0, coords.data_ptr(), z_vals.data_ptr(),
+                                       ray_dir.data_ptr(), _stream(cam2world)), "uorf_sample_coords")
+        if partitioned:
+            return coords, z_vals, ray_dir
+        return coords[0], z_vals[0], ray_dir[0]
+
+
+# ======================================================================================================
+# SlotAttention
+# ======================================================================================================
+class SlotAttention(nn.Module):
+    """reference models/model.py:164-258 (same parameters / state-dict keys)."""
+
+    def __init__(self, num_slots, in_dim=64, slot_dim=64, iters=3, eps=1e-8, hidden_dim=128):
+        super().__init__()
+        self.num_slots = num_slots
+        self.iters = iters
+        self.eps = eps
+        self.scale = slot_dim ** -0.5
+        self.slots_mu = nn.Parameter(torch.randn(1, 1, slot_dim))
+        self.slots_logsigma = nn.Parameter(torch.zeros(1, 1, slot_dim))
+        init.xavier_uniform_(self.slots_logsigma)
+        self.slots_mu_bg = nn.Parameter(torch.randn(1, 1, slot_dim))
+        self.slots_logsigma_bg = nn.Parameter(torch.zeros(1, 1, slot_dim))
+        init.xavier_uniform_(self.slots_logsigma_bg)
+        self.to_k = nn.Linear(in_dim, slot_dim, bias=False)
+        self.to_v = nn.Linear(in_dim, slot_dim, bias=False)
+        self.to_q = nn.Sequential(nn.LayerNorm(slot_dim), nn.Linear(slot_dim, slot_dim, bias=False))
+        self.to_q_bg = nn.Sequential(nn.LayerNorm(slot_dim), nn.Linear(slot_dim, slot_dim, bias=False))
+        self.gru = nn.GRUCell(slot_dim, slot_dim)
+        self.gru_bg = nn.GRUCell(slot_dim, slot_dim)
+        hidden_dim = max(slot_dim, hidden_dim)
+        self.hidden_dim = hidden_dim
+        self.to_res = nn.Sequential(nn.LayerNorm(slot_dim), nn.Linear(slot_dim, hidden_dim), nn.ReLU(inplace=True),
+                                    nn.Linear(hidden_dim, slot_dim))
+        self.to_res_bg = nn.Sequential(nn.LayerNorm(slot_dim), nn.Linear(slot_dim, hidden_dim), nn.ReLU(inplace=True),
+                                       nn.Linear(hidden_dim, slot_dim))
+        self.norm_feat = nn.LayerNorm(in_dim)
+        self.slot_dim = slot_dim
+        self.in_dim = in_dim
+
+    def _weights(self) -> _lib.SlotAttentionWeights:
+        sd = dict(self.named_parameters())
+        w = _lib.SlotAttentionWeights()
+        keep = []
+        for field, key in _lib.SA_STATE_KEYS.items():
+            t = _f32c(sd[key].detach())
+            keep.append(t)
+            setattr(w, field, t.data_ptr())
+        w._keep = keep
+        return w
+
+    def forward(self, feat, num_slots=None, noise=None):
+        """feat BxNxC (B must be 1, as in every reference driver) -> slots BxKxC, attn BxKxN.
+        `noise` = (noise_fg (K-1)xC, noise_bg 1xC) overrides the two randn draws (model.py:216,219);
+        by default they are drawn from torch's CUDA generator in the reference's order."""
+        _require_cuda(feat)
+        if torch.is_grad_enabled() and (feat.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError(
+                "SlotAttention backward kernel is not built yet (SURVEY section 8 row a2, backward): call under "
+                "torch.no_grad(); uorf_b200 does not fall back to eager PyTorch")
+        B, N, Cin = feat.shape
+        if B != 1:
+            raise _lib.UorfError("SlotAttention kernel handles batch 1 (one scene), as the reference drivers do")
+        K = num_slots if num_slots is not None else self.num_slots
+        Cs = self.slot_dim
+        if Cin != Cs:
+            raise _lib.UorfError("in_dim must equal slot_dim (true for every reference configuration)")
+        dev = feat.device
+        if noise is None:
+            noise_fg = torch.randn(1, K - 1, Cs, device=dev)
+            noise_bg = torch.randn(1, 1, Cs, device=dev)
+        else:
+            noise_fg, noise_bg = noise
+        noise_fg = _f32c(noise_fg.reshape(K - 1, Cs))
+        noise_bg = _f32c(noise_bg.reshape(Cs))
+        feat = feat if feat.dtype == torch.float32 else feat.float()
+        f0 = feat[0]
+        ws = torch.empty(lib().uorf_slot_attention_workspace_floats(N, Cs, K), device=dev, dtype=torch.float32)
+        slots = torch.empty(1, K, Cs, device=dev, dtype=torch.float32)
+        attn = torch.empty(1, K, N, device=dev, dtype=torch.float32)
+        w = self._weights()
+        check(lib().uorf_slot_attention_forward(C.byref(w), f0.data_ptr(), f0.stride(0), f0.stride(1), noise_fg.data_ptr(),
+                                                noise_bg.data_ptr(), N, Cs, K, self.hidden_dim, self.iters, float(self.eps),
+                                                ws.data_ptr(), slots.data_ptr(), attn.data_ptr(), _stream(feat)),
+              "uorf_slot_attention_forward")
+        return slots, attn
+
+
+# ======================================================================================================
+# Decoder
+# ======================================================================================================
+class Decoder(nn.Module):
+    """reference models/model.py:64-161 (same parameters / state-dict keys, same forward signature).
+
+    Extra, B200-specific knobs (attributes; defaults reproduce the reference call):
+      precision   'bf16x3' (default): three-term bf16 split on the tensor cores, fp32 accumulation - meets the
+                  1e-4 fp32-parity bar;  'bf16': one pass, ~3x less tensor work, tolerance stated in DESIGN.md.
+      emit        which of ('raws', 'masked_raws', 'unmasked_raws', 'masks') to materialise; skipped outputs are
+                  returned as None (the API-mandated per-slot tensors are 36*K bytes per point of HBM writes).
+      match_rng_stream  draw the reference's unconditional randn_like (model.py:155) even when dens_noise == 0,
+                  so later draws from the same generator line up with the reference.
+    """
+
+    ALL_OUTPUTS = ("raws", "masked_raws", "unmasked_raws", "masks")
+
+    def __init__(self, n_freq=5, input_dim=33 + 64, z_dim=64, n_layers=3, locality=True, locality_ratio=4 / 7,
+                 fixed_locality=False):
+        super().__init__()
+        self.n_freq = n_freq
+        self.locality = locality
+        self.locality_ratio = locality_ratio
+        self.fixed_locality = fixed_locality
+        self.out_ch = 4
+        self.z_dim = z_dim
+        self.n_layers = n_layers
+        before_skip = [nn.Linear(input_dim, z_dim), nn.ReLU(True)]
+        after_skip = [nn.Linear(z_dim + input_dim, z_dim), nn.ReLU(True)]
+        for i in range(n_layers - 1):
+            before_skip += [nn.Linear(z_dim, z_dim), nn.ReLU(True)]
+            after_skip += [nn.Linear(z_dim, z_dim), nn.ReLU(True)]
+        self.f_before = nn.Sequential(*before_skip)
+        self.f_after = nn.Sequential(*after_skip)
+        self.f_after_latent = nn.Linear(z_dim, z_dim)
+        self.f_after_shape = nn.Linear(z_dim, self.out_ch - 3)
+        self.f_color = nn.Sequential(nn.Linear(z_dim, z_dim // 4), nn.ReLU(True), nn.Linear(z_dim // 4, 3))
+        before_skip = [nn.Linear(input_dim, z_dim), nn.ReLU(True)]
+        after_skip = [nn.Linear(z_dim + input_dim, z_dim), nn.ReLU(True)]
+        for i in range(n_layers - 1):
+            before_skip += [nn.Linear(z_dim, z_dim), nn.ReLU(True)]
+            after_skip += [nn.Linear(z_dim, z_dim), nn.ReLU(True)]
+        after_skip.append(nn.Linear(z_dim, self.out_ch))
+        self.b_before = nn.Sequential(*before_skip)
+        self.b_after = nn.Sequential(*after_skip)
+        self.precision = "bf16x3"
+        self.emit = self.ALL_OUTPUTS
+        self.match_rng_stream = False
+        self.return_outside = False
+        self.last_outside = None
+
+    # ---- C-ABI plumbing ----
+    def _weights(self) -> _lib.DecoderWeights:
+        w = _lib.DecoderWeights()
+        keep = []
+
+        def p(t):
+            t = _f32c(t.detach())
+            keep.append(t)
+            return t.data_ptr()
+
+        for i in range(3):
+            w.f_before_w[i], w.f_before_b[i] = p(self.f_before[2 * i].weight), p(self.f_before[2 * i].bias)
+            w.f_after_w[i], w.f_after_b[i] = p(self.f_after[2 * i].weight), p(self.f_after[2 * i].bias)
+            w.b_before_w[i], w.b_before_b[i] = p(self.b_before[2 * i].weight), p(self.b_before[2 * i].bias)
+        for i in range(4):
+            w.b_after_w[i], w.b_after_b[i] = p(self.b_after[2 * i].weight), p(self.b_after[2 * i].bias)
+        w.f_after_latent_w, w.f_after_latent_b = p(self.f_after_latent.weight), p(self.f_after_latent.bias)
+        w.f_after_shape_w, w.f_after_shape_b = p(self.f_after_shape.weight), p(self.f_after_shape.bias)
+        w.f_color0_w, w.f_color0_b = p(self.f_color[0].weight), p(self.f_color[0].bias)
+        w.f_color2_w, w.f_color2_b = p(self.f_color[2].weight), p(self.f_color[2].bias)
+        w._keep = keep
+        return w
+
+    def _passes(self) -> int:
+        if self.precision == "bf16x3":
+            return _lib.PASSES_BF16X3
+        if self.precision == "bf16":
+            return _lib.PASSES_BF16
+        raise ValueError(f"unknown precision {self.precision!r} (use 'bf16x3' or 'bf16')")
+
+    def forward(self, sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform, dens_noise=0., noise=None):
+        """
+        sampling_coor_bg Px3, sampling_coor_fg (K-1)xPx3 (an expand() view is consumed in place),
+        z_slots KxC (slot 0 = background), fg_transform 1x3x3 (1x4x4 when fixed_locality)
+        -> raws Px4, masked_raws KxPx4, unmasked_raws KxPx4, masks KxPx1
+        """
+        _require_cuda(sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform)
+        if torch.is_grad_enabled() and (z_slots.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError(
+                "Decoder backward kernel is not built yet (SURVEY section 8 row a8, backward): call under "
+                "torch.no_grad(); uorf_b200 does not fall back to eager PyTorch")
+        if self.n_layers != 3 or self.n_freq != 5:
+            raise _lib.UorfError("decoder kernel is built for n_freq=5, n_layers=3 (every shipped configuration)")
+        K, Cz = z_slots.shape
+        P = sampling_coor_bg.shape[0]
+        dev = sampling_coor_bg.device
+        passes = self._passes()
+        coor_bg = _f32c(sampling_coor_bg)
+        fg = sampling_coor_fg if sampling_coor_fg.dtype == torch.float32 else sampling_coor_fg.float()
+        if fg.stride(-1) != 1 or fg.stride(-2) != 3:
+            fg = fg.contiguous()
+        fg_stride = fg.stride(0) if fg.shape[0] > 1 else 0
+        z = _f32c(z_slots.detach())
+        T = _f32c(fg_transform.reshape(-1))
+        if T.numel() != (16 if self.fixed_locality else 9):
+            raise _lib.UorfError("fg_transform must be 1x4x4 with fixed_locality, else 1x3x3")
+
+        stream = _stream(coor_bg)
+        nbytes = lib().uorf_decoder_image_bytes(K, passes)
+        image = torch.empty(nbytes + 1024, device=dev, dtype=torch.uint8)
+        off = (-image.data_ptr()) % 1024
+        image_ptr = image.data_ptr() + off
+        w = self._weights()
+        check(lib().uorf_decoder_prepare(C.byref(w), z.data_ptr(), K, Cz, self.n_freq, self.n_layers, passes, image_ptr,
+                                         stream), "uorf_decoder_prepare")
+
+        if noise is None and (dens_noise != 0. or self.match_rng_stream):
+            noise = torch.randn(K, P, 1, device=dev)  # model.py:155 (always drawn by the reference)
+        noise_c = _f32c(noise.reshape(K, P)) if (noise is not None and dens_noise != 0.) else None
+
+        emit = set(self.emit)
+        mk = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+        raws = mk(P, 4) if "raws" in emit else None
+        masked = mk(K, P, 4) if "masked_raws" in emit else None
+        unmasked = mk(K, P, 4) if "unmasked_raws" in emit else None
+        masks = mk(K, P, 1) if "masks" in emit else None
+        outside = torch.empty(K - 1, P, device=dev, dtype=torch.uint8) if self.return_outside else None
+        workspace = mk(P, 4)
+
+        a = _lib.DecoderArgs()
+        a.coor_bg, a.coor_fg, a.fg_slot_stride = coor_bg.data_ptr(), fg.data_ptr(), int(fg_stride)
+        a.fg_transform, a.noise = T.data_ptr(), _ptr(noise_c)
+        a.dens_noise, a.locality_ratio = float(dens_noise), float(self.locality_ratio)
+        a.locality, a.fixed_locality = int(bool(self.locality)), int(bool(self.fixed_locality))
+        a.P, a.K, a.passes = P, K, passes
+        a.image, a.workspace = image_ptr, workspace.data_ptr()
+        a.raws, a.masked_raws, a.unmasked_raws, a.masks = _ptr(raws), _ptr(masked), _ptr(unmasked), _ptr(masks)
+        a.outside = _ptr(outside)
+        check(lib().uorf_decoder_forward(C.byref(a), stream), "uorf_decoder_forward")
+        self.last_outside = outside
+        return raws, masked, unmasked, masks
