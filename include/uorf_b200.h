@@ -82,19 +82,24 @@ typedef struct uorf_decoder_weights {
   const float *b_after_w[4], *b_after_b[4];   /* b_after.{0,2,4,6}; .6 is [4][Z] */
 } uorf_decoder_weights;
 
-/* precision of the width-Z layers on the tensor cores:
- *   1 = one bf16 pass (fast mode), 3 = three-term bf16 split with fp32 accumulation (fp32-parity mode) */
-#define UORF_PASSES_BF16 1
-#define UORF_PASSES_BF16X3 3
+/* precision of the width-Z layers on the tensor cores (accumulation is always fp32):
+ *   BF16 / FP16      one pass with 16-bit operands (fast modes);
+ *   BF16X3 / FP16X3  three-term split a_hi*w_hi + a_lo*w_hi + a_hi*w_lo: ~16 (bf16) / ~22 (fp16) operand mantissa
+ *                    bits.  FP16X3 is the fp32-parity mode; fp16 conversions saturate at +-65504 (never inf),
+ *                    BF16X3 keeps the full fp32 range. */
+#define UORF_PREC_BF16 1
+#define UORF_PREC_FP16 2
+#define UORF_PREC_BF16X3 3
+#define UORF_PREC_FP16X3 4
 
-/* Bytes of the prepared weight image for (K slots, passes). */
-size_t uorf_decoder_image_bytes(int32_t K, int32_t passes);
+/* Bytes of the prepared weight image for (K slots, precision). */
+size_t uorf_decoder_image_bytes(int32_t K, int32_t precision);
 
 /* Packs the weights into the tensor-core image and hoists the slot-latent columns of the two wide
  * layers into per-slot biases.  Must be re-run when weights or z_slots change (once per scene).
- *   z_slots [K][Z] (slot 0 = background), image: uorf_decoder_image_bytes(K, passes) bytes, 1024-aligned. */
+ *   z_slots [K][Z] (slot 0 = background), image: uorf_decoder_image_bytes(K, precision) bytes, 1024-aligned. */
 int uorf_decoder_prepare(const uorf_decoder_weights* w, const float* z_slots, int32_t K, int32_t Z,
-                         int32_t n_freq, int32_t n_layers, int32_t passes, void* image, void* stream);
+                         int32_t n_freq, int32_t n_layers, int32_t precision, void* image, void* stream);
 
 typedef struct uorf_decoder_args {
   const float* coor_bg;     /* [P][3] */
@@ -108,8 +113,8 @@ typedef struct uorf_decoder_args {
   int32_t fixed_locality;   /* Decoder.fixed_locality */
   int64_t P;
   int32_t K;
-  int32_t passes;
-  const void* image;        /* from uorf_decoder_prepare (same K, passes) */
+  int32_t precision;        /* UORF_PREC_* */
+  const void* image;        /* from uorf_decoder_prepare (same K, precision) */
   float* workspace;         /* [P][4] floats scratch */
   /* outputs; any may be NULL to skip the write */
   float* raws;              /* [P][4] */
@@ -123,16 +128,18 @@ int uorf_decoder_forward(const uorf_decoder_args* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 3 — alpha compositing.  Replaces raw2outputs (models/model.py:279-313).
- *   raw [R][D][4] (rgb, sigma), z_vals [R][D], rays_d [R][3]
+ *   raw [R][D][4] (rgb, sigma), z_vals [geom_rays][D], rays_d [geom_rays][3]
  *   rgb_map [R][3], depth_map [R], weights_norm [R][D] (may be NULL), mask_map [R] (NULL unless render_mask)
+ * geom_rays = R for the reference call; R = k*geom_rays composites k stacked ray sets that share one
+ * geometry in a single launch (the K per-slot renders of uorf_eval_model.py:181-190); 0 means R.
  * ------------------------------------------------------------------------------------------- */
-int uorf_composite_forward(const float* raw, const float* z_vals, const float* rays_d, int64_t R, int32_t D,
+int uorf_composite_forward(const float* raw, const float* z_vals, const float* rays_d, int64_t R, int64_t geom_rays, int32_t D,
                            float* rgb_map, float* depth_map, float* weights_norm, float* mask_map,
                            void* stream);
 /* Backward of rgb_map w.r.t. raw (weights_norm is detached in the reference, model.py:304, so depth
  * carries no gradient).  grad_rgb [R][3] -> grad_raw [R][D][4]. */
 int uorf_composite_backward(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb,
-                            int64_t R, int32_t D, float* grad_raw, void* stream);
+                            int64_t R, int64_t geom_rays, int32_t D, float* grad_raw, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 4 — slot attention.  Replaces SlotAttention.forward (models/model.py:205-258), batch 1.
@@ -164,9 +171,9 @@ int uorf_slot_attention_forward(const uorf_slot_attention_weights* w, const floa
 /* ---------------------------------------------------------------------------------------------
  * Test hook: one 128 x N x (16*ksteps) bf16 GEMM on the tcgen05 path the decoder uses
  * (A rows written to TMEM by threads, B a swizzled shared-memory tile).  a [128][64], b [N][64] fp32
- * (rounded to bf16 inside), d [128][N].  Used by tests/ to pin the tensor-core data layouts.
+ * (rounded to 16 bits inside), d [128][N].  Used by tests/ to pin the tensor-core data layouts.
  * ------------------------------------------------------------------------------------------- */
-int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, int32_t passes, float* d,
+int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, int32_t precision, float* d,
                     void* stream);
 /* Test hook: site code written by a kernel whose mbarrier wait timed out (0 = none). */
 int uorf_debug_flag(void);

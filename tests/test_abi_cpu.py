@@ -41,9 +41,10 @@ def test_binding_covers_header(built_lib):
 def test_image_size_helper(built_lib):
     from uorf_b200 import _lib
     l = _lib.lib()
-    assert l.uorf_decoder_image_bytes(1, 3) == 0 and l.uorf_decoder_image_bytes(5, 2) == 0
-    b1, b3 = l.uorf_decoder_image_bytes(5, 1), l.uorf_decoder_image_bytes(5, 3)
+    assert l.uorf_decoder_image_bytes(1, 3) == 0 and l.uorf_decoder_image_bytes(5, 7) == 0
+    b1, b3 = l.uorf_decoder_image_bytes(5, _lib.PREC_BF16), l.uorf_decoder_image_bytes(5, _lib.PREC_FP16X3)
     assert b1 % 1024 == 0 and b3 % 1024 == 0 and b3 > b1 > 2 * 61440
+    assert l.uorf_decoder_image_bytes(5, _lib.PREC_FP16) == b1 and l.uorf_decoder_image_bytes(5, _lib.PREC_BF16X3) == b3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libuorf_b200.so")
 
 UORF_OK = 0
-PASSES_BF16 = 1
-PASSES_BF16X3 = 3
+PREC_BF16, PREC_FP16, PREC_BF16X3, PREC_FP16X3 = 1, 2, 3, 4
+PRECISIONS = {"bf16": PREC_BF16, "fp16": PREC_FP16, "bf16x3": PREC_BF16X3, "fp16x3": PREC_FP16X3}
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -44,7 +44,7 @@ class DecoderArgs(C.Structure):
                 ("fg_transform", C.c_void_p), ("noise", C.c_void_p),
                 ("dens_noise", C.c_float), ("locality_ratio", C.c_float),
                 ("locality", C.c_int32), ("fixed_locality", C.c_int32),
-                ("P", C.c_int64), ("K", C.c_int32), ("passes", C.c_int32),
+                ("P", C.c_int64), ("K", C.c_int32), ("precision", C.c_int32),
                 ("image", C.c_void_p), ("workspace", C.c_void_p),
                 ("raws", C.c_void_p), ("masked_raws", C.c_void_p), ("unmasked_raws", C.c_void_p),
                 ("masks", C.c_void_p), ("outside", C.c_void_p)]
@@ -101,9 +101,9 @@ _SIGNATURES = {
     "uorf_decoder_prepare": (C.c_int, [C.POINTER(DecoderWeights), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_void_p]),
     "uorf_decoder_forward": (C.c_int, [C.POINTER(DecoderArgs), C.c_void_p]),
-    "uorf_composite_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+    "uorf_composite_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
-    "uorf_composite_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+    "uorf_composite_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
                                           C.c_void_p]),
     "uorf_slot_attention_workspace_floats": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "uorf_slot_attention_forward": (C.c_int, [C.POINTER(SlotAttentionWeights), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,

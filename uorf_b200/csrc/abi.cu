@@ -13,18 +13,18 @@ namespace uorf {
 int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float* cam2world, int n_views, int scale, int crop_h,
                          int crop_w, int Hc, int Wc, int ray_major, float* coords, float* z_vals, float* ray_dir,
                          cudaStream_t stream);
-int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int K, int Z, int passes, void* image,
+int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int K, int Z, int passes, int f16, void* image,
                         cudaStream_t stream);
 int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, cudaStream_t stream);
-int launch_composite_fwd(const float* raw, const float* z_vals, const float* rays_d, long long R, int D, float* rgb_map,
+int launch_composite_fwd(const float* raw, const float* z_vals, const float* rays_d, long long R, long long Rg, int D, float* rgb_map,
                          float* depth_map, float* weights_norm, float* mask_map, int num_sms, cudaStream_t stream);
-int launch_composite_bwd(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb, long long R, int D,
+int launch_composite_bwd(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb, long long R, long long Rg, int D,
                          float* grad_raw, int num_sms, cudaStream_t stream);
 size_t slot_attention_ws_floats(int ntok, int C, int K);
 int launch_slot_attention(const uorf_slot_attention_weights* w, const float* feat, long long feat_ts, long long feat_cs,
                           const float* noise_fg, const float* noise_bg, int ntok, int C, int K, int hidden, int iters, float eps,
                           float* workspace, float* slots, float* attn, cudaStream_t stream);
-int launch_probe_gemm(const float* a, const float* b, int N, int ksteps, int passes, float* d, int* err_flag, cudaStream_t stream);
+int launch_probe_gemm(const float* a, const float* b, int N, int ksteps, int passes, int f16, float* d, int* err_flag, cudaStream_t stream);
 }  // namespace uorf
 
 namespace {
@@ -140,22 +140,26 @@ int uorf_sample_coords(const uorf_frustum* f, const float* z_cam, const float* c
                       "uorf_sample_coords");
 }
 
-size_t uorf_decoder_image_bytes(int32_t K, int32_t passes) {
-  if (K < 2 || (passes != 1 && passes != 3)) return 0;
-  return (size_t)uorf::blob_bytes_total(passes, K);
+static bool prec_ok(int precision) { return precision >= 1 && precision <= 4; }
+static int prec_passes(int precision) { return precision >= 3 ? 3 : 1; }
+static int prec_f16(int precision) { return (precision % 2) == 0 ? 1 : 0; }
+
+size_t uorf_decoder_image_bytes(int32_t K, int32_t precision) {
+  if (K < 2 || !prec_ok(precision)) return 0;
+  return (size_t)uorf::blob_bytes_total(prec_passes(precision), K);
 }
 
 int uorf_decoder_prepare(const uorf_decoder_weights* w, const float* z_slots, int32_t K, int32_t Z, int32_t n_freq,
-                         int32_t n_layers, int32_t passes, void* image, void* stream) {
+                         int32_t n_layers, int32_t precision, void* image, void* stream) {
   DeviceCtx* c = ctx();
   if (!c) return UORF_ERR_DEVICE;
   if (!w || !z_slots || !image) return fail(UORF_ERR_ARG, "uorf_decoder_prepare: null pointer%s");
   if ((reinterpret_cast<uintptr_t>(image) & 1023) != 0) return fail(UORF_ERR_ARG, "uorf_decoder_prepare: image must be 1024-byte aligned%s");
-  if (passes != 1 && passes != 3) return fail(UORF_ERR_ARG, "uorf_decoder_prepare: passes must be 1 or 3%s");
+  if (!prec_ok(precision)) return fail(UORF_ERR_ARG, "uorf_decoder_prepare: precision must be one of UORF_PREC_*%s");
   if (K < 2 || K > 16) return fail(UORF_ERR_UNSUPPORTED, "uorf_decoder_prepare: K must be in [2,16]%s");
   if (Z < 4 || Z > uorf::kZPad || (Z % 4) != 0) return fail(UORF_ERR_UNSUPPORTED, "uorf_decoder_prepare: z_dim must be a multiple of 4, <= 64%s");
   if (n_freq != 5 || n_layers != 3) return fail(UORF_ERR_UNSUPPORTED, "uorf_decoder_prepare: only n_freq=5, n_layers=3 (all shipped configs)%s");
-  return check_launch(uorf::launch_decoder_prep(w, z_slots, K, Z, passes, image, static_cast<cudaStream_t>(stream)),
+  return check_launch(uorf::launch_decoder_prep(w, z_slots, K, Z, prec_passes(precision), prec_f16(precision), image, static_cast<cudaStream_t>(stream)),
                       "uorf_decoder_prepare");
 }
 
@@ -164,9 +168,10 @@ int uorf_decoder_forward(const uorf_decoder_args* a, void* stream) {
   if (!c) return UORF_ERR_DEVICE;
   if (!a || !a->coor_bg || !a->coor_fg || !a->fg_transform || !a->image || !a->workspace)
     return fail(UORF_ERR_ARG, "uorf_decoder_forward: null pointer%s");
-  if (a->passes != 1 && a->passes != 3) return fail(UORF_ERR_ARG, "uorf_decoder_forward: passes must be 1 or 3%s");
+  if (!prec_ok(a->precision)) return fail(UORF_ERR_ARG, "uorf_decoder_forward: precision must be one of UORF_PREC_*%s");
   if (a->K < 2 || a->K > 16) return fail(UORF_ERR_UNSUPPORTED, "uorf_decoder_forward: K must be in [2,16]%s");
   if (a->P < 0 || a->P > (1LL << 37)) return fail(UORF_ERR_ARG, "uorf_decoder_forward: bad P%s");
+  if (a->P == 0) return UORF_OK;
   if (a->dens_noise != 0.f && !a->noise) return fail(UORF_ERR_ARG, "uorf_decoder_forward: dens_noise != 0 needs a noise tensor%s");
   const uintptr_t al = reinterpret_cast<uintptr_t>(a->workspace) | reinterpret_cast<uintptr_t>(a->raws) |
                        reinterpret_cast<uintptr_t>(a->masked_raws) | reinterpret_cast<uintptr_t>(a->unmasked_raws) |
@@ -176,29 +181,33 @@ int uorf_decoder_forward(const uorf_decoder_args* a, void* stream) {
                       "uorf_decoder_forward");
 }
 
-int uorf_composite_forward(const float* raw, const float* z_vals, const float* rays_d, int64_t R, int32_t D, float* rgb_map,
+int uorf_composite_forward(const float* raw, const float* z_vals, const float* rays_d, int64_t R, int64_t geom_rays, int32_t D, float* rgb_map,
                            float* depth_map, float* weights_norm, float* mask_map, void* stream) {
   DeviceCtx* c = ctx();
   if (!c) return UORF_ERR_DEVICE;
+  if (R == 0) return UORF_OK;
   if (!raw || !z_vals || !rays_d || !rgb_map || !depth_map) return fail(UORF_ERR_ARG, "uorf_composite_forward: null pointer%s");
-  if (R < 0 || D < 1) return fail(UORF_ERR_ARG, "uorf_composite_forward: bad sizes%s");
+  if (geom_rays <= 0) geom_rays = R;
+  if (R < 0 || D < 1 || (R > 0 && R % geom_rays != 0)) return fail(UORF_ERR_ARG, "uorf_composite_forward: bad sizes%s");
   if (D > 256) return fail(UORF_ERR_UNSUPPORTED, "uorf_composite_forward: D > 256%s");
   if (reinterpret_cast<uintptr_t>(raw) & 15) return fail(UORF_ERR_ARG, "uorf_composite_forward: raw must be 16-byte aligned%s");
-  return check_launch(uorf::launch_composite_fwd(raw, z_vals, rays_d, R, D, rgb_map, depth_map, weights_norm, mask_map, c->num_sms,
+  return check_launch(uorf::launch_composite_fwd(raw, z_vals, rays_d, R, geom_rays > 0 ? geom_rays : 1, D, rgb_map, depth_map, weights_norm, mask_map, c->num_sms,
                                                  static_cast<cudaStream_t>(stream)),
                       "uorf_composite_forward");
 }
 
-int uorf_composite_backward(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb, int64_t R, int32_t D,
+int uorf_composite_backward(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb, int64_t R, int64_t geom_rays, int32_t D,
                             float* grad_raw, void* stream) {
   DeviceCtx* c = ctx();
   if (!c) return UORF_ERR_DEVICE;
+  if (R == 0) return UORF_OK;
   if (!raw || !z_vals || !rays_d || !grad_rgb || !grad_raw) return fail(UORF_ERR_ARG, "uorf_composite_backward: null pointer%s");
-  if (R < 0 || D < 1) return fail(UORF_ERR_ARG, "uorf_composite_backward: bad sizes%s");
+  if (geom_rays <= 0) geom_rays = R;
+  if (R < 0 || D < 1 || (R > 0 && R % geom_rays != 0)) return fail(UORF_ERR_ARG, "uorf_composite_backward: bad sizes%s");
   if (D > 256) return fail(UORF_ERR_UNSUPPORTED, "uorf_composite_backward: D > 256%s");
   if ((reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(grad_raw)) & 15)
     return fail(UORF_ERR_ARG, "uorf_composite_backward: raw/grad_raw must be 16-byte aligned%s");
-  return check_launch(uorf::launch_composite_bwd(raw, z_vals, rays_d, grad_rgb, R, D, grad_raw, c->num_sms,
+  return check_launch(uorf::launch_composite_bwd(raw, z_vals, rays_d, grad_rgb, R, geom_rays > 0 ? geom_rays : 1, D, grad_raw, c->num_sms,
                                                  static_cast<cudaStream_t>(stream)),
                       "uorf_composite_backward");
 }
@@ -221,13 +230,13 @@ int uorf_slot_attention_forward(const uorf_slot_attention_weights* w, const floa
                       "uorf_slot_attention_forward");
 }
 
-int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, int32_t passes, float* d, void* stream) {
+int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, int32_t precision, float* d, void* stream) {
   DeviceCtx* c = ctx();
   if (!c) return UORF_ERR_DEVICE;
   if (!a || !b || !d) return fail(UORF_ERR_ARG, "uorf_probe_gemm: null pointer%s");
-  if (N < 16 || N > 64 || (N % 16) || ksteps < 1 || ksteps > 4 || (passes != 1 && passes != 3))
+  if (N < 16 || N > 64 || (N % 16) || ksteps < 1 || ksteps > 4 || !prec_ok(precision))
     return fail(UORF_ERR_ARG, "uorf_probe_gemm: bad shape%s");
-  return check_launch(uorf::launch_probe_gemm(a, b, N, ksteps, passes, d, c->err_flag_dev, static_cast<cudaStream_t>(stream)),
+  return check_launch(uorf::launch_probe_gemm(a, b, N, ksteps, prec_passes(precision), prec_f16(precision), d, c->err_flag_dev, static_cast<cudaStream_t>(stream)),
                       "uorf_probe_gemm");
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "../../include/uorf_b200.h"  // UORF_OK / UORF_ERR_* codes
@@ -102,10 +103,10 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 // ----------------------------------------------------------------------------------------------
 // tcgen05.mma  kind::f16 (bf16 x bf16 -> fp32), M = 128, cta_group::1
 // ----------------------------------------------------------------------------------------------
-// Instruction descriptor (32 bit): c_format F32 @4, a/b_format BF16 @7/@10, K-major A and B,
+// Instruction descriptor (32 bit): c_format F32 @4, a/b_format (0 = F16, 1 = BF16) @7/@10, K-major A and B,
 // N>>3 @17, M>>4 @24.
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+__host__ __device__ constexpr uint32_t make_idesc_f32acc(int M, int N, bool f16) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 // Shared-memory matrix descriptor for a K-major operand tile stored as rows of 64 bf16 (128 B)
@@ -176,20 +177,45 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// bf16 packing.  pack2(e0, e1): e0 -> bits [0,16), e1 -> bits [16,32)  (element 2c in the low half
-// of TMEM/SMEM word c).  split2 additionally returns the packed residual (x - bf16(x)) -> "lo" word
-// of the 3-term bf16 split  a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.
+// 16-bit operand packing.  pack2<F16>(e0, e1): e0 -> bits [0,16), e1 -> bits [16,32)  (element 2c in the
+// low half of TMEM/SMEM word c); F16 = false: bf16, true: fp16 (saturating, so no inf is ever produced).
+// split2 additionally returns the packed residual (x - hi(x)) -> "lo" word of the 3-term split
+//   a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo      (bf16: ~16 mantissa bits, fp16: ~22 mantissa bits).
 // ----------------------------------------------------------------------------------------------
+template <bool F16>
 __device__ __forceinline__ uint32_t pack2(float e0, float e1) {
   uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+  if (F16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+  else     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
   return d;
 }
+template <bool F16>
 __device__ __forceinline__ void split2(float e0, float e1, uint32_t& hi, uint32_t& lo) {
-  hi = pack2(e0, e1);
-  const float h0 = __uint_as_float(hi << 16);
-  const float h1 = __uint_as_float(hi & 0xFFFF0000u);
-  lo = pack2(e0 - h0, e1 - h1);
+  hi = pack2<F16>(e0, e1);
+  float h0, h1;
+  if (F16) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+    const float2 f = __half22float2(h);
+    h0 = f.x;
+    h1 = f.y;
+  } else {
+    h0 = __uint_as_float(hi << 16);
+    h1 = __uint_as_float(hi & 0xFFFF0000u);
+  }
+  lo = pack2<F16>(e0 - h0, e1 - h1);
+}
+// scalar versions for the weight image
+template <bool F16>
+__device__ __forceinline__ unsigned short to16(float v) {
+  if (F16) {
+    const float c = fminf(fmaxf(v, -65504.f), 65504.f);
+    return __half_as_ushort(__float2half_rn(c));
+  }
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+template <bool F16>
+__device__ __forceinline__ float from16(unsigned short u) {
+  return F16 ? __half2float(__ushort_as_half(u)) : __bfloat162float(__ushort_as_bfloat16(u));
 }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

@@ -37,17 +37,18 @@ __device__ __forceinline__ float warp_rscan_add(float v, int lane) {
 }
 
 __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
-                                                            const float* __restrict__ rays_d, long long R, int D,
+                                                            const float* __restrict__ rays_d, long long R, long long Rg, int D,
                                                             float* __restrict__ rgb_map, float* __restrict__ depth_map,
                                                             float* __restrict__ weights_norm, float* __restrict__ mask_map) {
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int nchunks = (D + 31) >> 5;
   for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
-    const float dx = __ldg(rays_d + r * 3), dy = __ldg(rays_d + r * 3 + 1), dz = __ldg(rays_d + r * 3 + 2);
+    const long long rg = r % Rg;  // geometry (z_vals, rays_d) may be shared by several stacked ray sets
+    const float dx = __ldg(rays_d + rg * 3), dy = __ldg(rays_d + rg * 3 + 1), dz = __ldg(rays_d + rg * 3 + 2);
     const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
     const float4* rr = raw + r * D;
-    const float* zz = z_vals + r * D;
+    const float* zz = z_vals + rg * D;
     float w[kMaxChunks], zv[kMaxChunks];
     float carry = 1.f;  // product of (1 - alpha + 1e-10) over all previous chunks
     float ar = 0.f, ag = 0.f, ab = 0.f, am = 0.f, sw = 0.f;
@@ -115,16 +116,17 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
 //   d alpha_i = G_i T_i - S_i / (1 - alpha_i + 1e-10) ;  d sigma_i = d alpha_i * delta_i * exp(-sigma_i delta_i)
 __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
                                                             const float* __restrict__ rays_d, const float* __restrict__ grad_rgb,
-                                                            long long R, int D, float4* __restrict__ grad_raw) {
+                                                            long long R, long long Rg, int D, float4* __restrict__ grad_raw) {
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int nchunks = (D + 31) >> 5;
   for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
-    const float dx = __ldg(rays_d + r * 3), dy = __ldg(rays_d + r * 3 + 1), dz = __ldg(rays_d + r * 3 + 2);
+    const long long rg = r % Rg;  // geometry (z_vals, rays_d) may be shared by several stacked ray sets
+    const float dx = __ldg(rays_d + rg * 3), dy = __ldg(rays_d + rg * 3 + 1), dz = __ldg(rays_d + rg * 3 + 2);
     const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
     const float g0 = __ldg(grad_rgb + r * 3), g1 = __ldg(grad_rgb + r * 3 + 1), g2 = __ldg(grad_rgb + r * 3 + 2);
     const float4* rr = raw + r * D;
-    const float* zz = z_vals + r * D;
+    const float* zz = z_vals + rg * D;
     float w[kMaxChunks], T[kMaxChunks], term[kMaxChunks], G[kMaxChunks], de[kMaxChunks];
     float carry = 1.f;
 #pragma unroll
@@ -181,19 +183,19 @@ static int composite_grid(long long R, int num_sms) {
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
-int launch_composite_fwd(const float* raw, const float* z_vals, const float* rays_d, long long R, int D, float* rgb_map,
+int launch_composite_fwd(const float* raw, const float* z_vals, const float* rays_d, long long R, long long Rg, int D, float* rgb_map,
                          float* depth_map, float* weights_norm, float* mask_map, int num_sms, cudaStream_t stream) {
   if (R == 0) return UORF_OK;
-  composite_fwd_kernel<<<composite_grid(R, num_sms), 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, R, D,
+  composite_fwd_kernel<<<composite_grid(R, num_sms), 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, R, Rg, D,
                                                                        rgb_map, depth_map, weights_norm, mask_map);
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
 
-int launch_composite_bwd(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb, long long R, int D,
+int launch_composite_bwd(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb, long long R, long long Rg, int D,
                          float* grad_raw, int num_sms, cudaStream_t stream) {
   if (R == 0) return UORF_OK;
   composite_bwd_kernel<<<composite_grid(R, num_sms), 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, grad_rgb,
-                                                                       R, D, reinterpret_cast<float4*>(grad_raw));
+                                                                       R, Rg, D, reinterpret_cast<float4*>(grad_raw));
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
 

@@ -13,7 +13,8 @@
 // Per layer:  A (activations, bf16 hi [+lo]) lives in TMEM, written by the channel's threads with
 //   tcgen05.st; B (weights) is a 128B-swizzled K-major tile in shared memory; D (fp32) in TMEM.
 //   channel --a_full mbarrier--> issuer --tcgen05.commit / d_full mbarrier--> channel (bias+ReLU+split).
-// Precision: passes = 1: one bf16 MMA pass; passes = 3: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (fp32 accumulate).
+// Precision: passes = 1: one 16-bit MMA pass; passes = 3: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (fp32 accumulate);
+// operands bf16 (range-safe, ~16 bits after the split) or fp16 (saturating, ~22 bits after the split).
 // The kernel makes two sweeps over its tiles: background MLP first (raw bg output parked in a 16 B/point
 // scratch), then the foreground MLP for slots 1..K-1 followed by the cross-slot composition.  The split
 // lets the bf16x3 weight image of ONE MLP (124 KB) stay resident in shared memory.
@@ -61,7 +62,7 @@ struct DecFwdParams {
 
 // positional encoding of one point -> TMEM (48 K-columns: 33 values + zero padding), reference order
 // [x y z | sin(2^i x..z) cos(2^i x..z)]_{i<5}  (model.py:261-277).  Frequencies 2,4,8,16 by angle doubling.
-template <int PASSES>
+template <int PASSES, bool F16>
 __device__ __forceinline__ void posenc_to_tmem(float x, float y, float z, uint32_t t_phi, uint32_t t_plo) {
   float v[kPosencK];
   v[0] = x; v[1] = y; v[2] = z;
@@ -91,8 +92,8 @@ __device__ __forceinline__ void posenc_to_tmem(float x, float y, float z, uint32
   uint32_t hi[24], lo[24];
 #pragma unroll
   for (int i = 0; i < 24; ++i) {
-    if (PASSES == 3) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-    else hi[i] = pack2(v[2 * i], v[2 * i + 1]);
+    if (PASSES == 3) split2<F16>(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+    else hi[i] = pack2<F16>(v[2 * i], v[2 * i + 1]);
   }
   tmem_st16(t_phi, hi);
   tmem_st8(t_phi + 16, hi + 16);
@@ -104,7 +105,7 @@ __device__ __forceinline__ void posenc_to_tmem(float x, float y, float z, uint32
 }
 
 // hidden-layer epilogue: D (64 fp32 cols) + bias -> ReLU -> bf16 hi[/lo] -> H operand columns
-template <int PASSES>
+template <int PASSES, bool F16>
 __device__ __forceinline__ void hidden_epilogue(uint32_t t_d, uint32_t t_hhi, uint32_t t_hlo, const float* bias) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
@@ -120,11 +121,11 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t t_d, uint32_t t_hhi, ui
       const float v2 = fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, 0.f);
       const float v3 = fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, 0.f);
       if (PASSES == 3) {
-        split2(v0, v1, hi[2 * q], lo[2 * q]);
-        split2(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
+        split2<F16>(v0, v1, hi[2 * q], lo[2 * q]);
+        split2<F16>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
       } else {
-        hi[2 * q] = pack2(v0, v1);
-        hi[2 * q + 1] = pack2(v2, v3);
+        hi[2 * q] = pack2<F16>(v0, v1);
+        hi[2 * q + 1] = pack2<F16>(v2, v3);
       }
     }
     tmem_st16(t_hhi + half * 16, hi);
@@ -150,7 +151,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t t_d, uint32_t t_ahi, uint32_
   }
 }
 
-template <int PASSES>
+template <int PASSES, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdParams p) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_w;
@@ -213,8 +214,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
     }
     mbar_wait(&bar_w, phase & 1, p.err_flag, 100 + phase);
 
-    const uint32_t idesc64 = make_idesc_bf16_f32(128, 64);
-    const uint32_t idesc_head = make_idesc_bf16_f32(128, phase == 0 ? 16 : 32);
+    const uint32_t idesc64 = make_idesc_f32acc(128, 64, F16);
+    const uint32_t idesc_head = make_idesc_f32acc(128, phase == 0 ? 16 : 32, F16);
 
     if (warp == 8) {
       // =========================== MMA issuer ===========================
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
             if (!p.fixed_locality) outside = fabsf(x) > p.locality_ratio || fabsf(y) > p.locality_ratio || fabsf(z) > p.locality_ratio;
             if (p.outside && valid) p.outside[(long long)s * p.P + pt] = outside ? 1 : 0;
           }
-          posenc_to_tmem<PASSES>(x, y, z, tb + kColPHi, tb + kColPLo);
+          posenc_to_tmem<PASSES, F16>(x, y, z, tb + kColPHi, tb + kColPLo);
           tc_fence_before();
           mbar_arrive(&bar_a[ch]);
 
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
             mbar_wait(&bar_d[ch], n_d[ch] & 1, p.err_flag, 300 + st);
             ++n_d[ch];
             tc_fence_after();
-            hidden_epilogue<PASSES>(tb + kColD, tb + kColHHi, tb + kColHLo, bias);
+            hidden_epilogue<PASSES, F16>(tb + kColD, tb + kColHHi, tb + kColHLo, bias);
             tc_fence_before();
             mbar_arrive(&bar_a[ch]);
           }
@@ -399,20 +400,21 @@ int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, c
   p.locality = a->locality;
   p.num_tiles = (int)((a->P + kTileM - 1) / kTileM);
   p.err_flag = err_flag;
-  const size_t smem = decoder_smem_bytes(a->passes, a->K);
+  const size_t smem = decoder_smem_bytes(a->precision >= 3 ? 3 : 1, a->K);
   if (smem > 227 * 1024) return UORF_ERR_UNSUPPORTED;
   int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   if (grid < 1) return UORF_OK;
-  cudaError_t e;
-  if (a->passes == 3) {
-    e = cudaFuncSetAttribute(decoder_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return UORF_ERR_DEVICE;
-    decoder_fwd_kernel<3><<<grid, kThreads, smem, stream>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(decoder_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return UORF_ERR_DEVICE;
-    decoder_fwd_kernel<1><<<grid, kThreads, smem, stream>>>(p);
-  }
+  const int passes = a->precision >= 3 ? 3 : 1;
+  const bool f16 = (a->precision % 2) == 0;
+  auto launch = [&](auto kern) -> int {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UORF_ERR_DEVICE;
+    kern<<<grid, kThreads, smem, stream>>>(p);
+    return UORF_OK;
+  };
+  int rc;
+  if (passes == 3) rc = f16 ? launch(decoder_fwd_kernel<3, true>) : launch(decoder_fwd_kernel<3, false>);
+  else rc = f16 ? launch(decoder_fwd_kernel<1, true>) : launch(decoder_fwd_kernel<1, false>);
+  if (rc != UORF_OK) return rc;
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
 

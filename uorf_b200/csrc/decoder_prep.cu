@@ -10,7 +10,7 @@ namespace uorf {
 struct PrepArgs {
   uorf_decoder_weights w;
   const float* z_slots;
-  int K, Z, passes;
+  int K, Z, passes, f16;
   unsigned char* image;
 };
 
@@ -19,12 +19,12 @@ __device__ __forceinline__ int sw128_off(int n, int k) {
   return (n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ (n & 7)) & 7) << 4) + (k & 7) * 2;
 }
 
-__device__ __forceinline__ void put(unsigned char* plane0, int passes, int off, float v) {
-  __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  *reinterpret_cast<__nv_bfloat16*>(plane0 + off) = hi;
+__device__ __forceinline__ void put(unsigned char* plane0, int passes, int f16, int off, float v) {
+  const unsigned short hi = f16 ? to16<true>(v) : to16<false>(v);
+  *reinterpret_cast<unsigned short*>(plane0 + off) = hi;
   if (passes == 3) {
-    __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    *reinterpret_cast<__nv_bfloat16*>(plane0 + kPlaneBytes + off) = lo;
+    const float r = v - (f16 ? from16<true>(hi) : from16<false>(hi));
+    *reinterpret_cast<unsigned short*>(plane0 + kPlaneBytes + off) = f16 ? to16<true>(r) : to16<false>(r);
   }
 }
 
@@ -57,7 +57,7 @@ __global__ void decoder_prep_kernel(PrepArgs a) {
           case 6: if (k < Z) v = after_w[2][n * Z + k]; break;
         }
       }
-      put(tile, a.passes, sw128_off(n, k), v);
+      put(tile, a.passes, a.f16, sw128_off(n, k), v);
     }
   } else if (bx == 7) {
     unsigned char* tile = img + 7 * kTileBytes;
@@ -78,7 +78,7 @@ __global__ void decoder_prep_kernel(PrepArgs a) {
           v = a.w.b_after_w[3][n * Z + k];
         }
       }
-      put(tile, a.passes, sw128_off(n, k), v);
+      put(tile, a.passes, a.f16, sw128_off(n, k), v);
     }
   } else if (bx == 8) {
     float* prm = reinterpret_cast<float*>(img + nplanes * kPlaneBytes);
@@ -130,7 +130,7 @@ __global__ void decoder_prep_kernel(PrepArgs a) {
   }
 }
 
-int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int K, int Z, int passes, void* image,
+int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int K, int Z, int passes, int f16, void* image,
                         cudaStream_t stream) {
   PrepArgs a;
   a.w = *w;
@@ -138,6 +138,7 @@ int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int
   a.K = K;
   a.Z = Z;
   a.passes = passes;
+  a.f16 = f16;
   a.image = static_cast<unsigned char*>(image);
   dim3 grid(9 + (K - 1 > 1 ? K - 1 : 1), 2);
   decoder_prep_kernel<<<grid, 256, 0, stream>>>(a);

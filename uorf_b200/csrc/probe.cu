@@ -8,7 +8,7 @@
 namespace uorf {
 
 __global__ void __launch_bounds__(160, 1) probe_gemm_kernel(const float* __restrict__ a, const float* __restrict__ b, int N,
-                                                            int ksteps, int passes, float* __restrict__ d, int* err_flag) {
+                                                            int ksteps, int passes, int f16, float* __restrict__ d, int* err_flag) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_a, bar_d;
   __shared__ uint32_t tmem_base_s;
@@ -29,9 +29,10 @@ __global__ void __launch_bounds__(160, 1) probe_gemm_kernel(const float* __restr
     const int n = e >> 6, k = e & 63;
     const float v = n < N ? b[n * 64 + k] : 0.f;
     const int off = (n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ (n & 7)) & 7) << 4) + (k & 7) * 2;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    *reinterpret_cast<__nv_bfloat16*>(smem + off) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(smem + kTileBytes + off) = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const unsigned short hi = f16 ? to16<true>(v) : to16<false>(v);
+    *reinterpret_cast<unsigned short*>(smem + off) = hi;
+    const float res = v - (f16 ? from16<true>(hi) : from16<false>(hi));
+    *reinterpret_cast<unsigned short*>(smem + kTileBytes + off) = f16 ? to16<true>(res) : to16<false>(res);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -44,7 +45,10 @@ __global__ void __launch_bounds__(160, 1) probe_gemm_kernel(const float* __restr
     const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint32_t hi[32], lo[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) split2(a[t * 64 + 2 * i], a[t * 64 + 2 * i + 1], hi[i], lo[i]);
+    for (int i = 0; i < 32; ++i) {
+      if (f16) split2<true>(a[t * 64 + 2 * i], a[t * 64 + 2 * i + 1], hi[i], lo[i]);
+      else split2<false>(a[t * 64 + 2 * i], a[t * 64 + 2 * i + 1], hi[i], lo[i]);
+    }
     tmem_st16(tb + colHi, hi);
     tmem_st16(tb + colHi + 16, hi + 16);
     tmem_st16(tb + colLo, lo);
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(160, 1) probe_gemm_kernel(const float* __restr
     mbar_wait(&bar_a, 0, err_flag, 1);
     tc_fence_after();
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16_f32(128, N);
+      const uint32_t idesc = make_idesc_f32acc(128, N, f16 != 0);
       const uint32_t ws = smem_u32(smem);
       const uint64_t dhi = make_sdesc_sw128(ws), dlo = make_sdesc_sw128(ws + kTileBytes);
       bool first = true;
@@ -84,9 +88,9 @@ __global__ void __launch_bounds__(160, 1) probe_gemm_kernel(const float* __restr
   if (warp == 4) tmem_dealloc(tmem_base, 256);
 }
 
-int launch_probe_gemm(const float* a, const float* b, int N, int ksteps, int passes, float* d, int* err_flag, cudaStream_t stream) {
+int launch_probe_gemm(const float* a, const float* b, int N, int ksteps, int passes, int f16, float* d, int* err_flag, cudaStream_t stream) {
   const int smem = 1024 + 2 * kTileBytes;
-  probe_gemm_kernel<<<1, 160, smem, stream>>>(a, b, N, ksteps, passes, d, err_flag);
+  probe_gemm_kernel<<<1, 160, smem, stream>>>(a, b, N, ksteps, passes, f16, d, err_flag);
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
 

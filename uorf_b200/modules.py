@@ -114,11 +114,14 @@ class _Composite(torch.autograd.Function):
         _require_cuda(raw, z_vals, rays_d)
         raw_c, z_c, d_c = _f32c(raw), _f32c(z_vals), _f32c(rays_d)
         R, D = raw_c.shape[0], raw_c.shape[1]
+        Rg = z_c.shape[0]
+        if R % max(Rg, 1) != 0 or d_c.shape[0] != Rg:
+            raise _lib.UorfError("raw2outputs: raw rows must be a multiple of the z_vals / rays_d rows")
         rgb = torch.empty(R, 3, device=raw.device, dtype=torch.float32)
         depth = torch.empty(R, device=raw.device, dtype=torch.float32)
         wn = torch.empty(R, D, device=raw.device, dtype=torch.float32)
         mm = torch.empty(R, device=raw.device, dtype=torch.float32) if render_mask else None
-        check(lib().uorf_composite_forward(raw_c.data_ptr(), z_c.data_ptr(), d_c.data_ptr(), R, D, rgb.data_ptr(),
+        check(lib().uorf_composite_forward(raw_c.data_ptr(), z_c.data_ptr(), d_c.data_ptr(), R, Rg, D, rgb.data_ptr(),
                                            depth.data_ptr(), wn.data_ptr(), _ptr(mm), _stream(raw)),
               "uorf_composite_forward")
         ctx.save_for_backward(raw_c, z_c, d_c)
@@ -134,7 +137,7 @@ class _Composite(torch.autograd.Function):
         R, D = raw_c.shape[0], raw_c.shape[1]
         g = _f32c(g_rgb)
         g_raw = torch.empty_like(raw_c)
-        check(lib().uorf_composite_backward(raw_c.data_ptr(), z_c.data_ptr(), d_c.data_ptr(), g.data_ptr(), R, D,
+        check(lib().uorf_composite_backward(raw_c.data_ptr(), z_c.data_ptr(), d_c.data_ptr(), g.data_ptr(), R, z_c.shape[0], D,
                                             g_raw.data_ptr(), _stream(raw_c)), "uorf_composite_backward")
         return g_raw, None, None, None
 
@@ -143,7 +146,9 @@ def raw2outputs(raw, z_vals, rays_d, render_mask=False):
     """reference models/model.py:279-313.  raw RxDx4, z_vals RxD, rays_d Rx3 ->
     rgb_map Rx3, depth_map R, weights_norm RxD [, mask_map R].
     Gradients flow from rgb_map to raw (depth uses detached weights in the reference; mask_map is only used
-    under no_grad by the reference's drivers)."""
+    under no_grad by the reference's drivers).
+    Extension: raw may hold k stacked ray sets ((k*R)xDx4) sharing one geometry (z_vals RxD, rays_d Rx3); they are
+    composited in one launch (the per-slot renders of uorf_eval_model.py:181-190)."""
     return _Composite.apply(raw, z_vals, rays_d, bool(render_mask))
 
 
@@ -311,8 +316,9 @@ class Decoder(nn.Module):
     """reference models/model.py:64-161 (same parameters / state-dict keys, same forward signature).
 
     Extra, B200-specific knobs (attributes; defaults reproduce the reference call):
-      precision   'bf16x3' (default): three-term bf16 split on the tensor cores, fp32 accumulation - meets the
-                  1e-4 fp32-parity bar;  'bf16': one pass, ~3x less tensor work, tolerance stated in DESIGN.md.
+      precision   'fp16x3' (default, fp32-parity mode): three-term fp16 split on the tensor cores, fp32 accumulation;
+                  'bf16x3': same with bf16 operands (full fp32 range, ~16 instead of ~22 operand bits);
+                  'bf16' / 'fp16': one pass, ~3x less tensor work, tolerance stated in DESIGN.md.
       emit        which of ('raws', 'masked_raws', 'unmasked_raws', 'masks') to materialise; skipped outputs are
                   returned as None (the API-mandated per-slot tensors are 36*K bytes per point of HBM writes).
       match_rng_stream  draw the reference's unconditional randn_like (model.py:155) even when dens_noise == 0,
@@ -349,11 +355,12 @@ class Decoder(nn.Module):
         after_skip.append(nn.Linear(z_dim, self.out_ch))
         self.b_before = nn.Sequential(*before_skip)
         self.b_after = nn.Sequential(*after_skip)
-        self.precision = "bf16x3"
+        self.precision = "fp16x3"
         self.emit = self.ALL_OUTPUTS
         self.match_rng_stream = False
         self.return_outside = False
         self.last_outside = None
+        self.events = None   # set to a list to collect (start, end) CUDA events around the fused kernel
 
     # ---- C-ABI plumbing ----
     def _weights(self) -> _lib.DecoderWeights:
@@ -378,12 +385,11 @@ class Decoder(nn.Module):
         w._keep = keep
         return w
 
-    def _passes(self) -> int:
-        if self.precision == "bf16x3":
-            return _lib.PASSES_BF16X3
-        if self.precision == "bf16":
-            return _lib.PASSES_BF16
-        raise ValueError(f"unknown precision {self.precision!r} (use 'bf16x3' or 'bf16')")
+    def _precision(self) -> int:
+        try:
+            return _lib.PRECISIONS[self.precision]
+        except KeyError:
+            raise ValueError(f"unknown precision {self.precision!r} (use one of {sorted(_lib.PRECISIONS)})") from None
 
     def forward(self, sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform, dens_noise=0., noise=None):
         """
@@ -401,7 +407,7 @@ class Decoder(nn.Module):
         K, Cz = z_slots.shape
         P = sampling_coor_bg.shape[0]
         dev = sampling_coor_bg.device
-        passes = self._passes()
+        prec = self._precision()
         coor_bg = _f32c(sampling_coor_bg)
         fg = sampling_coor_fg if sampling_coor_fg.dtype == torch.float32 else sampling_coor_fg.float()
         if fg.stride(-1) != 1 or fg.stride(-2) != 3:
@@ -413,12 +419,12 @@ class Decoder(nn.Module):
             raise _lib.UorfError("fg_transform must be 1x4x4 with fixed_locality, else 1x3x3")
 
         stream = _stream(coor_bg)
-        nbytes = lib().uorf_decoder_image_bytes(K, passes)
+        nbytes = lib().uorf_decoder_image_bytes(K, prec)
         image = torch.empty(nbytes + 1024, device=dev, dtype=torch.uint8)
         off = (-image.data_ptr()) % 1024
         image_ptr = image.data_ptr() + off
         w = self._weights()
-        check(lib().uorf_decoder_prepare(C.byref(w), z.data_ptr(), K, Cz, self.n_freq, self.n_layers, passes, image_ptr,
+        check(lib().uorf_decoder_prepare(C.byref(w), z.data_ptr(), K, Cz, self.n_freq, self.n_layers, prec, image_ptr,
                                          stream), "uorf_decoder_prepare")
 
         if noise is None and (dens_noise != 0. or self.match_rng_stream):
@@ -439,10 +445,18 @@ class Decoder(nn.Module):
         a.fg_transform, a.noise = T.data_ptr(), _ptr(noise_c)
         a.dens_noise, a.locality_ratio = float(dens_noise), float(self.locality_ratio)
         a.locality, a.fixed_locality = int(bool(self.locality)), int(bool(self.fixed_locality))
-        a.P, a.K, a.passes = P, K, passes
+        a.P, a.K, a.precision = P, K, prec
         a.image, a.workspace = image_ptr, workspace.data_ptr()
         a.raws, a.masked_raws, a.unmasked_raws, a.masks = _ptr(raws), _ptr(masked), _ptr(unmasked), _ptr(masks)
         a.outside = _ptr(outside)
+        ev = self.events
+        if ev is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(dev))
         check(lib().uorf_decoder_forward(C.byref(a), stream), "uorf_decoder_forward")
+        if ev is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream(dev))
+            ev.append((e0, e1))
         self.last_outside = outside
         return raws, masked, unmasked, masks

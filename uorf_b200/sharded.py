@@ -1,0 +1,58 @@
+"""Ray-sharded multi-GPU rendering (one process per GPU, torch.distributed).
+
+Rays are independent once the slot latents exist, so the only exchange on the path is:
+  1. rank 0 runs Encoder -> SlotAttention on view 0 and BROADCASTS z_slots (K x C fp32, < 5 KB) and the fg transform;
+  2. every rank renders its own contiguous block of (view, row) rays with the single-GPU kernels;
+  3. (optional) the rendered image tiles are ALL-GATHERED.
+No collective sits inside the per-point work.  The backend is NCCL on GPUs; the same host logic runs over gloo in
+the CPU tests, where `render_fn` is a stand-in supplied by the test.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, world: int, rank: int) -> Tuple[int, int]:
+    """contiguous [lo, hi) block of `n_items` for `rank`; the first n_items % world ranks get one extra item."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_views(n_views: int, world: int, rank: int) -> Tuple[int, int]:
+    return shard_range(n_views, world, rank)
+
+
+def broadcast_slots(z_slots: Optional[torch.Tensor], K: int, C: int, device, src: int = 0, group=None) -> torch.Tensor:
+    """rank `src` passes its z_slots; the others pass None and receive them."""
+    if z_slots is None:
+        z_slots = torch.empty(K, C, device=device, dtype=torch.float32)
+    z_slots = z_slots.contiguous()
+    dist.broadcast(z_slots, src=src, group=group)
+    return z_slots
+
+
+def sharded_render(encode_fn: Callable[[], torch.Tensor], render_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
+                   cam2world: torch.Tensor, K: int, C: int, gather: bool = True, group=None):
+    """One scene, views sharded over the ranks of `group`.
+
+    encode_fn()                        -> z_slots KxC         (called on rank 0 only)
+    render_fn(z_slots, cam2world[lo:hi]) -> images (hi-lo)x3xHxW
+    Returns (local images, (lo, hi), all images Nx3xHxW on every rank or None).
+    Views must divide evenly when gather=True (all_gather_into_tensor needs equal shards)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    device = cam2world.device
+    z_slots = encode_fn() if rank == 0 else None
+    z_slots = broadcast_slots(z_slots, K, C, device, 0, group)
+    lo, hi = shard_views(cam2world.shape[0], world, rank)
+    local = render_fn(z_slots, cam2world[lo:hi]).contiguous()
+    full = None
+    if gather:
+        if cam2world.shape[0] % world != 0:
+            raise ValueError("gather=True needs n_views divisible by the world size")
+        full = torch.empty((cam2world.shape[0],) + tuple(local.shape[1:]), device=device, dtype=local.dtype)
+        dist.all_gather_into_tensor(full, local, group=group)
+    return local, (lo, hi), full
