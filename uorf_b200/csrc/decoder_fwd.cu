@@ -6,18 +6,24 @@
 //   ReLU density / tanh colour, density-weighted composition over the K slots.
 // No activation ever leaves the SM: the only HBM traffic is coords in, API-mandated outputs out.
 //
-// Structure (one persistent CTA per SM, 288 threads):
-//   warps 0-3  "channel 0"  : 128 threads, thread t owns point t of the channel's current 128-point tile
-//   warps 4-7  "channel 1"  : same, on another tile  (the two channels ping-pong on the tensor pipe)
-//   warp  8    MMA issuer   : lane 0 issues tcgen05.mma; also owns TMEM alloc and the weight bulk copies
-// Per layer:  A (activations, bf16 hi [+lo]) lives in TMEM, written by the channel's threads with
-//   tcgen05.st; B (weights) is a 128B-swizzled K-major tile in shared memory; D (fp32) in TMEM.
-//   channel --a_full mbarrier--> issuer --tcgen05.commit / d_full mbarrier--> channel (bias+ReLU+split).
-// Precision: passes = 1: one 16-bit MMA pass; passes = 3: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (fp32 accumulate);
-// operands bf16 (range-safe, ~16 bits after the split) or fp16 (saturating, ~22 bits after the split).
+// Structure: one persistent CTA per SM, 17 warps.
+//   warps 0-15  epilogue warps, grouped into NCH "channels"; a channel owns one 128-point tile at a time and
+//               walks it through bg MLP / the K-1 fg slots.  Thread <-> TMEM lane <-> point.
+//                 3-pass modes : NCH = 2 channels x 8 warps; the two warps sharing a lane quadrant split the
+//                                64 feature columns (TMEM: D 2x64 | H hi 32 | H lo 32 | P hi 24 | P lo 24 columns)
+//                 1-pass modes : NCH = 4 channels x 4 warps (TMEM: D 64 | H 32 | P 24 columns per channel)
+//   warp 16     MMA issuer: lane 0 polls the channels' mbarriers round-robin and issues tcgen05.mma for
+//               whichever channel has operands ready; it also owns TMEM alloc and the weight bulk copies.
+// Per layer:  A (activations, 16-bit hi [+lo]) lives in TMEM, written by the epilogue threads with tcgen05.st;
+//   B (weights) is a 128B-swizzled K-major tile in shared memory; D (fp32) in TMEM.
+//   The epilogue signals the issuer per K-step (16 feature columns) so the next layer's MMAs start while the
+//   rest of the tile is still in its bias + ReLU + split epilogue; MMA completion comes back through
+//   tcgen05.commit on the channel's d_full mbarrier.
+// Precision: 1 pass of 16-bit operands, or 3 passes a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (fp32 accumulate);
+//   operands bf16 (range-safe, ~16 bits after the split) or fp16 (saturating, ~22 bits after the split).
 // The kernel makes two sweeps over its tiles: background MLP first (raw bg output parked in a 16 B/point
 // scratch), then the foreground MLP for slots 1..K-1 followed by the cross-slot composition.  The split
-// lets the bf16x3 weight image of ONE MLP (124 KB) stay resident in shared memory.
+// lets the 3-pass weight image of ONE MLP (124 KB) stay resident in shared memory.
 #include "common.cuh"
 #include "decoder_layout.h"
 #include "../../include/uorf_b200.h"
@@ -25,15 +31,27 @@
 namespace uorf {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 288;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = (kEpiWarps + 1) * 32;  // 544
 constexpr int kTmemCols = 512;
-// TMEM column map of one channel (channel c at column c*256)
-constexpr int kColD = 0;      // 64 fp32 accumulator columns
-constexpr int kColHHi = 64;   // 32 columns: hidden activations, bf16 pairs (K = 64)
-constexpr int kColHLo = 96;   // 32 columns: residuals
-constexpr int kColPHi = 128;  // 24 columns: positional encoding (K = 48)
-constexpr int kColPLo = 160;  // 24 columns
-constexpr int kChanCols = 256;
+
+template <int PASSES>
+struct Cfg {
+  static constexpr int NCH = PASSES == 3 ? 2 : 4;       // channels
+  static constexpr int CS = PASSES == 3 ? 2 : 1;        // threads per point (column split)
+  static constexpr int WPC = 4 * CS;                    // warps per channel
+  static constexpr int CHAN_COLS = 512 / NCH;           // TMEM columns per channel
+  // With two threads per point the accumulator is double buffered (layer l in D[l & 1]): the first MMA of the next
+  // layer is released by the column half that finishes first, while the other half may still be reading D.
+  static constexpr bool DBUF = PASSES == 3;
+  static constexpr int COL_D = 0;
+  static constexpr int COL_HHI = DBUF ? 128 : 64;
+  static constexpr int COL_HLO = 160;                   // 3-pass only
+  static constexpr int COL_PHI = DBUF ? 192 : 96;
+  static constexpr int COL_PLO = 224;                   // 3-pass only
+  static constexpr int NPL = PASSES == 3 ? 2 : 1;       // weight planes
+  __device__ static constexpr int dcol(int stage) { return COL_D + (DBUF ? (stage & 1) * 64 : 0); }
+};
 
 struct DecFwdParams {
   const float* coor_bg;
@@ -58,13 +76,17 @@ struct DecFwdParams {
   int* err_flag;
 };
 
-// ---- channel-side helpers -------------------------------------------------------------------------
+struct ChanBars {
+  uint64_t a_pos;       // positional encoding written (all threads of the channel)
+  uint64_t a_chunk[4];  // H columns of K-step j written (the 128 threads owning those columns)
+  uint64_t d_full;      // MMAs of the current layer complete (tcgen05.commit)
+};
 
-// positional encoding of one point -> TMEM (48 K-columns: 33 values + zero padding), reference order
-// [x y z | sin(2^i x..z) cos(2^i x..z)]_{i<5}  (model.py:261-277).  Frequencies 2,4,8,16 by angle doubling.
-template <int PASSES, bool F16>
-__device__ __forceinline__ void posenc_to_tmem(float x, float y, float z, uint32_t t_phi, uint32_t t_plo) {
-  float v[kPosencK];
+// ---- epilogue-side helpers ------------------------------------------------------------------------
+
+// positional encoding of one point, reference order [x y z | sin(2^i x..z) cos(2^i x..z)]_{i<5}
+// (model.py:261-277), zero padded to 48.  Frequencies 2,4,8,16 by angle doubling.
+__device__ __forceinline__ void posenc48(float x, float y, float z, float (&v)[kPosencK]) {
   v[0] = x; v[1] = y; v[2] = z;
   float s[3], c[3];
   sincosf(x, &s[0], &c[0]);
@@ -89,74 +111,76 @@ __device__ __forceinline__ void posenc_to_tmem(float x, float y, float z, uint32
   }
 #pragma unroll
   for (int i = kPosenc; i < kPosencK; ++i) v[i] = 0.f;
-  uint32_t hi[24], lo[24];
-#pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    if (PASSES == 3) split2<F16>(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-    else hi[i] = pack2<F16>(v[2 * i], v[2 * i + 1]);
-  }
-  tmem_st16(t_phi, hi);
-  tmem_st8(t_phi + 16, hi + 16);
-  if (PASSES == 3) {
-    tmem_st16(t_plo, lo);
-    tmem_st8(t_plo + 16, lo + 16);
-  }
-  tc_wait_st();
 }
 
-// hidden-layer epilogue: D (64 fp32 cols) + bias -> ReLU -> bf16 hi[/lo] -> H operand columns
-template <int PASSES, bool F16>
-__device__ __forceinline__ void hidden_epilogue(uint32_t t_d, uint32_t t_hhi, uint32_t t_hlo, const float* bias) {
+// write values v[2*W0 .. 2*(W0+NW)) as NW packed words at TMEM columns W0.. of the P operand
+template <int PASSES, bool F16, int W0, int NW>
+__device__ __forceinline__ void posenc_store(const float (&v)[kPosencK], uint32_t t_phi, uint32_t t_plo) {
+  uint32_t hi[NW], lo[NW];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t r[32];
-    tmem_ld32(t_d + half * 32, r);
-    tc_wait_ld();
-    uint32_t hi[16], lo[16];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 b = *reinterpret_cast<const float4*>(bias + half * 32 + 4 * q);
-      const float v0 = fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, 0.f);
-      const float v1 = fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, 0.f);
-      const float v2 = fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, 0.f);
-      const float v3 = fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, 0.f);
-      if (PASSES == 3) {
-        split2<F16>(v0, v1, hi[2 * q], lo[2 * q]);
-        split2<F16>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
-      } else {
-        hi[2 * q] = pack2<F16>(v0, v1);
-        hi[2 * q + 1] = pack2<F16>(v2, v3);
-      }
-    }
-    tmem_st16(t_hhi + half * 16, hi);
-    if (PASSES == 3) tmem_st16(t_hlo + half * 16, lo);
+  for (int i = 0; i < NW; ++i) {
+    if (PASSES == 3) split2<F16>(v[2 * (W0 + i)], v[2 * (W0 + i) + 1], hi[i], lo[i]);
+    else hi[i] = pack2<F16>(v[2 * (W0 + i)], v[2 * (W0 + i) + 1]);
   }
+  static_assert(NW == 24 || NW == 12, "posenc split");
+  if constexpr (NW == 24) {
+    tmem_st16(t_phi + W0, hi);
+    tmem_st8(t_phi + W0 + 16, hi + 16);
+    if (PASSES == 3) { tmem_st16(t_plo + W0, lo); tmem_st8(t_plo + W0 + 16, lo + 16); }
+  } else {
+    tmem_st8(t_phi + W0, hi);
+    tmem_st4(t_phi + W0 + 8, hi + 8);
+    if (PASSES == 3) { tmem_st8(t_plo + W0, lo); tmem_st4(t_plo + W0 + 8, lo + 8); }
+  }
+}
+
+// one 16-column chunk: r (fp32 accumulators) + bias -> ReLU -> 16-bit hi[/lo] -> 8 H operand columns
+template <int PASSES, bool F16>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const float* bias, uint32_t t_hhi, uint32_t t_hlo) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
+    const float v0 = fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, 0.f);
+    const float v1 = fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, 0.f);
+    const float v2 = fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, 0.f);
+    const float v3 = fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, 0.f);
+    if (PASSES == 3) {
+      split2<F16>(v0, v1, hi[2 * q], lo[2 * q]);
+      split2<F16>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
+    } else {
+      hi[2 * q] = pack2<F16>(v0, v1);
+      hi[2 * q + 1] = pack2<F16>(v2, v3);
+    }
+  }
+  tmem_st8(t_hhi, hi);
+  if (PASSES == 3) tmem_st8(t_hlo, lo);
   tc_wait_st();
 }
 
 // ---- issuer-side helper ---------------------------------------------------------------------------
-// D (+)= A[tmem] . W[tile]^T over `ksteps` K-steps of 16, in 1 or 3 bf16 passes
+// D (+)= A[tmem, K-steps j0..j1) . W[tile]^T, in 1 or 3 passes
 template <int PASSES>
-__device__ __forceinline__ void issue_gemm(uint32_t t_d, uint32_t t_ahi, uint32_t t_alo, uint32_t w_smem,
-                                           int ksteps, uint32_t idesc, bool& first) {
+__device__ __forceinline__ void issue_ksteps(uint32_t t_d, uint32_t t_ahi, uint32_t t_alo, uint32_t w_smem, int j0, int j1,
+                                             uint32_t idesc, bool& first) {
   const uint64_t dhi = make_sdesc_sw128(w_smem);
-  const uint64_t dlo = make_sdesc_sw128(w_smem + kPlaneBytes);
-  for (int j = 0; j < ksteps; ++j) {
+  for (int j = j0; j < j1; ++j) {
     mma_ts(t_d, t_ahi + 8 * j, dhi + 2 * j, idesc, first ? 0u : 1u);
     first = false;
   }
   if (PASSES == 3) {
-    for (int j = 0; j < ksteps; ++j) mma_ts(t_d, t_alo + 8 * j, dhi + 2 * j, idesc, 1u);
-    for (int j = 0; j < ksteps; ++j) mma_ts(t_d, t_ahi + 8 * j, dlo + 2 * j, idesc, 1u);
+    const uint64_t dlo = make_sdesc_sw128(w_smem + kPlaneBytes);
+    for (int j = j0; j < j1; ++j) mma_ts(t_d, t_alo + 8 * j, dhi + 2 * j, idesc, 1u);
+    for (int j = j0; j < j1; ++j) mma_ts(t_d, t_ahi + 8 * j, dlo + 2 * j, idesc, 1u);
   }
 }
 
 template <int PASSES, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdParams p) {
+  using C = Cfg<PASSES>;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_w;
-  __shared__ __align__(8) uint64_t bar_a[2];
-  __shared__ __align__(8) uint64_t bar_d[2];
+  __shared__ __align__(8) ChanBars bars[C::NCH];
   __shared__ uint32_t tmem_base_s;
 
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -164,21 +188,21 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int K = p.K;
-  constexpr int NPL = PASSES == 3 ? 2 : 1;
-  const int w_region = NPL * kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
-  const float* s_params = reinterpret_cast<const float*>(smem + NPL * kPlaneBytes);
+  const int w_region = C::NPL * kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
+  const float* s_params = reinterpret_cast<const float*>(smem + C::NPL * kPlaneBytes);
   const float* s_slotb = s_params + kParamFloats;
-  float4* s_stash = reinterpret_cast<float4*>(smem + ((w_region + 127) & ~127));  // [2][K][128]
+  float4* s_stash = reinterpret_cast<float4*>(smem + ((w_region + 127) & ~127));  // [NCH][K][128]
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_a[0], kTileM);
-    mbar_init(&bar_a[1], kTileM);
-    mbar_init(&bar_d[0], 1);
-    mbar_init(&bar_d[1], 1);
+    for (int c = 0; c < C::NCH; ++c) {
+      mbar_init(&bars[c].a_pos, kTileM * C::CS);
+      for (int j = 0; j < 4; ++j) mbar_init(&bars[c].a_chunk[j], kTileM);
+      mbar_init(&bars[c].d_full, 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 8) {
+  if (warp == kEpiWarps) {
     tmem_alloc(&tmem_base_s, kTmemCols);
     tmem_relinquish();
   }
@@ -196,13 +220,16 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
       T[r * 4 + c] = p.fixed_locality ? __ldg(p.fg_transform + r * 4 + c) : (c < 3 ? __ldg(p.fg_transform + r * 3 + c) : 0.f);
   }
 
-  // running completion counts of the channel barriers (parity = count & 1); every role tracks its own copy
-  uint32_t n_a[2] = {0, 0}, n_d[2] = {0, 0};
+  // completion counts of the barriers (parity = count & 1); the epilogue threads and the issuer keep their own copies
+  uint32_t n_d = 0;                                   // epilogue: d_full completions consumed by this thread
+  uint32_t i_pos[C::NCH], i_chunk[C::NCH];            // issuer: a_pos / a_chunk completions consumed per channel
+#pragma unroll
+  for (int c = 0; c < C::NCH; ++c) i_pos[c] = i_chunk[c] = 0;
 
   for (int phase = 0; phase < 2; ++phase) {  // 0: background MLP, 1: foreground MLP + composition
     const int nslots = phase == 0 ? 1 : K - 1;
     // ---- load this phase's weight image ----------------------------------------------------------
-    if (warp == 8 && lane == 0) {
+    if (warp == kEpiWarps && lane == 0) {
       fence_proxy_async_smem();
       const unsigned char* src = p.image + (phase ? blob_fg_offset(PASSES) : 0);
       const uint32_t bytes = (uint32_t)blob_bytes_one(PASSES, nslots);
@@ -214,54 +241,95 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
     }
     mbar_wait(&bar_w, phase & 1, p.err_flag, 100 + phase);
 
-    const uint32_t idesc64 = make_idesc_f32acc(128, 64, F16);
-    const uint32_t idesc_head = make_idesc_f32acc(128, phase == 0 ? 16 : 32, F16);
-
-    if (warp == 8) {
-      // =========================== MMA issuer ===========================
-      const uint32_t w_smem = smem_u32(smem);
-      for (int it = 0;; ++it) {
-        const long long tile0 = (long long)blockIdx.x + (long long)gridDim.x * (2 * it);
-        const long long tile1 = tile0 + gridDim.x;
-        if (tile0 >= p.num_tiles) break;
-        const bool has1 = tile1 < p.num_tiles;
-        for (int s = 0; s < nslots; ++s) {
-          for (int st = 0; st < 7; ++st) {
-            for (int ch = 0; ch < 2; ++ch) {
-              if (ch == 1 && !has1) continue;
-              mbar_wait(&bar_a[ch], n_a[ch] & 1, p.err_flag, 200 + st);
-              ++n_a[ch];
+    if (warp == kEpiWarps) {
+      // =========================== MMA issuer (lane 0 polls all channels) ===========================
+      if (lane == 0) {
+        const uint32_t idesc64 = make_idesc_f32acc(128, 64, F16);
+        const uint32_t idesc_head = make_idesc_f32acc(128, phase == 0 ? 16 : 32, F16);
+        const uint32_t w_smem = smem_u32(smem);
+        // per-channel cursor: tile iteration, slot, stage (0..6), K-step chunk within the stage (0..3)
+        int c_it[C::NCH], c_slot[C::NCH], c_stage[C::NCH], c_chunk[C::NCH];
+        bool c_done[C::NCH];
+        int n_active = 0;
+#pragma unroll
+        for (int c = 0; c < C::NCH; ++c) {
+          c_it[c] = c_slot[c] = c_stage[c] = c_chunk[c] = 0;
+          c_done[c] = (long long)blockIdx.x + (long long)gridDim.x * c >= p.num_tiles;
+          n_active += c_done[c] ? 0 : 1;
+        }
+        long long t_last = clock64();
+        while (n_active > 0) {
+          bool progress = false;
+#pragma unroll
+          for (int c = 0; c < C::NCH; ++c) {
+            if (c_done[c]) continue;
+            const uint32_t tb = tmem_base + c * C::CHAN_COLS;
+            const int st = c_stage[c];
+            if (st == 0) {
+              if (!mbar_test_wait(&bars[c].a_pos, i_pos[c] & 1)) continue;
+              ++i_pos[c];
               tc_fence_after();
-              if (lane == 0) {
-                const uint32_t tb = tmem_base + ch * kChanCols;
-                bool first = true;
-                switch (st) {
-                  case 0: issue_gemm<PASSES>(tb + kColD, tb + kColPHi, tb + kColPLo, w_smem + 0 * kTileBytes, 3, idesc64, first); break;
-                  case 1: issue_gemm<PASSES>(tb + kColD, tb + kColHHi, tb + kColHLo, w_smem + 1 * kTileBytes, 4, idesc64, first); break;
-                  case 2: issue_gemm<PASSES>(tb + kColD, tb + kColHHi, tb + kColHLo, w_smem + 2 * kTileBytes, 4, idesc64, first); break;
-                  case 3:
-                    issue_gemm<PASSES>(tb + kColD, tb + kColPHi, tb + kColPLo, w_smem + 3 * kTileBytes, 3, idesc64, first);
-                    issue_gemm<PASSES>(tb + kColD, tb + kColHHi, tb + kColHLo, w_smem + 4 * kTileBytes, 4, idesc64, first);
-                    break;
-                  case 4: issue_gemm<PASSES>(tb + kColD, tb + kColHHi, tb + kColHLo, w_smem + 5 * kTileBytes, 4, idesc64, first); break;
-                  case 5: issue_gemm<PASSES>(tb + kColD, tb + kColHHi, tb + kColHLo, w_smem + 6 * kTileBytes, 4, idesc64, first); break;
-                  default: issue_gemm<PASSES>(tb + kColD, tb + kColHHi, tb + kColHLo, w_smem + 7 * kTileBytes, 4, idesc_head, first); break;
+              bool first = true;
+              issue_ksteps<PASSES>(tb + C::dcol(0), tb + C::COL_PHI, tb + C::COL_PLO, w_smem + 0 * kTileBytes, 0, 3, idesc64, first);
+              tc_commit(&bars[c].d_full);
+              c_stage[c] = 1;
+              c_chunk[c] = 0;
+            } else {
+              const int j = c_chunk[c];
+              if (!mbar_test_wait(&bars[c].a_chunk[j], i_chunk[c] & 1)) continue;
+              tc_fence_after();
+              bool first = (j == 0);
+              if (st == 3 && j == 0)  // skip connection: the positional-encoding half of after.0 needs no new operand
+                issue_ksteps<PASSES>(tb + C::dcol(3), tb + C::COL_PHI, tb + C::COL_PLO, w_smem + 3 * kTileBytes, 0, 3, idesc64, first);
+              const int tile_idx = st < 3 ? st : st + 1;  // stages 1,2 -> tiles 1,2 ; 3 -> 4 ; 4,5 -> 5,6 ; 6 -> 7
+              issue_ksteps<PASSES>(tb + C::dcol(st), tb + C::COL_HHI, tb + C::COL_HLO, w_smem + tile_idx * kTileBytes, j, j + 1,
+                                   st == 6 ? idesc_head : idesc64, first);
+              if (j == 3) {
+                tc_commit(&bars[c].d_full);
+                ++i_chunk[c];
+                c_chunk[c] = 0;
+                if (st == 6) {  // slot finished
+                  c_stage[c] = 0;
+                  if (++c_slot[c] == nslots) {
+                    c_slot[c] = 0;
+                    ++c_it[c];
+                    if ((long long)blockIdx.x + (long long)gridDim.x * ((long long)c_it[c] * C::NCH + c) >= p.num_tiles) {
+                      c_done[c] = true;
+                      --n_active;
+                    }
+                  }
+                } else {
+                  c_stage[c] = st + 1;
                 }
-                tc_commit(&bar_d[ch]);
+              } else {
+                c_chunk[c] = j + 1;
               }
-              __syncwarp();
             }
+            progress = true;
+          }
+          if (progress) {
+            t_last = clock64();
+          } else if (clock64() - t_last > 4000000000LL) {  // ~2 s without progress: protocol bug, do not hang the box
+            if (p.err_flag) atomicExch(p.err_flag, 200);
+            __threadfence_system();
+            __trap();
           }
         }
       }
+      __syncwarp();
     } else {
-      // =========================== channel (one point per thread) ===========================
-      const int ch = warp >> 2;
-      const int t = threadIdx.x & 127;
-      const uint32_t tb = tmem_base + ch * kChanCols + ((uint32_t)((warp & 3) * 32) << 16);
+      // =========================== epilogue warps ===========================
+      const int ch = warp / C::WPC;
+      const int wic = warp % C::WPC;          // warp within channel
+      const int half = wic >> 2;              // which half of the feature columns (3-pass modes); 0 otherwise
+      const int t = (wic & 3) * 32 + lane;    // point within the tile == TMEM lane
+      const uint32_t tb = tmem_base + ch * C::CHAN_COLS + ((uint32_t)((warp & 3) * 32) << 16);
+      ChanBars& cb = bars[ch];
       float4* stash = s_stash + (size_t)ch * K * kTileM;
+      constexpr int NCOL = 64 / C::CS;        // accumulator columns this thread owns per hidden layer
+      const int col0 = half * NCOL;
       for (int it = 0;; ++it) {
-        const long long tile = (long long)blockIdx.x + (long long)gridDim.x * (2 * it + ch);
+        const long long tile = (long long)blockIdx.x + (long long)gridDim.x * ((long long)it * C::NCH + ch);
         if (tile >= p.num_tiles) break;
         const long long pt = tile * kTileM + t;
         const bool valid = pt < p.P;
@@ -282,67 +350,96 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
             const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], x), __fmul_rn(T[9], y)), __fmul_rn(T[10], z)), T[11]);
             x = tx; y = ty; z = tz;
             if (!p.fixed_locality) outside = fabsf(x) > p.locality_ratio || fabsf(y) > p.locality_ratio || fabsf(z) > p.locality_ratio;
-            if (p.outside && valid) p.outside[(long long)s * p.P + pt] = outside ? 1 : 0;
+            if (p.outside && valid && half == 0) p.outside[(long long)s * p.P + pt] = outside ? 1 : 0;
           }
-          posenc_to_tmem<PASSES, F16>(x, y, z, tb + kColPHi, tb + kColPLo);
+          {
+            float v[kPosencK];
+            posenc48(x, y, z, v);
+            if (C::CS == 1) {
+              posenc_store<PASSES, F16, 0, 24>(v, tb + C::COL_PHI, tb + C::COL_PLO);
+            } else if (half == 0) {
+              posenc_store<PASSES, F16, 0, 12>(v, tb + C::COL_PHI, tb + C::COL_PLO);
+            } else {
+              posenc_store<PASSES, F16, 12, 12>(v, tb + C::COL_PHI, tb + C::COL_PLO);
+            }
+            tc_wait_st();
+          }
           tc_fence_before();
-          mbar_arrive(&bar_a[ch]);
+          mbar_arrive(&cb.a_pos);
 
           // ---- stages 1..6: hidden layers ----
           const float* sb = s_slotb + s * kSlotBiasFloats;
 #pragma unroll 1
           for (int st = 1; st <= 6; ++st) {
-            const float* bias = st == 1 ? sb : st == 2 ? s_params + kPB1 : st == 3 ? s_params + kPB2
-                              : st == 4 ? sb + 64 : st == 5 ? s_params + kPA1 : s_params + kPA2;
-            mbar_wait(&bar_d[ch], n_d[ch] & 1, p.err_flag, 300 + st);
-            ++n_d[ch];
+            const float* bias = (st == 1 ? sb : st == 2 ? s_params + kPB1 : st == 3 ? s_params + kPB2
+                               : st == 4 ? sb + 64 : st == 5 ? s_params + kPA1 : s_params + kPA2) + col0;
+            mbar_wait(&cb.d_full, n_d & 1, p.err_flag, 300 + st);
+            ++n_d;
             tc_fence_after();
-            hidden_epilogue<PASSES, F16>(tb + kColD, tb + kColHHi, tb + kColHLo, bias);
-            tc_fence_before();
-            mbar_arrive(&bar_a[ch]);
-          }
-          // ---- stage 7: heads ----
-          mbar_wait(&bar_d[ch], n_d[ch] & 1, p.err_flag, 307);
-          ++n_d[ch];
-          tc_fence_after();
-          if (phase == 0) {
-            uint32_t r[16];
-            tmem_ld16(tb + kColD, r);
+            // pull every accumulator column this thread owns into registers first; the next layer's first
+            // (overwriting) MMA is released by chunk 0, so D must be either fully read by then (one thread per
+            // point arrives on chunk 0 only after this load) or double buffered (two threads per point)
+            uint32_t r[NCOL];
+            const uint32_t t_d = tb + C::dcol(st - 1) + col0;   // written by MMA stage st-1
+            tmem_ld32(t_d, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+            if (NCOL == 64) tmem_ld32(t_d + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[NCOL == 64 ? 32 : 0]));
             tc_wait_ld();
-            const float* hb = s_params + kPHeadB;
-            float4 o;
-            o.x = __uint_as_float(r[0]) + hb[0];
-            o.y = __uint_as_float(r[1]) + hb[1];
-            o.z = __uint_as_float(r[2]) + hb[2];
-            o.w = __uint_as_float(r[3]) + hb[3];
-            if (valid) p.scratch_bg[pt] = o;
-          } else {
-            uint32_t r[32];
-            tmem_ld32(tb + kColD, r);
-            tc_wait_ld();
-            const float* hb = s_params + kPHeadB;
-            const float* wc2 = s_params + kPWc2;
-            float c0 = s_params[kPBc2 + 0], c1 = s_params[kPBc2 + 1], c2 = s_params[kPBc2 + 2];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float h = fmaxf(__uint_as_float(r[i]) + hb[i], 0.f);
-              c0 = fmaf(wc2[i], h, c0);
-              c1 = fmaf(wc2[16 + i], h, c1);
-              c2 = fmaf(wc2[32 + i], h, c2);
+            for (int jc = 0; jc < NCOL / 16; ++jc) {
+              const int j = half * (NCOL / 16) + jc;  // K-step index of the next layer
+              epilogue_chunk<PASSES, F16>(r + 16 * jc, bias + 16 * jc, tb + C::COL_HHI + 8 * j, tb + C::COL_HLO + 8 * j);
+              tc_fence_before();
+              mbar_arrive(&cb.a_chunk[j]);
             }
-            float sig = __uint_as_float(r[kHeadShapeRow]) + hb[kHeadShapeRow];
-            if (p.locality && outside) sig = 0.f;  // model.py:147-148
-            stash[(s + 1) * kTileM + t] = make_float4(c0, c1, c2, sig);
+          }
+          // ---- stage 7: heads (computed by the first column half; every thread consumes the barrier phase) ----
+          mbar_wait(&cb.d_full, n_d & 1, p.err_flag, 307);
+          ++n_d;
+          tc_fence_after();
+          if (half == 0) {
+            if (phase == 0) {
+              uint32_t r[16];
+              tmem_ld16(tb + C::dcol(6), r);
+              tc_wait_ld();
+              const float* hb = s_params + kPHeadB;
+              float4 o;
+              o.x = __uint_as_float(r[0]) + hb[0];
+              o.y = __uint_as_float(r[1]) + hb[1];
+              o.z = __uint_as_float(r[2]) + hb[2];
+              o.w = __uint_as_float(r[3]) + hb[3];
+              if (valid) p.scratch_bg[pt] = o;
+            } else {
+              uint32_t r[32];
+              tmem_ld32(tb + C::dcol(6), r);
+              tc_wait_ld();
+              const float* hb = s_params + kPHeadB;
+              const float* wc2 = s_params + kPWc2;
+              float c0 = s_params[kPBc2 + 0], c1 = s_params[kPBc2 + 1], c2 = s_params[kPBc2 + 2];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float h = fmaxf(__uint_as_float(r[i]) + hb[i], 0.f);
+                c0 = fmaf(wc2[i], h, c0);
+                c1 = fmaf(wc2[16 + i], h, c1);
+                c2 = fmaf(wc2[32 + i], h, c2);
+              }
+              float sig = __uint_as_float(r[kHeadShapeRow]) + hb[kHeadShapeRow];
+              if (p.locality && outside) sig = 0.f;  // model.py:147-148
+              stash[(s + 1) * kTileM + t] = make_float4(c0, c1, c2, sig);
+            }
           }
         }
         if (phase == 1) {
-          // ---- cross-slot composition (model.py:151-159) ----
-          if (valid) stash[t] = p.scratch_bg[pt];
+          // ---- cross-slot composition (model.py:151-159); the two column halves take alternate slots ----
+          if (half == 0 && valid) stash[t] = p.scratch_bg[pt];
+          if (C::CS == 2) named_bar_sync(1 + ch * 4 + (wic & 3), 64);  // head results of the partner warp are visible
           float S = 0.f;
           for (int k = 0; k < K; ++k) S += fmaxf(stash[k * kTileM + t].w, 0.f);
           const float denom = S + 1e-5f;
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool want_sum = half == 0 && p.raws != nullptr;
           for (int k = 0; k < K; ++k) {
+            const bool mine = C::CS == 1 || (k & 1) == half;
+            if (!mine && !want_sum) continue;
             const float4 rw = stash[k * kTileM + t];
             const float dens = fmaxf(rw.w, 0.f);
             const float m = dens / denom;
@@ -354,13 +451,14 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
             if (p.noise != nullptr && valid) u.w = dens + p.dens_noise * __ldg(p.noise + (long long)k * p.P + pt);
             const float4 mk = make_float4(u.x * m, u.y * m, u.z * m, u.w * m);
             acc.x += mk.x; acc.y += mk.y; acc.z += mk.z; acc.w += mk.w;
-            if (valid) {
+            if (valid && mine) {
               if (p.unmasked) p.unmasked[(long long)k * p.P + pt] = u;
               if (p.masked) p.masked[(long long)k * p.P + pt] = mk;
               if (p.masks) p.masks[(long long)k * p.P + pt] = m;
             }
           }
-          if (valid && p.raws) p.raws[pt] = acc;
+          if (valid && want_sum) p.raws[pt] = acc;
+          if (C::CS == 2) named_bar_sync(1 + ch * 4 + (wic & 3), 64);  // stash may be overwritten by the next tile
         }
       }
     }
@@ -369,13 +467,14 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
     __syncthreads();
     tc_fence_after();
   }
-  if (warp == 8) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kEpiWarps) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 static size_t decoder_smem_bytes(int passes, int K) {
   const int npl = passes == 3 ? 2 : 1;
+  const int nch = passes == 3 ? 2 : 4;
   const int w_region = npl * kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
-  return 1024 + ((w_region + 127) & ~127) + (size_t)2 * K * kTileM * sizeof(float4);
+  return 1024 + ((w_region + 127) & ~127) + (size_t)nch * K * kTileM * sizeof(float4);
 }
 
 int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, cudaStream_t stream) {
@@ -400,12 +499,12 @@ int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, c
   p.locality = a->locality;
   p.num_tiles = (int)((a->P + kTileM - 1) / kTileM);
   p.err_flag = err_flag;
-  const size_t smem = decoder_smem_bytes(a->precision >= 3 ? 3 : 1, a->K);
+  const int passes = a->precision >= 3 ? 3 : 1;
+  const bool f16 = (a->precision % 2) == 0;
+  const size_t smem = decoder_smem_bytes(passes, a->K);
   if (smem > 227 * 1024) return UORF_ERR_UNSUPPORTED;
   int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   if (grid < 1) return UORF_OK;
-  const int passes = a->precision >= 3 ? 3 : 1;
-  const bool f16 = (a->precision % 2) == 0;
   auto launch = [&](auto kern) -> int {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UORF_ERR_DEVICE;
     kern<<<grid, kThreads, smem, stream>>>(p);

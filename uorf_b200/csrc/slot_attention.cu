@@ -6,8 +6,8 @@
 //             attn = softmax over SLOTS + eps ; per-slot renormalise over tokens ;     (:235-238)
 //             updates = attn_w . v ; slot = GRUCell(updates, slot) ; slot += MLP(LN(slot)) }  (:240-255)
 // The work is ~0.1 GFLOP and latency-bound, so it is fp32 FFMA, organised to need only two kinds of
-// launch per iteration: a token-parallel pass over all SMs (q, dots, softmax, partial weighted sums) and a
-// single-CTA slot update (reduction of the partials, GRU, residual MLP).  Reductions run in a fixed order,
+// launch per iteration: a token-parallel pass over all SMs (dots, softmax, partial weighted sums) and a
+// one-CTA-per-slot update (reduction of the partials, GRU, residual MLP, next query).  Reductions run in a fixed order,
 // so results are deterministic.
 #include "common.cuh"
 #include "../../include/uorf_b200.h"
@@ -31,6 +31,7 @@ struct SaParams {
   float* kbuf;     // [ntok][C]
   float* vbuf;     // [ntok][C]
   float* partial;  // [nblk][K][C+1]
+  float* qbuf;     // [K][C] queries of the current iteration
   float* slots;    // [K][C] state (slot 0 = bg)
   float* attn;     // [K][ntok]
 };
@@ -75,54 +76,78 @@ __global__ void __launch_bounds__(kSaThreads) sa_kv_kernel(const SaParams p) {
   }
 }
 
-// ---- slot initialisation --------------------------------------------------------------------------
-__global__ void sa_init_kernel(const SaParams p) {
-  const int C = p.C;
-  for (int e = threadIdx.x; e < p.K * C; e += blockDim.x) {
-    const int k = e / C, c = e % C;
-    p.slots[e] = k == 0 ? p.w.slots_mu_bg[c] + expf(p.w.slots_logsigma_bg[c]) * p.noise_bg[c]
-                        : p.w.slots_mu[c] + expf(p.w.slots_logsigma[c]) * p.noise_fg[(k - 1) * C + c];
+// ---- helpers for the per-slot CTAs (256 threads = 8 warps) -----------------------------------------
+// y[o] = bias[o] + sum_c W[o][c] * x[c] for o < n_out: one warp per output row, lanes stride over c, so the
+// weight rows are read with unit stride (coalesced) and reduced with shuffles.
+__device__ __forceinline__ void warp_matvec(const float* __restrict__ W, const float* __restrict__ bias, const float* x, float* y,
+                                            int n_out, int n_in, bool relu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < n_out; o += nw) {
+    float acc = 0.f;
+    for (int c = lane; c < n_in; c += 32) acc = fmaf(__ldg(W + (long long)o * n_in + c), x[c], acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) {
+      acc += bias ? bias[o] : 0.f;
+      y[o] = relu ? fmaxf(acc, 0.f) : acc;
+    }
   }
 }
+// LayerNorm of x[0..C) by warp 0 -> y
+__device__ __forceinline__ void warp0_layernorm(const float* x, const float* __restrict__ w, const float* __restrict__ b, float* y, int C) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += x[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = x[c] - mean; q += d * d; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / C + 1e-5f);
+    for (int c = lane; c < C; c += 32) y[c] = (x[c] - mean) * rstd * w[c] + b[c];
+  }
+}
+// q_k = to_q(LN(slot_k)) -> global q buffer
+__device__ __forceinline__ void slot_query(const SaParams& p, int k, const float* slot, float* s_ln, float* s_q) {
+  warp0_layernorm(slot, k == 0 ? p.w.to_q_bg_ln_w : p.w.to_q_ln_w, k == 0 ? p.w.to_q_bg_ln_b : p.w.to_q_ln_b, s_ln, p.C);
+  __syncthreads();
+  warp_matvec(k == 0 ? p.w.to_q_bg_w : p.w.to_q_w, nullptr, s_ln, s_q, p.C, p.C, false);
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) p.qbuf[k * p.C + c] = s_q[c];
+}
 
-// ---- pass B (per iteration): q, dots, softmax over slots, partial sums ----------------------------
+// ---- slot initialisation + first query; one CTA per slot -------------------------------------------
+__global__ void __launch_bounds__(kSaThreads) sa_init_kernel(const SaParams p) {
+  __shared__ float s_slot[kSaMaxC], s_ln[kSaMaxC], s_q[kSaMaxC];
+  const int k = blockIdx.x, C = p.C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = k == 0 ? p.w.slots_mu_bg[c] + expf(p.w.slots_logsigma_bg[c]) * p.noise_bg[c]
+                           : p.w.slots_mu[c] + expf(p.w.slots_logsigma[c]) * p.noise_fg[(k - 1) * C + c];
+    s_slot[c] = v;
+    p.slots[k * C + c] = v;
+  }
+  __syncthreads();
+  slot_query(p, k, s_slot, s_ln, s_q);
+}
+
+// ---- pass B (per iteration): dots, softmax over slots, partial weighted sums -------------------------
 __global__ void __launch_bounds__(kSaThreads) sa_attn_kernel(const SaParams p) {
   __shared__ float s_q[kSaMaxK][kSaMaxC + 1];
-  __shared__ float s_ln[kSaMaxK][kSaMaxC + 1];
   __shared__ float s_k[kSaTok][kSaMaxC + 1];
   __shared__ float s_v[kSaTok][kSaMaxC + 1];
   __shared__ float s_a[kSaMaxK][kSaTok];
   const int C = p.C, K = p.K;
   const int t0 = blockIdx.x * kSaTok;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int e = threadIdx.x; e < kSaTok * C; e += kSaThreads) {
     const int t = e / C, c = e % C;
     const bool in = t0 + t < p.ntok;
     s_k[t][c] = in ? p.kbuf[(long long)(t0 + t) * C + c] : 0.f;
     s_v[t][c] = in ? p.vbuf[(long long)(t0 + t) * C + c] : 0.f;
   }
-  // LN of each slot (warp per slot)
-  for (int k = warp; k < K; k += kSaThreads / 32) {
-    const float* lw = k == 0 ? p.w.to_q_bg_ln_w : p.w.to_q_ln_w;
-    const float* lb = k == 0 ? p.w.to_q_bg_ln_b : p.w.to_q_ln_b;
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += p.slots[k * C + c];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / C;
-    float q = 0.f;
-    for (int c = lane; c < C; c += 32) { const float d = p.slots[k * C + c] - mean; q += d * d; }
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / C + 1e-5f);
-    for (int c = lane; c < C; c += 32) s_ln[k][c] = (p.slots[k * C + c] - mean) * rstd * lw[c] + lb[c];
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < K * C; e += kSaThreads) {
-    const int k = e / C, o = e % C;
-    const float* wq = (k == 0 ? p.w.to_q_bg_w : p.w.to_q_w) + o * C;
-    float acc = 0.f;
-    for (int c = 0; c < C; ++c) acc = fmaf(s_ln[k][c], __ldg(wq + c), acc);
-    s_q[k][o] = acc;
-  }
+  for (int e = threadIdx.x; e < K * C; e += kSaThreads) s_q[e / C][e % C] = p.qbuf[e];
   __syncthreads();
   const float scale = rsqrtf((float)C);
   for (int e = threadIdx.x; e < K * kSaTok; e += kSaThreads) {
@@ -157,81 +182,58 @@ __global__ void __launch_bounds__(kSaThreads) sa_attn_kernel(const SaParams p) {
   }
 }
 
-// ---- pass C (per iteration): reduce partials, GRUCell, residual MLP; one CTA ----------------------
+// ---- pass C (per iteration): reduce partials, GRUCell, residual MLP, next query; one CTA per slot ------
 __global__ void __launch_bounds__(kSaThreads) sa_update_kernel(const SaParams p, int nblk) {
-  __shared__ float s_u[kSaMaxK][kSaMaxC + 1];   // updates
-  __shared__ float s_h[kSaMaxK][kSaMaxC + 1];   // previous slots
-  __shared__ float s_g[kSaMaxK][6 * kSaMaxC];   // gi (3C) | gh (3C)
-  __shared__ float s_n[kSaMaxK][kSaMaxC + 1];   // new slot / LN
-  __shared__ float s_m[kSaMaxK][kSaMaxHid];
-  const int C = p.C, K = p.K, Hd = p.hidden;
+  __shared__ float s_u[kSaMaxC], s_h[kSaMaxC], s_g[6 * kSaMaxC], s_n[kSaMaxC], s_ln[kSaMaxC], s_m[kSaMaxHid], s_o[kSaMaxC];
+  __shared__ float s_red[kSaThreads / 32][kSaMaxC + 1];
+  const int C = p.C, K = p.K, Hd = p.hidden, k = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int e = threadIdx.x; e < K * C; e += kSaThreads) {
-    const int k = e / C, c = e % C;
-    float num = 0.f, den = 0.f;
-    for (int b = 0; b < nblk; ++b) {
-      const float* part = p.partial + ((long long)b * K + k) * (C + 1);
-      num += part[c];
-      den += part[C];
-    }
-    s_u[k][c] = num / den;
-    s_h[k][c] = p.slots[e];
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < K * 6 * C; e += kSaThreads) {
-    const int k = e / (6 * C), j = e % (6 * C);
-    const bool hh = j >= 3 * C;
-    const int o = hh ? j - 3 * C : j;
-    const float* W = k == 0 ? (hh ? p.w.gru_bg_w_hh : p.w.gru_bg_w_ih) : (hh ? p.w.gru_w_hh : p.w.gru_w_ih);
-    const float* B = k == 0 ? (hh ? p.w.gru_bg_b_hh : p.w.gru_bg_b_ih) : (hh ? p.w.gru_b_hh : p.w.gru_b_ih);
-    const float* x = hh ? s_h[k] : s_u[k];
+  // fixed-order reduction of the per-CTA partials: warp w sums blocks w, w+8, ...; then the 8 warp sums in order
+  for (int c = lane; c <= C; c += 32) {
     float acc = 0.f;
-    for (int c = 0; c < C; ++c) acc = fmaf(x[c], __ldg(W + o * C + c), acc);
-    s_g[k][j] = acc + B[o];
+    for (int b = warp; b < nblk; b += kSaThreads / 32) acc += p.partial[((long long)b * K + k) * (C + 1) + c];
+    s_red[warp][c] = acc;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < K * C; e += kSaThreads) {
-    const int k = e / C, c = e % C;
-    const float r = 1.f / (1.f + expf(-(s_g[k][c] + s_g[k][3 * C + c])));
-    const float z = 1.f / (1.f + expf(-(s_g[k][C + c] + s_g[k][4 * C + c])));
-    const float n = tanhf(s_g[k][2 * C + c] + r * s_g[k][5 * C + c]);
-    s_u[k][c] = (1.f - z) * n + z * s_h[k][c];  // new hidden state
+  if (threadIdx.x <= C) {
+    float acc = 0.f;
+    for (int w = 0; w < kSaThreads / 32; ++w) acc += s_red[w][threadIdx.x];
+    s_red[0][threadIdx.x] = acc;
   }
   __syncthreads();
-  for (int k = warp; k < K; k += kSaThreads / 32) {
-    const float* lw = k == 0 ? p.w.to_res_bg_ln_w : p.w.to_res_ln_w;
-    const float* lb = k == 0 ? p.w.to_res_bg_ln_b : p.w.to_res_ln_b;
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += s_u[k][c];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / C;
-    float q = 0.f;
-    for (int c = lane; c < C; c += 32) { const float d = s_u[k][c] - mean; q += d * d; }
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / C + 1e-5f);
-    for (int c = lane; c < C; c += 32) s_n[k][c] = (s_u[k][c] - mean) * rstd * lw[c] + lb[c];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_u[c] = s_red[0][c] / s_red[0][C];
+    s_h[c] = p.slots[k * C + c];
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < K * Hd; e += kSaThreads) {
-    const int k = e / Hd, j = e % Hd;
-    const float* W = (k == 0 ? p.w.to_res_bg_w1 : p.w.to_res_w1) + j * C;
-    float acc = (k == 0 ? p.w.to_res_bg_b1 : p.w.to_res_b1)[j];
-    for (int c = 0; c < C; ++c) acc = fmaf(s_n[k][c], __ldg(W + c), acc);
-    s_m[k][j] = fmaxf(acc, 0.f);
+  warp_matvec(k == 0 ? p.w.gru_bg_w_ih : p.w.gru_w_ih, k == 0 ? p.w.gru_bg_b_ih : p.w.gru_b_ih, s_u, s_g, 3 * C, C, false);
+  warp_matvec(k == 0 ? p.w.gru_bg_w_hh : p.w.gru_w_hh, k == 0 ? p.w.gru_bg_b_hh : p.w.gru_b_hh, s_h, s_g + 3 * C, 3 * C, C, false);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float r = 1.f / (1.f + expf(-(s_g[c] + s_g[3 * C + c])));
+    const float z = 1.f / (1.f + expf(-(s_g[C + c] + s_g[4 * C + c])));
+    const float n = tanhf(s_g[2 * C + c] + r * s_g[5 * C + c]);
+    s_n[c] = (1.f - z) * n + z * s_h[c];  // new hidden state
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < K * C; e += kSaThreads) {
-    const int k = e / C, c = e % C;
-    const float* W = (k == 0 ? p.w.to_res_bg_w2 : p.w.to_res_w2) + c * Hd;
-    float acc = (k == 0 ? p.w.to_res_bg_b2 : p.w.to_res_b2)[c];
-    for (int j = 0; j < Hd; ++j) acc = fmaf(s_m[k][j], __ldg(W + j), acc);
-    p.slots[e] = s_u[k][c] + acc;
+  warp0_layernorm(s_n, k == 0 ? p.w.to_res_bg_ln_w : p.w.to_res_ln_w, k == 0 ? p.w.to_res_bg_ln_b : p.w.to_res_ln_b, s_ln, C);
+  __syncthreads();
+  warp_matvec(k == 0 ? p.w.to_res_bg_w1 : p.w.to_res_w1, k == 0 ? p.w.to_res_bg_b1 : p.w.to_res_b1, s_ln, s_m, Hd, C, true);
+  __syncthreads();
+  warp_matvec(k == 0 ? p.w.to_res_bg_w2 : p.w.to_res_w2, k == 0 ? p.w.to_res_bg_b2 : p.w.to_res_b2, s_m, s_o, C, Hd, false);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = s_n[c] + s_o[c];
+    s_n[c] = v;
+    p.slots[k * C + c] = v;
   }
+  __syncthreads();
+  slot_query(p, k, s_n, s_ln, s_o);   // query for the next iteration
 }
 
 size_t slot_attention_ws_floats(int ntok, int C, int K) {
   const size_t nblk = (ntok + kSaTok - 1) / kSaTok;
-  return (size_t)2 * ntok * C + nblk * K * (C + 1);
+  return (size_t)2 * ntok * C + nblk * K * (C + 1) + (size_t)K * C;
 }
 
 int launch_slot_attention(const uorf_slot_attention_weights* w, const float* feat, long long feat_ts, long long feat_cs,
@@ -247,13 +249,14 @@ int launch_slot_attention(const uorf_slot_attention_weights* w, const float* fea
   p.kbuf = workspace;
   p.vbuf = workspace + (size_t)ntok * C;
   p.partial = workspace + (size_t)2 * ntok * C;
+  p.qbuf = p.partial + (size_t)nblk * K * (C + 1);
   p.slots = slots;
   p.attn = attn;
   sa_kv_kernel<<<nblk, kSaThreads, 0, stream>>>(p);
-  sa_init_kernel<<<1, 256, 0, stream>>>(p);
+  sa_init_kernel<<<K, kSaThreads, 0, stream>>>(p);
   for (int it = 0; it < iters; ++it) {
     sa_attn_kernel<<<nblk, kSaThreads, 0, stream>>>(p);
-    sa_update_kernel<<<1, kSaThreads, 0, stream>>>(p, nblk);
+    sa_update_kernel<<<K, kSaThreads, 0, stream>>>(p, nblk);
   }
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }

@@ -63,6 +63,9 @@ class uorfEvalModel:
             raise RuntimeError("uorf_b200 drivers need a CUDA device (gpu_ids must not be empty); there is no CPU path")
         self.device = torch.device(f"cuda:{self.gpu_ids[0]}")
         self.isTrain = False
+        # the reference runs fp32 convolutions / matmuls with TF32 disabled (util/util.py:210-211, set_seed)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
         self.layout = layout
         self.model_names = ["Encoder", "SlotAttention", "Decoder"]
         render_size = (opt.render_size, opt.render_size)
