@@ -175,6 +175,8 @@ int uorf_slot_attention_forward(const uorf_slot_attention_weights* w, const floa
  * ------------------------------------------------------------------------------------------- */
 int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, int32_t precision, float* d,
                     void* stream);
+/* Diagnostic hook: SM-cycle counts of the decoder's handshake building blocks (out: 256 int64, device). */
+int uorf_probe_timing(int64_t* out, int32_t reps, void* stream);
 /* Test hook: site code written by a kernel whose mbarrier wait timed out (0 = none). */
 int uorf_debug_flag(void);
 

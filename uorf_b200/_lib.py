@@ -109,6 +109,7 @@ _SIGNATURES = {
     "uorf_slot_attention_forward": (C.c_int, [C.POINTER(SlotAttentionWeights), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                               C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uorf_probe_timing": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "uorf_probe_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 # entry points added after the first ABI cut; bound when present, listed in the header

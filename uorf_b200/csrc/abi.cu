@@ -25,6 +25,7 @@ int launch_slot_attention(const uorf_slot_attention_weights* w, const float* fea
                           const float* noise_fg, const float* noise_bg, int ntok, int C, int K, int hidden, int iters, float eps,
                           float* workspace, float* slots, float* attn, cudaStream_t stream);
 int launch_probe_gemm(const float* a, const float* b, int N, int ksteps, int passes, int f16, float* d, int* err_flag, cudaStream_t stream);
+int launch_probe_timing(long long* out, int reps, cudaStream_t stream);
 }  // namespace uorf
 
 namespace {
@@ -238,6 +239,13 @@ int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, i
     return fail(UORF_ERR_ARG, "uorf_probe_gemm: bad shape%s");
   return check_launch(uorf::launch_probe_gemm(a, b, N, ksteps, prec_passes(precision), prec_f16(precision), d, c->err_flag_dev, static_cast<cudaStream_t>(stream)),
                       "uorf_probe_gemm");
+}
+
+int uorf_probe_timing(int64_t* out, int32_t reps, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  if (!out || reps < 1) return fail(UORF_ERR_ARG, "uorf_probe_timing: bad arguments%s");
+  return check_launch(uorf::launch_probe_timing(reinterpret_cast<long long*>(out), reps, static_cast<cudaStream_t>(stream)), "uorf_probe_timing");
 }
 
 }  // extern "C"

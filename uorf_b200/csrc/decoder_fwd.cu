@@ -6,19 +6,18 @@
 //   ReLU density / tanh colour, density-weighted composition over the K slots.
 // No activation ever leaves the SM: the only HBM traffic is coords in, API-mandated outputs out.
 //
-// Structure: one persistent CTA per SM, 17 warps.
-//   warps 0-15  epilogue warps, grouped into NCH "channels"; a channel owns one 128-point tile at a time and
-//               walks it through bg MLP / the K-1 fg slots.  Thread <-> TMEM lane <-> point.
-//                 3-pass modes : NCH = 2 channels x 8 warps; the two warps sharing a lane quadrant split the
-//                                64 feature columns (TMEM: D 2x64 | H hi 32 | H lo 32 | P hi 24 | P lo 24 columns)
-//                 1-pass modes : NCH = 4 channels x 4 warps (TMEM: D 64 | H 32 | P 24 columns per channel)
-//   warp 16     MMA issuer: lane 0 polls the channels' mbarriers round-robin and issues tcgen05.mma for
-//               whichever channel has operands ready; it also owns TMEM alloc and the weight bulk copies.
+// Structure: one persistent CTA per SM, 16 epilogue warps + one MMA-issuer warp per channel.
+//   warps 0-15      epilogue warps, grouped into NCH "channels"; a channel owns one 128-point tile at a time and
+//                   walks it through bg MLP / the K-1 fg slots.  Thread <-> TMEM lane <-> point.
+//                     3-pass modes : NCH = 2 channels x 8 warps; the two warps sharing a lane quadrant split the
+//                                    64 feature columns (TMEM: D 64 | H hi 32 | H lo 32 | P hi 24 | P lo 24 columns)
+//                     1-pass modes : NCH = 4 channels x 4 warps (TMEM: D 64 | H 32 | P 24 columns per channel)
+//   warp 16 + c     MMA issuer of channel c (lane 0 issues tcgen05.mma); warp 16 also owns TMEM alloc and the weight
+//                   bulk copies.  One issuer per channel keeps the channels out of lock-step: while one channel is in
+//                   its epilogue the tensor pipe works for another.
 // Per layer:  A (activations, 16-bit hi [+lo]) lives in TMEM, written by the epilogue threads with tcgen05.st;
 //   B (weights) is a 128B-swizzled K-major tile in shared memory; D (fp32) in TMEM.
-//   The epilogue signals the issuer per K-step (16 feature columns) so the next layer's MMAs start while the
-//   rest of the tile is still in its bias + ReLU + split epilogue; MMA completion comes back through
-//   tcgen05.commit on the channel's d_full mbarrier.
+//   epilogue --a_full mbarrier--> issuer --tcgen05.commit / d_full mbarrier--> epilogue (bias + ReLU + split).
 // Precision: 1 pass of 16-bit operands, or 3 passes a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (fp32 accumulate);
 //   operands bf16 (range-safe, ~16 bits after the split) or fp16 (saturating, ~22 bits after the split).
 // The kernel makes two sweeps over its tiles: background MLP first (raw bg output parked in a 16 B/point
@@ -32,7 +31,6 @@ namespace uorf {
 
 constexpr int kTileM = 128;
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = (kEpiWarps + 1) * 32;  // 544
 constexpr int kTmemCols = 512;
 
 template <int PASSES>
@@ -40,17 +38,14 @@ struct Cfg {
   static constexpr int NCH = PASSES == 3 ? 2 : 4;       // channels
   static constexpr int CS = PASSES == 3 ? 2 : 1;        // threads per point (column split)
   static constexpr int WPC = 4 * CS;                    // warps per channel
+  static constexpr int THREADS = (kEpiWarps + NCH) * 32;
   static constexpr int CHAN_COLS = 512 / NCH;           // TMEM columns per channel
-  // With two threads per point the accumulator is double buffered (layer l in D[l & 1]): the first MMA of the next
-  // layer is released by the column half that finishes first, while the other half may still be reading D.
-  static constexpr bool DBUF = PASSES == 3;
   static constexpr int COL_D = 0;
-  static constexpr int COL_HHI = DBUF ? 128 : 64;
-  static constexpr int COL_HLO = 160;                   // 3-pass only
-  static constexpr int COL_PHI = DBUF ? 192 : 96;
-  static constexpr int COL_PLO = 224;                   // 3-pass only
+  static constexpr int COL_HHI = 64;
+  static constexpr int COL_HLO = 96;                    // 3-pass only
+  static constexpr int COL_PHI = PASSES == 3 ? 128 : 96;
+  static constexpr int COL_PLO = 160;                   // 3-pass only
   static constexpr int NPL = PASSES == 3 ? 2 : 1;       // weight planes
-  __device__ static constexpr int dcol(int stage) { return COL_D + (DBUF ? (stage & 1) * 64 : 0); }
 };
 
 struct DecFwdParams {
@@ -77,8 +72,7 @@ struct DecFwdParams {
 };
 
 struct ChanBars {
-  uint64_t a_pos;       // positional encoding written (all threads of the channel)
-  uint64_t a_chunk[4];  // H columns of K-step j written (the 128 threads owning those columns)
+  uint64_t a_full;      // A operand of the next layer written (all threads of the channel)
   uint64_t d_full;      // MMAs of the current layer complete (tcgen05.commit)
 };
 
@@ -134,12 +128,15 @@ __device__ __forceinline__ void posenc_store(const float (&v)[kPosencK], uint32_
   }
 }
 
-// one 16-column chunk: r (fp32 accumulators) + bias -> ReLU -> 16-bit hi[/lo] -> 8 H operand columns
+// 32 accumulator columns: D + bias -> ReLU -> 16-bit hi[/lo] -> 16 H operand columns
 template <int PASSES, bool F16>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const float* bias, uint32_t t_hhi, uint32_t t_hlo) {
-  uint32_t hi[8], lo[8];
+__device__ __forceinline__ void epilogue32(uint32_t t_d, const float* bias, uint32_t t_hhi, uint32_t t_hlo) {
+  uint32_t r[32];
+  tmem_ld32(t_d, r);
+  tc_wait_ld();
+  uint32_t hi[16], lo[16];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
     const float v0 = fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, 0.f);
     const float v1 = fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, 0.f);
@@ -153,9 +150,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t* r, const float* b
       hi[2 * q + 1] = pack2<F16>(v2, v3);
     }
   }
-  tmem_st8(t_hhi, hi);
-  if (PASSES == 3) tmem_st8(t_hlo, lo);
-  tc_wait_st();
+  tmem_st16(t_hhi, hi);
+  if (PASSES == 3) tmem_st16(t_hlo, lo);
 }
 
 // ---- issuer-side helper ---------------------------------------------------------------------------
@@ -165,18 +161,18 @@ __device__ __forceinline__ void issue_ksteps(uint32_t t_d, uint32_t t_ahi, uint3
                                              uint32_t idesc, bool& first) {
   const uint64_t dhi = make_sdesc_sw128(w_smem);
   for (int j = j0; j < j1; ++j) {
-    mma_ts(t_d, t_ahi + 8 * j, dhi + 2 * j, idesc, first ? 0u : 1u);
+    mma_ts_elect(t_d, t_ahi + 8 * j, dhi + 2 * j, idesc, first ? 0u : 1u);
     first = false;
   }
   if (PASSES == 3) {
     const uint64_t dlo = make_sdesc_sw128(w_smem + kPlaneBytes);
-    for (int j = j0; j < j1; ++j) mma_ts(t_d, t_alo + 8 * j, dhi + 2 * j, idesc, 1u);
-    for (int j = j0; j < j1; ++j) mma_ts(t_d, t_ahi + 8 * j, dlo + 2 * j, idesc, 1u);
+    for (int j = j0; j < j1; ++j) mma_ts_elect(t_d, t_alo + 8 * j, dhi + 2 * j, idesc, 1u);
+    for (int j = j0; j < j1; ++j) mma_ts_elect(t_d, t_ahi + 8 * j, dlo + 2 * j, idesc, 1u);
   }
 }
 
 template <int PASSES, bool F16>
-__global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdParams p) {
+__global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(const DecFwdParams p) {
   using C = Cfg<PASSES>;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_w;
@@ -196,8 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
     for (int c = 0; c < C::NCH; ++c) {
-      mbar_init(&bars[c].a_pos, kTileM * C::CS);
-      for (int j = 0; j < 4; ++j) mbar_init(&bars[c].a_chunk[j], kTileM);
+      mbar_init(&bars[c].a_full, kTileM * C::CS);
       mbar_init(&bars[c].d_full, 1);
     }
     fence_mbar_init();
@@ -221,10 +216,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
   }
 
   // completion counts of the barriers (parity = count & 1); the epilogue threads and the issuer keep their own copies
-  uint32_t n_d = 0;                                   // epilogue: d_full completions consumed by this thread
-  uint32_t i_pos[C::NCH], i_chunk[C::NCH];            // issuer: a_pos / a_chunk completions consumed per channel
-#pragma unroll
-  for (int c = 0; c < C::NCH; ++c) i_pos[c] = i_chunk[c] = 0;
+  uint32_t n_d = 0;   // epilogue: d_full completions consumed by this thread
+  uint32_t n_a = 0;   // issuer: a_full completions consumed
 
   for (int phase = 0; phase < 2; ++phase) {  // 0: background MLP, 1: foreground MLP + composition
     const int nslots = phase == 0 ? 1 : K - 1;
@@ -241,82 +234,45 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
     }
     mbar_wait(&bar_w, phase & 1, p.err_flag, 100 + phase);
 
-    if (warp == kEpiWarps) {
-      // =========================== MMA issuer (lane 0 polls all channels) ===========================
-      if (lane == 0) {
-        const uint32_t idesc64 = make_idesc_f32acc(128, 64, F16);
-        const uint32_t idesc_head = make_idesc_f32acc(128, phase == 0 ? 16 : 32, F16);
-        const uint32_t w_smem = smem_u32(smem);
-        // per-channel cursor: tile iteration, slot, stage (0..6), K-step chunk within the stage (0..3)
-        int c_it[C::NCH], c_slot[C::NCH], c_stage[C::NCH], c_chunk[C::NCH];
-        bool c_done[C::NCH];
-        int n_active = 0;
-#pragma unroll
-        for (int c = 0; c < C::NCH; ++c) {
-          c_it[c] = c_slot[c] = c_stage[c] = c_chunk[c] = 0;
-          c_done[c] = (long long)blockIdx.x + (long long)gridDim.x * c >= p.num_tiles;
-          n_active += c_done[c] ? 0 : 1;
-        }
-        long long t_last = clock64();
-        while (n_active > 0) {
-          bool progress = false;
-#pragma unroll
-          for (int c = 0; c < C::NCH; ++c) {
-            if (c_done[c]) continue;
-            const uint32_t tb = tmem_base + c * C::CHAN_COLS;
-            const int st = c_stage[c];
-            if (st == 0) {
-              if (!mbar_test_wait(&bars[c].a_pos, i_pos[c] & 1)) continue;
-              ++i_pos[c];
-              tc_fence_after();
+    if (warp >= kEpiWarps) {
+      // =========================== MMA issuer of channel (warp - 16) ===========================
+      // warp-uniform values are routed through a shuffle so the compiler keeps the MMA operands in uniform registers
+      // (otherwise every tcgen05.mma is wrapped in an elect / R2UR.BROADCAST waterfall loop)
+      const int c = __shfl_sync(0xffffffffu, warp - kEpiWarps, 0);
+      const uint32_t idesc64 = make_idesc_f32acc(128, 64, F16);
+      const uint32_t idesc_head = make_idesc_f32acc(128, phase == 0 ? 16 : 32, F16);
+      const uint32_t w_smem = smem_u32(smem);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base + c * C::CHAN_COLS, 0);
+      for (int it = 0;; ++it) {
+        const long long tile = (long long)blockIdx.x + (long long)gridDim.x * ((long long)it * C::NCH + c);
+        if (tile >= p.num_tiles) break;
+        for (int s = 0; s < nslots; ++s) {
+#pragma unroll 1
+          for (int st = 0; st < 7; ++st) {
+            mbar_wait(&bars[c].a_full, n_a & 1, p.err_flag, 200 + st);
+            ++n_a;
+            tc_fence_after();
+            {
               bool first = true;
-              issue_ksteps<PASSES>(tb + C::dcol(0), tb + C::COL_PHI, tb + C::COL_PLO, w_smem + 0 * kTileBytes, 0, 3, idesc64, first);
-              tc_commit(&bars[c].d_full);
-              c_stage[c] = 1;
-              c_chunk[c] = 0;
-            } else {
-              const int j = c_chunk[c];
-              if (!mbar_test_wait(&bars[c].a_chunk[j], i_chunk[c] & 1)) continue;
-              tc_fence_after();
-              bool first = (j == 0);
-              if (st == 3 && j == 0)  // skip connection: the positional-encoding half of after.0 needs no new operand
-                issue_ksteps<PASSES>(tb + C::dcol(3), tb + C::COL_PHI, tb + C::COL_PLO, w_smem + 3 * kTileBytes, 0, 3, idesc64, first);
-              const int tile_idx = st < 3 ? st : st + 1;  // stages 1,2 -> tiles 1,2 ; 3 -> 4 ; 4,5 -> 5,6 ; 6 -> 7
-              issue_ksteps<PASSES>(tb + C::dcol(st), tb + C::COL_HHI, tb + C::COL_HLO, w_smem + tile_idx * kTileBytes, j, j + 1,
-                                   st == 6 ? idesc_head : idesc64, first);
-              if (j == 3) {
-                tc_commit(&bars[c].d_full);
-                ++i_chunk[c];
-                c_chunk[c] = 0;
-                if (st == 6) {  // slot finished
-                  c_stage[c] = 0;
-                  if (++c_slot[c] == nslots) {
-                    c_slot[c] = 0;
-                    ++c_it[c];
-                    if ((long long)blockIdx.x + (long long)gridDim.x * ((long long)c_it[c] * C::NCH + c) >= p.num_tiles) {
-                      c_done[c] = true;
-                      --n_active;
-                    }
-                  }
-                } else {
-                  c_stage[c] = st + 1;
-                }
-              } else {
-                c_chunk[c] = j + 1;
+              const uint32_t t_d = tb + C::COL_D, t_p = tb + C::COL_PHI, t_pl = tb + C::COL_PLO, t_h = tb + C::COL_HHI, t_hl = tb + C::COL_HLO;
+              switch (st) {
+                case 0: issue_ksteps<PASSES>(t_d, t_p, t_pl, w_smem + 0 * kTileBytes, 0, 3, idesc64, first); break;
+                case 1: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 1 * kTileBytes, 0, 4, idesc64, first); break;
+                case 2: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 2 * kTileBytes, 0, 4, idesc64, first); break;
+                case 3:
+                  issue_ksteps<PASSES>(t_d, t_p, t_pl, w_smem + 3 * kTileBytes, 0, 3, idesc64, first);
+                  issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 4 * kTileBytes, 0, 4, idesc64, first);
+                  break;
+                case 4: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 5 * kTileBytes, 0, 4, idesc64, first); break;
+                case 5: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 6 * kTileBytes, 0, 4, idesc64, first); break;
+                default: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 7 * kTileBytes, 0, 4, idesc_head, first); break;
               }
+              tc_commit_elect(&bars[c].d_full);
             }
-            progress = true;
-          }
-          if (progress) {
-            t_last = clock64();
-          } else if (clock64() - t_last > 4000000000LL) {  // ~2 s without progress: protocol bug, do not hang the box
-            if (p.err_flag) atomicExch(p.err_flag, 200);
-            __threadfence_system();
-            __trap();
+            __syncwarp();
           }
         }
       }
-      __syncwarp();
     } else {
       // =========================== epilogue warps ===========================
       const int ch = warp / C::WPC;
@@ -365,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
             tc_wait_st();
           }
           tc_fence_before();
-          mbar_arrive(&cb.a_pos);
+          mbar_arrive(&cb.a_full);
 
           // ---- stages 1..6: hidden layers ----
           const float* sb = s_slotb + s * kSlotBiasFloats;
@@ -376,21 +332,14 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
             mbar_wait(&cb.d_full, n_d & 1, p.err_flag, 300 + st);
             ++n_d;
             tc_fence_after();
-            // pull every accumulator column this thread owns into registers first; the next layer's first
-            // (overwriting) MMA is released by chunk 0, so D must be either fully read by then (one thread per
-            // point arrives on chunk 0 only after this load) or double buffered (two threads per point)
-            uint32_t r[NCOL];
-            const uint32_t t_d = tb + C::dcol(st - 1) + col0;   // written by MMA stage st-1
-            tmem_ld32(t_d, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-            if (NCOL == 64) tmem_ld32(t_d + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[NCOL == 64 ? 32 : 0]));
-            tc_wait_ld();
 #pragma unroll
-            for (int jc = 0; jc < NCOL / 16; ++jc) {
-              const int j = half * (NCOL / 16) + jc;  // K-step index of the next layer
-              epilogue_chunk<PASSES, F16>(r + 16 * jc, bias + 16 * jc, tb + C::COL_HHI + 8 * j, tb + C::COL_HLO + 8 * j);
-              tc_fence_before();
-              mbar_arrive(&cb.a_chunk[j]);
+            for (int h32 = 0; h32 < NCOL / 32; ++h32) {
+              const int c32 = col0 + 32 * h32;   // first accumulator column of this 32-column block
+              epilogue32<PASSES, F16>(tb + C::COL_D + c32, bias + 32 * h32, tb + C::COL_HHI + c32 / 2, tb + C::COL_HLO + c32 / 2);
             }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&cb.a_full);
           }
           // ---- stage 7: heads (computed by the first column half; every thread consumes the barrier phase) ----
           mbar_wait(&cb.d_full, n_d & 1, p.err_flag, 307);
@@ -399,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
           if (half == 0) {
             if (phase == 0) {
               uint32_t r[16];
-              tmem_ld16(tb + C::dcol(6), r);
+              tmem_ld16(tb + C::COL_D, r);
               tc_wait_ld();
               const float* hb = s_params + kPHeadB;
               float4 o;
@@ -410,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_fwd_kernel(const DecFwdPa
               if (valid) p.scratch_bg[pt] = o;
             } else {
               uint32_t r[32];
-              tmem_ld32(tb + C::dcol(6), r);
+              tmem_ld32(tb + C::COL_D, r);
               tc_wait_ld();
               const float* hb = s_params + kPHeadB;
               const float* wc2 = s_params + kPWc2;
@@ -505,9 +454,10 @@ int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, c
   if (smem > 227 * 1024) return UORF_ERR_UNSUPPORTED;
   int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   if (grid < 1) return UORF_OK;
+  const int threads = passes == 3 ? Cfg<3>::THREADS : Cfg<1>::THREADS;
   auto launch = [&](auto kern) -> int {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UORF_ERR_DEVICE;
-    kern<<<grid, kThreads, smem, stream>>>(p);
+    kern<<<grid, threads, smem, stream>>>(p);
     return UORF_OK;
   };
   int rc;

@@ -95,3 +95,141 @@ int launch_probe_gemm(const float* a, const float* b, int N, int ksteps, int pas
 }
 
 }  // namespace uorf
+
+// ---------------------------------------------------------------------------------------------------
+// Latency probe (test/diagnostic hook): cycle counts of the building blocks of the decoder's handshake,
+// measured with clock64() on one SM.  out[0..] = see the labels in scripts/probe_timing.py.
+// ---------------------------------------------------------------------------------------------------
+namespace uorf {
+
+__global__ void __launch_bounds__(160, 1) probe_timing_kernel(long long* out, int reps) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar_a, bar_d;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_a, 128);
+    mbar_init(&bar_d, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  for (int e = threadIdx.x; e < 8 * kTileBytes / 4; e += blockDim.x) reinterpret_cast<uint32_t*>(smem)[e] = 0;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t idesc = make_idesc_f32acc(128, 64, true);
+  const uint64_t dhi = make_sdesc_sw128(smem_u32(smem));
+  uint32_t na = 0, nd = 0;
+  // ---- experiment A: 48 back-to-back MMAs (elect-issued, uniform operands) + commit; cycles until the commit lands ----
+  // variant v: 0: N=64 TS same D | 1: N=64 TS 2 rotating D | 2: N=64 TS 4 rotating D | 3: N=128 TS same D | 4: N=256 TS same D
+  //            5: N=64 SS same D | 6: N=64 SS 4 rotating D | 7: N=32 TS same D
+  if (warp == 4) {
+    const uint32_t tbu = __shfl_sync(0xffffffffu, tmem_base, 0);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const int N = v == 3 ? 128 : v == 4 ? 256 : v == 7 ? 32 : 64;
+      const int ND = v == 1 ? 2 : (v == 2 || v == 6) ? 4 : 1;
+      const bool ss = v == 5 || v == 6;
+      const uint32_t id = make_idesc_f32acc(128, N, true);
+      long long best = 1LL << 60, best_issue = 1LL << 60;
+      for (int r = 0; r < reps; ++r) {
+        const long long t0 = clock64();
+#pragma unroll
+        for (int j = 0; j < 48; ++j) {
+          const uint32_t d = tbu + (j % ND) * 64;
+          const uint32_t acc = j >= ND ? 1u : 0u;
+          if (ss) mma_ss_elect(d, dhi + 2 * (j & 3), dhi + 512 + 2 * (j & 3), id, acc);
+          else mma_ts_elect(d, tbu + 256 + 8 * (j & 3), dhi + 2 * (j & 3), id, acc);
+        }
+        tc_commit_elect(&bar_d);
+        const long long t1 = clock64();
+        mbar_wait(&bar_d, nd & 1);
+        ++nd;
+        const long long t2 = clock64();
+        best = min(best, t2 - t0);
+        best_issue = min(best_issue, t1 - t0);
+      }
+      if (lane == 0) { out[32 + v * 2] = best; out[32 + v * 2 + 1] = best_issue; }
+    }
+  }
+  __syncthreads();
+  // ---- experiment B: epilogue pieces on 4 warps ----
+  if (warp < 4) {
+    const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
+    long long b_ld = 1LL << 60, b_cmp = 1LL << 60, b_st = 1LL << 60, b_fence = 1LL << 60, b_all = 1LL << 60;
+    float bias = 0.01f * lane;
+    for (int r = 0; r < reps; ++r) {
+      const long long t0 = clock64();
+      uint32_t v[32], hi[16], lo[16];
+      tmem_ld32(tb, v);
+      tc_wait_ld();
+      const long long t1 = clock64();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float a = fmaxf(__uint_as_float(v[2 * q]) + bias, 0.f), b = fmaxf(__uint_as_float(v[2 * q + 1]) + bias, 0.f);
+        split2<true>(a, b, hi[q], lo[q]);
+      }
+      const long long t2 = clock64();
+      tmem_st16(tb + 64, hi);
+      tmem_st16(tb + 96, lo);
+      tc_wait_st();
+      const long long t3 = clock64();
+      tc_fence_before();
+      mbar_arrive(&bar_a);
+      const long long t4 = clock64();
+      b_ld = min(b_ld, t1 - t0); b_cmp = min(b_cmp, t2 - t1); b_st = min(b_st, t3 - t2); b_fence = min(b_fence, t4 - t3);
+      b_all = min(b_all, t4 - t0);
+      mbar_wait(&bar_a, na & 1);
+      ++na;
+    }
+    if (threadIdx.x == 0) { out[16] = b_ld; out[17] = b_cmp; out[18] = b_st; out[19] = b_fence; out[20] = b_all; }
+  }
+  __syncthreads();
+  // ---- experiment C: full round trip  epilogue arrive -> issuer wake -> 4 MMAs -> commit -> epilogue wake ----
+  {
+    long long best = 1LL << 60;
+    for (int r = 0; r < reps; ++r) {
+      if (warp < 4) {
+        const long long t0 = clock64();
+        tc_fence_before();
+        mbar_arrive(&bar_a);
+        mbar_wait(&bar_d, nd & 1);
+        tc_fence_after();
+        const long long t1 = clock64();
+        best = min(best, t1 - t0);
+      } else {
+        mbar_wait(&bar_a, na & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          for (int j = 0; j < 4; ++j) mma_ts(tmem_base, tmem_base + 64 + 8 * j, dhi + 2 * j, idesc, j ? 1u : 0u);
+          tc_commit(&bar_d);
+        }
+        __syncwarp();
+      }
+      ++na;
+      ++nd;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[24] = best;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+int launch_probe_timing(long long* out, int reps, cudaStream_t stream) {
+  const int smem = 1024 + 8 * kTileBytes;
+  cudaFuncSetAttribute(probe_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  probe_timing_kernel<<<1, 160, smem, stream>>>(out, reps);
+  return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
+}
+
+}  // namespace uorf
