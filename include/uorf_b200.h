@@ -127,6 +127,49 @@ typedef struct uorf_decoder_args {
 int uorf_decoder_forward(const uorf_decoder_args* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Kernel 5 (decoder part) — backward of Decoder.forward w.r.t. every decoder weight and z_slots, given dL/d raws.
+ * Replaces torch.autograd through models/model.py:106-161 as exercised by uorfNoGanModel.backward
+ * (models/uorf_nogan_model.py:223-227; only `raws` carries gradient, masked/unmasked/masks are detached :185-196).
+ * Activations are recomputed per tile on chip (fp16 activations/weights, bf16 activation gradients, fp32 accumulation); nothing is stored by
+ * the forward pass except its `unmasked_raws` output.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct uorf_decoder_grads {   /* same fields / shapes as uorf_decoder_weights, written by the call */
+  float *f_before_w[3], *f_before_b[3];
+  float *f_after_w[3], *f_after_b[3];
+  float *f_after_latent_w, *f_after_latent_b;
+  float *f_after_shape_w, *f_after_shape_b;
+  float *f_color0_w, *f_color0_b;
+  float *f_color2_w, *f_color2_b;
+  float *b_before_w[3], *b_before_b[3];
+  float *b_after_w[4], *b_after_b[4];
+} uorf_decoder_grads;
+
+typedef struct uorf_decoder_bwd_args {
+  const float* coor_bg;       /* as in uorf_decoder_args */
+  const float* coor_fg;
+  int64_t fg_slot_stride;
+  const float* fg_transform;
+  const float* noise;         /* the noise tensor the forward used, or NULL */
+  float dens_noise;
+  float locality_ratio;
+  int32_t locality;
+  int32_t fixed_locality;
+  int64_t P;
+  int32_t K;
+  int32_t Z;
+  const float* z_slots;       /* [K][Z] */
+  const void* image;          /* uorf_decoder_prepare(..., UORF_PREC_FP16, ...) of the same weights / slots */
+  const float* unmasked_raws; /* [K][P][4] forward output */
+  const float* grad_raws;     /* [P][4] */
+  float* workspace;           /* uorf_decoder_backward_workspace_floats(P, K) floats */
+  float* grad_z_slots;        /* [K][Z] out */
+} uorf_decoder_bwd_args;
+
+size_t uorf_decoder_backward_workspace_floats(int64_t P, int32_t K);
+int uorf_decoder_backward(const uorf_decoder_weights* w, const uorf_decoder_grads* g, const uorf_decoder_bwd_args* a,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Kernel 3 — alpha compositing.  Replaces raw2outputs (models/model.py:279-313).
  *   raw [R][D][4] (rgb, sigma), z_vals [geom_rays][D], rays_d [geom_rays][3]
  *   rgb_map [R][3], depth_map [R], weights_norm [R][D] (may be NULL), mask_map [R] (NULL unless render_mask)
@@ -175,6 +218,9 @@ int uorf_slot_attention_forward(const uorf_slot_attention_weights* w, const floa
  * ------------------------------------------------------------------------------------------- */
 int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, int32_t precision, float* d,
                     void* stream);
+/* Test hook for the weight-gradient data path: d1 = a^T b1, d2 = a^T b2 with a, b [128][64] (points x features, rounded to
+ * bf16), d [64][64]; both operands are read through MN-major shared-memory descriptors, M = 64, two accumulators interleaved. */
+int uorf_probe_gemm_tn(const float* a, const float* b1, const float* b2, float* d1, float* d2, void* stream);
 /* Diagnostic hook: SM-cycle counts of the decoder's handshake building blocks (out: 256 int64, device). */
 int uorf_probe_timing(int64_t* out, int32_t reps, void* stream);
 /* Test hook: site code written by a kernel whose mbarrier wait timed out (0 = none). */

@@ -1,8 +1,8 @@
 # quick GPU visit: parity tests + bench in the given precisions (no profiler)
 mkdir -p gpurun_out; rm -f gpurun_out/*.log
-for grp in probe composite sample_coords slot_attention decoder_golden decoder_vs_oracle eval_driver $EXTRA_GROUPS; do
+for grp in ${TEST_GROUPS:-probe composite sample_coords slot_attention decoder_golden decoder_vs_oracle eval_driver}; do
   echo "=== $grp" >> gpurun_out/tests.log
-  timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -s --timeout 240 -k "$grp" 2>&1 | tail -45 >> gpurun_out/tests.log
+  timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -s --timeout 240 -k "$grp" 2>&1 | tail -${TAILN:-45} >> gpurun_out/tests.log
 done
 python -c "
 from uorf_b200 import _lib

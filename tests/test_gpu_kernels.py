@@ -303,3 +303,80 @@ def test_eval_driver_golden(layout):
     agree = (m.mask_idx_pred.cpu() == g["mask_idx"]).float().mean().item()
     assert agree > 0.99, agree
     assert hasattr(m, "slot3_view1") and m.slot3_view1.shape == (3, 16, 16)
+
+
+# ------------------------------------------------------------------------------------------------------
+# kernel 5: decoder backward (fp16 tensor-core operands, fp32 accumulation, activations recomputed on chip) against fp32
+# autograd through the oracle / the reference's golden gradients
+# ------------------------------------------------------------------------------------------------------
+# Stated tolerances, as max |grad - ref| / max |ref| per tensor:
+#   COHERENT loss (every point pulls the same way, like a real reconstruction loss): 5e-3.
+#   RANDOM-SIGN probe loss (the golden vectors): every weight gradient is then a random-walk sum over the points, and the
+#   handful of ReLU gates that flip because the recomputed fp16 pre-activation differs from the fp32 one in the last bits
+#   change it by ~sqrt(flip fraction) - a property of the probe, not of the kernel.  Bound: 0.15.
+GRAD_TOL_COHERENT = 5e-3
+GRAD_TOL_RANDOM = 0.15
+
+
+def check_grads(got, ref, tag, tol):
+    worst = {}
+    for k, v in ref.items():
+        scale = max(v.abs().max().item(), 1e-30)
+        worst[k] = (got[k].detach().cpu() - v).abs().max().item() / scale
+    print(tag, {k: f"{e:.1e}" for k, e in worst.items()})
+    bad = {k: e for k, e in worst.items() if not e < tol}
+    assert not bad, f"{tag}: {bad} exceed {tol}"
+
+
+@pytest.mark.parametrize("Z", [64, 40])
+def test_decoder_grads_golden(Z):
+    g = load_golden(f"decoder_z{Z}_fixed0")
+    dec = _load_decoder(g, Z, 0, "fp16x3")
+    dec.return_outside = False
+    zs = g["z_slots"].to(dev()).requires_grad_(True)
+    raws, *_ = dec(g["coor_bg"].to(dev()), g["coor_fg"].to(dev()), zs, g["fg_transform"].to(dev()), dens_noise=0.)
+    assert maxerr(raws, g["raws_nonoise"]) < 2e-4
+    (raws * g["probe"].to(dev())).sum().backward()
+    got = {k: p.grad for k, p in dec.named_parameters()}
+    got["z_slots"] = zs.grad
+    ref = dict(g["grad"])
+    ref["z_slots"] = g["grad_z_slots"]
+    check_grads(got, ref, f"decoder grads golden z{Z}", GRAD_TOL_RANDOM)
+
+
+@pytest.mark.parametrize("K,P,Z,fixed,dens_noise,coherent", [(5, 128 * 148 + 55, 64, 0, 0.0, True), (8, 9000, 40, 1, 0.5, True),
+                                                              (16, 3000, 64, 0, 0.0, True), (2, 1, 64, 0, 0.0, True),
+                                                              (5, 128 * 148 + 55, 64, 0, 0.0, False)])
+def test_decoder_grads_vs_oracle(K, P, Z, fixed, dens_noise, coherent):
+    from uorf_b200.modules import Decoder
+    gen = torch.Generator().manual_seed(K * 11 + P)
+    params = O.init_decoder_params(Z, seed=K + 1)
+    for k in params:
+        if k.endswith("bias"):
+            params[k] = torch.randn(params[k].shape, generator=gen) * 0.1
+    params["b_after.6.bias"][3] = 0.5        # the background has density, as in any trained scene
+    cb = (torch.rand(P, 3, generator=gen) * 2 - 1) * 1.5
+    zs = torch.randn(K, Z, generator=gen)
+    noise = torch.randn(K, P, 1, generator=gen)
+    probe = torch.tensor([0.3, -0.2, 0.5, 0.1]).expand(P, 4).contiguous() if coherent else torch.randn(P, 4, generator=gen)
+    c2w, azi = O.lookat_cameras(1)
+    T = (c2w if fixed else azi)[0:1].inverse()
+    ratio = 4.5 / 7
+    # oracle gradients (fp32 autograd on the CPU)
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    zs_ref = zs.clone().requires_grad_(True)
+    r_o, *_ = O.decoder_forward(p_ref, cb, cb[None].expand(K - 1, -1, -1), zs_ref, T, locality=True, locality_ratio=ratio,
+                                fixed_locality=bool(fixed), dens_noise=dens_noise, noise=noise)
+    (r_o * probe).sum().backward()
+    dec = Decoder(n_freq=5, input_dim=33 + Z, z_dim=Z, n_layers=3, locality=True, locality_ratio=ratio,
+                  fixed_locality=bool(fixed)).to(dev())
+    dec.load_state_dict(params)
+    zs_g = zs.to(dev()).requires_grad_(True)
+    cbd = cb.to(dev())
+    raws, *_ = dec(cbd, cbd[None].expand(K - 1, -1, -1), zs_g, T.to(dev()), dens_noise=dens_noise, noise=noise.to(dev()))
+    (raws * probe.to(dev())).sum().backward()
+    got = {k: p.grad for k, p in dec.named_parameters()}
+    got["z_slots"] = zs_g.grad
+    ref = {k: v.grad for k, v in p_ref.items()}
+    ref["z_slots"] = zs_ref.grad
+    check_grads(got, ref, f"decoder grads K{K} P{P} Z{Z} coherent={coherent}", GRAD_TOL_COHERENT if coherent else GRAD_TOL_RANDOM)

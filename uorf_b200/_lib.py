@@ -56,9 +56,8 @@ class DecoderBwdArgs(C.Structure):
                 ("dens_noise", C.c_float), ("locality_ratio", C.c_float),
                 ("locality", C.c_int32), ("fixed_locality", C.c_int32),
                 ("P", C.c_int64), ("K", C.c_int32), ("Z", C.c_int32),
-                ("z_slots", C.c_void_p), ("grad_raws", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_floats", C.c_int64),
-                ("grad_weights", C.c_void_p), ("grad_z_slots", C.c_void_p)]
+                ("z_slots", C.c_void_p), ("image", C.c_void_p), ("unmasked_raws", C.c_void_p), ("grad_raws", C.c_void_p),
+                ("workspace", C.c_void_p), ("grad_z_slots", C.c_void_p)]
 
 
 _SA_FIELDS = ["slots_mu", "slots_logsigma", "slots_mu_bg", "slots_logsigma_bg",
@@ -101,6 +100,8 @@ _SIGNATURES = {
     "uorf_decoder_prepare": (C.c_int, [C.POINTER(DecoderWeights), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_void_p]),
     "uorf_decoder_forward": (C.c_int, [C.POINTER(DecoderArgs), C.c_void_p]),
+    "uorf_decoder_backward_workspace_floats": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "uorf_decoder_backward": (C.c_int, [C.POINTER(DecoderWeights), C.POINTER(DecoderWeights), C.POINTER(DecoderBwdArgs), C.c_void_p]),
     "uorf_composite_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "uorf_composite_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
@@ -109,15 +110,11 @@ _SIGNATURES = {
     "uorf_slot_attention_forward": (C.c_int, [C.POINTER(SlotAttentionWeights), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                               C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uorf_probe_gemm_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uorf_probe_timing": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "uorf_probe_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
-# entry points added after the first ABI cut; bound when present, listed in the header
-_OPTIONAL = {
-    "uorf_decoder_backward_workspace_floats": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
-    "uorf_decoder_grad_floats": (C.c_size_t, [C.c_int32]),
-    "uorf_decoder_backward": (C.c_int, [C.POINTER(DecoderWeights), C.POINTER(DecoderBwdArgs), C.c_void_p]),
-}
+_OPTIONAL = {}
 
 _lib = None
 _lock = threading.Lock()

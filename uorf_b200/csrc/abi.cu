@@ -26,6 +26,10 @@ int launch_slot_attention(const uorf_slot_attention_weights* w, const float* fea
                           float* workspace, float* slots, float* attn, cudaStream_t stream);
 int launch_probe_gemm(const float* a, const float* b, int N, int ksteps, int passes, int f16, float* d, int* err_flag, cudaStream_t stream);
 int launch_probe_timing(long long* out, int reps, cudaStream_t stream);
+size_t decoder_bwd_workspace_floats(long long P, int K, int num_sms);
+int launch_decoder_bwd(const uorf_decoder_weights* w, const uorf_decoder_grads* g, const uorf_decoder_bwd_args* a, int num_sms,
+                       int* err_flag, cudaStream_t stream);
+int launch_probe_gemm_tn(const float* a, const float* b1, const float* b2, float* d1, float* d2, int* err_flag, cudaStream_t stream);
 }  // namespace uorf
 
 namespace {
@@ -182,6 +186,29 @@ int uorf_decoder_forward(const uorf_decoder_args* a, void* stream) {
                       "uorf_decoder_forward");
 }
 
+size_t uorf_decoder_backward_workspace_floats(int64_t P, int32_t K) {
+  DeviceCtx* c = ctx();
+  if (!c || P < 0 || K < 2) return 0;
+  return uorf::decoder_bwd_workspace_floats(P, K, c->num_sms);
+}
+
+int uorf_decoder_backward(const uorf_decoder_weights* w, const uorf_decoder_grads* g, const uorf_decoder_bwd_args* a, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  if (!w || !g || !a || !a->coor_bg || !a->coor_fg || !a->fg_transform || !a->image || !a->workspace || !a->unmasked_raws ||
+      !a->grad_raws || !a->z_slots || !a->grad_z_slots)
+    return fail(UORF_ERR_ARG, "uorf_decoder_backward: null pointer%s");
+  if (a->K < 2 || a->K > 16) return fail(UORF_ERR_UNSUPPORTED, "uorf_decoder_backward: K must be in [2,16]%s");
+  if (a->Z < 4 || a->Z > uorf::kZPad || (a->Z % 4) != 0) return fail(UORF_ERR_UNSUPPORTED, "uorf_decoder_backward: bad z_dim%s");
+  if (a->P <= 0) return fail(UORF_ERR_ARG, "uorf_decoder_backward: bad P%s");
+  if (a->dens_noise != 0.f && !a->noise) return fail(UORF_ERR_ARG, "uorf_decoder_backward: dens_noise != 0 needs the noise tensor%s");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a->workspace) | reinterpret_cast<uintptr_t>(a->unmasked_raws) |
+                       reinterpret_cast<uintptr_t>(a->grad_raws) | reinterpret_cast<uintptr_t>(a->image);
+  if (al & 15) return fail(UORF_ERR_ARG, "uorf_decoder_backward: buffers must be 16-byte aligned%s");
+  return check_launch(uorf::launch_decoder_bwd(w, g, a, c->num_sms, c->err_flag_dev, static_cast<cudaStream_t>(stream)),
+                      "uorf_decoder_backward");
+}
+
 int uorf_composite_forward(const float* raw, const float* z_vals, const float* rays_d, int64_t R, int64_t geom_rays, int32_t D, float* rgb_map,
                            float* depth_map, float* weights_norm, float* mask_map, void* stream) {
   DeviceCtx* c = ctx();
@@ -239,6 +266,13 @@ int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, i
     return fail(UORF_ERR_ARG, "uorf_probe_gemm: bad shape%s");
   return check_launch(uorf::launch_probe_gemm(a, b, N, ksteps, prec_passes(precision), prec_f16(precision), d, c->err_flag_dev, static_cast<cudaStream_t>(stream)),
                       "uorf_probe_gemm");
+}
+
+int uorf_probe_gemm_tn(const float* a, const float* b1, const float* b2, float* d1, float* d2, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  if (!a || !b1 || !b2 || !d1 || !d2) return fail(UORF_ERR_ARG, "uorf_probe_gemm_tn: null pointer%s");
+  return check_launch(uorf::launch_probe_gemm_tn(a, b1, b2, d1, d2, c->err_flag_dev, static_cast<cudaStream_t>(stream)), "uorf_probe_gemm_tn");
 }
 
 int uorf_probe_timing(int64_t* out, int32_t reps, void* stream) {

@@ -1,0 +1,706 @@
+// Kernel 5 (decoder part) — fused K-slot decoder BACKWARD on tcgen05 / TMEM.
+//
+// Gradient of Decoder.forward (reference models/model.py:106-161) w.r.t. every decoder weight and z_slots, given
+// dL/d raws (Px4).  The reference's drivers only differentiate through `raws` (masked/unmasked/masks are detached,
+// models/uorf_nogan_model.py:172-196).
+//
+// Per 128-point tile and slot the kernel recomputes the forward activations (they are never stored in HBM), keeps
+// them as fp16 [point][feature] tiles in shared memory, and walks the MLP backwards:
+//     dZ_l = dX_{l+1} * [X_{l+1} > 0]                       (epilogue threads, thread <-> point)
+//     dX_l = dZ_l . W_l                                      tcgen05.mma  M=128  A = dZ tile (K-major),  B = W tile (MN-major view)
+//     dW_l += dZ_l^T . X_l   (contraction over the points)   tcgen05.mma  M=64   A = dZ tile (MN-major), B = X tile (MN-major)
+// The SAME shared-memory tile serves as K-major and as MN-major operand (rows of 128 B, 128B swizzle), so no transpose
+// is ever materialised.  The eight dW accumulators (fp32) stay resident in TMEM for the whole kernel, two per 64 columns
+// (M=64 accumulators use 16 of every 32 lanes; the partner sits at lane offset 16).  Bias gradients are reduced with a
+// shuffle reduce-scatter; the per-slot column sums that carry d z_slots ride on spare positional-encoding columns
+// (a one-hot slot indicator in columns 33..47 of the P tile).  Tensor-core operands are fp16 (11-bit significand) with
+// fp32 accumulation; activation gradients are kept in range by a global power-of-two scale taken from max |d raw|, which a
+// small elementwise pre-kernel (the backward of the slot composition) produces together with d raw itself.
+//
+// Outputs are per-CTA partial sums; decoder_bwd_finalize reduces them in a fixed order (deterministic) and unfolds the
+// folded head (f_color.0 . f_after_latent) and the hoisted slot-latent columns into the reference's parameter shapes.
+#include "common.cuh"
+#include "decoder_layout.h"
+#include "../../include/uorf_b200.h"
+
+namespace uorf {
+
+constexpr int kTileM128 = 128;
+constexpr int kBwdThreads = 160;  // 4 epilogue warps + 1 MMA-issuer warp
+constexpr int kAccFloats = 64 * 64;
+// accumulators: 0: before.0 (x P)  1: before.2  2: before.4  3: after.0 (x P)  4: after.0 (x tmp)  5: after.2  6: after.4  7: head
+constexpr int kNumAcc = 8;
+// per-CTA partial record (floats): 8 accumulators, bias sums [7][64] (layers 1,2,4,5 -> rows 0..3, head -> row 4), f_color.2 (48 + 3)
+constexpr int kPartBias = kNumAcc * kAccFloats;
+constexpr int kPartWc2 = kPartBias + 5 * 64;
+constexpr int kPartFloats = kPartWc2 + 64;
+
+struct DecBwdParams {
+  const float* coor_bg;
+  const float* coor_fg;
+  long long fg_slot_stride;
+  const float* noise;
+  const float4* unmasked;   // [K][P] forward output (rgb in [0,1], sigma)
+  const float4* grad_raws;  // [P]
+  const unsigned char* image;  // fp16 1-pass image of uorf_decoder_prepare
+  float4* scratch_draw;     // [K][P] d raw (rgb_raw x3, sigma_raw), written by the composition-backward pre-kernel
+  const float* draw_amax;   // max |d raw| (device scalar, bit pattern written with atomicMax)
+  float* partials;          // [2 phases][grid][kPartFloats]
+  const float* fg_transform;
+  float locality_ratio;
+  float dens_noise;
+  long long P;
+  int K;
+  int fixed_locality;
+  int locality;
+  int num_tiles;
+  int* err_flag;
+};
+
+// TMEM columns
+constexpr int kBColD = 0;
+__device__ __forceinline__ uint32_t acc_taddr(uint32_t base, int acc) {
+  // pairs share columns: (0,3) 48 cols @64 ; (1,2) @112 ; (4,5) @176 ; (6,7) @240 ; second of each pair at lane 16
+  const int col = acc == 0 || acc == 3 ? 64 : acc == 1 || acc == 2 ? 112 : acc == 4 || acc == 5 ? 176 : 240;
+  const int hi = (acc == 3 || acc == 2 || acc == 5 || acc == 7) ? 16 : 0;
+  return base + col + ((uint32_t)hi << 16);
+}
+
+// MN-major view of a [rows][64 x bf16] swizzled tile (rows = contraction index)
+__device__ __forceinline__ uint64_t sdesc_mn(uint32_t smem_addr) {
+  return (static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4)) | (static_cast<uint64_t>(1024) << 16) |
+         (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+}
+// fp16 x fp16 -> fp32 (tcgen05 rejects mixed fp16 / bf16 operands).  Activation gradients are made fp16-safe by a global
+// power-of-two loss scale derived from max |d raw| (see grad_scale()).
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+// power of two that maps max |d raw| into (512, 1024]
+__device__ __forceinline__ float grad_scale(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);   // amax = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.f, 10 - e);
+}
+
+// write one 64-feature row (fp32 regs v[64]) as 16-bit values (F16: fp16, else bf16) into row `t` of a swizzled tile
+template <bool F16>
+__device__ __forceinline__ void store_row16(unsigned char* tile, int t, const float (&v)[64]) {
+  unsigned char* row = tile + (t >> 3) * 1024 + (t & 7) * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 q;
+    q.x = pack2<F16>(v[8 * c + 0], v[8 * c + 1]);
+    q.y = pack2<F16>(v[8 * c + 2], v[8 * c + 3]);
+    q.z = pack2<F16>(v[8 * c + 4], v[8 * c + 5]);
+    q.w = pack2<F16>(v[8 * c + 6], v[8 * c + 7]);
+    *reinterpret_cast<uint4*>(row + (((c ^ (t & 7)) & 7) << 4)) = q;
+  }
+}
+// ReLU gate: multiply g[i] by [x_i > 0] where x is the 16-bit row `t` of a swizzled tile (bf16 and fp16 both keep
+// their magnitude in the low 15 bits)
+__device__ __forceinline__ void gate_by_row(const unsigned char* tile, int t, float (&g)[64]) {
+  const unsigned char* row = tile + (t >> 3) * 1024 + (t & 7) * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 q = *reinterpret_cast<const uint4*>(row + (((c ^ (t & 7)) & 7) << 4));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // positive <=> magnitude bits non-zero (activations are ReLU outputs: never negative)
+      if ((w[i] & 0x7FFFu) == 0) g[8 * c + 2 * i] = 0.f;
+      if ((w[i] & 0x7FFF0000u) == 0) g[8 * c + 2 * i + 1] = 0.f;
+    }
+  }
+}
+// column sums over the 32 lanes of a warp of v[0..63] (reduce-scatter butterfly: lane l ends with features 2l, 2l+1),
+// accumulated into dst[64] (shared memory) with one atomic pair per lane
+__device__ __forceinline__ void warp_colsum_add(const float (&v)[64], float* dst, int lane) {
+  float a[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {  // step 1: lanes with bit 4 set keep the upper half
+    const bool up = lane & 16;
+    const float keep = up ? v[32 + i] : v[i];
+    const float send = up ? v[i] : v[32 + i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 8;
+    const float keep = up ? a[16 + i] : a[i];
+    const float send = up ? a[i] : a[16 + i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 4;
+    const float keep = up ? a[8 + i] : a[i];
+    const float send = up ? a[i] : a[8 + i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 2;
+    const float keep = up ? a[4 + i] : a[i];
+    const float send = up ? a[i] : a[4 + i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 1;
+    const float keep = up ? a[2 + i] : a[i];
+    const float send = up ? a[i] : a[2 + i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  // lane bits (16,8,4,2,1) selected halves in that order: feature index = 32*b4 + 16*b3 + 8*b2 + 4*b1 + 2*b0 + i
+  const int f0 = ((lane & 16) ? 32 : 0) + ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
+  atomicAdd(dst + f0, a[0]);
+  atomicAdd(dst + f0 + 1, a[1]);
+}
+
+__device__ __forceinline__ void load_d64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  tc_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  tmem_ld32(taddr + 32, r);
+  tc_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBwdParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_d;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_db[5][64];   // bias-gradient sums: layers 1, 2, 4, 5, head
+  __shared__ float s_red[4][64];
+
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = p.K;
+  // shared-memory map: [weights plane 61440][params + slot biases -> padded to 1024][X tiles 7 x 16384][dZ 2 x 16384]
+  const int w_region = kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
+  const int x_off = (w_region + 1023) & ~1023;
+  unsigned char* s_x = smem + x_off;               // tile i: P (i=0), X1..X6
+  unsigned char* s_dz = s_x + 7 * 16384;           // two buffers
+  const float* s_params = reinterpret_cast<const float*>(smem + kPlaneBytes);
+  const float* s_slotb = s_params + kParamFloats;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_w, 1);
+    mbar_init(&bar_a, kTileM128);
+    mbar_init(&bar_d, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  float T[12];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      T[r * 4 + c] = p.fixed_locality ? __ldg(p.fg_transform + r * 4 + c) : (c < 3 ? __ldg(p.fg_transform + r * 3 + c) : 0.f);
+  }
+
+  const float gscale = grad_scale(__ldg(p.draw_amax));
+  uint32_t n_a = 0, n_d = 0;
+  for (int phase = 0; phase < 2; ++phase) {
+    const int nslots = phase == 0 ? 1 : K - 1;
+    if (warp == 4 && lane == 0) {
+      fence_proxy_async_smem();
+      const unsigned char* src = p.image + (phase ? blob_fg_offset(1) : 0);
+      const uint32_t bytes = (uint32_t)blob_bytes_one(1, nslots);
+      mbar_arrive_expect_tx(&bar_w, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768u) {
+        const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+        bulk_g2s(smem + off, src + off, n, &bar_w);
+      }
+    }
+    for (int e = threadIdx.x; e < 5 * 64; e += blockDim.x) (&s_db[0][0])[e] = 0.f;
+    mbar_wait(&bar_w, phase & 1, p.err_flag, 100 + phase);
+    __syncthreads();
+
+    float wc2_acc[51];  // f_color.2 weight (3x16) + bias (3) gradient, per thread
+#pragma unroll
+    for (int i = 0; i < 51; ++i) wc2_acc[i] = 0.f;
+
+    if (warp == 4) {
+      // =========================== MMA issuer ===========================
+      const uint32_t tbu = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t w_s = smem_u32(smem);
+      const uint32_t x_s = smem_u32(s_x);
+      const uint32_t dz_s = smem_u32(s_dz);
+      const uint32_t id_fwd64 = idesc_f16(128, 64, false, false);          // X . W^T
+      const uint32_t id_fwd_head = idesc_f16(128, phase == 0 ? 16 : 32, false, false);
+      const uint32_t id_dx = idesc_f16(128, 64, false, true);              // dZ . W
+      const uint32_t id_dw64 = idesc_f16(64, 64, true, true);              // dZ^T . X
+      const uint32_t id_dw48 = idesc_f16(64, 48, true, true);
+      uint32_t acc_live = 0;  // bit a set once accumulator a holds data
+      auto wait_a = [&](int site) {
+        mbar_wait(&bar_a, n_a & 1, p.err_flag, site);
+        ++n_a;
+        tc_fence_after();
+      };
+      // forward GEMM, both operands K-major: D (+)= X[tile xi] . W[tile wi]^T
+      auto fwd = [&](int xi, int wi, int ksteps, uint32_t idesc, bool first) {
+        const uint64_t da = make_sdesc_sw128(x_s + xi * 16384), db = make_sdesc_sw128(w_s + wi * kTileBytes);
+        for (int j = 0; j < ksteps; ++j) mma_ss_elect(tbu + kBColD, da + 2 * j, db + 2 * j, idesc, (first && j == 0) ? 0u : 1u);
+      };
+      // dX = dZ[buf] . W[tile wi] : A K-major (K = out features), B = MN-major view of the weight tile
+      auto dx = [&](int buf, int wi, int ksteps) {
+        const uint64_t da = make_sdesc_sw128(dz_s + buf * 16384), db = sdesc_mn(w_s + wi * kTileBytes);
+        for (int j = 0; j < ksteps; ++j) mma_ss_elect(tbu + kBColD, da + 2 * j, db + 128 * j, id_dx, j ? 1u : 0u);
+      };
+      // dW[acc] += dZ[buf]^T . X[tile xi] : both MN-major views, contraction over the 128 points (8 K-steps)
+      auto dw = [&](int acc, int buf, int xi, uint32_t idesc) {
+        const uint64_t da = sdesc_mn(dz_s + buf * 16384), db = sdesc_mn(x_s + xi * 16384);
+        const uint32_t t_acc = acc_taddr(tbu, acc);
+        const bool live = (acc_live >> acc) & 1u;
+        for (int j = 0; j < 8; ++j) mma_ss_elect(t_acc, da + 128 * j, db + 128 * j, idesc, (live || j) ? 1u : 0u);
+        acc_live |= 1u << acc;
+      };
+      for (int it = 0;; ++it) {
+        const long long tile = (long long)blockIdx.x + (long long)gridDim.x * it;
+        if (tile >= p.num_tiles) break;
+        for (int s = 0; s < nslots; ++s) {
+          // ---- forward recompute ----
+          wait_a(200); fwd(0, 0, 3, id_fwd64, true); tc_commit_elect(&bar_d);
+          wait_a(201); fwd(1, 1, 4, id_fwd64, true); tc_commit_elect(&bar_d);
+          wait_a(202); fwd(2, 2, 4, id_fwd64, true); tc_commit_elect(&bar_d);
+          wait_a(203); fwd(0, 3, 3, id_fwd64, true); fwd(3, 4, 4, id_fwd64, false); tc_commit_elect(&bar_d);
+          wait_a(204); fwd(4, 5, 4, id_fwd64, true); tc_commit_elect(&bar_d);
+          wait_a(205); fwd(5, 6, 4, id_fwd64, true); tc_commit_elect(&bar_d);
+          wait_a(206); fwd(6, 7, 4, id_fwd_head, true); tc_commit_elect(&bar_d);
+          // ---- backward ----   (dZ buffers alternate: head -> 0, layer 5 -> 1, 4 -> 0, 3 -> 1, 2 -> 0, 1 -> 1, 0 -> 0)
+          wait_a(207); dx(0, 7, 2); tc_commit_elect(&bar_d); dw(7, 0, 6, id_dw64);
+          wait_a(208); dx(1, 6, 4); tc_commit_elect(&bar_d); dw(6, 1, 5, id_dw64);
+          wait_a(209); dx(0, 5, 4); tc_commit_elect(&bar_d); dw(5, 0, 4, id_dw64);
+          wait_a(210); dx(1, 4, 4); tc_commit_elect(&bar_d); dw(4, 1, 3, id_dw64); dw(3, 1, 0, id_dw48);
+          wait_a(211); dx(0, 2, 4); tc_commit_elect(&bar_d); dw(2, 0, 2, id_dw64);
+          wait_a(212); dx(1, 1, 4); tc_commit_elect(&bar_d); dw(1, 1, 1, id_dw64);
+          wait_a(213); dw(0, 0, 0, id_dw48); tc_commit_elect(&bar_d);   // all tiles free for the next slot once this lands
+        }
+      }
+      __syncwarp();
+    } else {
+      // =========================== epilogue warps (thread <-> point) ===========================
+      const int t = threadIdx.x;  // 0..127
+      const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
+      auto wait_d = [&](int site) {
+        mbar_wait(&bar_d, n_d & 1, p.err_flag, site);
+        ++n_d;
+        tc_fence_after();
+      };
+      auto publish = [&]() {  // make this thread's shared-memory tile writes visible to the tensor core, then signal
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&bar_a);
+      };
+      for (int it = 0;; ++it) {
+        const long long tile = (long long)blockIdx.x + (long long)gridDim.x * it;
+        if (tile >= p.num_tiles) break;
+        const long long pt = tile * kTileM128 + t;
+        const bool valid = pt < p.P;
+        for (int s = 0; s < nslots; ++s) {
+          const int kslot = phase == 0 ? 0 : s + 1;
+          // ---- stage 0: coordinates -> positional encoding tile (column 33 + s carries the per-slot column sums) ----
+          float x = 0.f, y = 0.f, z = 0.f;
+          bool outside = false;
+          if (valid) {
+            const float* src = phase == 0 ? p.coor_bg + pt * 3 : p.coor_fg + (long long)s * p.fg_slot_stride + pt * 3;
+            x = __ldg(src); y = __ldg(src + 1); z = __ldg(src + 2);
+          }
+          if (phase == 1) {
+            if (p.fixed_locality) outside = fabsf(x) > p.locality_ratio || fabsf(y) > p.locality_ratio || fabsf(z) > p.locality_ratio;
+            const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], x), __fmul_rn(T[1], y)), __fmul_rn(T[2], z)), T[3]);
+            const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], x), __fmul_rn(T[5], y)), __fmul_rn(T[6], z)), T[7]);
+            const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], x), __fmul_rn(T[9], y)), __fmul_rn(T[10], z)), T[11]);
+            x = tx; y = ty; z = tz;
+            if (!p.fixed_locality) outside = fabsf(x) > p.locality_ratio || fabsf(y) > p.locality_ratio || fabsf(z) > p.locality_ratio;
+          }
+          // wait until the previous slot's last weight-gradient MMAs have finished reading the tiles
+          if (it > 0 || s > 0) wait_d(300);
+          {
+            float v[64];
+            float sn[3], cs[3];
+            sincosf(x, &sn[0], &cs[0]);
+            sincosf(y, &sn[1], &cs[1]);
+            sincosf(z, &sn[2], &cs[2]);
+            v[0] = x; v[1] = y; v[2] = z;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+#pragma unroll
+              for (int j = 0; j < 3; ++j) { v[3 + 6 * i + j] = sn[j]; v[6 + 6 * i + j] = cs[j]; }
+              if (i < 4) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { const float s2 = 2.f * sn[j] * cs[j], c2 = 1.f - 2.f * sn[j] * sn[j]; sn[j] = s2; cs[j] = c2; }
+              }
+            }
+#pragma unroll
+            for (int i = kPosenc; i < 64; ++i) v[i] = (valid && i == kPosenc + (s < 15 ? s : 14)) ? 1.f : 0.f;
+            if (!valid) {
+#pragma unroll
+              for (int i = 0; i < kPosenc; ++i) v[i] = 0.f;   // padded points contribute nothing to any gradient
+            }
+            store_row16<true>(s_x, t, v);
+          }
+          publish();
+          // ---- stages 1..6: hidden activations ----
+          const float* sb = s_slotb + s * kSlotBiasFloats;
+#pragma unroll 1
+          for (int st = 1; st <= 6; ++st) {
+            const float* bias = st == 1 ? sb : st == 2 ? s_params + kPB1 : st == 3 ? s_params + kPB2
+                              : st == 4 ? sb + 64 : st == 5 ? s_params + kPA1 : s_params + kPA2;
+            wait_d(300 + st);
+            float v[64];
+            load_d64(tb + kBColD, v);
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = valid ? fmaxf(v[i] + bias[i], 0.f) : 0.f;
+            store_row16<true>(s_x + st * 16384, t, v);
+            publish();
+          }
+          // ---- head forward + backward seed ----
+          wait_d(307);
+          float dzh[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) dzh[i] = 0.f;
+          {
+            uint32_t r[32];
+            tmem_ld32(tb + kBColD, r);
+            tc_wait_ld();
+            float4 dr = valid ? p.scratch_draw[(long long)kslot * p.P + pt] : make_float4(0.f, 0.f, 0.f, 0.f);
+            dr.x *= gscale; dr.y *= gscale; dr.z *= gscale; dr.w *= gscale;
+            const float* hb = s_params + kPHeadB;
+            if (phase == 0) {
+              dzh[0] = dr.x; dzh[1] = dr.y; dzh[2] = dr.z; dzh[3] = dr.w;
+            } else {
+              const float* wc2 = s_params + kPWc2;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float pre = __uint_as_float(r[i]) + hb[i];
+                const float h = fmaxf(pre, 0.f);
+                wc2_acc[i] += dr.x * h;
+                wc2_acc[16 + i] += dr.y * h;
+                wc2_acc[32 + i] += dr.z * h;
+                const float dh = wc2[i] * dr.x + wc2[16 + i] * dr.y + wc2[32 + i] * dr.z;
+                dzh[i] = pre > 0.f ? dh : 0.f;
+              }
+              wc2_acc[48] += dr.x; wc2_acc[49] += dr.y; wc2_acc[50] += dr.z;
+              dzh[kHeadShapeRow] = (p.locality && outside) ? 0.f : dr.w;   // model.py:147-148 zeroes sigma outside the box
+            }
+          }
+          warp_colsum_add(dzh, s_db[4], lane);
+          store_row16<true>(s_dz, t, dzh);
+          publish();
+          // ---- layers 5..0 ----
+#pragma unroll 1
+          for (int l = 5; l >= 0; --l) {
+            wait_d(320 + l);
+            float g[64];
+            load_d64(tb + kBColD, g);              // dX_{l+1}
+            gate_by_row(s_x + (l + 1) * 16384, t, g);   // * [X_{l+1} > 0]  -> dZ_l
+            if (l == 1 || l == 2) warp_colsum_add(g, s_db[l - 1], lane);
+            if (l == 4 || l == 5) warp_colsum_add(g, s_db[l - 2], lane);
+            store_row16<true>(s_dz + ((l & 1) ? 16384 : 0), t, g);
+            publish();
+          }
+        }
+      }
+    }
+    // ---- end of phase: drain, dump accumulators + bias sums as this CTA's partial record ----
+    if (warp < 4) {
+      // the issuer's last commit (dW of layer 0) has not been consumed yet
+      bool any = (long long)blockIdx.x < p.num_tiles;
+      if (any) {
+        mbar_wait(&bar_d, n_d & 1, p.err_flag, 399);
+        ++n_d;
+        tc_fence_after();
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    float* part = p.partials + ((long long)phase * gridDim.x + blockIdx.x) * kPartFloats;
+    if (warp < 4) {
+      const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
+      const int row = warp * 16 + (lane & 15);
+      const int second = lane >> 4;
+#pragma unroll 1
+      for (int pair = 0; pair < 4; ++pair) {
+        const int col = pair == 0 ? 64 : pair == 1 ? 112 : pair == 2 ? 176 : 240;
+        const int acc = pair == 0 ? (second ? 3 : 0) : pair == 1 ? (second ? 2 : 1) : pair == 2 ? (second ? 5 : 4) : (second ? 7 : 6);
+        const int ncol = pair == 0 ? 48 : 64;
+        for (int c0 = 0; c0 < ncol; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tb + col + c0, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) part[acc * kAccFloats + row * 64 + c0 + i] = __uint_as_float(r[i]);
+        }
+        if (ncol == 48)
+          for (int c = 48; c < 64; ++c) part[acc * kAccFloats + row * 64 + c] = 0.f;
+      }
+      // f_color.2 gradient: block reduction of the per-thread sums (fixed order)
+#pragma unroll
+      for (int base = 0; base < 51; base += 1) {
+        float v = wc2_acc[base];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[warp][base] = v;
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 5 * 64; e += blockDim.x) part[kPartBias + e] = (&s_db[0][0])[e];
+    if (threadIdx.x < 64) part[kPartWc2 + threadIdx.x] = threadIdx.x < 51 ? s_red[0][threadIdx.x] + s_red[1][threadIdx.x] + s_red[2][threadIdx.x] + s_red[3][threadIdx.x] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward of the slot composition (model.py:151-159), elementwise, one thread per point:
+//   d raw_k = (d rgb_raw x3, d sigma_raw) for every slot, and max |d raw| for the loss scale
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) decoder_compose_bwd_kernel(const float4* __restrict__ grad_raws, const float4* __restrict__ unmasked,
+                                                                  const float* __restrict__ noise, float dens_noise, long long P, int K,
+                                                                  float4* __restrict__ draw, float* __restrict__ amax) {
+  const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float local = 0.f;
+  if (pt < P) {
+    const float4 g = __ldg(grad_raws + pt);
+    float S = 0.f, qm = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float4 u = __ldg(unmasked + (long long)k * P + pt);
+      S += fmaxf(noise ? u.w - dens_noise * __ldg(noise + (long long)k * P + pt) : u.w, 0.f);
+    }
+    const float denom = S + 1e-5f;
+    for (int k = 0; k < K; ++k) {
+      const float4 u = __ldg(unmasked + (long long)k * P + pt);
+      const float dens = fmaxf(noise ? u.w - dens_noise * __ldg(noise + (long long)k * P + pt) : u.w, 0.f);
+      qm += (g.x * u.x + g.y * u.y + g.z * u.z + g.w * u.w) * (dens / denom);
+    }
+    for (int k = 0; k < K; ++k) {
+      const float4 u = __ldg(unmasked + (long long)k * P + pt);
+      const float dens = fmaxf(noise ? u.w - dens_noise * __ldg(noise + (long long)k * P + pt) : u.w, 0.f);
+      const float m = dens / denom;
+      const float q = g.x * u.x + g.y * u.y + g.z * u.z + g.w * u.w;
+      float4 d;
+      // rgb = (tanh(raw) + 1) / 2  ->  d raw = d rgb * (1 - tanh^2) / 2 = d rgb * 2 rgb (1 - rgb)
+      d.x = g.x * m * 2.f * u.x * (1.f - u.x);
+      d.y = g.y * m * 2.f * u.y * (1.f - u.y);
+      d.z = g.z * m * 2.f * u.z * (1.f - u.z);
+      // m_k = dens_k / (sum dens + 1e-5), sigma_k = dens_k + noise;  sigma_raw gated by its ReLU
+      d.w = dens > 0.f ? g.w * m + (q - qm) / denom : 0.f;
+      draw[(long long)k * P + pt] = d;
+      local = fmaxf(local, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local = fmaxf(local, __shfl_xor_sync(0xffffffffu, local, o));
+  if ((threadIdx.x & 31) == 0 && local > 0.f && isfinite(local))
+    atomicMax(reinterpret_cast<int*>(amax), __float_as_int(local));   // non-negative floats order like their bit patterns
+}
+
+// ---------------------------------------------------------------------------------------------------
+// finalize: fixed-order reduction over the CTAs' partial records, then unfold into the reference's parameter shapes
+// ---------------------------------------------------------------------------------------------------
+struct FinalizeParams {
+  uorf_decoder_weights w;       // forward weights (needed to unfold the folded head and the hoisted latent columns)
+  uorf_decoder_grads g;         // gradient outputs, same shapes
+  const float* z_slots;
+  float* grad_z_slots;          // [K][Z]
+  const float* partials;
+  float* reduced;               // [2][kPartFloats] scratch
+  int grid, K, Z;
+};
+
+__global__ void decoder_bwd_reduce_kernel(const float* partials, float* reduced, int grid, const float* draw_amax) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * kPartFloats) return;
+  const int phase = i / kPartFloats, e = i % kPartFloats;
+  float acc = 0.f;
+  for (int b = 0; b < grid; ++b) acc += partials[((long long)phase * grid + b) * kPartFloats + e];
+  reduced[i] = acc / grad_scale(__ldg(draw_amax));   // undo the loss scale (exact: power of two)
+}
+
+// one CTA; all loops are tiny (<= 64x161 outputs)
+__global__ void decoder_bwd_unfold_kernel(const FinalizeParams f) {
+  const int Z = f.Z, K = f.K, I = kPosenc + Z, CH = Z / 4;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int fg = 0; fg < 2; ++fg) {
+    const float* R = f.reduced + fg * kPartFloats;   // phase 0 = background, 1 = foreground
+    const float* A0 = R + 0 * kAccFloats;   // [out][P cols]   before.0
+    const float* A1 = R + 1 * kAccFloats;
+    const float* A2 = R + 2 * kAccFloats;
+    const float* A3 = R + 3 * kAccFloats;   // after.0 x P
+    const float* A4 = R + 4 * kAccFloats;   // after.0 x tmp
+    const float* A5 = R + 5 * kAccFloats;
+    const float* A6 = R + 6 * kAccFloats;
+    const float* A7 = R + 7 * kAccFloats;   // head
+    const float* DB = R + kPartBias;        // [5][64]: before.2, before.4, after.2, after.4, head
+    float* const* gbw = fg ? f.g.f_before_w : f.g.b_before_w;
+    float* const* gbb = fg ? f.g.f_before_b : f.g.b_before_b;
+    float* const* gaw = fg ? f.g.f_after_w : f.g.b_after_w;
+    float* const* gab = fg ? f.g.f_after_b : f.g.b_after_b;
+    const float* const* bw = fg ? f.w.f_before_w : f.w.b_before_w;
+    const float* const* aw = fg ? f.w.f_after_w : f.w.b_after_w;
+    const int nslots = fg ? K - 1 : 1;
+    // square layers + biases
+    for (int e = tid; e < Z * Z; e += nt) {
+      const int n = e / Z, k = e % Z;
+      gbw[1][e] = A1[n * 64 + k];
+      gbw[2][e] = A2[n * 64 + k];
+      gaw[1][e] = A5[n * 64 + k];
+      gaw[2][e] = A6[n * 64 + k];
+    }
+    for (int n = tid; n < Z; n += nt) {
+      gbb[1][n] = DB[0 * 64 + n];
+      gbb[2][n] = DB[1 * 64 + n];
+      gab[1][n] = DB[2 * 64 + n];
+      gab[2][n] = DB[3 * 64 + n];
+      // wide layers: bias = sum over slots of the per-slot column sums (one-hot columns 33 + s, slot >= 14 share column 47)
+      float b0 = 0.f, b3 = 0.f;
+      for (int c = kPosenc; c < 48; ++c) { b0 += A0[n * 64 + c]; b3 += A3[n * 64 + c]; }
+      gbb[0][n] = b0;
+      gab[0][n] = b3;
+    }
+    // wide layers: posenc columns, tmp columns, latent columns (outer product of per-slot column sums with z)
+    for (int e = tid; e < Z * (I + Z); e += nt) {
+      const int n = e / (I + Z), c = e % (I + Z);
+      float v;
+      if (c < kPosenc) v = A3[n * 64 + c];
+      else if (c < I) {
+        v = 0.f;
+        for (int s = 0; s < nslots && s < 15; ++s) v += A3[n * 64 + kPosenc + s] * f.z_slots[(fg ? s + 1 : 0) * Z + (c - kPosenc)];
+      } else v = A4[n * 64 + (c - I)];
+      gaw[0][e] = v;
+    }
+    for (int e = tid; e < Z * I; e += nt) {
+      const int n = e / I, c = e % I;
+      float v;
+      if (c < kPosenc) v = A0[n * 64 + c];
+      else {
+        v = 0.f;
+        for (int s = 0; s < nslots && s < 15; ++s) v += A0[n * 64 + kPosenc + s] * f.z_slots[(fg ? s + 1 : 0) * Z + (c - kPosenc)];
+      }
+      gbw[0][e] = v;
+    }
+    // d z_slots: W0z^T colsum0_s + W3z^T colsum3_s
+    for (int e = tid; e < nslots * Z; e += nt) {
+      const int s = e / Z, c = e % Z;
+      float v = 0.f;
+      if (s < 15) {
+        for (int n = 0; n < Z; ++n)
+          v += bw[0][n * I + kPosenc + c] * A0[n * 64 + kPosenc + s] + aw[0][n * (I + Z) + kPosenc + c] * A3[n * 64 + kPosenc + s];
+      }
+      f.grad_z_slots[(fg ? s + 1 : 0) * Z + c] = v;
+    }
+    // heads
+    if (fg) {
+      const float* dbf = DB + 4 * 64;  // [0..CH) colour-hidden bias sums, [16] shape bias sum
+      const float* WC2 = R + kPartWc2; // [3][16] + [3]
+      for (int e = tid; e < 3 * CH; e += nt) f.g.f_color2_w[e] = WC2[(e / CH) * 16 + (e % CH)];
+      for (int e = tid; e < 3; e += nt) f.g.f_color2_b[e] = WC2[48 + e];
+      for (int e = tid; e < Z; e += nt) f.g.f_after_shape_w[e] = A7[kHeadShapeRow * 64 + e];
+      if (tid == 0) f.g.f_after_shape_b[0] = dbf[kHeadShapeRow];
+      // folded head: Zh = Wc0 (Wlat x + blat) + bc0 ;  dWf = A7[0..CH) , dbf
+      for (int e = tid; e < CH * Z; e += nt) {   // d Wc0 = dWf . Wlat^T + dbf (x) blat
+        const int n = e / Z, m = e % Z;
+        float v = dbf[n] * f.w.f_after_latent_b[m];
+        for (int k = 0; k < Z; ++k) v += A7[n * 64 + k] * f.w.f_after_latent_w[m * Z + k];
+        f.g.f_color0_w[e] = v;
+      }
+      for (int e = tid; e < CH; e += nt) f.g.f_color0_b[e] = dbf[e];
+      for (int e = tid; e < Z * Z; e += nt) {    // d Wlat = Wc0^T . dWf
+        const int m = e / Z, k = e % Z;
+        float v = 0.f;
+        for (int n = 0; n < CH; ++n) v += f.w.f_color0_w[n * Z + m] * A7[n * 64 + k];
+        f.g.f_after_latent_w[e] = v;
+      }
+      for (int m = tid; m < Z; m += nt) {        // d blat = Wc0^T dbf
+        float v = 0.f;
+        for (int n = 0; n < CH; ++n) v += f.w.f_color0_w[n * Z + m] * dbf[n];
+        f.g.f_after_latent_b[m] = v;
+      }
+    } else {
+      const float* dbh = DB + 4 * 64;
+      for (int e = tid; e < 4 * Z; e += nt) f.g.b_after_w[3][e] = A7[(e / Z) * 64 + (e % Z)];
+      for (int e = tid; e < 4; e += nt) f.g.b_after_b[3][e] = dbh[e];
+    }
+  }
+}
+
+size_t decoder_bwd_workspace_floats(long long P, int K, int num_sms) {
+  const long long tiles = (P + 127) / 128;
+  const long long grid = tiles < num_sms ? tiles : num_sms;
+  return (size_t)K * P * 4 + (size_t)2 * grid * kPartFloats + (size_t)2 * kPartFloats + 64;   // d raw | partials | reduced | amax
+}
+
+static size_t decoder_bwd_smem(int K) {
+  const int w_region = kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
+  return 1024 + ((w_region + 1023) & ~1023) + 9 * 16384;
+}
+
+int launch_decoder_bwd(const uorf_decoder_weights* w, const uorf_decoder_grads* g, const uorf_decoder_bwd_args* a, int num_sms,
+                       int* err_flag, cudaStream_t stream) {
+  DecBwdParams p;
+  p.coor_bg = a->coor_bg;
+  p.coor_fg = a->coor_fg;
+  p.fg_slot_stride = a->fg_slot_stride;
+  p.noise = a->dens_noise != 0.f ? a->noise : nullptr;
+  p.unmasked = reinterpret_cast<const float4*>(a->unmasked_raws);
+  p.grad_raws = reinterpret_cast<const float4*>(a->grad_raws);
+  p.image = static_cast<const unsigned char*>(a->image);
+  p.fg_transform = a->fg_transform;
+  p.locality_ratio = a->locality_ratio;
+  p.dens_noise = a->dens_noise;
+  p.P = a->P;
+  p.K = a->K;
+  p.fixed_locality = a->fixed_locality;
+  p.locality = a->locality;
+  p.num_tiles = (int)((a->P + 127) / 128);
+  p.err_flag = err_flag;
+  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  float* ws = a->workspace;
+  p.scratch_draw = reinterpret_cast<float4*>(ws);
+  p.partials = ws + (size_t)a->K * a->P * 4;
+  float* reduced = p.partials + (size_t)2 * grid * kPartFloats;
+  float* amax = reduced + (size_t)2 * kPartFloats;
+  p.draw_amax = amax;
+  cudaMemsetAsync(amax, 0, sizeof(float), stream);
+  decoder_compose_bwd_kernel<<<(unsigned)((a->P + 255) / 256), 256, 0, stream>>>(p.grad_raws, p.unmasked, p.noise, p.dens_noise, a->P, a->K,
+                                                                               p.scratch_draw, amax);
+  const size_t smem = decoder_bwd_smem(a->K);
+  if (smem > 227 * 1024) return UORF_ERR_UNSUPPORTED;
+  if (cudaFuncSetAttribute(decoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UORF_ERR_DEVICE;
+  decoder_bwd_kernel<<<grid, kBwdThreads, smem, stream>>>(p);
+  decoder_bwd_reduce_kernel<<<(2 * kPartFloats + 255) / 256, 256, 0, stream>>>(p.partials, reduced, grid, amax);
+  FinalizeParams f;
+  f.w = *w;
+  f.g = *g;
+  f.z_slots = a->z_slots;
+  f.grad_z_slots = a->grad_z_slots;
+  f.partials = p.partials;
+  f.reduced = reduced;
+  f.grid = grid;
+  f.K = a->K;
+  f.Z = a->Z;
+  decoder_bwd_unfold_kernel<<<1, 512, 0, stream>>>(f);
+  return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
+}
+
+}  // namespace uorf

@@ -233,3 +233,88 @@ int launch_probe_timing(long long* out, int reps, cudaStream_t stream) {
 }
 
 }  // namespace uorf
+
+// ---------------------------------------------------------------------------------------------------
+// Test hook for the weight-gradient data path: D[m][n] = sum_p A[p][m] * B[p][n]  (p < 128 points, m, n < 64)
+// with BOTH operands read from [point][feature] shared-memory tiles through MN-major descriptors, M = 64, and two
+// accumulators interleaved in the same TMEM columns (lane offset 16).  d1 = A^T B1, d2 = A^T B2.
+// ---------------------------------------------------------------------------------------------------
+namespace uorf {
+
+// smem matrix descriptor, MN-major operand, 128B swizzle: rows (K index = point) are 128 B = 64 features;
+// 8-row groups 1024 B apart (SBO); LBO = distance between 64-feature blocks (single block here).
+__device__ __forceinline__ uint64_t make_sdesc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4)) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+}
+
+__global__ void __launch_bounds__(160, 1) probe_gemm_tn_kernel(const float* __restrict__ a, const float* __restrict__ b1,
+                                                               const float* __restrict__ b2, float* __restrict__ d1,
+                                                               float* __restrict__ d2, int* err_flag) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar_d;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // 3 tiles [128 rows][128 B]
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_d, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(&tmem_base_s, 64);
+    tmem_relinquish();
+  }
+  for (int e = threadIdx.x; e < 3 * 128 * 64; e += blockDim.x) {
+    const int which = e / (128 * 64), r = (e / 64) % 128, c = e % 64;
+    const float v = (which == 0 ? a : which == 1 ? b1 : b2)[r * 64 + c];
+    const int off = which * 16384 + (r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2;
+    *reinterpret_cast<unsigned short*>(smem + off) = to16<false>(v);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (warp == 4) {
+    const uint32_t tbu = __shfl_sync(0xffffffffu, tmem_base, 0);
+    // M = 64, N = 64, bf16, both operands MN-major (bits 15, 16)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((64u >> 4) << 24);
+    const uint32_t s0 = smem_u32(smem);
+    const uint64_t da = make_sdesc_mn_sw128(s0, 16384), db1 = make_sdesc_mn_sw128(s0 + 16384, 16384),
+                   db2 = make_sdesc_mn_sw128(s0 + 32768, 16384);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // K-step = 16 points = 2048 B
+      mma_ss_elect(tbu, da + 128 * j, db1 + 128 * j, idesc, j ? 1u : 0u);
+      mma_ss_elect(tbu + (16u << 16), da + 128 * j, db2 + 128 * j, idesc, j ? 1u : 0u);
+    }
+    tc_commit_elect(&bar_d);
+    __syncwarp();
+  } else {
+    mbar_wait(&bar_d, 0, err_flag, 3);
+    tc_fence_after();
+    const int lane = threadIdx.x & 31;
+    const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float* dst = (lane < 16 ? d1 : d2) + (warp * 16 + (lane & 15)) * 64;
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tb + c0, r);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dst[c0 + i] = __uint_as_float(r[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4) tmem_dealloc(tmem_base, 64);
+}
+
+int launch_probe_gemm_tn(const float* a, const float* b1, const float* b2, float* d1, float* d2, int* err_flag, cudaStream_t stream) {
+  const int smem = 1024 + 3 * 16384;
+  cudaFuncSetAttribute(probe_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  probe_gemm_tn_kernel<<<1, 160, smem, stream>>>(a, b1, b2, d1, d2, err_flag);
+  return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
+}
+
+}  // namespace uorf

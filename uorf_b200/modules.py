@@ -391,47 +391,37 @@ class Decoder(nn.Module):
         except KeyError:
             raise ValueError(f"unknown precision {self.precision!r} (use one of {sorted(_lib.PRECISIONS)})") from None
 
-    def forward(self, sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform, dens_noise=0., noise=None):
-        """
-        sampling_coor_bg Px3, sampling_coor_fg (K-1)xPx3 (an expand() view is consumed in place),
-        z_slots KxC (slot 0 = background), fg_transform 1x3x3 (1x4x4 when fixed_locality)
-        -> raws Px4, masked_raws KxPx4, unmasked_raws KxPx4, masks KxPx1
-        """
-        _require_cuda(sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform)
-        if torch.is_grad_enabled() and (z_slots.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(
-                "Decoder backward kernel is not built yet (SURVEY section 8 row a8, backward): call under "
-                "torch.no_grad(); uorf_b200 does not fall back to eager PyTorch")
+    def _prepared_image(self, z, K, Cz, prec, dev, stream):
+        nbytes = lib().uorf_decoder_image_bytes(K, prec)
+        image = torch.empty(nbytes + 1024, device=dev, dtype=torch.uint8)
+        image_ptr = image.data_ptr() + (-image.data_ptr()) % 1024
+        w = self._weights()
+        check(lib().uorf_decoder_prepare(C.byref(w), z.data_ptr(), K, Cz, self.n_freq, self.n_layers, prec, image_ptr,
+                                         stream), "uorf_decoder_prepare")
+        return image, image_ptr, w
+
+    @staticmethod
+    def _canon_inputs(sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform):
+        coor_bg = _f32c(sampling_coor_bg)
+        fg = sampling_coor_fg if sampling_coor_fg.dtype == torch.float32 else sampling_coor_fg.float()
+        if fg.stride(-1) != 1 or fg.stride(-2) != 3:
+            fg = fg.contiguous()
+        fg_stride = fg.stride(0) if fg.shape[0] > 1 else 0
+        return coor_bg, fg, int(fg_stride), _f32c(z_slots.detach()), _f32c(fg_transform.detach().reshape(-1))
+
+    def _launch_forward(self, sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform, dens_noise, noise, emit):
         if self.n_layers != 3 or self.n_freq != 5:
             raise _lib.UorfError("decoder kernel is built for n_freq=5, n_layers=3 (every shipped configuration)")
         K, Cz = z_slots.shape
         P = sampling_coor_bg.shape[0]
         dev = sampling_coor_bg.device
         prec = self._precision()
-        coor_bg = _f32c(sampling_coor_bg)
-        fg = sampling_coor_fg if sampling_coor_fg.dtype == torch.float32 else sampling_coor_fg.float()
-        if fg.stride(-1) != 1 or fg.stride(-2) != 3:
-            fg = fg.contiguous()
-        fg_stride = fg.stride(0) if fg.shape[0] > 1 else 0
-        z = _f32c(z_slots.detach())
-        T = _f32c(fg_transform.reshape(-1))
+        coor_bg, fg, fg_stride, z, T = self._canon_inputs(sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform)
         if T.numel() != (16 if self.fixed_locality else 9):
             raise _lib.UorfError("fg_transform must be 1x4x4 with fixed_locality, else 1x3x3")
-
         stream = _stream(coor_bg)
-        nbytes = lib().uorf_decoder_image_bytes(K, prec)
-        image = torch.empty(nbytes + 1024, device=dev, dtype=torch.uint8)
-        off = (-image.data_ptr()) % 1024
-        image_ptr = image.data_ptr() + off
-        w = self._weights()
-        check(lib().uorf_decoder_prepare(C.byref(w), z.data_ptr(), K, Cz, self.n_freq, self.n_layers, prec, image_ptr,
-                                         stream), "uorf_decoder_prepare")
-
-        if noise is None and (dens_noise != 0. or self.match_rng_stream):
-            noise = torch.randn(K, P, 1, device=dev)  # model.py:155 (always drawn by the reference)
+        image, image_ptr, w = self._prepared_image(z, K, Cz, prec, dev, stream)
         noise_c = _f32c(noise.reshape(K, P)) if (noise is not None and dens_noise != 0.) else None
-
-        emit = set(self.emit)
         mk = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
         raws = mk(P, 4) if "raws" in emit else None
         masked = mk(K, P, 4) if "masked_raws" in emit else None
@@ -439,9 +429,8 @@ class Decoder(nn.Module):
         masks = mk(K, P, 1) if "masks" in emit else None
         outside = torch.empty(K - 1, P, device=dev, dtype=torch.uint8) if self.return_outside else None
         workspace = mk(P, 4)
-
         a = _lib.DecoderArgs()
-        a.coor_bg, a.coor_fg, a.fg_slot_stride = coor_bg.data_ptr(), fg.data_ptr(), int(fg_stride)
+        a.coor_bg, a.coor_fg, a.fg_slot_stride = coor_bg.data_ptr(), fg.data_ptr(), fg_stride
         a.fg_transform, a.noise = T.data_ptr(), _ptr(noise_c)
         a.dens_noise, a.locality_ratio = float(dens_noise), float(self.locality_ratio)
         a.locality, a.fixed_locality = int(bool(self.locality)), int(bool(self.fixed_locality))
@@ -460,3 +449,85 @@ class Decoder(nn.Module):
             ev.append((e0, e1))
         self.last_outside = outside
         return raws, masked, unmasked, masks
+
+    def _launch_backward(self, sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform, dens_noise, noise, unmasked, grad_raws):
+        """-> (grad_z_slots KxC, {param name: grad}) through uorf_decoder_backward."""
+        K, Cz = z_slots.shape
+        P = sampling_coor_bg.shape[0]
+        dev = sampling_coor_bg.device
+        coor_bg, fg, fg_stride, z, T = self._canon_inputs(sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform)
+        stream = _stream(coor_bg)
+        image, image_ptr, w = self._prepared_image(z, K, Cz, _lib.PREC_FP16, dev, stream)
+        named = dict(self.named_parameters())
+        grads = {n: torch.empty_like(p_, dtype=torch.float32, memory_format=torch.contiguous_format) for n, p_ in named.items()}
+        g = _lib.DecoderWeights()
+        for i in range(3):
+            g.f_before_w[i], g.f_before_b[i] = grads[f"f_before.{2 * i}.weight"].data_ptr(), grads[f"f_before.{2 * i}.bias"].data_ptr()
+            g.f_after_w[i], g.f_after_b[i] = grads[f"f_after.{2 * i}.weight"].data_ptr(), grads[f"f_after.{2 * i}.bias"].data_ptr()
+            g.b_before_w[i], g.b_before_b[i] = grads[f"b_before.{2 * i}.weight"].data_ptr(), grads[f"b_before.{2 * i}.bias"].data_ptr()
+        for i in range(4):
+            g.b_after_w[i], g.b_after_b[i] = grads[f"b_after.{2 * i}.weight"].data_ptr(), grads[f"b_after.{2 * i}.bias"].data_ptr()
+        g.f_after_latent_w, g.f_after_latent_b = grads["f_after_latent.weight"].data_ptr(), grads["f_after_latent.bias"].data_ptr()
+        g.f_after_shape_w, g.f_after_shape_b = grads["f_after_shape.weight"].data_ptr(), grads["f_after_shape.bias"].data_ptr()
+        g.f_color0_w, g.f_color0_b = grads["f_color.0.weight"].data_ptr(), grads["f_color.0.bias"].data_ptr()
+        g.f_color2_w, g.f_color2_b = grads["f_color.2.weight"].data_ptr(), grads["f_color.2.bias"].data_ptr()
+        ws = torch.empty(lib().uorf_decoder_backward_workspace_floats(P, K), device=dev, dtype=torch.float32)
+        gz = torch.empty(K, Cz, device=dev, dtype=torch.float32)
+        noise_c = _f32c(noise.reshape(K, P)) if (noise is not None and dens_noise != 0.) else None
+        gr = _f32c(grad_raws)
+        un = _f32c(unmasked)
+        a = _lib.DecoderBwdArgs()
+        a.coor_bg, a.coor_fg, a.fg_slot_stride = coor_bg.data_ptr(), fg.data_ptr(), fg_stride
+        a.fg_transform, a.noise = T.data_ptr(), _ptr(noise_c)
+        a.dens_noise, a.locality_ratio = float(dens_noise), float(self.locality_ratio)
+        a.locality, a.fixed_locality = int(bool(self.locality)), int(bool(self.fixed_locality))
+        a.P, a.K, a.Z = P, K, Cz
+        a.z_slots, a.image, a.unmasked_raws, a.grad_raws = z.data_ptr(), image_ptr, un.data_ptr(), gr.data_ptr()
+        a.workspace, a.grad_z_slots = ws.data_ptr(), gz.data_ptr()
+        check(lib().uorf_decoder_backward(C.byref(w), C.byref(g), C.byref(a), stream), "uorf_decoder_backward")
+        return gz, grads
+
+    def forward(self, sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform, dens_noise=0., noise=None):
+        """
+        sampling_coor_bg Px3, sampling_coor_fg (K-1)xPx3 (an expand() view is consumed in place),
+        z_slots KxC (slot 0 = background), fg_transform 1x3x3 (1x4x4 when fixed_locality)
+        -> raws Px4, masked_raws KxPx4, unmasked_raws KxPx4, masks KxPx1
+        Under autograd, gradients flow from `raws` to z_slots and every decoder parameter through the fused backward
+        kernel; masked/unmasked/masks are non-differentiable (the reference detaches them, uorf_nogan_model.py:185-196).
+        """
+        _require_cuda(sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform)
+        K = z_slots.shape[0]
+        P = sampling_coor_bg.shape[0]
+        if noise is None and (dens_noise != 0. or self.match_rng_stream):
+            noise = torch.randn(K, P, 1, device=sampling_coor_bg.device)  # model.py:155 (always drawn by the reference)
+        needs_grad = torch.is_grad_enabled() and (z_slots.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if not needs_grad:
+            return self._launch_forward(sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform, dens_noise, noise, set(self.emit))
+        names = [n for n, _ in self.named_parameters()]
+        params = [p_ for _, p_ in self.named_parameters()]
+        raws, masked, unmasked, masks = _DecoderFn.apply(self, sampling_coor_bg, sampling_coor_fg, fg_transform, noise,
+                                                         float(dens_noise), names, z_slots, *params)
+        emit = set(self.emit)
+        return (raws, masked if "masked_raws" in emit else None, unmasked if "unmasked_raws" in emit else None,
+                masks if "masks" in emit else None)
+
+
+class _DecoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, coor_bg, coor_fg, fg_transform, noise, dens_noise, names, z_slots, *params):
+        emit = set(module.emit) | {"raws", "unmasked_raws"}   # unmasked is what the backward kernel re-reads
+        raws, masked, unmasked, masks = module._launch_forward(coor_bg, coor_fg, z_slots, fg_transform, dens_noise, noise, emit)
+        ctx.module, ctx.dens_noise, ctx.names = module, dens_noise, names
+        ctx.save_for_backward(coor_bg, coor_fg, fg_transform, z_slots.detach(), unmasked)
+        ctx.noise = noise
+        dummy = lambda t, *shape: t if t is not None else raws.new_empty(0)
+        outs = (raws, dummy(masked), unmasked, dummy(masks))
+        ctx.mark_non_differentiable(outs[1], outs[2], outs[3])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_raws, *unused):
+        coor_bg, coor_fg, fg_transform, z_slots, unmasked = ctx.saved_tensors
+        gz, grads = ctx.module._launch_backward(coor_bg, coor_fg, z_slots, fg_transform, ctx.dens_noise, ctx.noise, unmasked,
+                                                g_raws)
+        return (None, None, None, None, None, None, None, gz) + tuple(grads[n] for n in ctx.names)
