@@ -199,6 +199,18 @@ typedef struct uorf_slot_attention_weights {
   const float *to_res_bg_ln_w, *to_res_bg_ln_b, *to_res_bg_w1, *to_res_bg_b1, *to_res_bg_w2, *to_res_bg_b2;
 } uorf_slot_attention_weights;
 
+typedef struct uorf_slot_attention_grads {   /* same fields / shapes as uorf_slot_attention_weights, written by the backward */
+  float *slots_mu, *slots_logsigma, *slots_mu_bg, *slots_logsigma_bg;
+  float *norm_feat_w, *norm_feat_b;
+  float *to_k_w, *to_v_w;
+  float *to_q_ln_w, *to_q_ln_b, *to_q_w;
+  float *to_q_bg_ln_w, *to_q_bg_ln_b, *to_q_bg_w;
+  float *gru_w_ih, *gru_w_hh, *gru_b_ih, *gru_b_hh;
+  float *gru_bg_w_ih, *gru_bg_w_hh, *gru_bg_b_ih, *gru_bg_b_hh;
+  float *to_res_ln_w, *to_res_ln_b, *to_res_w1, *to_res_b1, *to_res_w2, *to_res_b2;
+  float *to_res_bg_ln_w, *to_res_bg_ln_b, *to_res_bg_w1, *to_res_bg_b1, *to_res_bg_w2, *to_res_bg_b2;
+} uorf_slot_attention_grads;
+
 /* Floats of workspace uorf_slot_attention_forward needs. */
 size_t uorf_slot_attention_workspace_floats(int32_t n_tokens, int32_t C, int32_t K);
 
@@ -210,6 +222,17 @@ int uorf_slot_attention_forward(const uorf_slot_attention_weights* w, const floa
                                 int64_t feat_chan_stride, const float* noise_fg, const float* noise_bg,
                                 int32_t n_tokens, int32_t C, int32_t K, int32_t hidden, int32_t iters, float eps,
                                 float* workspace, float* slots, float* attn, void* stream);
+
+/* Kernel 5 (slot-attention part) - backward of SlotAttention.forward (torch.autograd through models/model.py:205-258 as
+ * run by uorfNoGanModel.backward): gradient of every parameter and of feat, given d slots [K][C] (attn is detached by the
+ * reference's driver).  fwd_workspace is the workspace the forward call filled (it keeps k, v and 3KC+K floats of state per
+ * iteration; everything else is recomputed).  grad_feat [n_tokens][C] contiguous. */
+size_t uorf_slot_attention_backward_workspace_floats(int32_t n_tokens, int32_t C, int32_t K, int32_t hidden);
+int uorf_slot_attention_backward(const uorf_slot_attention_weights* w, const uorf_slot_attention_grads* g, const float* feat,
+                                 int64_t feat_token_stride, int64_t feat_chan_stride, const float* noise_fg,
+                                 const float* noise_bg, int32_t n_tokens, int32_t C, int32_t K, int32_t hidden, int32_t iters,
+                                 float eps, const float* fwd_workspace, const float* grad_slots, float* workspace,
+                                 float* grad_feat, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Test hook: one 128 x N x (16*ksteps) bf16 GEMM on the tcgen05 path the decoder uses

@@ -110,6 +110,10 @@ _SIGNATURES = {
     "uorf_slot_attention_forward": (C.c_int, [C.POINTER(SlotAttentionWeights), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                               C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uorf_slot_attention_backward_workspace_floats": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "uorf_slot_attention_backward": (C.c_int, [C.POINTER(SlotAttentionWeights), C.POINTER(SlotAttentionWeights), C.c_void_p, C.c_int64,
+                                               C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uorf_probe_gemm_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uorf_probe_timing": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "uorf_probe_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

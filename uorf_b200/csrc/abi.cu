@@ -26,6 +26,11 @@ int launch_slot_attention(const uorf_slot_attention_weights* w, const float* fea
                           float* workspace, float* slots, float* attn, cudaStream_t stream);
 int launch_probe_gemm(const float* a, const float* b, int N, int ksteps, int passes, int f16, float* d, int* err_flag, cudaStream_t stream);
 int launch_probe_timing(long long* out, int reps, cudaStream_t stream);
+size_t slot_attention_bwd_ws_floats(int ntok, int C, int K, int hidden);
+int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_slot_attention_grads* g, const float* feat, long long feat_ts,
+                              long long feat_cs, const float* noise_fg, const float* noise_bg, int ntok, int C, int K, int hidden, int iters,
+                              float eps, const float* fwd_workspace, const float* grad_slots, float* workspace, float* grad_feat,
+                              cudaStream_t stream);
 size_t decoder_bwd_workspace_floats(long long P, int K, int num_sms);
 int launch_decoder_bwd(const uorf_decoder_weights* w, const uorf_decoder_grads* g, const uorf_decoder_bwd_args* a, int num_sms,
                        int* err_flag, cudaStream_t stream);
@@ -256,6 +261,25 @@ int uorf_slot_attention_forward(const uorf_slot_attention_weights* w, const floa
   return check_launch(uorf::launch_slot_attention(w, feat, feat_token_stride, feat_chan_stride, noise_fg, noise_bg, n_tokens, C, K,
                                                   hidden, iters, eps, workspace, slots, attn, static_cast<cudaStream_t>(stream)),
                       "uorf_slot_attention_forward");
+}
+
+size_t uorf_slot_attention_backward_workspace_floats(int32_t n_tokens, int32_t C, int32_t K, int32_t hidden) {
+  return uorf::slot_attention_bwd_ws_floats(n_tokens, C, K, hidden);
+}
+
+int uorf_slot_attention_backward(const uorf_slot_attention_weights* w, const uorf_slot_attention_grads* g, const float* feat,
+                                 int64_t feat_token_stride, int64_t feat_chan_stride, const float* noise_fg, const float* noise_bg,
+                                 int32_t n_tokens, int32_t C, int32_t K, int32_t hidden, int32_t iters, float eps,
+                                 const float* fwd_workspace, const float* grad_slots, float* workspace, float* grad_feat, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  if (!w || !g || !feat || !noise_fg || !noise_bg || !fwd_workspace || !grad_slots || !workspace || !grad_feat)
+    return fail(UORF_ERR_ARG, "uorf_slot_attention_backward: null pointer%s");
+  if (n_tokens < 1 || iters < 1) return fail(UORF_ERR_ARG, "uorf_slot_attention_backward: bad sizes%s");
+  return check_launch(uorf::launch_slot_attention_bwd(w, g, feat, feat_token_stride, feat_chan_stride, noise_fg, noise_bg, n_tokens, C, K,
+                                                      hidden, iters, eps, fwd_workspace, grad_slots, workspace, grad_feat,
+                                                      static_cast<cudaStream_t>(stream)),
+                      "uorf_slot_attention_backward");
 }
 
 int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, int32_t precision, float* d, void* stream) {

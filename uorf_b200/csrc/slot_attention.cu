@@ -19,6 +19,7 @@ constexpr int kSaThreads = 256;
 constexpr int kSaMaxC = 64;
 constexpr int kSaMaxK = 16;
 constexpr int kSaMaxHid = 128;
+__host__ __device__ inline int sa_saved_stride(int K, int C) { return 3 * K * C + ((K + 3) & ~3); }
 
 struct SaParams {
   uorf_slot_attention_weights w;
@@ -32,6 +33,7 @@ struct SaParams {
   float* vbuf;     // [ntok][C]
   float* partial;  // [nblk][K][C+1]
   float* qbuf;     // [K][C] queries of the current iteration
+  float* saved;    // per iteration: slot_in [K][C] | q [K][C] | upd [K][C] | asum [K]   (re-read by the backward kernels)
   float* slots;    // [K][C] state (slot 0 = bg)
   float* attn;     // [K][ntok]
 };
@@ -111,26 +113,30 @@ __device__ __forceinline__ void warp0_layernorm(const float* x, const float* __r
   }
 }
 // q_k = to_q(LN(slot_k)) -> global q buffer
-__device__ __forceinline__ void slot_query(const SaParams& p, int k, const float* slot, float* s_ln, float* s_q) {
+__device__ __forceinline__ void slot_query(const SaParams& p, int k, const float* slot, float* s_ln, float* s_q, float* q_save) {
   warp0_layernorm(slot, k == 0 ? p.w.to_q_bg_ln_w : p.w.to_q_ln_w, k == 0 ? p.w.to_q_bg_ln_b : p.w.to_q_ln_b, s_ln, p.C);
   __syncthreads();
   warp_matvec(k == 0 ? p.w.to_q_bg_w : p.w.to_q_w, nullptr, s_ln, s_q, p.C, p.C, false);
   __syncthreads();
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) p.qbuf[k * p.C + c] = s_q[c];
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    p.qbuf[k * p.C + c] = s_q[c];
+    if (q_save) q_save[k * p.C + c] = s_q[c];
+  }
 }
 
 // ---- slot initialisation + first query; one CTA per slot -------------------------------------------
 __global__ void __launch_bounds__(kSaThreads) sa_init_kernel(const SaParams p) {
   __shared__ float s_slot[kSaMaxC], s_ln[kSaMaxC], s_q[kSaMaxC];
-  const int k = blockIdx.x, C = p.C;
+  const int k = blockIdx.x, C = p.C, K = p.K;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float v = k == 0 ? p.w.slots_mu_bg[c] + expf(p.w.slots_logsigma_bg[c]) * p.noise_bg[c]
                            : p.w.slots_mu[c] + expf(p.w.slots_logsigma[c]) * p.noise_fg[(k - 1) * C + c];
     s_slot[c] = v;
     p.slots[k * C + c] = v;
+    p.saved[k * C + c] = v;                       // slot_in of iteration 0
   }
   __syncthreads();
-  slot_query(p, k, s_slot, s_ln, s_q);
+  slot_query(p, k, s_slot, s_ln, s_q, p.saved + K * C);
 }
 
 // ---- pass B (per iteration): dots, softmax over slots, partial weighted sums -------------------------
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(kSaThreads) sa_attn_kernel(const SaParams p) {
 }
 
 // ---- pass C (per iteration): reduce partials, GRUCell, residual MLP, next query; one CTA per slot ------
-__global__ void __launch_bounds__(kSaThreads) sa_update_kernel(const SaParams p, int nblk) {
+__global__ void __launch_bounds__(kSaThreads) sa_update_kernel(const SaParams p, int nblk, int it) {
   __shared__ float s_u[kSaMaxC], s_h[kSaMaxC], s_g[6 * kSaMaxC], s_n[kSaMaxC], s_ln[kSaMaxC], s_m[kSaMaxHid], s_o[kSaMaxC];
   __shared__ float s_red[kSaThreads / 32][kSaMaxC + 1];
   const int C = p.C, K = p.K, Hd = p.hidden, k = blockIdx.x;
@@ -201,10 +207,13 @@ __global__ void __launch_bounds__(kSaThreads) sa_update_kernel(const SaParams p,
     s_red[0][threadIdx.x] = acc;
   }
   __syncthreads();
+  float* sv = p.saved + (long long)it * sa_saved_stride(K, C);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     s_u[c] = s_red[0][c] / s_red[0][C];
     s_h[c] = p.slots[k * C + c];
+    sv[2 * K * C + k * C + c] = s_u[c];          // upd
   }
+  if (threadIdx.x == 0) sv[3 * K * C + k] = s_red[0][C];   // sum over tokens of attn
   __syncthreads();
   warp_matvec(k == 0 ? p.w.gru_bg_w_ih : p.w.gru_w_ih, k == 0 ? p.w.gru_bg_b_ih : p.w.gru_b_ih, s_u, s_g, 3 * C, C, false);
   warp_matvec(k == 0 ? p.w.gru_bg_w_hh : p.w.gru_w_hh, k == 0 ? p.w.gru_bg_b_hh : p.w.gru_b_hh, s_h, s_g + 3 * C, 3 * C, C, false);
@@ -226,20 +235,21 @@ __global__ void __launch_bounds__(kSaThreads) sa_update_kernel(const SaParams p,
     const float v = s_n[c] + s_o[c];
     s_n[c] = v;
     p.slots[k * C + c] = v;
+    if (it + 1 < p.iters) sv[sa_saved_stride(K, C) + k * C + c] = v;   // slot_in of the next iteration
   }
   __syncthreads();
-  slot_query(p, k, s_n, s_ln, s_o);   // query for the next iteration
+  slot_query(p, k, s_n, s_ln, s_o, it + 1 < p.iters ? sv + sa_saved_stride(K, C) + K * C : nullptr);   // query for the next iteration
 }
 
 size_t slot_attention_ws_floats(int ntok, int C, int K) {
   const size_t nblk = (ntok + kSaTok - 1) / kSaTok;
-  return (size_t)2 * ntok * C + nblk * K * (C + 1) + (size_t)K * C;
+  return (size_t)2 * ntok * C + nblk * K * (C + 1) + (size_t)K * C + (size_t)8 * sa_saved_stride(K, C);   // k | v | partials | q | saved (<= 8 iterations)
 }
 
 int launch_slot_attention(const uorf_slot_attention_weights* w, const float* feat, long long feat_ts, long long feat_cs,
                           const float* noise_fg, const float* noise_bg, int ntok, int C, int K, int hidden, int iters, float eps,
                           float* workspace, float* slots, float* attn, cudaStream_t stream) {
-  if (C > kSaMaxC || K > kSaMaxK || hidden > kSaMaxHid || K < 2) return UORF_ERR_UNSUPPORTED;
+  if (C > kSaMaxC || K > kSaMaxK || hidden > kSaMaxHid || K < 2 || iters > 8) return UORF_ERR_UNSUPPORTED;
   SaParams p;
   p.w = *w;
   p.feat = feat; p.feat_ts = feat_ts; p.feat_cs = feat_cs;
@@ -250,13 +260,14 @@ int launch_slot_attention(const uorf_slot_attention_weights* w, const float* fea
   p.vbuf = workspace + (size_t)ntok * C;
   p.partial = workspace + (size_t)2 * ntok * C;
   p.qbuf = p.partial + (size_t)nblk * K * (C + 1);
+  p.saved = p.qbuf + (size_t)K * C;
   p.slots = slots;
   p.attn = attn;
   sa_kv_kernel<<<nblk, kSaThreads, 0, stream>>>(p);
   sa_init_kernel<<<K, kSaThreads, 0, stream>>>(p);
   for (int it = 0; it < iters; ++it) {
     sa_attn_kernel<<<nblk, kSaThreads, 0, stream>>>(p);
-    sa_update_kernel<<<K, kSaThreads, 0, stream>>>(p, nblk);
+    sa_update_kernel<<<K, kSaThreads, 0, stream>>>(p, nblk, it);
   }
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }

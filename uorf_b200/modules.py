@@ -272,15 +272,49 @@ class SlotAttention(nn.Module):
         w._keep = keep
         return w
 
+    def _launch_forward(self, feat, K, noise_fg, noise_bg):
+        B, N, Cin = feat.shape
+        Cs = self.slot_dim
+        dev = feat.device
+        f0 = feat[0]
+        ws = torch.empty(lib().uorf_slot_attention_workspace_floats(N, Cs, K), device=dev, dtype=torch.float32)
+        slots = torch.empty(1, K, Cs, device=dev, dtype=torch.float32)
+        attn = torch.empty(1, K, N, device=dev, dtype=torch.float32)
+        w = self._weights()
+        check(lib().uorf_slot_attention_forward(C.byref(w), f0.data_ptr(), f0.stride(0), f0.stride(1), noise_fg.data_ptr(),
+                                                noise_bg.data_ptr(), N, Cs, K, self.hidden_dim, self.iters, float(self.eps),
+                                                ws.data_ptr(), slots.data_ptr(), attn.data_ptr(), _stream(feat)),
+              "uorf_slot_attention_forward")
+        return slots, attn, ws
+
+    def _launch_backward(self, feat, K, noise_fg, noise_bg, fwd_ws, grad_slots):
+        """-> (grad_feat 1xNxC, {param name: grad})"""
+        B, N, Cin = feat.shape
+        Cs = self.slot_dim
+        dev = feat.device
+        f0 = feat[0]
+        named = dict(self.named_parameters())
+        grads = {n: torch.zeros_like(p_, dtype=torch.float32, memory_format=torch.contiguous_format) for n, p_ in named.items()}
+        g = _lib.SlotAttentionWeights()
+        for field, key in _lib.SA_STATE_KEYS.items():
+            setattr(g, field, grads[key].data_ptr())
+        w = self._weights()
+        ws = torch.empty(lib().uorf_slot_attention_backward_workspace_floats(N, Cs, K, self.hidden_dim), device=dev, dtype=torch.float32)
+        gfeat = torch.empty(1, N, Cs, device=dev, dtype=torch.float32)
+        gs = _f32c(grad_slots.reshape(K, Cs))
+        check(lib().uorf_slot_attention_backward(C.byref(w), C.byref(g), f0.data_ptr(), f0.stride(0), f0.stride(1),
+                                                 noise_fg.data_ptr(), noise_bg.data_ptr(), N, Cs, K, self.hidden_dim, self.iters,
+                                                 float(self.eps), fwd_ws.data_ptr(), gs.data_ptr(), ws.data_ptr(), gfeat.data_ptr(),
+                                                 _stream(feat)), "uorf_slot_attention_backward")
+        return gfeat, grads
+
     def forward(self, feat, num_slots=None, noise=None):
         """feat BxNxC (B must be 1, as in every reference driver) -> slots BxKxC, attn BxKxN.
         `noise` = (noise_fg (K-1)xC, noise_bg 1xC) overrides the two randn draws (model.py:216,219);
-        by default they are drawn from torch's CUDA generator in the reference's order."""
+        by default they are drawn from torch's CUDA generator in the reference's order.
+        Under autograd, gradients flow from `slots` to `feat` and every parameter through the backward kernels; `attn`
+        is non-differentiable (the reference's training driver detaches it, uorf_nogan_model.py:186)."""
         _require_cuda(feat)
-        if torch.is_grad_enabled() and (feat.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(
-                "SlotAttention backward kernel is not built yet (SURVEY section 8 row a2, backward): call under "
-                "torch.no_grad(); uorf_b200 does not fall back to eager PyTorch")
         B, N, Cin = feat.shape
         if B != 1:
             raise _lib.UorfError("SlotAttention kernel handles batch 1 (one scene), as the reference drivers do")
@@ -297,16 +331,29 @@ class SlotAttention(nn.Module):
         noise_fg = _f32c(noise_fg.reshape(K - 1, Cs))
         noise_bg = _f32c(noise_bg.reshape(Cs))
         feat = feat if feat.dtype == torch.float32 else feat.float()
-        f0 = feat[0]
-        ws = torch.empty(lib().uorf_slot_attention_workspace_floats(N, Cs, K), device=dev, dtype=torch.float32)
-        slots = torch.empty(1, K, Cs, device=dev, dtype=torch.float32)
-        attn = torch.empty(1, K, N, device=dev, dtype=torch.float32)
-        w = self._weights()
-        check(lib().uorf_slot_attention_forward(C.byref(w), f0.data_ptr(), f0.stride(0), f0.stride(1), noise_fg.data_ptr(),
-                                                noise_bg.data_ptr(), N, Cs, K, self.hidden_dim, self.iters, float(self.eps),
-                                                ws.data_ptr(), slots.data_ptr(), attn.data_ptr(), _stream(feat)),
-              "uorf_slot_attention_forward")
+        needs_grad = torch.is_grad_enabled() and (feat.requires_grad or any(p_.requires_grad for p_ in self.parameters()))
+        if not needs_grad:
+            slots, attn, _ = self._launch_forward(feat, K, noise_fg, noise_bg)
+            return slots, attn
+        names = [n for n, _ in self.named_parameters()]
+        params = [p_ for _, p_ in self.named_parameters()]
+        return _SlotAttentionFn.apply(self, feat, noise_fg, noise_bg, K, names, *params)
+
+
+class _SlotAttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, feat, noise_fg, noise_bg, K, names, *params):
+        slots, attn, ws = module._launch_forward(feat, K, noise_fg, noise_bg)
+        ctx.module, ctx.K, ctx.names = module, K, names
+        ctx.save_for_backward(feat, noise_fg, noise_bg, ws)
+        ctx.mark_non_differentiable(attn)
         return slots, attn
+
+    @staticmethod
+    def backward(ctx, g_slots, g_attn):
+        feat, noise_fg, noise_bg, ws = ctx.saved_tensors
+        gfeat, grads = ctx.module._launch_backward(feat, ctx.K, noise_fg, noise_bg, ws, g_slots)
+        return (None, gfeat, None, None, None, None) + tuple(grads[n] for n in ctx.names)
 
 
 # ======================================================================================================
