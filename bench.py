@@ -303,6 +303,99 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------
+# training arm (BASELINE.json configs[2]): CLEVR-567 coarse-stage step, fwd + bwd + Adam, scene-sharded data parallel
+# ----------------------------------------------------------------------------------------------------
+TRAIN_CFG = dict(workload="clevr567_train_coarse_K8_F64_D64_N4", K=8, z_dim=64, n_views=4, frustum=64, n_samp=64,
+                 supervision_size=64, input_size=64, load_size=128)
+
+
+def run_train(args):
+    import torch.distributed as dist
+    from uorf_b200.nogan_model import uorfNoGanModel, default_train_options
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --mode train needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    c = TRAIN_CFG
+    torch.manual_seed(2021)   # identical replicas
+    opt = default_train_options(num_slots=c["K"], z_dim=c["z_dim"], n_samp=c["n_samp"], frustum_size=c["frustum"],
+                                render_size=c["supervision_size"], supervision_size=c["supervision_size"], input_size=c["input_size"],
+                                n_img_each_scene=c["n_views"], stage="coarse", gpu_ids=[local_rank], warmup_steps=10)
+    model = uorfNoGanModel(opt, precision=args.precision)
+    if world > 1:
+        model.process_group = dist.group.WORLD
+    img, c2w, azi = synthetic_scene(c["n_views"], c["load_size"], seed=2021 + rank)   # one scene per rank
+    host = {"img_data": img.pin_memory(), "cam2world": c2w.pin_memory(), "azi_rot": azi.pin_memory()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    loss_host = torch.empty(1).pin_memory()
+
+    def step(inputs):
+        model.set_input(inputs)
+        model.optimize_parameters(epoch=0)
+        model.update_learning_rate()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sampler.start()
+    ms_total = timed(lambda: step(resident), args.steps)
+    t_end = time.time() + 1.0
+    while time.time() < t_end and sampler.ok and len(sampler.samples) < 40:
+        step(resident)
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+
+    def e2e_step():
+        step(host)
+        loss_host.copy_(model.loss_recon.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    if rank == 0:
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        line = {"metric": "train_scene_steps_per_sec", "value": world * args.steps / (ms_total * 1e-3), "unit": "scene-steps/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision + " forward; fp16 tensor-core backward with fp32 accumulation; fp32 elsewhere", "data": "synthetic",
+                "config": dict(c, step="Encoder+SlotAttention+sampling+decoder+compositing fwd+bwd, MSE + VGG16-relu4_3 perceptual "
+                               "(random-init VGG, weight 0 at epoch 0 exactly as the reference computes it), Adam",
+                               parallelism=f"scene-sharded data parallel x{world}, one flat gradient all-reduce (NCCL)",
+                               loss_last=float(model.loss_recon)),
+                "clocks": clocks,
+                "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "scene-steps/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "impl": "b200"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -311,9 +404,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "bf16x3", "bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="render", choices=["render", "train"],
+                    help="render: the headline eval-render metric (default); train: CLEVR-567 coarse training step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "train":
+        run_train(args)
     else:
         run_b200(args)
 

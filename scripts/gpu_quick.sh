@@ -19,3 +19,6 @@ except Exception as e:
     print("ERR", e); print(open(sys.argv[1]).read()[-1500:])
 PY
 done
+if [ -n "$TRAIN" ]; then
+  timeout 900 python bench.py --mode train --steps 10 --warmup 3 > gpurun_out/bench_train.log 2>&1; tail -c 1800 gpurun_out/bench_train.log
+fi

@@ -1,0 +1,266 @@
+"""Training driver: the B200 mirror of the reference's uorfNoGanModel (models/uorf_nogan_model.py:15-285).
+
+Same driver-level API (`set_input`, `forward(epoch)`, `backward`, `optimize_parameters(ret_grad, epoch)`, `compute_visuals`,
+`save_networks` / `load_networks`, attributes `loss_recon`, `loss_perc`, `x_rec{i}`, `x{i}`, `masked_raws`, `unmasked_raws`,
+`attn`) and the same option names.  One step = one scene of N views:
+
+  Encoder (cuDNN, torch autograd) -> SlotAttention (kernel 4 / 5) -> frustum sampling (kernel 1; coarse 64^3 frustum or the
+  fine-stage 64x64 crop of the 128^2 frustum, generated directly - the reference builds all 128^2 rays and slices) ->
+  fused decoder (kernel 2 / 5) -> compositing (kernel 3 / 5) -> MSE + VGG16-relu4_3 perceptual loss (torch) -> Adam.
+
+Everything runs in ray-major order, so no permute copies are made (reference :172).  Data-parallel training shards scenes
+over ranks and averages gradients with one flat NCCL all-reduce (`uorf_b200.sharded.allreduce_gradients`).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+from itertools import chain
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn, optim
+from torch.optim.lr_scheduler import LambdaLR
+
+from .eval_model import init_weights_like_reference
+from .modules import Decoder, Encoder, Projection, SlotAttention, raw2outputs
+
+
+def default_train_options(**over) -> argparse.Namespace:
+    """Option names and defaults of uorfNoGanModel.modify_commandline_options (uorf_nogan_model.py:28-55)."""
+    opt = argparse.Namespace(num_slots=8, z_dim=64, attn_iter=3, warmup_steps=1000, nss_scale=7.0, render_size=64,
+                             supervision_size=64, obj_scale=4.5, n_freq=5, n_samp=64, n_layer=3, weight_percept=0.006,
+                             percept_in=100, no_locality_epoch=300, bottom=False, input_size=64, frustum_size=64,
+                             frustum_size_fine=128, attn_decay_steps=2e5, coarse_epoch=600, near_plane=6.0, far_plane=20.0,
+                             fixed_locality=False, dens_noise=1.0, lr=3e-4, stage="coarse", n_img_each_scene=4, gpu_ids=[0],
+                             isTrain=True, vgg_weights=None)
+    for k, v in over.items():
+        setattr(opt, k, v)
+    return opt
+
+
+def exp_decay_schedule_with_warmup(optimizer, num_warmup_steps, num_decay_steps=2e5, decay_base=0.5):
+    """reference models/networks.py:815-842 (lr_policy 'warmup')"""
+    def lr_lambda(step: int):
+        if step < num_warmup_steps:
+            return float(step) / float(max(1, num_warmup_steps))
+        return decay_base ** (float(step - num_warmup_steps) / float(num_decay_steps))
+    return LambdaLR(optimizer, lr_lambda)
+
+
+def perceptual_net(weights_path: Optional[str] = None) -> nn.Module:
+    """reference models/model.py:316-324: frozen VGG16 features[:23] (through relu4_3).  The reference downloads the ImageNet
+    weights; there is no network here, so they are loaded from `weights_path` when given and randomly initialised otherwise."""
+    from torchvision.models import vgg16
+    vgg = vgg16(weights=None)
+    if weights_path:
+        vgg.load_state_dict(torch.load(weights_path, map_location="cpu"))
+    net = nn.Sequential(*list(vgg.features)[:23]).eval()
+    for p in net.parameters():
+        p.requires_grad = False
+    return net
+
+
+class uorfNoGanModel:
+    """reference models/uorf_nogan_model.py (forward :128-196, backward :223-227, optimize_parameters :229-245)."""
+
+    def __init__(self, opt, precision: str = "fp16x3", with_perceptual: bool = True):
+        self.opt = opt
+        self.gpu_ids = list(getattr(opt, "gpu_ids", [0]))
+        if not self.gpu_ids or not torch.cuda.is_available():
+            raise RuntimeError("uorf_b200 drivers need a CUDA device (gpu_ids must not be empty); there is no CPU path")
+        self.device = torch.device(f"cuda:{self.gpu_ids[0]}")
+        self.isTrain = bool(getattr(opt, "isTrain", True))
+        torch.backends.cudnn.allow_tf32 = False           # util/util.py:210-211 (set_seed)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        self.loss_names = ["recon", "perc"]
+        self.model_names = ["Encoder", "SlotAttention", "Decoder"]
+        self.with_perceptual = with_perceptual
+        if with_perceptual:
+            self.perceptual_net = perceptual_net(getattr(opt, "vgg_weights", None)).to(self.device)
+            self._vgg_mean = torch.tensor([0.485, 0.456, 0.406], device=self.device).view(1, 3, 1, 1)
+            self._vgg_std = torch.tensor([0.229, 0.224, 0.225], device=self.device).view(1, 3, 1, 1)
+        render_size = (opt.render_size, opt.render_size)
+        self.projection = Projection(device=self.device, nss_scale=opt.nss_scale,
+                                     frustum_size=[opt.frustum_size, opt.frustum_size, opt.n_samp], near=opt.near_plane,
+                                     far=opt.far_plane, render_size=render_size)
+        self.projection_fine = Projection(device=self.device, nss_scale=opt.nss_scale,
+                                          frustum_size=[opt.frustum_size_fine, opt.frustum_size_fine, opt.n_samp],
+                                          near=opt.near_plane, far=opt.far_plane, render_size=render_size)
+        z_dim = opt.z_dim
+        self.num_slots = opt.num_slots
+        self.netEncoder = init_weights_like_reference(Encoder(3, z_dim=z_dim, bottom=opt.bottom), "normal").to(self.device)
+        self.netSlotAttention = init_weights_like_reference(
+            SlotAttention(num_slots=opt.num_slots, in_dim=z_dim, slot_dim=z_dim, iters=opt.attn_iter), "normal").to(self.device)
+        self.netDecoder = init_weights_like_reference(
+            Decoder(n_freq=opt.n_freq, input_dim=6 * opt.n_freq + 3 + z_dim, z_dim=opt.z_dim, n_layers=opt.n_layer,
+                    locality_ratio=opt.obj_scale / opt.nss_scale, fixed_locality=opt.fixed_locality), "xavier").to(self.device)
+        self.netDecoder.precision = precision
+        self.netDecoder.emit = ("raws", "masked_raws", "unmasked_raws")   # the driver keeps these for its visuals (:185-196)
+        self.netDecoder.match_rng_stream = bool(getattr(opt, "match_rng_stream", False))
+        if self.isTrain:
+            self.optimizer = optim.Adam(chain(self.netEncoder.parameters(), self.netSlotAttention.parameters(),
+                                              self.netDecoder.parameters()), lr=opt.lr)
+            self.optimizers = [self.optimizer]
+            self.schedulers = [exp_decay_schedule_with_warmup(self.optimizer, opt.warmup_steps, opt.attn_decay_steps)]
+        self.L2_loss = nn.MSELoss()
+        self.slot_noise = None        # (noise_fg, noise_bg) overrides the randn draws of SlotAttention
+        self.crop_override = None     # (h0, w0) overrides the fine-stage randint draws
+        self.process_group = None     # set (with world size > 1) for data-parallel training
+
+    def parameters(self):
+        return chain(self.netEncoder.parameters(), self.netSlotAttention.parameters(), self.netDecoder.parameters())
+
+    def named_parameters(self):
+        for pre, net in (("Encoder", self.netEncoder), ("SlotAttention", self.netSlotAttention), ("Decoder", self.netDecoder)):
+            for n, p in net.named_parameters():
+                yield pre + "." + n, p
+
+    def set_input(self, input):
+        """reference :117-126 (the fg transform is inverted on the host copy when the input arrives on the CPU)"""
+        self.x = input["img_data"].to(self.device, non_blocking=True)
+        c2w = input["cam2world"]
+        self.cam2world = c2w.to(self.device, non_blocking=True)
+        src = c2w if self.opt.fixed_locality else input["azi_rot"]
+        if not self.opt.fixed_locality:
+            self.cam2world_azi = input["azi_rot"].to(self.device, non_blocking=True)
+        self.nss2cam0 = src[0:1].inverse() if src.is_cuda else src[0:1].inverse().to(self.device, non_blocking=True)
+
+    def forward(self, epoch=0):
+        opt = self.opt
+        self.weight_percept = opt.weight_percept if epoch >= opt.percept_in else 0
+        dens_noise = opt.dens_noise if (epoch <= opt.percept_in and opt.fixed_locality) else 0
+        dev = self.device
+        feature_map = self.netEncoder(F.interpolate(self.x[0:1], size=opt.input_size, mode="bilinear", align_corners=False))
+        feat = feature_map.flatten(start_dim=2).permute([0, 2, 1])
+        z_slots, attn = self.netSlotAttention(feat, noise=self.slot_noise)
+        z_slots, attn = z_slots.squeeze(0), attn.squeeze(0)
+        K = attn.shape[0]
+        cam2world = self.cam2world
+        N = cam2world.shape[0]
+        D = opt.n_samp
+        if opt.stage == "coarse":
+            coords, z_vals, ray_dir = self.projection.construct_sampling_coor(cam2world, ray_major=True)
+            x = F.interpolate(self.x, size=opt.supervision_size, mode="bilinear", align_corners=False)
+        else:
+            rs = opt.render_size
+            if self.crop_override is not None:
+                h0, w0 = int(self.crop_override[0]), int(self.crop_override[1])
+            else:   # same two device draws as the reference (:160-161); .item() is the sync the reference's slicing implies
+                start_range = opt.frustum_size_fine - rs
+                h0 = int(torch.randint(low=0, high=start_range, size=(1,), device=dev).item())
+                w0 = int(torch.randint(low=0, high=start_range, size=(1,), device=dev).item())
+            coords, z_vals, ray_dir = self.projection_fine.construct_sampling_coor(cam2world, ray_major=True, crop=(h0, w0))
+            x = self.x[:, :, h0:h0 + rs, w0:w0 + rs]
+        self.z_vals, self.ray_dir = z_vals, ray_dir
+        W = H = opt.supervision_size
+        raws, masked_raws, unmasked_raws, _ = self.netDecoder(coords, coords[None, ...].expand(K - 1, -1, -1), z_slots, self.nss2cam0,
+                                                              dens_noise=dens_noise)
+        rgb_map, _, _ = raw2outputs(raws.view(N * H * W, D, 4), z_vals, ray_dir)
+        rendered = rgb_map.view(N, H, W, 3).permute([0, 3, 1, 2])
+        x_recon = rendered * 2 - 1
+        self.loss_recon = self.L2_loss(x_recon, x)
+        if self.with_perceptual:
+            x_norm = ((x + 1) / 2 - self._vgg_mean) / self._vgg_std
+            rendered_norm = (rendered - self._vgg_mean) / self._vgg_std
+            rendered_feat, x_feat = self.perceptual_net(rendered_norm), self.perceptual_net(x_norm)
+            self.loss_perc = self.weight_percept * self.L2_loss(rendered_feat, x_feat)
+        else:
+            self.loss_perc = torch.zeros((), device=dev)
+        with torch.no_grad():
+            self.x_recon, self.rendered = x_recon.detach(), rendered.detach()
+            for i in range(min(N, opt.n_img_each_scene)):
+                setattr(self, f"x_rec{i}", x_recon[i].detach())
+                setattr(self, f"x{i}", x[i])
+            # reference shape [K,N,D,H,W,4] as views of the ray-major buffers; attn stays on the device (the reference's
+            # .cpu() at :186 is a per-step host sync that only feeds the visualiser)
+            self._masked_rm, self._unmasked_rm = masked_raws, unmasked_raws
+            self.masked_raws = masked_raws.detach().view(K, N, H, W, D, 4).permute(0, 1, 4, 2, 3, 5)
+            self.unmasked_raws = unmasked_raws.detach().view(K, N, H, W, D, 4).permute(0, 1, 4, 2, 3, 5)
+            self.attn_raw, self._feat_hw = attn.detach(), (feature_map.shape[2], feature_map.shape[3])
+
+    @property
+    def attn(self):
+        """K x 1 x H x W attention maps resized to the supervision size (reference :186-190), built on demand."""
+        H_, W_ = self._feat_hw
+        a = self.attn_raw.view(self.opt.num_slots, 1, H_, W_)
+        S = self.opt.supervision_size
+        return a if H_ == S else F.interpolate(a, size=[S, S], mode="bilinear")
+
+    def compute_visuals(self):
+        """reference :198-221: per-slot masked / unmasked renders, 2K compositing passes in two launches"""
+        with torch.no_grad():
+            K, N, D, H, W, _ = self.masked_raws.shape
+            for name, buf in (("slot", self._masked_rm), ("unmasked_slot", self._unmasked_rm)):
+                rgb_map, _, _ = raw2outputs(buf.detach().view(K * N * H * W, D, 4), self.z_vals, self.ray_dir)
+                x_recon = rgb_map.view(K, N, H, W, 3).permute([0, 1, 4, 2, 3]) * 2 - 1
+                for k in range(K):
+                    for i in range(min(N, self.opt.n_img_each_scene)):
+                        setattr(self, f"{name}{k}_view{i}", x_recon[k, i])
+            a = self.attn
+            for k in range(K):
+                setattr(self, f"slot{k}_attn", a[k] * 2 - 1)
+
+    def backward(self):
+        loss = self.loss_recon + self.loss_perc
+        loss.backward()
+        self.loss_perc = self.loss_perc / self.weight_percept if self.weight_percept > 0 else self.loss_perc
+
+    def optimize_parameters(self, ret_grad=False, epoch=0):
+        self.forward(epoch)
+        for opm in self.optimizers:
+            opm.zero_grad(set_to_none=False)
+        self.backward()
+        if self.process_group is not None:
+            from .sharded import allreduce_gradients
+            allreduce_gradients(list(self.parameters()), self.process_group)
+        layers, avg_grads = [], []
+        if ret_grad:
+            for n, p in self.named_parameters():
+                if p.grad is not None and "bias" not in n:
+                    layers.append(n.split(".", 1)[1])
+                    avg_grads.append(p.grad.abs().mean().item())
+        for opm in self.optimizers:
+            opm.step()
+        return layers, avg_grads
+
+    def update_learning_rate(self):
+        for s in self.schedulers:
+            s.step()
+
+    def get_current_losses(self):
+        return {"recon": float(self.loss_recon), "perc": float(self.loss_perc)}
+
+    # ---- checkpoints, reference base_model.py:142-201 + uorf_nogan_model.py:247-285 file names ----
+    def save_networks(self, save_dir, suffix="latest"):
+        os.makedirs(save_dir, exist_ok=True)
+        for name in self.model_names:
+            sd = {k: v.detach().cpu() for k, v in getattr(self, "net" + name).state_dict().items()}
+            torch.save(sd, os.path.join(save_dir, f"{suffix}_net_{name}.pth"))
+        for i, opm in enumerate(self.optimizers):
+            torch.save(opm.state_dict(), os.path.join(save_dir, f"{suffix}_optimizer_{i}.pth"))
+        for i, sch in enumerate(self.schedulers):
+            torch.save(sch.state_dict(), os.path.join(save_dir, f"{suffix}_lr_scheduler_{i}.pth"))
+
+    def load_networks(self, save_dir, suffix="latest", with_optimizer=True):
+        for name in self.model_names:
+            sd = torch.load(os.path.join(save_dir, f"{suffix}_net_{name}.pth"), map_location=str(self.device))
+            getattr(self, "net" + name).load_state_dict(sd, strict=False)
+        if with_optimizer and self.isTrain:
+            for i, opm in enumerate(self.optimizers):
+                p = os.path.join(save_dir, f"{suffix}_optimizer_{i}.pth")
+                if os.path.exists(p):
+                    opm.load_state_dict(torch.load(p, map_location=str(self.device)))
+            for i, sch in enumerate(self.schedulers):
+                p = os.path.join(save_dir, f"{suffix}_lr_scheduler_{i}.pth")
+                if os.path.exists(p):
+                    sch.load_state_dict(torch.load(p))
+
+    def load_networks_from_state_dicts(self, enc=None, sa=None, dec=None):
+        if enc is not None:
+            self.netEncoder.load_state_dict(enc)
+        if sa is not None:
+            self.netSlotAttention.load_state_dict(sa)
+        if dec is not None:
+            self.netDecoder.load_state_dict(dec)

@@ -56,3 +56,25 @@ def sharded_render(encode_fn: Callable[[], torch.Tensor], render_fn: Callable[[t
         full = torch.empty((cam2world.shape[0],) + tuple(local.shape[1:]), device=device, dtype=local.dtype)
         dist.all_gather_into_tensor(full, local, group=group)
     return local, (lo, hi), full
+
+
+def allreduce_gradients(params, group=None, average: bool = True) -> None:
+    """Data-parallel training: scenes are sharded over ranks, weights replicated; after backward
+    every gradient is summed over ranks with ONE flat-bucket all-reduce (0.7 - 1.9 MB fp32: latency-bound on NVLink, so
+    one message beats per-tensor calls) and divided by the world size (the step then averages the per-scene losses;
+    world size 1 reproduces the reference's one-scene step exactly)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= world
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
