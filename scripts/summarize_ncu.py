@@ -17,8 +17,10 @@ G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
 
-def launches(tag):
-    rows = list(csv.reader(open(os.path.join(G, "launches.csv"))))
+def launches(tag, fname="launches.csv", suffix="launches", cmd="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"):
+    if not os.path.exists(os.path.join(G, fname)):
+        return
+    rows = list(csv.reader(open(os.path.join(G, fname))))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr, data = rows[hi], rows[hi + 1:]
     ki, mi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -33,16 +35,18 @@ def launches(tag):
         a[1] += v
         tot += v
         n += 1
-    out = [f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`",
+    out = [f"# {tag}: ncu launch list of `{cmd}`",
            "", "`ncu --metrics gpu__time_duration.sum --clock-control none -c 200` (cold-cache, serialised: compare SHARES).",
            f"{n} launches captured, {tot:.1f} us in total.", "", "| us | launches | share | kernel |", "|---:|---:|---:|---|"]
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
         out.append(f"| {t:.1f} | {c} | {100 * t / tot:.1f}% | `{k}` |")
-    open(os.path.join(P, f"{tag}_launches.md"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(P, f"{tag}_{suffix}.md"), "w").write("\n".join(out) + "\n")
 
 
-def decoder(tag, precision):
-    rep = os.path.join(G, "prof_decoder.ncu-rep")
+def decoder(tag, precision, repname="prof_decoder.ncu-rep"):
+    rep = os.path.join(G, repname)
+    if not os.path.exists(rep):
+        return
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
@@ -65,7 +69,7 @@ def decoder(tag, precision):
     out += ["", "Warp stall reasons (PC samples, share of all samples):", "", "| reason | samples | share |", "|---|---:|---:|"]
     for h, v in sorted(stalls, key=lambda x: -x[1])[:10]:
         out.append(f"| {h.replace('smsp__pcsamp_warps_issue_stalled_', '')} | {v:.0f} | {100 * v / tot:.1f}% |")
-    open(os.path.join(P, f"{tag}_decoder_ncu.md"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(P, f"{tag}_decoder_ncu_{precision}.md"), "w").write("\n".join(out) + "\n")
     try:
         rd, wr = float(d["dram__bytes_read.sum"][1]), float(d["dram__bytes_write.sum"][1])
         mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
@@ -84,5 +88,7 @@ if __name__ == "__main__":
     prec = sys.argv[2] if len(sys.argv) > 2 else "fp16x3"
     os.makedirs(P, exist_ok=True)
     launches(tag)
+    launches(tag, "launches_train.csv", "launches_train", "python bench.py --mode train --steps 2 --warmup 1 (launches 600..1000)")
     decoder(tag, prec)
+    decoder(tag, "bf16", "prof_decoder_bf16.ncu-rep")
     print("wrote profiles/%s_*.md" % tag)
