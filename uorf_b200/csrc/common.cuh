@@ -255,6 +255,31 @@ __device__ __forceinline__ void split2(float e0, float e1, uint32_t& hi, uint32_
   }
   lo = pack2<F16>(e0 - h0, e1 - h1);
 }
+// ReLU fused into the conversion (cvt.relu): pack2_relu(e0, e1) = pack2(max(e0,0), max(e1,0)) in one instruction.
+// split2_relu rounds the hi part TOWARD ZERO, so for x >= 0 the residual x - hi is >= 0, and for x < 0 hi = 0 and the
+// residual x is negative: a second cvt.relu then yields exactly the split of max(x, 0) without any explicit max.
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2_relu(float e0, float e1) {
+  uint32_t d;
+  if (F16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+  else     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+  return d;
+}
+template <bool F16>
+__device__ __forceinline__ void split2_relu(float e0, float e1, uint32_t& hi, uint32_t& lo) {
+  if (F16) asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(e1), "f"(e0));
+  else     asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(e1), "f"(e0));
+  float h0, h1;
+  if (F16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    h0 = f.x;
+    h1 = f.y;
+  } else {
+    h0 = __uint_as_float(hi << 16);
+    h1 = __uint_as_float(hi & 0xFFFF0000u);
+  }
+  lo = pack2_relu<F16>(e0 - h0, e1 - h1);
+}
 // scalar versions for the weight image
 template <bool F16>
 __device__ __forceinline__ unsigned short to16(float v) {

@@ -138,16 +138,20 @@ __device__ __forceinline__ void epilogue32(uint32_t t_d, const float* bias, uint
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
-    const float v0 = fmaxf(__uint_as_float(r[4 * q + 0]) + b.x, 0.f);
-    const float v1 = fmaxf(__uint_as_float(r[4 * q + 1]) + b.y, 0.f);
-    const float v2 = fmaxf(__uint_as_float(r[4 * q + 2]) + b.z, 0.f);
-    const float v3 = fmaxf(__uint_as_float(r[4 * q + 3]) + b.w, 0.f);
-    if (PASSES == 3) {
-      split2<F16>(v0, v1, hi[2 * q], lo[2 * q]);
-      split2<F16>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
+    // bias, then ReLU folded into the 16-bit conversion
+    const float v0 = __uint_as_float(r[4 * q + 0]) + b.x;
+    const float v1 = __uint_as_float(r[4 * q + 1]) + b.y;
+    const float v2 = __uint_as_float(r[4 * q + 2]) + b.z;
+    const float v3 = __uint_as_float(r[4 * q + 3]) + b.w;
+    if (PASSES == 3 && F16) {
+      split2_relu<F16>(v0, v1, hi[2 * q], lo[2 * q]);
+      split2_relu<F16>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
+    } else if (PASSES == 3) {   // bf16: keep round-to-nearest on the hi part (truncation would cost one of its 16 bits)
+      split2<F16>(fmaxf(v0, 0.f), fmaxf(v1, 0.f), hi[2 * q], lo[2 * q]);
+      split2<F16>(fmaxf(v2, 0.f), fmaxf(v3, 0.f), hi[2 * q + 1], lo[2 * q + 1]);
     } else {
-      hi[2 * q] = pack2<F16>(v0, v1);
-      hi[2 * q + 1] = pack2<F16>(v2, v3);
+      hi[2 * q] = pack2_relu<F16>(v0, v1);
+      hi[2 * q + 1] = pack2_relu<F16>(v2, v3);
     }
   }
   tmem_st16(t_hhi, hi);
