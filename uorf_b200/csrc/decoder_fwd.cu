@@ -11,18 +11,21 @@
 //                   walks it through bg MLP / the K-1 fg slots.  Thread <-> TMEM lane <-> point.
 //                     3-pass modes : NCH = 2 channels x 8 warps; the two warps sharing a lane quadrant split the
 //                                    64 feature columns (TMEM: D 64 | H hi 32 | H lo 32 | P hi 24 | P lo 24 columns)
-//                     1-pass modes : NCH = 4 channels x 4 warps (TMEM: D 64 | H 32 | P 24 columns per channel)
+//                     1-pass modes : NCH = 4 channels x 4 warps (TMEM: D 64 | H 32 | P 24 | selector 8 columns per channel)
 //   warp 16 + c     MMA issuer of channel c (lane 0 issues tcgen05.mma); warp 16 also owns TMEM alloc and the weight
 //                   bulk copies.  One issuer per channel keeps the channels out of lock-step: while one channel is in
 //                   its epilogue the tensor pipe works for another.
 // Per layer:  A (activations, 16-bit hi [+lo]) lives in TMEM, written by the epilogue threads with tcgen05.st;
 //   B (weights) is a 128B-swizzled K-major tile in shared memory; D (fp32) in TMEM.
-//   epilogue --a_full mbarrier--> issuer --tcgen05.commit / d_full mbarrier--> epilogue (bias + ReLU + split).
+//   epilogue --a_full mbarrier--> issuer --tcgen05.commit / d_full mbarrier--> epilogue (ReLU + 16-bit split).
+//   Biases never touch the CUDA cores: the weight image carries a bias tile whose COLUMN j is bias vector j, the epilogue
+//   writes a one-hot "selector" K-step (8 TMEM columns) naming the next layer's bias, and the issuer appends one MMA
+//   D += selector . bias_tile^T to the layer - the accumulator the epilogue reads already contains the bias.
 // Precision: 1 pass of 16-bit operands, or 3 passes a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (fp32 accumulate);
 //   operands bf16 (range-safe, ~16 bits after the split) or fp16 (saturating, ~22 bits after the split).
 // The kernel makes two sweeps over its tiles: background MLP first (raw bg output parked in a 16 B/point
 // scratch), then the foreground MLP for slots 1..K-1 followed by the cross-slot composition.  The split
-// lets the 3-pass weight image of ONE MLP (124 KB) stay resident in shared memory.
+// lets the 3-pass weight image of ONE MLP (136 KB) stay resident in shared memory.
 #include "common.cuh"
 #include "decoder_layout.h"
 #include "../../include/uorf_b200.h"
@@ -45,7 +48,11 @@ struct Cfg {
   static constexpr int COL_HLO = 96;                    // 3-pass only
   static constexpr int COL_PHI = PASSES == 3 ? 128 : 96;
   static constexpr int COL_PLO = 160;                   // 3-pass only
+  static constexpr int COL_SEL = PASSES == 3 ? 192 : 120; // 8 columns: one-hot K-step that selects a bias column
   static constexpr int NPL = PASSES == 3 ? 2 : 1;       // weight planes
+  // bias through the tensor core (selector MMA) pays off where the epilogue is the bottleneck (1-pass modes); in the 3-pass
+  // modes the extra MMAs lengthen the dependent chain more than two FADDs per pair cost, so the bias stays in the epilogue
+  static constexpr bool BIAS_MMA = PASSES == 1;
 };
 
 struct DecFwdParams {
@@ -80,12 +87,20 @@ struct ChanBars {
 
 // positional encoding of one point, reference order [x y z | sin(2^i x..z) cos(2^i x..z)]_{i<5}
 // (model.py:261-277), zero padded to 48.  Frequencies 2,4,8,16 by angle doubling.
+// FAST: MUFU sin/cos (abs error ~5e-7 on the |x| <= 2 NSS range; one-pass modes only), else the accurate sincosf.
+template <bool FAST>
 __device__ __forceinline__ void posenc48(float x, float y, float z, float (&v)[kPosencK]) {
   v[0] = x; v[1] = y; v[2] = z;
   float s[3], c[3];
-  sincosf(x, &s[0], &c[0]);
-  sincosf(y, &s[1], &c[1]);
-  sincosf(z, &s[2], &c[2]);
+  if (FAST) {
+    __sincosf(x, &s[0], &c[0]);
+    __sincosf(y, &s[1], &c[1]);
+    __sincosf(z, &s[2], &c[2]);
+  } else {
+    sincosf(x, &s[0], &c[0]);
+    sincosf(y, &s[1], &c[1]);
+    sincosf(z, &s[2], &c[2]);
+  }
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
 #pragma unroll
@@ -128,7 +143,7 @@ __device__ __forceinline__ void posenc_store(const float (&v)[kPosencK], uint32_
   }
 }
 
-// 32 accumulator columns: D + bias -> ReLU -> 16-bit hi[/lo] -> 16 H operand columns
+// 32 accumulator columns (bias already added by the selector MMA): ReLU -> 16-bit hi[/lo] -> 16 H operand columns
 template <int PASSES, bool F16>
 __device__ __forceinline__ void epilogue32(uint32_t t_d, const float* bias, uint32_t t_hhi, uint32_t t_hlo) {
   uint32_t r[32];
@@ -137,12 +152,15 @@ __device__ __forceinline__ void epilogue32(uint32_t t_d, const float* bias, uint
   uint32_t hi[16], lo[16];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
-    // bias, then ReLU folded into the 16-bit conversion
-    const float v0 = __uint_as_float(r[4 * q + 0]) + b.x;
-    const float v1 = __uint_as_float(r[4 * q + 1]) + b.y;
-    const float v2 = __uint_as_float(r[4 * q + 2]) + b.z;
-    const float v3 = __uint_as_float(r[4 * q + 3]) + b.w;
+    // ReLU is folded into the 16-bit conversion; the bias is either already in the accumulator (selector MMA) or added here
+    float v0 = __uint_as_float(r[4 * q + 0]);
+    float v1 = __uint_as_float(r[4 * q + 1]);
+    float v2 = __uint_as_float(r[4 * q + 2]);
+    float v3 = __uint_as_float(r[4 * q + 3]);
+    if (!Cfg<PASSES>::BIAS_MMA) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
+      v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
+    }
     if (PASSES == 3 && F16) {
       split2_relu<F16>(v0, v1, hi[2 * q], lo[2 * q]);
       split2_relu<F16>(v2, v3, hi[2 * q + 1], lo[2 * q + 1]);
@@ -156,6 +174,24 @@ __device__ __forceinline__ void epilogue32(uint32_t t_d, const float* bias, uint
   }
   tmem_st16(t_hhi, hi);
   if (PASSES == 3) tmem_st16(t_hlo, lo);
+}
+
+// one-hot selector K-step (16 values -> 8 words) with 1.0 at position (bias_id & 15)
+template <bool F16>
+__device__ __forceinline__ void write_selector(uint32_t t_sel, int bias_id) {
+  const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
+  const int pos = bias_id & 15;
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = (pos >> 1) == i ? (one << ((pos & 1) * 16)) : 0u;
+  tmem_st8(t_sel, w);
+}
+
+// colour activation (tanh(x) + 1) / 2 = 1 / (1 + exp(-2x)); FAST uses ex2.approx + fast division (abs error ~1e-6)
+template <bool FAST>
+__device__ __forceinline__ float rgb_act(float x) {
+  if (FAST) return __fdividef(1.f, 1.f + __expf(-2.f * x));
+  return (tanhf(x) + 1.f) * 0.5f;
 }
 
 // ---- issuer-side helper ---------------------------------------------------------------------------
@@ -190,7 +226,6 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
   const int K = p.K;
   const int w_region = C::NPL * kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
   const float* s_params = reinterpret_cast<const float*>(smem + C::NPL * kPlaneBytes);
-  const float* s_slotb = s_params + kParamFloats;
   float4* s_stash = reinterpret_cast<float4*>(smem + ((w_region + 127) & ~127));  // [NCH][K][128]
 
   if (threadIdx.x == 0) {
@@ -259,6 +294,13 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
             {
               bool first = true;
               const uint32_t t_d = tb + C::COL_D, t_p = tb + C::COL_PHI, t_pl = tb + C::COL_PLO, t_h = tb + C::COL_HHI, t_hl = tb + C::COL_HLO;
+              if (C::BIAS_MMA && st < 6) {   // bias of this layer: D = selector . bias_tile^T  (K-step = bias_id / 16), hi [+ lo] plane
+                const int bid = st == 0 ? bias_id_slot(s, 0) : st == 3 ? bias_id_slot(s, 1) : bias_id_fixed(st < 3 ? st - 1 : st - 2);
+                const uint64_t db = make_sdesc_sw128(w_smem + kBiasTileOff) + 2 * (bid >> 4);
+                mma_ts_elect(t_d, tb + C::COL_SEL, db, idesc64, 0u);
+                if (PASSES == 3) mma_ts_elect(t_d, tb + C::COL_SEL, make_sdesc_sw128(w_smem + kPlaneBytes + kBiasTileOff) + 2 * (bid >> 4), idesc64, 1u);
+                first = false;
+              }
               switch (st) {
                 case 0: issue_ksteps<PASSES>(t_d, t_p, t_pl, w_smem + 0 * kTileBytes, 0, 3, idesc64, first); break;
                 case 1: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 1 * kTileBytes, 0, 4, idesc64, first); break;
@@ -293,13 +335,20 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
         if (tile >= p.num_tiles) break;
         const long long pt = tile * kTileM + t;
         const bool valid = pt < p.P;
+        // coordinates are fetched one slot ahead (and once per tile when all fg slots share them, fg_slot_stride == 0), so
+        // the global-load latency is off the per-slot critical path
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        if (valid) {
+          const float* src = (phase == 0 ? p.coor_bg : p.coor_fg) + pt * 3;
+          nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
+        }
         for (int s = 0; s < nslots; ++s) {
           // ---- stage 0: coordinates -> object frame -> locality flag -> positional encoding ----
-          float x = 0.f, y = 0.f, z = 0.f;
+          float x = nx, y = ny, z = nz;
           bool outside = false;
-          if (valid) {
-            const float* src = phase == 0 ? p.coor_bg + pt * 3 : p.coor_fg + (long long)s * p.fg_slot_stride + pt * 3;
-            x = __ldg(src); y = __ldg(src + 1); z = __ldg(src + 2);
+          if (valid && phase == 1 && p.fg_slot_stride != 0 && s + 1 < nslots) {
+            const float* src = p.coor_fg + (long long)(s + 1) * p.fg_slot_stride + pt * 3;
+            nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
           }
           if (phase == 1) {
             if (p.fixed_locality) outside = fabsf(x) > p.locality_ratio || fabsf(y) > p.locality_ratio || fabsf(z) > p.locality_ratio;
@@ -314,7 +363,7 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
           }
           {
             float v[kPosencK];
-            posenc48(x, y, z, v);
+            posenc48<PASSES == 1>(x, y, z, v);
             if (C::CS == 1) {
               posenc_store<PASSES, F16, 0, 24>(v, tb + C::COL_PHI, tb + C::COL_PLO);
             } else if (half == 0) {
@@ -322,13 +371,14 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
             } else {
               posenc_store<PASSES, F16, 12, 12>(v, tb + C::COL_PHI, tb + C::COL_PLO);
             }
+            if (C::BIAS_MMA && half == 0) write_selector<F16>(tb + C::COL_SEL, bias_id_slot(s, 0));
             tc_wait_st();
           }
           tc_fence_before();
           mbar_arrive(&cb.a_full);
 
           // ---- stages 1..6: hidden layers ----
-          const float* sb = s_slotb + s * kSlotBiasFloats;
+          const float* sb = s_params + kParamFloats + s * kSlotBiasFloats;
 #pragma unroll 1
           for (int st = 1; st <= 6; ++st) {
             const float* bias = (st == 1 ? sb : st == 2 ? s_params + kPB1 : st == 3 ? s_params + kPB2
@@ -341,6 +391,9 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
               const int c32 = col0 + 32 * h32;   // first accumulator column of this 32-column block
               epilogue32<PASSES, F16>(tb + C::COL_D + c32, bias + 32 * h32, tb + C::COL_HHI + c32 / 2, tb + C::COL_HLO + c32 / 2);
             }
+            // selector for the bias of the layer the next MMA stage (index st) computes; the head (st == 6) keeps its bias here
+            if (C::BIAS_MMA && half == 0 && st < 6)
+              write_selector<F16>(tb + C::COL_SEL, st == 3 ? bias_id_slot(s, 1) : bias_id_fixed(st < 3 ? st - 1 : st - 2));
             tc_wait_st();
             tc_fence_before();
             mbar_arrive(&cb.a_full);
@@ -397,9 +450,9 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
             const float dens = fmaxf(rw.w, 0.f);
             const float m = dens / denom;
             float4 u;
-            u.x = (tanhf(rw.x) + 1.f) * 0.5f;
-            u.y = (tanhf(rw.y) + 1.f) * 0.5f;
-            u.z = (tanhf(rw.z) + 1.f) * 0.5f;
+            u.x = rgb_act<PASSES == 1>(rw.x);
+            u.y = rgb_act<PASSES == 1>(rw.y);
+            u.z = rgb_act<PASSES == 1>(rw.z);
             u.w = dens;
             if (p.noise != nullptr && valid) u.w = dens + p.dens_noise * __ldg(p.noise + (long long)k * p.P + pt);
             const float4 mk = make_float4(u.x * m, u.y * m, u.z * m, u.w * m);

@@ -10,6 +10,9 @@
 //     tile 7 at 7*kTileBytes        : 32 head rows x 64 K
 //        fg: rows 0..Z/4-1 = f_color.0 . f_after_latent (folded), row 16 = f_after_shape
 //        bg: rows 0..3     = b_after.6
+//     bias tile at kBiasTileOff     : 64 feature rows x 64 K; COLUMN j is bias vector j, added to the accumulator by one
+//        extra MMA whose A operand is a one-hot "selector" K-step (forward kernel):
+//        j = 0..3 : before.2, before.4, after.2, after.4 ;  j = 16+2s / 17+2s : the hoisted biases of slot s (before.0 / after.0)
 //   params (fp32, kParamFloats) : b_before.2, b_before.4, b_after.2, b_after.4 (64 each, zero padded),
 //        head bias [32], f_color.2 weight [3][16], f_color.2 bias [4 (3 used)]
 //   slot biases (fp32) : per slot s: bias0[64] = before.0.bias + before.0[:, 33:] . z_s
@@ -23,7 +26,10 @@ constexpr int kPosencK = 48;       // padded to a multiple of the MMA K (16)
 constexpr int kZPad = 64;          // hidden width the kernels run at (z_dim <= 64, zero padded)
 constexpr int kTileBytes = 64 * 128;
 constexpr int kHeadTileBytes = 32 * 128;
-constexpr int kPlaneBytes = 7 * kTileBytes + kHeadTileBytes;  // 61440
+constexpr int kBiasTileOff = 7 * kTileBytes + kHeadTileBytes;              // 61440
+constexpr int kPlaneBytes = kBiasTileOff + kTileBytes;                     // 69632
+__host__ __device__ constexpr int bias_id_fixed(int which) { return which; }              // 0..3
+__host__ __device__ constexpr int bias_id_slot(int s, int which) { return 16 + 2 * s + which; }   // which: 0 before.0, 1 after.0
 constexpr int kParamFloats = 352;
 constexpr int kParamBytes = kParamFloats * 4;                 // 1408
 constexpr int kSlotBiasFloats = 128;

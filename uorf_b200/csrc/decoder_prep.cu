@@ -28,7 +28,7 @@ __device__ __forceinline__ void put(unsigned char* plane0, int passes, int f16, 
   }
 }
 
-// grid: x = 0..7 tile, y = 0 (bg) / 1 (fg);   x = 8: params;   x = 9..: slot biases
+// grid: x = 0..7 tile, y = 0 (bg) / 1 (fg);   x = 8: params;   x = 9: bias tile;   x = 10..: slot biases
 __global__ void decoder_prep_kernel(PrepArgs a) {
   const int fg = blockIdx.y;
   const int Z = a.Z;
@@ -109,9 +109,30 @@ __global__ void decoder_prep_kernel(PrepArgs a) {
       }
       prm[e] = v;
     }
+  } else if (bx == 9) {
+    // bias tile: column j holds bias vector j (see decoder_layout.h)
+    unsigned char* tile = img + kBiasTileOff;
+    const int nslots = fg ? a.K - 1 : 1;
+    for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+      const int n = e >> 6, j = e & 63;
+      float v = 0.f;
+      if (n < Z) {
+        if (j < 4) {
+          v = j == 0 ? before_b[1][n] : j == 1 ? before_b[2][n] : j == 2 ? after_b[1][n] : after_b[2][n];
+        } else if (j >= 16 && (j - 16) / 2 < nslots && (j - 16) / 2 < 15) {
+          const int s = (j - 16) / 2, which = (j - 16) & 1;
+          const float* z = a.z_slots + (fg ? (s + 1) : 0) * Z;
+          const float* wrow = which == 0 ? before_w[0] + n * I + kPosenc : after_w[0] + n * (I + Z) + kPosenc;
+          float acc = which == 0 ? before_b[0][n] : after_b[0][n];
+          for (int c = 0; c < Z; ++c) acc = fmaf(wrow[c], z[c], acc);
+          v = acc;
+        }
+      }
+      put(tile, a.passes, a.f16, sw128_off(n, j), v);
+    }
   } else {
-    // slot biases: block (bx - 9) = slot index within this image
-    const int s = bx - 9;
+    // slot biases (fp32, read by the backward kernel): block (bx - 10) = slot index within this image
+    const int s = bx - 10;
     const int nslots = fg ? a.K - 1 : 1;
     if (s >= nslots) return;
     const float* z = a.z_slots + (fg ? (s + 1) : 0) * Z;
@@ -140,7 +161,7 @@ int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int
   a.passes = passes;
   a.f16 = f16;
   a.image = static_cast<unsigned char*>(image);
-  dim3 grid(9 + (K - 1 > 1 ? K - 1 : 1), 2);
+  dim3 grid(10 + (K - 1 > 1 ? K - 1 : 1), 2);
   decoder_prep_kernel<<<grid, 256, 0, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }

@@ -16,6 +16,7 @@ namespace uorf {
 
 constexpr int kSaTok = 32;      // tokens per CTA in the token-parallel passes
 constexpr int kSaThreads = 256;
+constexpr int kSaSlotThreads = 1024;   // per-slot CTAs: more warps = more weight rows in flight (latency-bound matvecs)
 constexpr int kSaMaxC = 64;
 constexpr int kSaMaxK = 16;
 constexpr int kSaMaxHid = 128;
@@ -125,7 +126,7 @@ __device__ __forceinline__ void slot_query(const SaParams& p, int k, const float
 }
 
 // ---- slot initialisation + first query; one CTA per slot -------------------------------------------
-__global__ void __launch_bounds__(kSaThreads) sa_init_kernel(const SaParams p) {
+__global__ void __launch_bounds__(kSaSlotThreads) sa_init_kernel(const SaParams p) {
   __shared__ float s_slot[kSaMaxC], s_ln[kSaMaxC], s_q[kSaMaxC];
   const int k = blockIdx.x, C = p.C, K = p.K;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -189,21 +190,21 @@ __global__ void __launch_bounds__(kSaThreads) sa_attn_kernel(const SaParams p) {
 }
 
 // ---- pass C (per iteration): reduce partials, GRUCell, residual MLP, next query; one CTA per slot ------
-__global__ void __launch_bounds__(kSaThreads) sa_update_kernel(const SaParams p, int nblk, int it) {
+__global__ void __launch_bounds__(kSaSlotThreads) sa_update_kernel(const SaParams p, int nblk, int it) {
   __shared__ float s_u[kSaMaxC], s_h[kSaMaxC], s_g[6 * kSaMaxC], s_n[kSaMaxC], s_ln[kSaMaxC], s_m[kSaMaxHid], s_o[kSaMaxC];
-  __shared__ float s_red[kSaThreads / 32][kSaMaxC + 1];
+  __shared__ float s_red[kSaSlotThreads / 32][kSaMaxC + 1];
   const int C = p.C, K = p.K, Hd = p.hidden, k = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // fixed-order reduction of the per-CTA partials: warp w sums blocks w, w+8, ...; then the 8 warp sums in order
+  // fixed-order reduction of the per-CTA partials: warp w sums blocks w, w+32, ...; then the 32 warp sums in order
   for (int c = lane; c <= C; c += 32) {
     float acc = 0.f;
-    for (int b = warp; b < nblk; b += kSaThreads / 32) acc += p.partial[((long long)b * K + k) * (C + 1) + c];
+    for (int b = warp; b < nblk; b += kSaSlotThreads / 32) acc += p.partial[((long long)b * K + k) * (C + 1) + c];
     s_red[warp][c] = acc;
   }
   __syncthreads();
   if (threadIdx.x <= C) {
     float acc = 0.f;
-    for (int w = 0; w < kSaThreads / 32; ++w) acc += s_red[w][threadIdx.x];
+    for (int w = 0; w < kSaSlotThreads / 32; ++w) acc += s_red[w][threadIdx.x];
     s_red[0][threadIdx.x] = acc;
   }
   __syncthreads();
@@ -264,10 +265,10 @@ int launch_slot_attention(const uorf_slot_attention_weights* w, const float* fea
   p.slots = slots;
   p.attn = attn;
   sa_kv_kernel<<<nblk, kSaThreads, 0, stream>>>(p);
-  sa_init_kernel<<<K, kSaThreads, 0, stream>>>(p);
+  sa_init_kernel<<<K, kSaSlotThreads, 0, stream>>>(p);
   for (int it = 0; it < iters; ++it) {
     sa_attn_kernel<<<nblk, kSaThreads, 0, stream>>>(p);
-    sa_update_kernel<<<K, kSaThreads, 0, stream>>>(p, nblk, it);
+    sa_update_kernel<<<K, kSaSlotThreads, 0, stream>>>(p, nblk, it);
   }
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }

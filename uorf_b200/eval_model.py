@@ -66,6 +66,7 @@ class uorfEvalModel:
         # the reference runs fp32 convolutions / matmuls with TF32 disabled (util/util.py:210-211, set_seed)
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.benchmark = True             # as the reference's set_seed does
         self.layout = layout
         self.model_names = ["Encoder", "SlotAttention", "Decoder"]
         render_size = (opt.render_size, opt.render_size)

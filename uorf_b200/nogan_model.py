@@ -74,6 +74,7 @@ class uorfNoGanModel:
         self.isTrain = bool(getattr(opt, "isTrain", True))
         torch.backends.cudnn.allow_tf32 = False           # util/util.py:210-211 (set_seed)
         torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.benchmark = True             # as the reference's set_seed does
         self.loss_names = ["recon", "perc"]
         self.model_names = ["Encoder", "SlotAttention", "Decoder"]
         self.with_perceptual = with_perceptual
