@@ -277,7 +277,7 @@ def test_no_cpu_fallback():
 # ------------------------------------------------------------------------------------------------------
 # eval driver (uorf_eval_model.py:116-157 + compute_visuals:181-193) against the live-reference golden
 # ------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("layout", ["reference", "native"])
+@pytest.mark.parametrize("layout", ["reference", "native", "native+graph"])
 def test_eval_driver_golden(layout):
     from uorf_b200.eval_model import uorfEvalModel, default_eval_options
     g = load_golden("eval_driver")
@@ -285,10 +285,15 @@ def test_eval_driver_golden(layout):
                                n_img_each_scene=2, gpu_ids=[0])
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    m = uorfEvalModel(opt, layout=layout, precision="fp16x3").eval()
+    m = uorfEvalModel(opt, layout=layout.split("+")[0], precision="fp16x3").eval()
     m.load_networks_from_state_dicts(g["enc"], g["sa"], g["dec"])
     m.slot_noise = (g["noise_fg"].to(dev()), g["noise_bg"].to(dev()))
-    m.set_input({"img_data": g["img"], "cam2world": g["cam2world"], "azi_rot": g["azi_rot"], "paths": []})
+    inp = {"img_data": g["img"], "cam2world": g["cam2world"], "azi_rot": g["azi_rot"], "paths": []}
+    m.set_input(inp)
+    if layout.endswith("+graph"):      # whole forward captured into a CUDA graph, then replayed on fresh inputs
+        m.enable_cuda_graph()
+        m.forward()
+        m.set_input(inp)
     m.test()
     x_recon = torch.stack([m.x_rec0, m.x_rec1])
     assert maxerr(x_recon, g["x_recon"]) < FP32_TOL                       # rendered RGB in [-1,1]

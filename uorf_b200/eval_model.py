@@ -153,7 +153,44 @@ class uorfEvalModel:
         return dict(rendered=rendered, depth=depth_map.view(N, H, W), masked=masked, unmasked=unmasked, z_vals=z_vals,
                     ray_dir=ray_dir)
 
+    # ---- CUDA graph: the whole forward (about 60 small launches around the decoder) replayed as one graph launch ----
+    def enable_cuda_graph(self, enabled: bool = True):
+        """After this, forward() captures itself into a CUDA graph on its first call (shapes must then stay fixed) and
+        replays the graph afterwards; inputs are copied into static buffers by forward(), outputs live in the graph's pool."""
+        self._graph_enabled = enabled
+        self._graph = None
+        return self
+
+    def _forward_graphed(self):
+        cur = torch.cuda.current_stream(self.device)
+        if self._graph is None:
+            self._static = {"x": self.x.clone(), "cam2world": self.cam2world.clone(), "nss2cam0": self.nss2cam0.clone()}
+            self.x, self.cam2world, self.nss2cam0 = self._static["x"], self._static["cam2world"], self._static["nss2cam0"]
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._forward_impl()
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._forward_impl()
+            self._graph = g
+        else:
+            st = self._static
+            if self.x.data_ptr() != st["x"].data_ptr():
+                st["x"].copy_(self.x, non_blocking=True)
+                st["cam2world"].copy_(self.cam2world, non_blocking=True)
+                st["nss2cam0"].copy_(self.nss2cam0, non_blocking=True)
+                self.x, self.cam2world, self.nss2cam0 = st["x"], st["cam2world"], st["nss2cam0"]
+        self._graph.replay()
+
     def forward(self, epoch=0):
+        if getattr(self, "_graph_enabled", False):
+            return self._forward_graphed()
+        return self._forward_impl()
+
+    def _forward_impl(self, epoch=0):
         with torch.no_grad():
             opt = self.opt
             nss2cam0 = self.nss2cam0
