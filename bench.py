@@ -258,11 +258,11 @@ def run_b200(args):
     ev = model.netDecoder.events
     model.netDecoder.events = None
     dec_ms = sum(a.elapsed_time(b) for a, b in ev) / max(len(ev), 1)
-    # keep the device busy until the sampler has a few readings under load (not part of any reported number)
-    t_end = time.time() + 1.0
-    while time.time() < t_end and sampler.ok and len(sampler.samples) < 40:
+    # keep the device busy for ~1 s so the sampler has readings under load (not part of any reported number); the number of
+    # extra steps derives from the all-reduced time, so every rank runs the same count (the steps contain collectives)
+    for _ in range(int(min(400, 1000.0 / max(ms_total / args.steps, 1e-3))) + 1):
         step(resident)
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
     clocks = sampler.stop()
     if use_graph:
         model.enable_cuda_graph()
@@ -378,10 +378,9 @@ def run_train(args):
         step(resident)
     sampler.start()
     ms_total = timed(lambda: step(resident), args.steps)
-    t_end = time.time() + 1.0
-    while time.time() < t_end and sampler.ok and len(sampler.samples) < 40:
+    for _ in range(int(min(400, 1000.0 / max(ms_total / args.steps, 1e-3))) + 1):   # same count on every rank (collectives inside)
         step(resident)
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
     clocks = sampler.stop()
 
     def e2e_step():
@@ -400,7 +399,7 @@ def run_train(args):
                 "config": dict(c, step="Encoder+SlotAttention+sampling+decoder+compositing fwd+bwd, MSE + VGG16-relu4_3 perceptual "
                                "(random-init VGG, weight 0 at epoch 0 exactly as the reference computes it), Adam",
                                parallelism=f"scene-sharded data parallel x{world}, one flat gradient all-reduce (NCCL)",
-                               loss_last=float(model.loss_recon)),
+                               loss_last=float(model.loss_recon.detach())),
                 "clocks": clocks,
                 "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "scene-steps/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
