@@ -209,6 +209,8 @@ def run_b200(args):
     K, Z = c["K"], c["z_dim"]
     out_host = torch.empty(hi - lo, 3, c["frustum"], c["frustum"]).pin_memory()
 
+    graph_on = [True]
+
     def step(inputs):
         model.set_input(inputs)
         if world == 1:
@@ -217,7 +219,7 @@ def run_b200(args):
         with torch.no_grad():
             z = model.encode()[0] if rank == 0 else None
             z = sharded.broadcast_slots(z, K, Z, dev)
-            out = model.render(z, model.cam2world, model.nss2cam0)
+            out = (model.render if (args.no_graph or not graph_on[0]) else model.render_graphed)(z, model.cam2world, model.nss2cam0)
             return out["rendered"] * 2 - 1
 
     def barrier():
@@ -251,12 +253,14 @@ def run_b200(args):
     # (events cannot be recorded inside a replayed graph); same stream, same inputs, same launch configuration
     if use_graph:
         model.enable_cuda_graph(False)
+    graph_on[0] = False
     model.netDecoder.events = []
     for _ in range(args.steps):
         step(resident)
     torch.cuda.synchronize()
     ev = model.netDecoder.events
     model.netDecoder.events = None
+    graph_on[0] = True
     dec_ms = sum(a.elapsed_time(b) for a, b in ev) / max(len(ev), 1)
     # keep the device busy for ~1 s so the sampler has readings under load (not part of any reported number); the number of
     # extra steps derives from the all-reduced time, so every rank runs the same count (the steps contain collectives)
@@ -296,7 +300,8 @@ def run_b200(args):
                 "dtype": args.precision + " (tensor-core operands; fp32 accumulate, fp32 elsewhere)", "data": "synthetic",
                 "config": dict(c, n_views_total=n_total, sharding=f"views over {world} rank(s), slot latents broadcast from rank 0",
                                layout="native ray-major, raws+masked+unmasked materialised",
-                               launch="forward replayed as one CUDA graph" if use_graph else "eager launches",
+                               launch=("eager launches" if args.no_graph else "forward replayed as one CUDA graph" if world == 1
+                                       else "rank 0: encoder + slot attention eager, NCCL broadcast; render replayed as a CUDA graph"),
                                l2="no flush: each step streams ~0.8 GB of outputs per GPU (>> 126 MB L2)",
                                weights="random init, seed 2021"),
                 "clocks": clocks,

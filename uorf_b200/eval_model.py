@@ -185,6 +185,31 @@ class uorfEvalModel:
                 self.x, self.cam2world, self.nss2cam0 = st["x"], st["cam2world"], st["nss2cam0"]
         self._graph.replay()
 
+    def render_graphed(self, z_slots, cam2world, nss2cam0):
+        """render() replayed as a CUDA graph (captured on first use; shapes must stay fixed).  Used by the ray-sharded
+        multi-GPU path, where the slot latents arrive by broadcast and only the render is rank-local."""
+        cur = torch.cuda.current_stream(self.device)
+        st = getattr(self, "_render_static", None)
+        if st is None:
+            st = {"z": z_slots.clone(), "c2w": cam2world.clone(), "T": nss2cam0.clone()}
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(2):
+                    self.render(st["z"], st["c2w"], st["T"])
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g), torch.no_grad():
+                st["out"] = self.render(st["z"], st["c2w"], st["T"])
+            st["graph"] = g
+            self._render_static = st
+        else:
+            st["z"].copy_(z_slots, non_blocking=True)
+            st["c2w"].copy_(cam2world, non_blocking=True)
+            st["T"].copy_(nss2cam0, non_blocking=True)
+        st["graph"].replay()
+        return st["out"]
+
     def forward(self, epoch=0):
         if getattr(self, "_graph_enabled", False):
             return self._forward_graphed()
