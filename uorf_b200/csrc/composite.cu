@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __rest
 
 static int composite_grid(long long R, int num_sms) {
   long long blocks = (R + 7) / 8;  // 8 warps (rays) per 256-thread block
-  const long long cap = (long long)num_sms * 8;
+  const long long cap = (long long)num_sms * 64;   // 8 resident CTAs per SM x 8 waves: enough rays in flight to cover HBM latency
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
 }

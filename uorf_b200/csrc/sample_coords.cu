@@ -23,17 +23,19 @@ struct CoordParams {
   float* ray_dir;
 };
 
+// IdxT = unsigned for every realistic frustum (< 2^32 samples): 32-bit div/mod is several times cheaper than 64-bit
+template <typename IdxT>
 __global__ void __launch_bounds__(256) sample_coords_kernel(const CoordParams p) {
-  const long long per_chunk = (long long)p.N * p.D * p.Hc * p.Wc;
-  const long long rays_per_chunk = (long long)p.N * p.Hc * p.Wc;
-  const long long total = per_chunk * p.scale * p.scale;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const IdxT per_chunk = (IdxT)p.N * p.D * p.Hc * p.Wc;
+  const IdxT rays_per_chunk = (IdxT)p.N * p.Hc * p.Wc;
+  const IdxT total = per_chunk * p.scale * p.scale;
+  const IdxT idx = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
 
   // ---- coords ----
   {
     const int chunk = (int)(idx / per_chunk);
-    long long q = idx - (long long)chunk * per_chunk;
+    IdxT q = idx - (IdxT)chunk * per_chunk;
     int n, d, hc, wc;
     if (p.ray_major) {
       d = (int)(q % p.D); q /= p.D;
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(256) sample_coords_kernel(const CoordParams p)
                             fmaf(__ldg(C + r * 4 + 2), cam[2], fmaf(__ldg(C + r * 4 + 1), cam[1], __ldg(C + r * 4) * cam[0])));
       out[r] = wv * p.inv_nss;
     }
-    float* dst = p.coords + idx * 3;
+    float* dst = p.coords + (long long)idx * 3;
     dst[0] = out[0];
     dst[1] = out[1];
     dst[2] = out[2];
@@ -74,13 +76,13 @@ __global__ void __launch_bounds__(256) sample_coords_kernel(const CoordParams p)
   // ---- ray_dir: [chunk][ray][3]; the first rays_total threads each write one ray ----
   if (p.ray_dir && idx < rays_per_chunk * p.scale * p.scale) {
     const int chunk = (int)(idx / rays_per_chunk);
-    long long q = idx - (long long)chunk * rays_per_chunk;
+    IdxT q = idx - (IdxT)chunk * rays_per_chunk;
     const int wc = (int)(q % p.Wc); q /= p.Wc;
     const int hc = (int)(q % p.Hc);
     const int h0 = p.crop_h >= 0 ? p.crop_h : chunk / p.scale;
     const int w0 = p.crop_w >= 0 ? p.crop_w : chunk % p.scale;
     const float x = (float)(w0 + wc * p.scale), y = (float)(h0 + hc * p.scale);
-    float* dst = p.ray_dir + idx * 3;
+    float* dst = p.ray_dir + (long long)idx * 3;
 #pragma unroll
     for (int r = 0; r < 3; ++r) dst[r] = fmaf(p.S[r * 4 + 2], 1.f, fmaf(p.S[r * 4 + 1], y, p.S[r * 4] * x));
   }
@@ -102,7 +104,8 @@ int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float*
   const long long total = (long long)n_views * f->D * Hc * Wc * scale * scale;
   if (total == 0) return UORF_OK;
   const long long blocks = (total + 255) / 256;
-  sample_coords_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  if (total < (1LL << 32) - 256) sample_coords_kernel<unsigned><<<(unsigned)blocks, 256, 0, stream>>>(p);
+  else sample_coords_kernel<unsigned long long><<<(unsigned)blocks, 256, 0, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
 
