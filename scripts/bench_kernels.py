@@ -23,7 +23,13 @@ def timeit(fn, n=50):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e-3
 out = {}
-t = timeit(lambda: pr.construct_sampling_coor(c2w, ray_major=True))
+import ctypes as C
+from uorf_b200 import _lib
+co = torch.empty(P, 3, device=dev); zo = torch.empty(R, D, device=dev); ro = torch.empty(R, 3, device=dev)
+def coords_kernel_only():      # the C-ABI call alone, outputs preallocated (no allocator / wrapper work in the timed loop)
+    _lib.check(_lib.lib().uorf_sample_coords(C.byref(pr._frustum), pr._z_cam.data_ptr(), c2w.data_ptr(), N, 1, -1, -1, F_, F_, 1,
+                                             co.data_ptr(), zo.data_ptr(), ro.data_ptr(), None), "coords")
+t = timeit(coords_kernel_only)
 bytes_ = P * 16 + R * 12          # coords 12 B + z_vals 4 B per sample, ray_dir 12 B per ray
 out["sample_coords"] = dict(us=t * 1e6, algorithmic_bytes=bytes_, GBps=bytes_ / t / 1e9, frac_of_measured_hbm=bytes_ / t / 1e9 / pk["hbm"])
 nbuf = 3                           # rotating buffers: each launch reads data that left L2 long ago
@@ -46,5 +52,12 @@ t_fb = timeit(comp_bwd, 60)
 bytes_b = R * D * (16 + 4 + 16) + R * 24
 out["composite_fwd_plus_bwd"] = dict(us=t_fb * 1e6, note="forward + backward launch pair", bwd_algorithmic_bytes=bytes_b,
                                      bwd_GBps_estimate=bytes_b / max(t_fb - t, 1e-9) / 1e9)
+big = torch.empty(256 * 1024 * 1024, device=dev)       # 1 GiB fp32
+t_w = timeit(lambda: big.fill_(1.0), 20)
+out["context_write_only_fill_GBps"] = big.numel() * 4 / t_w / 1e9
+src = torch.empty_like(big)
+t_c = timeit(lambda: big.copy_(src), 20)
+out["context_copy_GBps"] = 2 * big.numel() * 4 / t_c / 1e9
+out["sample_coords"]["frac_of_write_only_fill"] = out["sample_coords"]["GBps"] / out["context_write_only_fill_GBps"]
 out["peak_hbm_GBps"] = pk["hbm"]; out["peak_source"] = pk["src"]; out["n_views"] = N
 print(json.dumps(out, indent=1))

@@ -11,7 +11,7 @@
 
 namespace uorf {
 int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float* cam2world, int n_views, int scale, int crop_h,
-                         int crop_w, int Hc, int Wc, int ray_major, float* coords, float* z_vals, float* ray_dir,
+                         int crop_w, int Hc, int Wc, int ray_major, float* coords, float* z_vals, float* ray_dir, int num_sms,
                          cudaStream_t stream);
 int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int K, int Z, int passes, int f16, void* image,
                         cudaStream_t stream);
@@ -146,7 +146,7 @@ int uorf_sample_coords(const uorf_frustum* f, const float* z_cam, const float* c
     return fail(UORF_ERR_ARG, "uorf_sample_coords: Hc*scale != H or Wc*scale != W%s");
   }
   return check_launch(uorf::launch_sample_coords(f, z_cam, cam2world, n_views, scale, crop ? crop_h : -1, crop ? crop_w : -1, Hc, Wc,
-                                                 ray_major, coords, z_vals, ray_dir, static_cast<cudaStream_t>(stream)),
+                                                 ray_major, coords, z_vals, ray_dir, c->num_sms, static_cast<cudaStream_t>(stream)),
                       "uorf_sample_coords");
 }
 

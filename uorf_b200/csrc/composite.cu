@@ -4,105 +4,120 @@
 //   alpha_i = 1 - exp(-sigma_i * delta_i);  T_i = prod_{j<i} (1 - alpha_j + 1e-10);  w_i = alpha_i * T_i
 //   rgb_map = sum_i w_i rgb_i;  weights_norm = (w + 1e-5) / sum(w + 1e-5) [detached];  depth = sum wn_i z_i
 //   mask_map = sum_i w_i sigma_i   (render_mask)
-// One warp per ray; lane l owns samples l, l+32, ...; the transmittance is an exclusive product scan
-// (shuffle-based, carried across the 32-sample chunks).  HBM-bound: 24 B per sample + 28 B per ray.
+// A ray is owned by a group of L lanes (L = power of two <= 32, several rays per warp when D is small); every lane holds S
+// CONSECUTIVE samples (S = 4, or 8 for D > 128), which it loads as S contiguous float4 (64-128 B per lane, 1-4 KB per
+// warp).  The transmittance is an exclusive product scan: sequential inside a lane, a log2(L)-step segmented shuffle scan
+// across the group; the ray sums are segmented butterfly reductions.  HBM-bound: 24 B per sample + 28 B per ray.
 #include "common.cuh"
 
 namespace uorf {
 
-constexpr int kMaxChunks = 8;  // D <= 256
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-// inclusive product scan across the warp
-__device__ __forceinline__ float warp_scan_mul(float v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const float u = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v *= u;
-  }
-  return v;
-}
-// inclusive suffix-sum scan across the warp (lane l gets sum over lanes >= l)
-__device__ __forceinline__ float warp_rscan_add(float v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const float u = __shfl_down_sync(0xffffffffu, v, o);
-    if (lane + o < 32) v += u;
-  }
+__device__ __forceinline__ float group_sum(float v, int L) {
+  for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
+// loads the S samples [i0, i0+S) of ray r and the geometry they need; out-of-range samples get neutral values
+template <int S>
+__device__ __forceinline__ void load_samples(const float4* __restrict__ raw, const float* __restrict__ zz, long long roff, int i0, int D,
+                                             bool active, bool vec_z, float4 (&v)[S], float (&z)[S + 1]) {
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    const int i = i0 + j;
+    v[j] = (active && i < D) ? __ldg(raw + roff + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (vec_z && active && i0 + S <= D) {
+#pragma unroll
+    for (int q = 0; q < S / 4; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(zz + i0) + q);
+      z[4 * q] = t.x; z[4 * q + 1] = t.y; z[4 * q + 2] = t.z; z[4 * q + 3] = t.w;
+    }
+    z[S] = (i0 + S < D) ? __ldg(zz + i0 + S) : 0.f;
+  } else {
+#pragma unroll
+    for (int j = 0; j <= S; ++j) z[j] = (active && i0 + j < D) ? __ldg(zz + i0 + j) : 0.f;
+  }
+}
+
+template <int S>
 __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
-                                                            const float* __restrict__ rays_d, long long R, long long Rg, int D,
+                                                            const float* __restrict__ rays_d, long long R, long long Rg, int D, int L, int vec,
                                                             float* __restrict__ rgb_map, float* __restrict__ depth_map,
                                                             float* __restrict__ weights_norm, float* __restrict__ mask_map) {
   const int lane = threadIdx.x & 31;
+  const int sub = lane & (L - 1);          // lane within the ray's group
+  const int rpw = 32 / L;                  // rays per warp
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int nchunks = (D + 31) >> 5;
-  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
-    const long long rg = r % Rg;  // geometry (z_vals, rays_d) may be shared by several stacked ray sets
-    const float dx = __ldg(rays_d + rg * 3), dy = __ldg(rays_d + rg * 3 + 1), dz = __ldg(rays_d + rg * 3 + 2);
-    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
-    const float4* rr = raw + r * D;
-    const float* zz = z_vals + rg * D;
-    float w[kMaxChunks], zv[kMaxChunks];
-    float carry = 1.f;  // product of (1 - alpha + 1e-10) over all previous chunks
+  const bool vec_z = vec != 0;   // D % 4 == 0 and 16-byte aligned z_vals / weights_norm: float4 accesses
+  const int i0 = sub * S;
+  for (long long wi = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi * rpw < R; wi += warps) {
+    const long long r = wi * rpw + lane / L;
+    const bool active = r < R;
+    const long long rg = active ? r % Rg : 0;   // geometry (z_vals, rays_d) may be shared by several stacked ray sets
+    float nrm = 0.f;
+    if (active) {
+      const float dx = __ldg(rays_d + rg * 3), dy = __ldg(rays_d + rg * 3 + 1), dz = __ldg(rays_d + rg * 3 + 2);
+      nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+    float4 v[S];
+    float z[S + 1];
+    load_samples<S>(raw, z_vals + rg * D, active ? r * D : 0, i0, D, active, vec_z, v, z);
+    float w[S], texc[S];
+    float lane_prod = 1.f;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      const int i = i0 + j;
+      const bool in = active && i < D;
+      const float delta = ((i + 1 < D) ? (z[j + 1] - z[j]) : 1e-2f) * nrm;
+      const float alpha = in ? 1.f - expf(-v[j].w * delta) : 0.f;
+      texc[j] = lane_prod;                 // product of the terms before sample j inside this lane
+      lane_prod *= in ? (1.f - alpha + 1e-10f) : 1.f;
+      w[j] = alpha;
+    }
+    // exclusive product over the previous lanes of the group
+    float inc = lane_prod;
+    for (int o = 1; o < L; o <<= 1) {
+      const float u = __shfl_up_sync(0xffffffffu, inc, o, L);
+      if (sub >= o) inc *= u;
+    }
+    float exc = __shfl_up_sync(0xffffffffu, inc, 1, L);
+    if (sub == 0) exc = 1.f;
     float ar = 0.f, ag = 0.f, ab = 0.f, am = 0.f, sw = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-      w[c] = 0.f;
-      zv[c] = 0.f;
-      if (c < nchunks) {
-        const int i = c * 32 + lane;
-        const bool in = i < D;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        float z0 = 0.f, z1 = 0.f;
-        if (in) {
-          v = __ldg(rr + i);
-          z0 = __ldg(zz + i);
-          z1 = (i + 1 < D) ? __ldg(zz + i + 1) : 0.f;
-        }
-        const float delta = ((i + 1 < D) ? (z1 - z0) : 1e-2f) * nrm;
-        const float alpha = in ? 1.f - expf(-v.w * delta) : 0.f;
-        const float term = in ? (1.f - alpha + 1e-10f) : 1.f;
-        const float inc = warp_scan_mul(term, lane);
-        float exc = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) exc = 1.f;
-        const float T = carry * exc;
-        carry *= __shfl_sync(0xffffffffu, inc, 31);
-        const float wi = alpha * T;
-        w[c] = wi;
-        zv[c] = z0;
-        ar += wi * v.x;
-        ag += wi * v.y;
-        ab += wi * v.z;
-        am += wi * v.w;
-        if (in) sw += wi + 1e-5f;
-      }
+    for (int j = 0; j < S; ++j) {
+      const float wi_ = w[j] * (exc * texc[j]);
+      w[j] = wi_;
+      ar += wi_ * v[j].x;
+      ag += wi_ * v[j].y;
+      ab += wi_ * v[j].z;
+      am += wi_ * v[j].w;
+      if (active && i0 + j < D) sw += wi_ + 1e-5f;
     }
-    ar = warp_sum(ar);
-    ag = warp_sum(ag);
-    ab = warp_sum(ab);
-    sw = warp_sum(sw);
+    ar = group_sum(ar, L);
+    ag = group_sum(ag, L);
+    ab = group_sum(ab, L);
+    sw = group_sum(sw, L);
+    if (mask_map) am = group_sum(am, L);
     float dep = 0.f;
+    float wn[S];
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-      if (c < nchunks) {
-        const int i = c * 32 + lane;
-        if (i < D) {
-          const float wn = (w[c] + 1e-5f) / sw;
-          dep += wn * zv[c];
-          if (weights_norm) weights_norm[r * D + i] = wn;
-        }
+    for (int j = 0; j < S; ++j) {
+      wn[j] = (active && i0 + j < D) ? (w[j] + 1e-5f) / sw : 0.f;
+      dep += wn[j] * z[j];
+    }
+    dep = group_sum(dep, L);
+    if (weights_norm && active) {
+      float* dst = weights_norm + r * D + i0;
+      if (vec_z && i0 + S <= D) {
+#pragma unroll
+        for (int q = 0; q < S / 4; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(wn[4 * q], wn[4 * q + 1], wn[4 * q + 2], wn[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < S; ++j)
+          if (i0 + j < D) dst[j] = wn[j];
       }
     }
-    dep = warp_sum(dep);
-    if (mask_map) am = warp_sum(am);
-    if (lane == 0) {
+    if (sub == 0 && active) {
       rgb_map[r * 3] = ar;
       rgb_map[r * 3 + 1] = ag;
       rgb_map[r * 3 + 2] = ab;
@@ -114,70 +129,95 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
 
 // grad of rgb_map w.r.t. raw:  d rgb_i = g * w_i ;  G_i = g . rgb_i ;  S_i = sum_{m>i} G_m w_m ;
 //   d alpha_i = G_i T_i - S_i / (1 - alpha_i + 1e-10) ;  d sigma_i = d alpha_i * delta_i * exp(-sigma_i delta_i)
+template <int S>
 __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
                                                             const float* __restrict__ rays_d, const float* __restrict__ grad_rgb,
-                                                            long long R, long long Rg, int D, float4* __restrict__ grad_raw) {
+                                                            long long R, long long Rg, int D, int L, int vec, float4* __restrict__ grad_raw) {
   const int lane = threadIdx.x & 31;
+  const int sub = lane & (L - 1);
+  const int rpw = 32 / L;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int nchunks = (D + 31) >> 5;
-  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
-    const long long rg = r % Rg;  // geometry (z_vals, rays_d) may be shared by several stacked ray sets
-    const float dx = __ldg(rays_d + rg * 3), dy = __ldg(rays_d + rg * 3 + 1), dz = __ldg(rays_d + rg * 3 + 2);
-    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
-    const float g0 = __ldg(grad_rgb + r * 3), g1 = __ldg(grad_rgb + r * 3 + 1), g2 = __ldg(grad_rgb + r * 3 + 2);
-    const float4* rr = raw + r * D;
-    const float* zz = z_vals + rg * D;
-    float w[kMaxChunks], T[kMaxChunks], term[kMaxChunks], G[kMaxChunks], de[kMaxChunks];
-    float carry = 1.f;
-#pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-      w[c] = T[c] = G[c] = de[c] = 0.f;
-      term[c] = 1.f;
-      if (c < nchunks) {
-        const int i = c * 32 + lane;
-        const bool in = i < D;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        float z0 = 0.f, z1 = 0.f;
-        if (in) {
-          v = __ldg(rr + i);
-          z0 = __ldg(zz + i);
-          z1 = (i + 1 < D) ? __ldg(zz + i + 1) : 0.f;
-        }
-        const float delta = ((i + 1 < D) ? (z1 - z0) : 1e-2f) * nrm;
-        const float e = in ? expf(-v.w * delta) : 1.f;
-        const float alpha = 1.f - e;
-        const float tm = in ? (1.f - alpha + 1e-10f) : 1.f;
-        const float inc = warp_scan_mul(tm, lane);
-        float exc = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) exc = 1.f;
-        T[c] = carry * exc;
-        carry *= __shfl_sync(0xffffffffu, inc, 31);
-        w[c] = in ? alpha * T[c] : 0.f;
-        term[c] = tm;
-        G[c] = g0 * v.x + g1 * v.y + g2 * v.z;
-        de[c] = delta * e;
-      }
+  const bool vec_z = vec != 0;   // D % 4 == 0 and 16-byte aligned z_vals / weights_norm: float4 accesses
+  const int i0 = sub * S;
+  for (long long wi = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi * rpw < R; wi += warps) {
+    const long long r = wi * rpw + lane / L;
+    const bool active = r < R;
+    const long long rg = active ? r % Rg : 0;
+    float nrm = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (active) {
+      const float dx = __ldg(rays_d + rg * 3), dy = __ldg(rays_d + rg * 3 + 1), dz = __ldg(rays_d + rg * 3 + 2);
+      nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+      g0 = __ldg(grad_rgb + r * 3); g1 = __ldg(grad_rgb + r * 3 + 1); g2 = __ldg(grad_rgb + r * 3 + 2);
     }
-    float tail = 0.f;  // sum of G*w over all later chunks
+    float4 v[S];
+    float z[S + 1];
+    load_samples<S>(raw, z_vals + rg * D, active ? r * D : 0, i0, D, active, vec_z, v, z);
+    float alpha[S], term[S], texc[S], de[S];
+    float lane_prod = 1.f;
 #pragma unroll
-    for (int c = kMaxChunks - 1; c >= 0; --c) {
-      if (c < nchunks) {
-        const int i = c * 32 + lane;
-        const float gw = G[c] * w[c];
-        const float incl = warp_rscan_add(gw, lane);
-        const float S = tail + incl - gw;
-        tail += __shfl_sync(0xffffffffu, incl, 0);
-        if (i < D) {
-          const float dalpha = G[c] * T[c] - S / term[c];
-          grad_raw[r * D + i] = make_float4(g0 * w[c], g1 * w[c], g2 * w[c], dalpha * de[c]);
+    for (int j = 0; j < S; ++j) {
+      const int i = i0 + j;
+      const bool in = active && i < D;
+      const float delta = ((i + 1 < D) ? (z[j + 1] - z[j]) : 1e-2f) * nrm;
+      const float e = in ? expf(-v[j].w * delta) : 1.f;
+      alpha[j] = 1.f - e;
+      term[j] = in ? (1.f - alpha[j] + 1e-10f) : 1.f;
+      de[j] = delta * e;
+      texc[j] = lane_prod;
+      lane_prod *= term[j];
+    }
+    float inc = lane_prod;
+    for (int o = 1; o < L; o <<= 1) {
+      const float u = __shfl_up_sync(0xffffffffu, inc, o, L);
+      if (sub >= o) inc *= u;
+    }
+    float exc = __shfl_up_sync(0xffffffffu, inc, 1, L);
+    if (sub == 0) exc = 1.f;
+    // suffix sums of G*w: sequential inside the lane (from the last sample), segmented reverse scan across the group
+    float T[S], w[S], G[S], gw_after[S];
+    float lane_gw = 0.f;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      T[j] = exc * texc[j];
+      w[j] = (active && i0 + j < D) ? alpha[j] * T[j] : 0.f;
+      G[j] = g0 * v[j].x + g1 * v[j].y + g2 * v[j].z;
+    }
+#pragma unroll
+    for (int j = S - 1; j >= 0; --j) {
+      gw_after[j] = lane_gw;               // sum over the later samples of this lane
+      lane_gw += G[j] * w[j];
+    }
+    float rinc = lane_gw;                  // inclusive suffix sum over lanes >= sub of the group
+    for (int o = 1; o < L; o <<= 1) {
+      const float u = __shfl_down_sync(0xffffffffu, rinc, o, L);
+      if (sub + o < L) rinc += u;
+    }
+    const float later = rinc - lane_gw;    // lanes after this one
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        if (i0 + j < D) {
+          const float Ssum = later + gw_after[j];
+          const float dalpha = G[j] * T[j] - Ssum / term[j];
+          grad_raw[r * D + i0 + j] = make_float4(g0 * w[j], g1 * w[j], g2 * w[j], dalpha * de[j]);
         }
       }
     }
   }
 }
 
-static int composite_grid(long long R, int num_sms) {
-  long long blocks = (R + 7) / 8;  // 8 warps (rays) per 256-thread block
+static void composite_shape(int D, int& S, int& L) {
+  S = D > 128 ? 8 : 4;
+  const int need = (D + S - 1) / S;
+  L = 1;
+  while (L < need) L <<= 1;
+}
+static int composite_vec(int D, const void* a, const void* b) {
+  return ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0) ? 1 : 0;
+}
+static int composite_grid(long long R, int L, int num_sms) {
+  const long long rays_per_block = 8LL * (32 / L);
+  long long blocks = (R + rays_per_block - 1) / rays_per_block;
   const long long cap = (long long)num_sms * 64;   // 8 resident CTAs per SM x 8 waves: enough rays in flight to cover HBM latency
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
@@ -186,16 +226,32 @@ static int composite_grid(long long R, int num_sms) {
 int launch_composite_fwd(const float* raw, const float* z_vals, const float* rays_d, long long R, long long Rg, int D, float* rgb_map,
                          float* depth_map, float* weights_norm, float* mask_map, int num_sms, cudaStream_t stream) {
   if (R == 0) return UORF_OK;
-  composite_fwd_kernel<<<composite_grid(R, num_sms), 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, R, Rg, D,
-                                                                       rgb_map, depth_map, weights_norm, mask_map);
+  int S, L;
+  composite_shape(D, S, L);
+  const int grid = composite_grid(R, L, num_sms);
+  const int vec = composite_vec(D, z_vals, weights_norm);
+  if (S == 4)
+    composite_fwd_kernel<4><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, R, Rg, D, L, vec, rgb_map, depth_map,
+                                                      weights_norm, mask_map);
+  else
+    composite_fwd_kernel<8><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, R, Rg, D, L, vec, rgb_map, depth_map,
+                                                      weights_norm, mask_map);
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
 
 int launch_composite_bwd(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb, long long R, long long Rg, int D,
                          float* grad_raw, int num_sms, cudaStream_t stream) {
   if (R == 0) return UORF_OK;
-  composite_bwd_kernel<<<composite_grid(R, num_sms), 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, grad_rgb,
-                                                                       R, Rg, D, reinterpret_cast<float4*>(grad_raw));
+  int S, L;
+  composite_shape(D, S, L);
+  const int grid = composite_grid(R, L, num_sms);
+  const int vec = composite_vec(D, z_vals, nullptr);
+  if (S == 4)
+    composite_bwd_kernel<4><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, grad_rgb, R, Rg, D, L, vec,
+                                                      reinterpret_cast<float4*>(grad_raw));
+  else
+    composite_bwd_kernel<8><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, grad_rgb, R, Rg, D, L, vec,
+                                                      reinterpret_cast<float4*>(grad_raw));
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
 

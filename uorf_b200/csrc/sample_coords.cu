@@ -3,12 +3,17 @@
 //   pixel grid (x, y, depth index) -> [x*z, y*z, z, 1] -> spixel2cam -> cam2world[n] -> world2nss (1/nss_scale),
 //   z_vals = (z_cam - near) / (far - near), ray_dir = spixel2cam[:3,:3] . [x, y, 1],
 //   optional strided partition into scale^2 ray chunks (projection.py:71-77) or a crop window
-//   (uorf_nogan_model.py:153-165).  HBM-bound: ~16 B written per sample, inputs are a few hundred bytes.
-// One thread per sample; all three outputs are written with unit-stride across the warp.
+//   (uorf_nogan_model.py:153-165).  HBM-bound (write-only): 16 B per sample + 12 B per ray; inputs are a few hundred bytes.
+// Persistent CTAs (a multiple of the SM count) loop over groups of 256 consecutive samples: the per-depth tables and the
+// camera matrices are staged in shared memory once per CTA, and the xyz triples of a group are staged through shared
+// memory so that global stores are full 16-byte, unit-stride vectors (a direct 12-byte-stride store would touch every
+// 32-byte sector three times).
 #include "common.cuh"
 #include "../../include/uorf_b200.h"
 
 namespace uorf {
+
+constexpr int kMaxStagedViews = 64;
 
 struct CoordParams {
   float S[16];   // spixel2cam
@@ -18,78 +23,174 @@ struct CoordParams {
   float near_plane, inv_range_den;  // z_vals = (z - near) / den
   int W, H, D, N;
   int scale, crop_h, crop_w, Hc, Wc, ray_major;
+  int sh_d, sh_w, sh_h;   // log2 of D, Wc, Hc when they are powers of two (index math by shifts), else -1
   float* coords;
   float* z_vals;
   float* ray_dir;
 };
 
-// IdxT = unsigned for every realistic frustum (< 2^32 samples): 32-bit div/mod is several times cheaper than 64-bit
+// IdxT = unsigned for every realistic frustum (< 2^32 samples): 32-bit index math is several times cheaper than 64-bit
 template <typename IdxT>
 __global__ void __launch_bounds__(256) sample_coords_kernel(const CoordParams p) {
+  __shared__ __align__(16) float s_xyz[2][256 * 3];
+  __shared__ float s_zc[256], s_zv[256];                 // z_cam and normalised z_vals per depth index (D <= 256)
+  __shared__ float s_c2w[kMaxStagedViews][12];           // rows 0..2 of every view's cam2world
   const IdxT per_chunk = (IdxT)p.N * p.D * p.Hc * p.Wc;
   const IdxT rays_per_chunk = (IdxT)p.N * p.Hc * p.Wc;
   const IdxT total = per_chunk * p.scale * p.scale;
-  const IdxT idx = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+  const IdxT rays_total = rays_per_chunk * p.scale * p.scale;
+  const bool ztab = p.D <= 256;
+  const bool cstage = p.N <= kMaxStagedViews;
+  const bool pow2 = p.sh_d >= 0 && p.sh_w >= 0 && p.sh_h >= 0;
+  if (ztab && (int)threadIdx.x < p.D) {
+    const float zc = __ldg(p.z_cam + threadIdx.x);
+    s_zc[threadIdx.x] = zc;
+    s_zv[threadIdx.x] = (zc - p.near_plane) / p.inv_range_den;
+  }
+  if (cstage)
+    for (int e = threadIdx.x; e < p.N * 12; e += blockDim.x) s_c2w[e / 12][e % 12] = __ldg(p.cam2world + (e / 12) * 16 + e % 12);
+  __syncthreads();
 
-  // ---- coords ----
-  {
-    const int chunk = (int)(idx / per_chunk);
-    IdxT q = idx - (IdxT)chunk * per_chunk;
-    int n, d, hc, wc;
-    if (p.ray_major) {
-      d = (int)(q % p.D); q /= p.D;
-      wc = (int)(q % p.Wc); q /= p.Wc;
-      hc = (int)(q % p.Hc); n = (int)(q / p.Hc);
-    } else {
-      wc = (int)(q % p.Wc); q /= p.Wc;
-      hc = (int)(q % p.Hc); q /= p.Hc;
-      d = (int)(q % p.D); n = (int)(q / p.D);
+  const IdxT ngroups = (total + 255) / 256;
+  int buf = 0;
+  for (IdxT g = blockIdx.x; g < ngroups; g += gridDim.x, buf ^= 1) {
+    const IdxT idx = g * 256 + threadIdx.x;
+    const bool live = idx < total;
+    if (live) {
+      // ---- coords ----
+      const int chunk = p.scale == 1 ? 0 : (int)(idx / per_chunk);
+      IdxT q = idx - (IdxT)chunk * per_chunk;
+      int n, d, hc, wc;
+      if (p.ray_major && pow2) {
+        d = (int)(q & (IdxT)(p.D - 1)); q >>= p.sh_d;
+        wc = (int)(q & (IdxT)(p.Wc - 1)); q >>= p.sh_w;
+        hc = (int)(q & (IdxT)(p.Hc - 1)); n = (int)(q >> p.sh_h);
+      } else if (pow2) {
+        wc = (int)(q & (IdxT)(p.Wc - 1)); q >>= p.sh_w;
+        hc = (int)(q & (IdxT)(p.Hc - 1)); q >>= p.sh_h;
+        d = (int)(q & (IdxT)(p.D - 1)); n = (int)(q >> p.sh_d);
+      } else if (p.ray_major) {
+        d = (int)(q % p.D); q /= p.D;
+        wc = (int)(q % p.Wc); q /= p.Wc;
+        hc = (int)(q % p.Hc); n = (int)(q / p.Hc);
+      } else {
+        wc = (int)(q % p.Wc); q /= p.Wc;
+        hc = (int)(q % p.Hc); q /= p.Hc;
+        d = (int)(q % p.D); n = (int)(q / p.D);
+      }
+      const int h0 = p.crop_h >= 0 ? p.crop_h : chunk / p.scale;
+      const int w0 = p.crop_w >= 0 ? p.crop_w : chunk % p.scale;
+      const int h = h0 + hc * p.scale, w = w0 + wc * p.scale;
+      const float zc = ztab ? s_zc[d] : __ldg(p.z_cam + d);
+      const float p0 = (float)w * zc, p1 = (float)h * zc, p2 = zc;
+      float cam[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        cam[r] = fmaf(p.S[r * 4 + 3], 1.f, fmaf(p.S[r * 4 + 2], p2, fmaf(p.S[r * 4 + 1], p1, p.S[r * 4] * p0)));
+      const float* Cg = p.cam2world + n * 16;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float c0 = cstage ? s_c2w[n][r * 4 + 0] : __ldg(Cg + r * 4 + 0);
+        const float c1 = cstage ? s_c2w[n][r * 4 + 1] : __ldg(Cg + r * 4 + 1);
+        const float c2 = cstage ? s_c2w[n][r * 4 + 2] : __ldg(Cg + r * 4 + 2);
+        const float c3 = cstage ? s_c2w[n][r * 4 + 3] : __ldg(Cg + r * 4 + 3);
+        const float wv = fmaf(c3, cam[3], fmaf(c2, cam[2], fmaf(c1, cam[1], c0 * cam[0])));
+        s_xyz[buf][threadIdx.x * 3 + r] = wv * p.inv_nss;   // stride 3 is coprime with the 32 banks: conflict-free
+      }
+      // ---- z_vals: [chunk][ray][D]; identical for every ray, so the flat index idx maps onto it directly ----
+      if (p.z_vals) {
+        const int dz = p.sh_d >= 0 ? (int)(idx & (IdxT)(p.D - 1)) : (int)(idx % p.D);
+        p.z_vals[idx] = ztab ? s_zv[dz] : (__ldg(p.z_cam + dz) - p.near_plane) / p.inv_range_den;
+      }
+      // ---- ray_dir: [chunk][ray][3]; the first rays_total flat indices each write one ray ----
+      if (p.ray_dir && idx < rays_total) {
+        const int rchunk = p.scale == 1 ? 0 : (int)(idx / rays_per_chunk);
+        IdxT qr = idx - (IdxT)rchunk * rays_per_chunk;
+        int rwc, rhc;
+        if (pow2) { rwc = (int)(qr & (IdxT)(p.Wc - 1)); rhc = (int)((qr >> p.sh_w) & (IdxT)(p.Hc - 1)); }
+        else { rwc = (int)(qr % p.Wc); qr /= p.Wc; rhc = (int)(qr % p.Hc); }
+        const int rh0 = p.crop_h >= 0 ? p.crop_h : rchunk / p.scale;
+        const int rw0 = p.crop_w >= 0 ? p.crop_w : rchunk % p.scale;
+        const float x = (float)(rw0 + rwc * p.scale), y = (float)(rh0 + rhc * p.scale);
+        float* dst = p.ray_dir + (long long)idx * 3;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) dst[r] = fmaf(p.S[r * 4 + 2], 1.f, fmaf(p.S[r * 4 + 1], y, p.S[r * 4] * x));
+      }
     }
-    const int h0 = p.crop_h >= 0 ? p.crop_h : chunk / p.scale;
-    const int w0 = p.crop_w >= 0 ? p.crop_w : chunk % p.scale;
-    const int h = h0 + hc * p.scale, w = w0 + wc * p.scale;
-    const float zc = __ldg(p.z_cam + d);
-    const float p0 = (float)w * zc, p1 = (float)h * zc, p2 = zc;
-    float cam[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-      cam[r] = fmaf(p.S[r * 4 + 3], 1.f, fmaf(p.S[r * 4 + 2], p2, fmaf(p.S[r * 4 + 1], p1, p.S[r * 4] * p0)));
-    const float* C = p.cam2world + n * 16;
-    float out[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const float wv = fmaf(__ldg(C + r * 4 + 3), cam[3],
-                            fmaf(__ldg(C + r * 4 + 2), cam[2], fmaf(__ldg(C + r * 4 + 1), cam[1], __ldg(C + r * 4) * cam[0])));
-      out[r] = wv * p.inv_nss;
+    __syncthreads();   // s_xyz[buf] complete; the other buffer was drained before the previous barrier
+    {
+      const IdxT first = g * 256;                                  // 768 floats = 3072 B per group: 16 B aligned
+      const IdxT n_here = total - first < (IdxT)256 ? total - first : (IdxT)256;
+      float* dst = p.coords + (long long)first * 3;
+      if (n_here == (IdxT)256 && (reinterpret_cast<uintptr_t>(p.coords) & 15) == 0) {
+        if (threadIdx.x < 192) reinterpret_cast<float4*>(dst)[threadIdx.x] = reinterpret_cast<const float4*>(s_xyz[buf])[threadIdx.x];
+      } else {
+        for (unsigned e = threadIdx.x; e < (unsigned)n_here * 3; e += blockDim.x) dst[e] = s_xyz[buf][e];
+      }
     }
-    float* dst = p.coords + (long long)idx * 3;
-    dst[0] = out[0];
-    dst[1] = out[1];
-    dst[2] = out[2];
   }
-  // ---- z_vals: [chunk][ray][D]; identical for every ray, so the flat index idx maps onto it directly ----
-  if (p.z_vals) {
-    const int d = (int)(idx % p.D);
-    p.z_vals[idx] = (__ldg(p.z_cam + d) - p.near_plane) / p.inv_range_den;
+}
+
+// Fast path for the layout the B200 drivers use (ray-major, D % 4 == 0, unpartitioned or cropped): one thread produces FOUR
+// consecutive depth samples of one ray, so the pixel / view decode and the 12 camera-matrix reads are shared by 4 samples and
+// every store is a 16-byte vector (3 x float4 of xyz, 1 x float4 of z_vals) - no shared-memory staging needed.
+// Arithmetic per sample is unchanged (same FMA chain as the general kernel).
+__global__ void __launch_bounds__(256) sample_coords_rm4_kernel(const CoordParams p) {
+  __shared__ float s_zc[256], s_zv[256];
+  __shared__ float s_c2w[kMaxStagedViews][12];
+  const bool ztab = p.D <= 256;
+  const bool cstage = p.N <= kMaxStagedViews;
+  if (ztab && (int)threadIdx.x < p.D) {
+    const float zc = __ldg(p.z_cam + threadIdx.x);
+    s_zc[threadIdx.x] = zc;
+    s_zv[threadIdx.x] = (zc - p.near_plane) / p.inv_range_den;
   }
-  // ---- ray_dir: [chunk][ray][3]; the first rays_total threads each write one ray ----
-  if (p.ray_dir && idx < rays_per_chunk * p.scale * p.scale) {
-    const int chunk = (int)(idx / rays_per_chunk);
-    IdxT q = idx - (IdxT)chunk * rays_per_chunk;
-    const int wc = (int)(q % p.Wc); q /= p.Wc;
-    const int hc = (int)(q % p.Hc);
-    const int h0 = p.crop_h >= 0 ? p.crop_h : chunk / p.scale;
-    const int w0 = p.crop_w >= 0 ? p.crop_w : chunk % p.scale;
-    const float x = (float)(w0 + wc * p.scale), y = (float)(h0 + hc * p.scale);
-    float* dst = p.ray_dir + (long long)idx * 3;
+  if (cstage)
+    for (int e = threadIdx.x; e < p.N * 12; e += blockDim.x) s_c2w[e / 12][e % 12] = __ldg(p.cam2world + (e / 12) * 16 + e % 12);
+  __syncthreads();
+  const int dq = p.D >> 2;                                    // quads per ray
+  const long long rays = (long long)p.N * p.Hc * p.Wc;
+  const long long nquads = rays * dq;
+  for (long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x; qi < nquads; qi += (long long)gridDim.x * blockDim.x) {
+    const long long ray = qi / dq;
+    const int d0 = (int)(qi - ray * dq) * 4;
+    const int wc = (int)(ray % p.Wc);
+    const long long t2 = ray / p.Wc;
+    const int hc = (int)(t2 % p.Hc), n = (int)(t2 / p.Hc);
+    const int h = (p.crop_h >= 0 ? p.crop_h : 0) + hc, w = (p.crop_w >= 0 ? p.crop_w : 0) + wc;
+    float c[12];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) dst[r] = fmaf(p.S[r * 4 + 2], 1.f, fmaf(p.S[r * 4 + 1], y, p.S[r * 4] * x));
+    for (int e = 0; e < 12; ++e) c[e] = cstage ? s_c2w[n][e] : __ldg(p.cam2world + n * 16 + e);
+    float xyz[12], zv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = d0 + j;
+      const float zc = ztab ? s_zc[d] : __ldg(p.z_cam + d);
+      zv[j] = ztab ? s_zv[d] : (zc - p.near_plane) / p.inv_range_den;
+      const float p0 = (float)w * zc, p1 = (float)h * zc, p2 = zc;
+      float cam[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        cam[r] = fmaf(p.S[r * 4 + 3], 1.f, fmaf(p.S[r * 4 + 2], p2, fmaf(p.S[r * 4 + 1], p1, p.S[r * 4] * p0)));
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        xyz[3 * j + r] = fmaf(c[r * 4 + 3], cam[3], fmaf(c[r * 4 + 2], cam[2], fmaf(c[r * 4 + 1], cam[1], c[r * 4] * cam[0]))) * p.inv_nss;
+    }
+    float4* dst = reinterpret_cast<float4*>(p.coords + qi * 12);
+    dst[0] = make_float4(xyz[0], xyz[1], xyz[2], xyz[3]);
+    dst[1] = make_float4(xyz[4], xyz[5], xyz[6], xyz[7]);
+    dst[2] = make_float4(xyz[8], xyz[9], xyz[10], xyz[11]);
+    if (p.z_vals) reinterpret_cast<float4*>(p.z_vals)[qi] = make_float4(zv[0], zv[1], zv[2], zv[3]);
+    if (p.ray_dir && d0 == 0) {
+      const float x = (float)w, y = (float)h;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) p.ray_dir[ray * 3 + r] = fmaf(p.S[r * 4 + 2], 1.f, fmaf(p.S[r * 4 + 1], y, p.S[r * 4] * x));
+    }
   }
 }
 
 int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float* cam2world, int n_views, int scale, int crop_h,
-                         int crop_w, int Hc, int Wc, int ray_major, float* coords, float* z_vals, float* ray_dir,
+                         int crop_w, int Hc, int Wc, int ray_major, float* coords, float* z_vals, float* ray_dir, int num_sms,
                          cudaStream_t stream) {
   CoordParams p;
   for (int i = 0; i < 16; ++i) p.S[i] = f->spixel2cam[i];
@@ -101,10 +202,19 @@ int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float*
   p.W = f->W; p.H = f->H; p.D = f->D; p.N = n_views;
   p.scale = scale; p.crop_h = crop_h; p.crop_w = crop_w; p.Hc = Hc; p.Wc = Wc; p.ray_major = ray_major;
   p.coords = coords; p.z_vals = z_vals; p.ray_dir = ray_dir;
+  auto lg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; };
+  p.sh_d = lg(f->D); p.sh_w = lg(Wc); p.sh_h = lg(Hc);
   const long long total = (long long)n_views * f->D * Hc * Wc * scale * scale;
   if (total == 0) return UORF_OK;
-  const long long blocks = (total + 255) / 256;
-  if (total < (1LL << 32) - 256) sample_coords_kernel<unsigned><<<(unsigned)blocks, 256, 0, stream>>>(p);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms * 8;   // persistent: 8 resident CTAs per SM
+  if (blocks > cap) blocks = cap;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(coords) | reinterpret_cast<uintptr_t>(z_vals)) & 15) == 0;
+  if (ray_major && scale == 1 && (f->D & 3) == 0 && aligned) {
+    long long b4 = (total / 4 + 255) / 256;
+    if (b4 > cap) b4 = cap;
+    sample_coords_rm4_kernel<<<(unsigned)b4, 256, 0, stream>>>(p);
+  } else if (total < (1LL << 32) - 512) sample_coords_kernel<unsigned><<<(unsigned)blocks, 256, 0, stream>>>(p);
   else sample_coords_kernel<unsigned long long><<<(unsigned)blocks, 256, 0, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }

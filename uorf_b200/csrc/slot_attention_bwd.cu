@@ -22,6 +22,7 @@ namespace uorf {
 
 constexpr int kBTok = 32;
 constexpr int kBThreads = 256;
+constexpr int kBSlotThreads = 1024;   // per-slot CTAs: latency-bound matvecs, more warps = more weight rows in flight
 constexpr int kBMaxC = 64;
 constexpr int kBMaxK = 16;
 constexpr int kBMaxHid = 128;
@@ -138,7 +139,7 @@ __device__ __forceinline__ void b_ln_bwd(const float* dy, const float* xhat, con
 // do_q : query-path backward of iteration it_q (needs dq_part from the token pass of that iteration); adds into dS
 // do_a : MLP / GRU backward of iteration it_a, consuming dS (= d slot_out of it_a) -> dU, dS (= d slot_in via the GRU state)
 // order inside one launch: do_q first (it completes d slot_in of iteration it_q = d slot_out of it_a = it_q - 1)
-__global__ void __launch_bounds__(kBThreads) sa_bwd_slot_kernel(const SabParams p, int do_q, int it_q, int do_a, int it_a, int first) {
+__global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabParams p, int do_q, int it_q, int do_a, int it_a, int first) {
   __shared__ float s_a[kBMaxC], s_b[kBMaxC], s_c[kBMaxC], s_d[kBMaxC], s_e[kBMaxC], s_f[kBMaxC], s_xh[kBMaxC], s_ds[kBMaxC];
   __shared__ float s_g[6 * kBMaxC], s_dg[6 * kBMaxC], s_m[kBMaxHid], s_dm[kBMaxHid];
   __shared__ float s_stat[2];
@@ -482,10 +483,10 @@ int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_s
   for (int it = iters - 1; it >= 0; --it) {
     const bool last = it == iters - 1;
     // query path of iteration it+1 (if any) + MLP/GRU of iteration it
-    sa_bwd_slot_kernel<<<K, kBThreads, 0, stream>>>(p, last ? 0 : 1, it + 1, 1, it, last ? 1 : 0);
+    sa_bwd_slot_kernel<<<K, kBSlotThreads, 0, stream>>>(p, last ? 0 : 1, it + 1, 1, it, last ? 1 : 0);
     sa_bwd_token_kernel<<<nblk, kBThreads, 0, stream>>>(p, it);
   }
-  sa_bwd_slot_kernel<<<K, kBThreads, 0, stream>>>(p, 1, 0, 0, 0, 0);   // query path of iteration 0 -> d slot_0
+  sa_bwd_slot_kernel<<<K, kBSlotThreads, 0, stream>>>(p, 1, 0, 0, 0, 0);   // query path of iteration 0 -> d slot_0
   sa_bwd_feat_kernel<<<nblk, kBThreads, 0, stream>>>(p);
   sa_bwd_reduce_kernel<<<32, 256, 0, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
