@@ -158,6 +158,45 @@ def cpu_reference_run(steps: int, warmup: int, views_sample: int = 1):
     return units / dt, dt, cores, f"{views_sample} of {c['n_views']} views per step ({units} sample-slots), oracle eval_render, {cores} threads"
 
 
+def eager_gpu_run(dev, reps: int = 3):
+    """The as-written algorithm (oracle decoder_forward + the permute copy + composite: ~93 % of the reference's render path,
+    SURVEY 8(a)) executed as stock torch eager ops on the GPU, TF32 off like the reference: what running the reference's own
+    modules on this B200 would cost for one of the 4 chunks of the bench workload.  A baseline leg like cpu_baseline."""
+    from oracle import uorf_oracle as O
+    c = CFG
+    K, Z, N, D, rs = c["K"], c["z_dim"], c["n_views"], c["n_samp"], c["render_size"]
+    _, c2w, azi = synthetic_scene(N, c["load_size"])
+    spec = O.FrustumSpec([c["frustum"], c["frustum"], D], near=6.0, far=20.0, nss_scale=7.0, render_size=rs)
+    coords, zv, rd = O.sampling_coords(spec, c2w, partitioned=True)
+    coor, zv0, rd0 = coords[0].to(dev), zv[0].to(dev), rd[0].to(dev)
+    dec_p = {k: v.to(dev) for k, v in O.init_decoder_params(Z).items()}
+    g = torch.Generator().manual_seed(11)
+    slots = torch.randn(K, Z, generator=g).to(dev)
+    T = azi[0:1].inverse().to(dev)
+    noise = torch.zeros(K, coor.shape[0], 1, device=dev)
+
+    def one():
+        with torch.no_grad():
+            raws, masked, unmasked, _ = O.decoder_forward(dec_p, coor, coor[None].expand(K - 1, -1, -1), slots, T, locality=False,
+                                                          locality_ratio=4.5 / 7.0, noise=noise)
+            raws = raws.view(N, D, rs, rs, 4).permute(0, 2, 3, 1, 4).flatten(0, 2)
+            return O.composite(raws, zv0, rd0)
+    one()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        one()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    units = coor.shape[0] * K
+    torch.cuda.empty_cache()
+    return {"value": units / (ms * 1e-3), "unit": UNIT, "ms": ms,
+            "sample": f"1 of {(c['frustum'] // rs) ** 2} chunks ({units} sample-slots): oracle decoder_forward + permute + composite as torch "
+                      "eager fp32 (TF32 off) on cuda, encoder/slot attention/sampling excluded"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -317,6 +356,10 @@ def run_b200(args):
         if not args.no_cpu_baseline and world == 1:
             v, dt, cores, sample = cpu_reference_run(1, 0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            try:
+                line["cpu_baseline"]["eager_gpu"] = eager_gpu_run(dev)
+            except Exception as e:   # a baseline leg must never take the product line down with it
+                line["cpu_baseline"]["eager_gpu"] = {"error": repr(e)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

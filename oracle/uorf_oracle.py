@@ -279,10 +279,10 @@ def decoder_forward(p: Params, coor_bg: Tensor, coor_fg: Tensor, z_slots: Tensor
 def composite(raw: Tensor, z_vals: Tensor, rays_d: Tensor, render_mask: bool = False):
     """raw RxDx4, z_vals RxD, rays_d Rx3 -> rgb_map Rx3, depth_map R, weights_norm RxD [, mask_map R]."""
     R = raw.shape[0]
-    delta = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full((R, 1), 1e-2, dtype=raw.dtype)], dim=1)
+    delta = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full((R, 1), 1e-2, dtype=raw.dtype, device=raw.device)], dim=1)
     delta = delta * rays_d.norm(dim=-1, keepdim=True)
     alpha = 1.0 - torch.exp(-raw[..., 3] * delta)
-    trans = torch.cumprod(torch.cat([torch.ones(R, 1, dtype=raw.dtype), 1.0 - alpha + 1e-10], dim=1), dim=1)[:, :-1]
+    trans = torch.cumprod(torch.cat([torch.ones(R, 1, dtype=raw.dtype, device=raw.device), 1.0 - alpha + 1e-10], dim=1), dim=1)[:, :-1]
     w = alpha * trans
     rgb_map = (w[..., None] * raw[..., :3]).sum(dim=1)
     wn = w.detach() + 1e-5
