@@ -130,10 +130,12 @@ def lib() -> C.CDLL:
     if _lib is None:
         with _lock:
             if _lib is None:
-                if not os.path.exists(LIB_PATH):
-                    raise UorfError(f"{LIB_PATH} not found: build it with `python -m uorf_b200.build` "
+                # UORF_B200_LIB: a tuning variant of the same library (uorf_b200/build.py, --tag); never a different backend
+                path = os.environ.get("UORF_B200_LIB") or LIB_PATH
+                if not os.path.exists(path):
+                    raise UorfError(f"{path} not found: build it with `python -m uorf_b200.build` "
                                     "(uorf_b200 has no CPU or PyTorch fallback)")
-                l = C.CDLL(LIB_PATH)
+                l = C.CDLL(path)
                 for name, (res, args) in _SIGNATURES.items():
                     fn = getattr(l, name)
                     fn.restype, fn.argtypes = res, args

@@ -47,17 +47,23 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OUT, exist_ok=True)
-    stamp = os.path.join(OUT, "fingerprint.txt")
-    fp = _fingerprint()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
-        return LIB
+def build_library(force: bool = False, verbose: bool = False, defines=(), tag: str = "") -> str:
+    """`defines`/`tag`: tuning variants (e.g. defines=["-DUORF_WAIT_HINT_NS=1000"], tag="hint1000") are built next to the
+    product library as _build/variants/libuorf_b200_<tag>.so; UORF_B200_LIB=<path> makes the loader pick one up."""
+    out, lib = OUT, LIB
+    if tag:
+        out = os.path.join(OUT, "variants", tag)
+        lib = os.path.join(OUT, "variants", f"libuorf_b200_{tag}.so")
+    os.makedirs(out, exist_ok=True)
+    stamp = os.path.join(out, "fingerprint.txt")
+    fp = _fingerprint() + " " + " ".join(defines)
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
+        return lib
     nvcc = _nvcc()
-    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if verbose else [])
+    flags = list(NVCC_FLAGS) + list(defines) + (["-Xptxas", "-v"] if verbose else [])
 
     def compile_one(src):
-        obj = os.path.join(OUT, src.replace(".cu", ".o"))
+        obj = os.path.join(out, src.replace(".cu", ".o"))
         cmd = [nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -68,14 +74,16 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as fh:
         fh.write(fp)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    _defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    _tag = next((a[len("--tag="):] for a in sys.argv[1:] if a.startswith("--tag=")), "")
+    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=_defs, tag=_tag))

@@ -65,14 +65,66 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// Bounded wait: a protocol bug must never hang the GPU box.  After ~2^28 failed probes the CTA
-// records the failing site in *err_flag (if given) and traps; the host sees a launch failure.
+// Up to `iters` probes of the barrier phase in a 5-instruction loop (SYNCS.TRYWAIT, BRA, IADD, ISETP, BRA).  Waiting warps
+// share issue slots with the warps doing the work they wait for, so the loop is kept as small as it can be; the optional
+// suspend-time hint (UORF_WAIT_HINT_NS > 0) lets the hardware park the warp for longer per probe.
+#ifndef UORF_WAIT_HINT_NS
+#define UORF_WAIT_HINT_NS 0
+#endif
+#ifndef UORF_WAIT_SLEEP_NS
+#define UORF_WAIT_SLEEP_NS 0
+#endif
+#define UORF_STR2(x) #x
+#define UORF_STR(x) UORF_STR2(x)
+#if UORF_WAIT_SLEEP_NS > 0
+#define UORF_WAIT_BACKOFF "nanosleep.u32 " UORF_STR(UORF_WAIT_SLEEP_NS) ";\n\t"
+#else
+#define UORF_WAIT_BACKOFF ""
+#endif
+__device__ __forceinline__ bool mbar_spin(uint32_t addr, uint32_t parity, uint32_t iters) {
+  uint32_t ok;
+#if UORF_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, %3;\n"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %4;\n\t"
+      "@p bra LAB_DONE;\n\t" UORF_WAIT_BACKOFF
+      "sub.u32 n, n, 1;\n\t"
+      "setp.ne.u32 q, n, 0;\n\t"
+      "@q bra LAB_WAIT;\n"
+      "LAB_DONE:\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity), "r"(iters), "r"((uint32_t)UORF_WAIT_HINT_NS)
+      : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, %3;\n"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra LAB_DONE;\n\t" UORF_WAIT_BACKOFF
+      "sub.u32 n, n, 1;\n\t"
+      "setp.ne.u32 q, n, 0;\n\t"
+      "@q bra LAB_WAIT;\n"
+      "LAB_DONE:\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity), "r"(iters)
+      : "memory");
+#endif
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must never hang the GPU box.  The fast path never reads the clock; after 2^14 failed probes
+// the wait continues in rounds of 2^14 with a wall-clock check between rounds, and after ~2 s the CTA records the failing
+// site in *err_flag (if given) and traps; the host sees a launch failure.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag = nullptr, int site = 0) {
-  if (mbar_try_wait(bar, parity)) return;
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_spin(addr, parity, 1u << 14)) return;
   const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xFFu) == 0 && clock64() - t0 > 4000000000LL) {  // ~2 s: protocol bug, do not hang the box
+  while (!mbar_spin(addr, parity, 1u << 14)) {
+    if (clock64() - t0 > 4000000000LL) {
       if (err_flag) atomicExch(err_flag, site ? site : 1);
       __threadfence_system();
       __trap();
