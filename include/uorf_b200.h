@@ -122,6 +122,9 @@ typedef struct uorf_decoder_args {
   float* unmasked_raws;     /* [K][P][4] */
   float* masks;             /* [K][P] */
   uint8_t* outside;         /* [K-1][P] locality flags (outsider_idx, model.py:121/128) */
+  const float* fg_slot_offset; /* device [K-1][3] or NULL.  Slot s evaluates coor_fg - fg_slot_offset[s] (fp32 subtract, then the
+                                  reference's transform / locality test): the moved-object render of uorf_manip_model.py:201-204
+                                  without materialising its (K-1)xPx3 clone of the coordinates. */
 } uorf_decoder_args;
 
 int uorf_decoder_forward(const uorf_decoder_args* a, void* stream);

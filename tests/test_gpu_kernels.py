@@ -311,6 +311,87 @@ def test_eval_driver_golden(layout):
 
 
 # ------------------------------------------------------------------------------------------------------
+# moved-object render (uorf_manip_model.py:196-232): per-slot offset table in the kernel vs the reference's shifted clone
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fixed", [0, 1])
+@pytest.mark.parametrize("precision", ["fp16x3", "bf16"])
+def test_decoder_slot_offset_equals_shifted_clone(fixed, precision):
+    from uorf_b200.modules import Decoder
+    K, P, Z = 5, 128 * 9 + 31, 64
+    gen = torch.Generator().manual_seed(99 + fixed)
+    params = O.init_decoder_params(Z, seed=3)
+    cb = (torch.rand(P, 3, generator=gen) * 2 - 1) * 1.5
+    zs = torch.randn(K, Z, generator=gen)
+    c2w, azi = O.lookat_cameras(1)
+    T = (c2w if fixed else azi)[0:1].inverse()
+    off = torch.zeros(K - 1, 3)
+    off[2] = torch.tensor([0.31, -0.17, 0.05])
+    dec = Decoder(locality=True, locality_ratio=4.5 / 7, fixed_locality=bool(fixed)).to(dev())
+    dec.load_state_dict(params)
+    dec.precision = precision
+    dec.return_outside = True
+    cbd = cb.to(dev())
+    shifted = cbd[None].expand(K - 1, -1, -1).clone()
+    shifted[2] = shifted[2] - off[2].to(dev())                      # the reference's data movement
+    with torch.no_grad():
+        want = dec(cbd, shifted, zs.to(dev()), T.to(dev()))
+        want_out = dec.last_outside.clone()
+        dec.fg_slot_offset = off.to(dev())
+        got = dec(cbd, cbd[None].expand(K - 1, -1, -1), zs.to(dev()), T.to(dev()))
+        dec.fg_slot_offset = None
+    assert torch.equal(dec.last_outside, want_out)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)                                       # same arithmetic, bit for bit
+    if precision == "fp16x3":
+        sh = cb[None].expand(K - 1, -1, -1).clone()
+        sh[2] = sh[2] - off[2]
+        ref = O.decoder_forward(params, cb, sh, zs, T, locality=True, locality_ratio=4.5 / 7, fixed_locality=bool(fixed),
+                                noise=torch.zeros(K, P, 1))
+        check_decoder_outputs(got, ref, FP32_TOL, f"moved slot fixed{fixed}")
+    with pytest.raises(Exception):                                     # inference-only knob
+        dec.fg_slot_offset = off.to(dev())
+        dec(cbd, cbd[None].expand(K - 1, -1, -1), zs.to(dev()).requires_grad_(True), T.to(dev()))
+
+
+def test_manip_driver_vs_oracle():
+    """reconstruct -> select the slot by IoU -> moved render, against the oracle's decoder + compositing on shifted coords."""
+    from uorf_b200.manip_model import uorfManipModel
+    from uorf_b200.eval_model import default_eval_options
+    g = load_golden("eval_driver")
+    opt = default_eval_options(num_slots=4, z_dim=40, n_samp=8, frustum_size=16, render_size=8, input_size=32,
+                               n_img_each_scene=1, gpu_ids=[0])
+    m = uorfManipModel(opt, layout="native", precision="fp16x3").eval()
+    m.load_networks_from_state_dicts(g["enc"], g["sa"], g["dec"])
+    m.slot_noise = (g["noise_fg"].to(dev()), g["noise_bg"].to(dev()))
+    movement = torch.tensor([[1.4, -0.7, 0.0]])
+    inp = {"img_data": g["img"][:1], "cam2world": g["cam2world"][:1], "azi_rot": g["azi_rot"][:1], "paths": [],
+           "movement": movement}
+    m.set_input(inp)
+    m.forward(move_slot_idx=1)                                          # explicit choice
+    assert maxerr(m.x_recon, g["x_recon"][:1]) < FP32_TOL
+    # oracle: same latents, coordinates of fg slot 1 shifted by movement / nss_scale
+    spec = O.FrustumSpec([16, 16, 8], near=6.0, far=20.0, nss_scale=7.0, render_size=16)
+    coords, zv, rd = O.sampling_coords(spec, g["cam2world"][:1])
+    K = 4
+    fg = coords[None].expand(K - 1, -1, -1).clone()
+    fg[1] = fg[1] - movement / 7.0
+    dec_p = {k: v for k, v in g["dec"].items()}
+    raws, masked, _, _ = O.decoder_forward(dec_p, coords, fg, m.z_slots.cpu(), g["azi_rot"][0:1].inverse(), locality=False,
+                                           locality_ratio=opt.obj_scale / opt.nss_scale, noise=torch.zeros(K, coords.shape[0], 1))
+    raws = raws.view(1, 8, 16, 16, 4).permute(0, 2, 3, 1, 4).flatten(0, 2)
+    rgb, _, _ = O.composite(raws, zv, rd)
+    want = rgb.view(1, 16, 16, 3).permute(0, 3, 1, 2) * 2 - 1
+    assert maxerr(m.x_moved, want) < FP32_TOL
+    assert (m.x_moved - m.x_recon).abs().max().item() > 1e-3            # the object did move
+    # slot selection on the device: fg_idx = the argmax mask of fg slot 2 must pick index 1 (0-based among fg slots)
+    inp["fg_idx"] = (m.mask_idx_pred[0:1] == 2).cpu()
+    m.set_input(inp)
+    m.forward()
+    assert int(m.move_slot_idx) == 1 and abs(float(m.ious[1]) - 1.0) < 1e-6
+    assert maxerr(m.x_moved, want) < FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------------------
 # kernel 5: decoder backward (fp16 tensor-core operands, fp32 accumulation, activations recomputed on chip) against fp32
 # autograd through the oracle / the reference's golden gradients
 # ------------------------------------------------------------------------------------------------------

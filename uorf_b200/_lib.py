@@ -47,7 +47,7 @@ class DecoderArgs(C.Structure):
                 ("P", C.c_int64), ("K", C.c_int32), ("precision", C.c_int32),
                 ("image", C.c_void_p), ("workspace", C.c_void_p),
                 ("raws", C.c_void_p), ("masked_raws", C.c_void_p), ("unmasked_raws", C.c_void_p),
-                ("masks", C.c_void_p), ("outside", C.c_void_p)]
+                ("masks", C.c_void_p), ("outside", C.c_void_p), ("fg_slot_offset", C.c_void_p)]
 
 
 class DecoderBwdArgs(C.Structure):

@@ -68,6 +68,7 @@ struct DecFwdParams {
   float* masks;
   unsigned char* outside;
   const float* fg_transform;  // device: 3x3, or 4x4 when fixed_locality
+  const float* fg_slot_offset;  // device [K-1][3] or null
   float locality_ratio;
   float dens_noise;
   long long P;
@@ -364,6 +365,11 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
             nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
           }
           if (phase == 1) {
+            if (p.fg_slot_offset != nullptr) {   // moved object: same fp32 subtraction the reference applies to its coordinate copy
+              x = __fsub_rn(x, __ldg(p.fg_slot_offset + 3 * s));
+              y = __fsub_rn(y, __ldg(p.fg_slot_offset + 3 * s + 1));
+              z = __fsub_rn(z, __ldg(p.fg_slot_offset + 3 * s + 2));
+            }
             if (p.fixed_locality) outside = fabsf(x) > p.locality_ratio || fabsf(y) > p.locality_ratio || fabsf(z) > p.locality_ratio;
             // unfused multiply/add in the order ((r0*x + r1*y) + r2*z) [+ t]: bit-equal to the reference's
             // CPU matmul
@@ -506,6 +512,7 @@ int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, c
   p.masks = a->masks;
   p.outside = a->outside;
   p.fg_transform = a->fg_transform;
+  p.fg_slot_offset = a->fg_slot_offset;
   p.locality_ratio = a->locality_ratio;
   p.dens_noise = a->dens_noise;
   p.P = a->P;

@@ -140,14 +140,19 @@ class uorfEvalModel:
         z_slots, attn = self.netSlotAttention(feat, noise=self.slot_noise)
         return z_slots.squeeze(0), attn.squeeze(0)
 
-    def render(self, z_slots, cam2world, nss2cam0):
+    def render(self, z_slots, cam2world, nss2cam0, fg_slot_offset=None):
         """frustum sampling -> fused decoder -> compositing for the given views, ray-major layout.
+        fg_slot_offset (K-1)x3: per-object translation in NSS units (the moved-object render of uorf_manip_model.py:196-204).
         Returns dict(rendered Nx3xHxW, depth NxHxW, masked / unmasked ray-major KxPx4, z_vals, ray_dir)."""
         K = z_slots.shape[0]
         N = cam2world.shape[0]
         W, H, D = self.projection.frustum_size
         coords, z_vals, ray_dir = self.projection.construct_sampling_coor(cam2world, ray_major=True)
-        raws, masked, unmasked, _ = self.netDecoder(coords, coords[None].expand(K - 1, -1, -1), z_slots, nss2cam0)
+        self.netDecoder.fg_slot_offset = fg_slot_offset
+        try:
+            raws, masked, unmasked, _ = self.netDecoder(coords, coords[None].expand(K - 1, -1, -1), z_slots, nss2cam0)
+        finally:
+            self.netDecoder.fg_slot_offset = None
         rgb_map, depth_map, _ = raw2outputs(raws.view(N * H * W, D, 4), z_vals, ray_dir)
         rendered = rgb_map.view(N, H, W, 3).permute([0, 3, 1, 2])
         return dict(rendered=rendered, depth=depth_map.view(N, H, W), masked=masked, unmasked=unmasked, z_vals=z_vals,

@@ -370,6 +370,9 @@ class Decoder(nn.Module):
                   returned as None (the API-mandated per-slot tensors are 36*K bytes per point of HBM writes).
       match_rng_stream  draw the reference's unconditional randn_like (model.py:155) even when dens_noise == 0,
                   so later draws from the same generator line up with the reference.
+      fg_slot_offset    (K-1)x3 tensor or None (inference only): slot s is evaluated at sampling_coor_fg[s] - fg_slot_offset[s],
+                  bit-identical to passing the reference's shifted clone (uorf_manip_model.py:201-204) but without
+                  materialising (K-1)xPx3 coordinates.
     """
 
     ALL_OUTPUTS = ("raws", "masked_raws", "unmasked_raws", "masks")
@@ -408,6 +411,7 @@ class Decoder(nn.Module):
         self.return_outside = False
         self.last_outside = None
         self.events = None   # set to a list to collect (start, end) CUDA events around the fused kernel
+        self.fg_slot_offset = None
 
     # ---- C-ABI plumbing ----
     def _weights(self) -> _lib.DecoderWeights:
@@ -485,6 +489,12 @@ class Decoder(nn.Module):
         a.image, a.workspace = image_ptr, workspace.data_ptr()
         a.raws, a.masked_raws, a.unmasked_raws, a.masks = _ptr(raws), _ptr(masked), _ptr(unmasked), _ptr(masks)
         a.outside = _ptr(outside)
+        off = getattr(self, "fg_slot_offset", None)
+        if off is not None:
+            if tuple(off.shape) != (K - 1, 3) or not off.is_cuda:
+                raise _lib.UorfError(f"fg_slot_offset must be a CUDA tensor of shape ({K - 1}, 3)")
+            off = _f32c(off.detach())
+        a.fg_slot_offset = _ptr(off)
         ev = self.events
         if ev is not None:
             e0 = torch.cuda.Event(enable_timing=True)
@@ -550,6 +560,8 @@ class Decoder(nn.Module):
         needs_grad = torch.is_grad_enabled() and (z_slots.requires_grad or any(p.requires_grad for p in self.parameters()))
         if not needs_grad:
             return self._launch_forward(sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform, dens_noise, noise, set(self.emit))
+        if getattr(self, "fg_slot_offset", None) is not None:
+            raise _lib.UorfError("fg_slot_offset is an inference-only knob (the backward kernel does not take it)")
         names = [n for n, _ in self.named_parameters()]
         params = [p_ for _, p_ in self.named_parameters()]
         raws, masked, unmasked, masks = _DecoderFn.apply(self, sampling_coor_bg, sampling_coor_fg, fg_transform, noise,
