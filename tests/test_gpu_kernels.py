@@ -353,6 +353,26 @@ def test_decoder_slot_offset_equals_shifted_clone(fixed, precision):
         dec(cbd, cbd[None].expand(K - 1, -1, -1), zs.to(dev()).requires_grad_(True), T.to(dev()))
 
 
+def test_render_row_blocks_equal_full_render():
+    """rows=(h0, h1) (the per-rank block of the row-sharded multi-GPU render) reproduces the full render bit for bit."""
+    from uorf_b200.eval_model import uorfEvalModel, default_eval_options
+    g = load_golden("eval_driver")
+    opt = default_eval_options(num_slots=4, z_dim=40, n_samp=8, frustum_size=16, render_size=8, input_size=32,
+                               n_img_each_scene=2, gpu_ids=[0])
+    m = uorfEvalModel(opt, layout="native", precision="fp16x3").eval()
+    m.load_networks_from_state_dicts(g["enc"], g["sa"], g["dec"])
+    m.slot_noise = (g["noise_fg"].to(dev()), g["noise_bg"].to(dev()))
+    m.set_input({"img_data": g["img"], "cam2world": g["cam2world"], "azi_rot": g["azi_rot"], "paths": []})
+    with torch.no_grad():
+        z, _ = m.encode()
+        full = m.render(z, m.cam2world, m.nss2cam0)
+        parts = [m.render(z, m.cam2world, m.nss2cam0, rows=r) for r in ((0, 5), (5, 16))]
+    assert torch.equal(torch.cat([p["rendered"] for p in parts], dim=2), full["rendered"])
+    assert torch.equal(torch.cat([p["depth"] for p in parts], dim=1), full["depth"])
+    with pytest.raises(ValueError):
+        m.render(z, m.cam2world, m.nss2cam0, rows=(10, 20))
+
+
 def test_manip_driver_vs_oracle():
     """reconstruct -> select the slot by IoU -> moved render, against the oracle's decoder + compositing on shifted coords."""
     from uorf_b200.manip_model import uorfManipModel

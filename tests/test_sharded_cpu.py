@@ -43,7 +43,15 @@ def _worker(rank, world, port, out):
     sharded.allreduce_gradients(params)
     ok_grad = torch.allclose(params[0].grad, torch.full((3, 4), 1.5)) and torch.allclose(params[1].grad, torch.arange(7.) * 1.5) \
         and params[2].grad is None
-    out[rank] = bool(ok_render and ok_grad)
+    # row sharding (one view, large frustum): rank r renders rows [r*H/world, (r+1)*H/world)
+    Hh, Ww = 6, 5
+    image = torch.arange(2 * 3 * Hh * Ww, dtype=torch.float32).view(2, 3, Hh, Ww)
+
+    def render_rows(z, h0, h1):
+        return image[:, :, h0:h1] + z.sum()
+    loc, (h0, h1), full_rows = sharded.sharded_render_rows(encode, render_rows, Hh, K, C, torch.device("cpu"), gather=True)
+    ok_rows = torch.equal(full_rows, image + slots_rank0.sum()) and (h1 - h0) == Hh // world and torch.equal(loc, full_rows[:, :, h0:h1])
+    out[rank] = bool(ok_render and ok_grad and ok_rows)
     dist.destroy_process_group()
 
 

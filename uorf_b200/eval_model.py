@@ -140,14 +140,20 @@ class uorfEvalModel:
         z_slots, attn = self.netSlotAttention(feat, noise=self.slot_noise)
         return z_slots.squeeze(0), attn.squeeze(0)
 
-    def render(self, z_slots, cam2world, nss2cam0, fg_slot_offset=None):
+    def render(self, z_slots, cam2world, nss2cam0, fg_slot_offset=None, rows=None):
         """frustum sampling -> fused decoder -> compositing for the given views, ray-major layout.
         fg_slot_offset (K-1)x3: per-object translation in NSS units (the moved-object render of uorf_manip_model.py:196-204).
-        Returns dict(rendered Nx3xHxW, depth NxHxW, masked / unmasked ray-major KxPx4, z_vals, ray_dir)."""
+        rows=(h0, h1): only image rows h0..h1-1 of every view (one rank's block when the rays of a view are sharded).
+        Returns dict(rendered Nx3xHxW, depth NxHxW, masked / unmasked ray-major KxPx4, z_vals, ray_dir); H = h1-h0 with rows."""
         K = z_slots.shape[0]
         N = cam2world.shape[0]
         W, H, D = self.projection.frustum_size
-        coords, z_vals, ray_dir = self.projection.construct_sampling_coor(cam2world, ray_major=True)
+        if rows is None:
+            coords, z_vals, ray_dir = self.projection.construct_sampling_coor(cam2world, ray_major=True)
+        else:
+            h0, h1 = int(rows[0]), int(rows[1])
+            coords, z_vals, ray_dir = self.projection.construct_sampling_coor(cam2world, ray_major=True, crop=(h0, 0, h1 - h0, W))
+            H = h1 - h0
         self.netDecoder.fg_slot_offset = fg_slot_offset
         try:
             raws, masked, unmasked, _ = self.netDecoder(coords, coords[None].expand(K - 1, -1, -1), z_slots, nss2cam0)

@@ -196,7 +196,8 @@ class Projection(object):
           ray_major=True  points ordered (n, h, w, d): the decoder output is then directly the RxDx4 tensor
                           raw2outputs wants (no permute copy, reference uorf_eval_model.py:147);
           crop=(h0, w0)   only the render_size window at (h0, w0) (fine-stage training crop,
-                          reference uorf_nogan_model.py:153-165), never materialising the full frustum.
+                          reference uorf_nogan_model.py:153-165), never materialising the full frustum;
+          crop=(h0, w0, Hc, Wc)  an arbitrary window (row blocks of one view when rays are sharded over GPUs).
         """
         _require_cuda(cam2world)
         cam2world = _f32c(cam2world)
@@ -210,6 +211,10 @@ class Projection(object):
                 raise ValueError("crop and partitioned are mutually exclusive")
             scale, Hc, Wc = 1, int(self.render_size[0]), int(self.render_size[1])
             ch, cw = int(crop[0]), int(crop[1])
+            if len(crop) == 4:
+                Hc, Wc = int(crop[2]), int(crop[3])
+            if ch < 0 or cw < 0 or Hc < 1 or Wc < 1 or ch + Hc > H or cw + Wc > W:
+                raise ValueError(f"crop window {tuple(crop)} does not fit the {H}x{W} frustum")
         else:
             scale = H // self.render_size[0] if partitioned else 1
             Hc, Wc = H // scale, W // scale

@@ -58,6 +58,31 @@ def sharded_render(encode_fn: Callable[[], torch.Tensor], render_fn: Callable[[t
     return local, (lo, hi), full
 
 
+def sharded_render_rows(encode_fn: Callable[[], torch.Tensor], render_rows_fn: Callable[[torch.Tensor, int, int], torch.Tensor],
+                        height: int, K: int, C: int, device, gather: bool = True, group=None):
+    """One scene, the image ROWS of every view sharded over the ranks of `group` (few views, large frustum: the
+    manipulation render at 256x256x128).
+
+    encode_fn()                      -> z_slots KxC          (rank 0 only)
+    render_rows_fn(z_slots, h0, h1)  -> images Nx3x(h1-h0)xW for rows h0..h1-1
+    Returns (local rows, (h0, h1), full images Nx3xHxW on every rank or None)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    z_slots = encode_fn() if rank == 0 else None
+    z_slots = broadcast_slots(z_slots, K, C, device, 0, group)
+    h0, h1 = shard_range(height, world, rank)
+    local = render_rows_fn(z_slots, h0, h1).contiguous()
+    full = None
+    if gather:
+        if height % world != 0:
+            raise ValueError("gather=True needs the image height divisible by the world size")
+        n = local.shape[0]
+        stacked = torch.empty((world * n,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+        dist.all_gather_into_tensor(stacked, local, group=group)
+        # [world*N, 3, h, W] -> N x 3 x (world*h) x W
+        full = stacked.view((world, n) + tuple(local.shape[1:])).permute(1, 2, 0, 3, 4).reshape(n, local.shape[1], height, local.shape[3])
+    return local, (h0, h1), full
+
+
 def allreduce_gradients(params, group=None, average: bool = True) -> None:
     """Data-parallel training: scenes are sharded over ranks, weights replicated; after backward
     every gradient is summed over ranks with ONE flat-bucket all-reduce (0.7 - 1.9 MB fp32: latency-bound on NVLink, so
