@@ -30,6 +30,8 @@ def main():
     m.netDecoder.emit = ("raws",)
     img, c2w, azi = synthetic_scene(1, 128)
     m.set_input({"img_data": img, "cam2world": c2w, "azi_rot": azi, "paths": [], "movement": torch.tensor([[1.0, 0.5, 0.0]])})
+    g = torch.Generator().manual_seed(7)      # fixed slot-initialisation noise: every encode() yields the same latents
+    m.slot_noise = (torch.randn(1, K - 1, Z, generator=g).to(dev), torch.randn(1, 1, Z, generator=g).to(dev))
     offsets = torch.zeros(K - 1, 3, device=dev)
     offsets[1] = m.movement[0] / opt.nss_scale
 
