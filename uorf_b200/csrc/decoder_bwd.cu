@@ -26,7 +26,8 @@
 namespace uorf {
 
 constexpr int kTileM128 = 128;
-constexpr int kBwdThreads = 160;  // 4 epilogue warps + 1 MMA-issuer warp
+constexpr int kBwdEpiWarps = 8;    // two warps per TMEM lane quadrant: warp w and w + 4 split the 64 feature columns of a point
+constexpr int kBwdThreads = (kBwdEpiWarps + 1) * 32;  // + 1 MMA-issuer warp
 constexpr int kAccFloats = 64 * 64;
 // accumulators: 0: before.0 (x P)  1: before.2  2: before.4  3: after.0 (x P)  4: after.0 (x tmp)  5: after.2  6: after.4  7: head
 constexpr int kNumAcc = 8;
@@ -85,27 +86,28 @@ __device__ __forceinline__ float grad_scale(float amax) {
   return ldexpf(1.f, 10 - e);
 }
 
-// write one 64-feature row (fp32 regs v[64]) as 16-bit values (F16: fp16, else bf16) into row `t` of a swizzled tile
+// Each point's 64 feature columns are split between two threads (`half` = 0 / 1 owns columns 32*half .. 32*half+31).
+// write 32 features (fp32 regs) as 16-bit values (F16: fp16, else bf16) into this thread's half of row `t` of a swizzled tile
 template <bool F16>
-__device__ __forceinline__ void store_row16(unsigned char* tile, int t, const float (&v)[64]) {
+__device__ __forceinline__ void store_half16(unsigned char* tile, int t, int half, const float (&v)[32]) {
   unsigned char* row = tile + (t >> 3) * 1024 + (t & 7) * 128;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
     uint4 q;
     q.x = pack2<F16>(v[8 * c + 0], v[8 * c + 1]);
     q.y = pack2<F16>(v[8 * c + 2], v[8 * c + 3]);
     q.z = pack2<F16>(v[8 * c + 4], v[8 * c + 5]);
     q.w = pack2<F16>(v[8 * c + 6], v[8 * c + 7]);
-    *reinterpret_cast<uint4*>(row + (((c ^ (t & 7)) & 7) << 4)) = q;
+    *reinterpret_cast<uint4*>(row + ((((4 * half + c) ^ (t & 7)) & 7) << 4)) = q;
   }
 }
-// ReLU gate: multiply g[i] by [x_i > 0] where x is the 16-bit row `t` of a swizzled tile (bf16 and fp16 both keep
-// their magnitude in the low 15 bits)
-__device__ __forceinline__ void gate_by_row(const unsigned char* tile, int t, float (&g)[64]) {
+// ReLU gate: multiply g[i] by [x_i > 0] where x is this thread's half of the 16-bit row `t` of a swizzled tile (bf16 and
+// fp16 both keep their magnitude in the low 15 bits)
+__device__ __forceinline__ void gate_by_half(const unsigned char* tile, int t, int half, float (&g)[32]) {
   const unsigned char* row = tile + (t >> 3) * 1024 + (t & 7) * 128;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 q = *reinterpret_cast<const uint4*>(row + (((c ^ (t & 7)) & 7) << 4));
+  for (int c = 0; c < 4; ++c) {
+    const uint4 q = *reinterpret_cast<const uint4*>(row + ((((4 * half + c) ^ (t & 7)) & 7) << 4));
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -115,61 +117,54 @@ __device__ __forceinline__ void gate_by_row(const unsigned char* tile, int t, fl
     }
   }
 }
-// column sums over the 32 lanes of a warp of v[0..63] (reduce-scatter butterfly: lane l ends with features 2l, 2l+1),
-// accumulated into dst[64] (shared memory) with one atomic pair per lane
-__device__ __forceinline__ void warp_colsum_add(const float (&v)[64], float* dst, int lane) {
-  float a[32];
+// column sums over the 32 lanes of a warp of v[0..31] (reduce-scatter butterfly: lane l ends with feature l),
+// accumulated into dst[32] (shared memory) with one atomic per lane
+__device__ __forceinline__ void warp_colsum_add(const float (&v)[32], float* dst, int lane) {
+  float a[16];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {  // step 1: lanes with bit 4 set keep the upper half
+  for (int i = 0; i < 16; ++i) {  // step 1: lanes with bit 4 set keep the upper half
     const bool up = lane & 16;
-    const float keep = up ? v[32 + i] : v[i];
-    const float send = up ? v[i] : v[32 + i];
+    const float keep = up ? v[16 + i] : v[i];
+    const float send = up ? v[i] : v[16 + i];
     a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
   }
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < 8; ++i) {
     const bool up = lane & 8;
-    const float keep = up ? a[16 + i] : a[i];
-    const float send = up ? a[i] : a[16 + i];
+    const float keep = up ? a[8 + i] : a[i];
+    const float send = up ? a[i] : a[8 + i];
     a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const bool up = lane & 4;
-    const float keep = up ? a[8 + i] : a[i];
-    const float send = up ? a[i] : a[8 + i];
+    const float keep = up ? a[4 + i] : a[i];
+    const float send = up ? a[i] : a[4 + i];
     a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool up = lane & 2;
-    const float keep = up ? a[4 + i] : a[i];
-    const float send = up ? a[i] : a[4 + i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-#pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const bool up = lane & 1;
+    const bool up = lane & 2;
     const float keep = up ? a[2 + i] : a[i];
     const float send = up ? a[i] : a[2 + i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
   }
-  // lane bits (16,8,4,2,1) selected halves in that order: feature index = 32*b4 + 16*b3 + 8*b2 + 4*b1 + 2*b0 + i
-  const int f0 = ((lane & 16) ? 32 : 0) + ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
-  atomicAdd(dst + f0, a[0]);
-  atomicAdd(dst + f0 + 1, a[1]);
+  {
+    const bool up = lane & 1;
+    const float keep = up ? a[1] : a[0];
+    const float send = up ? a[0] : a[1];
+    a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  // lane bits (16,8,4,2,1) selected halves in that order: feature index = 16*b4 + 8*b3 + 4*b2 + 2*b1 + b0 = lane
+  atomicAdd(dst + lane, a[0]);
 }
 
-__device__ __forceinline__ void load_d64(uint32_t taddr, float (&v)[64]) {
+__device__ __forceinline__ void load_d32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   tmem_ld32(taddr, r);
   tc_wait_ld();
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-  tmem_ld32(taddr + 32, r);
-  tc_wait_ld();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[32 + i] = __uint_as_float(r[i]);
 }
 
 __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBwdParams p) {
@@ -193,11 +188,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_a, kTileM128);
+    mbar_init(&bar_a, kTileM128 * 2);
     mbar_init(&bar_d, 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == kBwdEpiWarps) {
     tmem_alloc(&tmem_base_s, 512);
     tmem_relinquish();
   }
@@ -218,7 +213,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
   uint32_t n_a = 0, n_d = 0;
   for (int phase = 0; phase < 2; ++phase) {
     const int nslots = phase == 0 ? 1 : K - 1;
-    if (warp == 4 && lane == 0) {
+    if (warp == kBwdEpiWarps && lane == 0) {
       fence_proxy_async_smem();
       const unsigned char* src = p.image + (phase ? blob_fg_offset(1) : 0);
       const uint32_t bytes = (uint32_t)blob_bytes_one(1, nslots);
@@ -236,7 +231,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
 #pragma unroll
     for (int i = 0; i < 51; ++i) wc2_acc[i] = 0.f;
 
-    if (warp == 4) {
+    if (warp == kBwdEpiWarps) {
       // =========================== MMA issuer ===========================
       const uint32_t tbu = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t w_s = smem_u32(smem);
@@ -295,9 +290,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
       }
       __syncwarp();
     } else {
-      // =========================== epilogue warps (thread <-> point) ===========================
-      const int t = threadIdx.x;  // 0..127
-      const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
+      // =========================== epilogue warps (two threads <-> point) ===========================
+      const int t = (warp & 3) * 32 + lane;   // point within the tile == TMEM lane
+      const int half = warp >> 2;             // this thread owns feature columns 32*half .. 32*half + 31
+      const int c0 = 32 * half;
+      const uint32_t tb = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
       auto wait_d = [&](int site) {
         mbar_wait(&bar_d, n_d & 1, p.err_flag, site);
         ++n_d;
@@ -332,8 +329,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
           }
           // wait until the previous slot's last weight-gradient MMAs have finished reading the tiles
           if (it > 0 || s > 0) wait_d(300);
-          {
-            float v[64];
+          if (half == 0) {
+            // columns 0..31: x y z, then [sin, cos](2^i xyz) up to sin(16 xyz) and cos(16 x), cos(16 y)
+            float v[32];
             float sn[3], cs[3];
             sincosf(x, &sn[0], &cs[0]);
             sincosf(y, &sn[1], &cs[1]);
@@ -342,85 +340,99 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
 #pragma unroll
-              for (int j = 0; j < 3; ++j) { v[3 + 6 * i + j] = sn[j]; v[6 + 6 * i + j] = cs[j]; }
+              for (int j = 0; j < 3; ++j) {
+                v[3 + 6 * i + j] = sn[j];
+                if (6 + 6 * i + j < 32) v[6 + 6 * i + j] = cs[j];
+              }
               if (i < 4) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) { const float s2 = 2.f * sn[j] * cs[j], c2 = 1.f - 2.f * sn[j] * sn[j]; sn[j] = s2; cs[j] = c2; }
               }
             }
-#pragma unroll
-            for (int i = kPosenc; i < 64; ++i) v[i] = (valid && i == kPosenc + (s < 15 ? s : 14)) ? 1.f : 0.f;
             if (!valid) {
 #pragma unroll
-              for (int i = 0; i < kPosenc; ++i) v[i] = 0.f;   // padded points contribute nothing to any gradient
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;   // padded points contribute nothing to any gradient
             }
-            store_row16<true>(s_x, t, v);
+            store_half16<true>(s_x, t, 0, v);
+          } else {
+            // columns 32..63: cos(16 z), the one-hot slot indicator, zero padding
+            float v[32];
+            float sn, cs;
+            sincosf(z, &sn, &cs);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn; sn = s2; cs = c2; }
+            v[0] = valid ? cs : 0.f;
+#pragma unroll
+            for (int i = 1; i < 32; ++i) v[i] = (valid && i == 1 + (s < 15 ? s : 14)) ? 1.f : 0.f;
+            store_half16<true>(s_x, t, 1, v);
           }
           publish();
           // ---- stages 1..6: hidden activations ----
           const float* sb = s_slotb + s * kSlotBiasFloats;
 #pragma unroll 1
           for (int st = 1; st <= 6; ++st) {
-            const float* bias = st == 1 ? sb : st == 2 ? s_params + kPB1 : st == 3 ? s_params + kPB2
-                              : st == 4 ? sb + 64 : st == 5 ? s_params + kPA1 : s_params + kPA2;
+            const float* bias = (st == 1 ? sb : st == 2 ? s_params + kPB1 : st == 3 ? s_params + kPB2
+                               : st == 4 ? sb + 64 : st == 5 ? s_params + kPA1 : s_params + kPA2) + c0;
             wait_d(300 + st);
-            float v[64];
-            load_d64(tb + kBColD, v);
+            float v[32];
+            load_d32(tb + kBColD + c0, v);
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = valid ? fmaxf(v[i] + bias[i], 0.f) : 0.f;
-            store_row16<true>(s_x + st * 16384, t, v);
+            for (int i = 0; i < 32; ++i) v[i] = valid ? fmaxf(v[i] + bias[i], 0.f) : 0.f;
+            store_half16<true>(s_x + st * 16384, t, half, v);
             publish();
           }
-          // ---- head forward + backward seed ----
+          // ---- head forward + backward seed (the 17 head rows live in the first column half) ----
           wait_d(307);
-          float dzh[64];
-#pragma unroll
-          for (int i = 0; i < 64; ++i) dzh[i] = 0.f;
           {
-            uint32_t r[32];
-            tmem_ld32(tb + kBColD, r);
-            tc_wait_ld();
-            float4 dr = valid ? p.scratch_draw[(long long)kslot * p.P + pt] : make_float4(0.f, 0.f, 0.f, 0.f);
-            dr.x *= gscale; dr.y *= gscale; dr.z *= gscale; dr.w *= gscale;
-            const float* hb = s_params + kPHeadB;
-            if (phase == 0) {
-              dzh[0] = dr.x; dzh[1] = dr.y; dzh[2] = dr.z; dzh[3] = dr.w;
-            } else {
-              const float* wc2 = s_params + kPWc2;
+            float dzh[32];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float pre = __uint_as_float(r[i]) + hb[i];
-                const float h = fmaxf(pre, 0.f);
-                wc2_acc[i] += dr.x * h;
-                wc2_acc[16 + i] += dr.y * h;
-                wc2_acc[32 + i] += dr.z * h;
-                const float dh = wc2[i] * dr.x + wc2[16 + i] * dr.y + wc2[32 + i] * dr.z;
-                dzh[i] = pre > 0.f ? dh : 0.f;
+            for (int i = 0; i < 32; ++i) dzh[i] = 0.f;
+            if (half == 0) {
+              uint32_t r[32];
+              tmem_ld32(tb + kBColD, r);
+              tc_wait_ld();
+              float4 dr = valid ? p.scratch_draw[(long long)kslot * p.P + pt] : make_float4(0.f, 0.f, 0.f, 0.f);
+              dr.x *= gscale; dr.y *= gscale; dr.z *= gscale; dr.w *= gscale;
+              const float* hb = s_params + kPHeadB;
+              if (phase == 0) {
+                dzh[0] = dr.x; dzh[1] = dr.y; dzh[2] = dr.z; dzh[3] = dr.w;
+              } else {
+                const float* wc2 = s_params + kPWc2;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float pre = __uint_as_float(r[i]) + hb[i];
+                  const float h = fmaxf(pre, 0.f);
+                  wc2_acc[i] += dr.x * h;
+                  wc2_acc[16 + i] += dr.y * h;
+                  wc2_acc[32 + i] += dr.z * h;
+                  const float dh = wc2[i] * dr.x + wc2[16 + i] * dr.y + wc2[32 + i] * dr.z;
+                  dzh[i] = pre > 0.f ? dh : 0.f;
+                }
+                wc2_acc[48] += dr.x; wc2_acc[49] += dr.y; wc2_acc[50] += dr.z;
+                dzh[kHeadShapeRow] = (p.locality && outside) ? 0.f : dr.w;   // model.py:147-148 zeroes sigma outside the box
               }
-              wc2_acc[48] += dr.x; wc2_acc[49] += dr.y; wc2_acc[50] += dr.z;
-              dzh[kHeadShapeRow] = (p.locality && outside) ? 0.f : dr.w;   // model.py:147-148 zeroes sigma outside the box
+              warp_colsum_add(dzh, s_db[4], lane);
             }
+            store_half16<true>(s_dz, t, half, dzh);   // the second half writes the zero padding of the head's dZ tile
           }
-          warp_colsum_add(dzh, s_db[4], lane);
-          store_row16<true>(s_dz, t, dzh);
           publish();
           // ---- layers 5..0 ----
 #pragma unroll 1
           for (int l = 5; l >= 0; --l) {
             wait_d(320 + l);
-            float g[64];
-            load_d64(tb + kBColD, g);              // dX_{l+1}
-            gate_by_row(s_x + (l + 1) * 16384, t, g);   // * [X_{l+1} > 0]  -> dZ_l
-            if (l == 1 || l == 2) warp_colsum_add(g, s_db[l - 1], lane);
-            if (l == 4 || l == 5) warp_colsum_add(g, s_db[l - 2], lane);
-            store_row16<true>(s_dz + ((l & 1) ? 16384 : 0), t, g);
+            float g[32];
+            load_d32(tb + kBColD + c0, g);                  // dX_{l+1}
+            gate_by_half(s_x + (l + 1) * 16384, t, half, g);     // * [X_{l+1} > 0]  -> dZ_l
+            if (l == 1 || l == 2) warp_colsum_add(g, s_db[l - 1] + c0, lane);
+            if (l == 4 || l == 5) warp_colsum_add(g, s_db[l - 2] + c0, lane);
+            store_half16<true>(s_dz + ((l & 1) ? 16384 : 0), t, half, g);
             publish();
           }
         }
       }
     }
     // ---- end of phase: drain, dump accumulators + bias sums as this CTA's partial record ----
-    if (warp < 4) {
+    if (warp < kBwdEpiWarps) {
       // the issuer's last commit (dW of layer 0) has not been consumed yet
       bool any = (long long)blockIdx.x < p.num_tiles;
       if (any) {
@@ -468,7 +480,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
     __syncthreads();
     tc_fence_after();
   }
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == kBwdEpiWarps) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------
