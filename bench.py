@@ -390,7 +390,11 @@ def run_train(args):
     opt = default_train_options(num_slots=c["K"], z_dim=c["z_dim"], n_samp=c["n_samp"], frustum_size=c["frustum"],
                                 render_size=c["supervision_size"], supervision_size=c["supervision_size"], input_size=c["input_size"],
                                 n_img_each_scene=c["n_views"], stage="coarse", gpu_ids=[local_rank], warmup_steps=10)
+    use_graph = world == 1 and not args.no_graph
+    opt.cuda_graph = use_graph
     model = uorfNoGanModel(opt, precision=args.precision)
+    if use_graph:
+        model.enable_cuda_graph()
     if world > 1:
         model.process_group = dist.group.WORLD
     img, c2w, azi = synthetic_scene(c["n_views"], c["load_size"], seed=2021 + rank)   # one scene per rank
@@ -422,6 +426,8 @@ def run_train(args):
         return ms.item()
 
     sampler = ClockSampler(local_rank)
+    for _ in range(5 if use_graph else 0):      # three eager steps + the capture happen before the warm-up
+        step(resident)
     for _ in range(max(args.warmup, 3)):
         step(resident)
     sampler.start()
@@ -447,6 +453,7 @@ def run_train(args):
                 "config": dict(c, step="Encoder+SlotAttention+sampling+decoder+compositing fwd+bwd, MSE + VGG16-relu4_3 perceptual "
                                "(random-init VGG, weight 0 at epoch 0 exactly as the reference computes it), Adam",
                                parallelism=f"scene-sharded data parallel x{world}, one flat gradient all-reduce (NCCL)",
+                               launch="whole step (forward + backward + Adam) replayed as one CUDA graph" if use_graph else "eager launches",
                                loss_last=float(model.loss_recon.detach())),
                 "clocks": clocks,
                 "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "scene-steps/s", "h2d_bytes_per_step": h2d,

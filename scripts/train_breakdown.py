@@ -19,6 +19,12 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(5):
         m.set_input(inp); m.optimize_parameters(epoch=0)
     torch.cuda.synchronize()
+from torch.autograd import DeviceType
+kern = [e for e in prof.events() if e.device_type == DeviceType.CUDA]
+busy = sum(e.device_time_total for e in kern)
+t_lo, t_hi = min(e.time_range.start for e in kern), max(e.time_range.end for e in kern)
+print(f"kernel events: {len(kern) / 5:.0f} per step, span {(t_hi - t_lo) / 5 / 1000:.3f} ms per step")
+print(f"sum of kernel durations per step: {busy / 5 / 1000:.3f} ms (compare with bench.py --mode train ms_per_step: the rest is idle gaps)")
 ev = [e for e in prof.key_averages() if e.device_time_total > 0]
 tot = sum(e.device_time_total for e in ev)
 print(f"total device time per step: {tot / 5 / 1000:.3f} ms")

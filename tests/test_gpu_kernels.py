@@ -576,3 +576,35 @@ def test_train_driver_golden(stage):
     assert not torch.equal(w0, m.netDecoder.f_before[0].weight)
     m.compute_visuals()
     assert m.slot2_view1.shape == (3, 8, 8) and m.unmasked_slot0_view0.shape == (3, 8, 8) and m.slot1_attn.shape[-1] == 8
+
+
+def test_train_step_cuda_graph_matches_eager():
+    """whole training step (forward + backward + Adam) replayed as one CUDA graph follows the eager trajectory."""
+    from uorf_b200.nogan_model import uorfNoGanModel, default_train_options
+    g = load_golden("train_driver_coarse")
+    inp = {"img_data": g["img"], "cam2world": g["cam2world"], "azi_rot": g["azi_rot"], "paths": []}
+    models = []
+    for graphed in (False, True):
+        opt = default_train_options(num_slots=3, z_dim=40, n_samp=8, frustum_size=8, frustum_size_fine=16, render_size=8,
+                                    supervision_size=8, input_size=32, n_img_each_scene=2, stage="coarse", gpu_ids=[0],
+                                    warmup_steps=4, cuda_graph=True)
+        m = uorfNoGanModel(opt, precision="fp16x3")
+        m.load_networks_from_state_dicts(g["enc"], g["sa"], g["dec"])
+        m.slot_noise = (g["noise_fg"].to(dev()), g["noise_bg"].to(dev()))
+        if graphed:
+            m.enable_cuda_graph()
+        losses = []
+        for _ in range(8):                      # graphed: 3 eager steps, capture, then replays
+            m.set_input(inp)
+            m.optimize_parameters(epoch=0)
+            m.update_learning_rate()
+            losses.append(m.loss_recon.item())
+        models.append((m, losses))
+    (me, le), (mg, lg) = models
+    assert mg._graph is not None
+    assert le[-1] < le[0]                       # it trains
+    assert max(abs(a - b) for a, b in zip(le, lg)) < 1e-5, (le, lg)
+    for (n, pe), (_, pg) in zip(me.named_parameters(), mg.named_parameters()):
+        assert (pe - pg).abs().max().item() < 1e-5, n
+    with pytest.raises(RuntimeError):           # needs the capturable optimizer
+        uorfNoGanModel(default_train_options(num_slots=3, z_dim=40, gpu_ids=[0]), with_perceptual=False).enable_cuda_graph()

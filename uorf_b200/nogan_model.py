@@ -100,9 +100,14 @@ class uorfNoGanModel:
         self.netDecoder.precision = precision
         self.netDecoder.emit = ("raws", "masked_raws", "unmasked_raws")   # the driver keeps these for its visuals (:185-196)
         self.netDecoder.match_rng_stream = bool(getattr(opt, "match_rng_stream", False))
+        # opt.cuda_graph: build the optimizer graph-capturable (device-side step counter, learning rate held in a device
+        # scalar that the scheduler fills in place) so enable_cuda_graph() can replay the whole step as one graph launch
+        self._capturable = bool(getattr(opt, "cuda_graph", False))
+        self._graph_enabled, self._graph, self._graph_key, self._graph_warm, self._static = False, None, None, 0, None
         if self.isTrain:
+            lr = torch.tensor(float(opt.lr), device=self.device) if self._capturable else opt.lr
             self.optimizer = optim.Adam(chain(self.netEncoder.parameters(), self.netSlotAttention.parameters(),
-                                              self.netDecoder.parameters()), lr=opt.lr)
+                                              self.netDecoder.parameters()), lr=lr, capturable=self._capturable)
             self.optimizers = [self.optimizer]
             self.schedulers = [exp_decay_schedule_with_warmup(self.optimizer, opt.warmup_steps, opt.attn_decay_steps)]
         self.L2_loss = nn.MSELoss()
@@ -208,10 +213,58 @@ class uorfNoGanModel:
         loss.backward()
         self.loss_perc = self.loss_perc / self.weight_percept if self.weight_percept > 0 else self.loss_perc
 
+    # ---- whole-step CUDA graph ------------------------------------------------------
+    def enable_cuda_graph(self, enabled: bool = True):
+        """After this, optimize_parameters() runs three more eager steps (cuDNN autotuning, optimizer state, .grad buffers must
+        exist before capture), captures forward + backward + Adam into ONE CUDA graph and replays it from then on: ~460 small
+        launches (Encoder, VGG, slot attention, Adam, losses) stop costing host time and inter-kernel gaps.  Inputs are
+        copied into static buffers; a change of the epoch-dependent constants (perceptual weight, density noise, locality)
+        or of the input shapes re-captures.  Coarse stage, single process only (the fine stage draws its crop window on the
+        host every step; data-parallel steps keep the eager path)."""
+        if enabled and not self._capturable:
+            raise RuntimeError("construct the model with opt.cuda_graph=True (capturable Adam) to use enable_cuda_graph()")
+        self._graph_enabled, self._graph, self._graph_key, self._graph_warm = bool(enabled), None, None, 0
+        return self
+
+    def _step_graphed(self, epoch):
+        opt = self.opt
+        key = (opt.weight_percept if epoch >= opt.percept_in else 0,
+               opt.dens_noise if (epoch <= opt.percept_in and opt.fixed_locality) else 0, bool(self.netDecoder.locality),
+               tuple(self.x.shape), tuple(self.cam2world.shape), self.slot_noise is None)
+        st = self._static
+        if st is None or st["x"].shape != self.x.shape or st["cam2world"].shape != self.cam2world.shape:
+            st = self._static = {"x": self.x.clone(), "cam2world": self.cam2world.clone(), "nss2cam0": self.nss2cam0.clone()}
+            self._graph = None
+        for name in ("x", "cam2world", "nss2cam0"):
+            cur = getattr(self, name)
+            if cur.data_ptr() != st[name].data_ptr():
+                st[name].copy_(cur, non_blocking=True)
+                setattr(self, name, st[name])
+        if self._graph is None or key != self._graph_key:
+            if key != self._graph_key:
+                self._graph_key, self._graph_warm, self._graph = key, 0, None
+            if self._graph_warm < 3:
+                self._graph_warm += 1
+                return self._step_eager(False, epoch)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_eager(False, epoch)
+            self._graph = g
+        self._graph.replay()
+        return [], []
+
     def optimize_parameters(self, ret_grad=False, epoch=0):
+        if self._graph_enabled and not ret_grad and self.process_group is None and self.opt.stage == "coarse":
+            return self._step_graphed(epoch)
+        return self._step_eager(ret_grad, epoch)
+
+    def _step_eager(self, ret_grad=False, epoch=0):
         self.forward(epoch)
-        for opm in self.optimizers:
-            opm.zero_grad(set_to_none=False)
+        # optimizer.zero_grad() of the reference (:235-236, zero in place): one multi-tensor launch instead of one fill per tensor
+        grads = [p.grad for p in self.parameters() if p.grad is not None]
+        if grads:
+            torch._foreach_zero_(grads)
         self.backward()
         if self.process_group is not None:
             from .sharded import allreduce_gradients
