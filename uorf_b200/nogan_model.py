@@ -246,6 +246,11 @@ class uorfNoGanModel:
             if self._graph_warm < 3:
                 self._graph_warm += 1
                 return self._step_eager(False, epoch)
+            # drop every reference to the previous step's autograd graph (its AccumulateGrad nodes belong to the eager
+            # stream and would invalidate the capture) and let the captured backward allocate .grad in the graph's pool
+            self.loss_recon = self.loss_perc = None
+            for p_ in self.parameters():
+                p_.grad = None
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
