@@ -33,22 +33,24 @@
 namespace uorf {
 
 constexpr int kTileM = 128;
-constexpr int kEpiWarps = 16;
 constexpr int kTmemCols = 512;
 
-template <int PASSES>
+template <int PASSES, int NCH_>
 struct Cfg {
-  static constexpr int NCH = PASSES == 3 ? 2 : 4;       // channels
+  static constexpr int NCH = NCH_;                      // channels: 4 (1-pass), 3 or 2 (3-pass; 2 when K > 13 needs the shared memory)
   static constexpr int CS = PASSES == 3 ? 2 : 1;        // threads per point (column split)
   static constexpr int WPC = 4 * CS;                    // warps per channel
-  static constexpr int THREADS = (kEpiWarps + NCH) * 32;
-  static constexpr int CHAN_COLS = 512 / NCH;           // TMEM columns per channel
+  static constexpr int EPI_WARPS = NCH * WPC;           // 16 (1-pass), 24 / 16 (3-pass)
+  static constexpr int THREADS = (EPI_WARPS + NCH) * 32;
+  static constexpr int CHAN_COLS = PASSES == 3 ? 160 : 128;  // TMEM columns per channel (3 x 160 or 4 x 128 <= 512)
+  static constexpr int NKP = PASSES == 3 ? 2 : 3;       // K-steps of the positional-encoding operand (3-pass: elements 0..31
+                                                        // on the tensor core, element 32 by an fp32 FMA in the epilogue)
   static constexpr int COL_D = 0;
   static constexpr int COL_HHI = 64;
   static constexpr int COL_HLO = 96;                    // 3-pass only
   static constexpr int COL_PHI = PASSES == 3 ? 128 : 96;
-  static constexpr int COL_PLO = 160;                   // 3-pass only
-  static constexpr int COL_SEL = PASSES == 3 ? 192 : 120; // 8 columns: one-hot K-step that selects a bias column
+  static constexpr int COL_PLO = 144;                   // 3-pass only
+  static constexpr int COL_SEL = 120;                   // 1-pass only: 8 columns, one-hot K-step that selects a bias column
   static constexpr int NPL = PASSES == 3 ? 2 : 1;       // weight planes
   // bias through the tensor core (selector MMA) pays off where the epilogue is the bottleneck (1-pass modes); in the 3-pass
   // modes the extra MMAs lengthen the dependent chain more than two FADDs per pair cost, so the bias stays in the epilogue
@@ -132,21 +134,21 @@ __device__ __forceinline__ void posenc_store(const float (&v)[kPosencK], uint32_
     if (PASSES == 3) split2<F16>(v[2 * (W0 + i)], v[2 * (W0 + i) + 1], hi[i], lo[i]);
     else hi[i] = pack2<F16>(v[2 * (W0 + i)], v[2 * (W0 + i) + 1]);
   }
-  static_assert(NW == 24 || NW == 12, "posenc split");
-  if constexpr (NW == 24) {
+  static_assert(NW == 24 || NW == 8, "posenc split");
+  if constexpr (NW == 8) {
+    tmem_st8(t_phi + W0, hi);
+    if (PASSES == 3) tmem_st8(t_plo + W0, lo);
+  } else if constexpr (NW == 24) {
     tmem_st16(t_phi + W0, hi);
     tmem_st8(t_phi + W0 + 16, hi + 16);
     if (PASSES == 3) { tmem_st16(t_plo + W0, lo); tmem_st8(t_plo + W0 + 16, lo + 16); }
-  } else {
-    tmem_st8(t_phi + W0, hi);
-    tmem_st4(t_phi + W0 + 8, hi + 8);
-    if (PASSES == 3) { tmem_st8(t_plo + W0, lo); tmem_st4(t_plo + W0 + 8, lo + 8); }
   }
 }
 
 // 32 accumulator columns (bias already added by the selector MMA): ReLU -> 16-bit hi[/lo] -> 16 H operand columns
+// wx / xe (3-pass modes, layers fed by the positional encoding): adds wx[col] * xe, the contribution of encoding element 32
 template <int PASSES, bool F16>
-__device__ __forceinline__ void epilogue32(uint32_t t_d, const float* bias, uint32_t t_hhi, uint32_t t_hlo) {
+__device__ __forceinline__ void epilogue32(uint32_t t_d, const float* bias, const float* wx, float xe, uint32_t t_hhi, uint32_t t_hlo) {
   uint32_t r[32];
   tmem_ld32(t_d, r);
   tc_wait_ld();
@@ -158,8 +160,12 @@ __device__ __forceinline__ void epilogue32(uint32_t t_d, const float* bias, uint
     float v1 = __uint_as_float(r[4 * q + 1]);
     float v2 = __uint_as_float(r[4 * q + 2]);
     float v3 = __uint_as_float(r[4 * q + 3]);
-    if (!Cfg<PASSES>::BIAS_MMA) {
-      const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
+    if (PASSES == 3) {
+      float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
+      if (wx != nullptr) {
+        const float4 w = *reinterpret_cast<const float4*>(wx + 4 * q);
+        b.x = fmaf(w.x, xe, b.x); b.y = fmaf(w.y, xe, b.y); b.z = fmaf(w.z, xe, b.z); b.w = fmaf(w.w, xe, b.w);
+      }
       v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
     }
     if (PASSES == 3 && F16) {
@@ -212,9 +218,10 @@ __device__ __forceinline__ void issue_ksteps(uint32_t t_d, uint32_t t_ahi, uint3
   }
 }
 
-template <int PASSES, bool F16>
-__global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(const DecFwdParams p) {
-  using C = Cfg<PASSES>;
+template <int PASSES, bool F16, int NCH>
+__global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kernel(const DecFwdParams p) {
+  using C = Cfg<PASSES, NCH>;
+  constexpr int kEpiWarps = C::EPI_WARPS;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_w;
   __shared__ __align__(8) ChanBars bars[C::NCH];
@@ -303,11 +310,11 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
                 first = false;
               }
               switch (st) {
-                case 0: issue_ksteps<PASSES>(t_d, t_p, t_pl, w_smem + 0 * kTileBytes, 0, 3, idesc64, first); break;
+                case 0: issue_ksteps<PASSES>(t_d, t_p, t_pl, w_smem + 0 * kTileBytes, 0, C::NKP, idesc64, first); break;
                 case 1: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 1 * kTileBytes, 0, 4, idesc64, first); break;
                 case 2: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 2 * kTileBytes, 0, 4, idesc64, first); break;
                 case 3:
-                  issue_ksteps<PASSES>(t_d, t_p, t_pl, w_smem + 3 * kTileBytes, 0, 3, idesc64, first);
+                  issue_ksteps<PASSES>(t_d, t_p, t_pl, w_smem + 3 * kTileBytes, 0, C::NKP, idesc64, first);
                   issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 4 * kTileBytes, 0, 4, idesc64, first);
                   break;
                 case 4: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 5 * kTileBytes, 0, 4, idesc64, first); break;
@@ -337,7 +344,7 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
           // 3-pass modes (8 warps per channel): one polling warp, the others sleep in a hardware barrier and spend no issue
           // slots on probing (measured 3 % faster; no difference with 4 warps per channel)
           if (wic == 0) mbar_wait(&cb.d_full, n_d & 1, p.err_flag, site);
-          named_bar_sync(9 + ch, C::WPC * 32);
+          named_bar_sync(13 + ch, C::WPC * 32);
         } else {
           mbar_wait(&cb.d_full, n_d & 1, p.err_flag, site);
         }
@@ -359,6 +366,7 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
         for (int s = 0; s < nslots; ++s) {
           // ---- stage 0: coordinates -> object frame -> locality flag -> positional encoding ----
           float x = nx, y = ny, z = nz;
+          float x_last = 0.f;
           bool outside = false;
           if (valid && phase == 1 && p.fg_slot_stride != 0 && s + 1 < nslots) {
             const float* src = p.coor_fg + (long long)(s + 1) * p.fg_slot_stride + pt * 3;
@@ -386,10 +394,11 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
             if (C::CS == 1) {
               posenc_store<PASSES, F16, 0, 24>(v, tb + C::COL_PHI, tb + C::COL_PLO);
             } else if (half == 0) {
-              posenc_store<PASSES, F16, 0, 12>(v, tb + C::COL_PHI, tb + C::COL_PLO);
+              posenc_store<PASSES, F16, 0, 8>(v, tb + C::COL_PHI, tb + C::COL_PLO);
             } else {
-              posenc_store<PASSES, F16, 12, 12>(v, tb + C::COL_PHI, tb + C::COL_PLO);
+              posenc_store<PASSES, F16, 8, 8>(v, tb + C::COL_PHI, tb + C::COL_PLO);
             }
+            if (PASSES == 3) x_last = v[kPosencMma3];   // cos(16 z): added by FMA in the epilogues of layers before.0 / after.0
             if (C::BIAS_MMA && half == 0) write_selector<F16>(tb + C::COL_SEL, bias_id_slot(s, 0));
             tc_wait_st();
           }
@@ -406,7 +415,8 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
 #pragma unroll
             for (int h32 = 0; h32 < NCOL / 32; ++h32) {
               const int c32 = col0 + 32 * h32;   // first accumulator column of this 32-column block
-              epilogue32<PASSES, F16>(tb + C::COL_D + c32, bias + 32 * h32, tb + C::COL_HHI + c32 / 2, tb + C::COL_HLO + c32 / 2);
+              const float* wx = PASSES == 3 && (st == 1 || st == 4) ? s_params + (st == 1 ? kPW0x : kPW3x) + c32 : nullptr;
+              epilogue32<PASSES, F16>(tb + C::COL_D + c32, bias + 32 * h32, wx, x_last, tb + C::COL_HHI + c32 / 2, tb + C::COL_HLO + c32 / 2);
             }
             // selector for the bias of the layer the next MMA stage (index st) computes; the head (st == 6) keeps its bias here
             if (C::BIAS_MMA && half == 0 && st < 6)
@@ -491,9 +501,8 @@ __global__ void __launch_bounds__(Cfg<PASSES>::THREADS, 1) decoder_fwd_kernel(co
   if (warp == kEpiWarps) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-static size_t decoder_smem_bytes(int passes, int K) {
+static size_t decoder_smem_bytes(int passes, int K, int nch) {
   const int npl = passes == 3 ? 2 : 1;
-  const int nch = passes == 3 ? 2 : 4;
   const int w_region = npl * kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
   return 1024 + ((w_region + 127) & ~127) + (size_t)nch * K * kTileM * sizeof(float4);
 }
@@ -523,19 +532,23 @@ int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, c
   p.err_flag = err_flag;
   const int passes = a->precision >= 3 ? 3 : 1;
   const bool f16 = (a->precision % 2) == 0;
-  const size_t smem = decoder_smem_bytes(passes, a->K);
+  // 3-pass modes run three tiles per SM when the per-slot stash of three channels fits beside the weight image (K <= 13)
+  int nch = passes == 3 ? 3 : 4;
+  if (passes == 3 && decoder_smem_bytes(passes, a->K, 3) > 227 * 1024) nch = 2;
+  const size_t smem = decoder_smem_bytes(passes, a->K, nch);
   if (smem > 227 * 1024) return UORF_ERR_UNSUPPORTED;
   int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   if (grid < 1) return UORF_OK;
-  const int threads = passes == 3 ? Cfg<3>::THREADS : Cfg<1>::THREADS;
+  const int threads = passes == 3 ? (nch == 3 ? Cfg<3, 3>::THREADS : Cfg<3, 2>::THREADS) : Cfg<1, 4>::THREADS;
   auto launch = [&](auto kern) -> int {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UORF_ERR_DEVICE;
     kern<<<grid, threads, smem, stream>>>(p);
     return UORF_OK;
   };
   int rc;
-  if (passes == 3) rc = f16 ? launch(decoder_fwd_kernel<3, true>) : launch(decoder_fwd_kernel<3, false>);
-  else rc = f16 ? launch(decoder_fwd_kernel<1, true>) : launch(decoder_fwd_kernel<1, false>);
+  if (passes == 3 && nch == 3) rc = f16 ? launch(decoder_fwd_kernel<3, true, 3>) : launch(decoder_fwd_kernel<3, false, 3>);
+  else if (passes == 3) rc = f16 ? launch(decoder_fwd_kernel<3, true, 2>) : launch(decoder_fwd_kernel<3, false, 2>);
+  else rc = f16 ? launch(decoder_fwd_kernel<1, true, 4>) : launch(decoder_fwd_kernel<1, false, 4>);
   if (rc != UORF_OK) return rc;
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }

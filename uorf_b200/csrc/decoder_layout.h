@@ -14,7 +14,10 @@
 //        extra MMA whose A operand is a one-hot "selector" K-step (forward kernel):
 //        j = 0..3 : before.2, before.4, after.2, after.4 ;  j = 16+2s / 17+2s : the hoisted biases of slot s (before.0 / after.0)
 //   params (fp32, kParamFloats) : b_before.2, b_before.4, b_after.2, b_after.4 (64 each, zero padded),
-//        head bias [32], f_color.2 weight [3][16], f_color.2 bias [4 (3 used)]
+//        head bias [32], f_color.2 weight [3][16], f_color.2 bias [4 (3 used)],
+//        before.0[:, 32] and after.0[:, 32] (64 each): the weight column of the LAST positional-encoding element cos(16 z).
+//        The 3-pass forward feeds only elements 0..31 (two K-steps) through the tensor core and adds this column with one
+//        fp32 FMA per output, which frees 16 TMEM columns per tile - enough for a third tile in flight.
 //   slot biases (fp32) : per slot s: bias0[64] = before.0.bias + before.0[:, 33:] . z_s
 //                                     bias3[64] = after.0.bias  + after.0[:, 33:33+Z] . z_s
 //        (the slot-latent columns of the two wide layers are hoisted out of the per-point GEMM)
@@ -30,12 +33,13 @@ constexpr int kBiasTileOff = 7 * kTileBytes + kHeadTileBytes;              // 61
 constexpr int kPlaneBytes = kBiasTileOff + kTileBytes;                     // 69632
 __host__ __device__ constexpr int bias_id_fixed(int which) { return which; }              // 0..3
 __host__ __device__ constexpr int bias_id_slot(int s, int which) { return 16 + 2 * s + which; }   // which: 0 before.0, 1 after.0
-constexpr int kParamFloats = 352;
-constexpr int kParamBytes = kParamFloats * 4;                 // 1408
+constexpr int kParamFloats = 480;
+constexpr int kParamBytes = kParamFloats * 4;                 // 1920
 constexpr int kSlotBiasFloats = 128;
 constexpr int kSlotBiasBytes = kSlotBiasFloats * 4;           // 512
 // float offsets inside params
-constexpr int kPB1 = 0, kPB2 = 64, kPA1 = 128, kPA2 = 192, kPHeadB = 256, kPWc2 = 288, kPBc2 = 336;
+constexpr int kPB1 = 0, kPB2 = 64, kPA1 = 128, kPA2 = 192, kPHeadB = 256, kPWc2 = 288, kPBc2 = 336, kPW0x = 352, kPW3x = 416;
+constexpr int kPosencMma3 = 32;    // positional-encoding elements the 3-pass forward sends through the tensor core
 constexpr int kHeadShapeRow = 16;
 
 __host__ __device__ inline long long blob_bytes_one(int passes, int nslots) {

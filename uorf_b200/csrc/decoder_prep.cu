@@ -106,6 +106,9 @@ __global__ void decoder_prep_kernel(PrepArgs a) {
         if (fg && i < CH) v = a.w.f_color2_w[c * CH + i];
       } else if (e < kPBc2 + 3) {
         if (fg) v = a.w.f_color2_b[e - kPBc2];
+      } else if (e >= kPW0x) {
+        const int which = (e - kPW0x) >> 6, n = (e - kPW0x) & 63;
+        if (n < Z) v = which == 0 ? before_w[0][n * I + kPosencMma3] : after_w[0][n * (I + Z) + kPosencMma3];
       }
       prm[e] = v;
     }
