@@ -43,7 +43,7 @@ def launches(tag, fname="launches.csv", suffix="launches", cmd="python bench.py 
     open(os.path.join(P, f"{tag}_{suffix}.md"), "w").write("\n".join(out) + "\n")
 
 
-def decoder(tag, precision, repname="prof_decoder.ncu-rep"):
+def decoder(tag, precision, repname="prof_decoder.ncu-rep", title=None, outname=None):
     rep = os.path.join(G, repname)
     if not os.path.exists(rep):
         return
@@ -52,14 +52,15 @@ def decoder(tag, precision, repname="prof_decoder.ncu-rep"):
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
     keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
-            "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+            "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
             "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
             "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
             "smsp__inst_executed.sum", "sm__cycles_elapsed.avg", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
             "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
-    out = [f"# {tag}: `ncu --set full --clock-control none` of one decoder_fwd_kernel launch ({precision}, bench workload)", "",
+    out = [f"# {tag}: `ncu --set full --clock-control none` of one " + (title or f"decoder_fwd_kernel launch ({precision}, bench workload)"), "",
            "| metric | value | unit |", "|---|---:|---|"]
     for k in keys:
         if k in d:
@@ -69,7 +70,9 @@ def decoder(tag, precision, repname="prof_decoder.ncu-rep"):
     out += ["", "Warp stall reasons (PC samples, share of all samples):", "", "| reason | samples | share |", "|---|---:|---:|"]
     for h, v in sorted(stalls, key=lambda x: -x[1])[:10]:
         out.append(f"| {h.replace('smsp__pcsamp_warps_issue_stalled_', '')} | {v:.0f} | {100 * v / tot:.1f}% |")
-    open(os.path.join(P, f"{tag}_decoder_ncu_{precision}.md"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(P, outname or f"{tag}_decoder_ncu_{precision}.md"), "w").write("\n".join(out) + "\n")
+    if outname:
+        return
     try:
         rd, wr = float(d["dram__bytes_read.sum"][1]), float(d["dram__bytes_write.sum"][1])
         mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
@@ -91,4 +94,10 @@ if __name__ == "__main__":
     launches(tag, "launches_train.csv", "launches_train", "python bench.py --mode train --steps 2 --warmup 1 (launches 600..1000)")
     decoder(tag, prec)
     decoder(tag, "bf16", "prof_decoder_bf16.ncu-rep")
+    decoder(tag, "", "prof_composite.ncu-rep", "composite_fwd_kernel launch (scripts/bench_kernels.py 32: 524,288 rays x 64 samples)",
+            f"{tag}_composite_ncu.md")
+    decoder(tag, "", "prof_sample_coords.ncu-rep", "sample_coords launch (scripts/bench_kernels.py 32: 32 views, 128x128x64 frustum, ray-major)",
+            f"{tag}_sample_coords_ncu.md")
+    decoder(tag, "", "prof_decoder_bwd.ncu-rep", "decoder_bwd_kernel launch (bench.py --mode train: K=8, 64^3 frustum, 4 views)",
+            f"{tag}_decoder_bwd_ncu.md")
     print("wrote profiles/%s_*.md" % tag)
