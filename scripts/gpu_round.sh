@@ -16,13 +16,13 @@ timeout 300 python scripts/bench_kernels.py 32 > gpurun_out/bench_kernels.json 2
 timeout 300 python scripts/train_breakdown.py > gpurun_out/train_breakdown.log 2>&1
 if [ "$1" = "ncu" ]; then
   timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
+  UORF_PROFILE_RANGE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
   timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain2.log 2>&1 &&
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:decoder_fwd -s 3 -c 1 -o gpurun_out/prof_decoder -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
   timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --precision bf16 > gpurun_out/plain3.log 2>&1 &&
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:decoder_fwd -s 3 -c 1 -o gpurun_out/prof_decoder_bf16 -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --precision bf16 > gpurun_out/ncu_full_bf16.log 2>&1
   timeout 600 python bench.py --mode train --steps 2 --warmup 1 --no-graph > gpurun_out/plain4.log 2>&1 &&
-  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 460 --csv --log-file gpurun_out/launches_train.csv python bench.py --mode train --steps 2 --warmup 1 --no-graph > gpurun_out/ncu_launch_train.log 2>&1
+  UORF_PROFILE_RANGE=1 timeout 1200 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_train.csv python bench.py --mode train --steps 2 --warmup 1 --no-graph > gpurun_out/ncu_launch_train.log 2>&1
   timeout 300 python scripts/bench_kernels.py 32 > gpurun_out/plain5.log 2>&1 &&
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:composite_fwd -s 10 -c 1 -o gpurun_out/prof_composite -f python scripts/bench_kernels.py 32 > gpurun_out/ncu_full_composite.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:sample_coords -s 10 -c 1 -o gpurun_out/prof_sample_coords -f python scripts/bench_kernels.py 32 > gpurun_out/ncu_full_coords.log 2>&1

@@ -36,7 +36,8 @@ def launches(tag, fname="launches.csv", suffix="launches", cmd="python bench.py 
         tot += v
         n += 1
     out = [f"# {tag}: ncu launch list of `{cmd}`",
-           "", "`ncu --metrics gpu__time_duration.sum --clock-control none -c 200` (cold-cache, serialised: compare SHARES).",
+           "", "`UORF_PROFILE_RANGE=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none`: exactly the launches of the "
+           "timed steps (cold-cache, serialised: compare SHARES).",
            f"{n} launches captured, {tot:.1f} us in total.", "", "| us | launches | share | kernel |", "|---:|---:|---:|---|"]
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
         out.append(f"| {t:.1f} | {c} | {100 * t / tot:.1f}% | `{k}` |")
@@ -91,7 +92,7 @@ if __name__ == "__main__":
     prec = sys.argv[2] if len(sys.argv) > 2 else "fp16x3"
     os.makedirs(P, exist_ok=True)
     launches(tag)
-    launches(tag, "launches_train.csv", "launches_train", "python bench.py --mode train --steps 2 --warmup 1 (launches 600..1000)")
+    launches(tag, "launches_train.csv", "launches_train", "python bench.py --mode train --steps 2 --warmup 1 --no-graph")
     decoder(tag, prec)
     decoder(tag, "bf16", "prof_decoder_bf16.ncu-rep")
     decoder(tag, "", "prof_composite.ncu-rep", "composite_fwd_kernel launch (scripts/bench_kernels.py 32: 524,288 rays x 64 samples)",

@@ -605,7 +605,10 @@ def test_train_step_cuda_graph_matches_eager():
     assert le[-1] < le[0]                       # it trains
     assert max(abs(a - b) for a, b in zip(le, lg)) < 1e-5, (le, lg)
     for (n, pe), (_, pg) in zip(me.named_parameters(), mg.named_parameters()):
-        # cuDNN autotuning may pick different (non-bitwise-equal) conv algorithms for the two models: weights agree to 1e-4
-        assert (pe - pg).abs().max().item() < 1e-4, n
+        # cuDNN autotuning may pick different (not bitwise-equal) conv algorithms for the two models, and Adam turns a
+        # last-bit difference of a near-zero gradient into a step of up to lr: bound the drift by the summed learning rate
+        # (8 steps, lr <= 3e-4) for the worst element and require the bulk to agree closely
+        d = (pe - pg).abs()
+        assert d.max().item() < 1e-3 and d.mean().item() < 1e-5, (n, d.max().item(), d.mean().item())
     with pytest.raises(RuntimeError):           # needs the capturable optimizer
         uorfNoGanModel(default_train_options(num_slots=3, z_dim=40, gpu_ids=[0]), with_perceptual=False).enable_cuda_graph()
