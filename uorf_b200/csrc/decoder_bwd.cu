@@ -310,11 +310,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
         if (tile >= p.num_tiles) break;
         const long long pt = tile * kTileM128 + t;
         const bool valid = pt < p.P;
+        // fg slots that share their coordinates (the reference's expand() view) share the encoding: the first column half of
+        // the P tile is written once per tile, only the one-hot slot indicator in the second half changes from slot to slot
+        const bool shared_enc = phase == 1 && p.fg_slot_stride == 0;
+        float x = 0.f, y = 0.f, z = 0.f;
+        bool outside = false;
+        float cos16z = 0.f;
         for (int s = 0; s < nslots; ++s) {
           const int kslot = phase == 0 ? 0 : s + 1;
+          const bool fresh = s == 0 || !shared_enc;
           // ---- stage 0: coordinates -> positional encoding tile (column 33 + s carries the per-slot column sums) ----
-          float x = 0.f, y = 0.f, z = 0.f;
-          bool outside = false;
+          if (fresh) {
+          x = y = z = 0.f;
+          outside = false;
           if (valid) {
             const float* src = phase == 0 ? p.coor_bg + pt * 3 : p.coor_fg + (long long)s * p.fg_slot_stride + pt * 3;
             x = __ldg(src); y = __ldg(src + 1); z = __ldg(src + 2);
@@ -327,9 +335,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
             x = tx; y = ty; z = tz;
             if (!p.fixed_locality) outside = fabsf(x) > p.locality_ratio || fabsf(y) > p.locality_ratio || fabsf(z) > p.locality_ratio;
           }
+          }
           // wait until the previous slot's last weight-gradient MMAs have finished reading the tiles
           if (it > 0 || s > 0) wait_d(300);
           if (half == 0) {
+            if (fresh) {
             // columns 0..31: x y z, then [sin, cos](2^i xyz) up to sin(16 xyz) and cos(16 x), cos(16 y)
             float v[32];
             float sn[3], cs[3];
@@ -354,14 +364,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
               for (int i = 0; i < 32; ++i) v[i] = 0.f;   // padded points contribute nothing to any gradient
             }
             store_half16<true>(s_x, t, 0, v);
+            }
           } else {
             // columns 32..63: cos(16 z), the one-hot slot indicator, zero padding
             float v[32];
-            float sn, cs;
-            sincosf(z, &sn, &cs);
+            if (fresh) {
+              float sn, cs;
+              sincosf(z, &sn, &cs);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn; sn = s2; cs = c2; }
-            v[0] = valid ? cs : 0.f;
+              for (int i = 0; i < 4; ++i) { const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn; sn = s2; cs = c2; }
+              cos16z = cs;
+            }
+            v[0] = valid ? cos16z : 0.f;
 #pragma unroll
             for (int i = 1; i < 32; ++i) v[i] = (valid && i == 1 + (s < 15 ? s : 14)) ? 1.f : 0.f;
             store_half16<true>(s_x, t, 1, v);

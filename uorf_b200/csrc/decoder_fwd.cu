@@ -363,32 +363,35 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
           const float* src = (phase == 0 ? p.coor_bg : p.coor_fg) + pt * 3;
           nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
         }
+        // When every fg slot sees the same coordinates (the reference's expand() view, no moved object) the encoding operand
+        // written for the first slot is still in TMEM, and the locality flag is the same: later slots skip straight to the MMA.
+        const bool shared_enc = phase == 1 && p.fg_slot_stride == 0 && p.fg_slot_offset == nullptr;
+        float x_last = 0.f;
+        bool outside = false;
         for (int s = 0; s < nslots; ++s) {
           // ---- stage 0: coordinates -> object frame -> locality flag -> positional encoding ----
-          float x = nx, y = ny, z = nz;
-          float x_last = 0.f;
-          bool outside = false;
-          if (valid && phase == 1 && p.fg_slot_stride != 0 && s + 1 < nslots) {
-            const float* src = p.coor_fg + (long long)(s + 1) * p.fg_slot_stride + pt * 3;
-            nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
-          }
-          if (phase == 1) {
-            if (p.fg_slot_offset != nullptr) {   // moved object: same fp32 subtraction the reference applies to its coordinate copy
-              x = __fsub_rn(x, __ldg(p.fg_slot_offset + 3 * s));
-              y = __fsub_rn(y, __ldg(p.fg_slot_offset + 3 * s + 1));
-              z = __fsub_rn(z, __ldg(p.fg_slot_offset + 3 * s + 2));
+          if (s == 0 || !shared_enc) {
+            float x = nx, y = ny, z = nz;
+            outside = false;
+            if (valid && phase == 1 && p.fg_slot_stride != 0 && s + 1 < nslots) {
+              const float* src = p.coor_fg + (long long)(s + 1) * p.fg_slot_stride + pt * 3;
+              nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
             }
-            if (p.fixed_locality) outside = fabsf(x) > p.locality_ratio || fabsf(y) > p.locality_ratio || fabsf(z) > p.locality_ratio;
-            // unfused multiply/add in the order ((r0*x + r1*y) + r2*z) [+ t]: bit-equal to the reference's
-            // CPU matmul
-            const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], x), __fmul_rn(T[1], y)), __fmul_rn(T[2], z)), T[3]);
-            const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], x), __fmul_rn(T[5], y)), __fmul_rn(T[6], z)), T[7]);
-            const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], x), __fmul_rn(T[9], y)), __fmul_rn(T[10], z)), T[11]);
-            x = tx; y = ty; z = tz;
-            if (!p.fixed_locality) outside = fabsf(x) > p.locality_ratio || fabsf(y) > p.locality_ratio || fabsf(z) > p.locality_ratio;
-            if (p.outside && valid && half == 0) p.outside[(long long)s * p.P + pt] = outside ? 1 : 0;
-          }
-          {
+            if (phase == 1) {
+              if (p.fg_slot_offset != nullptr) {   // moved object: same fp32 subtraction the reference applies to its coordinate copy
+                x = __fsub_rn(x, __ldg(p.fg_slot_offset + 3 * s));
+                y = __fsub_rn(y, __ldg(p.fg_slot_offset + 3 * s + 1));
+                z = __fsub_rn(z, __ldg(p.fg_slot_offset + 3 * s + 2));
+              }
+              if (p.fixed_locality) outside = fabsf(x) > p.locality_ratio || fabsf(y) > p.locality_ratio || fabsf(z) > p.locality_ratio;
+              // unfused multiply/add in the order ((r0*x + r1*y) + r2*z) [+ t]: bit-equal to the reference's
+              // CPU matmul
+              const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], x), __fmul_rn(T[1], y)), __fmul_rn(T[2], z)), T[3]);
+              const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], x), __fmul_rn(T[5], y)), __fmul_rn(T[6], z)), T[7]);
+              const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], x), __fmul_rn(T[9], y)), __fmul_rn(T[10], z)), T[11]);
+              x = tx; y = ty; z = tz;
+              if (!p.fixed_locality) outside = fabsf(x) > p.locality_ratio || fabsf(y) > p.locality_ratio || fabsf(z) > p.locality_ratio;
+            }
             float v[kPosencK];
             posenc48<PASSES == 1>(x, y, z, v);
             if (C::CS == 1) {
@@ -399,9 +402,10 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
               posenc_store<PASSES, F16, 8, 8>(v, tb + C::COL_PHI, tb + C::COL_PLO);
             }
             if (PASSES == 3) x_last = v[kPosencMma3];   // cos(16 z): added by FMA in the epilogues of layers before.0 / after.0
-            if (C::BIAS_MMA && half == 0) write_selector<F16>(tb + C::COL_SEL, bias_id_slot(s, 0));
-            tc_wait_st();
           }
+          if (phase == 1 && p.outside && valid && half == 0) p.outside[(long long)s * p.P + pt] = outside ? 1 : 0;
+          if (C::BIAS_MMA && half == 0) write_selector<F16>(tb + C::COL_SEL, bias_id_slot(s, 0));
+          tc_wait_st();
           tc_fence_before();
           mbar_arrive(&cb.a_full);
 
