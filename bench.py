@@ -250,16 +250,19 @@ def run_b200(args):
 
     graph_on = [True]
 
+    graphed_sharded = sharded.GraphedShardedRender(model, K, Z) if world > 1 else None
+
     def step(inputs):
         model.set_input(inputs)
         if world == 1:
             model.forward()
             return model.x_recon
         with torch.no_grad():
+            if not (args.no_graph or not graph_on[0]):      # encode + broadcast + render replayed as one graph per rank
+                return graphed_sharded()["rendered"] * 2 - 1
             z = model.encode()[0] if rank == 0 else None
             z = sharded.broadcast_slots(z, K, Z, dev)
-            out = (model.render if (args.no_graph or not graph_on[0]) else model.render_graphed)(z, model.cam2world, model.nss2cam0)
-            return out["rendered"] * 2 - 1
+            return model.render(z, model.cam2world, model.nss2cam0)["rendered"] * 2 - 1
 
     def barrier():
         if world > 1:
@@ -345,7 +348,7 @@ def run_b200(args):
                 "config": dict(c, n_views_total=n_total, sharding=f"views over {world} rank(s), slot latents broadcast from rank 0",
                                layout="native ray-major, raws+masked+unmasked materialised",
                                launch=("eager launches" if args.no_graph else "forward replayed as one CUDA graph" if world == 1
-                                       else "rank 0: encoder + slot attention eager, NCCL broadcast; render replayed as a CUDA graph"),
+                                       else "per rank one CUDA graph: [rank 0: encoder + slot attention] -> NCCL broadcast of the slot latents -> render"),
                                l2="no flush: each step streams ~0.8 GB of outputs per GPU (>> 126 MB L2)",
                                weights="random init, seed 2021"),
                 "clocks": clocks,
@@ -395,13 +398,13 @@ def run_train(args):
     opt = default_train_options(num_slots=c["K"], z_dim=c["z_dim"], n_samp=c["n_samp"], frustum_size=c["frustum"],
                                 render_size=c["supervision_size"], supervision_size=c["supervision_size"], input_size=c["input_size"],
                                 n_img_each_scene=c["n_views"], stage="coarse", gpu_ids=[local_rank], warmup_steps=10)
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph
     opt.cuda_graph = use_graph
     model = uorfNoGanModel(opt, precision=args.precision)
-    if use_graph:
-        model.enable_cuda_graph()
     if world > 1:
         model.process_group = dist.group.WORLD
+    if use_graph:
+        model.enable_cuda_graph()
     img, c2w, azi = synthetic_scene(c["n_views"], c["load_size"], seed=2021 + rank)   # one scene per rank
     host = {"img_data": img.pin_memory(), "cam2world": c2w.pin_memory(), "azi_rot": azi.pin_memory()}
     resident = {k: v.to(dev) for k, v in host.items()}
@@ -463,7 +466,8 @@ def run_train(args):
                 "config": dict(c, step="Encoder+SlotAttention+sampling+decoder+compositing fwd+bwd, MSE + VGG16-relu4_3 perceptual "
                                "(random-init VGG, weight 0 at epoch 0 exactly as the reference computes it), Adam",
                                parallelism=f"scene-sharded data parallel x{world}, one flat gradient all-reduce (NCCL)",
-                               launch="whole step (forward + backward + Adam) replayed as one CUDA graph" if use_graph else "eager launches",
+                               launch=("whole step (forward + backward" + (" + gradient all-reduce" if world > 1 else "") + " + Adam) replayed as one CUDA graph")
+                               if use_graph else "eager launches",
                                loss_last=float(model.loss_recon.detach())),
                 "clocks": clocks,
                 "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "scene-steps/s", "h2d_bytes_per_step": h2d,

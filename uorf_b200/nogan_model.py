@@ -219,8 +219,8 @@ class uorfNoGanModel:
         exist before capture), captures forward + backward + Adam into ONE CUDA graph and replays it from then on: ~460 small
         launches (Encoder, VGG, slot attention, Adam, losses) stop costing host time and inter-kernel gaps.  Inputs are
         copied into static buffers; a change of the epoch-dependent constants (perceptual weight, density noise, locality)
-        or of the input shapes re-captures.  Coarse stage, single process only (the fine stage draws its crop window on the
-        host every step; data-parallel steps keep the eager path)."""
+        or of the input shapes re-captures.  Coarse stage only (the fine stage draws its crop window on the host every
+        step).  With a process group set, the flat gradient all-reduce (NCCL) is captured inside the same graph."""
         if enabled and not self._capturable:
             raise RuntimeError("construct the model with opt.cuda_graph=True (capturable Adam) to use enable_cuda_graph()")
         self._graph_enabled, self._graph, self._graph_key, self._graph_warm = bool(enabled), None, None, 0
@@ -253,14 +253,15 @@ class uorfNoGanModel:
                 p_.grad = None
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread-local capture mode: the NCCL watchdog thread of a data-parallel run may touch the CUDA API meanwhile
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._step_eager(False, epoch)
             self._graph = g
         self._graph.replay()
         return [], []
 
     def optimize_parameters(self, ret_grad=False, epoch=0):
-        if self._graph_enabled and not ret_grad and self.process_group is None and self.opt.stage == "coarse":
+        if self._graph_enabled and not ret_grad and self.opt.stage == "coarse":
             return self._step_graphed(epoch)
         return self._step_eager(ret_grad, epoch)
 

@@ -83,6 +83,53 @@ def sharded_render_rows(encode_fn: Callable[[], torch.Tensor], render_rows_fn: C
     return local, (h0, h1), full
 
 
+class GraphedShardedRender:
+    """encode (rank 0) -> NCCL broadcast of the slot latents -> rank-local render, captured as ONE CUDA graph per rank.
+
+    The eager form of this step costs rank 0 about 60 small launches (encoder, slot attention) and every rank a separate
+    broadcast launch per scene; replaying it as a graph (NCCL collectives are capturable) removes that host time from the
+    multi-GPU step.  `model` is a uorfEvalModel whose set_input() has been called with THIS rank's views (rank 0 must hold
+    view 0's image); shapes must stay fixed after the first call."""
+
+    def __init__(self, model, K: int, C: int, group=None):
+        self.model, self.K, self.C, self.group = model, K, C, group
+        self.graph, self.static, self.out = None, None, None
+
+    def _body(self):
+        m, st = self.model, self.static
+        rank = dist.get_rank(self.group)
+        with torch.no_grad():
+            m.x = st["x"]
+            z = m.encode()[0] if rank == 0 else torch.empty(self.K, self.C, device=st["x"].device)
+            z = broadcast_slots(z, self.K, self.C, z.device, 0, self.group)
+            return m.render(z, st["c2w"], st["T"])
+
+    def __call__(self):
+        m = self.model
+        dev = m.x.device
+        if self.graph is None:
+            self.static = {"x": m.x.clone(), "c2w": m.cam2world.clone(), "T": m.nss2cam0.clone()}
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(3):          # NCCL communicator, cuDNN autotuning and allocator pools exist before the capture
+                    self._body()
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self.out = self._body()
+            self.graph = g
+        else:
+            st = self.static
+            st["x"].copy_(m.x, non_blocking=True)
+            st["c2w"].copy_(m.cam2world, non_blocking=True)
+            st["T"].copy_(m.nss2cam0, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 def allreduce_gradients(params, group=None, average: bool = True) -> None:
     """Data-parallel training: scenes are sharded over ranks, weights replicated; after backward
     every gradient is summed over ranks with ONE flat-bucket all-reduce (0.7 - 1.9 MB fp32: latency-bound on NVLink, so
