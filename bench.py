@@ -213,6 +213,17 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _shutdown(dist):
+    """End of a multi-rank run.  The NCCL collectives of the step live inside CUDA graphs, and destroy_process_group() can block
+    on a communicator that graphs still reference; everything has been printed and synchronised, so leave without teardown."""
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 # ----------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------
@@ -370,8 +381,7 @@ def run_b200(args):
                 line["cpu_baseline"]["eager_gpu"] = {"error": repr(e)[:200]}
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        _shutdown(dist)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -475,8 +485,7 @@ def run_train(args):
                 "impl": "b200"}
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        _shutdown(dist)
 
 
 def main():
