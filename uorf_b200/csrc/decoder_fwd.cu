@@ -6,19 +6,19 @@
 //   ReLU density / tanh colour, density-weighted composition over the K slots.
 // No activation ever leaves the SM: the only HBM traffic is coords in, API-mandated outputs out.
 //
-// Structure: one persistent CTA per SM, 16 epilogue warps + one MMA-issuer warp per channel.
-//   warps 0-15      epilogue warps, grouped into NCH "channels"; a channel owns one 128-point tile at a time and
-//                   walks it through bg MLP / the K-1 fg slots.  Thread <-> TMEM lane <-> point.
-//                     3-pass modes : NCH = 2 channels x 8 warps; the two warps sharing a lane quadrant split the
-//                                    64 feature columns (TMEM: D 64 | H hi 32 | H lo 32 | P hi 24 | P lo 24 columns)
-//                     1-pass modes : NCH = 4 channels x 4 warps (TMEM: D 64 | H 32 | P 24 | selector 8 columns per channel)
-//   warp 16 + c     MMA issuer of channel c (lane 0 issues tcgen05.mma); warp 16 also owns TMEM alloc and the weight
-//                   bulk copies.  One issuer per channel keeps the channels out of lock-step: while one channel is in
+// Structure: one persistent CTA per SM, epilogue warps grouped into NCH "channels" + one MMA-issuer warp per channel.
+//   A channel owns one 128-point tile at a time and walks it through bg MLP / the K-1 fg slots.  Thread <-> TMEM lane <-> point.
+//     3-pass modes : NCH = 3 channels x 8 warps (2 when K > 13); the two warps sharing a lane quadrant split the 64 feature
+//                    columns.  TMEM: accumulators D at 64c, operand blocks at 192 + 104c = H hi 32 | H lo 32 | P hi 16 | P lo 16 | 8 spare.
+//                    Only 32 of the 33 encoding elements go through the tensor core; cos(16 z) is an fp32 FMA in the epilogue.
+//     1-pass modes : NCH = 4 channels x 4 warps (TMEM per channel: D 64 | H 32 | P 24 | selector 8 columns)
+//   warp EPI + c    MMA issuer of channel c (elected lane issues tcgen05.mma); the first issuer warp also owns TMEM alloc and the
+//                   weight bulk copies.  One issuer per channel keeps the channels out of lock-step: while one channel is in
 //                   its epilogue the tensor pipe works for another.
 // Per layer:  A (activations, 16-bit hi [+lo]) lives in TMEM, written by the epilogue threads with tcgen05.st;
 //   B (weights) is a 128B-swizzled K-major tile in shared memory; D (fp32) in TMEM.
 //   epilogue --a_full mbarrier--> issuer --tcgen05.commit / d_full mbarrier--> epilogue (ReLU + 16-bit split).
-//   Biases never touch the CUDA cores: the weight image carries a bias tile whose COLUMN j is bias vector j, the epilogue
+//   1-pass modes: biases never touch the CUDA cores: the weight image carries a bias tile whose COLUMN j is bias vector j, the epilogue
 //   writes a one-hot "selector" K-step (8 TMEM columns) naming the next layer's bias, and the issuer appends one MMA
 //   D += selector . bias_tile^T to the layer - the accumulator the epilogue reads already contains the bias.
 // Precision: 1 pass of 16-bit operands, or 3 passes a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (fp32 accumulate);
@@ -29,6 +29,12 @@
 #include "common.cuh"
 #include "decoder_layout.h"
 #include "../../include/uorf_b200.h"
+
+// Bias through the selector MMA in the 3-pass modes too (tuning experiment, off: measured 7 % (bf16x3) to 20 % (fp16x3) SLOWER -
+// the two extra MMAs per layer sit on the dependent chain, which is what bounds these modes)
+#ifndef UORF_X3_BIAS_MMA
+#define UORF_X3_BIAS_MMA 0
+#endif
 
 namespace uorf {
 
@@ -42,19 +48,22 @@ struct Cfg {
   static constexpr int WPC = 4 * CS;                    // warps per channel
   static constexpr int EPI_WARPS = NCH * WPC;           // 16 (1-pass), 24 / 16 (3-pass)
   static constexpr int THREADS = (EPI_WARPS + NCH) * 32;
-  static constexpr int CHAN_COLS = PASSES == 3 ? 160 : 128;  // TMEM columns per channel (3 x 160 or 4 x 128 <= 512)
   static constexpr int NKP = PASSES == 3 ? 2 : 3;       // K-steps of the positional-encoding operand (3-pass: elements 0..31
                                                         // on the tensor core, element 32 by an fp32 FMA in the epilogue)
-  static constexpr int COL_D = 0;
-  static constexpr int COL_HHI = 64;
-  static constexpr int COL_HLO = 96;                    // 3-pass only
-  static constexpr int COL_PHI = PASSES == 3 ? 128 : 96;
-  static constexpr int COL_PLO = 144;                   // 3-pass only
-  static constexpr int COL_SEL = 120;                   // 1-pass only: 8 columns, one-hot K-step that selects a bias column
+  // TMEM map.  1-pass: channel c owns columns 128c .. 128c+127 = D 64 | H 32 | P 24 | selector 8.
+  // 3-pass: accumulators first (D of channel c at 64c), then one 104-column operand block per channel at 192 + 104c =
+  //         H hi 32 | H lo 32 | P hi 16 | P lo 16 | selector 8   (3 x 64 + 3 x 104 = 504 <= 512 columns)
+  static constexpr int d_col(int c) { return PASSES == 3 ? 64 * c : 128 * c; }
+  static constexpr int a_col(int c) { return PASSES == 3 ? 192 + 104 * c : 128 * c + 64; }
+  static constexpr int COL_HHI = 0;                     // offsets inside the operand block
+  static constexpr int COL_HLO = 32;                    // 3-pass only
+  static constexpr int COL_PHI = PASSES == 3 ? 64 : 32;
+  static constexpr int COL_PLO = 80;                    // 3-pass only
+  static constexpr int COL_SEL = PASSES == 3 ? 96 : 56; // 8 columns: one-hot K-step that selects a bias column
   static constexpr int NPL = PASSES == 3 ? 2 : 1;       // weight planes
   // bias through the tensor core (selector MMA) pays off where the epilogue is the bottleneck (1-pass modes); in the 3-pass
   // modes the extra MMAs lengthen the dependent chain more than two FADDs per pair cost, so the bias stays in the epilogue
-  static constexpr bool BIAS_MMA = PASSES == 1;
+  static constexpr bool BIAS_MMA = PASSES == 1 || UORF_X3_BIAS_MMA;
 };
 
 struct DecFwdParams {
@@ -160,13 +169,16 @@ __device__ __forceinline__ void epilogue32(uint32_t t_d, const float* bias, cons
     float v1 = __uint_as_float(r[4 * q + 1]);
     float v2 = __uint_as_float(r[4 * q + 2]);
     float v3 = __uint_as_float(r[4 * q + 3]);
-    if (PASSES == 3) {
+    if (PASSES == 3 && !UORF_X3_BIAS_MMA) {
       float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
       if (wx != nullptr) {
         const float4 w = *reinterpret_cast<const float4*>(wx + 4 * q);
         b.x = fmaf(w.x, xe, b.x); b.y = fmaf(w.y, xe, b.y); b.z = fmaf(w.z, xe, b.z); b.w = fmaf(w.w, xe, b.w);
       }
       v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
+    } else if (PASSES == 3 && wx != nullptr) {
+      const float4 w = *reinterpret_cast<const float4*>(wx + 4 * q);
+      v0 = fmaf(w.x, xe, v0); v1 = fmaf(w.y, xe, v1); v2 = fmaf(w.z, xe, v2); v3 = fmaf(w.w, xe, v3);
     }
     if (PASSES == 3 && F16) {
       split2_relu<F16>(v0, v1, hi[2 * q], lo[2 * q]);
@@ -289,7 +301,8 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
       const uint32_t idesc64 = make_idesc_f32acc(128, 64, F16);
       const uint32_t idesc_head = make_idesc_f32acc(128, phase == 0 ? 16 : 32, F16);
       const uint32_t w_smem = smem_u32(smem);
-      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base + c * C::CHAN_COLS, 0);
+      const uint32_t tbd = __shfl_sync(0xffffffffu, tmem_base + (c == 0 ? C::d_col(0) : c == 1 ? C::d_col(1) : c == 2 ? C::d_col(2) : C::d_col(3)), 0);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base + (c == 0 ? C::a_col(0) : c == 1 ? C::a_col(1) : c == 2 ? C::a_col(2) : C::a_col(3)), 0);
       for (int it = 0;; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)gridDim.x * ((long long)it * C::NCH + c);
         if (tile >= p.num_tiles) break;
@@ -301,7 +314,7 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
             tc_fence_after();
             {
               bool first = true;
-              const uint32_t t_d = tb + C::COL_D, t_p = tb + C::COL_PHI, t_pl = tb + C::COL_PLO, t_h = tb + C::COL_HHI, t_hl = tb + C::COL_HLO;
+              const uint32_t t_d = tbd, t_p = tb + C::COL_PHI, t_pl = tb + C::COL_PLO, t_h = tb + C::COL_HHI, t_hl = tb + C::COL_HLO;
               if (C::BIAS_MMA && st < 6) {   // bias of this layer: D = selector . bias_tile^T  (K-step = bias_id / 16), hi [+ lo] plane
                 const int bid = st == 0 ? bias_id_slot(s, 0) : st == 3 ? bias_id_slot(s, 1) : bias_id_fixed(st < 3 ? st - 1 : st - 2);
                 const uint64_t db = make_sdesc_sw128(w_smem + kBiasTileOff) + 2 * (bid >> 4);
@@ -333,7 +346,9 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
       const int wic = warp % C::WPC;          // warp within channel
       const int half = wic >> 2;              // which half of the feature columns (3-pass modes); 0 otherwise
       const int t = (wic & 3) * 32 + lane;    // point within the tile == TMEM lane
-      const uint32_t tb = tmem_base + ch * C::CHAN_COLS + ((uint32_t)((warp & 3) * 32) << 16);
+      const uint32_t lane_bits = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t tbd = tmem_base + (PASSES == 3 ? 64 * ch : 128 * ch) + lane_bits;             // accumulator
+      const uint32_t tb = tmem_base + (PASSES == 3 ? 192 + 104 * ch : 128 * ch + 64) + lane_bits;  // operand block
       ChanBars& cb = bars[ch];
       float4* stash = s_stash + (size_t)ch * K * kTileM;
       constexpr int NCOL = 64 / C::CS;        // accumulator columns this thread owns per hidden layer
@@ -420,7 +435,7 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
             for (int h32 = 0; h32 < NCOL / 32; ++h32) {
               const int c32 = col0 + 32 * h32;   // first accumulator column of this 32-column block
               const float* wx = PASSES == 3 && (st == 1 || st == 4) ? s_params + (st == 1 ? kPW0x : kPW3x) + c32 : nullptr;
-              epilogue32<PASSES, F16>(tb + C::COL_D + c32, bias + 32 * h32, wx, x_last, tb + C::COL_HHI + c32 / 2, tb + C::COL_HLO + c32 / 2);
+              epilogue32<PASSES, F16>(tbd + c32, bias + 32 * h32, wx, x_last, tb + C::COL_HHI + c32 / 2, tb + C::COL_HLO + c32 / 2);
             }
             // selector for the bias of the layer the next MMA stage (index st) computes; the head (st == 6) keeps its bias here
             if (C::BIAS_MMA && half == 0 && st < 6)
@@ -434,7 +449,7 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
           if (half == 0) {
             if (phase == 0) {
               uint32_t r[16];
-              tmem_ld16(tb + C::COL_D, r);
+              tmem_ld16(tbd, r);
               tc_wait_ld();
               const float* hb = s_params + kPHeadB;
               float4 o;
@@ -445,7 +460,7 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
               if (valid) p.scratch_bg[pt] = o;
             } else {
               uint32_t r[32];
-              tmem_ld32(tb + C::COL_D, r);
+              tmem_ld32(tbd, r);
               tc_wait_ld();
               const float* hb = s_params + kPHeadB;
               const float* wc2 = s_params + kPWc2;
