@@ -36,6 +36,18 @@
 #define UORF_X3_BIAS_MMA 0
 #endif
 
+// -DUORF_TIMELINE (tuning variant only, scripts/timeline.py): CTA 0 / channel 0 records clock64 stamps of the hand-off
+// points of every stage into a global buffer read back through uorf_debug_timeline()
+#ifdef UORF_TIMELINE
+__device__ long long g_tl_epi[8192];
+__device__ long long g_tl_iss[8192];
+#define TL_EPI(id) do { if (tl_on && tl_ne < 8192) g_tl_epi[tl_ne++] = (clock64() << 8) | (id); } while (0)
+#define TL_ISS(id) do { if (tl_on && tl_ni < 8192) g_tl_iss[tl_ni++] = (clock64() << 8) | (id); } while (0)
+#else
+#define TL_EPI(id)
+#define TL_ISS(id)
+#endif
+
 namespace uorf {
 
 constexpr int kTileM = 128;
@@ -214,20 +226,64 @@ __device__ __forceinline__ float rgb_act(float x) {
 }
 
 // ---- issuer-side helper ---------------------------------------------------------------------------
-// D (+)= A[tmem, K-steps j0..j1) . W[tile]^T, in 1 or 3 passes
-template <int PASSES>
-__device__ __forceinline__ void issue_ksteps(uint32_t t_d, uint32_t t_ahi, uint32_t t_alo, uint32_t w_smem, int j0, int j1,
-                                             uint32_t idesc, bool& first) {
-  const uint64_t dhi = make_sdesc_sw128(w_smem);
-  for (int j = j0; j < j1; ++j) {
-    mma_ts_elect(t_d, t_ahi + 8 * j, dhi + 2 * j, idesc, first ? 0u : 1u);
-    first = false;
+// D (+)= A[tmem, K-steps 0..NK) . W[tile]^T, in 1 or 3 passes, issued under ONE elect.sync: the whole group is a single
+// asm block, so per MMA the issuer spends the tcgen05.mma itself plus the operand moves - not an elect / vote / descriptor
+// rebuild each (the issuer warp shares its scheduler with six epilogue warps; every instruction it saves shortens the
+// dependent chain of its channel).  K-step j: A columns + 8j, B descriptor + 2j (32 bytes >> 4).
+#define UORF_MMA(A, B, ACC) "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [" A "], " B ", %5, " ACC ";\n\t"
+template <int NK, int PASSES>
+__device__ __forceinline__ void mma_group_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                                             uint32_t accumulate) {
+  static_assert((PASSES == 1 && (NK == 3 || NK == 4)) || (PASSES == 3 && (NK == 2 || NK == 4)), "unsupported group");
+  if constexpr (PASSES == 1 && NK == 3) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, t;\n\t.reg .b32 a1, a2;\n\t.reg .b64 h1, h2;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, %6, %6;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\t"
+        "add.u64 h1, %3, 2;\n\tadd.u64 h2, %3, 4;\n\t"
+        UORF_MMA("%1", "%3", "p") UORF_MMA("a1", "h1", "t") UORF_MMA("a2", "h2", "t")
+        "}" ::"r"(d), "r"(a_hi), "r"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate) : "memory");
+  } else if constexpr (PASSES == 1 && NK == 4) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, t;\n\t.reg .b32 a1, a2, a3;\n\t.reg .b64 h1, h2, h3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, %6, %6;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+        "add.u64 h1, %3, 2;\n\tadd.u64 h2, %3, 4;\n\tadd.u64 h3, %3, 6;\n\t"
+        UORF_MMA("%1", "%3", "p") UORF_MMA("a1", "h1", "t") UORF_MMA("a2", "h2", "t") UORF_MMA("a3", "h3", "t")
+        "}" ::"r"(d), "r"(a_hi), "r"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate) : "memory");
+  } else if constexpr (PASSES == 3 && NK == 2) {
+    asm volatile(
+        "{\n\t.reg .pred e, p, t;\n\t.reg .b32 a1, l1;\n\t.reg .b64 h1, w1;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, %6, %6;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 l1, %2, 8;\n\t"
+        "add.u64 h1, %3, 2;\n\tadd.u64 w1, %4, 2;\n\t"
+        UORF_MMA("%1", "%3", "p") UORF_MMA("a1", "h1", "t")      // a_hi . w_hi
+        UORF_MMA("%2", "%3", "t") UORF_MMA("l1", "h1", "t")      // a_lo . w_hi
+        UORF_MMA("%1", "%4", "t") UORF_MMA("a1", "w1", "t")      // a_hi . w_lo
+        "}" ::"r"(d), "r"(a_hi), "r"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred e, p, t;\n\t.reg .b32 a1, a2, a3, l1, l2, l3;\n\t.reg .b64 h1, h2, h3, w1, w2, w3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, %6, %6;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+        "add.u32 l1, %2, 8;\n\tadd.u32 l2, %2, 16;\n\tadd.u32 l3, %2, 24;\n\t"
+        "add.u64 h1, %3, 2;\n\tadd.u64 h2, %3, 4;\n\tadd.u64 h3, %3, 6;\n\t"
+        "add.u64 w1, %4, 2;\n\tadd.u64 w2, %4, 4;\n\tadd.u64 w3, %4, 6;\n\t"
+        UORF_MMA("%1", "%3", "p") UORF_MMA("a1", "h1", "t") UORF_MMA("a2", "h2", "t") UORF_MMA("a3", "h3", "t")
+        UORF_MMA("%2", "%3", "t") UORF_MMA("l1", "h1", "t") UORF_MMA("l2", "h2", "t") UORF_MMA("l3", "h3", "t")
+        UORF_MMA("%1", "%4", "t") UORF_MMA("a1", "w1", "t") UORF_MMA("a2", "w2", "t") UORF_MMA("a3", "w3", "t")
+        "}" ::"r"(d), "r"(a_hi), "r"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate) : "memory");
   }
-  if (PASSES == 3) {
-    const uint64_t dlo = make_sdesc_sw128(w_smem + kPlaneBytes);
-    for (int j = j0; j < j1; ++j) mma_ts_elect(t_d, t_alo + 8 * j, dhi + 2 * j, idesc, 1u);
-    for (int j = j0; j < j1; ++j) mma_ts_elect(t_d, t_ahi + 8 * j, dlo + 2 * j, idesc, 1u);
-  }
+}
+#undef UORF_MMA
+template <int NK, int PASSES>
+__device__ __forceinline__ void issue_group(uint32_t t_d, uint32_t t_ahi, uint32_t t_alo, uint32_t w_smem, uint32_t idesc, bool& first) {
+  mma_group_ts<NK, PASSES>(t_d, t_ahi, t_alo, make_sdesc_sw128(w_smem), make_sdesc_sw128(w_smem + kPlaneBytes), idesc, first ? 0u : 1u);
+  first = false;
 }
 
 template <int PASSES, bool F16, int NCH>
@@ -294,15 +350,22 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
     mbar_wait(&bar_w, phase & 1, p.err_flag, 100 + phase);
 
     if (warp >= kEpiWarps) {
-      // =========================== MMA issuer of channel (warp - 16) ===========================
-      // warp-uniform values are routed through a shuffle so the compiler keeps the MMA operands in uniform registers
-      // (otherwise every tcgen05.mma is wrapped in an elect / R2UR.BROADCAST waterfall loop)
-      const int c = __shfl_sync(0xffffffffu, warp - kEpiWarps, 0);
+      // =========================== MMA issuer of channel (warp - EPI_WARPS) ===========================
+      // The loop is instantiated once per channel with the channel index as a compile-time constant: every MMA operand is
+      // then derived from kernel parameters, constants and one shared-memory word, so the compiler keeps descriptors and
+      // TMEM addresses on the uniform datapath (a runtime channel index costs ~10 vector instructions + R2URs per MMA, and
+      // the issuer shares its scheduler with six epilogue warps: the hand-off timeline showed 80 cycles per MMA issued).
+      auto issuer = [&](auto CH) {
+      constexpr int c = decltype(CH)::value;
       const uint32_t idesc64 = make_idesc_f32acc(128, 64, F16);
       const uint32_t idesc_head = make_idesc_f32acc(128, phase == 0 ? 16 : 32, F16);
       const uint32_t w_smem = smem_u32(smem);
-      const uint32_t tbd = __shfl_sync(0xffffffffu, tmem_base + (c == 0 ? C::d_col(0) : c == 1 ? C::d_col(1) : c == 2 ? C::d_col(2) : C::d_col(3)), 0);
-      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base + (c == 0 ? C::a_col(0) : c == 1 ? C::a_col(1) : c == 2 ? C::a_col(2) : C::a_col(3)), 0);
+      const uint32_t tbd = tmem_base + C::d_col(c);
+      const uint32_t tb = tmem_base + C::a_col(c);
+#ifdef UORF_TIMELINE
+      const bool tl_on = blockIdx.x == 0 && c == 0 && lane == 0 && phase == 1;
+      int tl_ni = 0;
+#endif
       for (int it = 0;; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)gridDim.x * ((long long)it * C::NCH + c);
         if (tile >= p.num_tiles) break;
@@ -312,6 +375,7 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
             mbar_wait(&bars[c].a_full, n_a & 1, p.err_flag, 200 + st);
             ++n_a;
             tc_fence_after();
+            TL_ISS(0x10 + st);
             {
               bool first = true;
               const uint32_t t_d = tbd, t_p = tb + C::COL_PHI, t_pl = tb + C::COL_PLO, t_h = tb + C::COL_HHI, t_hl = tb + C::COL_HLO;
@@ -323,22 +387,30 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
                 first = false;
               }
               switch (st) {
-                case 0: issue_ksteps<PASSES>(t_d, t_p, t_pl, w_smem + 0 * kTileBytes, 0, C::NKP, idesc64, first); break;
-                case 1: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 1 * kTileBytes, 0, 4, idesc64, first); break;
-                case 2: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 2 * kTileBytes, 0, 4, idesc64, first); break;
+                case 0: issue_group<C::NKP, PASSES>(t_d, t_p, t_pl, w_smem + 0 * kTileBytes, idesc64, first); break;
+                case 1: issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 1 * kTileBytes, idesc64, first); break;
+                case 2: issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 2 * kTileBytes, idesc64, first); break;
                 case 3:
-                  issue_ksteps<PASSES>(t_d, t_p, t_pl, w_smem + 3 * kTileBytes, 0, C::NKP, idesc64, first);
-                  issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 4 * kTileBytes, 0, 4, idesc64, first);
+                  issue_group<C::NKP, PASSES>(t_d, t_p, t_pl, w_smem + 3 * kTileBytes, idesc64, first);
+                  issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 4 * kTileBytes, idesc64, first);
                   break;
-                case 4: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 5 * kTileBytes, 0, 4, idesc64, first); break;
-                case 5: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 6 * kTileBytes, 0, 4, idesc64, first); break;
-                default: issue_ksteps<PASSES>(t_d, t_h, t_hl, w_smem + 7 * kTileBytes, 0, 4, idesc_head, first); break;
+                case 4: issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 5 * kTileBytes, idesc64, first); break;
+                case 5: issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 6 * kTileBytes, idesc64, first); break;
+                default: issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 7 * kTileBytes, idesc_head, first); break;
               }
               tc_commit_elect(&bars[c].d_full);
+              TL_ISS(0x20 + st);
             }
             __syncwarp();
           }
         }
+      }
+      };
+      switch (warp - kEpiWarps) {
+        case 0: issuer(std::integral_constant<int, 0>{}); break;
+        case 1: issuer(std::integral_constant<int, 1>{}); break;
+        case 2: if constexpr (C::NCH > 2) issuer(std::integral_constant<int, 2>{}); break;
+        default: if constexpr (C::NCH > 3) issuer(std::integral_constant<int, 3>{}); break;
       }
     } else {
       // =========================== epilogue warps ===========================
@@ -354,6 +426,10 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
       constexpr int NCOL = 64 / C::CS;        // accumulator columns this thread owns per hidden layer
       const int col0 = half * NCOL;
       // wait for the MMAs of the current stage
+#ifdef UORF_TIMELINE
+      const bool tl_on = blockIdx.x == 0 && ch == 0 && wic == 0 && lane == 0 && phase == 1;
+      int tl_ne = 0;
+#endif
       auto wait_d = [&](int site) {
         if (C::CS == 2) {
           // 3-pass modes (8 warps per channel): one polling warp, the others sleep in a hardware barrier and spend no issue
@@ -365,6 +441,7 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
         }
         ++n_d;
         tc_fence_after();
+        TL_EPI(0x30 + (site & 15));
       };
       for (int it = 0;; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)gridDim.x * ((long long)it * C::NCH + ch);
@@ -423,6 +500,7 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(&cb.a_full);
+          TL_EPI(0x40);
 
           // ---- stages 1..6: hidden layers ----
           const float* sb = s_params + kParamFloats + s * kSlotBiasFloats;
@@ -443,6 +521,7 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
             tc_wait_st();
             tc_fence_before();
             mbar_arrive(&cb.a_full);
+            TL_EPI(0x40 + st);
           }
           // ---- stage 7: heads (computed by the first column half; every thread consumes the barrier phase) ----
           wait_d(307);
@@ -573,3 +652,13 @@ int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, c
 }
 
 }  // namespace uorf
+
+#ifdef UORF_TIMELINE
+extern "C" int uorf_debug_timeline(long long* epi, long long* iss, int n) {
+  if (n > 8192) n = 8192;
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(epi, g_tl_epi, n * sizeof(long long)) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(iss, g_tl_iss, n * sizeof(long long)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
