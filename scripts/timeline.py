@@ -59,6 +59,12 @@ for st in range(7):
     t4 = (ea[st + 1][:nslot] - nxt).mean() if st < 6 else float("nan")
     tot += t1 + t2 + t3 + (0 if st == 6 else t4)
     print(f" {st}  | {t1:8.0f}            | {t2:8.0f}             | {t3:8.0f}              | {t4:8.0f}")
+if (ei == 0x51).any():
+    print(" epilogue split (stages 1..6): wake -> ld+math+st issued -> st complete -> arrive")
+    for st in range(1, 7):
+        w = ew[:, st - 1]
+        b = et[ei == 0x50 + st][:nslot]; c2 = et[ei == 0x60 + st][:nslot]; a = ea[st][:nslot]
+        print(f"   st {st}: {(b - w).mean():7.0f} {(c2 - b).mean():7.0f} {(a - c2).mean():7.0f}")
 print(f"sum over the 7 stages: {tot:.0f} cycles per slot (excluding the head epilogue / composition)")
 span = (ea[0][1:nslot] - ea[0][: nslot - 1])
 print(f"slot period (arrive0 -> arrive0): mean {span.mean():.0f}, median {np.median(span):.0f}")

@@ -292,20 +292,25 @@ __device__ __forceinline__ uint32_t pack2(float e0, float e1) {
   else     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
   return d;
 }
+// residual of a 16-bit pair against its fp32 source: r = e - float(hi half), ONE mixed-precision FMA per element
+// (fma.rn.f32.f16 / .bf16, SASS FHFMA, reads the half straight out of the packed register: no unpack, no separate subtract)
+template <bool F16>
+__device__ __forceinline__ void residual2(float e0, float e1, uint32_t hi, float& r0, float& r1) {
+  if (F16)
+    asm("{\n\t.reg .f16 x0, x1, m;\n\tmov.b32 {x0, x1}, %4;\n\tmov.b16 m, 0xBC00;\n\t"
+        "fma.rn.f32.f16 %0, x0, m, %2;\n\tfma.rn.f32.f16 %1, x1, m, %3;\n\t}"
+        : "=f"(r0), "=f"(r1) : "f"(e0), "f"(e1), "r"(hi));
+  else
+    asm("{\n\t.reg .b16 x0, x1, m;\n\tmov.b32 {x0, x1}, %4;\n\tmov.b16 m, 0xBF80;\n\t"
+        "fma.rn.f32.bf16 %0, x0, m, %2;\n\tfma.rn.f32.bf16 %1, x1, m, %3;\n\t}"
+        : "=f"(r0), "=f"(r1) : "f"(e0), "f"(e1), "r"(hi));
+}
 template <bool F16>
 __device__ __forceinline__ void split2(float e0, float e1, uint32_t& hi, uint32_t& lo) {
   hi = pack2<F16>(e0, e1);
-  float h0, h1;
-  if (F16) {
-    const __half2 h = *reinterpret_cast<const __half2*>(&hi);
-    const float2 f = __half22float2(h);
-    h0 = f.x;
-    h1 = f.y;
-  } else {
-    h0 = __uint_as_float(hi << 16);
-    h1 = __uint_as_float(hi & 0xFFFF0000u);
-  }
-  lo = pack2<F16>(e0 - h0, e1 - h1);
+  float r0, r1;
+  residual2<F16>(e0, e1, hi, r0, r1);
+  lo = pack2<F16>(r0, r1);
 }
 // ReLU fused into the conversion (cvt.relu): pack2_relu(e0, e1) = pack2(max(e0,0), max(e1,0)) in one instruction.
 // split2_relu rounds the hi part TOWARD ZERO, so for x >= 0 the residual x - hi is >= 0, and for x < 0 hi = 0 and the
@@ -321,16 +326,9 @@ template <bool F16>
 __device__ __forceinline__ void split2_relu(float e0, float e1, uint32_t& hi, uint32_t& lo) {
   if (F16) asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(e1), "f"(e0));
   else     asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(e1), "f"(e0));
-  float h0, h1;
-  if (F16) {
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-    h0 = f.x;
-    h1 = f.y;
-  } else {
-    h0 = __uint_as_float(hi << 16);
-    h1 = __uint_as_float(hi & 0xFFFF0000u);
-  }
-  lo = pack2_relu<F16>(e0 - h0, e1 - h1);
+  float r0, r1;
+  residual2<F16>(e0, e1, hi, r0, r1);
+  lo = pack2_relu<F16>(r0, r1);
 }
 // scalar versions for the weight image
 template <bool F16>

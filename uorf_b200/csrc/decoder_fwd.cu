@@ -518,7 +518,9 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
             // selector for the bias of the layer the next MMA stage (index st) computes; the head (st == 6) keeps its bias here
             if (C::BIAS_MMA && half == 0 && st < 6)
               write_selector<F16>(tb + C::COL_SEL, st == 3 ? bias_id_slot(s, 1) : bias_id_fixed(st < 3 ? st - 1 : st - 2));
+            TL_EPI(0x50 + st);
             tc_wait_st();
+            TL_EPI(0x60 + st);
             tc_fence_before();
             mbar_arrive(&cb.a_full);
             TL_EPI(0x40 + st);
