@@ -30,6 +30,17 @@
 #include "decoder_layout.h"
 #include "../../include/uorf_b200.h"
 
+// Tuning experiments kept as compile-time switches (uorf_b200/build.py --tag builds a variant; scripts/gpu_variants.sh A/Bs it):
+// One mbarrier arrival per epilogue WARP (after __syncwarp) instead of one per thread: measured 2 % slower, off.
+#ifndef UORF_WARP_ARRIVE
+#define UORF_WARP_ARRIVE 0
+#endif
+// 3-pass modes: the epilogue writes the NEXT layer's bias into the accumulator columns it has just read (tcgen05.st) and the
+// layer's first MMA accumulates on top of it: 2 instructions per 32 columns instead of 32 FADDs in the following epilogue.
+// Measured neutral (the epilogue is bound by its dependent chain, not by issue slots), off.
+#ifndef UORF_X3_BIAS_PRELOAD
+#define UORF_X3_BIAS_PRELOAD 0
+#endif
 // Bias through the selector MMA in the 3-pass modes too (tuning experiment, off: measured 7 % (bf16x3) to 20 % (fp16x3) SLOWER -
 // the two extra MMAs per layer sit on the dependent chain, which is what bounds these modes)
 #ifndef UORF_X3_BIAS_MMA
@@ -181,7 +192,7 @@ __device__ __forceinline__ void epilogue32(uint32_t t_d, const float* bias, cons
     float v1 = __uint_as_float(r[4 * q + 1]);
     float v2 = __uint_as_float(r[4 * q + 2]);
     float v3 = __uint_as_float(r[4 * q + 3]);
-    if (PASSES == 3 && !UORF_X3_BIAS_MMA) {
+    if (PASSES == 3 && !UORF_X3_BIAS_MMA && !UORF_X3_BIAS_PRELOAD) {
       float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
       if (wx != nullptr) {
         const float4 w = *reinterpret_cast<const float4*>(wx + 4 * q);
@@ -207,6 +218,21 @@ __device__ __forceinline__ void epilogue32(uint32_t t_d, const float* bias, cons
   if (PASSES == 3) tmem_st16(t_hlo, lo);
 }
 
+// 32 accumulator columns <- bias[0..31] (the same vector on every row / TMEM lane)
+__device__ __forceinline__ void preload_bias32(uint32_t t_d, const float* bias) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t r[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + 16 * h + 4 * q);
+      r[4 * q + 0] = __float_as_uint(b.x); r[4 * q + 1] = __float_as_uint(b.y);
+      r[4 * q + 2] = __float_as_uint(b.z); r[4 * q + 3] = __float_as_uint(b.w);
+    }
+    tmem_st16(t_d + 16 * h, r);
+  }
+}
+
 // one-hot selector K-step (16 values -> 8 words) with 1.0 at position (bias_id & 15)
 template <bool F16>
 __device__ __forceinline__ void write_selector(uint32_t t_sel, int bias_id) {
@@ -223,6 +249,16 @@ template <bool FAST>
 __device__ __forceinline__ float rgb_act(float x) {
   if (FAST) return __fdividef(1.f, 1.f + __expf(-2.f * x));
   return (tanhf(x) + 1.f) * 0.5f;
+}
+
+// hand-off epilogue -> issuer: every thread has completed and fenced its tcgen05.st; the warp converges and one lane arrives
+__device__ __forceinline__ void chan_arrive(uint64_t* bar) {
+#if UORF_WARP_ARRIVE
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+#else
+  mbar_arrive(bar);
+#endif
 }
 
 // ---- issuer-side helper ---------------------------------------------------------------------------
@@ -307,7 +343,7 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
     for (int c = 0; c < C::NCH; ++c) {
-      mbar_init(&bars[c].a_full, kTileM * C::CS);
+      mbar_init(&bars[c].a_full, UORF_WARP_ARRIVE ? C::WPC : kTileM * C::CS);
       mbar_init(&bars[c].d_full, 1);
     }
     fence_mbar_init();
@@ -377,7 +413,7 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
             tc_fence_after();
             TL_ISS(0x10 + st);
             {
-              bool first = true;
+              bool first = !(PASSES == 3 && UORF_X3_BIAS_PRELOAD && st < 6);   // preloaded bias: accumulate from the first K-step
               const uint32_t t_d = tbd, t_p = tb + C::COL_PHI, t_pl = tb + C::COL_PLO, t_h = tb + C::COL_HHI, t_hl = tb + C::COL_HLO;
               if (C::BIAS_MMA && st < 6) {   // bias of this layer: D = selector . bias_tile^T  (K-step = bias_id / 16), hi [+ lo] plane
                 const int bid = st == 0 ? bias_id_slot(s, 0) : st == 3 ? bias_id_slot(s, 1) : bias_id_fixed(st < 3 ? st - 1 : st - 2);
@@ -496,10 +532,11 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
             if (PASSES == 3) x_last = v[kPosencMma3];   // cos(16 z): added by FMA in the epilogues of layers before.0 / after.0
           }
           if (phase == 1 && p.outside && valid && half == 0) p.outside[(long long)s * p.P + pt] = outside ? 1 : 0;
+          if (PASSES == 3 && UORF_X3_BIAS_PRELOAD) preload_bias32(tbd + col0, s_params + kParamFloats + s * kSlotBiasFloats + col0);
           if (C::BIAS_MMA && half == 0) write_selector<F16>(tb + C::COL_SEL, bias_id_slot(s, 0));
           tc_wait_st();
           tc_fence_before();
-          mbar_arrive(&cb.a_full);
+          chan_arrive(&cb.a_full);
           TL_EPI(0x40);
 
           // ---- stages 1..6: hidden layers ----
@@ -515,6 +552,9 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
               const float* wx = PASSES == 3 && (st == 1 || st == 4) ? s_params + (st == 1 ? kPW0x : kPW3x) + c32 : nullptr;
               epilogue32<PASSES, F16>(tbd + c32, bias + 32 * h32, wx, x_last, tb + C::COL_HHI + c32 / 2, tb + C::COL_HLO + c32 / 2);
             }
+            if (PASSES == 3 && UORF_X3_BIAS_PRELOAD && st < 6)   // bias of the layer MMA stage `st` computes (read back at st + 1)
+              preload_bias32(tbd + col0, (st == 1 ? s_params + kPB1 : st == 2 ? s_params + kPB2 : st == 3 ? sb + 64
+                                          : st == 4 ? s_params + kPA1 : s_params + kPA2) + col0);
             // selector for the bias of the layer the next MMA stage (index st) computes; the head (st == 6) keeps its bias here
             if (C::BIAS_MMA && half == 0 && st < 6)
               write_selector<F16>(tb + C::COL_SEL, st == 3 ? bias_id_slot(s, 1) : bias_id_fixed(st < 3 ? st - 1 : st - 2));
@@ -522,7 +562,7 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
             tc_wait_st();
             TL_EPI(0x60 + st);
             tc_fence_before();
-            mbar_arrive(&cb.a_full);
+            chan_arrive(&cb.a_full);
             TL_EPI(0x40 + st);
           }
           // ---- stage 7: heads (computed by the first column half; every thread consumes the barrier phase) ----
