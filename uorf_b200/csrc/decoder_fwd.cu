@@ -30,6 +30,11 @@
 #include "decoder_layout.h"
 #include "../../include/uorf_b200.h"
 
+// Diagnostic: only the first UORF_ACTIVE_CHANNELS channels take tiles (the others idle; output is then incomplete) - used with
+// the timeline variant to see a channel's uncontended stage times.
+#ifndef UORF_ACTIVE_CHANNELS
+#define UORF_ACTIVE_CHANNELS 99
+#endif
 // Tuning experiments kept as compile-time switches (uorf_b200/build.py --tag builds a variant; scripts/gpu_variants.sh A/Bs it):
 // One mbarrier arrival per epilogue WARP (after __syncwarp) instead of one per thread: measured 2 % slower, off.
 #ifndef UORF_WARP_ARRIVE
@@ -404,41 +409,47 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
 #endif
       for (int it = 0;; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)gridDim.x * ((long long)it * C::NCH + c);
-        if (tile >= p.num_tiles) break;
-        for (int s = 0; s < nslots; ++s) {
-#pragma unroll 1
-          for (int st = 0; st < 7; ++st) {
-            mbar_wait(&bars[c].a_full, n_a & 1, p.err_flag, 200 + st);
-            ++n_a;
-            tc_fence_after();
-            TL_ISS(0x10 + st);
-            {
-              bool first = !(PASSES == 3 && UORF_X3_BIAS_PRELOAD && st < 6);   // preloaded bias: accumulate from the first K-step
-              const uint32_t t_d = tbd, t_p = tb + C::COL_PHI, t_pl = tb + C::COL_PLO, t_h = tb + C::COL_HHI, t_hl = tb + C::COL_HLO;
-              if (C::BIAS_MMA && st < 6) {   // bias of this layer: D = selector . bias_tile^T  (K-step = bias_id / 16), hi [+ lo] plane
-                const int bid = st == 0 ? bias_id_slot(s, 0) : st == 3 ? bias_id_slot(s, 1) : bias_id_fixed(st < 3 ? st - 1 : st - 2);
-                const uint64_t db = make_sdesc_sw128(w_smem + kBiasTileOff) + 2 * (bid >> 4);
-                mma_ts_elect(t_d, tb + C::COL_SEL, db, idesc64, 0u);
-                if (PASSES == 3) mma_ts_elect(t_d, tb + C::COL_SEL, make_sdesc_sw128(w_smem + kPlaneBytes + kBiasTileOff) + 2 * (bid >> 4), idesc64, 1u);
-                first = false;
-              }
-              switch (st) {
-                case 0: issue_group<C::NKP, PASSES>(t_d, t_p, t_pl, w_smem + 0 * kTileBytes, idesc64, first); break;
-                case 1: issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 1 * kTileBytes, idesc64, first); break;
-                case 2: issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 2 * kTileBytes, idesc64, first); break;
-                case 3:
-                  issue_group<C::NKP, PASSES>(t_d, t_p, t_pl, w_smem + 3 * kTileBytes, idesc64, first);
-                  issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 4 * kTileBytes, idesc64, first);
-                  break;
-                case 4: issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 5 * kTileBytes, idesc64, first); break;
-                case 5: issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 6 * kTileBytes, idesc64, first); break;
-                default: issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 7 * kTileBytes, idesc_head, first); break;
-              }
-              tc_commit_elect(&bars[c].d_full);
-              TL_ISS(0x20 + st);
-            }
-            __syncwarp();
+        if (tile >= p.num_tiles || (UORF_ACTIVE_CHANNELS < C::NCH && c >= UORF_ACTIVE_CHANNELS)) break;
+        // the seven stages are instantiated separately (compile-time stage index): tile addresses, K-step counts and descriptors
+        // are constants on the uniform datapath and the issuer's path between wake-up and commit is short straight-line code
+        // (the loop + switch form spent ~500 cycles there per stage on branches and descriptor rebuilds - hand-off timeline)
+        auto stage = [&](auto ST, int s) {
+          constexpr int st = decltype(ST)::value;
+          mbar_wait(&bars[c].a_full, n_a & 1, p.err_flag, 200 + st);
+          ++n_a;
+          tc_fence_after();
+          TL_ISS(0x10 + st);
+          bool first = !(PASSES == 3 && UORF_X3_BIAS_PRELOAD && st < 6);   // preloaded bias: accumulate from the first K-step
+          const uint32_t t_d = tbd, t_p = tb + C::COL_PHI, t_pl = tb + C::COL_PLO, t_h = tb + C::COL_HHI, t_hl = tb + C::COL_HLO;
+          if (C::BIAS_MMA && st < 6) {   // bias of this layer: D = selector . bias_tile^T  (K-step = bias_id / 16), hi [+ lo] plane
+            const int bid = st == 0 ? bias_id_slot(s, 0) : st == 3 ? bias_id_slot(s, 1) : bias_id_fixed(st < 3 ? st - 1 : st - 2);
+            const uint64_t db = make_sdesc_sw128(w_smem + kBiasTileOff) + 2 * (bid >> 4);
+            mma_ts_elect(t_d, tb + C::COL_SEL, db, idesc64, 0u);
+            if (PASSES == 3) mma_ts_elect(t_d, tb + C::COL_SEL, make_sdesc_sw128(w_smem + kPlaneBytes + kBiasTileOff) + 2 * (bid >> 4), idesc64, 1u);
+            first = false;
           }
+          if constexpr (st == 0) {
+            issue_group<C::NKP, PASSES>(t_d, t_p, t_pl, w_smem + 0 * kTileBytes, idesc64, first);
+          } else if constexpr (st == 3) {
+            issue_group<C::NKP, PASSES>(t_d, t_p, t_pl, w_smem + 3 * kTileBytes, idesc64, first);
+            issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 4 * kTileBytes, idesc64, first);
+          } else if constexpr (st == 6) {
+            issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 7 * kTileBytes, idesc_head, first);
+          } else {
+            issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + (st < 3 ? st : st + 1) * kTileBytes, idesc64, first);
+          }
+          tc_commit_elect(&bars[c].d_full);
+          TL_ISS(0x20 + st);
+          __syncwarp();
+        };
+        for (int s = 0; s < nslots; ++s) {
+          stage(std::integral_constant<int, 0>{}, s);
+          stage(std::integral_constant<int, 1>{}, s);
+          stage(std::integral_constant<int, 2>{}, s);
+          stage(std::integral_constant<int, 3>{}, s);
+          stage(std::integral_constant<int, 4>{}, s);
+          stage(std::integral_constant<int, 5>{}, s);
+          stage(std::integral_constant<int, 6>{}, s);
         }
       }
       };
@@ -481,7 +492,7 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
       };
       for (int it = 0;; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)gridDim.x * ((long long)it * C::NCH + ch);
-        if (tile >= p.num_tiles) break;
+        if (tile >= p.num_tiles || (UORF_ACTIVE_CHANNELS < C::NCH && ch >= UORF_ACTIVE_CHANNELS)) break;
         const long long pt = tile * kTileM + t;
         const bool valid = pt < p.P;
         // coordinates are fetched one slot ahead (and once per tile when all fg slots share them, fg_slot_stride == 0), so
