@@ -217,6 +217,27 @@ __device__ __forceinline__ void mma_ss_elect(uint32_t d_tmem, uint64_t a_desc, u
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// NK accumulating MMAs (both operands from shared memory) under ONE elect.sync, in a single asm block: K-step j uses
+// a_desc + j * ASTEP and b_desc + j * BSTEP (descriptor units of 16 bytes).  The first MMA overwrites D when accumulate == 0.
+#define UORF_SS_FIRST "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, p;\n\t"
+#define UORF_SS_NEXT "add.u64 a, a, %5;\n\tadd.u64 b, b, %6;\n\t@e tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, t;\n\t"
+#define UORF_SS_HEAD                                                                                      \
+  "{\n\t.reg .pred e, p, t;\n\t.reg .b64 a, b;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t" \
+  "setp.eq.b32 t, %4, %4;\n\tmov.b64 a, %1;\n\tmov.b64 b, %2;\n\t"
+#define UORF_SS_ARGS ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "l"((uint64_t)ASTEP), "l"((uint64_t)BSTEP) : "memory"
+template <int NK, int ASTEP, int BSTEP>
+__device__ __forceinline__ void mma_group_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  static_assert(NK == 2 || NK == 3 || NK == 4 || NK == 8, "unsupported group");
+  if constexpr (NK == 2) asm volatile(UORF_SS_HEAD UORF_SS_FIRST UORF_SS_NEXT "}" UORF_SS_ARGS);
+  else if constexpr (NK == 3) asm volatile(UORF_SS_HEAD UORF_SS_FIRST UORF_SS_NEXT UORF_SS_NEXT "}" UORF_SS_ARGS);
+  else if constexpr (NK == 4) asm volatile(UORF_SS_HEAD UORF_SS_FIRST UORF_SS_NEXT UORF_SS_NEXT UORF_SS_NEXT "}" UORF_SS_ARGS);
+  else asm volatile(UORF_SS_HEAD UORF_SS_FIRST UORF_SS_NEXT UORF_SS_NEXT UORF_SS_NEXT UORF_SS_NEXT UORF_SS_NEXT UORF_SS_NEXT UORF_SS_NEXT "}"
+                    UORF_SS_ARGS);
+}
+#undef UORF_SS_FIRST
+#undef UORF_SS_NEXT
+#undef UORF_SS_HEAD
+#undef UORF_SS_ARGS
 __device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"

@@ -19,6 +19,8 @@
 //
 // Outputs are per-CTA partial sums; decoder_bwd_finalize reduces them in a fixed order (deterministic) and unfolds the
 // folded head (f_color.0 . f_after_latent) and the hoisted slot-latent columns into the reference's parameter shapes.
+#include <type_traits>
+
 #include "common.cuh"
 #include "decoder_layout.h"
 #include "../../include/uorf_b200.h"
@@ -249,43 +251,45 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
         tc_fence_after();
       };
       // forward GEMM, both operands K-major: D (+)= X[tile xi] . W[tile wi]^T
-      auto fwd = [&](int xi, int wi, int ksteps, uint32_t idesc, bool first) {
-        const uint64_t da = make_sdesc_sw128(x_s + xi * 16384), db = make_sdesc_sw128(w_s + wi * kTileBytes);
-        for (int j = 0; j < ksteps; ++j) mma_ss_elect(tbu + kBColD, da + 2 * j, db + 2 * j, idesc, (first && j == 0) ? 0u : 1u);
+      // every group of K-steps is one asm block under a single elect (common.cuh: mma_group_ss); tile indices and K-step
+      // counts are compile-time, so the issuer's path between wake-up and commit is short straight-line code
+      auto fwd = [&](auto XI, auto WI, auto NKS, uint32_t idesc, bool first) {
+        constexpr int xi = decltype(XI)::value, wi = decltype(WI)::value, nk = decltype(NKS)::value;
+        mma_group_ss<nk, 2, 2>(tbu + kBColD, make_sdesc_sw128(x_s + xi * 16384), make_sdesc_sw128(w_s + wi * kTileBytes), idesc, first ? 0u : 1u);
       };
       // dX = dZ[buf] . W[tile wi] : A K-major (K = out features), B = MN-major view of the weight tile
-      auto dx = [&](int buf, int wi, int ksteps) {
-        const uint64_t da = make_sdesc_sw128(dz_s + buf * 16384), db = sdesc_mn(w_s + wi * kTileBytes);
-        for (int j = 0; j < ksteps; ++j) mma_ss_elect(tbu + kBColD, da + 2 * j, db + 128 * j, id_dx, j ? 1u : 0u);
+      auto dx = [&](auto BUF, auto WI, auto NKS) {
+        constexpr int buf = decltype(BUF)::value, wi = decltype(WI)::value, nk = decltype(NKS)::value;
+        mma_group_ss<nk, 2, 128>(tbu + kBColD, make_sdesc_sw128(dz_s + buf * 16384), sdesc_mn(w_s + wi * kTileBytes), id_dx, 0u);
       };
       // dW[acc] += dZ[buf]^T . X[tile xi] : both MN-major views, contraction over the 128 points (8 K-steps)
-      auto dw = [&](int acc, int buf, int xi, uint32_t idesc) {
-        const uint64_t da = sdesc_mn(dz_s + buf * 16384), db = sdesc_mn(x_s + xi * 16384);
-        const uint32_t t_acc = acc_taddr(tbu, acc);
+      auto dw = [&](auto ACC, auto BUF, auto XI, uint32_t idesc) {
+        constexpr int acc = decltype(ACC)::value, buf = decltype(BUF)::value, xi = decltype(XI)::value;
         const bool live = (acc_live >> acc) & 1u;
-        for (int j = 0; j < 8; ++j) mma_ss_elect(t_acc, da + 128 * j, db + 128 * j, idesc, (live || j) ? 1u : 0u);
+        mma_group_ss<8, 128, 128>(acc_taddr(tbu, acc), sdesc_mn(dz_s + buf * 16384), sdesc_mn(x_s + xi * 16384), idesc, live ? 1u : 0u);
         acc_live |= 1u << acc;
       };
+#define I_(n) std::integral_constant<int, n>{}
       for (int it = 0;; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)gridDim.x * it;
         if (tile >= p.num_tiles) break;
         for (int s = 0; s < nslots; ++s) {
           // ---- forward recompute ----
-          wait_a(200); fwd(0, 0, 3, id_fwd64, true); tc_commit_elect(&bar_d);
-          wait_a(201); fwd(1, 1, 4, id_fwd64, true); tc_commit_elect(&bar_d);
-          wait_a(202); fwd(2, 2, 4, id_fwd64, true); tc_commit_elect(&bar_d);
-          wait_a(203); fwd(0, 3, 3, id_fwd64, true); fwd(3, 4, 4, id_fwd64, false); tc_commit_elect(&bar_d);
-          wait_a(204); fwd(4, 5, 4, id_fwd64, true); tc_commit_elect(&bar_d);
-          wait_a(205); fwd(5, 6, 4, id_fwd64, true); tc_commit_elect(&bar_d);
-          wait_a(206); fwd(6, 7, 4, id_fwd_head, true); tc_commit_elect(&bar_d);
+          wait_a(200); fwd(I_(0), I_(0), I_(3), id_fwd64, true); tc_commit_elect(&bar_d);
+          wait_a(201); fwd(I_(1), I_(1), I_(4), id_fwd64, true); tc_commit_elect(&bar_d);
+          wait_a(202); fwd(I_(2), I_(2), I_(4), id_fwd64, true); tc_commit_elect(&bar_d);
+          wait_a(203); fwd(I_(0), I_(3), I_(3), id_fwd64, true); fwd(I_(3), I_(4), I_(4), id_fwd64, false); tc_commit_elect(&bar_d);
+          wait_a(204); fwd(I_(4), I_(5), I_(4), id_fwd64, true); tc_commit_elect(&bar_d);
+          wait_a(205); fwd(I_(5), I_(6), I_(4), id_fwd64, true); tc_commit_elect(&bar_d);
+          wait_a(206); fwd(I_(6), I_(7), I_(4), id_fwd_head, true); tc_commit_elect(&bar_d);
           // ---- backward ----   (dZ buffers alternate: head -> 0, layer 5 -> 1, 4 -> 0, 3 -> 1, 2 -> 0, 1 -> 1, 0 -> 0)
-          wait_a(207); dx(0, 7, 2); tc_commit_elect(&bar_d); dw(7, 0, 6, id_dw64);
-          wait_a(208); dx(1, 6, 4); tc_commit_elect(&bar_d); dw(6, 1, 5, id_dw64);
-          wait_a(209); dx(0, 5, 4); tc_commit_elect(&bar_d); dw(5, 0, 4, id_dw64);
-          wait_a(210); dx(1, 4, 4); tc_commit_elect(&bar_d); dw(4, 1, 3, id_dw64); dw(3, 1, 0, id_dw48);
-          wait_a(211); dx(0, 2, 4); tc_commit_elect(&bar_d); dw(2, 0, 2, id_dw64);
-          wait_a(212); dx(1, 1, 4); tc_commit_elect(&bar_d); dw(1, 1, 1, id_dw64);
-          wait_a(213); dw(0, 0, 0, id_dw48); tc_commit_elect(&bar_d);   // all tiles free for the next slot once this lands
+          wait_a(207); dx(I_(0), I_(7), I_(2)); tc_commit_elect(&bar_d); dw(I_(7), I_(0), I_(6), id_dw64);
+          wait_a(208); dx(I_(1), I_(6), I_(4)); tc_commit_elect(&bar_d); dw(I_(6), I_(1), I_(5), id_dw64);
+          wait_a(209); dx(I_(0), I_(5), I_(4)); tc_commit_elect(&bar_d); dw(I_(5), I_(0), I_(4), id_dw64);
+          wait_a(210); dx(I_(1), I_(4), I_(4)); tc_commit_elect(&bar_d); dw(I_(4), I_(1), I_(3), id_dw64); dw(I_(3), I_(1), I_(0), id_dw48);
+          wait_a(211); dx(I_(0), I_(2), I_(4)); tc_commit_elect(&bar_d); dw(I_(2), I_(0), I_(2), id_dw64);
+          wait_a(212); dx(I_(1), I_(1), I_(4)); tc_commit_elect(&bar_d); dw(I_(1), I_(1), I_(1), id_dw64);
+          wait_a(213); dw(I_(0), I_(0), I_(0), id_dw48); tc_commit_elect(&bar_d);   // all tiles free for the next slot once this lands
         }
       }
       __syncwarp();
