@@ -25,6 +25,17 @@
 #include "decoder_layout.h"
 #include "../../include/uorf_b200.h"
 
+// -DUORF_TIMELINE (tuning variant, scripts/timeline_bwd.py): CTA 0 stamps clock64 at the hand-off points of the fg sweep
+#ifdef UORF_TIMELINE
+__device__ long long g_tlb_epi[8192];
+__device__ long long g_tlb_iss[8192];
+#define TLB_EPI(id) do { if (tl_on && tl_ne < 8192) g_tlb_epi[tl_ne++] = (clock64() << 8) | (id); } while (0)
+#define TLB_ISS(id) do { if (tl_on && tl_ni < 8192) g_tlb_iss[tl_ni++] = (clock64() << 8) | (id); } while (0)
+#else
+#define TLB_EPI(id)
+#define TLB_ISS(id)
+#endif
+
 namespace uorf {
 
 constexpr int kTileM128 = 128;
@@ -90,16 +101,23 @@ __device__ __forceinline__ float grad_scale(float amax) {
 
 // Each point's 64 feature columns are split between two threads (`half` = 0 / 1 owns columns 32*half .. 32*half+31).
 // write 32 features (fp32 regs) as 16-bit values (F16: fp16, else bf16) into this thread's half of row `t` of a swizzled tile
-template <bool F16>
+template <bool F16, bool RELU = false>
 __device__ __forceinline__ void store_half16(unsigned char* tile, int t, int half, const float (&v)[32]) {
   unsigned char* row = tile + (t >> 3) * 1024 + (t & 7) * 128;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint4 q;
-    q.x = pack2<F16>(v[8 * c + 0], v[8 * c + 1]);
-    q.y = pack2<F16>(v[8 * c + 2], v[8 * c + 3]);
-    q.z = pack2<F16>(v[8 * c + 4], v[8 * c + 5]);
-    q.w = pack2<F16>(v[8 * c + 6], v[8 * c + 7]);
+    if (RELU) {   // ReLU folded into the conversion (cvt.rn.relu)
+      q.x = pack2_relu<F16>(v[8 * c + 0], v[8 * c + 1]);
+      q.y = pack2_relu<F16>(v[8 * c + 2], v[8 * c + 3]);
+      q.z = pack2_relu<F16>(v[8 * c + 4], v[8 * c + 5]);
+      q.w = pack2_relu<F16>(v[8 * c + 6], v[8 * c + 7]);
+    } else {
+      q.x = pack2<F16>(v[8 * c + 0], v[8 * c + 1]);
+      q.y = pack2<F16>(v[8 * c + 2], v[8 * c + 3]);
+      q.z = pack2<F16>(v[8 * c + 4], v[8 * c + 5]);
+      q.w = pack2<F16>(v[8 * c + 6], v[8 * c + 7]);
+    }
     *reinterpret_cast<uint4*>(row + ((((4 * half + c) ^ (t & 7)) & 7) << 4)) = q;
   }
 }
@@ -245,10 +263,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
       const uint32_t id_dw64 = idesc_f16(64, 64, true, true);              // dZ^T . X
       const uint32_t id_dw48 = idesc_f16(64, 48, true, true);
       uint32_t acc_live = 0;  // bit a set once accumulator a holds data
+#ifdef UORF_TIMELINE
+      const bool tl_on = blockIdx.x == 0 && lane == 0 && phase == 1;
+      int tl_ni = 0;
+#endif
       auto wait_a = [&](int site) {
+        TLB_ISS(0x20);                       // previous step fully issued (commit + trailing dW group)
         mbar_wait(&bar_a, n_a & 1, p.err_flag, site);
         ++n_a;
         tc_fence_after();
+        TLB_ISS(0x10);
       };
       // forward GEMM, both operands K-major: D (+)= X[tile xi] . W[tile wi]^T
       // every group of K-steps is one asm block under a single elect (common.cuh: mma_group_ss); tile indices and K-step
@@ -299,15 +323,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
       const int half = warp >> 2;             // this thread owns feature columns 32*half .. 32*half + 31
       const int c0 = 32 * half;
       const uint32_t tb = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+#ifdef UORF_TIMELINE
+      const bool tl_on = blockIdx.x == 0 && warp == 0 && lane == 0 && phase == 1;
+      int tl_ne = 0;
+#endif
       auto wait_d = [&](int site) {
         mbar_wait(&bar_d, n_d & 1, p.err_flag, site);
         ++n_d;
         tc_fence_after();
+        TLB_EPI(0x30);
       };
       auto publish = [&]() {  // make this thread's shared-memory tile writes visible to the tensor core, then signal
+        TLB_EPI(0x50);
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&bar_a);
+        TLB_EPI(0x40);
       };
       for (int it = 0;; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)gridDim.x * it;
@@ -323,6 +354,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
         for (int s = 0; s < nslots; ++s) {
           const int kslot = phase == 0 ? 0 : s + 1;
           const bool fresh = s == 0 || !shared_enc;
+          // d raw of this slot is needed seven hand-offs from now: fetch it here, off the critical path
+          float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && half == 0) dr = p.scratch_draw[(long long)kslot * p.P + pt];
           // ---- stage 0: coordinates -> positional encoding tile (column 33 + s carries the per-slot column sums) ----
           if (fresh) {
           x = y = z = 0.f;
@@ -395,8 +429,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
             float v[32];
             load_d32(tb + kBColD + c0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = valid ? fmaxf(v[i] + bias[i], 0.f) : 0.f;
-            store_half16<true>(s_x + st * 16384, t, half, v);
+            // rows of padded points need no masking here: their d raw is zero, so every dZ row derived from it is zero and
+            // nothing they hold reaches a gradient
+            for (int i = 0; i < 32; ++i) v[i] += bias[i];
+            store_half16<true, true>(s_x + st * 16384, t, half, v);
             publish();
           }
           // ---- head forward + backward seed (the 17 head rows live in the first column half) ----
@@ -409,7 +445,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
               uint32_t r[32];
               tmem_ld32(tb + kBColD, r);
               tc_wait_ld();
-              float4 dr = valid ? p.scratch_draw[(long long)kslot * p.P + pt] : make_float4(0.f, 0.f, 0.f, 0.f);
               dr.x *= gscale; dr.y *= gscale; dr.z *= gscale; dr.w *= gscale;
               const float* hb = s_params + kPHeadB;
               if (phase == 0) {
@@ -734,3 +769,13 @@ int launch_decoder_bwd(const uorf_decoder_weights* w, const uorf_decoder_grads* 
 }
 
 }  // namespace uorf
+
+#ifdef UORF_TIMELINE
+extern "C" int uorf_debug_timeline_bwd(long long* epi, long long* iss, int n) {
+  if (n > 8192) n = 8192;
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(epi, g_tlb_epi, n * sizeof(long long)) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(iss, g_tlb_iss, n * sizeof(long long)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
