@@ -330,6 +330,16 @@ def run_b200(args):
         model.enable_cuda_graph()
         step(resident)          # re-capture
 
+    # ---- informational: the render alone (sampling -> decoder -> compositing), without the Encoder / SlotAttention prefix ----
+    render_only_ms = None
+    if world == 1:
+        with torch.no_grad():
+            z_fixed = model.z_slots.detach().clone()
+            ro = (model.render if args.no_graph else model.render_graphed)
+            for _ in range(3):
+                ro(z_fixed, model.cam2world, model.nss2cam0)
+            render_only_ms = timed(lambda: ro(z_fixed, model.cam2world, model.nss2cam0), args.steps) / args.steps
+
     # ---- end-to-end arm: host buffers, H2D + D2H inside the timed region ----
     def e2e_step():
         x_recon = step(host)
@@ -361,7 +371,10 @@ def run_b200(args):
                                launch=("eager launches" if args.no_graph else "forward replayed as one CUDA graph" if world == 1
                                        else "per rank one CUDA graph: [rank 0: encoder + slot attention] -> NCCL broadcast of the slot latents -> render"),
                                l2="no flush: each step streams ~0.8 GB of outputs per GPU (>> 126 MB L2)",
-                               weights="random init, seed 2021"),
+                               weights="random init, seed 2021",
+                               render_only=(None if render_only_ms is None else
+                                            {"ms_per_step": render_only_ms, "value": units_total / (render_only_ms * 1e-3),
+                                             "note": "same step without the Encoder + SlotAttention prefix (SURVEY 8(d))"})),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
