@@ -11,9 +11,10 @@
 //     dW_l += dZ_l^T . X_l   (contraction over the points)   tcgen05.mma  M=64   A = dZ tile (MN-major), B = X tile (MN-major)
 // The SAME shared-memory tile serves as K-major and as MN-major operand (rows of 128 B, 128B swizzle), so no transpose
 // is ever materialised.  The eight dW accumulators (fp32) stay resident in TMEM for the whole kernel, two per 64 columns
-// (M=64 accumulators use 16 of every 32 lanes; the partner sits at lane offset 16).  Bias gradients are reduced with a
-// shuffle reduce-scatter; the per-slot column sums that carry d z_slots ride on spare positional-encoding columns
-// (a one-hot slot indicator in columns 33..47 of the P tile).  Tensor-core operands are fp16 (11-bit significand) with
+// (M=64 accumulators use 16 of every 32 lanes; the partner sits at lane offset 16).  The per-slot column sums that carry
+// d z_slots ride on spare positional-encoding columns (a one-hot slot indicator in columns 33..47 of the P tile), and the
+// bias gradients of the other layers come from the same columns: one extra N=16 MMA group dZ_l^T . P[:, 32..47] per layer
+// sums dZ_l over the points on the tensor core (the epilogue used to spend 31 shuffles per thread and layer on it).  Tensor-core operands are fp16 (11-bit significand) with
 // fp32 accumulation; activation gradients are kept in range by a global power-of-two scale taken from max |d raw|, which a
 // small elementwise pre-kernel (the backward of the slot composition) produces together with d raw itself.
 //
@@ -80,6 +81,12 @@ __device__ __forceinline__ uint32_t acc_taddr(uint32_t base, int acc) {
   return base + col + ((uint32_t)hi << 16);
 }
 
+// bias-gradient accumulators (M=64 features x N=16: dZ^T . P[:, 32..47], whose one-hot slot columns sum dZ over the points):
+// b = 0..3 for layers 1, 2, 4, 5, b = 4 for the head; pairs share 16 columns from 304 on, the second at lane offset 16
+__device__ __forceinline__ uint32_t bacc_taddr(uint32_t base, int b) {
+  return base + 304 + 16 * (b >> 1) + ((uint32_t)((b & 1) ? 16 : 0) << 16);
+}
+
 // MN-major view of a [rows][64 x bf16] swizzled tile (rows = contraction index)
 __device__ __forceinline__ uint64_t sdesc_mn(uint32_t smem_addr) {
   return (static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4)) | (static_cast<uint64_t>(1024) << 16) |
@@ -137,48 +144,6 @@ __device__ __forceinline__ void gate_by_half(const unsigned char* tile, int t, i
     }
   }
 }
-// column sums over the 32 lanes of a warp of v[0..31] (reduce-scatter butterfly: lane l ends with feature l),
-// accumulated into dst[32] (shared memory) with one atomic per lane
-__device__ __forceinline__ void warp_colsum_add(const float (&v)[32], float* dst, int lane) {
-  float a[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {  // step 1: lanes with bit 4 set keep the upper half
-    const bool up = lane & 16;
-    const float keep = up ? v[16 + i] : v[i];
-    const float send = up ? v[i] : v[16 + i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool up = lane & 8;
-    const float keep = up ? a[8 + i] : a[i];
-    const float send = up ? a[i] : a[8 + i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool up = lane & 4;
-    const float keep = up ? a[4 + i] : a[i];
-    const float send = up ? a[i] : a[4 + i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool up = lane & 2;
-    const float keep = up ? a[2 + i] : a[i];
-    const float send = up ? a[i] : a[2 + i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  {
-    const bool up = lane & 1;
-    const float keep = up ? a[1] : a[0];
-    const float send = up ? a[0] : a[1];
-    a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-  }
-  // lane bits (16,8,4,2,1) selected halves in that order: feature index = 16*b4 + 8*b3 + 4*b2 + 2*b1 + b0 = lane
-  atomicAdd(dst + lane, a[0]);
-}
-
 __device__ __forceinline__ void load_d32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   tmem_ld32(taddr, r);
@@ -191,7 +156,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, bar_a, bar_d;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_db[5][64];   // bias-gradient sums: layers 1, 2, 4, 5, head
   __shared__ float s_red[4][64];
 
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -243,7 +207,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
         bulk_g2s(smem + off, src + off, n, &bar_w);
       }
     }
-    for (int e = threadIdx.x; e < 5 * 64; e += blockDim.x) (&s_db[0][0])[e] = 0.f;
     mbar_wait(&bar_w, phase & 1, p.err_flag, 100 + phase);
     __syncthreads();
 
@@ -262,6 +225,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
       const uint32_t id_dx = idesc_f16(128, 64, false, true);              // dZ . W
       const uint32_t id_dw64 = idesc_f16(64, 64, true, true);              // dZ^T . X
       const uint32_t id_dw48 = idesc_f16(64, 48, true, true);
+      const uint32_t id_dwb = idesc_f16(64, 16, true, true);
       uint32_t acc_live = 0;  // bit a set once accumulator a holds data
 #ifdef UORF_TIMELINE
       const bool tl_on = blockIdx.x == 0 && lane == 0 && phase == 1;
@@ -293,6 +257,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
         mma_group_ss<8, 128, 128>(acc_taddr(tbu, acc), sdesc_mn(dz_s + buf * 16384), sdesc_mn(x_s + xi * 16384), idesc, live ? 1u : 0u);
         acc_live |= 1u << acc;
       };
+      // bias gradient of the layer whose dZ sits in buffer `buf`: dZ^T . (columns 32..47 of the encoding tile), N = 16.
+      // Columns 33+s are the one-hot slot indicator, so their sum over s is the column sum of dZ over all valid points -
+      // the tensor core does the reduction the epilogue used to do with 31 shuffles per thread.
+      uint32_t bacc_live = 0;
+      auto dwb = [&](auto B, auto BUF) {
+        constexpr int b = decltype(B)::value, buf = decltype(BUF)::value;
+        const bool live = (bacc_live >> b) & 1u;
+        mma_group_ss<8, 128, 128>(bacc_taddr(tbu, b), sdesc_mn(dz_s + buf * 16384), sdesc_mn(x_s) + 4, id_dwb, live ? 1u : 0u);
+        bacc_live |= 1u << b;
+      };
 #define I_(n) std::integral_constant<int, n>{}
       for (int it = 0;; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)gridDim.x * it;
@@ -307,12 +281,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
           wait_a(205); fwd(I_(5), I_(6), I_(4), id_fwd64, true); tc_commit_elect(&bar_d);
           wait_a(206); fwd(I_(6), I_(7), I_(4), id_fwd_head, true); tc_commit_elect(&bar_d);
           // ---- backward ----   (dZ buffers alternate: head -> 0, layer 5 -> 1, 4 -> 0, 3 -> 1, 2 -> 0, 1 -> 1, 0 -> 0)
-          wait_a(207); dx(I_(0), I_(7), I_(2)); tc_commit_elect(&bar_d); dw(I_(7), I_(0), I_(6), id_dw64);
-          wait_a(208); dx(I_(1), I_(6), I_(4)); tc_commit_elect(&bar_d); dw(I_(6), I_(1), I_(5), id_dw64);
-          wait_a(209); dx(I_(0), I_(5), I_(4)); tc_commit_elect(&bar_d); dw(I_(5), I_(0), I_(4), id_dw64);
+          wait_a(207); dx(I_(0), I_(7), I_(2)); tc_commit_elect(&bar_d); dw(I_(7), I_(0), I_(6), id_dw64); dwb(I_(4), I_(0));
+          wait_a(208); dx(I_(1), I_(6), I_(4)); tc_commit_elect(&bar_d); dw(I_(6), I_(1), I_(5), id_dw64); dwb(I_(3), I_(1));
+          wait_a(209); dx(I_(0), I_(5), I_(4)); tc_commit_elect(&bar_d); dw(I_(5), I_(0), I_(4), id_dw64); dwb(I_(2), I_(0));
           wait_a(210); dx(I_(1), I_(4), I_(4)); tc_commit_elect(&bar_d); dw(I_(4), I_(1), I_(3), id_dw64); dw(I_(3), I_(1), I_(0), id_dw48);
-          wait_a(211); dx(I_(0), I_(2), I_(4)); tc_commit_elect(&bar_d); dw(I_(2), I_(0), I_(2), id_dw64);
-          wait_a(212); dx(I_(1), I_(1), I_(4)); tc_commit_elect(&bar_d); dw(I_(1), I_(1), I_(1), id_dw64);
+          wait_a(211); dx(I_(0), I_(2), I_(4)); tc_commit_elect(&bar_d); dw(I_(2), I_(0), I_(2), id_dw64); dwb(I_(1), I_(0));
+          wait_a(212); dx(I_(1), I_(1), I_(4)); tc_commit_elect(&bar_d); dw(I_(1), I_(1), I_(1), id_dw64); dwb(I_(0), I_(1));
           wait_a(213); dw(I_(0), I_(0), I_(0), id_dw48); tc_commit_elect(&bar_d);   // all tiles free for the next slot once this lands
         }
       }
@@ -464,7 +438,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
                 wc2_acc[48] += dr.x; wc2_acc[49] += dr.y; wc2_acc[50] += dr.z;
                 dzh[kHeadShapeRow] = (p.locality && outside) ? 0.f : dr.w;   // model.py:147-148 zeroes sigma outside the box
               }
-              warp_colsum_add(dzh, s_db[4], lane);
             }
             store_half16<true>(s_dz, t, half, dzh);   // the second half writes the zero padding of the head's dZ tile
           }
@@ -476,8 +449,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
             float g[32];
             load_d32(tb + kBColD + c0, g);                  // dX_{l+1}
             gate_by_half(s_x + (l + 1) * 16384, t, half, g);     // * [X_{l+1} > 0]  -> dZ_l
-            if (l == 1 || l == 2) warp_colsum_add(g, s_db[l - 1] + c0, lane);
-            if (l == 4 || l == 5) warp_colsum_add(g, s_db[l - 2] + c0, lane);
             store_half16<true>(s_dz + ((l & 1) ? 16384 : 0), t, half, g);
             publish();
           }
@@ -517,6 +488,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
         if (ncol == 48)
           for (int c = 48; c < 64; ++c) part[acc * kAccFloats + row * 64 + c] = 0.f;
       }
+      // bias gradients: sum of the one-hot slot columns (local columns 1..15) of the N=16 accumulators
+#pragma unroll 1
+      for (int pb = 0; pb < 3; ++pb) {
+        uint32_t r[16];
+        tmem_ld16(tb + 304 + 16 * pb, r);
+        tc_wait_ld();
+        const int b = 2 * pb + second;
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 1; i < 16; ++i) sum += __uint_as_float(r[i]);
+        if (b < 5) part[kPartBias + b * 64 + row] = sum;
+      }
       // f_color.2 gradient: block reduction of the per-thread sums (fixed order)
 #pragma unroll
       for (int base = 0; base < 51; base += 1) {
@@ -527,7 +510,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
       }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < 5 * 64; e += blockDim.x) part[kPartBias + e] = (&s_db[0][0])[e];
     if (threadIdx.x < 64) part[kPartWc2 + threadIdx.x] = threadIdx.x < 51 ? s_red[0][threadIdx.x] + s_red[1][threadIdx.x] + s_red[2][threadIdx.x] + s_red[3][threadIdx.x] : 0.f;
     tc_fence_before();
     __syncthreads();
