@@ -612,3 +612,64 @@ def test_train_step_cuda_graph_matches_eager():
         assert d.max().item() < 1e-3 and d.mean().item() < 1e-5, (n, d.max().item(), d.mean().item())
     with pytest.raises(RuntimeError):           # needs the capturable optimizer
         uorfNoGanModel(default_train_options(num_slots=3, z_dim=40, gpu_ids=[0]), with_perceptual=False).enable_cuda_graph()
+
+
+# ------------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes (configs[1]: 4 views x 128 x 128 x 64 samples, K = 5): size-independent properties and
+# random sub-samples against the oracle (the oracle itself needs ~30 s per view at this size)
+# ------------------------------------------------------------------------------------------------------
+def test_full_size_render_properties():
+    from uorf_b200.modules import Decoder, Projection, raw2outputs
+    N, F_, D, K, Z = 4, 128, 64, 5, 64
+    gen = torch.Generator().manual_seed(2021)
+    c2w, azi = O.lookat_cameras(N)
+    proj = Projection(frustum_size=[F_, F_, D], near=6, far=20, nss_scale=7, render_size=(64, 64), device=dev())
+    coords, z_vals, ray_dir = proj.construct_sampling_coor(c2w.to(dev()), ray_major=True)
+    P, R = N * F_ * F_ * D, N * F_ * F_
+    assert coords.shape == (P, 3) and z_vals.shape == (R, D)
+    # (1) sampling: ray-major order is a pure re-indexing of the reference order, and a random sub-sample matches the oracle
+    ref_order, zv_ref, _ = proj.construct_sampling_coor(c2w.to(dev()))
+    assert torch.equal(coords.view(N, F_, F_, D, 3), ref_order.view(N, D, F_, F_, 3).permute(0, 2, 3, 1, 4))
+    spec = O.FrustumSpec([F_, F_, D], near=6.0, far=20.0, nss_scale=7.0, render_size=64)
+    co_o, zv_o, rd_o = O.sampling_coords(spec, c2w)
+    idx = torch.randint(0, P, (20000,), generator=gen)
+    assert maxerr(ref_order.cpu()[idx], co_o[idx]) < 2e-6
+    assert torch.equal(zv_ref.cpu(), zv_o)                                   # sample positions bit-exact
+    # (2) decoder at full size: composition identities on every point, oracle parity on a random sub-sample of points
+    params = O.init_decoder_params(Z, seed=5)
+    zs = torch.randn(K, Z, generator=gen)
+    T = azi[0:1].inverse()
+    dec = Decoder(locality=True, locality_ratio=4.5 / 7).to(dev())
+    dec.load_state_dict(params)
+    dec.emit = Decoder.ALL_OUTPUTS
+    dec.return_outside = True
+    with torch.no_grad():
+        raws, masked, unmasked, masks = dec(coords, coords[None].expand(K - 1, -1, -1), zs.to(dev()), T.to(dev()))
+        assert torch.isfinite(raws).all() and torch.isfinite(masked).all()
+        assert (masked.sum(0) - raws).abs().max().item() < 1e-5                # raws = sum_k masked_k        (model.py:158-159)
+        assert (masked - unmasked * masks).abs().max().item() < 1e-6           # masked = unmasked * mask     (model.py:157)
+        dens_sum = unmasked[..., 3].clamp(min=0).sum(0)
+        msum = masks.sum(0).squeeze(-1)
+        assert ((msum - dens_sum / (dens_sum + 1e-5)).abs().max().item()) < 1e-5   # masks = dens / (sum dens + 1e-5)
+        assert (unmasked[..., :3].min().item() >= 0) and (unmasked[..., :3].max().item() <= 1)
+        # the kernel's tiling must not matter: a permuted point set yields the permuted outputs, bit for bit
+        perm = torch.randperm(P, generator=gen)[:300000].to(dev())
+        sub = coords[perm].contiguous()
+        raws_s, masked_s, unmasked_s, masks_s = dec(sub, sub[None].expand(K - 1, -1, -1), zs.to(dev()), T.to(dev()))
+        assert torch.equal(raws_s, raws[perm]) and torch.equal(unmasked_s, unmasked[:, perm]) and torch.equal(masks_s, masks[:, perm])
+    idx = torch.randint(0, P, (16384,), generator=gen)
+    cs = coords.cpu()[idx]
+    ref = O.decoder_forward(params, cs, cs[None].expand(K - 1, -1, -1), zs, T, locality=True, locality_ratio=4.5 / 7,
+                            noise=torch.zeros(K, cs.shape[0], 1), return_aux=True)
+    idx_d = idx.to(dev())
+    assert torch.equal(dec.last_outside[:, idx_d].cpu().bool(), ref[4])         # locality mask bit-exact
+    check_decoder_outputs((raws[idx_d], masked[:, idx_d], unmasked[:, idx_d], masks[:, idx_d]), ref[:4], FP32_TOL, "full-size sub-sample")
+    # (3) compositing at full size: weights are a partition of at most 1, a sub-sample of rays matches the oracle
+    with torch.no_grad():
+        rgb, depth, wn = raw2outputs(raws.view(R, D, 4), z_vals, ray_dir)
+    assert (wn.sum(-1) - 1).abs().max().item() < 1e-5                          # normalised weights sum to 1 (model.py:304-306)
+    assert rgb.min().item() >= -1e-6 and rgb.max().item() <= 1 + 1e-5
+    ridx = torch.randint(0, R, (4096,), generator=gen)
+    rgb_o, depth_o, wn_o = O.composite(raws.view(R, D, 4).cpu()[ridx], z_vals.cpu()[ridx], ray_dir.cpu()[ridx])
+    assert maxerr(rgb[ridx.to(dev())], rgb_o) < 5e-6 and maxerr(depth[ridx.to(dev())], depth_o) < 5e-5
+    assert maxerr(wn[ridx.to(dev())], wn_o) < 5e-6
