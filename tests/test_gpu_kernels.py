@@ -645,6 +645,7 @@ def test_full_size_render_properties():
     dec.return_outside = True
     with torch.no_grad():
         raws, masked, unmasked, masks = dec(coords, coords[None].expand(K - 1, -1, -1), zs.to(dev()), T.to(dev()))
+        outside_full = dec.last_outside
         assert torch.isfinite(raws).all() and torch.isfinite(masked).all()
         assert (masked.sum(0) - raws).abs().max().item() < 1e-5                # raws = sum_k masked_k        (model.py:158-159)
         assert (masked - unmasked * masks).abs().max().item() < 1e-6           # masked = unmasked * mask     (model.py:157)
@@ -662,7 +663,7 @@ def test_full_size_render_properties():
     ref = O.decoder_forward(params, cs, cs[None].expand(K - 1, -1, -1), zs, T, locality=True, locality_ratio=4.5 / 7,
                             noise=torch.zeros(K, cs.shape[0], 1), return_aux=True)
     idx_d = idx.to(dev())
-    assert torch.equal(dec.last_outside[:, idx_d].cpu().bool(), ref[4])         # locality mask bit-exact
+    assert torch.equal(outside_full[:, idx_d].cpu().bool(), ref[4])            # locality mask bit-exact
     check_decoder_outputs((raws[idx_d], masked[:, idx_d], unmasked[:, idx_d], masks[:, idx_d]), ref[:4], FP32_TOL, "full-size sub-sample")
     # (3) compositing at full size: weights are a partition of at most 1, a sub-sample of rays matches the oracle
     with torch.no_grad():
