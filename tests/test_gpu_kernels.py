@@ -674,3 +674,33 @@ def test_full_size_render_properties():
     rgb_o, depth_o, wn_o = O.composite(raws.view(R, D, 4).cpu()[ridx], z_vals.cpu()[ridx], ray_dir.cpu()[ridx])
     assert maxerr(rgb[ridx.to(dev())], rgb_o) < 5e-6 and maxerr(depth[ridx.to(dev())], depth_o) < 5e-5
     assert maxerr(wn[ridx.to(dev())], wn_o) < 5e-6
+
+
+def test_full_size_backward_linearity_and_determinism():
+    """BASELINE configs[2] size (K = 8, 64^3 x 4 views = 1,048,576 points): the decoder backward is deterministic (fixed-order
+    reduction) and exactly linear under a power-of-two rescaling of d raws (the loss scale is a power of two taken from
+    max |d raw|, so the scaled operands are bit-identical) - properties that hold at any size."""
+    from uorf_b200.modules import Decoder
+    K, Z, P = 8, 64, 4 * 64 * 64 * 64
+    gen = torch.Generator().manual_seed(77)
+    dec = Decoder(locality=True, locality_ratio=4.5 / 7).to(dev())
+    dec.load_state_dict(O.init_decoder_params(Z, seed=9))
+    coords = ((torch.rand(P, 3, generator=gen) * 2 - 1) * 1.6).to(dev())
+    T = O.lookat_cameras(1)[1][0:1].inverse().to(dev())
+    g = (torch.rand(P, 4, generator=gen) - 0.3).to(dev()) * 1e-3
+
+    def grads(scale):
+        z = torch.randn(K, Z, generator=torch.Generator().manual_seed(5)).to(dev()).requires_grad_(True)
+        for p_ in dec.parameters():
+            p_.grad = None
+        raws, _, _, _ = dec(coords, coords[None].expand(K - 1, -1, -1), z, T)
+        raws.backward(g * scale)
+        out = {n: p_.grad.clone() for n, p_ in dec.named_parameters()}
+        out["z_slots"] = z.grad.clone()
+        return out
+    a, b, c = grads(1.0), grads(1.0), grads(4.0)
+    for n in a:
+        assert torch.isfinite(a[n]).all(), n
+        assert torch.equal(a[n], b[n]), f"non-deterministic gradient: {n}"
+        assert torch.equal(a[n] * 4.0, c[n]), f"not linear in d raws: {n}"
+    assert a["f_before.0.weight"].abs().max().item() > 0
