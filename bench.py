@@ -495,6 +495,9 @@ def run_train(args):
                 "clocks": clocks,
                 "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "scene-steps/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                # launches of this library's own kernels per step and rank (profiles/*_launches_train.md): slot attention 8 + 10,
+                # sampling 1, weight image 2, decoder fwd 1 + bwd 4 (compose, main, reduce, unfold), compositing 1 + 1
+                "gpu_launches": 27 * args.steps,
                 "impl": "b200"}
         print(json.dumps(line))
     if world > 1:
