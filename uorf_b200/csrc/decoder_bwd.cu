@@ -128,22 +128,27 @@ __device__ __forceinline__ void store_half16(unsigned char* tile, int t, int hal
     *reinterpret_cast<uint4*>(row + ((((4 * half + c) ^ (t & 7)) & 7) << 4)) = q;
   }
 }
-// ReLU gate: multiply g[i] by [x_i > 0] where x is this thread's half of the 16-bit row `t` of a swizzled tile (bf16 and
-// fp16 both keep their magnitude in the low 15 bits)
-__device__ __forceinline__ void gate_by_half(const unsigned char* tile, int t, int half, float (&g)[32]) {
-  const unsigned char* row = tile + (t >> 3) * 1024 + (t & 7) * 128;
+// dZ = dX * [X > 0], converted and stored in one go: dX (fp32) is packed to fp16 pairs and ANDed with a per-half mask taken
+// from the packed activations X of the same positions (activations are ReLU outputs: "non-zero" == "positive"), then written
+// to this thread's half of row `t` of the dZ tile.  Three instructions per pair (pack, compare-to-mask, and).
+__device__ __forceinline__ void gate_store_half(const unsigned char* x_tile, unsigned char* dz_tile, int t, int half, const float (&g)[32]) {
+  const int roff = (t >> 3) * 1024 + (t & 7) * 128;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const uint4 q = *reinterpret_cast<const uint4*>(row + ((((4 * half + c) ^ (t & 7)) & 7) << 4));
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    const int coff = (((4 * half + c) ^ (t & 7)) & 7) << 4;
+    const uint4 x = *reinterpret_cast<const uint4*>(x_tile + roff + coff);
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+    uint32_t q[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      // positive <=> magnitude bits non-zero (activations are ReLU outputs: never negative)
-      if ((w[i] & 0x7FFFu) == 0) g[8 * c + 2 * i] = 0.f;
-      if ((w[i] & 0x7FFF0000u) == 0) g[8 * c + 2 * i + 1] = 0.f;
+      uint32_t m;
+      asm("{\n\t.reg .b32 z;\n\tmov.b32 z, 0;\n\tset.ne.u32.f16x2 %0, %1, z;\n\t}" : "=r"(m) : "r"(xw[i]));   // 0xFFFF per non-zero half
+      q[i] = pack2<true>(g[8 * c + 2 * i], g[8 * c + 2 * i + 1]) & m;
     }
+    *reinterpret_cast<uint4*>(dz_tile + roff + coff) = make_uint4(q[0], q[1], q[2], q[3]);
   }
 }
+
 __device__ __forceinline__ void load_d32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   tmem_ld32(taddr, r);
@@ -448,8 +453,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
             wait_d(320 + l);
             float g[32];
             load_d32(tb + kBColD + c0, g);                  // dX_{l+1}
-            gate_by_half(s_x + (l + 1) * 16384, t, half, g);     // * [X_{l+1} > 0]  -> dZ_l
-            store_half16<true>(s_dz + ((l & 1) ? 16384 : 0), t, half, g);
+            gate_store_half(s_x + (l + 1) * 16384, s_dz + ((l & 1) ? 16384 : 0), t, half, g);   // dZ_l = dX_{l+1} * [X_{l+1} > 0]
             publish();
           }
         }
