@@ -472,6 +472,23 @@ def run_train(args):
         step(resident)
     torch.cuda.synchronize()
     clocks = sampler.stop()
+    # duration of the two decoder calls: CUDA events around them over a few eagerly launched steps (events cannot be recorded
+    # inside a replayed graph); same stream, same inputs, same launch configuration
+    fwd_ms = bwd_ms = None
+    if world == 1:
+        model.enable_cuda_graph(False) if use_graph else None
+        model.netDecoder.events, model.netDecoder.events_bwd = [], []
+        for _ in range(min(args.steps, 5)):
+            step(resident)
+        torch.cuda.synchronize()
+        ef, eb = model.netDecoder.events, model.netDecoder.events_bwd
+        model.netDecoder.events = model.netDecoder.events_bwd = None
+        fwd_ms = sum(a.elapsed_time(b) for a, b in ef) / max(len(ef), 1)
+        bwd_ms = sum(a.elapsed_time(b) for a, b in eb) / max(len(eb), 1)
+        if use_graph:
+            model.enable_cuda_graph()
+            for _ in range(5):
+                step(resident)
 
     def e2e_step():
         step(host)
@@ -499,6 +516,16 @@ def run_train(args):
                 # sampling 1, weight image 2, decoder fwd 1 + bwd 4 (compose, main, reduce, unfold), compositing 1 + 1
                 "gpu_launches": 27 * args.steps,
                 "impl": "b200"}
+        if bwd_ms:
+            pk = peaks()
+            pts = c["n_views"] * c["frustum"] ** 2 * c["n_samp"]
+            fl = f_min_per_point(c["K"], c["z_dim"])
+            ach = 4.0 * fl * pts / (bwd_ms * 1e-3) / 1e12
+            line["roofline"] = {"kernel": "decoder_bwd_kernel (+ composition-backward, reduce, unfold)", "bound": "tensor", "achieved": ach,
+                                "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None,
+                                "peak_source": pk["src"] + " bf16 burst", "kernel_ms": bwd_ms, "decoder_fwd_kernel_ms": fwd_ms,
+                                "flops_per_point_algorithmic": 4.0 * fl, "points_per_launch": pts,
+                                "note": "algorithmic flops = 4 x forward F_min (recompute + dX + dW at M=64 half rate)"}
         print(json.dumps(line))
     if world > 1:
         _shutdown(dist)

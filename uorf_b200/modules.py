@@ -416,6 +416,7 @@ class Decoder(nn.Module):
         self.return_outside = False
         self.last_outside = None
         self.events = None   # set to a list to collect (start, end) CUDA events around the fused kernel
+        self.events_bwd = None   # same for the backward call (composition-backward, main, reduce and unfold kernels)
         self.fg_slot_offset = None
 
     # ---- C-ABI plumbing ----
@@ -546,7 +547,15 @@ class Decoder(nn.Module):
         a.P, a.K, a.Z = P, K, Cz
         a.z_slots, a.image, a.unmasked_raws, a.grad_raws = z.data_ptr(), image_ptr, un.data_ptr(), gr.data_ptr()
         a.workspace, a.grad_z_slots = ws.data_ptr(), gz.data_ptr()
+        evb = getattr(self, "events_bwd", None)
+        if evb is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(dev))
         check(lib().uorf_decoder_backward(C.byref(w), C.byref(g), C.byref(a), stream), "uorf_decoder_backward")
+        if evb is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream(dev))
+            evb.append((e0, e1))
         return gz, grads
 
     def forward(self, sampling_coor_bg, sampling_coor_fg, z_slots, fg_transform, dens_noise=0., noise=None):
