@@ -30,6 +30,15 @@ import torch  # noqa: E402
 
 CFG = dict(workload="room_chair_eval_K5_F128_D64_N4", K=5, z_dim=64, n_views=4, frustum=128, n_samp=64, render_size=64,
            input_size=64, load_size=128)
+# the other shapes BASELINE.json names (parity-test cases; `--workload` runs them through the same arms for the record)
+WORKLOADS = {
+    "clevr567": dict(workload="clevr567_eval_K8_F64_D64_N4", K=8, z_dim=64, n_views=4, frustum=64, n_samp=64, render_size=64,
+                     input_size=64, load_size=128),
+}
+TRAIN_WORKLOADS = {
+    "room_diverse_fine": dict(workload="room_diverse_train_fine_K5_F128crop64_D64_N4", K=5, z_dim=64, n_views=4, frustum=64, n_samp=64,
+                              supervision_size=64, input_size=128, load_size=128, stage="fine", bottom=True, frustum_fine=128),
+}
 METRIC = "composited_ray_samples_x_slots_per_sec"
 UNIT = "sample-slots/s"
 HBM_FALLBACK_GBS, BF16_FALLBACK_TFLOPS = 6650.0, 1590.0
@@ -357,7 +366,7 @@ def run_b200(args):
     ach_tflops = pts_rank * f_min_per_point(K, Z) / (dec_ms * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "decoder_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.workload is None:     # the ncu capture is of the headline workload
         traffic = json.load(open(tpath)).get(args.precision)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = out_host.numel() * out_host.element_size()
@@ -420,8 +429,9 @@ def run_train(args):
     torch.manual_seed(2021)   # identical replicas
     opt = default_train_options(num_slots=c["K"], z_dim=c["z_dim"], n_samp=c["n_samp"], frustum_size=c["frustum"],
                                 render_size=c["supervision_size"], supervision_size=c["supervision_size"], input_size=c["input_size"],
-                                n_img_each_scene=c["n_views"], stage="coarse", gpu_ids=[local_rank], warmup_steps=10)
-    use_graph = not args.no_graph
+                                n_img_each_scene=c["n_views"], stage=c.get("stage", "coarse"), bottom=c.get("bottom", False),
+                                frustum_size_fine=c.get("frustum_fine", 128), gpu_ids=[local_rank], warmup_steps=10)
+    use_graph = not args.no_graph and opt.stage == "coarse"     # the fine stage draws its crop window on the host every step
     opt.cuda_graph = use_graph
     model = uorfNoGanModel(opt, precision=args.precision)
     if world > 1:
@@ -539,10 +549,18 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "bf16x3", "bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default=None, choices=[None] + sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS),
+                    help="another BASELINE.json shape instead of the headline one (clevr567: render; room_diverse_fine: --mode train)")
     ap.add_argument("--no-graph", action="store_true", help="launch the render step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--mode", default="render", choices=["render", "train"],
                     help="render: the headline eval-render metric (default); train: CLEVR-567 coarse training step")
     args = ap.parse_args()
+    global CFG, TRAIN_CFG
+    if args.workload in WORKLOADS:
+        CFG = WORKLOADS[args.workload]
+    elif args.workload in TRAIN_WORKLOADS:
+        TRAIN_CFG = TRAIN_WORKLOADS[args.workload]
+        args.mode = "train"
     if args.impl == "reference":
         run_reference(args)
     elif args.mode == "train":
