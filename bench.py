@@ -2,6 +2,7 @@
 """bench.py - headline benchmark of the uORF per-scene render hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision fp16x3|bf16x3|bf16|fp16]
+                    [--mode render|train] [--workload clevr567|room_diverse_fine] [--no-graph] [--no-cpu-baseline]
 
 Metric (BASELINE.json): composited ray-samples/s x K slots = P_total * K / t, where one STEP is one scene rendered
 through Encoder -> SlotAttention -> Projection -> Decoder -> raw2outputs (the eval driver's forward,
@@ -10,6 +11,14 @@ Workload (BASELINE.json configs[1]): Room-Chair novel-view render, K=5 slots, z_
 4 views per scene, synthetic images/cameras, random-init weights (seed 2021).
 N > 1 GPUs: rays shard by view - every rank renders 4 views of a 4N-view scene, rank 0 encodes and broadcasts the
 slot latents over NCCL (weak scaling, no collective inside the per-point work).
+
+The step is replayed as ONE CUDA graph per rank (N > 1: [rank 0: encoder + slot attention] -> NCCL broadcast -> render, the
+collective captured in the graph); `--no-graph` launches eagerly.  `--mode train` measures BASELINE configs[2] (CLEVR-567
+coarse-stage training step, K=8, scene-sharded data parallel, whole step incl. the gradient all-reduce as one graph).
+The JSON line carries `roofline` (dominant kernel: CUDA-event time over eagerly launched steps, algorithmic flops counted
+once), `cpu_baseline` (oracle on the host cores + the as-written algorithm as torch eager ops on the same GPU), `e2e`
+(host buffers, H2D + D2H inside the timed region), `clocks` (NVML samples under load) and `gpu_launches`.
+`UORF_PROFILE_RANGE=1` brackets the timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off).
 
 `--impl reference` times the CPU restatement of the reference algorithm (oracle/, the reference itself cannot travel
 to the GPU box) on the host cores, on a bounded sample of the same workload.
