@@ -238,6 +238,18 @@ int uorf_slot_attention_backward(const uorf_slot_attention_weights* w, const uor
                                  float* grad_feat, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Encoder layer (inference path) — 3x3 convolution (padding 1, stride 1 or 2) + bias + ReLU, fp32.
+ * Replaces one `nn.Sequential(nn.Conv2d(..., 3, stride, padding=1), nn.ReLU)` of Encoder (models/model.py:19-34) together with
+ * the data movement around it in Encoder.forward (models/model.py:36-61): the input is the channel concatenation of src_a
+ * [ca][*][*] and src_b [cb][h_in][w_in] (torch.cat, :49,:58,:60); with upsample_a != 0, src_a is stored at half resolution
+ * [ca][h_in/2][w_in/2] and read through nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) (:27-32).
+ * weight_t is the Conv2d weight transposed to [ca+cb][3][3][c_out]; out [c_out][h_out][w_out], h_out = (h_in-1)/stride + 1.
+ * Batch 1 (the drivers encode view 0 only, uorf_eval_model.py:121-123).  Training keeps torch autograd / cuDNN.
+ * ------------------------------------------------------------------------------------------- */
+int uorf_encoder_conv3x3(const float* src_a, int32_t ca, int32_t upsample_a, const float* src_b, int32_t cb, const float* weight_t,
+                         const float* bias, int32_t c_out, int32_t h_in, int32_t w_in, int32_t stride, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Test hook: one 128 x N x (16*ksteps) bf16 GEMM on the tcgen05 path the decoder uses
  * (A rows written to TMEM by threads, B a swizzled shared-memory tile).  a [128][64], b [N][64] fp32
  * (rounded to 16 bits inside), d [128][N].  Used by tests/ to pin the tensor-core data layouts.

@@ -704,3 +704,29 @@ def test_full_size_backward_linearity_and_determinism():
         assert torch.equal(a[n], b[n]), f"non-deterministic gradient: {n}"
         assert torch.equal(a[n] * 4.0, c[n]), f"not linear in d raws: {n}"
     assert a["f_before.0.weight"].abs().max().item() > 0
+
+
+@pytest.mark.parametrize("Z,S,bottom", [(64, 64, False), (40, 32, False), (64, 128, True), (64, 24, False)])
+def test_encoder_inference_kernels_match_cudnn(Z, S, bottom):
+    """direct-convolution inference path (cat / bilinear upsample folded into the input read) vs the torch layers, fp32"""
+    from uorf_b200.modules import Encoder
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(3)
+    enc = Encoder(3, z_dim=Z, bottom=bottom).to(dev())
+    for p_ in enc.parameters():
+        torch.nn.init.normal_(p_, 0.0, 0.05)
+    x = torch.rand(1, 3, S, S, device=dev()) * 2 - 1
+    with torch.no_grad():
+        enc.use_kernels = False
+        want = enc(x)
+        enc.use_kernels = True
+        got = enc(x)
+    assert got.shape == want.shape
+    assert maxerr(got, want) < 2e-5 * max(1.0, want.abs().max().item()), (maxerr(got, want), want.abs().max().item())
+    # oracle restatement of the reference encoder (CPU)
+    ref = O.encoder_forward({k: v.detach().cpu() for k, v in enc.state_dict().items()}, x.cpu(), bottom)
+    assert maxerr(got, ref) < 2e-5 * max(1.0, ref.abs().max().item())
+    # gradients still flow through the torch layers
+    y = enc(x.requires_grad_(True))
+    y.sum().backward()
+    assert enc.enc_up_1[0].weight.grad is not None

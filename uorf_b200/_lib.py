@@ -94,6 +94,8 @@ _SIGNATURES = {
     "uorf_last_error": (C.c_char_p, []),
     "uorf_init": (C.c_int, [C.c_int]),
     "uorf_debug_flag": (C.c_int, []),
+    "uorf_encoder_conv3x3": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "uorf_sample_coords": (C.c_int, [C.POINTER(Frustum), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uorf_decoder_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libuorf_b200.so")
-SOURCES = ["abi.cu", "sample_coords.cu", "decoder_prep.cu", "decoder_fwd.cu", "decoder_bwd.cu", "composite.cu",
+SOURCES = ["abi.cu", "encoder.cu", "sample_coords.cu", "decoder_prep.cu", "decoder_fwd.cu", "decoder_bwd.cu", "composite.cu",
            "slot_attention.cu", "slot_attention_bwd.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]

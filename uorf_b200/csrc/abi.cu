@@ -13,6 +13,8 @@ namespace uorf {
 int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float* cam2world, int n_views, int scale, int crop_h,
                          int crop_w, int Hc, int Wc, int ray_major, float* coords, float* z_vals, float* ray_dir, int num_sms,
                          cudaStream_t stream);
+int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* weight_t, const float* bias,
+                           int c_out, int h_in, int w_in, int stride, float* out, cudaStream_t stream);
 int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int K, int Z, int passes, int f16, void* image,
                         cudaStream_t stream);
 int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, cudaStream_t stream);
@@ -122,6 +124,18 @@ int uorf_init(int device) {
   std::call_once(c->once, init_device, c, device);
   if (c->status != UORF_OK) return fail(c->status, "%s", c->why);
   return UORF_OK;
+}
+
+int uorf_encoder_conv3x3(const float* src_a, int32_t ca, int32_t upsample_a, const float* src_b, int32_t cb, const float* weight_t,
+                         const float* bias, int32_t c_out, int32_t h_in, int32_t w_in, int32_t stride, float* out, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  if (!src_a || !weight_t || !bias || !out || (cb > 0 && !src_b)) return fail(UORF_ERR_ARG, "uorf_encoder_conv3x3: null pointer%s");
+  if (ca < 1 || cb < 0 || c_out < 1 || h_in < 1 || w_in < 1 || (stride != 1 && stride != 2))
+    return fail(UORF_ERR_ARG, "uorf_encoder_conv3x3: bad sizes (stride must be 1 or 2)%s");
+  if (upsample_a && ((h_in | w_in) & 1)) return fail(UORF_ERR_ARG, "uorf_encoder_conv3x3: upsampled source needs even h_in, w_in%s");
+  return check_launch(uorf::launch_encoder_conv3x3(src_a, ca, upsample_a, src_b, cb, weight_t, bias, c_out, h_in, w_in, stride, out,
+                                                   static_cast<cudaStream_t>(stream)), "uorf_encoder_conv3x3");
 }
 
 int uorf_debug_flag(void) {

@@ -68,6 +68,8 @@ class Encoder(nn.Module):
                                       nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False))
         self.enc_up_1 = nn.Sequential(nn.Conv2d(z_dim * 2, z_dim, 3, stride=1, padding=1), nn.ReLU(True))
         self._planes = {}
+        self._wt = {}              # transposed conv weights of the inference path, keyed by weight version
+        self.use_kernels = True    # False: always the torch / cuDNN layers (what the training path uses)
 
     def _pixel_planes(self, H, W, device):
         key = (H, W, str(device))
@@ -79,8 +81,45 @@ class Encoder(nn.Module):
             self._planes[key] = torch.stack([x1, 2 - x1, y1, 2 - y1]).unsqueeze(0).to(device)
         return self._planes[key]
 
+    # ---- inference path: six (seven) direct-convolution launches, no cat / upsample tensors -------------------------
+    def _conv(self, layer, src_a, up_a, src_b, h_in, w_in):
+        conv = layer[0]
+        key = (conv.weight.data_ptr(), conv.weight._version)
+        cache = self._wt.get(id(conv))
+        if cache is None or cache[0] != key:       # [out][in][3][3] -> [in][3][3][out], once per weight version
+            cache = (key, conv.weight.detach().permute(1, 2, 3, 0).contiguous().float())
+            self._wt[id(conv)] = cache
+        stride = conv.stride[0]
+        ca, cb = src_a.shape[0], (0 if src_b is None else src_b.shape[0])
+        out = torch.empty(conv.out_channels, (h_in - 1) // stride + 1, (w_in - 1) // stride + 1, device=src_a.device, dtype=torch.float32)
+        check(lib().uorf_encoder_conv3x3(src_a.data_ptr(), ca, int(up_a), _ptr(src_b), cb, cache[1].data_ptr(),
+                                         _f32c(conv.bias.detach()).data_ptr(), conv.out_channels, h_in, w_in, stride, out.data_ptr(),
+                                         _stream(src_a)), "uorf_encoder_conv3x3")
+        return out
+
+    def _forward_inference(self, x):
+        H, W = x.shape[2], x.shape[3]
+        img = _f32c(x[0])
+        planes = self._pixel_planes(H, W, x.device)[0]
+        if self.bottom:
+            d0 = self._conv(self.enc_down_0, img, False, planes, H, W)
+            d1 = self._conv(self.enc_down_1, d0, False, None, H, W)
+        else:
+            d1 = self._conv(self.enc_down_1, img, False, planes, H, W)
+        h1, w1 = d1.shape[1], d1.shape[2]
+        d2 = self._conv(self.enc_down_2, d1, False, None, h1, w1)
+        h2, w2 = d2.shape[1], d2.shape[2]
+        d3 = self._conv(self.enc_down_3, d2, False, None, h2, w2)
+        u3 = self._conv(self.enc_up_3, d3, False, None, d3.shape[1], d3.shape[2])      # kept at low resolution
+        u2 = self._conv(self.enc_up_2, u3, True, d2, h2, w2)                           # cat[upsample(u3), d2]
+        return self._conv(self.enc_up_1, u2, True, d1, h1, w1)[None]                  # cat[upsample(u2), d1]
+
     def forward(self, x):
         W, H = x.shape[3], x.shape[2]
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p_.requires_grad for p_ in self.parameters()))
+        if (not needs_grad and x.is_cuda and x.shape[0] == 1 and x.dtype == torch.float32 and self.use_kernels
+                and H % (8 if self.bottom else 4) == 0 and W % (8 if self.bottom else 4) == 0):
+            return self._forward_inference(x)
         x_ = torch.cat([x, self._pixel_planes(H, W, x.device).expand(x.shape[0], -1, -1, -1)], dim=1)
         if self.bottom:
             x_down_1 = self.enc_down_1(self.enc_down_0(x_))
