@@ -6,16 +6,21 @@
 // Replaces the six (seven with `bottom`) cuDNN launches + 2 upsample + 3 cat launches of Encoder.forward
 // (reference models/model.py:36-61) when no gradient is needed; training keeps torch autograd / cuDNN.
 // The layers are tiny (0.9 GFLOP for the whole U-Net at 64x64): latency-bound library kernels take ~60 us each, a direct
-// shared-memory-tiled kernel ~10 us.  CTA = 8x8 output pixels x 32 output channels, 128 threads, thread = 4 pixels x 4 channels.
+// shared-memory-tiled kernel ~10 us.  CTA = 8x8 output pixels x 32 output channels; 4 warp groups of 128 threads split the input channels of every chunk
+// (one warp per scheduler left every FFMA / LDS latency exposed: 30 % issue utilisation), thread = 4 pixels x 4 channels.
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include "../../include/uorf_b200.h"
 
 namespace uorf {
 
 constexpr int kEncTile = 8;      // output pixels per CTA side
 constexpr int kEncOcb = 32;      // output channels per CTA
-constexpr int kEncIcb = 8;       // input channels per shared-memory chunk
-constexpr int kEncThreads = 128;
+constexpr int kEncIcb = 16;      // input channels per shared-memory chunk
+constexpr int kEncGroups = 4;    // warp groups per CTA; group g accumulates input channels 4g..4g+3 of every chunk
+constexpr int kEncGroupThreads = 128;
+constexpr int kEncThreads = kEncGroups * kEncGroupThreads;
+constexpr int kEncIcPerGroup = kEncIcb / kEncGroups;
 
 struct EncConvParams {
   const float* src_a; int ca; int up_a;     // up_a: src_a is [ca][H/2][W/2], read through the x2 bilinear upsample
@@ -24,38 +29,78 @@ struct EncConvParams {
   const float* bias;                        // [c_out]
   int c_out, h_in, w_in, h_out, w_out;
   float* out;                               // [c_out][h_out][w_out]
+  int split;                                // CTAs per cluster sharing one output tile (chunk c goes to cluster rank c % split)
 };
 
-// logical input value (zero padding outside the image); PyTorch's upsample_bilinear2d arithmetic for the upsampled source
-__device__ __forceinline__ float enc_fetch(const EncConvParams& p, int c, int y, int x) {
-  if (y < 0 || y >= p.h_in || x < 0 || x >= p.w_in) return 0.f;
-  if (c < p.ca) {
-    if (!p.up_a) return __ldg(p.src_a + ((long long)c * p.h_in + y) * p.w_in + x);
+// One staged input element: the raw global loads (four taps when read through the upsample) stay in registers while the
+// FFMA loop of the previous chunk runs; the interpolation arithmetic happens when the element is written to shared memory,
+// so nothing waits on the loads before the loop.  Everything about an element that does not depend on the chunk (patch
+// position, tap offsets, interpolation weights) is computed once per thread before the channel loop.
+template <bool UP> struct EncSlot;
+template <> struct EncSlot<false> {
+  int pk;                                    // (channel within chunk << 16) | y * w_in + x, or -1: padding / beyond the patch
+  float v;
+  __device__ __forceinline__ void setup(const EncConvParams& p, int i, int y, int x, bool in_patch) {
+    pk = (in_patch && y >= 0 && y < p.h_in && x >= 0 && x < p.w_in) ? ((i << 16) | (y * p.w_in + x)) : -1;
+  }
+  __device__ __forceinline__ void load(const EncConvParams& p, int ic0, int cin) {
+    const int ic = ic0 + (pk >> 16), yx = pk & 0xffff, hw = p.h_in * p.w_in;
+    v = 0.f;
+    if (pk >= 0 && ic < cin) v = ic < p.ca ? __ldg(p.src_a + ic * hw + yx) : __ldg(p.src_b + (ic - p.ca) * hw + yx);
+  }
+  __device__ __forceinline__ float value() const { return v; }
+};
+template <> struct EncSlot<true> {
+  int pk;                                    // as above (full-resolution offset, used for src_b channels)
+  unsigned o0, o1;                           // low-resolution tap offsets of src_a: (y0,x0) | (y0,x1) << 16, (y1,x0) | (y1,x1) << 16
+  float ly, lx;
+  float a00, a01, a10, a11;
+  __device__ __forceinline__ void setup(const EncConvParams& p, int i, int y, int x, bool in_patch) {
+    pk = (in_patch && y >= 0 && y < p.h_in && x >= 0 && x < p.w_in) ? ((i << 16) | (y * p.w_in + x)) : -1;
+    // PyTorch's upsample_bilinear2d source index (align_corners=False, scale 2)
     const int hs = p.h_in >> 1, ws = p.w_in >> 1;
     const float sy = fmaxf(0.5f * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (x + 0.5f) - 0.5f, 0.f);
     const int y0 = (int)sy, x0 = (int)sx;
     const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
-    const float ly = sy - y0, lx = sx - x0;
-    const float* s = p.src_a + (long long)c * hs * ws;
-    const float a00 = __ldg(s + y0 * ws + x0), a01 = __ldg(s + y0 * ws + x1), a10 = __ldg(s + y1 * ws + x0), a11 = __ldg(s + y1 * ws + x1);
+    ly = sy - y0; lx = sx - x0;
+    o0 = pk >= 0 ? (unsigned)(y0 * ws + x0) | ((unsigned)(y0 * ws + x1) << 16) : 0u;
+    o1 = pk >= 0 ? (unsigned)(y1 * ws + x0) | ((unsigned)(y1 * ws + x1) << 16) : 0u;
+  }
+  __device__ __forceinline__ void load(const EncConvParams& p, int ic0, int cin) {
+    const int ic = ic0 + (pk >> 16);
+    a00 = a01 = a10 = a11 = 0.f;
+    if (pk >= 0 && ic < cin) {
+      if (ic < p.ca) {
+        const float* s = p.src_a + ic * ((p.h_in >> 1) * (p.w_in >> 1));
+        a00 = __ldg(s + (o0 & 0xffffu)); a01 = __ldg(s + (o0 >> 16)); a10 = __ldg(s + (o1 & 0xffffu)); a11 = __ldg(s + (o1 >> 16));
+      } else {
+        a00 = __ldg(p.src_b + (ic - p.ca) * (p.h_in * p.w_in) + (pk & 0xffff));
+      }
+    }
+  }
+  __device__ __forceinline__ float value(const EncConvParams& p, int ic0) const {
+    if (ic0 + (pk >> 16) >= p.ca) return a00;            // src_b channel (or padding: 0)
     return (1.f - ly) * ((1.f - lx) * a00 + lx * a01) + ly * ((1.f - lx) * a10 + lx * a11);
   }
-  return __ldg(p.src_b + ((long long)(c - p.ca) * p.h_in + y) * p.w_in + x);
-}
+};
 
-template <int STRIDE>
-__global__ void __launch_bounds__(kEncThreads) encoder_conv3x3_kernel(const EncConvParams p) {
+template <int STRIDE, bool UP>
+__global__ void __launch_bounds__(kEncThreads, 1) encoder_conv3x3_kernel(const EncConvParams p) {
   constexpr int PH = (kEncTile - 1) * STRIDE + 3;       // input patch side: 10 (stride 1) / 17 (stride 2)
-  constexpr int PW = PH + 1;                            // padded row
   constexpr int NCOL = 3 * STRIDE + 3;                  // input columns one thread touches per row: 6 / 9
-  __shared__ float s_in[kEncIcb][PH][PW];
-  __shared__ __align__(16) float s_w[kEncIcb][9][kEncOcb];
+  constexpr int IN_FLOATS = kEncIcb * PH * PH, W_FLOATS = kEncIcb * 9 * kEncOcb;
+  constexpr int RED_FLOATS = (kEncGroups - 1) * 16 * kEncGroupThreads;
+  constexpr int SMEM_FLOATS = IN_FLOATS + W_FLOATS > RED_FLOATS ? IN_FLOATS + W_FLOATS : RED_FLOATS;
+  __shared__ __align__(16) float smem[SMEM_FLOATS];
+  float (*s_w)[9][kEncOcb] = reinterpret_cast<float (*)[9][kEncOcb]>(smem);                       // [kEncIcb][9][kEncOcb]
+  float (*s_in)[PH][PH] = reinterpret_cast<float (*)[PH][PH]>(smem + W_FLOATS);                   // [kEncIcb][PH][PH]: flat index = staging index
   const int tiles_x = (p.w_out + kEncTile - 1) / kEncTile;
   const int ty0 = (blockIdx.x / tiles_x) * kEncTile, tx0 = (blockIdx.x % tiles_x) * kEncTile;
   const int oc_base = blockIdx.y * kEncOcb;
   const int tid = threadIdx.x;
-  const int og = tid & 7;                  // output-channel group: channels oc_base + 4*og .. +3
-  const int pg = tid >> 3;                 // pixel group 0..15: row pg >> 1, columns 4*(pg & 1) .. +3
+  const int grp = tid / kEncGroupThreads, t = tid % kEncGroupThreads;
+  const int og = t & 7;                    // output-channel group: channels oc_base + 4*og .. +3
+  const int pg = t >> 3;                   // pixel group 0..15: row pg >> 1, columns 4*(pg & 1) .. +3
   const int py = pg >> 1, px0 = (pg & 1) * 4;
   const int cin = p.ca + p.cb;
   float acc[4][4];
@@ -64,42 +109,123 @@ __global__ void __launch_bounds__(kEncThreads) encoder_conv3x3_kernel(const EncC
 #pragma unroll
     for (int o = 0; o < 4; ++o) acc[j][o] = 0.f;
 
-  for (int ic0 = 0; ic0 < cin; ic0 += kEncIcb) {
-    __syncthreads();
-    for (int e = tid; e < kEncIcb * PH * PH; e += kEncThreads) {
-      const int i = e / (PH * PH), r = (e / PH) % PH, c = e % PH;
-      const int ic = ic0 + i;
-      s_in[i][r][c] = ic < cin ? enc_fetch(p, ic, ty0 * STRIDE - 1 + r, tx0 * STRIDE - 1 + c) : 0.f;
+  // Register-staged software pipeline: the global loads of chunk c+1 (fixed trip counts, fully unrolled, so all of a thread's
+  // loads are in flight at once) are issued before the FFMA loop of chunk c and land in shared memory after it.
+  constexpr int N_IN = (IN_FLOATS + kEncThreads - 1) / kEncThreads;
+  constexpr int N_W = (W_FLOATS / 4 + kEncThreads - 1) / kEncThreads;
+  EncSlot<UP> vin[N_IN];
+  float4 vw[N_W];
+  int woff[N_W];                             // (channel within chunk << 24) | offset inside the chunk's [i][9][c_out] weight rows, or -1
+#pragma unroll
+  for (int q = 0; q < N_IN; ++q) {
+    const int e = tid + q * kEncThreads;
+    const int i = e / (PH * PH), r = (e / PH) % PH, c = e % PH;
+    vin[q].setup(p, i, ty0 * STRIDE - 1 + r, tx0 * STRIDE - 1 + c, e < IN_FLOATS);
+  }
+#pragma unroll
+  for (int q = 0; q < N_W; ++q) {
+    const int e = tid + q * kEncThreads;                    // float4 index: [i][k][o4]
+    const int i = e / (9 * kEncOcb / 4), k = (e / (kEncOcb / 4)) % 9, o = (e % (kEncOcb / 4)) * 4;
+    woff[q] = (e < W_FLOATS / 4 && oc_base + o < p.c_out) ? ((i << 24) | ((i * 9 + k) * p.c_out + oc_base + o)) : -1;   // c_out % 4 == 0
+  }
+  auto load_chunk = [&](int ic0) {
+#pragma unroll
+    for (int q = 0; q < N_IN; ++q) vin[q].load(p, ic0, cin);
+    const float* wbase = p.weight_t + ic0 * 9 * p.c_out;
+#pragma unroll
+    for (int q = 0; q < N_W; ++q) {
+      vw[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (woff[q] >= 0 && ic0 + (woff[q] >> 24) < cin) vw[q] = __ldg(reinterpret_cast<const float4*>(wbase + (woff[q] & 0xffffff)));
     }
-    for (int e = tid; e < kEncIcb * 9 * kEncOcb; e += kEncThreads) {
-      const int i = e / (9 * kEncOcb), k = (e / kEncOcb) % 9, o = e % kEncOcb;
-      const int ic = ic0 + i, oc = oc_base + o;
-      s_w[i][k][o] = (ic < cin && oc < p.c_out) ? __ldg(p.weight_t + ((long long)ic * 9 + k) * p.c_out + oc) : 0.f;
+  };
+  const int rank = p.split > 1 ? (int)blockIdx.z : 0;        // cluster dims are (1, 1, split) and gridDim.z == split
+  const int ic_step = kEncIcb * p.split;
+  load_chunk(rank * kEncIcb);
+  for (int ic0 = rank * kEncIcb; ic0 < cin; ic0 += ic_step) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < N_IN; ++q) {
+      const int e = tid + q * kEncThreads;
+      if (e < IN_FLOATS) {
+        if constexpr (UP) smem[W_FLOATS + e] = vin[q].value(p, ic0);
+        else smem[W_FLOATS + e] = vin[q].value();
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < N_W; ++q) {
+      const int e = tid + q * kEncThreads;
+      if (e < W_FLOATS / 4) reinterpret_cast<float4*>(smem)[e] = vw[q];
     }
     __syncthreads();
+    if (ic0 + ic_step < cin) load_chunk(ic0 + ic_step);
+    if (ic0 + grp * kEncIcPerGroup < cin) {                   // warp-uniform: skip channel slices beyond the input
 #pragma unroll 2
-    for (int i = 0; i < kEncIcb; ++i) {
+      for (int ii = 0; ii < kEncIcPerGroup; ++ii) {
+        const int i = grp * kEncIcPerGroup + ii;
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        float a[NCOL];
-        const float* row = &s_in[i][py * STRIDE + ky][px0 * STRIDE];
+        for (int ky = 0; ky < 3; ++ky) {
+          float a[NCOL];
+          const float* row = &s_in[i][py * STRIDE + ky][px0 * STRIDE];
 #pragma unroll
-        for (int c = 0; c < NCOL; ++c) a[c] = row[c];
+          for (int c = 0; c < NCOL; ++c) a[c] = row[c];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const float4 w = *reinterpret_cast<const float4*>(&s_w[i][ky * 3 + kx][4 * og]);
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 w = *reinterpret_cast<const float4*>(&s_w[i][ky * 3 + kx][4 * og]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float v = a[j * STRIDE + kx];
-            acc[j][0] = fmaf(v, w.x, acc[j][0]);
-            acc[j][1] = fmaf(v, w.y, acc[j][1]);
-            acc[j][2] = fmaf(v, w.z, acc[j][2]);
-            acc[j][3] = fmaf(v, w.w, acc[j][3]);
+            for (int j = 0; j < 4; ++j) {
+              const float v = a[j * STRIDE + kx];
+              acc[j][0] = fmaf(v, w.x, acc[j][0]);
+              acc[j][1] = fmaf(v, w.y, acc[j][1]);
+              acc[j][2] = fmaf(v, w.z, acc[j][2]);
+              acc[j][3] = fmaf(v, w.w, acc[j][3]);
+            }
           }
         }
       }
     }
   }
+  // fixed-order reduction of the groups' partial sums through shared memory (deterministic)
+  __syncthreads();
+  if (grp > 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int o = 0; o < 4; ++o) smem[((grp - 1) * 16 + j * 4 + o) * kEncGroupThreads + t] = acc[j][o];
+  }
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int g = 0; g < kEncGroups - 1; ++g)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[j][o] += smem[(g * 16 + j * 4 + o) * kEncGroupThreads + t];
+  }
+  // ... and of the cluster's CTAs (small images: the input channels are split over a cluster so more SMs work on the
+  // layer) through distributed shared memory, summed by rank 0 in rank order
+  if (p.split > 1) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __syncthreads();
+    if (grp == 0 && rank > 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) smem[(j * 4 + o) * kEncGroupThreads + t] = acc[j][o];
+    }
+    cluster.sync();
+    if (grp == 0 && rank == 0) {
+      for (int r = 1; r < p.split; ++r) {
+        const float* remote = cluster.map_shared_rank(smem, r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int o = 0; o < 4; ++o) acc[j][o] += remote[(j * 4 + o) * kEncGroupThreads + t];
+      }
+    }
+    cluster.sync();                                           // remote shared memory stays alive until rank 0 has read it
+  }
+  if (grp > 0 || rank > 0) return;
   const int y = ty0 + py;
   if (y >= p.h_out) return;
 #pragma unroll
@@ -124,9 +250,27 @@ int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* sr
   p.h_out = (h_in - 1) / stride + 1;
   p.w_out = (w_in - 1) / stride + 1;
   p.out = out;
-  dim3 grid(((p.h_out + kEncTile - 1) / kEncTile) * ((p.w_out + kEncTile - 1) / kEncTile), (c_out + kEncOcb - 1) / kEncOcb);
-  if (stride == 1) encoder_conv3x3_kernel<1><<<grid, kEncThreads, 0, stream>>>(p);
-  else encoder_conv3x3_kernel<2><<<grid, kEncThreads, 0, stream>>>(p);
+  if (c_out % 4 != 0 || (long long)h_in * w_in > 65536 || (long long)(ca + cb) * 9 * c_out >= (1 << 24)) return UORF_ERR_UNSUPPORTED;
+  const int base_ctas = ((p.h_out + kEncTile - 1) / kEncTile) * ((p.w_out + kEncTile - 1) / kEncTile) * ((c_out + kEncOcb - 1) / kEncOcb);
+  const int n_chunks = (ca + cb + kEncIcb - 1) / kEncIcb;
+  p.split = 1;
+  while (p.split < 8 && base_ctas * p.split * 2 <= 148 && p.split * 2 <= n_chunks) p.split *= 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(((p.h_out + kEncTile - 1) / kEncTile) * ((p.w_out + kEncTile - 1) / kEncTile), (c_out + kEncOcb - 1) / kEncOcb, p.split);
+  cfg.blockDim = dim3(kEncThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = p.split;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.split > 1 ? 1 : 0;
+  cudaError_t err;
+  if (stride == 1 && up_a) err = cudaLaunchKernelEx(&cfg, encoder_conv3x3_kernel<1, true>, p);
+  else if (stride == 1) err = cudaLaunchKernelEx(&cfg, encoder_conv3x3_kernel<1, false>, p);
+  else if (stride == 2 && !up_a) err = cudaLaunchKernelEx(&cfg, encoder_conv3x3_kernel<2, false>, p);
+  else return UORF_ERR_UNSUPPORTED;
+  if (err != cudaSuccess) return UORF_ERR_DEVICE;
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
 
