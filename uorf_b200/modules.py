@@ -48,7 +48,8 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 # ======================================================================================================
-# Encoder — stays on cuDNN (north_star lists no encoder kernel); identical structure and state-dict keys.
+# Encoder — identical structure and state-dict keys.  Inference (no gradient, batch 1): direct-convolution kernels
+# (csrc/encoder.cu) with torch.cat and the bilinear upsamples folded into the input read; training: torch / cuDNN autograd.
 # ======================================================================================================
 class Encoder(nn.Module):
     """reference models/model.py:11-61"""
