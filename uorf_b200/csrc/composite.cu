@@ -9,10 +9,13 @@
 // warp).  The transmittance is an exclusive product scan: sequential inside a lane, a log2(L)-step segmented shuffle scan
 // across the group; the ray sums are segmented butterfly reductions.  HBM-bound: 24 B per sample + 28 B per ray.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace uorf {
 
-__device__ __forceinline__ float group_sum(float v, int L) {
+template <int L>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
   for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
@@ -39,14 +42,14 @@ __device__ __forceinline__ void load_samples(const float4* __restrict__ raw, con
   }
 }
 
-template <int S>
+template <int S, int L>
 __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
-                                                            const float* __restrict__ rays_d, long long R, long long Rg, int D, int L, int vec,
+                                                            const float* __restrict__ rays_d, long long R, long long Rg, int D, int vec,
                                                             float* __restrict__ rgb_map, float* __restrict__ depth_map,
                                                             float* __restrict__ weights_norm, float* __restrict__ mask_map) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & (L - 1);          // lane within the ray's group
-  const int rpw = 32 / L;                  // rays per warp
+  constexpr int rpw = 32 / L;              // rays per warp
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const bool vec_z = vec != 0;   // D % 4 == 0 and 16-byte aligned z_vals / weights_norm: float4 accesses
   const int i0 = sub * S;
@@ -76,6 +79,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
     }
     // exclusive product over the previous lanes of the group
     float inc = lane_prod;
+#pragma unroll
     for (int o = 1; o < L; o <<= 1) {
       const float u = __shfl_up_sync(0xffffffffu, inc, o, L);
       if (sub >= o) inc *= u;
@@ -93,19 +97,20 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
       am += wi_ * v[j].w;
       if (active && i0 + j < D) sw += wi_ + 1e-5f;
     }
-    ar = group_sum(ar, L);
-    ag = group_sum(ag, L);
-    ab = group_sum(ab, L);
-    sw = group_sum(sw, L);
-    if (mask_map) am = group_sum(am, L);
+    ar = group_sum<L>(ar);
+    ag = group_sum<L>(ag);
+    ab = group_sum<L>(ab);
+    sw = group_sum<L>(sw);
+    if (mask_map) am = group_sum<L>(am);
     float dep = 0.f;
     float wn[S];
+    const float inv_sw = 1.f / sw;         // one division per lane; the per-sample products differ from w / sum by <= 1 ulp
 #pragma unroll
     for (int j = 0; j < S; ++j) {
-      wn[j] = (active && i0 + j < D) ? (w[j] + 1e-5f) / sw : 0.f;
+      wn[j] = (active && i0 + j < D) ? (w[j] + 1e-5f) * inv_sw : 0.f;
       dep += wn[j] * z[j];
     }
-    dep = group_sum(dep, L);
+    dep = group_sum<L>(dep);
     if (weights_norm && active) {
       float* dst = weights_norm + r * D + i0;
       if (vec_z && i0 + S <= D) {
@@ -129,13 +134,13 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
 
 // grad of rgb_map w.r.t. raw:  d rgb_i = g * w_i ;  G_i = g . rgb_i ;  S_i = sum_{m>i} G_m w_m ;
 //   d alpha_i = G_i T_i - S_i / (1 - alpha_i + 1e-10) ;  d sigma_i = d alpha_i * delta_i * exp(-sigma_i delta_i)
-template <int S>
+template <int S, int L>
 __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
                                                             const float* __restrict__ rays_d, const float* __restrict__ grad_rgb,
-                                                            long long R, long long Rg, int D, int L, int vec, float4* __restrict__ grad_raw) {
+                                                            long long R, long long Rg, int D, int vec, float4* __restrict__ grad_raw) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & (L - 1);
-  const int rpw = 32 / L;
+  constexpr int rpw = 32 / L;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const bool vec_z = vec != 0;   // D % 4 == 0 and 16-byte aligned z_vals / weights_norm: float4 accesses
   const int i0 = sub * S;
@@ -167,6 +172,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __rest
       lane_prod *= term[j];
     }
     float inc = lane_prod;
+#pragma unroll
     for (int o = 1; o < L; o <<= 1) {
       const float u = __shfl_up_sync(0xffffffffu, inc, o, L);
       if (sub >= o) inc *= u;
@@ -188,6 +194,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __rest
       lane_gw += G[j] * w[j];
     }
     float rinc = lane_gw;                  // inclusive suffix sum over lanes >= sub of the group
+#pragma unroll
     for (int o = 1; o < L; o <<= 1) {
       const float u = __shfl_down_sync(0xffffffffu, rinc, o, L);
       if (sub + o < L) rinc += u;
@@ -207,7 +214,9 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __rest
 }
 
 static void composite_shape(int D, int& S, int& L) {
+  static const int forced = [] { const char* e = getenv("UORF_COMPOSITE_S"); return e ? atoi(e) : 0; }();   // tuning override
   S = D > 128 ? 8 : 4;
+  if (forced == 8 && D > 32) S = 8;        // 8 consecutive samples per lane: 128 B of raw per lane in flight, one scan step fewer
   const int need = (D + S - 1) / S;
   L = 1;
   while (L < need) L <<= 1;
@@ -223,19 +232,37 @@ static int composite_grid(long long R, int L, int num_sms) {
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
+// (S, L) are compile-time: the shuffle scans / butterflies unroll and interleave
+#define UORF_COMPOSITE_DISPATCH(S_, L_, CALL)                                   \
+  do {                                                                          \
+    if (S_ == 4) {                                                              \
+      switch (L_) {                                                             \
+        case 1: { constexpr int kS = 4, kL = 1; CALL; } break;                  \
+        case 2: { constexpr int kS = 4, kL = 2; CALL; } break;                  \
+        case 4: { constexpr int kS = 4, kL = 4; CALL; } break;                  \
+        case 8: { constexpr int kS = 4, kL = 8; CALL; } break;                  \
+        case 16: { constexpr int kS = 4, kL = 16; CALL; } break;                \
+        default: { constexpr int kS = 4, kL = 32; CALL; } break;                \
+      }                                                                         \
+    } else {                                                                    \
+      switch (L_) {                                                             \
+        case 8: { constexpr int kS = 8, kL = 8; CALL; } break;                  \
+        case 16: { constexpr int kS = 8, kL = 16; CALL; } break;                \
+        default: { constexpr int kS = 8, kL = 32; CALL; } break;                \
+      }                                                                         \
+    }                                                                           \
+  } while (0)
+
 int launch_composite_fwd(const float* raw, const float* z_vals, const float* rays_d, long long R, long long Rg, int D, float* rgb_map,
                          float* depth_map, float* weights_norm, float* mask_map, int num_sms, cudaStream_t stream) {
   if (R == 0) return UORF_OK;
   int S, L;
   composite_shape(D, S, L);
+  if (L > 32) return UORF_ERR_UNSUPPORTED;       // D > 256
   const int grid = composite_grid(R, L, num_sms);
   const int vec = composite_vec(D, z_vals, weights_norm);
-  if (S == 4)
-    composite_fwd_kernel<4><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, R, Rg, D, L, vec, rgb_map, depth_map,
-                                                      weights_norm, mask_map);
-  else
-    composite_fwd_kernel<8><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, R, Rg, D, L, vec, rgb_map, depth_map,
-                                                      weights_norm, mask_map);
+  UORF_COMPOSITE_DISPATCH(S, L, (composite_fwd_kernel<kS, kL><<<grid, 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(raw), z_vals, rays_d, R, Rg, D, vec, rgb_map, depth_map, weights_norm, mask_map)));
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
 
@@ -244,14 +271,11 @@ int launch_composite_bwd(const float* raw, const float* z_vals, const float* ray
   if (R == 0) return UORF_OK;
   int S, L;
   composite_shape(D, S, L);
+  if (L > 32) return UORF_ERR_UNSUPPORTED;
   const int grid = composite_grid(R, L, num_sms);
   const int vec = composite_vec(D, z_vals, nullptr);
-  if (S == 4)
-    composite_bwd_kernel<4><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, grad_rgb, R, Rg, D, L, vec,
-                                                      reinterpret_cast<float4*>(grad_raw));
-  else
-    composite_bwd_kernel<8><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(raw), z_vals, rays_d, grad_rgb, R, Rg, D, L, vec,
-                                                      reinterpret_cast<float4*>(grad_raw));
+  UORF_COMPOSITE_DISPATCH(S, L, (composite_bwd_kernel<kS, kL><<<grid, 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(raw), z_vals, rays_d, grad_rgb, R, Rg, D, vec, reinterpret_cast<float4*>(grad_raw))));
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
 

@@ -135,6 +135,9 @@ __global__ void __launch_bounds__(256) sample_coords_kernel(const CoordParams p)
 // consecutive depth samples of one ray, so the pixel / view decode and the 12 camera-matrix reads are shared by 4 samples and
 // every store is a 16-byte vector (3 x float4 of xyz, 1 x float4 of z_vals) - no shared-memory staging needed.
 // Arithmetic per sample is unchanged (same FMA chain as the general kernel).
+// POW2: D/4, Wc, Hc are powers of two and there are < 2^32 quads: the index decode is shifts and masks on 32-bit values (the
+// generic 64-bit divisions were ~40 % of the kernel's instructions, which made it issue-bound rather than HBM-bound).
+template <bool POW2>
 __global__ void __launch_bounds__(256) sample_coords_rm4_kernel(const CoordParams p) {
   __shared__ float s_zc[256], s_zv[256];
   __shared__ float s_c2w[kMaxStagedViews][12];
@@ -152,11 +155,22 @@ __global__ void __launch_bounds__(256) sample_coords_rm4_kernel(const CoordParam
   const long long rays = (long long)p.N * p.Hc * p.Wc;
   const long long nquads = rays * dq;
   for (long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x; qi < nquads; qi += (long long)gridDim.x * blockDim.x) {
-    const long long ray = qi / dq;
-    const int d0 = (int)(qi - ray * dq) * 4;
-    const int wc = (int)(ray % p.Wc);
-    const long long t2 = ray / p.Wc;
-    const int hc = (int)(t2 % p.Hc), n = (int)(t2 / p.Hc);
+    long long ray;
+    int d0, wc, hc, n;
+    if (POW2) {
+      const unsigned q32 = (unsigned)qi, r32 = q32 >> (p.sh_d - 2);
+      ray = r32;
+      d0 = (int)(q32 & (unsigned)(dq - 1)) * 4;
+      wc = (int)(r32 & (unsigned)(p.Wc - 1));
+      hc = (int)((r32 >> p.sh_w) & (unsigned)(p.Hc - 1));
+      n = (int)(r32 >> (p.sh_w + p.sh_h));
+    } else {
+      ray = qi / dq;
+      d0 = (int)(qi - ray * dq) * 4;
+      wc = (int)(ray % p.Wc);
+      const long long t2 = ray / p.Wc;
+      hc = (int)(t2 % p.Hc); n = (int)(t2 / p.Hc);
+    }
     const int h = (p.crop_h >= 0 ? p.crop_h : 0) + hc, w = (p.crop_w >= 0 ? p.crop_w : 0) + wc;
     float c[12];
 #pragma unroll
@@ -213,7 +227,8 @@ int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float*
   if (ray_major && scale == 1 && (f->D & 3) == 0 && aligned) {
     long long b4 = (total / 4 + 255) / 256;
     if (b4 > cap) b4 = cap;
-    sample_coords_rm4_kernel<<<(unsigned)b4, 256, 0, stream>>>(p);
+    if (p.sh_d >= 2 && p.sh_w >= 0 && p.sh_h >= 0 && total / 4 < (1LL << 32)) sample_coords_rm4_kernel<true><<<(unsigned)b4, 256, 0, stream>>>(p);
+    else sample_coords_rm4_kernel<false><<<(unsigned)b4, 256, 0, stream>>>(p);
   } else if (total < (1LL << 32) - 512) sample_coords_kernel<unsigned><<<(unsigned)blocks, 256, 0, stream>>>(p);
   else sample_coords_kernel<unsigned long long><<<(unsigned)blocks, 256, 0, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
