@@ -29,6 +29,26 @@ struct CoordParams {
   float* ray_dir;
 };
 
+// A frustum point is affine in the camera depth of its sample: with a_k = S[k][0] w + S[k][1] h + S[k][2],
+//   cam_k = a_k z + S[k][3],  world_r = z (sum_k C[r][k] a_k) + sum_k C[r][k] S[k][3],
+// so a ray needs one direction and one origin (both pre-scaled by 1/nss_scale) and a sample is ONE FMA per coordinate
+// instead of the reference's 33-operation matmul chain (projection.py:64-67).  The result differs from the reference's
+// fp32 matmuls by rounding only (<= 5e-7 on the |x| <= 2 NSS range; tests: <= 2e-6).  Both kernels use this function, so
+// their outputs are bit-equal re-indexings of each other.
+__device__ __forceinline__ void ray_affine(const float (&S)[16], const float (&c)[12], float inv_nss, float w, float h,
+                                           float (&dirn)[3], float (&orgn)[3]) {
+  float a[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a[k] = fmaf(S[k * 4 + 1], h, fmaf(S[k * 4], w, S[k * 4 + 2]));
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float d = fmaf(c[r * 4 + 3], a[3], fmaf(c[r * 4 + 2], a[2], fmaf(c[r * 4 + 1], a[1], __fmul_rn(c[r * 4], a[0]))));
+    const float o = fmaf(c[r * 4 + 3], S[15], fmaf(c[r * 4 + 2], S[11], fmaf(c[r * 4 + 1], S[7], __fmul_rn(c[r * 4], S[3]))));
+    dirn[r] = __fmul_rn(d, inv_nss);
+    orgn[r] = __fmul_rn(o, inv_nss);
+  }
+}
+
 // IdxT = unsigned for every realistic frustum (< 2^32 samples): 32-bit index math is several times cheaper than 64-bit
 template <typename IdxT>
 __global__ void __launch_bounds__(256) sample_coords_kernel(const CoordParams p) {
@@ -82,21 +102,14 @@ __global__ void __launch_bounds__(256) sample_coords_kernel(const CoordParams p)
       const int w0 = p.crop_w >= 0 ? p.crop_w : chunk % p.scale;
       const int h = h0 + hc * p.scale, w = w0 + wc * p.scale;
       const float zc = ztab ? s_zc[d] : __ldg(p.z_cam + d);
-      const float p0 = (float)w * zc, p1 = (float)h * zc, p2 = zc;
-      float cam[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-        cam[r] = fmaf(p.S[r * 4 + 3], 1.f, fmaf(p.S[r * 4 + 2], p2, fmaf(p.S[r * 4 + 1], p1, p.S[r * 4] * p0)));
       const float* Cg = p.cam2world + n * 16;
+      float c[12];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const float c0 = cstage ? s_c2w[n][r * 4 + 0] : __ldg(Cg + r * 4 + 0);
-        const float c1 = cstage ? s_c2w[n][r * 4 + 1] : __ldg(Cg + r * 4 + 1);
-        const float c2 = cstage ? s_c2w[n][r * 4 + 2] : __ldg(Cg + r * 4 + 2);
-        const float c3 = cstage ? s_c2w[n][r * 4 + 3] : __ldg(Cg + r * 4 + 3);
-        const float wv = fmaf(c3, cam[3], fmaf(c2, cam[2], fmaf(c1, cam[1], c0 * cam[0])));
-        s_xyz[buf][threadIdx.x * 3 + r] = wv * p.inv_nss;   // stride 3 is coprime with the 32 banks: conflict-free
-      }
+      for (int e = 0; e < 12; ++e) c[e] = cstage ? s_c2w[n][e] : __ldg(Cg + e);
+      float dirn[3], orgn[3];
+      ray_affine(p.S, c, p.inv_nss, (float)w, (float)h, dirn, orgn);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) s_xyz[buf][threadIdx.x * 3 + r] = fmaf(zc, dirn[r], orgn[r]);   // stride 3 is coprime with the 32 banks: conflict-free
       // ---- z_vals: [chunk][ray][D]; identical for every ray, so the flat index idx maps onto it directly ----
       if (p.z_vals) {
         const int dz = p.sh_d >= 0 ? (int)(idx & (IdxT)(p.D - 1)) : (int)(idx % p.D);
@@ -134,11 +147,12 @@ __global__ void __launch_bounds__(256) sample_coords_kernel(const CoordParams p)
 // Fast path for the layout the B200 drivers use (ray-major, D % 4 == 0, unpartitioned or cropped): one thread produces FOUR
 // consecutive depth samples of one ray, so the pixel / view decode and the 12 camera-matrix reads are shared by 4 samples and
 // every store is a 16-byte vector (3 x float4 of xyz, 1 x float4 of z_vals) - no shared-memory staging needed.
-// Arithmetic per sample is unchanged (same FMA chain as the general kernel).
+// Arithmetic per sample is the general kernel's (ray_affine + one FMA per coordinate).
 // POW2: D/4, Wc, Hc are powers of two and there are < 2^32 quads: the index decode is shifts and masks on 32-bit values (the
 // generic 64-bit divisions were ~40 % of the kernel's instructions, which made it issue-bound rather than HBM-bound).
 template <bool POW2>
 __global__ void __launch_bounds__(256) sample_coords_rm4_kernel(const CoordParams p) {
+  __shared__ __align__(16) float4 s_strip[8][96];
   __shared__ float s_zc[256], s_zv[256];
   __shared__ float s_c2w[kMaxStagedViews][12];
   const bool ztab = p.D <= 256;
@@ -154,7 +168,12 @@ __global__ void __launch_bounds__(256) sample_coords_rm4_kernel(const CoordParam
   const int dq = p.D >> 2;                                    // quads per ray
   const long long rays = (long long)p.N * p.Hc * p.Wc;
   const long long nquads = rays * dq;
-  for (long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x; qi < nquads; qi += (long long)gridDim.x * blockDim.x) {
+  const unsigned lane = threadIdx.x & 31;
+  // warp-uniform loop over the first quad of each warp (the shared-memory transpose below needs whole warps)
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < nquads; base += (long long)gridDim.x * blockDim.x) {
+    const long long qi = base + lane;
+    const bool full = base + 32 <= nquads;
+    if (qi >= nquads) continue;                               // ragged last warp only (then full == false: no warp-level sync below)
     long long ray;
     int d0, wc, hc, n;
     if (POW2) {
@@ -175,25 +194,36 @@ __global__ void __launch_bounds__(256) sample_coords_rm4_kernel(const CoordParam
     float c[12];
 #pragma unroll
     for (int e = 0; e < 12; ++e) c[e] = cstage ? s_c2w[n][e] : __ldg(p.cam2world + n * 16 + e);
+    float dirn[3], orgn[3];
+    ray_affine(p.S, c, p.inv_nss, (float)w, (float)h, dirn, orgn);
     float xyz[12], zv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int d = d0 + j;
       const float zc = ztab ? s_zc[d] : __ldg(p.z_cam + d);
       zv[j] = ztab ? s_zv[d] : (zc - p.near_plane) / p.inv_range_den;
-      const float p0 = (float)w * zc, p1 = (float)h * zc, p2 = zc;
-      float cam[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-        cam[r] = fmaf(p.S[r * 4 + 3], 1.f, fmaf(p.S[r * 4 + 2], p2, fmaf(p.S[r * 4 + 1], p1, p.S[r * 4] * p0)));
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-        xyz[3 * j + r] = fmaf(c[r * 4 + 3], cam[3], fmaf(c[r * 4 + 2], cam[2], fmaf(c[r * 4 + 1], cam[1], c[r * 4] * cam[0]))) * p.inv_nss;
+      for (int r = 0; r < 3; ++r) xyz[3 * j + r] = fmaf(zc, dirn[r], orgn[r]);
     }
-    float4* dst = reinterpret_cast<float4*>(p.coords + qi * 12);
-    dst[0] = make_float4(xyz[0], xyz[1], xyz[2], xyz[3]);
-    dst[1] = make_float4(xyz[4], xyz[5], xyz[6], xyz[7]);
-    dst[2] = make_float4(xyz[8], xyz[9], xyz[10], xyz[11]);
+    // the 48 B a thread produces are transposed through a per-warp shared-memory strip so that each of the three store
+    // instructions of the warp writes 512 contiguous bytes (a direct store puts 16 B at a 48 B stride: every 32 B sector
+    // is written in two halves by different instructions)
+    float4* strip = s_strip[threadIdx.x >> 5];
+    if (full) {
+      strip[3 * lane] = make_float4(xyz[0], xyz[1], xyz[2], xyz[3]);
+      strip[3 * lane + 1] = make_float4(xyz[4], xyz[5], xyz[6], xyz[7]);
+      strip[3 * lane + 2] = make_float4(xyz[8], xyz[9], xyz[10], xyz[11]);
+      __syncwarp();
+      float4* dst = reinterpret_cast<float4*>(p.coords) + (qi - lane) * 3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dst[k * 32 + lane] = strip[k * 32 + lane];
+      __syncwarp();
+    } else {
+      float4* dst = reinterpret_cast<float4*>(p.coords + qi * 12);
+      dst[0] = make_float4(xyz[0], xyz[1], xyz[2], xyz[3]);
+      dst[1] = make_float4(xyz[4], xyz[5], xyz[6], xyz[7]);
+      dst[2] = make_float4(xyz[8], xyz[9], xyz[10], xyz[11]);
+    }
     if (p.z_vals) reinterpret_cast<float4*>(p.z_vals)[qi] = make_float4(zv[0], zv[1], zv[2], zv[3]);
     if (p.ray_dir && d0 == 0) {
       const float x = (float)w, y = (float)h;
