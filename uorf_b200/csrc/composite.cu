@@ -11,6 +11,14 @@
 #include "common.cuh"
 #include <cstdlib>
 
+// Resident CTAs per SM the register allocation aims for.  Measured on the 524,288-ray x 64-sample shape (fwd / bwd fraction
+// of the HBM peak): unconstrained (54 registers, 4 CTAs) 0.68-0.79 / 0.70, 5 CTAs 0.86 / 0.81, 6 CTAs 0.86 / 0.74.
+// Rejected: staging the raw loads through shared memory so each warp load is 512 contiguous bytes (0.44-0.78), and 8
+// samples per lane at D = 64 (0.55).
+#ifndef UORF_COMPOSITE_MINB
+#define UORF_COMPOSITE_MINB 5
+#endif
+
 namespace uorf {
 
 template <int L>
@@ -43,7 +51,7 @@ __device__ __forceinline__ void load_samples(const float4* __restrict__ raw, con
 }
 
 template <int S, int L>
-__global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
+__global__ void __launch_bounds__(256, UORF_COMPOSITE_MINB) composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
                                                             const float* __restrict__ rays_d, long long R, long long Rg, int D, int vec,
                                                             float* __restrict__ rgb_map, float* __restrict__ depth_map,
                                                             float* __restrict__ weights_norm, float* __restrict__ mask_map) {
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const float4* __rest
 // grad of rgb_map w.r.t. raw:  d rgb_i = g * w_i ;  G_i = g . rgb_i ;  S_i = sum_{m>i} G_m w_m ;
 //   d alpha_i = G_i T_i - S_i / (1 - alpha_i + 1e-10) ;  d sigma_i = d alpha_i * delta_i * exp(-sigma_i delta_i)
 template <int S, int L>
-__global__ void __launch_bounds__(256) composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
+__global__ void __launch_bounds__(256, UORF_COMPOSITE_MINB) composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z_vals,
                                                             const float* __restrict__ rays_d, const float* __restrict__ grad_rgb,
                                                             long long R, long long Rg, int D, int vec, float4* __restrict__ grad_raw) {
   const int lane = threadIdx.x & 31;
