@@ -730,3 +730,65 @@ def test_encoder_inference_kernels_match_cudnn(Z, S, bottom):
     y = enc(x.requires_grad_(True))
     y.sum().backward()
     assert enc.enc_up_1[0].weight.grad is not None
+
+
+# ------------------------------------------------------------------------------------------------------
+# adversarial driver (uorf_gan_model.py:137-311): generator step with the GAN term, discriminator step with R1
+# ------------------------------------------------------------------------------------------------------
+def test_gan_driver_generator_and_discriminator_steps():
+    from uorf_b200.gan_model import uorfGanModel, default_gan_options, g_nonsaturating_loss
+    from uorf_b200.nogan_model import uorfNoGanModel, default_train_options
+    g = load_golden("train_driver_coarse")
+    inp = {"img_data": g["img"], "cam2world": g["cam2world"], "azi_rot": g["azi_rot"], "paths": []}
+    # supervision 16: the reference discriminator only closes on a 4x4 map for sizes 16, 32, 64, 128 (1x1 stem with padding 1)
+    small = dict(num_slots=3, z_dim=40, n_samp=8, frustum_size=16, frustum_size_fine=16, render_size=16, supervision_size=16,
+                 input_size=32, n_img_each_scene=2, stage="coarse", gpu_ids=[0], percept_in=100)
+    torch.manual_seed(5)
+    m = uorfGanModel(default_gan_options(ndf=8, **small), precision="fp16x3", with_perceptual=False)
+    m.load_networks_from_state_dicts(g["enc"], g["sa"], g["dec"])
+    m.slot_noise = (g["noise_fg"].to(dev()), g["noise_bg"].to(dev()))
+    m.set_input(inp)
+    # before gan_train_epoch + gan_in the adversarial weight is 0: the step is exactly the no-GAN driver's step
+    ref = uorfNoGanModel(default_train_options(**small), precision="fp16x3", with_perceptual=False)
+    ref.load_networks_from_state_dicts(g["enc"], g["sa"], g["dec"])
+    ref.slot_noise = m.slot_noise
+    ref.set_input(inp)
+    ref.forward(epoch=0)
+    ref.backward()
+    m.forward(epoch=0)
+    assert m.weight_gan == 0 and m.loss_recon.item() == ref.loss_recon.item()
+    for o in m.optimizers:
+        o.zero_grad()
+    m.backward()
+    base = {n: p.grad.clone() for n, p in m.netDecoder.named_parameters() if p.grad is not None}
+    for n, p in ref.netDecoder.named_parameters():
+        assert torch.equal(base[n], p.grad), n
+    # with the adversarial term: loss_gan = softplus(-D(x_recon)).mean() (reported unweighted after backward), and the
+    # generator gradient is the no-GAN gradient plus weight_gan * d loss_gan / d theta
+    ep = m.opt.gan_train_epoch + m.opt.gan_in
+    m.forward(epoch=ep)
+    assert m.weight_gan == m.opt.weight_gan
+    with torch.no_grad():
+        want_gan = g_nonsaturating_loss(m.netDisc(m.x_recon)).item()
+    for o in m.optimizers:
+        o.zero_grad()
+    m.backward()
+    assert abs(float(m.loss_gan.detach()) - want_gan) < 1e-5
+    with_gan = {n: p.grad.clone() for n, p in m.netDecoder.named_parameters() if p.grad is not None}
+    assert any(not torch.equal(with_gan[n], base[n]) for n in base)
+    assert all(p.grad is None or not p.grad.abs().any() for p in m.netDisc.parameters()), "generator step touched D gradients"
+    # discriminator step: D moves, the generator does not; losses match a direct evaluation on (x, x_recon)
+    gen_before = [p.detach().clone() for p in m.parameters()]
+    d_before = [p.detach().clone() for p in m.netDisc.parameters()]
+    with torch.no_grad():
+        real = torch.nn.functional.interpolate(g["img"].to(dev()), size=16, mode="bilinear", align_corners=False)
+        want_real = torch.nn.functional.softplus(-m.netDisc(real)).mean().item()
+        want_fake = torch.nn.functional.softplus(m.netDisc(m.x_recon)).mean().item()
+    m.d_scheduler.step()                                   # the warm-up schedule starts at lr = 0, as in the reference
+    m.forward_disc(it=0)                                   # it % 32 == 0: logistic step + R1 step
+    assert abs(float(m.loss_d_real) - want_real) < 1e-5 and abs(float(m.loss_d_fake) - want_fake) < 1e-5
+    assert torch.isfinite(m.loss_r1)
+    assert all(torch.equal(a, b) for a, b in zip(gen_before, m.parameters()))
+    assert any(not torch.equal(a, b) for a, b in zip(d_before, m.netDisc.parameters()))
+    assert all(not p.requires_grad for p in m.netDisc.parameters())
+    assert set(m.get_current_losses()) == {"recon", "perc", "gan", "d_real", "d_fake"}

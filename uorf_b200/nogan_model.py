@@ -167,6 +167,7 @@ class uorfNoGanModel:
         rendered = rgb_map.view(N, H, W, 3).permute([0, 3, 1, 2])
         x_recon = rendered * 2 - 1
         self.loss_recon = self.L2_loss(x_recon, x)
+        self.loss_extra = self._extra_generator_loss(x_recon, x, epoch)   # None here; the adversarial term of the GAN driver
         if self.with_perceptual:
             x_norm = ((x + 1) / 2 - self._vgg_mean) / self._vgg_std
             rendered_norm = (rendered - self._vgg_mean) / self._vgg_std
@@ -175,7 +176,7 @@ class uorfNoGanModel:
         else:
             self.loss_perc = torch.zeros((), device=dev)
         with torch.no_grad():
-            self.x_recon, self.rendered = x_recon.detach(), rendered.detach()
+            self.x_recon, self.rendered, self.x_sup = x_recon.detach(), rendered.detach(), x.detach()
             for i in range(min(N, opt.n_img_each_scene)):
                 setattr(self, f"x_rec{i}", x_recon[i].detach())
                 setattr(self, f"x{i}", x[i])
@@ -208,8 +209,17 @@ class uorfNoGanModel:
             for k in range(K):
                 setattr(self, f"slot{k}_attn", a[k] * 2 - 1)
 
+    def _extra_generator_loss(self, x_recon, x, epoch):
+        return None
+
+    def _graph_key_extra(self, epoch):
+        """epoch-dependent constants of a subclass that are baked into a captured step"""
+        return ()
+
     def backward(self):
         loss = self.loss_recon + self.loss_perc
+        if self.loss_extra is not None:
+            loss = loss + self.loss_extra
         loss.backward()
         self.loss_perc = self.loss_perc / self.weight_percept if self.weight_percept > 0 else self.loss_perc
 
@@ -230,7 +240,7 @@ class uorfNoGanModel:
         opt = self.opt
         key = (opt.weight_percept if epoch >= opt.percept_in else 0,
                opt.dens_noise if (epoch <= opt.percept_in and opt.fixed_locality) else 0, bool(self.netDecoder.locality),
-               tuple(self.x.shape), tuple(self.cam2world.shape), self.slot_noise is None)
+               tuple(self.x.shape), tuple(self.cam2world.shape), self.slot_noise is None) + tuple(self._graph_key_extra(epoch))
         st = self._static
         if st is None or st["x"].shape != self.x.shape or st["cam2world"].shape != self.cam2world.shape:
             st = self._static = {"x": self.x.clone(), "cam2world": self.cam2world.clone(), "nss2cam0": self.nss2cam0.clone()}
