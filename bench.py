@@ -454,7 +454,7 @@ def run_train(args):
 
     def step(inputs):
         model.set_input(inputs)
-        model.optimize_parameters(epoch=0)
+        model.optimize_parameters(epoch=opt.percept_in)    # perceptual loss active: the steady-state step of the schedule
         model.update_learning_rate()
 
     def barrier():
@@ -523,7 +523,7 @@ def run_train(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision + " forward; fp16 tensor-core backward with fp32 accumulation; fp32 elsewhere", "data": "synthetic",
                 "config": dict(c, step="Encoder+SlotAttention+sampling+decoder+compositing fwd+bwd, MSE + VGG16-relu4_3 perceptual "
-                               "(random-init VGG, weight 0 at epoch 0 exactly as the reference computes it), Adam",
+                               "(random-init VGG, weight_percept 0.006 active: epoch = percept_in), Adam",
                                parallelism=f"scene-sharded data parallel x{world}, one flat gradient all-reduce (NCCL)",
                                launch=("whole step (forward + backward" + (" + gradient all-reduce" if world > 1 else "") + " + Adam) replayed as one CUDA graph")
                                if use_graph else "eager launches",

@@ -138,6 +138,7 @@ class uorfNoGanModel:
         self.weight_percept = opt.weight_percept if epoch >= opt.percept_in else 0
         dens_noise = opt.dens_noise if (epoch <= opt.percept_in and opt.fixed_locality) else 0
         dev = self.device
+        rs = opt.render_size
         feature_map = self.netEncoder(F.interpolate(self.x[0:1], size=opt.input_size, mode="bilinear", align_corners=False))
         feat = feature_map.flatten(start_dim=2).permute([0, 2, 1])
         z_slots, attn = self.netSlotAttention(feat, noise=self.slot_noise)
@@ -150,15 +151,14 @@ class uorfNoGanModel:
             coords, z_vals, ray_dir = self.projection.construct_sampling_coor(cam2world, ray_major=True)
             x = F.interpolate(self.x, size=opt.supervision_size, mode="bilinear", align_corners=False)
         else:
-            rs = opt.render_size
             if self.crop_override is not None:
                 h0, w0 = int(self.crop_override[0]), int(self.crop_override[1])
-            else:   # same two device draws as the reference (:160-161); .item() is the sync the reference's slicing implies
+            else:   # same two device draws, after the slot noise, as the reference (:160-161); .item() is the sync its slicing implies
                 start_range = opt.frustum_size_fine - rs
                 h0 = int(torch.randint(low=0, high=start_range, size=(1,), device=dev).item())
                 w0 = int(torch.randint(low=0, high=start_range, size=(1,), device=dev).item())
-            coords, z_vals, ray_dir = self.projection_fine.construct_sampling_coor(cam2world, ray_major=True, crop=(h0, w0))
             x = self.x[:, :, h0:h0 + rs, w0:w0 + rs]
+            coords, z_vals, ray_dir = self.projection_fine.construct_sampling_coor(cam2world, ray_major=True, crop=(h0, w0))
         self.z_vals, self.ray_dir = z_vals, ray_dir
         W = H = opt.supervision_size
         raws, masked_raws, unmasked_raws, _ = self.netDecoder(coords, coords[None, ...].expand(K - 1, -1, -1), z_slots, self.nss2cam0,
@@ -168,10 +168,14 @@ class uorfNoGanModel:
         x_recon = rendered * 2 - 1
         self.loss_recon = self.L2_loss(x_recon, x)
         self.loss_extra = self._extra_generator_loss(x_recon, x, epoch)   # None here; the adversarial term of the GAN driver
-        if self.with_perceptual:
-            x_norm = ((x + 1) / 2 - self._vgg_mean) / self._vgg_std
+        if self.with_perceptual and self.weight_percept == 0:
+            # the reference evaluates both VGG passes and multiplies by zero (:181-183): skipped, the loss is exactly 0
+            self.loss_perc = torch.zeros((), device=dev)
+        elif self.with_perceptual:
             rendered_norm = (rendered - self._vgg_mean) / self._vgg_std
-            rendered_feat, x_feat = self.perceptual_net(rendered_norm), self.perceptual_net(x_norm)
+            rendered_feat = self.perceptual_net(rendered_norm)
+            with torch.no_grad():      # the ground-truth branch carries no gradient (frozen VGG, constant images)
+                x_feat = self.perceptual_net(((x + 1) / 2 - self._vgg_mean) / self._vgg_std)
             self.loss_perc = self.weight_percept * self.L2_loss(rendered_feat, x_feat)
         else:
             self.loss_perc = torch.zeros((), device=dev)
