@@ -13,6 +13,10 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 900 python bench.py --mode train --steps 20 --warmup 3 > gpurun_out/bench_train.log 2>&1
 timeout 900 python bench.py --mode train --steps 20 --warmup 3 --no-graph > gpurun_out/bench_train_eager.log 2>&1
 timeout 300 python scripts/bench_kernels.py 32 > gpurun_out/bench_kernels.json 2> gpurun_out/bench_kernels.err
+timeout 120 python scripts/bench_encoder.py > gpurun_out/bench_encoder.log 2>&1
+timeout 300 python bench.py --workload clevr567 --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/wl_clevr_fp16x3.log 2>&1
+timeout 300 python bench.py --workload clevr567 --steps 30 --warmup 5 --no-cpu-baseline --precision bf16 > gpurun_out/wl_clevr_bf16.log 2>&1
+timeout 300 python bench.py --mode train --workload room_diverse_fine --steps 20 --warmup 3 > gpurun_out/wl_fine.log 2>&1
 timeout 300 python scripts/train_breakdown.py > gpurun_out/train_breakdown.log 2>&1
 if [ "$1" = "ncu" ]; then
   timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
@@ -26,6 +30,8 @@ if [ "$1" = "ncu" ]; then
   timeout 300 python scripts/bench_kernels.py 32 > gpurun_out/plain5.log 2>&1 &&
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:composite_fwd -s 10 -c 1 -o gpurun_out/prof_composite -f python scripts/bench_kernels.py 32 > gpurun_out/ncu_full_composite.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:sample_coords -s 10 -c 1 -o gpurun_out/prof_sample_coords -f python scripts/bench_kernels.py 32 > gpurun_out/ncu_full_coords.log 2>&1
+  timeout 100 python scripts/enc_once.py > gpurun_out/plain7.log 2>&1 &&
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:encoder_conv -s 12 -c 6 -o gpurun_out/prof_encoder -f python scripts/enc_once.py > gpurun_out/ncu_full_encoder.log 2>&1
   timeout 600 python bench.py --mode train --steps 2 --warmup 1 --no-graph > gpurun_out/plain6.log 2>&1 &&
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:decoder_bwd_kernel -s 2 -c 1 -o gpurun_out/prof_decoder_bwd -f python bench.py --mode train --steps 2 --warmup 1 --no-graph > gpurun_out/ncu_full_bwd.log 2>&1
 fi

@@ -87,6 +87,27 @@ def decoder(tag, precision, repname="prof_decoder.ncu-rep", title=None, outname=
         print("traffic not updated:", e)
 
 
+def encoder(tag, repname="prof_encoder.ncu-rep"):
+    """one row per launch of the six (seven with `bottom`) encoder convolution kernels of one Encoder.forward"""
+    rep = os.path.join(G, repname)
+    if not os.path.exists(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, data = rows[0], rows[2:]
+    cols = ["Kernel Name", "Grid Size", "launch__cluster_dim_z", "gpu__time_duration.sum", "launch__registers_per_thread",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum"]
+    cols = [c for c in cols if c in hdr]
+    out = [f"# {tag}: `ncu --set full --clock-control none` of the encoder convolution launches of one Encoder.forward (64x64 input, z_dim 64; "
+           "scripts/enc_once.py)", "", "Layers in launch order: down1 (7->64 @64^2), down2 (s2 -> 32^2), down3 (s2 -> 16^2), up3 (16^2), "
+           "up2 (upsample + cat, 128->64 @32^2), up1 (upsample + cat, 128->64 @64^2).", "",
+           "| " + " | ".join(cols) + " |", "|" + "---|" * len(cols)]
+    for r in data:
+        out.append("| " + " | ".join(r[hdr.index(c)][:60] for c in cols) + " |")
+    open(os.path.join(P, f"{tag}_encoder_ncu.md"), "w").write("\n".join(out) + "\n")
+
+
 if __name__ == "__main__":
     tag = sys.argv[1]
     prec = sys.argv[2] if len(sys.argv) > 2 else "fp16x3"
@@ -101,4 +122,5 @@ if __name__ == "__main__":
             f"{tag}_sample_coords_ncu.md")
     decoder(tag, "", "prof_decoder_bwd.ncu-rep", "decoder_bwd_kernel launch (bench.py --mode train: K=8, 64^3 frustum, 4 views)",
             f"{tag}_decoder_bwd_ncu.md")
+    encoder(tag)
     print("wrote profiles/%s_*.md" % tag)

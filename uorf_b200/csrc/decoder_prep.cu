@@ -28,8 +28,13 @@ __device__ __forceinline__ void put(unsigned char* plane0, int passes, int f16, 
   }
 }
 
-// grid: x = 0..7 tile, y = 0 (bg) / 1 (fg);   x = 8: params;   x = 9: bias tile;   x = 10..: slot biases
+// grid: x = 0..7 tile, y = 0 (bg) / 1 (fg);   x = 8: params;   x = 9: bias tile;   x = 10..: slot biases;
+//       z = 0..kPrepSplit-1: interleaved slices of a block's element range (the work is a handful of dependent global loads per
+//       element: spreading it over more CTAs shortens the serial chain, the kernel is latency-bound)
+constexpr int kPrepSplit = 4;
+
 __global__ void decoder_prep_kernel(PrepArgs a) {
+  const int e_first = blockIdx.z * blockDim.x + threadIdx.x, e_step = kPrepSplit * blockDim.x;
   const int fg = blockIdx.y;
   const int Z = a.Z;
   const int I = kPosenc + Z;
@@ -43,7 +48,7 @@ __global__ void decoder_prep_kernel(PrepArgs a) {
 
   if (bx < 7) {
     unsigned char* tile = img + bx * kTileBytes;
-    for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+    for (int e = e_first; e < 64 * 64; e += e_step) {
       const int n = e >> 6, k = e & 63;
       float v = 0.f;
       if (n < Z) {
@@ -62,7 +67,7 @@ __global__ void decoder_prep_kernel(PrepArgs a) {
   } else if (bx == 7) {
     unsigned char* tile = img + 7 * kTileBytes;
     const int CH = Z / 4;
-    for (int e = threadIdx.x; e < 32 * 64; e += blockDim.x) {
+    for (int e = e_first; e < 32 * 64; e += e_step) {
       const int n = e >> 6, k = e & 63;
       float v = 0.f;
       if (k < Z) {
@@ -83,7 +88,7 @@ __global__ void decoder_prep_kernel(PrepArgs a) {
   } else if (bx == 8) {
     float* prm = reinterpret_cast<float*>(img + nplanes * kPlaneBytes);
     const int CH = Z / 4;
-    for (int e = threadIdx.x; e < kParamFloats; e += blockDim.x) {
+    for (int e = e_first; e < kParamFloats; e += e_step) {
       float v = 0.f;
       if (e < kPHeadB) {
         const int which = e >> 6, n = e & 63;
@@ -116,7 +121,7 @@ __global__ void decoder_prep_kernel(PrepArgs a) {
     // bias tile: column j holds bias vector j (see decoder_layout.h)
     unsigned char* tile = img + kBiasTileOff;
     const int nslots = fg ? a.K - 1 : 1;
-    for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+    for (int e = e_first; e < 64 * 64; e += e_step) {
       const int n = e >> 6, j = e & 63;
       float v = 0.f;
       if (n < Z) {
@@ -140,7 +145,7 @@ __global__ void decoder_prep_kernel(PrepArgs a) {
     if (s >= nslots) return;
     const float* z = a.z_slots + (fg ? (s + 1) : 0) * Z;
     float* sb = reinterpret_cast<float*>(img + nplanes * kPlaneBytes + kParamBytes) + s * kSlotBiasFloats;
-    for (int e = threadIdx.x; e < kSlotBiasFloats; e += blockDim.x) {
+    for (int e = e_first; e < kSlotBiasFloats; e += e_step) {
       const int which = e >> 6, n = e & 63;
       float v = 0.f;
       if (n < Z) {
@@ -164,7 +169,7 @@ int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int
   a.passes = passes;
   a.f16 = f16;
   a.image = static_cast<unsigned char*>(image);
-  dim3 grid(10 + (K - 1 > 1 ? K - 1 : 1), 2);
+  dim3 grid(10 + (K - 1 > 1 ? K - 1 : 1), 2, kPrepSplit);
   decoder_prep_kernel<<<grid, 256, 0, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kSaThreads) sa_kv_kernel(const SaParams p) {
 // ---- helpers for the per-slot CTAs (256 threads = 8 warps) -----------------------------------------
 // y[o] = bias[o] + sum_c W[o][c] * x[c] for o < n_out: one warp per output row, lanes stride over c, so the
 // weight rows are read with unit stride (coalesced) and reduced with shuffles.
-__device__ __forceinline__ void warp_matvec(const float* __restrict__ W, const float* __restrict__ bias, const float* x, float* y,
+__device__ __forceinline__ void warp_matvec(const float* W, const float* bias, const float* x, float* y,
                                             int n_out, int n_in, bool relu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   // kRows rows of a warp are loaded before any of them is reduced: the weight reads (L2 latency ~1 us on a cold line) of a
@@ -96,7 +96,7 @@ __device__ __forceinline__ void warp_matvec(const float* __restrict__ W, const f
 #pragma unroll
       for (int j = 0; j < kPer; ++j) {
         const int c = lane + 32 * j;
-        w[r][j] = (o < n_out && c < n_in) ? __ldg(W + (long long)o * n_in + c) : 0.f;
+        w[r][j] = (o < n_out && c < n_in) ? W[(long long)o * n_in + c] : 0.f;   // generic load: global or staged shared memory
       }
     }
     float xv[kPer];
@@ -143,10 +143,11 @@ __device__ __forceinline__ void warp0_layernorm(const float* x, const float* __r
   }
 }
 // q_k = to_q(LN(slot_k)) -> global q buffer
-__device__ __forceinline__ void slot_query(const SaParams& p, int k, const float* slot, float* s_ln, float* s_q, float* q_save) {
+__device__ __forceinline__ void slot_query(const SaParams& p, int k, const float* slot, float* s_ln, float* s_q, float* q_save,
+                                           const float* wq_staged = nullptr) {
   warp0_layernorm(slot, k == 0 ? p.w.to_q_bg_ln_w : p.w.to_q_ln_w, k == 0 ? p.w.to_q_bg_ln_b : p.w.to_q_ln_b, s_ln, p.C);
   __syncthreads();
-  warp_matvec(k == 0 ? p.w.to_q_bg_w : p.w.to_q_w, nullptr, s_ln, s_q, p.C, p.C, false);
+  warp_matvec(wq_staged ? wq_staged : (k == 0 ? p.w.to_q_bg_w : p.w.to_q_w), nullptr, s_ln, s_q, p.C, p.C, false);
   __syncthreads();
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
     p.qbuf[k * p.C + c] = s_q[c];
@@ -219,18 +220,59 @@ __global__ void __launch_bounds__(kSaThreads) sa_attn_kernel(const SaParams p) {
 }
 
 // ---- pass C (per iteration): reduce partials, GRUCell, residual MLP, next query; one CTA per slot ------
-__global__ void __launch_bounds__(kSaSlotThreads) sa_update_kernel(const SaParams p, int nblk, int it) {
+// All of a slot's weights (GRU 2 x 3C x C, residual MLP 2 x Hd x C, next query C x C, their biases: <= 180 KB) are pulled
+// into shared memory by five TMA bulk copies issued before the partial sums are reduced, so the six dependent matvec phases
+// read shared memory instead of paying one L2 round trip each (`staged`; needs 16-byte aligned tensors and C, Hd % 4 == 0).
+__global__ void __launch_bounds__(kSaSlotThreads) sa_update_kernel(const SaParams p, int nblk, int it, int staged) {
+  extern __shared__ __align__(128) float s_dyn[];
+  __shared__ uint64_t s_bar;
   __shared__ float s_u[kSaMaxC], s_h[kSaMaxC], s_g[6 * kSaMaxC], s_n[kSaMaxC], s_ln[kSaMaxC], s_m[kSaMaxHid], s_o[kSaMaxC];
   __shared__ float s_red[kSaSlotThreads / 32][kSaMaxC + 1];
   const int C = p.C, K = p.K, Hd = p.hidden, k = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool bg = k == 0;
+  const float* w_ih = bg ? p.w.gru_bg_w_ih : p.w.gru_w_ih;
+  const float* w_hh = bg ? p.w.gru_bg_w_hh : p.w.gru_w_hh;
+  const float* w_1 = bg ? p.w.to_res_bg_w1 : p.w.to_res_w1;
+  const float* w_2 = bg ? p.w.to_res_bg_w2 : p.w.to_res_w2;
+  const float* w_q = bg ? p.w.to_q_bg_w : p.w.to_q_w;
+  const float* b_ih = bg ? p.w.gru_bg_b_ih : p.w.gru_b_ih;
+  const float* b_hh = bg ? p.w.gru_bg_b_hh : p.w.gru_b_hh;
+  const float* b_1 = bg ? p.w.to_res_bg_b1 : p.w.to_res_b1;
+  const float* b_2 = bg ? p.w.to_res_bg_b2 : p.w.to_res_b2;
+  if (staged) {
+    float* d_ih = s_dyn;
+    float* d_hh = d_ih + 3 * C * C;
+    float* d_1 = d_hh + 3 * C * C;
+    float* d_2 = d_1 + Hd * C;
+    float* d_q = d_2 + C * Hd;
+    float* d_bih = d_q + C * C;
+    float* d_bhh = d_bih + 3 * C;
+    float* d_b1 = d_bhh + 3 * C;
+    float* d_b2 = d_b1 + Hd;
+    if (threadIdx.x == 0) {
+      mbar_init(&s_bar, 1);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(&s_bar, (uint32_t)((2 * 3 * C * C + 2 * Hd * C + C * C + 6 * C + Hd + C) * sizeof(float)));
+      bulk_g2s(d_ih, w_ih, 3 * C * C * 4, &s_bar);
+      bulk_g2s(d_hh, w_hh, 3 * C * C * 4, &s_bar);
+      bulk_g2s(d_1, w_1, Hd * C * 4, &s_bar);
+      bulk_g2s(d_2, w_2, C * Hd * 4, &s_bar);
+      bulk_g2s(d_q, w_q, C * C * 4, &s_bar);
+      bulk_g2s(d_bih, b_ih, 3 * C * 4, &s_bar);
+      bulk_g2s(d_bhh, b_hh, 3 * C * 4, &s_bar);
+      bulk_g2s(d_b1, b_1, Hd * 4, &s_bar);
+      bulk_g2s(d_b2, b_2, C * 4, &s_bar);
+    }
+    w_ih = d_ih; w_hh = d_hh; w_1 = d_1; w_2 = d_2; w_q = d_q; b_ih = d_bih; b_hh = d_bhh; b_1 = d_b1; b_2 = d_b2;
+  }
   // fixed-order reduction of the per-CTA partials: warp w sums blocks w, w+32, ...; then the 32 warp sums in order
   for (int c = lane; c <= C; c += 32) {
     float acc = 0.f;
     for (int b = warp; b < nblk; b += kSaSlotThreads / 32) acc += p.partial[((long long)b * K + k) * (C + 1) + c];
     s_red[warp][c] = acc;
   }
-  __syncthreads();
+  __syncthreads();                                   // also publishes the mbarrier initialisation to the waiting threads
   if (threadIdx.x <= C) {
     float acc = 0.f;
     for (int w = 0; w < kSaSlotThreads / 32; ++w) acc += s_red[w][threadIdx.x];
@@ -245,8 +287,9 @@ __global__ void __launch_bounds__(kSaSlotThreads) sa_update_kernel(const SaParam
   }
   if (threadIdx.x == 0) sv[3 * K * C + k] = s_red[0][C];   // sum over tokens of attn
   __syncthreads();
-  warp_matvec(k == 0 ? p.w.gru_bg_w_ih : p.w.gru_w_ih, k == 0 ? p.w.gru_bg_b_ih : p.w.gru_b_ih, s_u, s_g, 3 * C, C, false);
-  warp_matvec(k == 0 ? p.w.gru_bg_w_hh : p.w.gru_w_hh, k == 0 ? p.w.gru_bg_b_hh : p.w.gru_b_hh, s_h, s_g + 3 * C, 3 * C, C, false);
+  if (staged) mbar_wait(&s_bar, 0);
+  warp_matvec(w_ih, b_ih, s_u, s_g, 3 * C, C, false);
+  warp_matvec(w_hh, b_hh, s_h, s_g + 3 * C, 3 * C, C, false);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float r = 1.f / (1.f + expf(-(s_g[c] + s_g[3 * C + c])));
@@ -255,11 +298,11 @@ __global__ void __launch_bounds__(kSaSlotThreads) sa_update_kernel(const SaParam
     s_n[c] = (1.f - z) * n + z * s_h[c];  // new hidden state
   }
   __syncthreads();
-  warp0_layernorm(s_n, k == 0 ? p.w.to_res_bg_ln_w : p.w.to_res_ln_w, k == 0 ? p.w.to_res_bg_ln_b : p.w.to_res_ln_b, s_ln, C);
+  warp0_layernorm(s_n, bg ? p.w.to_res_bg_ln_w : p.w.to_res_ln_w, bg ? p.w.to_res_bg_ln_b : p.w.to_res_ln_b, s_ln, C);
   __syncthreads();
-  warp_matvec(k == 0 ? p.w.to_res_bg_w1 : p.w.to_res_w1, k == 0 ? p.w.to_res_bg_b1 : p.w.to_res_b1, s_ln, s_m, Hd, C, true);
+  warp_matvec(w_1, b_1, s_ln, s_m, Hd, C, true);
   __syncthreads();
-  warp_matvec(k == 0 ? p.w.to_res_bg_w2 : p.w.to_res_w2, k == 0 ? p.w.to_res_bg_b2 : p.w.to_res_b2, s_m, s_o, C, Hd, false);
+  warp_matvec(w_2, b_2, s_m, s_o, C, Hd, false);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float v = s_n[c] + s_o[c];
@@ -268,7 +311,7 @@ __global__ void __launch_bounds__(kSaSlotThreads) sa_update_kernel(const SaParam
     if (it + 1 < p.iters) sv[sa_saved_stride(K, C) + k * C + c] = v;   // slot_in of the next iteration
   }
   __syncthreads();
-  slot_query(p, k, s_n, s_ln, s_o, it + 1 < p.iters ? sv + sa_saved_stride(K, C) + K * C : nullptr);   // query for the next iteration
+  slot_query(p, k, s_n, s_ln, s_o, it + 1 < p.iters ? sv + sa_saved_stride(K, C) + K * C : nullptr, staged ? w_q : nullptr);   // query for the next iteration
 }
 
 size_t slot_attention_ws_floats(int ntok, int C, int K) {
@@ -293,11 +336,25 @@ int launch_slot_attention(const uorf_slot_attention_weights* w, const float* fea
   p.saved = p.qbuf + (size_t)K * C;
   p.slots = slots;
   p.attn = attn;
+  // weight staging of the per-slot update kernel: every tensor it bulk-copies must be 16-byte aligned and a multiple of 16 bytes
+  const size_t stage_bytes = (size_t)(2 * 3 * C * C + 2 * hidden * C + C * C + 6 * C + hidden + C) * sizeof(float);
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const int staged = (C % 4 == 0 && hidden % 4 == 0 && al(w->gru_w_ih) && al(w->gru_w_hh) && al(w->gru_bg_w_ih) && al(w->gru_bg_w_hh) &&
+                      al(w->to_res_w1) && al(w->to_res_w2) && al(w->to_res_bg_w1) && al(w->to_res_bg_w2) && al(w->to_q_w) && al(w->to_q_bg_w) &&
+                      al(w->gru_b_ih) && al(w->gru_b_hh) && al(w->gru_bg_b_ih) && al(w->gru_bg_b_hh) && al(w->to_res_b1) && al(w->to_res_b2) &&
+                      al(w->to_res_bg_b1) && al(w->to_res_bg_b2)) ? 1 : 0;
+  if (staged) {
+    static bool attr_set = false;      // idempotent; a benign race at worst sets it twice
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(sa_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return UORF_ERR_DEVICE;
+      attr_set = true;
+    }
+  }
   sa_kv_kernel<<<nblk, kSaThreads, 0, stream>>>(p);
   sa_init_kernel<<<K, kSaSlotThreads, 0, stream>>>(p);
   for (int it = 0; it < iters; ++it) {
     sa_attn_kernel<<<nblk, kSaThreads, 0, stream>>>(p);
-    sa_update_kernel<<<K, kSaSlotThreads, 0, stream>>>(p, nblk, it);
+    sa_update_kernel<<<K, kSaSlotThreads, staged ? stage_bytes : 0, stream>>>(p, nblk, it, staged);
   }
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
