@@ -588,11 +588,14 @@ __global__ void decoder_bwd_reduce_kernel(const float* partials, float* reduced,
   reduced[i] = acc / grad_scale(__ldg(draw_amax));   // undo the loss scale (exact: power of two)
 }
 
-// one CTA; all loops are tiny (<= 64x161 outputs)
+// Every output element is independent (<= 64x161 outputs per tensor, dot products of <= 64 terms): grid = (CTAs, 2) with
+// blockIdx.y = background / foreground and a grid-stride over the elements (as ONE CTA this kernel took 120 us of pure
+// load latency).
 __global__ void decoder_bwd_unfold_kernel(const FinalizeParams f) {
   const int Z = f.Z, K = f.K, I = kPosenc + Z, CH = Z / 4;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int fg = 0; fg < 2; ++fg) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  {
+    const int fg = blockIdx.y;
     const float* R = f.reduced + fg * kPartFloats;   // phase 0 = background, 1 = foreground
     const float* A0 = R + 0 * kAccFloats;   // [out][P cols]   before.0
     const float* A1 = R + 1 * kAccFloats;
@@ -750,7 +753,7 @@ int launch_decoder_bwd(const uorf_decoder_weights* w, const uorf_decoder_grads* 
   f.grid = grid;
   f.K = a->K;
   f.Z = a->Z;
-  decoder_bwd_unfold_kernel<<<1, 512, 0, stream>>>(f);
+  decoder_bwd_unfold_kernel<<<dim3(32, 2), 256, 0, stream>>>(f);
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
 

@@ -73,22 +73,22 @@ struct SabParams {
 };
 
 // y[o] = (bias ? bias[o] : 0) + sum_c W[o][c] x[c]; one warp per output row (coalesced weight reads)
-__device__ __forceinline__ void b_matvec(const float* __restrict__ W, const float* __restrict__ bias, const float* x, float* y, int n_out,
-                                         int n_in) {
+__device__ __forceinline__ void b_matvec(const float* W, const float* bias, const float* x, float* y, int n_out, int n_in) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int o = warp; o < n_out; o += nw) {
     float acc = 0.f;
-    for (int c = lane; c < n_in; c += 32) acc = fmaf(__ldg(W + (long long)o * n_in + c), x[c], acc);
+    for (int c = lane; c < n_in; c += 32) acc = fmaf(W[(long long)o * n_in + c], x[c], acc);   // generic load: global or staged shared memory
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
     if (lane == 0) y[o] = acc + (bias ? bias[o] : 0.f);
   }
 }
 // y[c] = sum_o W[o][c] x[o]  (transposed product; threads over c -> coalesced)
-__device__ __forceinline__ void b_matvec_t(const float* __restrict__ W, const float* x, float* y, int n_out, int n_in) {
+__device__ __forceinline__ void b_matvec_t(const float* W, const float* x, float* y, int n_out, int n_in) {
   for (int c = threadIdx.x; c < n_in; c += blockDim.x) {
     float acc = 0.f;
-    for (int o = 0; o < n_out; ++o) acc = fmaf(__ldg(W + (long long)o * n_in + c), x[o], acc);
+#pragma unroll 8
+    for (int o = 0; o < n_out; ++o) acc = fmaf(W[(long long)o * n_in + c], x[o], acc);
     y[c] = acc;
   }
 }
@@ -139,7 +139,8 @@ __device__ __forceinline__ void b_ln_bwd(const float* dy, const float* xhat, con
 // do_q : query-path backward of iteration it_q (needs dq_part from the token pass of that iteration); adds into dS
 // do_a : MLP / GRU backward of iteration it_a, consuming dS (= d slot_out of it_a) -> dU, dS (= d slot_in via the GRU state)
 // order inside one launch: do_q first (it completes d slot_in of iteration it_q = d slot_out of it_a = it_q - 1)
-__global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabParams p, int do_q, int it_q, int do_a, int it_a, int first) {
+__global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabParams p, int do_q, int it_q, int do_a, int it_a, int first,
+                                                                          int staged) {
   __shared__ float s_a[kBMaxC], s_b[kBMaxC], s_c[kBMaxC], s_d[kBMaxC], s_e[kBMaxC], s_f[kBMaxC], s_xh[kBMaxC], s_ds[kBMaxC];
   __shared__ float s_g[6 * kBMaxC], s_dg[6 * kBMaxC], s_m[kBMaxHid], s_dm[kBMaxHid];
   __shared__ float s_stat[2];
@@ -147,14 +148,46 @@ __global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabPar
   const SlotRegion R = slot_region(C, Hd);
   float* G = p.slot_reg + (long long)k * R.total;
   const bool bg = k == 0;
+  // The kernel is a chain of ~10 dependent matvec phases over the slot's weights: with `staged` they are pulled into shared
+  // memory once, by TMA bulk copies that run while the first phases read their inputs (as in the forward update kernel).
+  extern __shared__ __align__(128) float s_dyn[];
+  __shared__ uint64_t s_bar;
+  const float* w_ih = bg ? p.w.gru_bg_w_ih : p.w.gru_w_ih;
+  const float* w_hh = bg ? p.w.gru_bg_w_hh : p.w.gru_w_hh;
+  const float* w_1 = bg ? p.w.to_res_bg_w1 : p.w.to_res_w1;
+  const float* w_2 = bg ? p.w.to_res_bg_w2 : p.w.to_res_w2;
+  const float* w_q = bg ? p.w.to_q_bg_w : p.w.to_q_w;
+  if (staged) {
+    float* d_q = s_dyn;
+    float* d_ih = d_q + C * C;
+    float* d_hh = d_ih + 3 * C * C;
+    float* d_1 = d_hh + 3 * C * C;
+    float* d_2 = d_1 + Hd * C;
+    if (threadIdx.x == 0) {
+      mbar_init(&s_bar, 1);
+      fence_mbar_init();
+      const uint32_t bytes = (uint32_t)(((do_q ? C * C : 0) + (do_a ? 2 * 3 * C * C + 2 * Hd * C : 0)) * sizeof(float));
+      mbar_arrive_expect_tx(&s_bar, bytes);
+      if (do_q) bulk_g2s(d_q, w_q, C * C * 4, &s_bar);
+      if (do_a) {
+        bulk_g2s(d_ih, w_ih, 3 * C * C * 4, &s_bar);
+        bulk_g2s(d_hh, w_hh, 3 * C * C * 4, &s_bar);
+        bulk_g2s(d_1, w_1, Hd * C * 4, &s_bar);
+        bulk_g2s(d_2, w_2, C * Hd * 4, &s_bar);
+      }
+    }
+    w_q = d_q; w_ih = d_ih; w_hh = d_hh; w_1 = d_1; w_2 = d_2;
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) s_ds[c] = first ? p.grad_slots[k * C + c] : p.dS[k * C + c];
-  __syncthreads();
+  __syncthreads();                                   // also publishes the mbarrier initialisation
+  bool landed = !staged;                             // block-uniform: the first consumer of a staged weight waits once
 
   if (do_q) {
     const float* sv = p.saved + (long long)it_q * sab_saved_stride(K, C);
     // d q = sum of the token CTAs' partials (fixed order)
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float acc = 0.f;
+#pragma unroll 8
       for (int b = 0; b < p.nblk; ++b) acc += p.dq_part[((long long)b * K + k) * C + c];
       s_a[c] = acc;               // d q
       s_b[c] = sv[k * C + c];     // slot_in
@@ -163,7 +196,8 @@ __global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabPar
     b_ln_fwd(s_b, bg ? p.w.to_q_bg_ln_w : p.w.to_q_ln_w, bg ? p.w.to_q_bg_ln_b : p.w.to_q_ln_b, s_xh, s_c, s_stat, C);   // s_c = LN_q(slot)
     __syncthreads();
     b_outer_acc(G + R.wq, s_a, s_c, C, C);                                   // d to_q.1.weight
-    b_matvec_t(bg ? p.w.to_q_bg_w : p.w.to_q_w, s_a, s_d, C, C);             // s_d = d LN_q output
+    if (!landed) { mbar_wait(&s_bar, 0); landed = true; }
+    b_matvec_t(w_q, s_a, s_d, C, C);                                         // s_d = d LN_q output
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       G[R.lnq_w + c] += s_d[c] * s_xh[c];
@@ -183,8 +217,9 @@ __global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabPar
     }
     __syncthreads();
     // ---- recompute the forward of this iteration for slot k ----
-    b_matvec(bg ? p.w.gru_bg_w_ih : p.w.gru_w_ih, bg ? p.w.gru_bg_b_ih : p.w.gru_b_ih, s_b, s_g, 3 * C, C);
-    b_matvec(bg ? p.w.gru_bg_w_hh : p.w.gru_w_hh, bg ? p.w.gru_bg_b_hh : p.w.gru_b_hh, s_a, s_g + 3 * C, 3 * C, C);
+    if (!landed) { mbar_wait(&s_bar, 0); landed = true; }
+    b_matvec(w_ih, bg ? p.w.gru_bg_b_ih : p.w.gru_b_ih, s_b, s_g, 3 * C, C);
+    b_matvec(w_hh, bg ? p.w.gru_bg_b_hh : p.w.gru_b_hh, s_a, s_g + 3 * C, 3 * C, C);
     __syncthreads();
     // s_c = r, s_d = z, s_e = n, s_f = h'
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -198,14 +233,14 @@ __global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabPar
     float* s_ln = s_dg;  // reuse: LN_res output (C floats) lives in s_dg[0..C) until the GRU gate gradients are formed
     b_ln_fwd(s_f, bg ? p.w.to_res_bg_ln_w : p.w.to_res_ln_w, bg ? p.w.to_res_bg_ln_b : p.w.to_res_ln_b, s_xh, s_ln, s_stat, C);
     __syncthreads();
-    b_matvec(bg ? p.w.to_res_bg_w1 : p.w.to_res_w1, bg ? p.w.to_res_bg_b1 : p.w.to_res_b1, s_ln, s_m, Hd, C);
+    b_matvec(w_1, bg ? p.w.to_res_bg_b1 : p.w.to_res_b1, s_ln, s_m, Hd, C);
     __syncthreads();
     for (int j = threadIdx.x; j < Hd; j += blockDim.x) s_m[j] = fmaxf(s_m[j], 0.f);
     __syncthreads();
     // ---- residual MLP backward: slot_out = h' + W2 relu(W1 LN(h') + b1) + b2 ----
     b_outer_acc(G + R.w2, s_ds, s_m, C, Hd);
     b_vec_acc(G + R.b2, s_ds, C);
-    b_matvec_t(bg ? p.w.to_res_bg_w2 : p.w.to_res_w2, s_ds, s_dm, C, Hd);    // d relu output
+    b_matvec_t(w_2, s_ds, s_dm, C, Hd);                                      // d relu output
     __syncthreads();
     for (int j = threadIdx.x; j < Hd; j += blockDim.x) s_dm[j] = s_m[j] > 0.f ? s_dm[j] : 0.f;
     __syncthreads();
@@ -216,7 +251,7 @@ __global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabPar
     __shared__ float s_hn[kBMaxC];
     for (int c = threadIdx.x; c < C; c += blockDim.x) s_hn[c] = s_g[5 * C + c];
     __syncthreads();
-    b_matvec_t(bg ? p.w.to_res_bg_w1 : p.w.to_res_w1, s_dm, s_dln, Hd, C);   // d LN_res output
+    b_matvec_t(w_1, s_dm, s_dln, Hd, C);                                     // d LN_res output
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       G[R.lnr_w + c] += s_dln[c] * s_xh[c];
@@ -244,8 +279,8 @@ __global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabPar
     b_vec_acc(G + R.bih, s_dg, 3 * C);
     b_outer_acc(G + R.whh, s_dg + 3 * C, s_a, 3 * C, C);
     b_vec_acc(G + R.bhh, s_dg + 3 * C, 3 * C);
-    b_matvec_t(bg ? p.w.gru_bg_w_ih : p.w.gru_w_ih, s_dg, s_xh, 3 * C, C);           // s_xh = d upd
-    b_matvec_t(bg ? p.w.gru_bg_w_hh : p.w.gru_w_hh, s_dg + 3 * C, s_hn, 3 * C, C);   // s_hn = W_hh^T d gh
+    b_matvec_t(w_ih, s_dg, s_xh, 3 * C, C);             // s_xh = d upd
+    b_matvec_t(w_hh, s_dg + 3 * C, s_hn, 3 * C, C);     // s_hn = W_hh^T d gh
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       p.dU[k * C + c] = s_xh[c];
@@ -412,7 +447,12 @@ __global__ void sa_bwd_reduce_kernel(const SabParams p) {
   const int C = p.C, K = p.K, Hd = p.hidden;
   const SlotRegion R = slot_region(C, Hd);
   const int gid = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
-  auto fg_sum = [&](int off) { float a = 0.f; for (int k = 1; k < K; ++k) a += p.slot_reg[(long long)k * R.total + off]; return a; };
+  auto fg_sum = [&](int off) {
+    float a = 0.f;
+#pragma unroll 4
+    for (int k = 1; k < K; ++k) a += p.slot_reg[(long long)k * R.total + off];
+    return a;
+  };
   auto bg_val = [&](int off) { return p.slot_reg[off]; };
   for (int e = gid; e < 3 * C * C; e += gn) { p.g.gru_w_ih[e] = fg_sum(R.wih + e); p.g.gru_w_hh[e] = fg_sum(R.whh + e);
                                                 p.g.gru_bg_w_ih[e] = bg_val(R.wih + e); p.g.gru_bg_w_hh[e] = bg_val(R.whh + e); }
@@ -435,12 +475,15 @@ __global__ void sa_bwd_reduce_kernel(const SabParams p) {
     p.g.slots_mu_bg[e] = p.dS[e];
     p.g.slots_logsigma_bg[e] = p.dS[e] * expf(p.w.slots_logsigma_bg[e]) * p.noise_bg[e];
     float gw = 0.f, gb = 0.f;
+#pragma unroll 8
     for (int b = 0; b < p.nblk; ++b) { const float* part = p.tok_part + (long long)b * (2 * C * C + 2 * C); gw += part[2 * C * C + e]; gb += part[2 * C * C + C + e]; }
     p.g.norm_feat_w[e] = gw; p.g.norm_feat_b[e] = gb;
   }
   for (int e = gid; e < C * C; e += gn) {
     float ak = 0.f, av = 0.f;
-    for (int b = 0; b < p.nblk; ++b) { const float* part = p.tok_part + (long long)b * (2 * C * C + 2 * C); ak += part[e]; av += part[C * C + e]; }
+#pragma unroll 8
+    for (int b = 0; b < p.nblk; ++b) {      // fixed order; the unrolled loads are in flight together
+ const float* part = p.tok_part + (long long)b * (2 * C * C + 2 * C); ak += part[e]; av += part[C * C + e]; }
     p.g.to_k_w[e] = ak; p.g.to_v_w[e] = av;
   }
 }
@@ -478,17 +521,30 @@ int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_s
   p.slot_reg = ws; ws += (size_t)K * R.total;
   p.tok_part = ws;
   p.grad_feat = grad_feat;
+  // weight staging of the per-slot kernel (TMA bulk copies: 16-byte aligned tensors, sizes multiples of 16 bytes)
+  const size_t stage_bytes = (size_t)(C * C + 2 * 3 * C * C + 2 * hidden * C) * sizeof(float);
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const int staged = (C % 4 == 0 && hidden % 4 == 0 && al(w->gru_w_ih) && al(w->gru_w_hh) && al(w->gru_bg_w_ih) && al(w->gru_bg_w_hh) &&
+                      al(w->to_res_w1) && al(w->to_res_w2) && al(w->to_res_bg_w1) && al(w->to_res_bg_w2) && al(w->to_q_w) && al(w->to_q_bg_w)) ? 1 : 0;
+  if (staged) {
+    static bool attr_set = false;      // idempotent; a benign race at worst sets it twice
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(sa_bwd_slot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return UORF_ERR_DEVICE;
+      attr_set = true;
+    }
+  }
+  const size_t dyn = staged ? stage_bytes : 0;
   cudaMemsetAsync(p.dK, 0, sizeof(float) * 2 * (size_t)ntok * C, stream);
   cudaMemsetAsync(p.slot_reg, 0, sizeof(float) * (size_t)K * R.total, stream);
   for (int it = iters - 1; it >= 0; --it) {
     const bool last = it == iters - 1;
     // query path of iteration it+1 (if any) + MLP/GRU of iteration it
-    sa_bwd_slot_kernel<<<K, kBSlotThreads, 0, stream>>>(p, last ? 0 : 1, it + 1, 1, it, last ? 1 : 0);
+    sa_bwd_slot_kernel<<<K, kBSlotThreads, dyn, stream>>>(p, last ? 0 : 1, it + 1, 1, it, last ? 1 : 0, staged);
     sa_bwd_token_kernel<<<nblk, kBThreads, 0, stream>>>(p, it);
   }
-  sa_bwd_slot_kernel<<<K, kBSlotThreads, 0, stream>>>(p, 1, 0, 0, 0, 0);   // query path of iteration 0 -> d slot_0
+  sa_bwd_slot_kernel<<<K, kBSlotThreads, dyn, stream>>>(p, 1, 0, 0, 0, 0, staged);   // query path of iteration 0 -> d slot_0
   sa_bwd_feat_kernel<<<nblk, kBThreads, 0, stream>>>(p);
-  sa_bwd_reduce_kernel<<<32, 256, 0, stream>>>(p);
+  sa_bwd_reduce_kernel<<<148, 256, 0, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
 }
 
