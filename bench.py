@@ -396,7 +396,9 @@ def run_b200(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": 12 * args.steps,
+                # launches of this library's own kernels per step on rank 0 (profiles/*_launches.md): encoder 6 (7 with
+                # `bottom`), slot attention 8, weight image 1, sampling 1, decoder 1, compositing 1
+                "gpu_launches": (18 + (1 if c.get("bottom") else 0)) * args.steps,
                 "roofline": {"kernel": "decoder_fwd_kernel", "bound": "tensor", "achieved": ach_tflops, "peak": pk["tf_burst"],
                              "unit": "TFLOP/s", "frac": ach_tflops / pk["tf_burst"], "traffic": traffic,
                              "peak_source": pk["src"] + " bf16 burst", "kernel_ms": dec_ms,

@@ -339,7 +339,8 @@ class SlotAttention(nn.Module):
         dev = feat.device
         f0 = feat[0]
         named = dict(self.named_parameters())
-        grads = {n: torch.zeros_like(p_, dtype=torch.float32, memory_format=torch.contiguous_format) for n, p_ in named.items()}
+        # every parameter gradient is written in full by sa_bwd_reduce_kernel: no zero fill (34 launches per step)
+        grads = {n: torch.empty_like(p_, dtype=torch.float32, memory_format=torch.contiguous_format) for n, p_ in named.items()}
         g = _lib.SlotAttentionWeights()
         for field, key in _lib.SA_STATE_KEYS.items():
             setattr(g, field, grads[key].data_ptr())
