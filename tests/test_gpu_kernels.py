@@ -726,10 +726,22 @@ def test_encoder_inference_kernels_match_cudnn(Z, S, bottom):
     # oracle restatement of the reference encoder (CPU)
     ref = O.encoder_forward({k: v.detach().cpu() for k, v in enc.state_dict().items()}, x.cpu(), bottom)
     assert maxerr(got, ref) < 2e-5 * max(1.0, ref.abs().max().item())
-    # gradients still flow through the torch layers
-    y = enc(x.requires_grad_(True))
-    y.sum().backward()
-    assert enc.enc_up_1[0].weight.grad is not None
+    # training path: forward by the kernels + per-layer cuDNN backward on the kept activations (_EncoderFn) against autograd
+    # through the torch layers
+    probe = torch.randn_like(want)
+    res = {}
+    for flag in (False, True):
+        enc.use_kernels_in_training = flag
+        enc.zero_grad()
+        xg = x.clone().requires_grad_(True)
+        y = enc(xg)
+        (y * probe).sum().backward()
+        res[flag] = ({n: p_.grad.clone() for n, p_ in enc.named_parameters()}, xg.grad.clone(), y.detach())
+    assert maxerr(res[True][2], res[False][2]) < 2e-5 * max(1.0, want.abs().max().item())
+    for n in res[False][0]:
+        ref_g = res[False][0][n]
+        assert maxerr(res[True][0][n], ref_g) < 2e-4 * max(1e-6, ref_g.abs().max().item()), n
+    assert maxerr(res[True][1], res[False][1]) < 2e-4 * max(1e-6, res[False][1].abs().max().item())
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -70,7 +70,8 @@ class Encoder(nn.Module):
         self.enc_up_1 = nn.Sequential(nn.Conv2d(z_dim * 2, z_dim, 3, stride=1, padding=1), nn.ReLU(True))
         self._planes = {}
         self._wt = {}              # transposed conv weights of the inference path, keyed by weight version
-        self.use_kernels = True    # False: always the torch / cuDNN layers (what the training path uses)
+        self.use_kernels = True    # False: always the torch / cuDNN layers
+        self.use_kernels_in_training = True   # forward by the kernels under autograd too; backward = cuDNN per layer (_EncoderFn)
 
     def _pixel_planes(self, H, W, device):
         key = (H, W, str(device))
@@ -98,10 +99,12 @@ class Encoder(nn.Module):
                                          _stream(src_a)), "uorf_encoder_conv3x3")
         return out
 
-    def _forward_inference(self, x):
+    def _forward_inference(self, x, keep=None):
+        """`keep`: dict that receives every layer's input / output activations (the training path's backward needs them)"""
         H, W = x.shape[2], x.shape[3]
         img = _f32c(x[0])
         planes = self._pixel_planes(H, W, x.device)[0]
+        d0 = None
         if self.bottom:
             d0 = self._conv(self.enc_down_0, img, False, planes, H, W)
             d1 = self._conv(self.enc_down_1, d0, False, None, H, W)
@@ -113,14 +116,24 @@ class Encoder(nn.Module):
         d3 = self._conv(self.enc_down_3, d2, False, None, h2, w2)
         u3 = self._conv(self.enc_up_3, d3, False, None, d3.shape[1], d3.shape[2])      # kept at low resolution
         u2 = self._conv(self.enc_up_2, u3, True, d2, h2, w2)                           # cat[upsample(u3), d2]
-        return self._conv(self.enc_up_1, u2, True, d1, h1, w1)[None]                  # cat[upsample(u2), d1]
+        out = self._conv(self.enc_up_1, u2, True, d1, h1, w1)                          # cat[upsample(u2), d1]
+        if keep is not None:
+            keep.update(img=img, planes=planes, d0=d0, d1=d1, d2=d2, d3=d3, u3=u3, u2=u2, out=out)
+        return out[None]
+
+    def _kernels_apply(self, x):
+        H, W = x.shape[2], x.shape[3]
+        return (x.is_cuda and x.shape[0] == 1 and x.dtype == torch.float32 and self.use_kernels
+                and H % (8 if self.bottom else 4) == 0 and W % (8 if self.bottom else 4) == 0)
 
     def forward(self, x):
         W, H = x.shape[3], x.shape[2]
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p_.requires_grad for p_ in self.parameters()))
-        if (not needs_grad and x.is_cuda and x.shape[0] == 1 and x.dtype == torch.float32 and self.use_kernels
-                and H % (8 if self.bottom else 4) == 0 and W % (8 if self.bottom else 4) == 0):
-            return self._forward_inference(x)
+        if self._kernels_apply(x):
+            if not needs_grad:
+                return self._forward_inference(x)
+            if self.use_kernels_in_training:
+                return _EncoderFn.apply(self, x, *self.parameters())
         x_ = torch.cat([x, self._pixel_planes(H, W, x.device).expand(x.shape[0], -1, -1, -1)], dim=1)
         if self.bottom:
             x_down_1 = self.enc_down_1(self.enc_down_0(x_))
@@ -131,6 +144,65 @@ class Encoder(nn.Module):
         x_up_3 = self.enc_up_3(x_down_3)
         x_up_2 = self.enc_up_2(torch.cat([x_up_3, x_down_2], dim=1))
         return self.enc_up_1(torch.cat([x_up_2, x_down_1], dim=1))
+
+
+class _EncoderFn(torch.autograd.Function):
+    """Training path of the Encoder (batch 1): the forward is the direct-convolution kernels (every activation kept); the backward
+    walks the U-Net in reverse with cuDNN's convolution_backward on the kept activations (the same op autograd would run), the
+    ReLU gates taken from the kept outputs, `torch.cat` / the bilinear upsamples re-materialised only here."""
+
+    @staticmethod
+    def forward(ctx, enc, x, *params):
+        keep = {}
+        with torch.no_grad():
+            out = enc._forward_inference(x, keep)
+        ctx.enc = enc
+        ctx.x_needs_grad = x.requires_grad
+        ctx.names = [n for n in ("img", "planes", "d0", "d1", "d2", "d3", "u3", "u2", "out") if keep[n] is not None]
+        ctx.save_for_backward(*[keep[n] for n in ctx.names])
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        gx, grads = _encoder_backward(ctx.enc, dict(zip(ctx.names, ctx.saved_tensors)), g_out, ctx.x_needs_grad)
+        return (None, gx) + tuple(grads[n] for n, _ in ctx.enc.named_parameters())
+
+
+def _encoder_backward(enc, a, g_out, x_needs_grad):
+    """Backward of Encoder.forward (batch 1) from the kept activations `a` (CxHxW each: img, planes, [d0], d1, d2, d3, u3 and u2
+    at low resolution, out): -> (grad of the image or None, {parameter name: gradient}).  Plain torch ops, device-agnostic."""
+    grads = {}
+
+    def up(t):        # nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False), model.py:27-32
+        return F.interpolate(t[None], scale_factor=2, mode="bilinear", align_corners=False)
+
+    def up_bwd(g, low):
+        return torch.ops.aten.upsample_bilinear2d_backward(g, [g.shape[2], g.shape[3]], [1, low.shape[0], low.shape[1], low.shape[2]],
+                                                           False, 2.0, 2.0)
+
+    def conv_bwd(name, g, out, inp, need_input=True):
+        conv = getattr(enc, name)[0]
+        g = g * (out[None] > 0)                                   # ReLU gate from the kept output
+        gi, gw, gb = torch.ops.aten.convolution_backward(g, inp, conv.weight, [conv.out_channels], list(conv.stride), list(conv.padding),
+                                                         list(conv.dilation), False, [0, 0], 1, [need_input, True, True])
+        grads[name + ".0.weight"], grads[name + ".0.bias"] = gw, gb
+        return gi
+
+    z = a["out"].shape[0]
+    gi = conv_bwd("enc_up_1", g_out, a["out"], torch.cat([up(a["u2"]), a["d1"][None]], dim=1))
+    g_d1 = gi[:, z:]
+    gi = conv_bwd("enc_up_2", up_bwd(gi[:, :z].contiguous(), a["u2"]), a["u2"], torch.cat([up(a["u3"]), a["d2"][None]], dim=1))
+    g_d2 = gi[:, z:]
+    g_d3 = conv_bwd("enc_up_3", up_bwd(gi[:, :z].contiguous(), a["u3"]), a["u3"], a["d3"][None])
+    g_d2 = g_d2 + conv_bwd("enc_down_3", g_d3, a["d3"], a["d2"][None])
+    g_d1 = g_d1 + conv_bwd("enc_down_2", g_d2, a["d2"], a["d1"][None])
+    x_in = torch.cat([a["img"], a["planes"]], dim=0)[None]
+    if enc.bottom:
+        g_d0 = conv_bwd("enc_down_1", g_d1, a["d1"], a["d0"][None])
+        gx = conv_bwd("enc_down_0", g_d0, a["d0"], x_in, x_needs_grad)
+    else:
+        gx = conv_bwd("enc_down_1", g_d1, a["d1"], x_in, x_needs_grad)
+    return (gx[:, :a["img"].shape[0]] if x_needs_grad else None), grads
 
 
 # ======================================================================================================
