@@ -343,13 +343,8 @@ int launch_slot_attention(const uorf_slot_attention_weights* w, const float* fea
                       al(w->to_res_w1) && al(w->to_res_w2) && al(w->to_res_bg_w1) && al(w->to_res_bg_w2) && al(w->to_q_w) && al(w->to_q_bg_w) &&
                       al(w->gru_b_ih) && al(w->gru_b_hh) && al(w->gru_bg_b_ih) && al(w->gru_bg_b_hh) && al(w->to_res_b1) && al(w->to_res_b2) &&
                       al(w->to_res_bg_b1) && al(w->to_res_bg_b2)) ? 1 : 0;
-  if (staged) {
-    static bool attr_set = false;      // idempotent; a benign race at worst sets it twice
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(sa_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return UORF_ERR_DEVICE;
-      attr_set = true;
-    }
-  }
+  // set on every launch, like the decoder kernels: function attributes are per device, a process may drive several
+  if (staged && cudaFuncSetAttribute(sa_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return UORF_ERR_DEVICE;
   sa_kv_kernel<<<nblk, kSaThreads, 0, stream>>>(p);
   sa_init_kernel<<<K, kSaSlotThreads, 0, stream>>>(p);
   for (int it = 0; it < iters; ++it) {

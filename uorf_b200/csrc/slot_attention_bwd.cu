@@ -526,13 +526,8 @@ int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_s
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const int staged = (C % 4 == 0 && hidden % 4 == 0 && al(w->gru_w_ih) && al(w->gru_w_hh) && al(w->gru_bg_w_ih) && al(w->gru_bg_w_hh) &&
                       al(w->to_res_w1) && al(w->to_res_w2) && al(w->to_res_bg_w1) && al(w->to_res_bg_w2) && al(w->to_q_w) && al(w->to_q_bg_w)) ? 1 : 0;
-  if (staged) {
-    static bool attr_set = false;      // idempotent; a benign race at worst sets it twice
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(sa_bwd_slot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return UORF_ERR_DEVICE;
-      attr_set = true;
-    }
-  }
+  // set on every launch, like the decoder kernels: function attributes are per device, a process may drive several
+  if (staged && cudaFuncSetAttribute(sa_bwd_slot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return UORF_ERR_DEVICE;
   const size_t dyn = staged ? stage_bytes : 0;
   cudaMemsetAsync(p.dK, 0, sizeof(float) * 2 * (size_t)ntok * C, stream);
   cudaMemsetAsync(p.slot_reg, 0, sizeof(float) * (size_t)K * R.total, stream);
