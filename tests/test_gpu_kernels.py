@@ -610,6 +610,15 @@ def test_train_step_cuda_graph_matches_eager():
         # (8 steps, lr <= 3e-4) for the worst element and require the bulk to agree closely
         d = (pe - pg).abs()
         assert d.max().item() < 1e-3 and d.mean().item() < 1e-5, (n, d.max().item(), d.mean().item())
+    # graph replays move the weights without bumping their version counters: an eager inference call afterwards must see the
+    # current weights (the encoder's cached transposed copies are dropped after every replay)
+    xq = torch.rand(1, 3, 32, 32, device=dev()) * 2 - 1
+    with torch.no_grad():
+        y_kernels = mg.netEncoder(xq)
+        mg.netEncoder.use_kernels = False
+        y_layers = mg.netEncoder(xq)
+        mg.netEncoder.use_kernels = True
+    assert maxerr(y_kernels, y_layers) < 2e-5 * max(1.0, y_layers.abs().max().item())
     with pytest.raises(RuntimeError):           # needs the capturable optimizer
         uorfNoGanModel(default_train_options(num_slots=3, z_dim=40, gpu_ids=[0]), with_perceptual=False).enable_cuda_graph()
 

@@ -96,7 +96,13 @@ class uorfEvalModel:
             getattr(self, "net" + n).eval()
         return self
 
+    def _weights_changed(self):
+        """captured graphs bake the encoder's transposed weight copies (made once per weight version): re-capture on next use"""
+        self._graph = None
+        self._render_static = None
+
     def load_networks_from_state_dicts(self, enc=None, sa=None, dec=None):
+        self._weights_changed()
         if enc is not None:
             self.netEncoder.load_state_dict(enc)
         if sa is not None:
@@ -107,6 +113,7 @@ class uorfEvalModel:
     def load_networks(self, save_dir: str, suffix: str = "latest"):
         """reference base_model.py:177-201: `{suffix}_net_{Name}.pth` state dicts (strict=False)."""
         import os
+        self._weights_changed()
         for name in self.model_names:
             path = os.path.join(save_dir, f"{suffix}_net_{name}.pth")
             sd = torch.load(path, map_location=str(self.device))

@@ -90,7 +90,10 @@ class Encoder(nn.Module):
         cache = self._wt.get(id(conv))
         if cache is None or cache[0] != key:       # [out][in][3][3] -> [in][3][3][out], once per weight version
             cache = (key, conv.weight.detach().permute(1, 2, 3, 0).contiguous().float())
-            self._wt[id(conv)] = cache
+            # a copy made while a CUDA graph is being captured lives in the graph's pool and is rewritten by every replay: it is
+            # never cached.  (Replays that update the weights do not bump `_version`: the training driver clears `_wt` after them.)
+            if not torch.cuda.is_current_stream_capturing():
+                self._wt[id(conv)] = cache
         stride = conv.stride[0]
         ca, cb = src_a.shape[0], (0 if src_b is None else src_b.shape[0])
         out = torch.empty(conv.out_channels, (h_in - 1) // stride + 1, (w_in - 1) // stride + 1, device=src_a.device, dtype=torch.float32)

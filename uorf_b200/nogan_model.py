@@ -272,6 +272,7 @@ class uorfNoGanModel:
                 self._step_eager(False, epoch)
             self._graph = g
         self._graph.replay()
+        self.netEncoder._wt.clear()      # the replay moved the weights without bumping their version counters
         return [], []
 
     def optimize_parameters(self, ret_grad=False, epoch=0):
