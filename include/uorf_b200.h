@@ -52,7 +52,7 @@ int uorf_init(int device);
  * chunks (chunk j <-> (h0,w0) = divmod(j, scale), Hc = H/scale, Wc = W/scale).
  * With crop_h/crop_w >= 0 (scale must be 1) only the window [crop_h, crop_h+Hc) x [crop_w, crop_w+Wc)
  * is produced (fine-stage training crop, models/uorf_nogan_model.py:153-165); pass Hc = Wc = render size.
- * Numerics: z_vals, ray_dir and every index layout are bit-identical to the reference; coords are evaluated as
+ * Numerics: z_vals and every index layout are bit-identical to the reference (ray_dir <= 1e-6); coords are evaluated as
  * origin + z * direction per ray (one FMA per coordinate) and agree with the reference's fp32 matmul chain to
  * rounding (<= 2e-6 abs on the NSS range; all layouts / kernels of this entry point agree bit for bit with each other).
  * ------------------------------------------------------------------------------------------- */
