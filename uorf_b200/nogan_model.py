@@ -106,8 +106,13 @@ class uorfNoGanModel:
         self._graph_enabled, self._graph, self._graph_key, self._graph_warm, self._static = False, None, None, 0, None
         if self.isTrain:
             lr = torch.tensor(float(opt.lr), device=self.device) if self._capturable else opt.lr
+            # torch's fused multi-tensor Adam (same update rule; one kernel per chunk of tensors instead of ~14 foreach launches
+            # per step: 9.24 -> 8.94 ms).  opt.fused_adam=False / UORF_FUSED_ADAM=0 selects torch's default (foreach) - passed as
+            # fused=None, never as an explicit False, which would select the slow single-tensor loop.
+            fused = bool(getattr(opt, "fused_adam", os.environ.get("UORF_FUSED_ADAM", "1") == "1"))
             self.optimizer = optim.Adam(chain(self.netEncoder.parameters(), self.netSlotAttention.parameters(),
-                                              self.netDecoder.parameters()), lr=lr, capturable=self._capturable)
+                                              self.netDecoder.parameters()), lr=lr, capturable=self._capturable,
+                                        fused=True if fused else None)
             self.optimizers = [self.optimizer]
             self.schedulers = [exp_decay_schedule_with_warmup(self.optimizer, opt.warmup_steps, opt.attn_decay_steps)]
         self.L2_loss = nn.MSELoss()
