@@ -1,31 +1,40 @@
 #!/usr/bin/env python
-"""bench.py - headline benchmark of the uORF per-scene render hot path on B200.
+"""bench.py - the uORF per-scene render hot path on B200: BASELINE.json's whole metric in one JSON line.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision fp16x3|bf16x3|bf16|fp16]
-                    [--mode render|train] [--workload clevr567|room_diverse_fine] [--no-graph] [--no-cpu-baseline]
+                    [--mode all|render|train|strong] [--workload clevr567|room_diverse_fine] [--no-graph] [--no-cpu-baseline]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...       (N > 1, one rank per GPU)
 
-Metric (BASELINE.json): composited ray-samples/s x K slots = P_total * K / t, where one STEP is one scene rendered
-through Encoder -> SlotAttention -> Projection -> Decoder -> raw2outputs (the eval driver's forward,
-reference models/uorf_eval_model.py:116-157) with per-slot masked/unmasked raws materialised as the reference does.
-Workload (BASELINE.json configs[1]): Room-Chair novel-view render, K=5 slots, z_dim 64, 128x128 frustum x 64 samples,
-4 views per scene, synthetic images/cameras, random-init weights (seed 2021).
-N > 1 GPUs: rays shard by view - every rank renders 4 views of a 4N-view scene, rank 0 encodes and broadcasts the
-slot latents over NCCL (weak scaling, no collective inside the per-point work).
+BASELINE.json's metric is "composited ray-samples/s x K slots AND train steps/s at 1/2/4/8 B200".  The headline fields of the
+line are the render half on the configuration the metric is quoted on; the sub-records carry the rest, all from this one run:
 
-The step is replayed as ONE CUDA graph per rank (N > 1: [rank 0: encoder + slot attention] -> NCCL broadcast -> render, the
-collective captured in the graph); `--no-graph` launches eagerly.  `--mode train` measures BASELINE configs[2] (CLEVR-567
-coarse-stage training step, K=8, scene-sharded data parallel, whole step incl. the gradient all-reduce as one graph).
-The JSON line carries `roofline` (dominant kernel: CUDA-event time over eagerly launched steps, algorithmic flops counted
-once), `cpu_baseline` (oracle on the host cores + the as-written algorithm as torch eager ops on the same GPU), `e2e`
-(host buffers, H2D + D2H inside the timed region), `clocks` (NVML samples under load) and `gpu_launches`.
-`UORF_PROFILE_RANGE=1` brackets the timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off).
+  headline      configs[1]  Room-Chair novel-view render, K=5, z_dim 64, 128x128 frustum x 64 samples, 4 views per rank
+                (weak scaling: rays shard by view, rank 0 encodes and broadcasts the slot latents, the rendered tiles are
+                all-gathered inside the timed step when N > 1).  One STEP = one scene through Encoder -> SlotAttention ->
+                Projection -> Decoder -> raw2outputs (reference models/uorf_eval_model.py:116-157), per-slot masked /
+                unmasked raws materialised as the reference does.  value = P_total * K / t.
+  "train"       configs[2]  CLEVR-567 coarse-stage training step (K=8, 64^3 frustum, 4 views): forward + backward + Adam
+                (reference models/uorf_nogan_model.py:229-245), one scene per rank, ONE flat gradient all-reduce (NCCL) when
+                N > 1; scene-steps/s summed over ranks.
+  "train_fine"  configs[3]  Room-Diverse fine stage (K=5, --bottom, 128 frustum, 64x64 crop drawn on the device).
+  "strong"      configs[4]  scene-manipulation render, ONE view of 256x256 rays x 128 samples, K in {5, 8, 16}: image rows
+                sharded over the N ranks, slot latents broadcast, tiles all-gathered inside the timed step (reference
+                models/uorf_manip_model.py:196-232).  Total work is fixed: ms per scene should fall ~1/N (strong scaling).
 
-`--impl reference` times the CPU restatement of the reference algorithm (oracle/, the reference itself cannot travel
-to the GPU box) on the host cores, on a bounded sample of the same workload.
+Every step is replayed as ONE CUDA graph per rank (NCCL collectives captured inside); `--no-graph` launches eagerly.
+The line carries `roofline` (dominant kernel: CUDA-event time over eagerly launched steps, algorithmic flops counted once),
+`cpu_baseline` (the unmodified reference, oracle/_ref, on the host cores and - `eager_gpu` - on the same GPU), `e2e` (host
+buffers, H2D + D2H inside the timed region), `clocks` (NVML samples under load) and `gpu_launches` (counted by the library:
+uorf_launch_count).  `UORF_PROFILE_RANGE=1` brackets the headline's timed steps with cudaProfilerStart/Stop.
+
+`--impl reference` times the reference's own CPU implementation of the headline step - the unmodified reference's
+uorfEvalModel.forward from oracle/_ref (scripts/install_ref.sh), or the oracle port when that copy is missing - on the host
+cores, all 4 views per step, a bounded number of steps.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -39,18 +48,20 @@ import torch  # noqa: E402
 
 CFG = dict(workload="room_chair_eval_K5_F128_D64_N4", K=5, z_dim=64, n_views=4, frustum=128, n_samp=64, render_size=64,
            input_size=64, load_size=128)
-# the other shapes BASELINE.json names (parity-test cases; `--workload` runs them through the same arms for the record)
+# the other render shape BASELINE.json names (`--workload clevr567` runs it through the same arms for the record)
 WORKLOADS = {
     "clevr567": dict(workload="clevr567_eval_K8_F64_D64_N4", K=8, z_dim=64, n_views=4, frustum=64, n_samp=64, render_size=64,
                      input_size=64, load_size=128),
 }
-TRAIN_WORKLOADS = {
-    "room_diverse_fine": dict(workload="room_diverse_train_fine_K5_F128crop64_D64_N4", K=5, z_dim=64, n_views=4, frustum=64, n_samp=64,
-                              supervision_size=64, input_size=128, load_size=128, stage="fine", bottom=True, frustum_fine=128),
-}
+TRAIN_CFG = dict(workload="clevr567_train_coarse_K8_F64_D64_N4", K=8, z_dim=64, n_views=4, frustum=64, n_samp=64,
+                 supervision_size=64, input_size=64, load_size=128)
+TRAIN_FINE_CFG = dict(workload="room_diverse_train_fine_K5_F128crop64_D64_N4", K=5, z_dim=64, n_views=4, frustum=64, n_samp=64,
+                      supervision_size=64, input_size=128, load_size=128, stage="fine", bottom=True, frustum_fine=128)
+STRONG_CFG = dict(frustum=256, n_samp=128, z_dim=64, n_views=1, input_size=64, load_size=128, slots=(5, 8, 16))
 METRIC = "composited_ray_samples_x_slots_per_sec"
 UNIT = "sample-slots/s"
 HBM_FALLBACK_GBS, BF16_FALLBACK_TFLOPS = 6650.0, 1590.0
+L2_NOTE = "no flush: each step streams ~0.8 GB of outputs per GPU (>> 126 MB L2)"
 
 
 def f_min_per_point(K: int, Z: int) -> float:
@@ -70,8 +81,13 @@ def peaks():
     return dict(hbm=HBM_FALLBACK_GBS, tf_burst=BF16_FALLBACK_TFLOPS, tf_sust=1400.0, src="fallback")
 
 
+def headline_config():
+    """`config` of the JSON line - identical for the b200 and the reference arm (the driver compares them)"""
+    return dict(CFG, l2=L2_NOTE, weights="random init, seed 2021")
+
+
 # ----------------------------------------------------------------------------------------------------
-# clocks sampler (NVML), runs during the timed region
+# clocks sampler (NVML), runs during the timed regions
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
@@ -149,121 +165,214 @@ def synthetic_scene(n_views, load_size, seed=2021):
 
 
 # ----------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU algorithm (oracle port) on the host cores
+# reference legs (the only places that execute oracle/): the unmodified reference from oracle/_ref, else the oracle port
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int, views_sample: int = 1):
-    """Times oracle.eval_render (the CPU restatement of uorf_eval_model.forward) on `views_sample` of the 4 views."""
-    from oracle import uorf_oracle as O
+def _ref_eval_model(device_ids):
+    """the reference's uorfEvalModel (models/uorf_eval_model.py) built by its own factory on the headline configuration"""
+    from oracle import ref_harness as R
+    c = CFG
+    torch.manual_seed(2021)
+    model, _ = R.create_model("uorf_eval", False, num_slots=c["K"], z_dim=c["z_dim"], n_samp=c["n_samp"], frustum_size=c["frustum"],
+                              render_size=c["render_size"], input_size=c["input_size"], n_img_each_scene=c["n_views"],
+                              gpu_ids=list(device_ids))
+    return model
+
+
+def cpu_reference_run(steps: int, warmup: int):
+    """-> (value, seconds per step, cores, kind, sample).  kind 'reference': uorfEvalModel.forward of the unmodified reference
+    (oracle/_ref), all views; kind 'port': oracle.eval_render when that copy is not installed."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     c = CFG
     img, c2w, azi = synthetic_scene(c["n_views"], c["load_size"])
-    spec = O.FrustumSpec([c["frustum"], c["frustum"], c["n_samp"]], near=6.0, far=20.0, nss_scale=7.0, render_size=c["render_size"])
-    enc_p, sa_p, dec_p = O.init_encoder_params(c["z_dim"]), O.init_slot_attention_params(c["z_dim"]), O.init_decoder_params(c["z_dim"])
-    g = torch.Generator().manual_seed(7)
-    nfg, nbg = torch.randn(1, c["K"] - 1, c["z_dim"], generator=g), torch.randn(1, 1, c["z_dim"], generator=g)
+    units = c["n_views"] * c["frustum"] ** 2 * c["n_samp"] * c["K"]
+    from oracle import ref_harness as R
+    if R.available():
+        model = _ref_eval_model([])
+        model.set_input({"img_data": img, "cam2world": c2w, "azi_rot": azi, "paths": []})
 
-    def one():
-        return O.eval_render(enc_p, sa_p, dec_p, img[:views_sample], c2w[:views_sample], azi[:views_sample], spec,
-                             num_slots=c["K"], input_size=c["input_size"], noise_fg=nfg, noise_bg=nbg)
+        def one():
+            with torch.no_grad():
+                model.forward()
+        kind = "reference"
+        what = "unmodified reference uorfEvalModel.forward (oracle/_ref, models/uorf_eval_model.py:116-157)"
+    else:
+        from oracle import uorf_oracle as O
+        spec = O.FrustumSpec([c["frustum"], c["frustum"], c["n_samp"]], near=6.0, far=20.0, nss_scale=7.0, render_size=c["render_size"])
+        enc_p, sa_p, dec_p = O.init_encoder_params(c["z_dim"]), O.init_slot_attention_params(c["z_dim"]), O.init_decoder_params(c["z_dim"])
+        g = torch.Generator().manual_seed(7)
+        nfg, nbg = torch.randn(1, c["K"] - 1, c["z_dim"], generator=g), torch.randn(1, 1, c["z_dim"], generator=g)
+
+        def one():
+            return O.eval_render(enc_p, sa_p, dec_p, img, c2w, azi, spec, num_slots=c["K"], input_size=c["input_size"],
+                                 noise_fg=nfg, noise_bg=nbg)
+        kind = "port"
+        what = "oracle eval_render (oracle/_ref not installed)"
     for _ in range(warmup):
         one()
     t0 = time.perf_counter()
     for _ in range(steps):
         one()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    units = views_sample * c["frustum"] ** 2 * c["n_samp"] * c["K"]
-    return units / dt, dt, cores, f"{views_sample} of {c['n_views']} views per step ({units} sample-slots), oracle eval_render, {cores} threads"
+    return units / dt, dt, cores, kind, f"all {c['n_views']} views per step ({units} sample-slots), {what}, {cores} threads, {steps} step(s)"
 
 
-def eager_gpu_run(dev, reps: int = 3):
-    """The as-written algorithm (oracle decoder_forward + the permute copy + composite: ~93 % of the reference's render path,
-    SURVEY 8(a)) executed as stock torch eager ops on the GPU, TF32 off like the reference: what running the reference's own
-    modules on this B200 would cost for one of the 4 chunks of the bench workload.  A baseline leg like cpu_baseline."""
-    from oracle import uorf_oracle as O
+def eager_gpu_reference(dev, reps: int = 3):
+    """The real bar: the reference's OWN eval driver, unmodified, as stock torch eager ops on this GPU (TF32 off as the
+    reference's set_seed does) - the whole step Encoder -> ... -> raw2outputs, all views.  A baseline leg like cpu_baseline."""
+    from oracle import ref_harness as R
+    if not R.available():
+        return {"unavailable": "oracle/_ref not installed (scripts/install_ref.sh)"}
     c = CFG
-    K, Z, N, D, rs = c["K"], c["z_dim"], c["n_views"], c["n_samp"], c["render_size"]
-    _, c2w, azi = synthetic_scene(N, c["load_size"])
-    spec = O.FrustumSpec([c["frustum"], c["frustum"], D], near=6.0, far=20.0, nss_scale=7.0, render_size=rs)
-    coords, zv, rd = O.sampling_coords(spec, c2w, partitioned=True)
-    coor, zv0, rd0 = coords[0].to(dev), zv[0].to(dev), rd[0].to(dev)
-    dec_p = {k: v.to(dev) for k, v in O.init_decoder_params(Z).items()}
-    g = torch.Generator().manual_seed(11)
-    slots = torch.randn(K, Z, generator=g).to(dev)
-    T = azi[0:1].inverse().to(dev)
-    noise = torch.zeros(K, coor.shape[0], 1, device=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = _ref_eval_model([dev.index])
+    img, c2w, azi = synthetic_scene(c["n_views"], c["load_size"])
+    model.set_input({"img_data": img, "cam2world": c2w, "azi_rot": azi, "paths": []})
+    with torch.no_grad():
+        model.forward()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            model.forward()
+        e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    units = c["n_views"] * c["frustum"] ** 2 * c["n_samp"] * c["K"]
+    del model
+    gc.collect()
+    torch.cuda.empty_cache()
+    return {"value": units / (ms * 1e-3), "unit": UNIT, "ms": ms,
+            "sample": f"all {c['n_views']} views ({units} sample-slots): unmodified reference uorfEvalModel.forward (oracle/_ref) as torch "
+                      "eager fp32 (TF32 off) on cuda, whole step"}
 
-    def one():
-        with torch.no_grad():
-            raws, masked, unmasked, _ = O.decoder_forward(dec_p, coor, coor[None].expand(K - 1, -1, -1), slots, T, locality=False,
-                                                          locality_ratio=4.5 / 7.0, noise=noise)
-            raws = raws.view(N, D, rs, rs, 4).permute(0, 2, 3, 1, 4).flatten(0, 2)
-            return O.composite(raws, zv0, rd0)
-    one()
+
+def eager_gpu_reference_train(dev, c, reps: int = 3):
+    """the reference's own training step (uorfNoGanModel.optimize_parameters, unmodified, torch eager + autograd) on this GPU"""
+    from oracle import ref_harness as R
+    if not R.available():
+        return {"unavailable": "oracle/_ref not installed (scripts/install_ref.sh)"}
+    torch.manual_seed(2021)
+    model, opt = R.create_model("uorf_nogan", True, num_slots=c["K"], z_dim=c["z_dim"], n_samp=c["n_samp"], frustum_size=c["frustum"],
+                                frustum_size_fine=c.get("frustum_fine", 128), render_size=c["supervision_size"],
+                                supervision_size=c["supervision_size"], input_size=c["input_size"], n_img_each_scene=c["n_views"],
+                                stage=c.get("stage", "coarse"), bottom=c.get("bottom", False), gpu_ids=[dev.index], warmup_steps=10)
+    img, c2w, azi = synthetic_scene(c["n_views"], c["load_size"])
+    model.set_input({"img_data": img, "cam2world": c2w, "azi_rot": azi, "paths": []})
+    model.optimize_parameters(epoch=opt.percept_in)
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        one()
+        model.optimize_parameters(epoch=opt.percept_in)
+        model.update_learning_rate()
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / reps
-    units = coor.shape[0] * K
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    del model
+    gc.collect()
     torch.cuda.empty_cache()
-    return {"value": units / (ms * 1e-3), "unit": UNIT, "ms": ms,
-            "sample": f"1 of {(c['frustum'] // rs) ** 2} chunks ({units} sample-slots): oracle decoder_forward + permute + composite as torch "
-                      "eager fp32 (TF32 off) on cuda, encoder/slot attention/sampling excluded"}
+    return {"value": 1e3 / ms, "unit": "scene-steps/s", "ms": ms, "peak_mem_gib": round(peak_gb, 1),
+            "sample": "unmodified reference uorfNoGanModel.optimize_parameters (oracle/_ref) as torch eager + autograd on cuda, same shapes"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 2))            # one step is the whole 4-view scene: ~10-20 s on the host cores
     warm = 1 if args.warmup > 0 else 0
-    value, dt, cores, sample = cpu_reference_run(steps, warm)
+    value, dt, cores, kind, sample = cpu_reference_run(steps, warm)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "impl": "reference", "config": dict(CFG, note="CPU reference arm; bounded sample, steps capped at 3"),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "data": "synthetic", "impl": "reference", "config": headline_config(),
+            "detail": {"note": "CPU reference arm: whole scene per step, steps capped at 2 and warm-up at 1 to bound the run"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def _shutdown(dist):
-    """End of a multi-rank run.  The NCCL collectives of the step live inside CUDA graphs, and destroy_process_group() can block
-    on a communicator that graphs still reference; everything has been printed and synchronised, so leave without teardown."""
+# ----------------------------------------------------------------------------------------------------
+# process context
+# ----------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device(f"cuda:{self.local_rank}")
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.graph_owners = []       # objects holding CUDA graphs with captured NCCL work: released before the group is destroyed
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """K steps bracketed by barrier + synchronize on both sides, device-timed, MAX over ranks -> total ms"""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return ms.item()
+
+    def shutdown(self):
+        """Ordered teardown: the step graphs hold captured NCCL kernels, so they are destroyed FIRST (their owners release them),
+        then the communicator.  A watchdog ends the process if NCCL teardown still blocks: every line has been printed by then."""
+        if self.world == 1:
+            return
+        torch.cuda.synchronize()
+        self.dist.barrier()
+        for o in self.graph_owners:
+            o.release()
+        self.graph_owners = []
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        t = threading.Timer(20.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        self.dist.destroy_process_group()
+        t.cancel()
+
+
+def keep_busy(step, ms_per_step):
+    """~0.5 s more of the same steps so the clock sampler has readings under load (not part of any reported number); the count
+    derives from an all-reduced time, so every rank runs the same number (the steps contain collectives)"""
+    for _ in range(int(min(300, 500.0 / max(ms_per_step, 1e-3))) + 1):
+        step()
     torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
-    sys.stdout.flush()
-    sys.stderr.flush()
-    os._exit(0)
 
 
 # ----------------------------------------------------------------------------------------------------
-# B200 arm
+# headline: eval render (BASELINE.json configs[1])
 # ----------------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch.distributed as dist
+def bench_render(ctx, args):
+    from uorf_b200 import _lib, sharded
     from uorf_b200.eval_model import uorfEvalModel, default_eval_options
-    from uorf_b200 import sharded
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device(f"cuda:{local_rank}")
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     c = CFG
     torch.manual_seed(2021)
     opt = default_eval_options(num_slots=c["K"], z_dim=c["z_dim"], n_samp=c["n_samp"], frustum_size=c["frustum"],
                                render_size=c["render_size"], input_size=c["input_size"], n_img_each_scene=c["n_views"],
-                               gpu_ids=[local_rank])
+                               gpu_ids=[ctx.local_rank])
     model = uorfEvalModel(opt, layout="native", precision=args.precision).eval()
     use_graph = world == 1 and not args.no_graph
     n_total = c["n_views"] * world
@@ -276,10 +385,11 @@ def run_b200(args):
     resident = {k: v.to(dev) for k, v in host.items()}
     K, Z = c["K"], c["z_dim"]
     out_host = torch.empty(hi - lo, 3, c["frustum"], c["frustum"]).pin_memory()
-
     graph_on = [True]
-
-    graphed_sharded = sharded.GraphedShardedRender(model, K, Z) if world > 1 else None
+    graphed_sharded = None
+    if world > 1:
+        graphed_sharded = sharded.GraphedShardedRender(model, K, Z, gather=True)
+        ctx.graph_owners.append(graphed_sharded)
 
     def step(inputs):
         model.set_input(inputs)
@@ -287,31 +397,13 @@ def run_b200(args):
             model.forward()
             return model.x_recon
         with torch.no_grad():
-            if not (args.no_graph or not graph_on[0]):      # encode + broadcast + render replayed as one graph per rank
+            if not (args.no_graph or not graph_on[0]):      # encode + broadcast + render + all-gather replayed as one graph per rank
                 return graphed_sharded()["rendered"] * 2 - 1
             z = model.encode()[0] if rank == 0 else None
             z = sharded.broadcast_slots(z, K, Z, dev)
             return model.render(z, model.cam2world, model.nss2cam0)["rendered"] * 2 - 1
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(ctx.local_rank)
     # ---- kernel arm: inputs resident in HBM ----
     step(resident)
     if use_graph:
@@ -322,31 +414,30 @@ def run_b200(args):
     prof_range = bool(os.environ.get("UORF_PROFILE_RANGE"))    # ncu --profile-from-start off: list exactly the timed launches
     if prof_range:
         torch.cuda.profiler.start()
-    ms_total = timed(lambda: step(resident), args.steps)
+    ms_total = ctx.timed(lambda: step(resident), args.steps)
     if prof_range:
         torch.cuda.profiler.stop()
     # duration of the dominant kernel: CUDA events around the decoder launch, over the same steps launched eagerly
-    # (events cannot be recorded inside a replayed graph); same stream, same inputs, same launch configuration
+    # (events cannot be recorded inside a replayed graph); same stream, same inputs, same launch configuration.
+    # The library's launch counter over these eager steps is the number of its kernels one step runs.
     if use_graph:
         model.enable_cuda_graph(False)
     graph_on[0] = False
     model.netDecoder.events = []
+    n0 = _lib.launch_count()
     for _ in range(args.steps):
         step(resident)
     torch.cuda.synchronize()
+    launches_per_step = (_lib.launch_count() - n0) / args.steps
     ev = model.netDecoder.events
     model.netDecoder.events = None
     graph_on[0] = True
     dec_ms = sum(a.elapsed_time(b) for a, b in ev) / max(len(ev), 1)
-    # keep the device busy for ~1 s so the sampler has readings under load (not part of any reported number); the number of
-    # extra steps derives from the all-reduced time, so every rank runs the same count (the steps contain collectives)
-    for _ in range(int(min(400, 1000.0 / max(ms_total / args.steps, 1e-3))) + 1):
-        step(resident)
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
     if use_graph:
         model.enable_cuda_graph()
         step(resident)          # re-capture
+    keep_busy(lambda: step(resident), ms_total / args.steps)
+    clocks = sampler.stop()
 
     # ---- informational: the render alone (sampling -> decoder -> compositing), without the Encoder / SlotAttention prefix ----
     render_only_ms = None
@@ -356,7 +447,7 @@ def run_b200(args):
             ro = (model.render if args.no_graph else model.render_graphed)
             for _ in range(3):
                 ro(z_fixed, model.cam2world, model.nss2cam0)
-            render_only_ms = timed(lambda: ro(z_fixed, model.cam2world, model.nss2cam0), args.steps) / args.steps
+            render_only_ms = ctx.timed(lambda: ro(z_fixed, model.cam2world, model.nss2cam0), args.steps) / args.steps
 
     # ---- end-to-end arm: host buffers, H2D + D2H inside the timed region ----
     def e2e_step():
@@ -365,7 +456,7 @@ def run_b200(args):
         torch.cuda.current_stream().synchronize()
     for _ in range(3):
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = ctx.timed(e2e_step, args.steps)
 
     pts_rank = (hi - lo) * c["frustum"] ** 2 * c["n_samp"]
     units_total = n_total * c["frustum"] ** 2 * c["n_samp"] * K
@@ -379,70 +470,55 @@ def run_b200(args):
         traffic = json.load(open(tpath)).get(args.precision)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = out_host.numel() * out_host.element_size()
-
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": args.precision + " (tensor-core operands; fp32 accumulate, fp32 elsewhere)", "data": "synthetic",
-                "config": dict(c, n_views_total=n_total, sharding=f"views over {world} rank(s), slot latents broadcast from rank 0",
-                               layout="native ray-major, raws+masked+unmasked materialised",
-                               launch=("eager launches" if args.no_graph else "forward replayed as one CUDA graph" if world == 1
-                                       else "per rank one CUDA graph: [rank 0: encoder + slot attention] -> NCCL broadcast of the slot latents -> render"),
-                               l2="no flush: each step streams ~0.8 GB of outputs per GPU (>> 126 MB L2)",
-                               weights="random init, seed 2021",
-                               render_only=(None if render_only_ms is None else
-                                            {"ms_per_step": render_only_ms, "value": units_total / (render_only_ms * 1e-3),
-                                             "note": "same step without the Encoder + SlotAttention prefix (SURVEY 8(d))"})),
-                "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps},
-                # launches of this library's own kernels per step on rank 0 (profiles/*_launches.md): encoder 6 (7 with
-                # `bottom`), slot attention 8, weight image 1, sampling 1, decoder 1, compositing 1
-                "gpu_launches": (18 + (1 if c.get("bottom") else 0)) * args.steps,
-                "roofline": {"kernel": "decoder_fwd_kernel", "bound": "tensor", "achieved": ach_tflops, "peak": pk["tf_burst"],
-                             "unit": "TFLOP/s", "frac": ach_tflops / pk["tf_burst"], "traffic": traffic,
-                             "peak_source": pk["src"] + " bf16 burst", "kernel_ms": dec_ms,
-                             "flops_per_point_algorithmic": f_min_per_point(K, Z), "points_per_launch": pts_rank,
-                             "note": "achieved counts ALGORITHMIC flops once; the x3 modes issue 3 MMA passes for them"},
-                "impl": "b200"}
-        if not args.no_cpu_baseline and world == 1:
-            v, dt, cores, sample = cpu_reference_run(1, 0)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-            try:
-                line["cpu_baseline"]["eager_gpu"] = eager_gpu_run(dev)
-            except Exception as e:   # a baseline leg must never take the product line down with it
-                line["cpu_baseline"]["eager_gpu"] = {"error": repr(e)[:200]}
-        print(json.dumps(line))
-    if world > 1:
-        _shutdown(dist)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision + " (tensor-core operands; fp32 accumulate, fp32 elsewhere)", "data": "synthetic",
+            "config": headline_config(),
+            "detail": {"n_views_total": n_total,
+                       "sharding": f"views over {world} rank(s), slot latents broadcast from rank 0" + (", rendered tiles all-gathered in the timed step" if world > 1 else ""),
+                       "layout": "native ray-major, raws+masked+unmasked materialised",
+                       "launch": ("eager launches" if args.no_graph else "forward replayed as one CUDA graph" if world == 1
+                                  else "per rank one CUDA graph: [rank 0: encoder + slot attention] -> NCCL broadcast of the slot latents -> render -> NCCL all-gather of the tiles"),
+                       "render_only": (None if render_only_ms is None else
+                                       {"ms_per_step": render_only_ms, "value": units_total / (render_only_ms * 1e-3),
+                                        "note": "same step without the Encoder + SlotAttention prefix (SURVEY 8(d))"})},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            # kernels of libuorf_b200.so launched inside the timed region on rank 0: uorf_launch_count() over one eagerly launched
+            # step x the timed steps (the timed steps replay exactly those launches from a graph)
+            "gpu_launches": int(round(launches_per_step * args.steps)),
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": {"kernel": "decoder_fwd_kernel", "bound": "tensor", "achieved": ach_tflops, "peak": pk["tf_burst"],
+                         "unit": "TFLOP/s", "frac": ach_tflops / pk["tf_burst"], "traffic": traffic,
+                         "peak_source": pk["src"] + " bf16 burst", "kernel_ms": dec_ms,
+                         "flops_per_point_algorithmic": f_min_per_point(K, Z), "points_per_launch": pts_rank,
+                         "note": "achieved counts ALGORITHMIC flops once; the x3 modes issue 3 MMA passes for them"},
+            "impl": "b200"}
+    if use_graph:
+        model.enable_cuda_graph(False)
+    if graphed_sharded is not None:
+        graphed_sharded.release()
+    del model
+    gc.collect()
+    torch.cuda.empty_cache()
+    return line
 
 
 # ----------------------------------------------------------------------------------------------------
-# training arm (BASELINE.json configs[2]): CLEVR-567 coarse-stage step, fwd + bwd + Adam, scene-sharded data parallel
+# training step (BASELINE.json configs[2] coarse / configs[3] fine): fwd + bwd + Adam, scene-sharded data parallel
 # ----------------------------------------------------------------------------------------------------
-TRAIN_CFG = dict(workload="clevr567_train_coarse_K8_F64_D64_N4", K=8, z_dim=64, n_views=4, frustum=64, n_samp=64,
-                 supervision_size=64, input_size=64, load_size=128)
-
-
-def run_train(args):
-    import torch.distributed as dist
+def bench_train(ctx, args, c, with_reference_gpu=True):
+    from uorf_b200 import _lib
     from uorf_b200.nogan_model import uorfNoGanModel, default_train_options
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --mode train needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device(f"cuda:{local_rank}")
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    c = TRAIN_CFG
+    world, rank, dev, dist = ctx.world, ctx.rank, ctx.dev, ctx.dist
     torch.manual_seed(2021)   # identical replicas
     opt = default_train_options(num_slots=c["K"], z_dim=c["z_dim"], n_samp=c["n_samp"], frustum_size=c["frustum"],
                                 render_size=c["supervision_size"], supervision_size=c["supervision_size"], input_size=c["input_size"],
                                 n_img_each_scene=c["n_views"], stage=c.get("stage", "coarse"), bottom=c.get("bottom", False),
-                                frustum_size_fine=c.get("frustum_fine", 128), gpu_ids=[local_rank], warmup_steps=10)
-    use_graph = not args.no_graph and opt.stage == "coarse"     # the fine stage draws its crop window on the host every step
+                                frustum_size_fine=c.get("frustum_fine", 128), gpu_ids=[ctx.local_rank], warmup_steps=10,
+                                vgg_random_init=True)       # no network for the ImageNet weights: arithmetic-identical random VGG
+    use_graph = not args.no_graph
     opt.cuda_graph = use_graph
     model = uorfNoGanModel(opt, precision=args.precision)
     if world > 1:
@@ -459,57 +535,21 @@ def run_train(args):
         model.optimize_parameters(epoch=opt.percept_in)    # perceptual loss active: the steady-state step of the schedule
         model.update_learning_rate()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
-    sampler = ClockSampler(local_rank)
-    for _ in range(5 if use_graph else 0):      # three eager steps + the capture happen before the warm-up
+    sampler = ClockSampler(ctx.local_rank)
+    # eager steps first (cuDNN autotuning, optimizer state); the library's launch counter over one of them = its kernels per step
+    step(resident)
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    step(resident)
+    launches_per_step = _lib.launch_count() - n0
+    for _ in range(3 if use_graph else 0):      # the remaining eager step(s) + the capture happen before the warm-up
         step(resident)
     for _ in range(max(args.warmup, 3)):
         step(resident)
     sampler.start()
-    prof_range = bool(os.environ.get("UORF_PROFILE_RANGE"))
-    if prof_range:
-        torch.cuda.profiler.start()
-    ms_total = timed(lambda: step(resident), args.steps)
-    if prof_range:
-        torch.cuda.profiler.stop()
-    for _ in range(int(min(400, 1000.0 / max(ms_total / args.steps, 1e-3))) + 1):   # same count on every rank (collectives inside)
-        step(resident)
-    torch.cuda.synchronize()
+    ms_total = ctx.timed(lambda: step(resident), args.steps)
+    keep_busy(lambda: step(resident), ms_total / args.steps)
     clocks = sampler.stop()
-    # duration of the two decoder calls: CUDA events around them over a few eagerly launched steps (events cannot be recorded
-    # inside a replayed graph); same stream, same inputs, same launch configuration
-    fwd_ms = bwd_ms = None
-    if world == 1:
-        model.enable_cuda_graph(False) if use_graph else None
-        model.netDecoder.events, model.netDecoder.events_bwd = [], []
-        for _ in range(min(args.steps, 5)):
-            step(resident)
-        torch.cuda.synchronize()
-        ef, eb = model.netDecoder.events, model.netDecoder.events_bwd
-        model.netDecoder.events = model.netDecoder.events_bwd = None
-        fwd_ms = sum(a.elapsed_time(b) for a, b in ef) / max(len(ef), 1)
-        bwd_ms = sum(a.elapsed_time(b) for a, b in eb) / max(len(eb), 1)
-        if use_graph:
-            model.enable_cuda_graph()
-            for _ in range(5):
-                step(resident)
 
     def e2e_step():
         step(host)
@@ -517,65 +557,179 @@ def run_train(args):
         torch.cuda.current_stream().synchronize()
     for _ in range(3):
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
-    if rank == 0:
-        h2d = sum(v.numel() * v.element_size() for v in host.values())
-        line = {"metric": "train_scene_steps_per_sec", "value": world * args.steps / (ms_total * 1e-3), "unit": "scene-steps/s",
-                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": args.precision + " forward; fp16 tensor-core backward with fp32 accumulation; fp32 elsewhere", "data": "synthetic",
-                "config": dict(c, step="Encoder+SlotAttention+sampling+decoder+compositing fwd+bwd, MSE + VGG16-relu4_3 perceptual "
-                               "(random-init VGG, weight_percept 0.006 active: epoch = percept_in), Adam",
-                               parallelism=f"scene-sharded data parallel x{world}, one flat gradient all-reduce (NCCL)",
-                               launch=("whole step (forward + backward" + (" + gradient all-reduce" if world > 1 else "") + " + Adam) replayed as one CUDA graph")
-                               if use_graph else "eager launches",
-                               loss_last=float(model.loss_recon.detach())),
-                "clocks": clocks,
-                "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "scene-steps/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-                # launches of this library's own kernels per step and rank (profiles/*_launches_train.md): slot attention 8 + 10,
-                # sampling 1, weight image 2, decoder fwd 1 + bwd 4 (compose, main, reduce, unfold), compositing 1 + 1
-                "gpu_launches": 27 * args.steps,
-                "impl": "b200"}
-        if bwd_ms:
-            pk = peaks()
-            pts = c["n_views"] * c["frustum"] ** 2 * c["n_samp"]
-            fl = f_min_per_point(c["K"], c["z_dim"])
-            ach = 4.0 * fl * pts / (bwd_ms * 1e-3) / 1e12
-            line["roofline"] = {"kernel": "decoder_bwd_kernel (+ composition-backward, reduce, unfold)", "bound": "tensor", "achieved": ach,
-                                "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None,
-                                "peak_source": pk["src"] + " bf16 burst", "kernel_ms": bwd_ms, "decoder_fwd_kernel_ms": fwd_ms,
-                                "flops_per_point_algorithmic": 4.0 * fl, "points_per_launch": pts,
-                                "note": "algorithmic flops = 4 x forward F_min (recompute + dX + dW at M=64 half rate)"}
-        print(json.dumps(line))
-    if world > 1:
-        _shutdown(dist)
+    ms_e2e = ctx.timed(e2e_step, args.steps)
+    loss_last = float(loss_host[0])
+    # duration of the two decoder calls: CUDA events around them over a few eagerly launched steps (events cannot be recorded
+    # inside a replayed graph); same stream, same inputs, same launch configuration.  Every rank runs them (collectives inside).
+    if use_graph:
+        model.enable_cuda_graph(False)
+    model.netDecoder.events, model.netDecoder.events_bwd = [], []
+    for _ in range(min(args.steps, 5)):
+        step(resident)
+    torch.cuda.synchronize()
+    ef, eb = model.netDecoder.events, model.netDecoder.events_bwd
+    model.netDecoder.events = model.netDecoder.events_bwd = None
+    fwd_ms = sum(a.elapsed_time(b) for a, b in ef) / max(len(ef), 1)
+    bwd_ms = sum(a.elapsed_time(b) for a, b in eb) / max(len(eb), 1)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    pk = peaks()
+    pts = c["n_views"] * c["supervision_size"] ** 2 * c["n_samp"]
+    fl = f_min_per_point(c["K"], c["z_dim"])
+    ach = 4.0 * fl * pts / (bwd_ms * 1e-3) / 1e12 if bwd_ms else None
+    rec = {"metric": "train_scene_steps_per_sec", "workload": c["workload"], "value": world * args.steps / (ms_total * 1e-3),
+           "unit": "scene-steps/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms_total / args.steps, "scaling": "weak",
+           "dtype": args.precision + " forward; fp16 tensor-core backward with fp32 accumulation; fp32 elsewhere",
+           "config": dict(c, step="Encoder+SlotAttention+sampling+decoder+compositing fwd+bwd, MSE + VGG16-relu4_3 perceptual "
+                          "(random-init VGG, weight_percept 0.006 active: epoch = percept_in), Adam (reference uorf_nogan_model.py:229-245)",
+                          parallelism=f"scene-sharded data parallel x{world}: one scene per rank, ONE flat-bucket gradient all-reduce (NCCL, average)"),
+           "launch": ("whole step (forward + backward" + (" + gradient all-reduce" if world > 1 else "") + " + Adam) replayed as one CUDA graph")
+           if use_graph else "eager launches",
+           "loss_last": loss_last, "clocks": clocks,
+           "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "scene-steps/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+           "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
+           "roofline": {"kernel": "decoder_bwd_kernel (+ composition-backward, reduce, unfold)", "bound": "tensor", "achieved": ach,
+                        "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": (ach / pk["tf_burst"]) if ach else None, "traffic": None,
+                        "peak_source": pk["src"] + " bf16 burst", "kernel_ms": bwd_ms, "decoder_fwd_kernel_ms": fwd_ms,
+                        "flops_per_point_algorithmic": 4.0 * fl, "points_per_launch": pts,
+                        "note": "algorithmic flops = 4 x forward F_min (recompute + dX + dW at M=64 half rate)"}}
+    model._graph = None
+    del model
+    gc.collect()
+    torch.cuda.empty_cache()
+    if with_reference_gpu and world == 1 and not args.no_cpu_baseline:
+        try:
+            rec["reference_eager_gpu"] = eager_gpu_reference_train(dev, c)
+        except Exception as e:   # a baseline leg must never take the product line down with it
+            rec["reference_eager_gpu"] = {"error": repr(e)[:300]}
+    return rec
+
+
+# ----------------------------------------------------------------------------------------------------
+# strong scaling (BASELINE.json configs[4]): one 256x256x128 view, rows sharded over the ranks, tiles gathered in the step
+# ----------------------------------------------------------------------------------------------------
+def bench_strong(ctx, args):
+    from uorf_b200 import sharded
+    from uorf_b200.eval_model import default_eval_options
+    from uorf_b200.manip_model import uorfManipModel
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    s = STRONG_CFG
+    F_, D, Z = s["frustum"], s["n_samp"], s["z_dim"]
+    if F_ % world != 0:
+        return {"error": f"{F_} image rows do not divide over {world} ranks"}
+    h0, h1 = sharded.shard_range(F_, world, rank)
+    pk = peaks()
+    runs = []
+    for K in s["slots"]:
+        torch.manual_seed(2021)
+        opt = default_eval_options(num_slots=K, z_dim=Z, n_samp=D, frustum_size=F_, render_size=F_, input_size=s["input_size"],
+                                   n_img_each_scene=1, gpu_ids=[ctx.local_rank])
+        m = uorfManipModel(opt, layout="native", precision=args.precision).eval()
+        m.netDecoder.emit = ("raws",)       # the reference stores per-slot raws of the moved render but never reads them (:205-216)
+        img, c2w, azi = synthetic_scene(1, s["load_size"])
+        m.set_input({"img_data": img, "cam2world": c2w, "azi_rot": azi, "paths": [], "movement": torch.tensor([1.0, 0.5, 0.0])})
+        g = torch.Generator().manual_seed(7)
+        m.slot_noise = (torch.randn(1, K - 1, Z, generator=g).to(dev), torch.randn(1, 1, Z, generator=g).to(dev))
+        offsets = torch.zeros(K - 1, 3, device=dev)
+        offsets[1] = m.movement[0] / opt.nss_scale           # object 1 moved (uorf_manip_model.py:203)
+        gr = sharded.GraphedShardedRender(m, K, Z, rows=(h0, h1), fg_slot_offset=offsets, gather=True)
+        ctx.graph_owners.append(gr)
+
+        step = gr.run_eager if args.no_graph else gr
+        for _ in range(max(args.warmup, 3)):
+            out = step()
+        ms = ctx.timed(step, args.steps) / args.steps
+        full = out["full"]
+        ok = bool(torch.isfinite(full).all().item()) and tuple(full.shape) == (1, 3, F_, F_)
+        # decoder kernel time on this rank's rows (eager launches, CUDA events)
+        with torch.no_grad():
+            z_fixed = m.encode()[0].clone()
+            m.netDecoder.events = []
+            for _ in range(3):
+                m.render(z_fixed, m.cam2world, m.nss2cam0, fg_slot_offset=offsets, rows=(h0, h1))
+        torch.cuda.synchronize()
+        ev = m.netDecoder.events
+        m.netDecoder.events = None
+        dec_ms = sum(a.elapsed_time(b) for a, b in ev) / max(len(ev), 1)
+        pts_rank = (h1 - h0) * F_ * D
+        ach = pts_rank * f_min_per_point(K, Z) / (dec_ms * 1e-3) / 1e12
+        units = F_ * F_ * D * K
+        runs.append({"workload": f"manip_K{K}_F{F_}_D{D}", "K": K, "ms_per_step": ms, "value": units / (ms * 1e-3), "unit": UNIT,
+                     "rows_per_rank": h1 - h0, "points_per_rank": pts_rank, "decoder_kernel_ms": dec_ms,
+                     "decoder_roofline_frac": ach / pk["tf_burst"], "gathered_image_ok": ok})
+        gr.release()
+        del m, gr
+        gc.collect()
+        torch.cuda.empty_cache()
+    return {"metric": METRIC, "scaling": "strong", "n_gpus": world, "steps": args.steps, "gather_in_timed_region": True,
+            "dtype": args.precision,
+            "step": "one view, 256x256 rays x 128 samples, one object moved: [rank 0: encoder + slot attention] -> NCCL broadcast of the "
+                    "slot latents -> each rank renders its block of image rows -> NCCL all-gather of the tiles; one CUDA graph per rank "
+                    "(reference models/uorf_manip_model.py:196-232; only `raws` is materialised)",
+            "limiter": "the encoder + slot-attention prefix (~0.2 ms, rank 0 only) and the two collectives do not shrink with N; the "
+                       "render itself is tensor-bound and divides by N",
+            "runs": runs}
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args):
+    ctx = Ctx()
+    rank = ctx.rank
+    line = None
+    try:
+        if args.mode in ("all", "render"):
+            line = bench_render(ctx, args)
+            if not args.no_cpu_baseline and ctx.world == 1 and rank == 0:
+                v, dt, cores, kind, sample = cpu_reference_run(1, 0)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+                try:
+                    line["cpu_baseline"]["eager_gpu"] = eager_gpu_reference(ctx.dev)
+                except Exception as e:   # a baseline leg must never take the product line down with it
+                    line["cpu_baseline"]["eager_gpu"] = {"error": repr(e)[:300]}
+        subs = {}
+        if args.mode in ("all", "train"):
+            subs["train"] = bench_train(ctx, args, TRAIN_CFG)
+        if args.mode in ("all", "train") and args.workload is None:
+            subs["train_fine"] = bench_train(ctx, args, TRAIN_FINE_CFG)
+        if args.mode in ("all", "strong"):
+            subs["strong"] = bench_strong(ctx, args)
+        if line is None:          # a single sub-record requested: it is the line
+            name, rec = next(iter(subs.items()))
+            line = dict(rec, impl="b200", higher_is_better=True, warmup=max(args.warmup, 3), vs_baseline=None, data="synthetic")
+            subs.pop(name)
+        line.update(subs)
+        if rank == 0:
+            print(json.dumps(line))
+            sys.stdout.flush()
+    finally:
+        ctx.shutdown()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "bf16x3", "bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default=None, choices=[None] + sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS),
-                    help="another BASELINE.json shape instead of the headline one (clevr567: render; room_diverse_fine: --mode train)")
-    ap.add_argument("--no-graph", action="store_true", help="launch the render step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--mode", default="render", choices=["render", "train"],
-                    help="render: the headline eval-render metric (default); train: CLEVR-567 coarse training step")
+    ap.add_argument("--workload", default=None, choices=[None] + sorted(WORKLOADS) + ["room_diverse_fine"],
+                    help="another BASELINE.json shape instead of the default one (clevr567: render; room_diverse_fine: --mode train)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--mode", default="all", choices=["all", "render", "train", "strong"],
+                    help="all (default): the headline render line with the train / train_fine / strong sub-records; "
+                         "render / train / strong: only that part")
     args = ap.parse_args()
     global CFG, TRAIN_CFG
     if args.workload in WORKLOADS:
         CFG = WORKLOADS[args.workload]
-    elif args.workload in TRAIN_WORKLOADS:
-        TRAIN_CFG = TRAIN_WORKLOADS[args.workload]
+        if args.mode == "all":
+            args.mode = "render"
+    elif args.workload == "room_diverse_fine":
+        TRAIN_CFG = TRAIN_FINE_CFG
         args.mode = "train"
     if args.impl == "reference":
         run_reference(args)
-    elif args.mode == "train":
-        run_train(args)
     else:
         run_b200(args)
 

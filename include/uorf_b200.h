@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UORF_ABI_VERSION 1
+#define UORF_ABI_VERSION 2
 
 #define UORF_OK 0
 #define UORF_ERR_ARG (-1)
@@ -37,6 +37,9 @@ const char* uorf_last_error(void);
 /* Checks that `device` is an sm_100 part and configures the kernels (max dynamic shared memory).
  * Idempotent; every other call does it implicitly for the current device. */
 int uorf_init(int device);
+/* Number of kernels this library has launched since it was loaded (all devices, all threads).  bench.py reports the
+ * difference across its timed region as `gpu_launches`; launches replayed from a CUDA graph are counted at capture time. */
+int64_t uorf_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 1 — frustum sample generation.
@@ -66,6 +69,13 @@ typedef struct uorf_frustum {
 int uorf_sample_coords(const uorf_frustum* f, const float* z_cam, const float* cam2world, int32_t n_views, int32_t scale,
                        int32_t crop_h, int32_t crop_w, int32_t Hc, int32_t Wc, int32_t ray_major,
                        float* coords, float* z_vals, float* ray_dir, void* stream);
+/* Same, for a crop window whose origin lives on the DEVICE: crop_origin -> int32 (h0, w0), read by the kernel and clamped to
+ * [0, H-Hc] x [0, W-Wc].  The fine-stage training step draws its window with torch.randint on the device
+ * (models/uorf_nogan_model.py:160-161); reading the two ints on the device keeps the step free of host synchronisation, so the
+ * whole fine-stage step can be captured and replayed as one CUDA graph. */
+int uorf_sample_coords_window(const uorf_frustum* f, const float* z_cam, const float* cam2world, int32_t n_views,
+                              const int32_t* crop_origin, int32_t Hc, int32_t Wc, int32_t ray_major,
+                              float* coords, float* z_vals, float* ray_dir, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel 2 — fused K-slot decoder.
@@ -136,7 +146,8 @@ int uorf_decoder_forward(const uorf_decoder_args* a, void* stream);
  * Kernel 5 (decoder part) — backward of Decoder.forward w.r.t. every decoder weight and z_slots, given dL/d raws.
  * Replaces torch.autograd through models/model.py:106-161 as exercised by uorfNoGanModel.backward
  * (models/uorf_nogan_model.py:223-227; only `raws` carries gradient, masked/unmasked/masks are detached :185-196).
- * Activations are recomputed per tile on chip (fp16 activations/weights, bf16 activation gradients, fp32 accumulation); nothing is stored by
+ * Activations are recomputed per tile on chip (fp16 activations, weights and activation gradients - the latter under a
+ * power-of-two loss scale -, fp32 accumulation); nothing is stored by
  * the forward pass except its `unmasked_raws` output.
  * ------------------------------------------------------------------------------------------- */
 typedef struct uorf_decoder_grads {   /* same fields / shapes as uorf_decoder_weights, written by the call */
@@ -252,18 +263,6 @@ int uorf_slot_attention_backward(const uorf_slot_attention_weights* w, const uor
 int uorf_encoder_conv3x3(const float* src_a, int32_t ca, int32_t upsample_a, const float* src_b, int32_t cb, const float* weight_t,
                          const float* bias, int32_t c_out, int32_t h_in, int32_t w_in, int32_t stride, float* out, void* stream);
 
-/* ---------------------------------------------------------------------------------------------
- * Test hook: one 128 x N x (16*ksteps) bf16 GEMM on the tcgen05 path the decoder uses
- * (A rows written to TMEM by threads, B a swizzled shared-memory tile).  a [128][64], b [N][64] fp32
- * (rounded to 16 bits inside), d [128][N].  Used by tests/ to pin the tensor-core data layouts.
- * ------------------------------------------------------------------------------------------- */
-int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, int32_t precision, float* d,
-                    void* stream);
-/* Test hook for the weight-gradient data path: d1 = a^T b1, d2 = a^T b2 with a, b [128][64] (points x features, rounded to
- * bf16), d [64][64]; both operands are read through MN-major shared-memory descriptors, M = 64, two accumulators interleaved. */
-int uorf_probe_gemm_tn(const float* a, const float* b1, const float* b2, float* d1, float* d2, void* stream);
-/* Diagnostic hook: SM-cycle counts of the decoder's handshake building blocks (out: 256 int64, device). */
-int uorf_probe_timing(int64_t* out, int32_t reps, void* stream);
 /* Test hook: site code written by a kernel whose mbarrier wait timed out (0 = none). */
 int uorf_debug_flag(void);
 

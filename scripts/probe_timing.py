@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from uorf_b200 import _lib
 out = torch.zeros(256, dtype=torch.int64, device="cuda")
-_lib.check(_lib.lib().uorf_probe_timing(out.data_ptr(), 50, None), "probe_timing")
+_lib.check(_lib.probe_lib().uorf_probe_timing(out.data_ptr(), 50, None), "probe_timing")
 torch.cuda.synchronize()
 o = out.cpu().tolist()
 names = ["N=64 TS same D", "N=64 TS 2 rotating D", "N=64 TS 4 rotating D", "N=128 TS same D", "N=256 TS same D",

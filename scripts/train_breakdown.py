@@ -8,7 +8,7 @@ from uorf_b200.nogan_model import uorfNoGanModel, default_train_options
 c = bench.TRAIN_CFG
 torch.manual_seed(2021)
 opt = default_train_options(num_slots=c["K"], z_dim=c["z_dim"], n_samp=c["n_samp"], frustum_size=c["frustum"], render_size=64,
-                            supervision_size=64, input_size=64, n_img_each_scene=4, stage="coarse", gpu_ids=[0], warmup_steps=10)
+                            supervision_size=64, input_size=64, n_img_each_scene=4, stage="coarse", gpu_ids=[0], warmup_steps=10, vgg_random_init=True)
 m = uorfNoGanModel(opt, precision=sys.argv[1] if len(sys.argv) > 1 else "fp16x3")
 img, c2w, azi = bench.synthetic_scene(4, 128)
 inp = {k: v.cuda() for k, v in {"img_data": img, "cam2world": c2w, "azi_rot": azi}.items()}

@@ -16,8 +16,8 @@ def built_lib():
     return build_library()
 
 
-def declared_symbols():
-    txt = open(os.path.join(ROOT, "include", "uorf_b200.h")).read()
+def declared_symbols(header="uorf_b200.h"):
+    txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(uorf_[a-z0-9_]+)\s*\(", txt)))
 
@@ -29,7 +29,22 @@ def test_library_exports_every_declared_symbol(built_lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/uorf_b200.h but not exported"
     lib.uorf_abi_version.restype = ctypes.c_int
-    assert lib.uorf_abi_version() == 1
+    assert lib.uorf_abi_version() == 2
+    lib.uorf_launch_count.restype = ctypes.c_int64
+    assert lib.uorf_launch_count() == 0          # nothing has been launched by loading the library
+
+
+def test_probe_hooks_live_in_their_own_library(built_lib):
+    """test / diagnostic kernels (include/uorf_b200_probe.h) are not part of the product library"""
+    from uorf_b200 import _lib
+    prod = ctypes.CDLL(built_lib)
+    probe = ctypes.CDLL(_lib.PROBE_LIB_PATH)
+    syms = declared_symbols("uorf_b200_probe.h")
+    assert len(syms) == 3
+    for s in syms:
+        assert hasattr(probe, s), f"{s} declared in include/uorf_b200_probe.h but not exported by the probe library"
+        assert not hasattr(prod, s), f"{s} must not ship in libuorf_b200.so"
+    _lib.probe_lib()
 
 
 def test_binding_covers_header(built_lib):

@@ -1,5 +1,6 @@
-"""bench.py contract on a machine without a GPU: the reference arm (CPU oracle on the host cores) prints ONE JSON line with the
-keys the driver reads, and the product arm refuses to run without a CUDA device (no CPU fallback)."""
+"""bench.py contract on a machine without a GPU: the reference arm (the unmodified reference from oracle/_ref - or the oracle
+port when that copy is missing - on the host cores) prints ONE JSON line with the keys the driver reads, and the product arm
+refuses to run without a CUDA device (no CPU fallback)."""
 import json
 import os
 import subprocess
@@ -17,7 +18,9 @@ def _run(*args, timeout=600):
 
 
 def test_reference_arm_json_line():
-    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1")
+    from oracle import ref_harness as R
+    R.install()                       # no-op without /root/reference (then the arm falls back to the oracle port)
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
     assert len(lines) == 1, r.stdout[-2000:]
@@ -27,10 +30,13 @@ def test_reference_arm_json_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["scaling"] == "weak"
     assert d["config"]["workload"] == "room_chair_eval_K5_F128_D64_N4" and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == d["unit"] and cb["sample"]
+    assert cb["kind"] == ("reference" if R.available() else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == d["unit"] and cb["sample"]
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
     assert d["gpu_launches"] == 0
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.headline_config()      # the two arms print the same `config`
 
 
 def test_product_arm_fails_loudly_without_gpu():

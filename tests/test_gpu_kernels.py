@@ -34,7 +34,7 @@ def test_probe_gemm(N, ksteps, prec):
     b = torch.randn(N, 64, generator=g)
     d = torch.full((128, N), float("nan"), device=dev())
     ad, bd = a.to(dev()), b.to(dev())
-    _lib.check(_lib.lib().uorf_probe_gemm(ad.data_ptr(), bd.data_ptr(), N, ksteps, prec, d.data_ptr(), None), "probe")
+    _lib.check(_lib.probe_lib().uorf_probe_gemm(ad.data_ptr(), bd.data_ptr(), N, ksteps, prec, d.data_ptr(), None), "probe")
     torch.cuda.synchronize()
     Kc = 16 * ksteps
     lowp = torch.float16 if prec % 2 == 0 else torch.bfloat16
@@ -547,7 +547,7 @@ def test_train_driver_golden(stage):
     g = load_golden(f"train_driver_{stage}")
     fine = stage == "fine"
     opt = default_train_options(num_slots=3, z_dim=40, n_samp=8, frustum_size=8, frustum_size_fine=16, render_size=8,
-                                supervision_size=8, input_size=32, n_img_each_scene=2, stage=stage, bottom=fine, gpu_ids=[0])
+                                supervision_size=8, input_size=32, n_img_each_scene=2, stage=stage, bottom=fine, gpu_ids=[0], vgg_random_init=True)
     m = uorfNoGanModel(opt, precision="fp16x3")
     m.load_networks_from_state_dicts(g["enc"], g["sa"], g["dec"])
     m.slot_noise = (g["noise_fg"].to(dev()), g["noise_bg"].to(dev()))
@@ -587,7 +587,7 @@ def test_train_step_cuda_graph_matches_eager():
     for graphed in (False, True):
         opt = default_train_options(num_slots=3, z_dim=40, n_samp=8, frustum_size=8, frustum_size_fine=16, render_size=8,
                                     supervision_size=8, input_size=32, n_img_each_scene=2, stage="coarse", gpu_ids=[0],
-                                    warmup_steps=4, cuda_graph=True)
+                                    warmup_steps=4, cuda_graph=True, vgg_random_init=True)
         m = uorfNoGanModel(opt, precision="fp16x3")
         m.load_networks_from_state_dicts(g["enc"], g["sa"], g["dec"])
         m.slot_noise = (g["noise_fg"].to(dev()), g["noise_bg"].to(dev()))

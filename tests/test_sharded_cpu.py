@@ -43,6 +43,15 @@ def _worker(rank, world, port, out):
     sharded.allreduce_gradients(params)
     ok_grad = torch.allclose(params[0].grad, torch.full((3, 4), 1.5)) and torch.allclose(params[1].grad, torch.arange(7.) * 1.5) \
         and params[2].grad is None
+    # the training driver's form: every .grad a view of ONE flat bucket, one all-reduce (average) over the bucket
+    ps = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+    flat = sharded.flatten_gradients(ps)
+    views_ok = all(p_.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() and p_.grad.shape == p_.shape and
+                   p_.grad.data_ptr() % 16 == 0 for p_ in ps)
+    for i, p_ in enumerate(ps):
+        p_.grad.copy_(torch.full(p_.shape, float((rank + 1) * (i + 1))))       # written in place, as the backward kernels do
+    sharded.allreduce_flat(flat)
+    ok_flat = views_ok and all(torch.allclose(p_.grad, torch.full(p_.shape, 1.5 * (i + 1))) for i, p_ in enumerate(ps))
     # row sharding (one view, large frustum): rank r renders rows [r*H/world, (r+1)*H/world)
     Hh, Ww = 6, 5
     image = torch.arange(2 * 3 * Hh * Ww, dtype=torch.float32).view(2, 3, Hh, Ww)
@@ -51,7 +60,7 @@ def _worker(rank, world, port, out):
         return image[:, :, h0:h1] + z.sum()
     loc, (h0, h1), full_rows = sharded.sharded_render_rows(encode, render_rows, Hh, K, C, torch.device("cpu"), gather=True)
     ok_rows = torch.equal(full_rows, image + slots_rank0.sum()) and (h1 - h0) == Hh // world and torch.equal(loc, full_rows[:, :, h0:h1])
-    out[rank] = bool(ok_render and ok_grad and ok_rows)
+    out[rank] = bool(ok_render and ok_grad and ok_rows and ok_flat)
     dist.destroy_process_group()
 
 

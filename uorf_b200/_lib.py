@@ -93,11 +93,14 @@ _SIGNATURES = {
     "uorf_abi_version": (C.c_int, []),
     "uorf_last_error": (C.c_char_p, []),
     "uorf_init": (C.c_int, [C.c_int]),
+    "uorf_launch_count": (C.c_int64, []),
     "uorf_debug_flag": (C.c_int, []),
     "uorf_encoder_conv3x3": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "uorf_sample_coords": (C.c_int, [C.POINTER(Frustum), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "uorf_sample_coords_window": (C.c_int, [C.POINTER(Frustum), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uorf_decoder_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "uorf_decoder_prepare": (C.c_int, [C.POINTER(DecoderWeights), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_void_p]),
@@ -116,11 +119,15 @@ _SIGNATURES = {
     "uorf_slot_attention_backward": (C.c_int, [C.POINTER(SlotAttentionWeights), C.POINTER(SlotAttentionWeights), C.c_void_p, C.c_int64,
                                                C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+_OPTIONAL = {}
+# libuorf_b200_probe.so (include/uorf_b200_probe.h): test / diagnostic hooks, a separate library loaded only by tests/ and scripts/
+PROBE_LIB_PATH = os.path.join(_HERE, "_build", "libuorf_b200_probe.so")
+_PROBE_SIGNATURES = {
     "uorf_probe_gemm_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "uorf_probe_timing": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "uorf_probe_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
-_OPTIONAL = {}
 
 _lib = None
 _lock = threading.Lock()
@@ -147,6 +154,30 @@ def lib() -> C.CDLL:
                         fn.restype, fn.argtypes = res, args
                 _lib = l
     return _lib
+
+
+_probe = None
+
+
+def probe_lib() -> C.CDLL:
+    """The test-hook library (tcgen05 layout probes, hand-off timing); built next to the product library."""
+    global _probe
+    if _probe is None:
+        with _lock:
+            if _probe is None:
+                if not os.path.exists(PROBE_LIB_PATH):
+                    raise UorfError(f"{PROBE_LIB_PATH} not found: build it with `python -m uorf_b200.build`")
+                l = C.CDLL(PROBE_LIB_PATH)
+                for name, (res, args) in _PROBE_SIGNATURES.items():
+                    fn = getattr(l, name)
+                    fn.restype, fn.argtypes = res, args
+                _probe = l
+    return _probe
+
+
+def launch_count() -> int:
+    """kernels launched by libuorf_b200.so since it was loaded (uorf_launch_count)"""
+    return int(lib().uorf_launch_count())
 
 
 def check(rc: int, what: str) -> None:

@@ -18,7 +18,10 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libuorf_b200.so")
 SOURCES = ["abi.cu", "encoder.cu", "sample_coords.cu", "decoder_prep.cu", "decoder_fwd.cu", "decoder_bwd.cu", "composite.cu",
-           "slot_attention.cu", "slot_attention_bwd.cu", "probe.cu"]
+           "slot_attention.cu", "slot_attention_bwd.cu"]
+# test / diagnostic hooks (tcgen05 layout probes, hand-off timing): their own library, never linked into the product .so
+PROBE_LIB = os.path.join(OUT, "libuorf_b200_probe.so")
+PROBE_SOURCES = ["probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 
@@ -36,7 +39,8 @@ def _sources():
 
 def _fingerprint() -> str:
     h = hashlib.sha256()
-    files = sorted(os.listdir(CSRC)) + [os.path.join("..", "..", "include", "uorf_b200.h")]
+    files = sorted(os.listdir(CSRC)) + [os.path.join("..", "..", "include", "uorf_b200.h"),
+                                        os.path.join("..", "..", "include", "uorf_b200_probe.h")]
     for f in files:
         p = os.path.join(CSRC, f)
         if os.path.isfile(p):
@@ -50,14 +54,16 @@ def _fingerprint() -> str:
 def build_library(force: bool = False, verbose: bool = False, defines=(), tag: str = "") -> str:
     """`defines`/`tag`: tuning variants (e.g. defines=["-DUORF_WAIT_HINT_NS=1000"], tag="hint1000") are built next to the
     product library as _build/variants/libuorf_b200_<tag>.so; UORF_B200_LIB=<path> makes the loader pick one up."""
-    out, lib = OUT, LIB
+    out, lib, probe_lib = OUT, LIB, PROBE_LIB
     if tag:
         out = os.path.join(OUT, "variants", tag)
         lib = os.path.join(OUT, "variants", f"libuorf_b200_{tag}.so")
+        probe_lib = None
     os.makedirs(out, exist_ok=True)
     stamp = os.path.join(out, "fingerprint.txt")
     fp = _fingerprint() + " " + " ".join(defines)
-    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == fp:
+    if (not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == fp
+            and (probe_lib is None or os.path.exists(probe_lib))):
         return lib
     nvcc = _nvcc()
     flags = list(NVCC_FLAGS) + list(defines) + (["-Xptxas", "-v"] if verbose else [])
@@ -72,12 +78,17 @@ def build_library(force: bool = False, verbose: bool = False, defines=(), tag: s
             sys.stderr.write(r.stderr)
         return obj
 
+    probe_srcs = PROBE_SOURCES if probe_lib else []
     with ThreadPoolExecutor(max_workers=8) as ex:
-        objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        all_objs = list(ex.map(compile_one, _sources() + probe_srcs))
+    objs, probe_objs = all_objs[:len(all_objs) - len(probe_srcs)], all_objs[len(all_objs) - len(probe_srcs):]
+    for target, o in ((lib, objs), (probe_lib, probe_objs)):
+        if not target:
+            continue
+        cmd = [nvcc, "-shared", "-o", target] + o + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as fh:
         fh.write(fp)
     return lib

@@ -1,6 +1,8 @@
 // extern "C" surface of libuorf_b200.so (declared in include/uorf_b200.h): argument validation, the
 // per-device context, error strings.  Kernels live in the sibling .cu files.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
+#include <atomic>
 #include <mutex>
 #include <stdio.h>
 #include <string.h>
@@ -11,8 +13,8 @@
 
 namespace uorf {
 int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float* cam2world, int n_views, int scale, int crop_h,
-                         int crop_w, int Hc, int Wc, int ray_major, float* coords, float* z_vals, float* ray_dir, int num_sms,
-                         cudaStream_t stream);
+                         int crop_w, const int* crop_origin, int Hc, int Wc, int ray_major, float* coords, float* z_vals, float* ray_dir,
+                         int num_sms, cudaStream_t stream);
 int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* weight_t, const float* bias,
                            int c_out, int h_in, int w_in, int stride, float* out, cudaStream_t stream);
 int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int K, int Z, int passes, int f16, void* image,
@@ -26,8 +28,6 @@ size_t slot_attention_ws_floats(int ntok, int C, int K);
 int launch_slot_attention(const uorf_slot_attention_weights* w, const float* feat, long long feat_ts, long long feat_cs,
                           const float* noise_fg, const float* noise_bg, int ntok, int C, int K, int hidden, int iters, float eps,
                           float* workspace, float* slots, float* attn, cudaStream_t stream);
-int launch_probe_gemm(const float* a, const float* b, int N, int ksteps, int passes, int f16, float* d, int* err_flag, cudaStream_t stream);
-int launch_probe_timing(long long* out, int reps, cudaStream_t stream);
 size_t slot_attention_bwd_ws_floats(int ntok, int C, int K, int hidden);
 int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_slot_attention_grads* g, const float* feat, long long feat_ts,
                               long long feat_cs, const float* noise_fg, const float* noise_bg, int ntok, int C, int K, int hidden, int iters,
@@ -36,12 +36,19 @@ int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_s
 size_t decoder_bwd_workspace_floats(long long P, int K, int num_sms);
 int launch_decoder_bwd(const uorf_decoder_weights* w, const uorf_decoder_grads* g, const uorf_decoder_bwd_args* a, int num_sms,
                        int* err_flag, cudaStream_t stream);
-int launch_probe_gemm_tn(const float* a, const float* b1, const float* b2, float* d1, float* d2, int* err_flag, cudaStream_t stream);
 }  // namespace uorf
 
 namespace {
 
 thread_local char g_err[512] = "";
+thread_local char g_cuda_err[256] = "";      // text of the CUDA error finish_launch() saw (cudaGetLastError clears it)
+std::atomic<long long> g_launches{0};        // kernels launched by this library since load (uorf_launch_count)
+
+// NVTX range around every launching entry point: names the C-ABI call in nsys / ncu timelines (no-op without a tool attached)
+struct Range {
+  explicit Range(const char* name) { nvtxRangePushA(name); }
+  ~Range() { nvtxRangePop(); }
+};
 
 int fail(int code, const char* fmt, const char* detail = "") {
   snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -103,9 +110,13 @@ DeviceCtx* ctx() {
 int check_launch(int rc, const char* what) {
   if (rc == UORF_OK) return rc;
   if (rc == UORF_ERR_DEVICE) {
-    cudaError_t e = cudaGetLastError();
-    static thread_local char buf[256];
-    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    static thread_local char buf[400];
+    if (g_cuda_err[0]) {                       // recorded by finish_launch (which consumed the CUDA error)
+      snprintf(buf, sizeof(buf), "%s: %s", what, g_cuda_err);
+      g_cuda_err[0] = 0;
+    } else {                                   // e.g. a failed cudaFuncSetAttribute: the error is still pending
+      snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(cudaGetLastError()));
+    }
     return fail(rc, "%s", buf);
   }
   return fail(rc, "%s: unsupported shape", what);
@@ -113,10 +124,21 @@ int check_launch(int rc, const char* what) {
 
 }  // namespace
 
+namespace uorf {
+int finish_launch(int n_kernels) {
+  g_launches.fetch_add(n_kernels, std::memory_order_relaxed);
+  const cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return UORF_OK;
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s (%s)", cudaGetErrorString(e), cudaGetErrorName(e));
+  return UORF_ERR_DEVICE;
+}
+}  // namespace uorf
+
 extern "C" {
 
 int uorf_abi_version(void) { return UORF_ABI_VERSION; }
 const char* uorf_last_error(void) { return g_err; }
+int64_t uorf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int uorf_init(int device) {
   if (device < 0 || device >= kMaxDevices) return fail(UORF_ERR_ARG, "device index out of range%s");
@@ -129,6 +151,7 @@ int uorf_init(int device) {
 int uorf_encoder_conv3x3(const float* src_a, int32_t ca, int32_t upsample_a, const float* src_b, int32_t cb, const float* weight_t,
                          const float* bias, int32_t c_out, int32_t h_in, int32_t w_in, int32_t stride, float* out, void* stream) {
   DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_encoder_conv3x3");
   if (!c) return UORF_ERR_DEVICE;
   if (!src_a || !weight_t || !bias || !out || (cb > 0 && !src_b)) return fail(UORF_ERR_ARG, "uorf_encoder_conv3x3: null pointer%s");
   if (ca < 1 || cb < 0 || c_out < 1 || h_in < 1 || w_in < 1 || (stride != 1 && stride != 2))
@@ -143,25 +166,41 @@ int uorf_debug_flag(void) {
   return c && c->err_flag_host ? *c->err_flag_host : -1;
 }
 
+static int sample_coords_impl(const char* what, const uorf_frustum* f, const float* z_cam, const float* cam2world, int32_t n_views,
+                              int32_t scale, int32_t crop_h, int32_t crop_w, const int32_t* crop_origin, int32_t Hc, int32_t Wc,
+                              int32_t ray_major, float* coords, float* z_vals, float* ray_dir, void* stream) {
+  DeviceCtx* c = ctx();
+  if (!c) return UORF_ERR_DEVICE;
+  Range nvtx_range(what);
+  if (!f || !z_cam || !cam2world || !coords) return fail(UORF_ERR_ARG, "%s: null pointer", what);
+  if (f->W <= 0 || f->H <= 0 || f->D <= 0 || n_views < 0 || scale < 1 || Hc <= 0 || Wc <= 0) return fail(UORF_ERR_ARG, "%s: bad sizes", what);
+  if (f->W != f->H) return fail(UORF_ERR_UNSUPPORTED, "%s: W != H (the reference's ray_dir view needs a square frustum)", what);
+  const bool crop = crop_origin != nullptr || crop_h >= 0 || crop_w >= 0;
+  if (crop_origin != nullptr) {
+    if (scale != 1 || Hc > f->H || Wc > f->W) return fail(UORF_ERR_ARG, "%s: bad crop window", what);
+    crop_h = crop_w = 0;   // the kernel reads the origin from the device and clamps it to [0, H-Hc] x [0, W-Wc]
+  } else if (crop) {
+    if (scale != 1 || crop_h < 0 || crop_w < 0 || crop_h + Hc > f->H || crop_w + Wc > f->W) return fail(UORF_ERR_ARG, "%s: bad crop window", what);
+  } else if (Hc * scale != f->H || Wc * scale != f->W) {
+    return fail(UORF_ERR_ARG, "%s: Hc*scale != H or Wc*scale != W", what);
+  }
+  return check_launch(uorf::launch_sample_coords(f, z_cam, cam2world, n_views, scale, crop ? crop_h : -1, crop ? crop_w : -1, crop_origin, Hc, Wc,
+                                                 ray_major, coords, z_vals, ray_dir, c->num_sms, static_cast<cudaStream_t>(stream)), what);
+}
+
 int uorf_sample_coords(const uorf_frustum* f, const float* z_cam, const float* cam2world, int32_t n_views, int32_t scale,
                        int32_t crop_h, int32_t crop_w, int32_t Hc, int32_t Wc, int32_t ray_major, float* coords, float* z_vals,
                        float* ray_dir, void* stream) {
-  DeviceCtx* c = ctx();
-  if (!c) return UORF_ERR_DEVICE;
-  if (!f || !z_cam || !cam2world || !coords) return fail(UORF_ERR_ARG, "uorf_sample_coords: null pointer%s");
-  if (f->W <= 0 || f->H <= 0 || f->D <= 0 || n_views < 0 || scale < 1 || Hc <= 0 || Wc <= 0)
-    return fail(UORF_ERR_ARG, "uorf_sample_coords: bad sizes%s");
-  if (f->W != f->H) return fail(UORF_ERR_UNSUPPORTED, "uorf_sample_coords: W != H (the reference's ray_dir view needs a square frustum)%s");
-  const bool crop = crop_h >= 0 || crop_w >= 0;
-  if (crop) {
-    if (scale != 1 || crop_h < 0 || crop_w < 0 || crop_h + Hc > f->H || crop_w + Wc > f->W)
-      return fail(UORF_ERR_ARG, "uorf_sample_coords: bad crop window%s");
-  } else if (Hc * scale != f->H || Wc * scale != f->W) {
-    return fail(UORF_ERR_ARG, "uorf_sample_coords: Hc*scale != H or Wc*scale != W%s");
-  }
-  return check_launch(uorf::launch_sample_coords(f, z_cam, cam2world, n_views, scale, crop ? crop_h : -1, crop ? crop_w : -1, Hc, Wc,
-                                                 ray_major, coords, z_vals, ray_dir, c->num_sms, static_cast<cudaStream_t>(stream)),
-                      "uorf_sample_coords");
+  return sample_coords_impl("uorf_sample_coords", f, z_cam, cam2world, n_views, scale, crop_h, crop_w, nullptr, Hc, Wc, ray_major, coords,
+                            z_vals, ray_dir, stream);
+}
+
+int uorf_sample_coords_window(const uorf_frustum* f, const float* z_cam, const float* cam2world, int32_t n_views,
+                              const int32_t* crop_origin, int32_t Hc, int32_t Wc, int32_t ray_major, float* coords, float* z_vals,
+                              float* ray_dir, void* stream) {
+  if (!crop_origin) return fail(UORF_ERR_ARG, "%s: null crop_origin", "uorf_sample_coords_window");
+  return sample_coords_impl("uorf_sample_coords_window", f, z_cam, cam2world, n_views, 1, 0, 0, crop_origin, Hc, Wc, ray_major, coords,
+                            z_vals, ray_dir, stream);
 }
 
 static bool prec_ok(int precision) { return precision >= 1 && precision <= 4; }
@@ -176,6 +215,7 @@ size_t uorf_decoder_image_bytes(int32_t K, int32_t precision) {
 int uorf_decoder_prepare(const uorf_decoder_weights* w, const float* z_slots, int32_t K, int32_t Z, int32_t n_freq,
                          int32_t n_layers, int32_t precision, void* image, void* stream) {
   DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_decoder_prepare");
   if (!c) return UORF_ERR_DEVICE;
   if (!w || !z_slots || !image) return fail(UORF_ERR_ARG, "uorf_decoder_prepare: null pointer%s");
   if ((reinterpret_cast<uintptr_t>(image) & 1023) != 0) return fail(UORF_ERR_ARG, "uorf_decoder_prepare: image must be 1024-byte aligned%s");
@@ -189,6 +229,7 @@ int uorf_decoder_prepare(const uorf_decoder_weights* w, const float* z_slots, in
 
 int uorf_decoder_forward(const uorf_decoder_args* a, void* stream) {
   DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_decoder_forward");
   if (!c) return UORF_ERR_DEVICE;
   if (!a || !a->coor_bg || !a->coor_fg || !a->fg_transform || !a->image || !a->workspace)
     return fail(UORF_ERR_ARG, "uorf_decoder_forward: null pointer%s");
@@ -213,6 +254,7 @@ size_t uorf_decoder_backward_workspace_floats(int64_t P, int32_t K) {
 
 int uorf_decoder_backward(const uorf_decoder_weights* w, const uorf_decoder_grads* g, const uorf_decoder_bwd_args* a, void* stream) {
   DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_decoder_backward");
   if (!c) return UORF_ERR_DEVICE;
   if (!w || !g || !a || !a->coor_bg || !a->coor_fg || !a->fg_transform || !a->image || !a->workspace || !a->unmasked_raws ||
       !a->grad_raws || !a->z_slots || !a->grad_z_slots)
@@ -231,6 +273,7 @@ int uorf_decoder_backward(const uorf_decoder_weights* w, const uorf_decoder_grad
 int uorf_composite_forward(const float* raw, const float* z_vals, const float* rays_d, int64_t R, int64_t geom_rays, int32_t D, float* rgb_map,
                            float* depth_map, float* weights_norm, float* mask_map, void* stream) {
   DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_composite_forward");
   if (!c) return UORF_ERR_DEVICE;
   if (R == 0) return UORF_OK;
   if (!raw || !z_vals || !rays_d || !rgb_map || !depth_map) return fail(UORF_ERR_ARG, "uorf_composite_forward: null pointer%s");
@@ -246,6 +289,7 @@ int uorf_composite_forward(const float* raw, const float* z_vals, const float* r
 int uorf_composite_backward(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb, int64_t R, int64_t geom_rays, int32_t D,
                             float* grad_raw, void* stream) {
   DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_composite_backward");
   if (!c) return UORF_ERR_DEVICE;
   if (R == 0) return UORF_OK;
   if (!raw || !z_vals || !rays_d || !grad_rgb || !grad_raw) return fail(UORF_ERR_ARG, "uorf_composite_backward: null pointer%s");
@@ -268,6 +312,7 @@ int uorf_slot_attention_forward(const uorf_slot_attention_weights* w, const floa
                                 int32_t C, int32_t K, int32_t hidden, int32_t iters, float eps, float* workspace, float* slots,
                                 float* attn, void* stream) {
   DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_slot_attention_forward");
   if (!c) return UORF_ERR_DEVICE;
   if (!w || !feat || !noise_fg || !noise_bg || !workspace || !slots || !attn)
     return fail(UORF_ERR_ARG, "uorf_slot_attention_forward: null pointer%s");
@@ -286,6 +331,7 @@ int uorf_slot_attention_backward(const uorf_slot_attention_weights* w, const uor
                                  int32_t n_tokens, int32_t C, int32_t K, int32_t hidden, int32_t iters, float eps,
                                  const float* fwd_workspace, const float* grad_slots, float* workspace, float* grad_feat, void* stream) {
   DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_slot_attention_backward");
   if (!c) return UORF_ERR_DEVICE;
   if (!w || !g || !feat || !noise_fg || !noise_bg || !fwd_workspace || !grad_slots || !workspace || !grad_feat)
     return fail(UORF_ERR_ARG, "uorf_slot_attention_backward: null pointer%s");
@@ -294,30 +340,6 @@ int uorf_slot_attention_backward(const uorf_slot_attention_weights* w, const uor
                                                       hidden, iters, eps, fwd_workspace, grad_slots, workspace, grad_feat,
                                                       static_cast<cudaStream_t>(stream)),
                       "uorf_slot_attention_backward");
-}
-
-int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, int32_t precision, float* d, void* stream) {
-  DeviceCtx* c = ctx();
-  if (!c) return UORF_ERR_DEVICE;
-  if (!a || !b || !d) return fail(UORF_ERR_ARG, "uorf_probe_gemm: null pointer%s");
-  if (N < 16 || N > 64 || (N % 16) || ksteps < 1 || ksteps > 4 || !prec_ok(precision))
-    return fail(UORF_ERR_ARG, "uorf_probe_gemm: bad shape%s");
-  return check_launch(uorf::launch_probe_gemm(a, b, N, ksteps, prec_passes(precision), prec_f16(precision), d, c->err_flag_dev, static_cast<cudaStream_t>(stream)),
-                      "uorf_probe_gemm");
-}
-
-int uorf_probe_gemm_tn(const float* a, const float* b1, const float* b2, float* d1, float* d2, void* stream) {
-  DeviceCtx* c = ctx();
-  if (!c) return UORF_ERR_DEVICE;
-  if (!a || !b1 || !b2 || !d1 || !d2) return fail(UORF_ERR_ARG, "uorf_probe_gemm_tn: null pointer%s");
-  return check_launch(uorf::launch_probe_gemm_tn(a, b1, b2, d1, d2, c->err_flag_dev, static_cast<cudaStream_t>(stream)), "uorf_probe_gemm_tn");
-}
-
-int uorf_probe_timing(int64_t* out, int32_t reps, void* stream) {
-  DeviceCtx* c = ctx();
-  if (!c) return UORF_ERR_DEVICE;
-  if (!out || reps < 1) return fail(UORF_ERR_ARG, "uorf_probe_timing: bad arguments%s");
-  return check_launch(uorf::launch_probe_timing(reinterpret_cast<long long*>(out), reps, static_cast<cudaStream_t>(stream)), "uorf_probe_timing");
 }
 
 }  // extern "C"

@@ -15,6 +15,10 @@
 
 namespace uorf {
 
+// End of every launch_* function (defined in abi.cu): adds `n_kernels` to the library's launch counter (uorf_launch_count) and
+// turns the CUDA launch status into UORF_OK / UORF_ERR_DEVICE, keeping the CUDA error text for uorf_last_error().
+int finish_launch(int n_kernels);
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -271,7 +271,7 @@ int launch_composite_fwd(const float* raw, const float* z_vals, const float* ray
   const int vec = composite_vec(D, z_vals, weights_norm);
   UORF_COMPOSITE_DISPATCH(S, L, (composite_fwd_kernel<kS, kL><<<grid, 256, 0, stream>>>(
       reinterpret_cast<const float4*>(raw), z_vals, rays_d, R, Rg, D, vec, rgb_map, depth_map, weights_norm, mask_map)));
-  return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
+  return finish_launch(1);
 }
 
 int launch_composite_bwd(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb, long long R, long long Rg, int D,
@@ -284,7 +284,7 @@ int launch_composite_bwd(const float* raw, const float* z_vals, const float* ray
   const int vec = composite_vec(D, z_vals, nullptr);
   UORF_COMPOSITE_DISPATCH(S, L, (composite_bwd_kernel<kS, kL><<<grid, 256, 0, stream>>>(
       reinterpret_cast<const float4*>(raw), z_vals, rays_d, grad_rgb, R, Rg, D, vec, reinterpret_cast<float4*>(grad_raw))));
-  return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
+  return finish_launch(1);
 }
 
 }  // namespace uorf

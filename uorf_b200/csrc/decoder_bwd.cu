@@ -754,7 +754,7 @@ int launch_decoder_bwd(const uorf_decoder_weights* w, const uorf_decoder_grads* 
   f.K = a->K;
   f.Z = a->Z;
   decoder_bwd_unfold_kernel<<<dim3(32, 2), 256, 0, stream>>>(f);
-  return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
+  return finish_launch(4);
 }
 
 }  // namespace uorf

@@ -701,7 +701,7 @@ int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, c
   else if (passes == 3) rc = f16 ? launch(decoder_fwd_kernel<3, true, 2>) : launch(decoder_fwd_kernel<3, false, 2>);
   else rc = f16 ? launch(decoder_fwd_kernel<1, true, 4>) : launch(decoder_fwd_kernel<1, false, 4>);
   if (rc != UORF_OK) return rc;
-  return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
+  return finish_launch(1);
 }
 
 }  // namespace uorf

@@ -171,7 +171,7 @@ int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int
   a.image = static_cast<unsigned char*>(image);
   dim3 grid(10 + (K - 1 > 1 ? K - 1 : 1), 2, kPrepSplit);
   decoder_prep_kernel<<<grid, 256, 0, stream>>>(a);
-  return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
+  return finish_launch(1);
 }
 
 }  // namespace uorf

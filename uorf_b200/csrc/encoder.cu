@@ -271,7 +271,7 @@ int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* sr
   else if (stride == 2 && !up_a) err = cudaLaunchKernelEx(&cfg, encoder_conv3x3_kernel<2, false>, p);
   else return UORF_ERR_UNSUPPORTED;
   if (err != cudaSuccess) return UORF_ERR_DEVICE;
-  return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
+  return finish_launch(1);
 }
 
 }  // namespace uorf

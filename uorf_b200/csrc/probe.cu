@@ -318,3 +318,33 @@ int launch_probe_gemm_tn(const float* a, const float* b1, const float* b2, float
 }
 
 }  // namespace uorf
+
+// ---------------------------------------------------------------------------------------------------
+// extern "C" surface of libuorf_b200_probe.so (include/uorf_b200_probe.h).  This file is built into its own TEST library:
+// the product library libuorf_b200.so contains none of these kernels.
+// ---------------------------------------------------------------------------------------------------
+#include "../../include/uorf_b200_probe.h"
+
+namespace uorf {
+int finish_launch(int) { return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE; }   // the probe library's own copy
+}
+
+extern "C" {
+
+int uorf_probe_gemm(const float* a, const float* b, int32_t N, int32_t ksteps, int32_t precision, float* d, void* stream) {
+  if (!a || !b || !d) return UORF_ERR_ARG;
+  if (N < 16 || N > 64 || (N % 16) || ksteps < 1 || ksteps > 4 || precision < 1 || precision > 4) return UORF_ERR_ARG;
+  return uorf::launch_probe_gemm(a, b, N, ksteps, precision >= 3 ? 3 : 1, (precision % 2) == 0 ? 1 : 0, d, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int uorf_probe_gemm_tn(const float* a, const float* b1, const float* b2, float* d1, float* d2, void* stream) {
+  if (!a || !b1 || !b2 || !d1 || !d2) return UORF_ERR_ARG;
+  return uorf::launch_probe_gemm_tn(a, b1, b2, d1, d2, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int uorf_probe_timing(int64_t* out, int32_t reps, void* stream) {
+  if (!out || reps < 1) return UORF_ERR_ARG;
+  return uorf::launch_probe_timing(reinterpret_cast<long long*>(out), reps, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

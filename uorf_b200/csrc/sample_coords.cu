@@ -23,6 +23,7 @@ struct CoordParams {
   float near_plane, inv_range_den;  // z_vals = (z - near) / den
   int W, H, D, N;
   int scale, crop_h, crop_w, Hc, Wc, ray_major;
+  const int* crop_origin;  // device (h0, w0) overriding crop_h / crop_w (clamped to the frustum), or null
   int sh_d, sh_w, sh_h;   // log2 of D, Wc, Hc when they are powers of two (index math by shifts), else -1
   float* coords;
   float* z_vals;
@@ -52,6 +53,12 @@ __device__ __forceinline__ void ray_affine(const float (&S)[16], const float (&c
 // IdxT = unsigned for every realistic frustum (< 2^32 samples): 32-bit index math is several times cheaper than 64-bit
 template <typename IdxT>
 __global__ void __launch_bounds__(256) sample_coords_kernel(const CoordParams p) {
+  // crop origin: host scalars, or (fine-stage training inside a CUDA graph) two device ints, clamped to the frustum
+  int crop_h = p.crop_h, crop_w = p.crop_w;
+  if (p.crop_origin != nullptr) {
+    crop_h = min(max(__ldg(p.crop_origin), 0), p.H - p.Hc);
+    crop_w = min(max(__ldg(p.crop_origin + 1), 0), p.W - p.Wc);
+  }
   __shared__ __align__(16) float s_xyz[2][256 * 3];
   __shared__ float s_zc[256], s_zv[256];                 // z_cam and normalised z_vals per depth index (D <= 256)
   __shared__ float s_c2w[kMaxStagedViews][12];           // rows 0..2 of every view's cam2world
@@ -98,8 +105,8 @@ __global__ void __launch_bounds__(256) sample_coords_kernel(const CoordParams p)
         hc = (int)(q % p.Hc); q /= p.Hc;
         d = (int)(q % p.D); n = (int)(q / p.D);
       }
-      const int h0 = p.crop_h >= 0 ? p.crop_h : chunk / p.scale;
-      const int w0 = p.crop_w >= 0 ? p.crop_w : chunk % p.scale;
+      const int h0 = crop_h >= 0 ? crop_h : chunk / p.scale;
+      const int w0 = crop_w >= 0 ? crop_w : chunk % p.scale;
       const int h = h0 + hc * p.scale, w = w0 + wc * p.scale;
       const float zc = ztab ? s_zc[d] : __ldg(p.z_cam + d);
       const float* Cg = p.cam2world + n * 16;
@@ -122,8 +129,8 @@ __global__ void __launch_bounds__(256) sample_coords_kernel(const CoordParams p)
         int rwc, rhc;
         if (pow2) { rwc = (int)(qr & (IdxT)(p.Wc - 1)); rhc = (int)((qr >> p.sh_w) & (IdxT)(p.Hc - 1)); }
         else { rwc = (int)(qr % p.Wc); qr /= p.Wc; rhc = (int)(qr % p.Hc); }
-        const int rh0 = p.crop_h >= 0 ? p.crop_h : rchunk / p.scale;
-        const int rw0 = p.crop_w >= 0 ? p.crop_w : rchunk % p.scale;
+        const int rh0 = crop_h >= 0 ? crop_h : rchunk / p.scale;
+        const int rw0 = crop_w >= 0 ? crop_w : rchunk % p.scale;
         const float x = (float)(rw0 + rwc * p.scale), y = (float)(rh0 + rhc * p.scale);
         float* dst = p.ray_dir + (long long)idx * 3;
 #pragma unroll
@@ -152,6 +159,12 @@ __global__ void __launch_bounds__(256) sample_coords_kernel(const CoordParams p)
 // generic 64-bit divisions were ~40 % of the kernel's instructions, which made it issue-bound rather than HBM-bound).
 template <bool POW2>
 __global__ void __launch_bounds__(256) sample_coords_rm4_kernel(const CoordParams p) {
+  // crop origin: host scalars, or (fine-stage training inside a CUDA graph) two device ints, clamped to the frustum
+  int crop_h = p.crop_h, crop_w = p.crop_w;
+  if (p.crop_origin != nullptr) {
+    crop_h = min(max(__ldg(p.crop_origin), 0), p.H - p.Hc);
+    crop_w = min(max(__ldg(p.crop_origin + 1), 0), p.W - p.Wc);
+  }
   __shared__ __align__(16) float4 s_strip[8][96];
   __shared__ float s_zc[256], s_zv[256];
   __shared__ float s_c2w[kMaxStagedViews][12];
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(256) sample_coords_rm4_kernel(const CoordParam
       const long long t2 = ray / p.Wc;
       hc = (int)(t2 % p.Hc); n = (int)(t2 / p.Hc);
     }
-    const int h = (p.crop_h >= 0 ? p.crop_h : 0) + hc, w = (p.crop_w >= 0 ? p.crop_w : 0) + wc;
+    const int h = (crop_h >= 0 ? crop_h : 0) + hc, w = (crop_w >= 0 ? crop_w : 0) + wc;
     float c[12];
 #pragma unroll
     for (int e = 0; e < 12; ++e) c[e] = cstage ? s_c2w[n][e] : __ldg(p.cam2world + n * 16 + e);
@@ -234,8 +247,8 @@ __global__ void __launch_bounds__(256) sample_coords_rm4_kernel(const CoordParam
 }
 
 int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float* cam2world, int n_views, int scale, int crop_h,
-                         int crop_w, int Hc, int Wc, int ray_major, float* coords, float* z_vals, float* ray_dir, int num_sms,
-                         cudaStream_t stream) {
+                         int crop_w, const int* crop_origin, int Hc, int Wc, int ray_major, float* coords, float* z_vals, float* ray_dir,
+                         int num_sms, cudaStream_t stream) {
   CoordParams p;
   for (int i = 0; i < 16; ++i) p.S[i] = f->spixel2cam[i];
   p.z_cam = z_cam;
@@ -244,7 +257,7 @@ int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float*
   p.near_plane = f->near_plane;
   p.inv_range_den = f->far_plane - f->near_plane;
   p.W = f->W; p.H = f->H; p.D = f->D; p.N = n_views;
-  p.scale = scale; p.crop_h = crop_h; p.crop_w = crop_w; p.Hc = Hc; p.Wc = Wc; p.ray_major = ray_major;
+  p.scale = scale; p.crop_h = crop_h; p.crop_w = crop_w; p.crop_origin = crop_origin; p.Hc = Hc; p.Wc = Wc; p.ray_major = ray_major;
   p.coords = coords; p.z_vals = z_vals; p.ray_dir = ray_dir;
   auto lg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; };
   p.sh_d = lg(f->D); p.sh_w = lg(Wc); p.sh_h = lg(Hc);
@@ -261,7 +274,7 @@ int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float*
     else sample_coords_rm4_kernel<false><<<(unsigned)b4, 256, 0, stream>>>(p);
   } else if (total < (1LL << 32) - 512) sample_coords_kernel<unsigned><<<(unsigned)blocks, 256, 0, stream>>>(p);
   else sample_coords_kernel<unsigned long long><<<(unsigned)blocks, 256, 0, stream>>>(p);
-  return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
+  return finish_launch(1);
 }
 
 }  // namespace uorf

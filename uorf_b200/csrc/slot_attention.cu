@@ -339,7 +339,7 @@ int launch_slot_attention(const uorf_slot_attention_weights* w, const float* fea
   // weight staging of the per-slot update kernel: every tensor it bulk-copies must be 16-byte aligned and a multiple of 16 bytes
   const size_t stage_bytes = (size_t)(2 * 3 * C * C + 2 * hidden * C + C * C + 6 * C + hidden + C) * sizeof(float);
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  const int staged = (C % 4 == 0 && hidden % 4 == 0 && al(w->gru_w_ih) && al(w->gru_w_hh) && al(w->gru_bg_w_ih) && al(w->gru_bg_w_hh) &&
+  const int staged = (stage_bytes <= 200 * 1024 && C % 4 == 0 && hidden % 4 == 0 && al(w->gru_w_ih) && al(w->gru_w_hh) && al(w->gru_bg_w_ih) && al(w->gru_bg_w_hh) &&
                       al(w->to_res_w1) && al(w->to_res_w2) && al(w->to_res_bg_w1) && al(w->to_res_bg_w2) && al(w->to_q_w) && al(w->to_q_bg_w) &&
                       al(w->gru_b_ih) && al(w->gru_b_hh) && al(w->gru_bg_b_ih) && al(w->gru_bg_b_hh) && al(w->to_res_b1) && al(w->to_res_b2) &&
                       al(w->to_res_bg_b1) && al(w->to_res_bg_b2)) ? 1 : 0;
@@ -351,7 +351,7 @@ int launch_slot_attention(const uorf_slot_attention_weights* w, const float* fea
     sa_attn_kernel<<<nblk, kSaThreads, 0, stream>>>(p);
     sa_update_kernel<<<K, kSaSlotThreads, staged ? stage_bytes : 0, stream>>>(p, nblk, it, staged);
   }
-  return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
+  return finish_launch(2 + 2 * iters);
 }
 
 }  // namespace uorf

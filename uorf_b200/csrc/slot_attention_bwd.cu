@@ -524,7 +524,7 @@ int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_s
   // weight staging of the per-slot kernel (TMA bulk copies: 16-byte aligned tensors, sizes multiples of 16 bytes)
   const size_t stage_bytes = (size_t)(C * C + 2 * 3 * C * C + 2 * hidden * C) * sizeof(float);
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  const int staged = (C % 4 == 0 && hidden % 4 == 0 && al(w->gru_w_ih) && al(w->gru_w_hh) && al(w->gru_bg_w_ih) && al(w->gru_bg_w_hh) &&
+  const int staged = (stage_bytes <= 200 * 1024 && C % 4 == 0 && hidden % 4 == 0 && al(w->gru_w_ih) && al(w->gru_w_hh) && al(w->gru_bg_w_ih) && al(w->gru_bg_w_hh) &&
                       al(w->to_res_w1) && al(w->to_res_w2) && al(w->to_res_bg_w1) && al(w->to_res_bg_w2) && al(w->to_q_w) && al(w->to_q_bg_w)) ? 1 : 0;
   // set on every launch, like the decoder kernels: function attributes are per device, a process may drive several
   if (staged && cudaFuncSetAttribute(sa_bwd_slot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return UORF_ERR_DEVICE;
@@ -540,7 +540,7 @@ int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_s
   sa_bwd_slot_kernel<<<K, kBSlotThreads, dyn, stream>>>(p, 1, 0, 0, 0, 0, staged);   // query path of iteration 0 -> d slot_0
   sa_bwd_feat_kernel<<<nblk, kBThreads, 0, stream>>>(p);
   sa_bwd_reduce_kernel<<<148, 256, 0, stream>>>(p);
-  return cudaGetLastError() == cudaSuccess ? UORF_OK : UORF_ERR_DEVICE;
+  return finish_launch(2 * iters + 3);
 }
 
 }  // namespace uorf

@@ -19,7 +19,9 @@ from .modules import raw2outputs
 class uorfManipModel(uorfEvalModel):
     def set_input(self, input):
         super().set_input(input)
-        self.movement = input["movement"].to(self.device)           # Nx3 world units (uorf_manip_model.py:112)
+        # world units.  The reference's dataset yields a flat (3,) tensor (multiscenes_manip_dataset.py: torch.tensor([x, y, 0]),
+        # collated as flat_batch[0]['movement']; the 'Nx3' comment at uorf_manip_model.py:112 is not what arrives): accept both
+        self.movement = input["movement"].to(self.device).float().reshape(-1, 3)
         for k, name in (("img_data_moved", "gt_moved"), ("img_data_changed", "gt_changed"), ("img_data_bg", "bg_img")):
             if k in input:
                 setattr(self, name, input[k].to(self.device))

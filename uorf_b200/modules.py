@@ -6,7 +6,7 @@ boundary runs in libuorf_b200.so (hand-written sm_100a kernels, C ABI in include
 for device memory, streams and autograd plumbing only.  There is no CPU / eager fallback: tensors must live on
 a CUDA device and the shared object must be loadable, otherwise the call raises.
 
-    Encoder            models/model.py:11-61     (cuDNN convolutions through torch; no custom kernel)
+    Encoder            models/model.py:11-61     -> uorf_encoder_conv3x3 (one fp32 image; other shapes: the torch layer stack)
     SlotAttention      models/model.py:164-258   -> uorf_slot_attention_forward
     Decoder            models/model.py:64-161    -> uorf_decoder_prepare + uorf_decoder_forward
     sin_emb            models/model.py:261-277   (fused into the decoder kernel; standalone version for callers)
@@ -15,6 +15,7 @@ a CUDA device and the shared object must be loadable, otherwise the call raises.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Optional, Sequence, Tuple
 
@@ -31,6 +32,17 @@ def _stream(t: torch.Tensor) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+_NULL_GUARD = contextlib.nullcontext()
+
+
+def _on(t: torch.Tensor):
+    """Device guard for a C-ABI call: the library takes its context (SM count, error flag) and launches on the CURRENT CUDA
+    device (csrc/abi.cu ctx()), while streams and pointers come from the tensor's device.  When they differ (opt.gpu_ids=[n]
+    in a process whose current device is another one) the call runs under torch.cuda.device(t.device), like the
+    at::DeviceGuard of the reference's own native ops (models/op/fused_bias_act.cpp:25)."""
+    return _NULL_GUARD if t.device.index == torch.cuda.current_device() else torch.cuda.device(t.device)
+
+
 def _require_cuda(*ts: torch.Tensor) -> None:
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -45,6 +57,20 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
+
+
+def _grad_buffers(named_params, sink):
+    """Where a backward kernel writes its parameter gradients (each is written in full, never accumulated).
+    Default: fresh tensors handed to autograd.  With `module.grad_sink = {name: tensor}` (the data-parallel driver points
+    every `.grad` at a slice of ONE flat buffer) the kernels write straight into the caller's storage and autograd receives
+    None for the parameters: the step then all-reduces that buffer with a single NCCL call, no gather / scatter copies."""
+    if sink is None:
+        return {n: torch.empty_like(p_, dtype=torch.float32, memory_format=torch.contiguous_format) for n, p_ in named_params.items()}
+    for n, p_ in named_params.items():
+        t = sink[n]
+        if t.shape != p_.shape or t.dtype != torch.float32 or not t.is_contiguous() or t.device != p_.device:
+            raise _lib.UorfError(f"grad_sink[{n!r}] must be a contiguous fp32 tensor of shape {tuple(p_.shape)} on {p_.device}")
+    return {n: sink[n] for n in named_params}
 
 
 # ======================================================================================================
@@ -72,6 +98,9 @@ class Encoder(nn.Module):
         self._wt = {}              # transposed conv weights of the inference path, keyed by weight version
         self.use_kernels = True    # False: always the torch / cuDNN layers
         self.use_kernels_in_training = True   # forward by the kernels under autograd too; backward = cuDNN per layer (_EncoderFn)
+        self.grad_sink = None                 # {parameter name: tensor}: the training path's backward writes gradients there (see _GradSink)
+        self.require_kernels = False          # True: raise instead of running the torch layer stack on a non-kernel shape
+        self.last_path = None                 # 'kernels' | 'torch': which path the last forward took
 
     def _pixel_planes(self, H, W, device):
         key = (H, W, str(device))
@@ -97,9 +126,10 @@ class Encoder(nn.Module):
         stride = conv.stride[0]
         ca, cb = src_a.shape[0], (0 if src_b is None else src_b.shape[0])
         out = torch.empty(conv.out_channels, (h_in - 1) // stride + 1, (w_in - 1) // stride + 1, device=src_a.device, dtype=torch.float32)
-        check(lib().uorf_encoder_conv3x3(src_a.data_ptr(), ca, int(up_a), _ptr(src_b), cb, cache[1].data_ptr(),
-                                         _f32c(conv.bias.detach()).data_ptr(), conv.out_channels, h_in, w_in, stride, out.data_ptr(),
-                                         _stream(src_a)), "uorf_encoder_conv3x3")
+        with _on(src_a):
+            check(lib().uorf_encoder_conv3x3(src_a.data_ptr(), ca, int(up_a), _ptr(src_b), cb, cache[1].data_ptr(),
+                                             _f32c(conv.bias.detach()).data_ptr(), conv.out_channels, h_in, w_in, stride, out.data_ptr(),
+                                             _stream(src_a)), "uorf_encoder_conv3x3")
         return out
 
     def _forward_inference(self, x, keep=None):
@@ -125,18 +155,32 @@ class Encoder(nn.Module):
         return out[None]
 
     def _kernels_apply(self, x):
+        """The direct-convolution kernels cover what every reference driver feeds the Encoder: ONE fp32 CUDA image (the
+        drivers encode view 0 only, uorf_eval_model.py:121) whose sides survive the stride-2 levels (multiples of 4, 8 with
+        `bottom`), at most 65,536 pixels and a channel count that is a multiple of 4 (launch_encoder_conv3x3's limits).
+        Anything else - a batch, another dtype, odd sizes, > 256x256 inputs - is NOT a kernel shape and takes the
+        reference's own layer stack below (cuDNN); `last_path` records which one ran, `require_kernels` turns the second
+        case into an error."""
         H, W = x.shape[2], x.shape[3]
+        z = self.enc_down_1[0].out_channels
         return (x.is_cuda and x.shape[0] == 1 and x.dtype == torch.float32 and self.use_kernels
-                and H % (8 if self.bottom else 4) == 0 and W % (8 if self.bottom else 4) == 0)
+                and H % (8 if self.bottom else 4) == 0 and W % (8 if self.bottom else 4) == 0
+                and H * W <= 65536 and z % 4 == 0)
 
     def forward(self, x):
         W, H = x.shape[3], x.shape[2]
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p_.requires_grad for p_ in self.parameters()))
         if self._kernels_apply(x):
             if not needs_grad:
+                self.last_path = "kernels"
                 return self._forward_inference(x)
             if self.use_kernels_in_training:
+                self.last_path = "kernels"
                 return _EncoderFn.apply(self, x, *self.parameters())
+        elif self.require_kernels:
+            raise _lib.UorfError(f"Encoder: input {tuple(x.shape)} {x.dtype} on {x.device} is outside the kernel shapes "
+                                 "(one fp32 CUDA image, sides multiples of 4 (8 with bottom), <= 65536 pixels) and require_kernels is set")
+        self.last_path = "torch"
         x_ = torch.cat([x, self._pixel_planes(H, W, x.device).expand(x.shape[0], -1, -1, -1)], dim=1)
         if self.bottom:
             x_down_1 = self.enc_down_1(self.enc_down_0(x_))
@@ -168,7 +212,12 @@ class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out):
         gx, grads = _encoder_backward(ctx.enc, dict(zip(ctx.names, ctx.saved_tensors)), g_out, ctx.x_needs_grad)
-        return (None, gx) + tuple(grads[n] for n, _ in ctx.enc.named_parameters())
+        names = [n for n, _ in ctx.enc.named_parameters()]
+        sink = ctx.enc.grad_sink
+        if sink is not None:       # gradients land in caller-owned buffers (one flat all-reduce bucket); autograd sees None
+            torch._foreach_copy_([sink[n] for n in names], [grads[n] for n in names])
+            return (None, gx) + (None,) * len(names)
+        return (None, gx) + tuple(grads[n] for n in names)
 
 
 def _encoder_backward(enc, a, g_out, x_needs_grad):
@@ -236,9 +285,10 @@ class _Composite(torch.autograd.Function):
         depth = torch.empty(R, device=raw.device, dtype=torch.float32)
         wn = torch.empty(R, D, device=raw.device, dtype=torch.float32)
         mm = torch.empty(R, device=raw.device, dtype=torch.float32) if render_mask else None
-        check(lib().uorf_composite_forward(raw_c.data_ptr(), z_c.data_ptr(), d_c.data_ptr(), R, Rg, D, rgb.data_ptr(),
-                                           depth.data_ptr(), wn.data_ptr(), _ptr(mm), _stream(raw)),
-              "uorf_composite_forward")
+        with _on(raw_c):
+            check(lib().uorf_composite_forward(raw_c.data_ptr(), z_c.data_ptr(), d_c.data_ptr(), R, Rg, D, rgb.data_ptr(),
+                                               depth.data_ptr(), wn.data_ptr(), _ptr(mm), _stream(raw)),
+                  "uorf_composite_forward")
         ctx.save_for_backward(raw_c, z_c, d_c)
         ctx.mark_non_differentiable(depth, wn)
         if render_mask:
@@ -252,8 +302,9 @@ class _Composite(torch.autograd.Function):
         R, D = raw_c.shape[0], raw_c.shape[1]
         g = _f32c(g_rgb)
         g_raw = torch.empty_like(raw_c)
-        check(lib().uorf_composite_backward(raw_c.data_ptr(), z_c.data_ptr(), d_c.data_ptr(), g.data_ptr(), R, z_c.shape[0], D,
-                                            g_raw.data_ptr(), _stream(raw_c)), "uorf_composite_backward")
+        with _on(raw_c):
+            check(lib().uorf_composite_backward(raw_c.data_ptr(), z_c.data_ptr(), d_c.data_ptr(), g.data_ptr(), R, z_c.shape[0], D,
+                                                g_raw.data_ptr(), _stream(raw_c)), "uorf_composite_backward")
         return g_raw, None, None, None
 
 
@@ -312,7 +363,9 @@ class Projection(object):
                           raw2outputs wants (no permute copy, reference uorf_eval_model.py:147);
           crop=(h0, w0)   only the render_size window at (h0, w0) (fine-stage training crop,
                           reference uorf_nogan_model.py:153-165), never materialising the full frustum;
-          crop=(h0, w0, Hc, Wc)  an arbitrary window (row blocks of one view when rays are sharded over GPUs).
+          crop=(h0, w0, Hc, Wc)  an arbitrary window (row blocks of one view when rays are sharded over GPUs);
+          crop=<CUDA int32 tensor (h0, w0)>  the render_size window at an origin that stays on the device
+                          (uorf_sample_coords_window: no host sync, so the fine-stage step is graph-capturable).
         """
         _require_cuda(cam2world)
         cam2world = _f32c(cam2world)
@@ -321,7 +374,18 @@ class Projection(object):
         dev = cam2world.device
         if self._z_cam.device != dev:
             self._z_cam = self._z_cam.to(dev)
-        if crop is not None:
+        crop_dev = None
+        if isinstance(crop, torch.Tensor):
+            # window origin (h0, w0) held on the device (int32, 2 elements): read and clamped by the kernel, no host sync
+            if partitioned:
+                raise ValueError("crop and partitioned are mutually exclusive")
+            if not crop.is_cuda or crop.dtype != torch.int32 or crop.numel() != 2 or not crop.is_contiguous():
+                raise ValueError("a device crop origin must be a contiguous CUDA int32 tensor (h0, w0)")
+            crop_dev = crop
+            scale, Hc, Wc, ch, cw = 1, int(self.render_size[0]), int(self.render_size[1]), 0, 0
+            if Hc > H or Wc > W:
+                raise ValueError(f"crop window {Hc}x{Wc} does not fit the {H}x{W} frustum")
+        elif crop is not None:
             if partitioned:
                 raise ValueError("crop and partitioned are mutually exclusive")
             scale, Hc, Wc = 1, int(self.render_size[0]), int(self.render_size[1])
@@ -339,9 +403,16 @@ class Projection(object):
         coords = torch.empty(nchunk, P, 3, device=dev, dtype=torch.float32)
         z_vals = torch.empty(nchunk, R, D, device=dev, dtype=torch.float32)
         ray_dir = torch.empty(nchunk, R, 3, device=dev, dtype=torch.float32)
-        check(lib().uorf_sample_coords(C.byref(self._frustum), self._z_cam.data_ptr(), cam2world.data_ptr(), N, scale, ch, cw,
-                                       Hc, Wc, 1 if ray_major else 0, coords.data_ptr(), z_vals.data_ptr(),
-                                       ray_dir.data_ptr(), _stream(cam2world)), "uorf_sample_coords")
+        with _on(cam2world):
+            if crop_dev is not None:
+                check(lib().uorf_sample_coords_window(C.byref(self._frustum), self._z_cam.data_ptr(), cam2world.data_ptr(), N,
+                                                      crop_dev.data_ptr(), Hc, Wc, 1 if ray_major else 0, coords.data_ptr(),
+                                                      z_vals.data_ptr(), ray_dir.data_ptr(), _stream(cam2world)),
+                      "uorf_sample_coords_window")
+            else:
+                check(lib().uorf_sample_coords(C.byref(self._frustum), self._z_cam.data_ptr(), cam2world.data_ptr(), N, scale, ch, cw,
+                                               Hc, Wc, 1 if ray_major else 0, coords.data_ptr(), z_vals.data_ptr(),
+                                               ray_dir.data_ptr(), _stream(cam2world)), "uorf_sample_coords")
         if partitioned:
             return coords, z_vals, ray_dir
         return coords[0], z_vals[0], ray_dir[0]
@@ -380,6 +451,8 @@ class SlotAttention(nn.Module):
         self.norm_feat = nn.LayerNorm(in_dim)
         self.slot_dim = slot_dim
         self.in_dim = in_dim
+        self.grad_sink = None     # {parameter name: tensor}: the backward kernels write parameter gradients there (see _grad_buffers)
+        self.noise_override = None   # (noise_fg, noise_bg) used when forward() gets no `noise` (a reference driver calls forward(feat))
 
     def _weights(self) -> _lib.SlotAttentionWeights:
         sd = dict(self.named_parameters())
@@ -401,10 +474,11 @@ class SlotAttention(nn.Module):
         slots = torch.empty(1, K, Cs, device=dev, dtype=torch.float32)
         attn = torch.empty(1, K, N, device=dev, dtype=torch.float32)
         w = self._weights()
-        check(lib().uorf_slot_attention_forward(C.byref(w), f0.data_ptr(), f0.stride(0), f0.stride(1), noise_fg.data_ptr(),
-                                                noise_bg.data_ptr(), N, Cs, K, self.hidden_dim, self.iters, float(self.eps),
-                                                ws.data_ptr(), slots.data_ptr(), attn.data_ptr(), _stream(feat)),
-              "uorf_slot_attention_forward")
+        with _on(feat):
+            check(lib().uorf_slot_attention_forward(C.byref(w), f0.data_ptr(), f0.stride(0), f0.stride(1), noise_fg.data_ptr(),
+                                                    noise_bg.data_ptr(), N, Cs, K, self.hidden_dim, self.iters, float(self.eps),
+                                                    ws.data_ptr(), slots.data_ptr(), attn.data_ptr(), _stream(feat)),
+                  "uorf_slot_attention_forward")
         return slots, attn, ws
 
     def _launch_backward(self, feat, K, noise_fg, noise_bg, fwd_ws, grad_slots):
@@ -415,7 +489,7 @@ class SlotAttention(nn.Module):
         f0 = feat[0]
         named = dict(self.named_parameters())
         # every parameter gradient is written in full by sa_bwd_reduce_kernel: no zero fill (34 launches per step)
-        grads = {n: torch.empty_like(p_, dtype=torch.float32, memory_format=torch.contiguous_format) for n, p_ in named.items()}
+        grads = _grad_buffers(named, self.grad_sink)
         g = _lib.SlotAttentionWeights()
         for field, key in _lib.SA_STATE_KEYS.items():
             setattr(g, field, grads[key].data_ptr())
@@ -423,10 +497,11 @@ class SlotAttention(nn.Module):
         ws = torch.empty(lib().uorf_slot_attention_backward_workspace_floats(N, Cs, K, self.hidden_dim), device=dev, dtype=torch.float32)
         gfeat = torch.empty(1, N, Cs, device=dev, dtype=torch.float32)
         gs = _f32c(grad_slots.reshape(K, Cs))
-        check(lib().uorf_slot_attention_backward(C.byref(w), C.byref(g), f0.data_ptr(), f0.stride(0), f0.stride(1),
-                                                 noise_fg.data_ptr(), noise_bg.data_ptr(), N, Cs, K, self.hidden_dim, self.iters,
-                                                 float(self.eps), fwd_ws.data_ptr(), gs.data_ptr(), ws.data_ptr(), gfeat.data_ptr(),
-                                                 _stream(feat)), "uorf_slot_attention_backward")
+        with _on(feat):
+            check(lib().uorf_slot_attention_backward(C.byref(w), C.byref(g), f0.data_ptr(), f0.stride(0), f0.stride(1),
+                                                     noise_fg.data_ptr(), noise_bg.data_ptr(), N, Cs, K, self.hidden_dim, self.iters,
+                                                     float(self.eps), fwd_ws.data_ptr(), gs.data_ptr(), ws.data_ptr(), gfeat.data_ptr(),
+                                                     _stream(feat)), "uorf_slot_attention_backward")
         return gfeat, grads
 
     def forward(self, feat, num_slots=None, noise=None):
@@ -444,6 +519,8 @@ class SlotAttention(nn.Module):
         if Cin != Cs:
             raise _lib.UorfError("in_dim must equal slot_dim (true for every reference configuration)")
         dev = feat.device
+        if noise is None:
+            noise = self.noise_override
         if noise is None:
             noise_fg = torch.randn(1, K - 1, Cs, device=dev)
             noise_bg = torch.randn(1, 1, Cs, device=dev)
@@ -474,6 +551,8 @@ class _SlotAttentionFn(torch.autograd.Function):
     def backward(ctx, g_slots, g_attn):
         feat, noise_fg, noise_bg, ws = ctx.saved_tensors
         gfeat, grads = ctx.module._launch_backward(feat, ctx.K, noise_fg, noise_bg, ws, g_slots)
+        if ctx.module.grad_sink is not None:
+            return (None, gfeat, None, None, None, None) + (None,) * len(ctx.names)
         return (None, gfeat, None, None, None, None) + tuple(grads[n] for n in ctx.names)
 
 
@@ -534,6 +613,7 @@ class Decoder(nn.Module):
         self.events = None   # set to a list to collect (start, end) CUDA events around the fused kernel
         self.events_bwd = None   # same for the backward call (composition-backward, main, reduce and unfold kernels)
         self.fg_slot_offset = None
+        self.grad_sink = None     # {parameter name: tensor}: the backward kernel writes parameter gradients there (see _grad_buffers)
 
     # ---- C-ABI plumbing ----
     def _weights(self) -> _lib.DecoderWeights:
@@ -569,8 +649,9 @@ class Decoder(nn.Module):
         image = torch.empty(nbytes + 1024, device=dev, dtype=torch.uint8)
         image_ptr = image.data_ptr() + (-image.data_ptr()) % 1024
         w = self._weights()
-        check(lib().uorf_decoder_prepare(C.byref(w), z.data_ptr(), K, Cz, self.n_freq, self.n_layers, prec, image_ptr,
-                                         stream), "uorf_decoder_prepare")
+        with _on(z):
+            check(lib().uorf_decoder_prepare(C.byref(w), z.data_ptr(), K, Cz, self.n_freq, self.n_layers, prec, image_ptr,
+                                             stream), "uorf_decoder_prepare")
         return image, image_ptr, w
 
     @staticmethod
@@ -621,7 +702,8 @@ class Decoder(nn.Module):
         if ev is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record(torch.cuda.current_stream(dev))
-        check(lib().uorf_decoder_forward(C.byref(a), stream), "uorf_decoder_forward")
+        with _on(coor_bg):
+            check(lib().uorf_decoder_forward(C.byref(a), stream), "uorf_decoder_forward")
         if ev is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record(torch.cuda.current_stream(dev))
@@ -638,7 +720,7 @@ class Decoder(nn.Module):
         stream = _stream(coor_bg)
         image, image_ptr, w = self._prepared_image(z, K, Cz, _lib.PREC_FP16, dev, stream)
         named = dict(self.named_parameters())
-        grads = {n: torch.empty_like(p_, dtype=torch.float32, memory_format=torch.contiguous_format) for n, p_ in named.items()}
+        grads = _grad_buffers(named, self.grad_sink)
         g = _lib.DecoderWeights()
         for i in range(3):
             g.f_before_w[i], g.f_before_b[i] = grads[f"f_before.{2 * i}.weight"].data_ptr(), grads[f"f_before.{2 * i}.bias"].data_ptr()
@@ -667,7 +749,8 @@ class Decoder(nn.Module):
         if evb is not None:
             e0 = torch.cuda.Event(enable_timing=True)
             e0.record(torch.cuda.current_stream(dev))
-        check(lib().uorf_decoder_backward(C.byref(w), C.byref(g), C.byref(a), stream), "uorf_decoder_backward")
+        with _on(coor_bg):
+            check(lib().uorf_decoder_backward(C.byref(w), C.byref(g), C.byref(a), stream), "uorf_decoder_backward")
         if evb is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record(torch.cuda.current_stream(dev))
@@ -719,4 +802,6 @@ class _DecoderFn(torch.autograd.Function):
         coor_bg, coor_fg, fg_transform, z_slots, unmasked = ctx.saved_tensors
         gz, grads = ctx.module._launch_backward(coor_bg, coor_fg, z_slots, fg_transform, ctx.dens_noise, ctx.noise, unmasked,
                                                 g_raws)
+        if ctx.module.grad_sink is not None:
+            return (None, None, None, None, None, None, None, gz) + (None,) * len(ctx.names)
         return (None, None, None, None, None, None, None, gz) + tuple(grads[n] for n in ctx.names)

@@ -34,7 +34,7 @@ def default_train_options(**over) -> argparse.Namespace:
                              percept_in=100, no_locality_epoch=300, bottom=False, input_size=64, frustum_size=64,
                              frustum_size_fine=128, attn_decay_steps=2e5, coarse_epoch=600, near_plane=6.0, far_plane=20.0,
                              fixed_locality=False, dens_noise=1.0, lr=3e-4, stage="coarse", n_img_each_scene=4, gpu_ids=[0],
-                             isTrain=True, vgg_weights=None)
+                             isTrain=True, vgg_weights=None, vgg_random_init=False)
     for k, v in over.items():
         setattr(opt, k, v)
     return opt
@@ -49,13 +49,19 @@ def exp_decay_schedule_with_warmup(optimizer, num_warmup_steps, num_decay_steps=
     return LambdaLR(optimizer, lr_lambda)
 
 
-def perceptual_net(weights_path: Optional[str] = None) -> nn.Module:
+def perceptual_net(weights_path: Optional[str] = None, allow_random_init: bool = False) -> nn.Module:
     """reference models/model.py:316-324: frozen VGG16 features[:23] (through relu4_3).  The reference downloads the ImageNet
-    weights; there is no network here, so they are loaded from `weights_path` when given and randomly initialised otherwise."""
+    weights (vgg16(pretrained=True)); there is no network here, so they are loaded from `weights_path` (a torchvision vgg16
+    state dict).  Without a path the call raises - a randomly initialised VGG silently changes the training objective -
+    unless `allow_random_init` is set (opt.vgg_random_init: benchmarks and parity tests, where only the arithmetic matters)."""
     from torchvision.models import vgg16
     vgg = vgg16(weights=None)
     if weights_path:
         vgg.load_state_dict(torch.load(weights_path, map_location="cpu"))
+    elif not allow_random_init:
+        raise RuntimeError("the perceptual loss needs the ImageNet VGG16 weights: set opt.vgg_weights to a torchvision vgg16 state dict "
+                           "(the reference downloads them, models/model.py:320), pass with_perceptual=False / weight_percept=0, or opt in "
+                           "to a randomly initialised network with opt.vgg_random_init=True (benchmarks and tests only)")
     net = nn.Sequential(*list(vgg.features)[:23]).eval()
     for p in net.parameters():
         p.requires_grad = False
@@ -78,8 +84,11 @@ class uorfNoGanModel:
         self.loss_names = ["recon", "perc"]
         self.model_names = ["Encoder", "SlotAttention", "Decoder"]
         self.with_perceptual = with_perceptual
+        if with_perceptual and float(getattr(opt, "weight_percept", 0)) <= 0:
+            self.with_perceptual = with_perceptual = False      # the term is multiplied by zero for the whole schedule (:181-183)
         if with_perceptual:
-            self.perceptual_net = perceptual_net(getattr(opt, "vgg_weights", None)).to(self.device)
+            self.perceptual_net = perceptual_net(getattr(opt, "vgg_weights", None),
+                                                 bool(getattr(opt, "vgg_random_init", False))).to(self.device)
             self._vgg_mean = torch.tensor([0.485, 0.456, 0.406], device=self.device).view(1, 3, 1, 1)
             self._vgg_std = torch.tensor([0.229, 0.224, 0.225], device=self.device).view(1, 3, 1, 1)
         render_size = (opt.render_size, opt.render_size)
@@ -119,6 +128,7 @@ class uorfNoGanModel:
         self.slot_noise = None        # (noise_fg, noise_bg) overrides the randn draws of SlotAttention
         self.crop_override = None     # (h0, w0) overrides the fine-stage randint draws
         self.process_group = None     # set (with world size > 1) for data-parallel training
+        self._flat_grad = None        # data-parallel mode: the flat gradient bucket every .grad is a view of
 
     def parameters(self):
         return chain(self.netEncoder.parameters(), self.netSlotAttention.parameters(), self.netDecoder.parameters())
@@ -156,14 +166,20 @@ class uorfNoGanModel:
             coords, z_vals, ray_dir = self.projection.construct_sampling_coor(cam2world, ray_major=True)
             x = F.interpolate(self.x, size=opt.supervision_size, mode="bilinear", align_corners=False)
         else:
+            # The crop origin never visits the host: the two draws stay on the device (same generator calls, after the slot
+            # noise, as the reference :160-161), the sampling kernel reads them there (uorf_sample_coords_window) and the
+            # supervision patch is gathered with device indices - the reference's slicing by a device scalar (:162-165) is a
+            # host sync per step, and the reason its fine stage cannot be graph-captured.
             if self.crop_override is not None:
-                h0, w0 = int(self.crop_override[0]), int(self.crop_override[1])
-            else:   # same two device draws, after the slot noise, as the reference (:160-161); .item() is the sync its slicing implies
+                origin = torch.as_tensor(self.crop_override, dtype=torch.int32).reshape(2).to(dev, non_blocking=True)
+            else:
                 start_range = opt.frustum_size_fine - rs
-                h0 = int(torch.randint(low=0, high=start_range, size=(1,), device=dev).item())
-                w0 = int(torch.randint(low=0, high=start_range, size=(1,), device=dev).item())
-            x = self.x[:, :, h0:h0 + rs, w0:w0 + rs]
-            coords, z_vals, ray_dir = self.projection_fine.construct_sampling_coor(cam2world, ray_major=True, crop=(h0, w0))
+                origin = torch.cat([torch.randint(low=0, high=start_range, size=(1,), device=dev),
+                                    torch.randint(low=0, high=start_range, size=(1,), device=dev)]).to(torch.int32)
+            self.crop_origin = origin
+            span = self._crop_span(rs)
+            x = self.x.index_select(2, span + origin[0]).index_select(3, span + origin[1])
+            coords, z_vals, ray_dir = self.projection_fine.construct_sampling_coor(cam2world, ray_major=True, crop=origin)
         self.z_vals, self.ray_dir = z_vals, ray_dir
         W = H = opt.supervision_size
         raws, masked_raws, unmasked_raws, _ = self.netDecoder(coords, coords[None, ...].expand(K - 1, -1, -1), z_slots, self.nss2cam0,
@@ -218,6 +234,11 @@ class uorfNoGanModel:
             for k in range(K):
                 setattr(self, f"slot{k}_attn", a[k] * 2 - 1)
 
+    def _crop_span(self, rs):
+        if getattr(self, "_span", None) is None or self._span.numel() != rs:
+            self._span = torch.arange(rs, device=self.device, dtype=torch.int32)
+        return self._span
+
     def _extra_generator_loss(self, x_recon, x, epoch):
         return None
 
@@ -238,8 +259,9 @@ class uorfNoGanModel:
         exist before capture), captures forward + backward + Adam into ONE CUDA graph and replays it from then on: ~460 small
         launches (Encoder, VGG, slot attention, Adam, losses) stop costing host time and inter-kernel gaps.  Inputs are
         copied into static buffers; a change of the epoch-dependent constants (perceptual weight, density noise, locality)
-        or of the input shapes re-captures.  Coarse stage only (the fine stage draws its crop window on the host every
-        step).  With a process group set, the flat gradient all-reduce (NCCL) is captured inside the same graph."""
+        or of the input shapes re-captures.  Coarse and fine stage alike: the fine-stage crop origin is drawn, read and applied
+        on the device (forward()), and the generator's Philox offset advances with every replay, so each replayed step crops a
+        new window.  With a process group set, the flat gradient all-reduce (NCCL) is captured inside the same graph."""
         if enabled and not self._capturable:
             raise RuntimeError("construct the model with opt.cuda_graph=True (capturable Adam) to use enable_cuda_graph()")
         self._graph_enabled, self._graph, self._graph_key, self._graph_warm = bool(enabled), None, None, 0
@@ -268,8 +290,9 @@ class uorfNoGanModel:
             # drop every reference to the previous step's autograd graph (its AccumulateGrad nodes belong to the eager
             # stream and would invalidate the capture) and let the captured backward allocate .grad in the graph's pool
             self.loss_recon = self.loss_perc = None
-            for p_ in self.parameters():
-                p_.grad = None
+            if self.process_group is None:     # (data-parallel mode keeps its persistent flat gradient views)
+                for p_ in self.parameters():
+                    p_.grad = None
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             # thread-local capture mode: the NCCL watchdog thread of a data-parallel run may touch the CUDA API meanwhile
@@ -281,20 +304,35 @@ class uorfNoGanModel:
         return [], []
 
     def optimize_parameters(self, ret_grad=False, epoch=0):
-        if self._graph_enabled and not ret_grad and self.opt.stage == "coarse":
+        if self._graph_enabled and not ret_grad:
             return self._step_graphed(epoch)
         return self._step_eager(ret_grad, epoch)
 
+    def _flat_gradients(self):
+        """Data-parallel mode: ONE persistent flat fp32 buffer holds every gradient; each `.grad` is a view of its slice and the
+        backward kernels write there directly (`grad_sink`), so the step issues exactly one all-reduce (average) over the
+        buffer - no torch.cat, no division pass, no per-tensor copy back (one flat-bucket ncclAllReduce)."""
+        if self._flat_grad is None:
+            from .sharded import flatten_gradients
+            self._flat_grad = flatten_gradients(list(self.parameters()))
+            for net in (self.netEncoder, self.netSlotAttention, self.netDecoder):
+                net.grad_sink = {n: p_.grad for n, p_ in net.named_parameters()}
+        return self._flat_grad
+
     def _step_eager(self, ret_grad=False, epoch=0):
         self.forward(epoch)
-        # optimizer.zero_grad() of the reference (:235-236, zero in place): one multi-tensor launch instead of one fill per tensor
-        grads = [p.grad for p in self.parameters() if p.grad is not None]
-        if grads:
-            torch._foreach_zero_(grads)
-        self.backward()
         if self.process_group is not None:
-            from .sharded import allreduce_gradients
-            allreduce_gradients(list(self.parameters()), self.process_group)
+            flat = self._flat_gradients()
+            flat.zero_()               # one fill; the kernels overwrite their slices, anything routed through autograd accumulates
+            self.backward()
+            from .sharded import allreduce_flat
+            allreduce_flat(flat, self.process_group)
+        else:
+            # optimizer.zero_grad() of the reference (:235-236, zero in place): one multi-tensor launch instead of one fill per tensor
+            grads = [p.grad for p in self.parameters() if p.grad is not None]
+            if grads:
+                torch._foreach_zero_(grads)
+            self.backward()
         layers, avg_grads = [], []
         if ret_grad:
             for n, p in self.named_parameters():
@@ -324,6 +362,9 @@ class uorfNoGanModel:
             torch.save(sch.state_dict(), os.path.join(save_dir, f"{suffix}_lr_scheduler_{i}.pth"))
 
     def load_networks(self, save_dir, suffix="latest", with_optimizer=True):
+        # a captured step holds the old optimizer state / lr tensors: capture again after the load
+        self._graph, self._graph_key, self._graph_warm = None, None, 0
+        self.netEncoder._wt.clear()
         for name in self.model_names:
             sd = torch.load(os.path.join(save_dir, f"{suffix}_net_{name}.pth"), map_location=str(self.device))
             getattr(self, "net" + name).load_state_dict(sd, strict=False)

@@ -84,25 +84,49 @@ def sharded_render_rows(encode_fn: Callable[[], torch.Tensor], render_rows_fn: C
 
 
 class GraphedShardedRender:
-    """encode (rank 0) -> NCCL broadcast of the slot latents -> rank-local render, captured as ONE CUDA graph per rank.
+    """encode (rank 0) -> NCCL broadcast of the slot latents -> rank-local render [-> all-gather of the image tiles], captured as
+    ONE CUDA graph per rank.
 
     The eager form of this step costs rank 0 about 60 small launches (encoder, slot attention) and every rank a separate
     broadcast launch per scene; replaying it as a graph (NCCL collectives are capturable) removes that host time from the
     multi-GPU step.  `model` is a uorfEvalModel whose set_input() has been called with THIS rank's views (rank 0 must hold
-    view 0's image); shapes must stay fixed after the first call."""
+    view 0's image); shapes must stay fixed after the first call.
 
-    def __init__(self, model, K: int, C: int, group=None):
+      rows=(h0, h1)     this rank renders image rows h0..h1-1 of every view (rays of ONE scene sharded over ranks: the 256^2 x 128
+                        manipulation render, reference models/uorf_manip_model.py:196-232) instead of whole views;
+      fg_slot_offset    (K-1)x3 per-object translation of the moved-object render (static tensor, read at replay time);
+      gather=True       the rendered tiles of all ranks are all-gathered inside the graph: every rank ends the step holding
+                        the full image set (`out['full']`: views sharded -> (world*N)x3xHxW, rows sharded -> Nx3xHxW).
+    `release()` drops the graph (and with it its references to the NCCL communicator) before the process group is destroyed."""
+
+    def __init__(self, model, K: int, C: int, group=None, rows=None, fg_slot_offset=None, gather: bool = False, height=None):
         self.model, self.K, self.C, self.group = model, K, C, group
+        self.rows, self.fg_slot_offset, self.gather, self.height = rows, fg_slot_offset, gather, height
         self.graph, self.static, self.out = None, None, None
 
     def _body(self):
         m, st = self.model, self.static
-        rank = dist.get_rank(self.group)
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
         with torch.no_grad():
             m.x = st["x"]
             z = m.encode()[0] if rank == 0 else torch.empty(self.K, self.C, device=st["x"].device)
-            z = broadcast_slots(z, self.K, self.C, z.device, 0, self.group)
-            return m.render(z, st["c2w"], st["T"])
+            if world > 1:
+                z = broadcast_slots(z, self.K, self.C, z.device, 0, self.group)
+            out = m.render(z, st["c2w"], st["T"], fg_slot_offset=self.fg_slot_offset, rows=self.rows)
+            if self.gather:
+                local = out["rendered"].contiguous()
+                if world == 1:
+                    out["full"] = local
+                else:
+                    n = local.shape[0]
+                    stacked = torch.empty((world * n,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+                    dist.all_gather_into_tensor(stacked, local, group=self.group)
+                    if self.rows is None:
+                        out["full"] = stacked
+                    else:   # [world*N, 3, h, W] -> N x 3 x (world*h) x W
+                        out["full"] = stacked.view((world, n) + tuple(local.shape[1:])).permute(1, 2, 0, 3, 4).reshape(
+                            n, local.shape[1], world * local.shape[2], local.shape[3])
+            return out
 
     def __call__(self):
         m = self.model
@@ -129,6 +153,15 @@ class GraphedShardedRender:
         self.graph.replay()
         return self.out
 
+    def run_eager(self):
+        """the same step launched eagerly on the model's current inputs (no graph)"""
+        m = self.model
+        self.static = {"x": m.x, "c2w": m.cam2world, "T": m.nss2cam0}
+        return self._body()
+
+    def release(self):
+        self.graph, self.out, self.static = None, None, None
+
 
 def allreduce_gradients(params, group=None, average: bool = True) -> None:
     """Data-parallel training: scenes are sharded over ranks, weights replicated; after backward
@@ -150,3 +183,31 @@ def allreduce_gradients(params, group=None, average: bool = True) -> None:
         n = g.numel()
         g.copy_(flat[off:off + n].view_as(g))
         off += n
+
+
+def flatten_gradients(params) -> torch.Tensor:
+    """One flat fp32 buffer for all gradients; every `p.grad` becomes a view of its slice (16-byte aligned slices, so the
+    backward kernels' vector stores and the fused optimizer's multi-tensor loads stay aligned).  Returns the buffer."""
+    params = [p for p in params if p.requires_grad]
+    offs, total = [], 0
+    for p in params:
+        offs.append(total)
+        total += (p.numel() + 3) // 4 * 4
+    flat = torch.zeros(total, device=params[0].device, dtype=torch.float32)
+    for p, o in zip(params, offs):
+        p.grad = flat[o:o + p.numel()].view(p.shape)
+    return flat
+
+
+def allreduce_flat(flat: torch.Tensor, group=None, average: bool = True) -> None:
+    """the data-parallel exchange: ONE all-reduce over the flat gradient buffer (NCCL: the average is taken inside the
+    collective; gloo has no AVG, so the CPU test path divides afterwards)"""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return
+    if average and dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+        return
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= world
