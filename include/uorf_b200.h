@@ -128,7 +128,7 @@ typedef struct uorf_decoder_args {
   int32_t K;
   int32_t precision;        /* UORF_PREC_* */
   const void* image;        /* from uorf_decoder_prepare (same K, precision) */
-  float* workspace;         /* [P][4] floats scratch */
+  float* workspace;         /* uorf_decoder_forward_workspace_floats(P, K) floats of scratch */
   /* outputs; any may be NULL to skip the write */
   float* raws;              /* [P][4] */
   float* masked_raws;       /* [K][P][4] */
@@ -140,6 +140,8 @@ typedef struct uorf_decoder_args {
                                   without materialising its (K-1)xPx3 clone of the coordinates. */
 } uorf_decoder_args;
 
+/* Floats of scratch uorf_decoder_forward needs (background sweep results + the per-tile head stash). */
+size_t uorf_decoder_forward_workspace_floats(int64_t P, int32_t K);
 int uorf_decoder_forward(const uorf_decoder_args* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -104,6 +104,7 @@ _SIGNATURES = {
     "uorf_decoder_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "uorf_decoder_prepare": (C.c_int, [C.POINTER(DecoderWeights), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_void_p]),
+    "uorf_decoder_forward_workspace_floats": (C.c_size_t, [C.c_int64, C.c_int32]),
     "uorf_decoder_forward": (C.c_int, [C.POINTER(DecoderArgs), C.c_void_p]),
     "uorf_decoder_backward_workspace_floats": (C.c_size_t, [C.c_int64, C.c_int32]),
     "uorf_decoder_backward": (C.c_int, [C.POINTER(DecoderWeights), C.POINTER(DecoderWeights), C.POINTER(DecoderBwdArgs), C.c_void_p]),

@@ -20,6 +20,7 @@ int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* sr
 int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int K, int Z, int passes, int f16, void* image,
                         cudaStream_t stream);
 int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, cudaStream_t stream);
+size_t decoder_fwd_workspace_floats(long long P, int K, int num_sms);
 int launch_composite_fwd(const float* raw, const float* z_vals, const float* rays_d, long long R, long long Rg, int D, float* rgb_map,
                          float* depth_map, float* weights_norm, float* mask_map, int num_sms, cudaStream_t stream);
 int launch_composite_bwd(const float* raw, const float* z_vals, const float* rays_d, const float* grad_rgb, long long R, long long Rg, int D,
@@ -225,6 +226,12 @@ int uorf_decoder_prepare(const uorf_decoder_weights* w, const float* z_slots, in
   if (n_freq != 5 || n_layers != 3) return fail(UORF_ERR_UNSUPPORTED, "uorf_decoder_prepare: only n_freq=5, n_layers=3 (all shipped configs)%s");
   return check_launch(uorf::launch_decoder_prep(w, z_slots, K, Z, prec_passes(precision), prec_f16(precision), image, static_cast<cudaStream_t>(stream)),
                       "uorf_decoder_prepare");
+}
+
+size_t uorf_decoder_forward_workspace_floats(int64_t P, int32_t K) {
+  DeviceCtx* c = ctx();
+  if (!c || P < 0 || K < 2) return 0;
+  return uorf::decoder_fwd_workspace_floats(P, K, c->num_sms);
 }
 
 int uorf_decoder_forward(const uorf_decoder_args* a, void* stream) {

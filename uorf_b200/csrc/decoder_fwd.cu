@@ -8,9 +8,14 @@
 //
 // Structure: one persistent CTA per SM, epilogue warps grouped into NCH "channels" + one MMA-issuer warp per channel.
 //   A channel owns one 128-point tile at a time and walks it through bg MLP / the K-1 fg slots.  Thread <-> TMEM lane <-> point.
-//     3-pass modes : NCH = 3 channels x 8 warps (2 when K > 13); the two warps sharing a lane quadrant split the 64 feature
-//                    columns.  TMEM: accumulators D at 64c, operand blocks at 192 + 104c = H hi 32 | H lo 32 | P hi 16 | P lo 16 | 8 spare.
+//     3-pass modes : NCH = 4 channels x 4 warps, one thread per point (PSM variant, the default).  TMEM per channel: D 64 | H hi 32 |
+//                    H lo 32 = 128 columns, so FOUR tiles are in flight in the 512 columns.  The positional-encoding operand P
+//                    (2 of a slot's 26 K-steps) lives in SHARED memory instead (one 16 KB strip per channel: 128 rows x [hi 32 | lo 32]
+//                    16-bit elements, K-major, 128-byte swizzle, written by the epilogue threads with st.shared + fence.proxy.async) and
+//                    is the A operand of SS MMAs (52 instead of 34.6 cycles, for those two K-steps only); the per-slot head results
+//                    are stashed in a small L2-resident global buffer instead of shared memory.
 //                    Only 32 of the 33 encoding elements go through the tensor core; cos(16 z) is an fp32 FMA in the epilogue.
+//                    (Previous form, kept as -DUORF_FWD_X3_LEGACY: 3 channels x 8 warps, P in TMEM, 160 columns per channel.)
 //     1-pass modes : NCH = 4 channels x 4 warps (TMEM per channel: D 64 | H 32 | P 24 | selector 8 columns)
 //   warp EPI + c    MMA issuer of channel c (elected lane issues tcgen05.mma); the first issuer warp also owns TMEM alloc and the
 //                   weight bulk copies.  One issuer per channel keeps the channels out of lock-step: while one channel is in
@@ -69,29 +74,32 @@ namespace uorf {
 constexpr int kTileM = 128;
 constexpr int kTmemCols = 512;
 
-template <int PASSES, int NCH_>
+template <int PASSES, int NCH_, bool PSM_ = false>
 struct Cfg {
-  static constexpr int NCH = NCH_;                      // channels: 4 (1-pass), 3 or 2 (3-pass; 2 when K > 13 needs the shared memory)
-  static constexpr int CS = PASSES == 3 ? 2 : 1;        // threads per point (column split)
+  static constexpr int NCH = NCH_;                      // channels (tiles in flight): 4 (1-pass; 3-pass PSM), legacy 3-pass: 3 or 2
+  static constexpr bool PSM = PSM_;                     // positional-encoding operand in shared memory (A of SS MMAs), stash in global
+  static constexpr int CS = (PASSES == 3 && !PSM) ? 2 : 1;   // threads per point (column split)
   static constexpr int WPC = 4 * CS;                    // warps per channel
-  static constexpr int EPI_WARPS = NCH * WPC;           // 16 (1-pass), 24 / 16 (3-pass)
+  static constexpr int EPI_WARPS = NCH * WPC;           // 16 (1-pass, PSM), 24 / 16 (legacy 3-pass)
   static constexpr int THREADS = (EPI_WARPS + NCH) * 32;
   static constexpr int NKP = PASSES == 3 ? 2 : 3;       // K-steps of the positional-encoding operand (3-pass: elements 0..31
                                                         // on the tensor core, element 32 by an fp32 FMA in the epilogue)
   // TMEM map.  1-pass: channel c owns columns 128c .. 128c+127 = D 64 | H 32 | P 24 | selector 8.
-  // 3-pass: accumulators first (D of channel c at 64c), then one 104-column operand block per channel at 192 + 104c =
+  // 3-pass PSM: channel c owns 128c .. 128c+127 = D 64 | H hi 32 | H lo 32.
+  // 3-pass legacy: accumulators first (D of channel c at 64c), then one 104-column operand block per channel at 192 + 104c =
   //         H hi 32 | H lo 32 | P hi 16 | P lo 16 | selector 8   (3 x 64 + 3 x 104 = 504 <= 512 columns)
-  static constexpr int d_col(int c) { return PASSES == 3 ? 64 * c : 128 * c; }
-  static constexpr int a_col(int c) { return PASSES == 3 ? 192 + 104 * c : 128 * c + 64; }
+  static constexpr int d_col(int c) { return (PASSES == 3 && !PSM) ? 64 * c : 128 * c; }
+  static constexpr int a_col(int c) { return (PASSES == 3 && !PSM) ? 192 + 104 * c : 128 * c + 64; }
   static constexpr int COL_HHI = 0;                     // offsets inside the operand block
   static constexpr int COL_HLO = 32;                    // 3-pass only
-  static constexpr int COL_PHI = PASSES == 3 ? 64 : 32;
-  static constexpr int COL_PLO = 80;                    // 3-pass only
-  static constexpr int COL_SEL = PASSES == 3 ? 96 : 56; // 8 columns: one-hot K-step that selects a bias column
+  static constexpr int COL_PHI = PASSES == 3 ? 64 : 32; // (not with PSM)
+  static constexpr int COL_PLO = 80;                    // legacy 3-pass only
+  static constexpr int COL_SEL = PASSES == 3 ? 96 : 56; // 8 columns: one-hot K-step that selects a bias column (not with PSM)
   static constexpr int NPL = PASSES == 3 ? 2 : 1;       // weight planes
   // bias through the tensor core (selector MMA) pays off where the epilogue is the bottleneck (1-pass modes); in the 3-pass
   // modes the extra MMAs lengthen the dependent chain more than two FADDs per pair cost, so the bias stays in the epilogue
-  static constexpr bool BIAS_MMA = PASSES == 1 || UORF_X3_BIAS_MMA;
+  static constexpr bool BIAS_MMA = !PSM && (PASSES == 1 || UORF_X3_BIAS_MMA);
+  static constexpr int kStripBytes = kTileM * 128;      // PSM: one P strip (128 rows x 128 B)
 };
 
 struct DecFwdParams {
@@ -101,6 +109,7 @@ struct DecFwdParams {
   const float* noise;
   const unsigned char* image;
   float4* scratch_bg;
+  float4* stash_g;      // PSM variant: [grid][NCH][K][128] per-slot head results (L2-resident, rewritten every tile)
   float4* raws;
   float4* masked;
   float4* unmasked;
@@ -179,6 +188,23 @@ __device__ __forceinline__ void posenc_store(const float (&v)[kPosencK], uint32_
     tmem_st16(t_phi + W0, hi);
     tmem_st8(t_phi + W0 + 16, hi + 16);
     if (PASSES == 3) { tmem_st16(t_plo + W0, lo); tmem_st8(t_plo + W0 + 16, lo + 16); }
+  }
+}
+
+// PSM: elements 0..31 of the encoding as one 128-byte K-major row [hi 32 | lo 32] of the channel's shared-memory strip
+// (row t at (t / 8) * 1024 + (t % 8) * 128, 16-byte chunk c stored at chunk c ^ (t & 7): the layout make_sdesc_sw128 describes).
+// Lanes t .. t+7 of a quarter warp hit 8 different chunk positions: the 16-byte stores are bank-conflict free.
+template <bool F16>
+__device__ __forceinline__ void posenc_store_smem(const float (&v)[kPosencK], unsigned char* strip, int t) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) split2<F16>(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+  unsigned char* row = strip + (t >> 3) * 1024 + (t & 7) * 128;
+  const int sw = t & 7;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+    *reinterpret_cast<uint4*>(row + (((4 + c) ^ sw) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
   }
 }
 
@@ -321,15 +347,31 @@ __device__ __forceinline__ void mma_group_ts(uint32_t d, uint32_t a_hi, uint32_t
   }
 }
 #undef UORF_MMA
+// PSM: D (+)= P[smem strip] . W[tile]^T for the two encoding K-steps, three passes, both operands from shared memory (SS).
+// Strip row = [hi K-steps 0,1 | lo K-steps 2,3]; descriptors advance by 2 (32 bytes >> 4) per K-step.
+#define UORF_MMA_SS(A, B, ACC) "@e tcgen05.mma.cta_group::1.kind::f16 [%0], " A ", " B ", %4, " ACC ";\n\t"
+__device__ __forceinline__ void mma_group_p_ss(uint32_t d, uint64_t a, uint64_t b_hi, uint64_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred e, p, t;\n\t.reg .b64 a1, a2, a3, h1, w1;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\tsetp.eq.b32 t, %5, %5;\n\t"
+      "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+      "add.u64 h1, %2, 2;\n\tadd.u64 w1, %3, 2;\n\t"
+      UORF_MMA_SS("%1", "%2", "p") UORF_MMA_SS("a1", "h1", "t")      // p_hi . w_hi
+      UORF_MMA_SS("a2", "%2", "t") UORF_MMA_SS("a3", "h1", "t")      // p_lo . w_hi
+      UORF_MMA_SS("%1", "%3", "t") UORF_MMA_SS("a1", "w1", "t")      // p_hi . w_lo
+      "}" ::"r"(d), "l"(a), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate) : "memory");
+}
+#undef UORF_MMA_SS
 template <int NK, int PASSES>
 __device__ __forceinline__ void issue_group(uint32_t t_d, uint32_t t_ahi, uint32_t t_alo, uint32_t w_smem, uint32_t idesc, bool& first) {
   mma_group_ts<NK, PASSES>(t_d, t_ahi, t_alo, make_sdesc_sw128(w_smem), make_sdesc_sw128(w_smem + kPlaneBytes), idesc, first ? 0u : 1u);
   first = false;
 }
 
-template <int PASSES, bool F16, int NCH>
-__global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kernel(const DecFwdParams p) {
-  using C = Cfg<PASSES, NCH>;
+template <int PASSES, bool F16, int NCH, bool PSM = false>
+__global__ void __launch_bounds__(Cfg<PASSES, NCH, PSM>::THREADS, 1) decoder_fwd_kernel(const DecFwdParams p) {
+  using C = Cfg<PASSES, NCH, PSM>;
   constexpr int kEpiWarps = C::EPI_WARPS;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_w;
@@ -343,7 +385,8 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
   const int K = p.K;
   const int w_region = C::NPL * kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
   const float* s_params = reinterpret_cast<const float*>(smem + C::NPL * kPlaneBytes);
-  float4* s_stash = reinterpret_cast<float4*>(smem + ((w_region + 127) & ~127));  // [NCH][K][128]
+  float4* s_stash = reinterpret_cast<float4*>(smem + ((w_region + 127) & ~127));  // [NCH][K][128]   (not PSM)
+  unsigned char* s_strips = smem + ((w_region + 1023) & ~1023);                   // [NCH][128 rows x 128 B] (PSM)
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
@@ -428,8 +471,17 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
             if (PASSES == 3) mma_ts_elect(t_d, tb + C::COL_SEL, make_sdesc_sw128(w_smem + kPlaneBytes + kBiasTileOff) + 2 * (bid >> 4), idesc64, 1u);
             first = false;
           }
-          if constexpr (st == 0) {
+          if constexpr (st == 0 && PSM) {
+            mma_group_p_ss(t_d, make_sdesc_sw128(smem_u32(s_strips) + c * C::kStripBytes), make_sdesc_sw128(w_smem + 0 * kTileBytes),
+                           make_sdesc_sw128(w_smem + kPlaneBytes + 0 * kTileBytes), idesc64, first ? 0u : 1u);
+            first = false;
+          } else if constexpr (st == 0) {
             issue_group<C::NKP, PASSES>(t_d, t_p, t_pl, w_smem + 0 * kTileBytes, idesc64, first);
+          } else if constexpr (st == 3 && PSM) {
+            mma_group_p_ss(t_d, make_sdesc_sw128(smem_u32(s_strips) + c * C::kStripBytes), make_sdesc_sw128(w_smem + 3 * kTileBytes),
+                           make_sdesc_sw128(w_smem + kPlaneBytes + 3 * kTileBytes), idesc64, first ? 0u : 1u);
+            first = false;
+            issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 4 * kTileBytes, idesc64, first);
           } else if constexpr (st == 3) {
             issue_group<C::NKP, PASSES>(t_d, t_p, t_pl, w_smem + 3 * kTileBytes, idesc64, first);
             issue_group<4, PASSES>(t_d, t_h, t_hl, w_smem + 4 * kTileBytes, idesc64, first);
@@ -466,10 +518,13 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
       const int half = wic >> 2;              // which half of the feature columns (3-pass modes); 0 otherwise
       const int t = (wic & 3) * 32 + lane;    // point within the tile == TMEM lane
       const uint32_t lane_bits = (uint32_t)((warp & 3) * 32) << 16;
-      const uint32_t tbd = tmem_base + (PASSES == 3 ? 64 * ch : 128 * ch) + lane_bits;             // accumulator
-      const uint32_t tb = tmem_base + (PASSES == 3 ? 192 + 104 * ch : 128 * ch + 64) + lane_bits;  // operand block
+      const uint32_t tbd = tmem_base + C::d_col(ch) + lane_bits;             // accumulator
+      const uint32_t tb = tmem_base + C::a_col(ch) + lane_bits;              // operand block
       ChanBars& cb = bars[ch];
-      float4* stash = s_stash + (size_t)ch * K * kTileM;
+      // per-slot head results of the tile in flight: shared memory, or (PSM) this channel's slice of a global buffer - each
+      // thread only ever reads back what it wrote itself, so no fence is needed, and the 10-40 KB stay L2-resident
+      float4* stash = PSM ? p.stash_g + ((size_t)blockIdx.x * C::NCH + ch) * K * kTileM : s_stash + (size_t)ch * K * kTileM;
+      unsigned char* strip = s_strips + ch * C::kStripBytes;
       constexpr int NCOL = 64 / C::CS;        // accumulator columns this thread owns per hidden layer
       const int col0 = half * NCOL;
       // wait for the MMAs of the current stage
@@ -533,7 +588,10 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
             }
             float v[kPosencK];
             posenc48<PASSES == 1>(x, y, z, v);
-            if (C::CS == 1) {
+            if constexpr (PSM) {
+              posenc_store_smem<F16>(v, strip, t);
+              fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+            } else if (C::CS == 1) {
               posenc_store<PASSES, F16, 0, 24>(v, tb + C::COL_PHI, tb + C::COL_PLO);
             } else if (half == 0) {
               posenc_store<PASSES, F16, 0, 8>(v, tb + C::COL_PHI, tb + C::COL_PLO);
@@ -615,10 +673,12 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
           if (half == 0 && valid) stash[t] = p.scratch_bg[pt];
           if (C::CS == 2) named_bar_sync(1 + ch * 4 + (wic & 3), 64);  // head results of the partner warp are visible
           float S = 0.f;
+#pragma unroll 4
           for (int k = 0; k < K; ++k) S += fmaxf(stash[k * kTileM + t].w, 0.f);
           const float denom = S + 1e-5f;
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           const bool want_sum = half == 0 && p.raws != nullptr;
+#pragma unroll 2
           for (int k = 0; k < K; ++k) {
             const bool mine = C::CS == 1 || (k & 1) == half;
             if (!mine && !want_sum) continue;
@@ -652,10 +712,24 @@ __global__ void __launch_bounds__(Cfg<PASSES, NCH>::THREADS, 1) decoder_fwd_kern
   if (warp == kEpiWarps) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-static size_t decoder_smem_bytes(int passes, int K, int nch) {
+static size_t decoder_smem_bytes(int passes, int K, int nch, bool psm) {
   const int npl = passes == 3 ? 2 : 1;
   const int w_region = npl * kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
+  if (psm) return 1024 + ((w_region + 1023) & ~1023) + (size_t)nch * kTileM * 128;
   return 1024 + ((w_region + 127) & ~127) + (size_t)nch * K * kTileM * sizeof(float4);
+}
+
+// 3-pass modes: the four-channel PSM variant unless the library is built with -DUORF_FWD_X3_LEGACY (tuning / A-B builds)
+#ifdef UORF_FWD_X3_LEGACY
+constexpr bool kX3Psm = false;
+#else
+constexpr bool kX3Psm = true;
+#endif
+constexpr int kPsmChannels = 4;
+
+// floats of `workspace`: the background sweep's raw outputs [P][4] + (PSM) the per-channel head stash [SMs][4][K][128][4]
+size_t decoder_fwd_workspace_floats(long long P, int K, int num_sms) {
+  return (size_t)P * 4 + (size_t)num_sms * kPsmChannels * K * kTileM * 4;
 }
 
 int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, cudaStream_t stream) {
@@ -666,6 +740,7 @@ int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, c
   p.noise = a->dens_noise != 0.f ? a->noise : nullptr;
   p.image = static_cast<const unsigned char*>(a->image);
   p.scratch_bg = reinterpret_cast<float4*>(a->workspace);
+  p.stash_g = reinterpret_cast<float4*>(a->workspace) + a->P;
   p.raws = reinterpret_cast<float4*>(a->raws);
   p.masked = reinterpret_cast<float4*>(a->masked_raws);
   p.unmasked = reinterpret_cast<float4*>(a->unmasked_raws);
@@ -683,23 +758,25 @@ int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, c
   p.err_flag = err_flag;
   const int passes = a->precision >= 3 ? 3 : 1;
   const bool f16 = (a->precision % 2) == 0;
-  // 3-pass modes run three tiles per SM when the per-slot stash of three channels fits beside the weight image (K <= 13)
-  int nch = passes == 3 ? 3 : 4;
-  if (passes == 3 && decoder_smem_bytes(passes, a->K, 3) > 227 * 1024) nch = 2;
-  const size_t smem = decoder_smem_bytes(passes, a->K, nch);
+  const bool psm = passes == 3 && kX3Psm;
+  // legacy 3-pass form: three tiles per SM when the per-slot stash of three channels fits beside the weight image (K <= 13)
+  int nch = passes == 3 ? (psm ? kPsmChannels : 3) : 4;
+  if (passes == 3 && !psm && decoder_smem_bytes(passes, a->K, 3, false) > 227 * 1024) nch = 2;
+  const size_t smem = decoder_smem_bytes(passes, a->K, nch, psm);
   if (smem > 227 * 1024) return UORF_ERR_UNSUPPORTED;
   int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   if (grid < 1) return UORF_OK;
-  const int threads = passes == 3 ? (nch == 3 ? Cfg<3, 3>::THREADS : Cfg<3, 2>::THREADS) : Cfg<1, 4>::THREADS;
-  auto launch = [&](auto kern) -> int {
+  auto launch = [&](auto kern, int threads) -> int {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UORF_ERR_DEVICE;
     kern<<<grid, threads, smem, stream>>>(p);
     return UORF_OK;
   };
   int rc;
-  if (passes == 3 && nch == 3) rc = f16 ? launch(decoder_fwd_kernel<3, true, 3>) : launch(decoder_fwd_kernel<3, false, 3>);
-  else if (passes == 3) rc = f16 ? launch(decoder_fwd_kernel<3, true, 2>) : launch(decoder_fwd_kernel<3, false, 2>);
-  else rc = f16 ? launch(decoder_fwd_kernel<1, true, 4>) : launch(decoder_fwd_kernel<1, false, 4>);
+  if (psm) rc = f16 ? launch(decoder_fwd_kernel<3, true, kPsmChannels, true>, Cfg<3, kPsmChannels, true>::THREADS)
+                    : launch(decoder_fwd_kernel<3, false, kPsmChannels, true>, Cfg<3, kPsmChannels, true>::THREADS);
+  else if (passes == 3 && nch == 3) rc = f16 ? launch(decoder_fwd_kernel<3, true, 3>, Cfg<3, 3>::THREADS) : launch(decoder_fwd_kernel<3, false, 3>, Cfg<3, 3>::THREADS);
+  else if (passes == 3) rc = f16 ? launch(decoder_fwd_kernel<3, true, 2>, Cfg<3, 2>::THREADS) : launch(decoder_fwd_kernel<3, false, 2>, Cfg<3, 2>::THREADS);
+  else rc = f16 ? launch(decoder_fwd_kernel<1, true, 4>, Cfg<1, 4>::THREADS) : launch(decoder_fwd_kernel<1, false, 4>, Cfg<1, 4>::THREADS);
   if (rc != UORF_OK) return rc;
   return finish_launch(1);
 }

@@ -113,15 +113,21 @@ class Encoder(nn.Module):
         return self._planes[key]
 
     # ---- inference path: six (seven) direct-convolution launches, no cat / upsample tensors -------------------------
-    def _conv(self, layer, src_a, up_a, src_b, h_in, w_in):
+    def invalidate_weight_cache(self):
+        """drop the cached transposed weights: call after anything that rewrites the weights WITHOUT bumping their version
+        counters - torch's fused Adam (`torch._fused_adam_`) and CUDA-graph replays of an optimizer step both do"""
+        self._wt.clear()
+
+    def _conv(self, layer, src_a, up_a, src_b, h_in, w_in, use_cache=True):
         conv = layer[0]
         key = (conv.weight.data_ptr(), conv.weight._version)
-        cache = self._wt.get(id(conv))
+        cache = self._wt.get(id(conv)) if use_cache else None
         if cache is None or cache[0] != key:       # [out][in][3][3] -> [in][3][3][out], once per weight version
             cache = (key, conv.weight.detach().permute(1, 2, 3, 0).contiguous().float())
             # a copy made while a CUDA graph is being captured lives in the graph's pool and is rewritten by every replay: it is
-            # never cached.  (Replays that update the weights do not bump `_version`: the training driver clears `_wt` after them.)
-            if not torch.cuda.is_current_stream_capturing():
+            # never cached.  The training path never caches either (use_cache=False): the weights move every step, and fused
+            # Adam / graph replays move them without bumping `_version` (invalidate_weight_cache covers inference after those).
+            if use_cache and not torch.cuda.is_current_stream_capturing():
                 self._wt[id(conv)] = cache
         stride = conv.stride[0]
         ca, cb = src_a.shape[0], (0 if src_b is None else src_b.shape[0])
@@ -138,18 +144,19 @@ class Encoder(nn.Module):
         img = _f32c(x[0])
         planes = self._pixel_planes(H, W, x.device)[0]
         d0 = None
+        uc = keep is None      # training forward: always the current weights
         if self.bottom:
-            d0 = self._conv(self.enc_down_0, img, False, planes, H, W)
-            d1 = self._conv(self.enc_down_1, d0, False, None, H, W)
+            d0 = self._conv(self.enc_down_0, img, False, planes, H, W, uc)
+            d1 = self._conv(self.enc_down_1, d0, False, None, H, W, uc)
         else:
-            d1 = self._conv(self.enc_down_1, img, False, planes, H, W)
+            d1 = self._conv(self.enc_down_1, img, False, planes, H, W, uc)
         h1, w1 = d1.shape[1], d1.shape[2]
-        d2 = self._conv(self.enc_down_2, d1, False, None, h1, w1)
+        d2 = self._conv(self.enc_down_2, d1, False, None, h1, w1, uc)
         h2, w2 = d2.shape[1], d2.shape[2]
-        d3 = self._conv(self.enc_down_3, d2, False, None, h2, w2)
-        u3 = self._conv(self.enc_up_3, d3, False, None, d3.shape[1], d3.shape[2])      # kept at low resolution
-        u2 = self._conv(self.enc_up_2, u3, True, d2, h2, w2)                           # cat[upsample(u3), d2]
-        out = self._conv(self.enc_up_1, u2, True, d1, h1, w1)                          # cat[upsample(u2), d1]
+        d3 = self._conv(self.enc_down_3, d2, False, None, h2, w2, uc)
+        u3 = self._conv(self.enc_up_3, d3, False, None, d3.shape[1], d3.shape[2], uc)      # kept at low resolution
+        u2 = self._conv(self.enc_up_2, u3, True, d2, h2, w2, uc)                           # cat[upsample(u3), d2]
+        out = self._conv(self.enc_up_1, u2, True, d1, h1, w1, uc)                          # cat[upsample(u2), d1]
         if keep is not None:
             keep.update(img=img, planes=planes, d0=d0, d1=d1, d2=d2, d3=d3, u3=u3, u2=u2, out=out)
         return out[None]
@@ -682,7 +689,7 @@ class Decoder(nn.Module):
         unmasked = mk(K, P, 4) if "unmasked_raws" in emit else None
         masks = mk(K, P, 1) if "masks" in emit else None
         outside = torch.empty(K - 1, P, device=dev, dtype=torch.uint8) if self.return_outside else None
-        workspace = mk(P, 4)
+        workspace = mk(lib().uorf_decoder_forward_workspace_floats(P, K))
         a = _lib.DecoderArgs()
         a.coor_bg, a.coor_fg, a.fg_slot_stride = coor_bg.data_ptr(), fg.data_ptr(), fg_stride
         a.fg_transform, a.noise = T.data_ptr(), _ptr(noise_c)

@@ -300,7 +300,7 @@ class uorfNoGanModel:
                 self._step_eager(False, epoch)
             self._graph = g
         self._graph.replay()
-        self.netEncoder._wt.clear()      # the replay moved the weights without bumping their version counters
+        self.netEncoder.invalidate_weight_cache()      # the replay moved the weights without bumping their version counters
         return [], []
 
     def optimize_parameters(self, ret_grad=False, epoch=0):
@@ -341,6 +341,9 @@ class uorfNoGanModel:
                     avg_grads.append(p.grad.abs().mean().item())
         for opm in self.optimizers:
             opm.step()
+        # fused Adam rewrites the weights without bumping their version counters: inference-path encoder calls (visuals,
+        # forward_disc) must not see transposed copies cached before the step
+        self.netEncoder.invalidate_weight_cache()
         return layers, avg_grads
 
     def update_learning_rate(self):
@@ -364,7 +367,7 @@ class uorfNoGanModel:
     def load_networks(self, save_dir, suffix="latest", with_optimizer=True):
         # a captured step holds the old optimizer state / lr tensors: capture again after the load
         self._graph, self._graph_key, self._graph_warm = None, None, 0
-        self.netEncoder._wt.clear()
+        self.netEncoder.invalidate_weight_cache()
         for name in self.model_names:
             sd = torch.load(os.path.join(save_dir, f"{suffix}_net_{name}.pth"), map_location=str(self.device))
             getattr(self, "net" + name).load_state_dict(sd, strict=False)

@@ -106,7 +106,7 @@ class GraphedShardedRender:
 
     def _body(self):
         m, st = self.model, self.static
-        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        rank, world = (dist.get_rank(self.group), dist.get_world_size(self.group)) if dist.is_initialized() else (0, 1)
         with torch.no_grad():
             m.x = st["x"]
             z = m.encode()[0] if rank == 0 else torch.empty(self.K, self.C, device=st["x"].device)
