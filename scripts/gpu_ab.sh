@@ -1,6 +1,6 @@
 # A/B of decoder-forward variants: parity tests of the default build, then bench --mode render per variant library
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x --timeout 300 -k "decoder or eval_driver or full_size_render or manip or row_blocks" > gpurun_out/pytest_dec.log 2>&1; tail -4 gpurun_out/pytest_dec.log
+[ -n "$SKIP_TESTS" ] || timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x --timeout 300 -k "decoder or eval_driver or full_size_render or manip or row_blocks" > gpurun_out/pytest_dec.log 2>&1; tail -4 gpurun_out/pytest_dec.log
 for v in default ${VARIANTS:-nopp legacy}; do
   if [ $v = default ]; then unset UORF_B200_LIB; else export UORF_B200_LIB=$PWD/uorf_b200/_build/variants/libuorf_b200_$v.so; fi
   for prec in ${PRECS:-fp16x3}; do

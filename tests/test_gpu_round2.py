@@ -304,7 +304,10 @@ def test_flat_gradient_bucket_equals_autograd_path():
             m.backward()
         grads.append({n: p_.grad.detach().clone() for n, p_ in m.named_parameters()})
     for n in grads[0]:
-        assert torch.equal(grads[0][n], grads[1][n]), n
+        if n.startswith("Encoder."):     # cuDNN's autotuner may pick different (not bit-equal) convolution_backward algorithms per model
+            assert maxerr(grads[0][n], grads[1][n]) < 1e-5 * max(1e-6, grads[0][n].abs().max().item()), n
+        else:
+            assert torch.equal(grads[0][n], grads[1][n]), n
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
@@ -333,3 +336,127 @@ def test_launch_counter_counts_kernels():
     raw = torch.rand(64, 16, 4, device=dev())
     raw2outputs(raw, torch.linspace(0, 1, 16, device=dev())[None].expand(64, 16).contiguous(), torch.randn(64, 3, device=dev()))
     assert _lib.launch_count() == n0 + 1
+
+
+# ------------------------------------------------------------------------------------------------------
+# compute-sanitizer is closed on this GPU pool (gpurun answers "closed ... find a bad access with bounds checks and asserts of
+# your own", profiles/r2_sanitizer_closed.txt), so the memcheck / racecheck gate is done here: every buffer the modules
+# allocate sits between sentinel-filled guard zones that must survive, every returned tensor must be overwritten in full,
+# and every kernel must be bit-reproducible from run to run (a data race shows up as run-to-run differences).
+# ------------------------------------------------------------------------------------------------------
+class _GuardedAlloc:
+    """stands in for `torch` inside uorf_b200.modules: empty / empty_like return the middle of a sentinel-filled buffer"""
+    GUARD = 1024          # elements on each side (keeps 16-byte / 1024-byte alignment of the payload)
+
+    def __init__(self):
+        self.live = []
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    def _alloc(self, shape, dtype, device):
+        n = 1
+        for s_ in shape:
+            n *= int(s_)
+        full = torch.empty(n + 2 * self.GUARD, dtype=dtype, device=device)
+        self._fill(full)
+        view = full[self.GUARD:self.GUARD + n].view(*shape) if n else full[self.GUARD:self.GUARD].view(*shape)
+        self.live.append((full, n))
+        return view
+
+    @staticmethod
+    def _fill(t):
+        if t.dtype == torch.float32:
+            t.view(torch.int32).fill_(0x7FC0DEAD)          # a quiet NaN with a recognisable payload
+        elif t.dtype == torch.uint8:
+            t.fill_(0xA5)
+        else:
+            t.view(torch.uint8).fill_(0xA5)
+
+    def empty(self, *shape, dtype=torch.float32, device=None, **kw):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)):
+            shape = tuple(shape[0])
+        if device is None or torch.device(device).type != "cuda":
+            return torch.empty(*shape, dtype=dtype, device=device, **kw)
+        return self._alloc(shape, dtype, device)
+
+    def empty_like(self, t, dtype=None, memory_format=None, **kw):
+        if not t.is_cuda:
+            return torch.empty_like(t, dtype=dtype, **kw)
+        return self._alloc(tuple(t.shape), dtype or t.dtype, t.device)
+
+    def check_guards(self):
+        bad = 0
+        for full, n in self.live:
+            ref = torch.empty_like(full)
+            self._fill(ref)
+            g = self.GUARD
+            raw, rraw = full.view(torch.uint8), ref.view(torch.uint8)
+            e = full.element_size()
+            bad += int((raw[:g * e] != rraw[:g * e]).sum()) + int((raw[(g + n) * e:] != rraw[(g + n) * e:]).sum())
+        return bad
+
+
+def _sentinels_left(t):
+    if t is None or t.numel() == 0:
+        return 0
+    if t.dtype == torch.float32:
+        return int((t.contiguous().view(torch.int32) == 0x7FC0DEAD).sum())
+    return 0
+
+
+def test_kernels_stay_inside_their_buffers_and_are_reproducible(monkeypatch):
+    import uorf_b200.modules as B
+    from uorf_b200.eval_model import init_weights_like_reference
+    ga = _GuardedAlloc()
+    monkeypatch.setattr(B, "torch", ga)
+    torch.manual_seed(0)
+    K, Z, N, F_, D = 4, 64, 2, 12, 24
+    c2w, azi = O.lookat_cameras(N)
+    proj = B.Projection(frustum_size=[F_, F_, D], near=6, far=20, nss_scale=7, render_size=(4, 4), device=dev())
+    enc = init_weights_like_reference(B.Encoder(3, z_dim=Z), "normal").to(dev())
+    sa = init_weights_like_reference(B.SlotAttention(num_slots=K, in_dim=Z, slot_dim=Z), "normal").to(dev())
+    dec = init_weights_like_reference(B.Decoder(n_freq=5, input_dim=33 + Z, z_dim=Z, locality=True, locality_ratio=4.5 / 7), "xavier").to(dev())
+    dec.emit = B.Decoder.ALL_OUTPUTS
+    T = azi[0:1].inverse().to(dev())
+    x = torch.rand(1, 3, 32, 32, device=dev()) * 2 - 1
+    noise = (torch.randn(1, K - 1, Z, device=dev()), torch.randn(1, 1, Z, device=dev()))
+
+    def run_once(train):
+        outs = []
+        with torch.set_grad_enabled(train):
+            for kw in (dict(ray_major=True), dict(), dict(partitioned=True), dict(ray_major=True, crop=(3, 5)),
+                       dict(ray_major=True, crop=torch.tensor([2, 1], dtype=torch.int32, device=dev()))):
+                outs += list(proj.construct_sampling_coor(c2w.to(dev()), **kw))
+            coords, z_vals, ray_dir = proj.construct_sampling_coor(c2w.to(dev()), ray_major=True)
+            P_ = coords.shape[0] - 45                                    # ragged last tile
+            fm = enc(x)
+            slots, attn = sa(fm.flatten(2).permute(0, 2, 1), noise=noise)
+            outs += [fm, slots, attn]
+            for prec in (("fp16x3",) if train else ("fp16x3", "bf16x3", "bf16", "fp16")):
+                dec.precision = prec
+                r = dec(coords[:P_], coords[:P_][None].expand(K - 1, -1, -1), slots[0], T)
+                outs += [t_ for t_ in r if t_ is not None and t_.numel()]
+            dec.precision = "fp16x3"
+            raws = dec(coords, coords[None].expand(K - 1, -1, -1), slots[0], T)[0]
+            res = B.raw2outputs(raws.view(-1, D, 4), z_vals, ray_dir, render_mask=not train)
+            outs += list(res)
+            if train:
+                for m_ in (enc, sa, dec):
+                    m_.zero_grad(set_to_none=True)
+                res[0].square().mean().backward()
+                outs += [p_.grad for m_ in (enc, sa, dec) for p_ in m_.parameters()]
+        torch.cuda.synchronize()
+        return outs
+
+    for train in (False, True):
+        a = run_once(train)
+        assert ga.check_guards() == 0, "a kernel wrote outside a buffer it was given"
+        left = sum(_sentinels_left(t_) for t_ in a)
+        assert left == 0, f"{left} output elements were never written (train={train})"
+        b = run_once(train)
+        assert ga.check_guards() == 0
+        assert len(a) == len(b)
+        for i, (u, v) in enumerate(zip(a, b)):
+            assert torch.equal(u, v), f"output {i} differs between two identical runs (train={train}): a data race or an uninitialised read"
+        ga.live.clear()

@@ -219,6 +219,65 @@ __global__ void __launch_bounds__(160, 1) probe_timing_kernel(long long* out, in
     }
     if (threadIdx.x == 0) out[24] = best;
   }
+  // ---- experiments D..G: do TMEM loads / stores / plain ALU work of the epilogue warps and a running MMA stream slow each other?
+  //   mode 0: LDTM loop (2 x ld32 + wait = one 128 x 64 fp32 accumulator read per iteration)   mode 1: STTM loop (4 x st16 + wait)
+  //   mode 2: ALU loop (16 hi/lo splits on registers, no TMEM access)
+  //   each mode is timed alone (out[64 + 4m]) and while warp 4 streams 192 N=64 TS MMAs (out[65 + 4m]); the MMA stream is timed
+  //   alone (out[80]) and against each mode (out[66 + 4m]).  64 iterations per loop; cycles for the whole loop.
+  {
+    const uint32_t tb = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tbu = __shfl_sync(0xffffffffu, tmem_base, 0);
+    for (int pass = 0; pass < 7; ++pass) {          // 0: MMA alone; 1..3: mode alone; 4..6: mode + MMA
+      const int mode = (pass - 1) % 3;
+      const bool with_mma = pass == 0 || pass >= 4, with_epi = pass >= 1;
+      long long best_e = 1LL << 60, best_m = 1LL << 60;
+      for (int r = 0; r < 5; ++r) {
+        __syncthreads();
+        if (warp == 4 && with_mma) {
+          const long long t0 = clock64();
+#pragma unroll 1
+          for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int j = 0; j < 48; ++j) mma_ts_elect(tbu + 384, tbu + 256 + 8 * (j & 3), dhi + 2 * (j & 3), idesc, (g | j) ? 1u : 0u);
+          }
+          tc_commit_elect(&bar_d);
+          mbar_wait(&bar_d, nd & 1);
+          best_m = min(best_m, clock64() - t0);
+        }
+        if (with_mma) ++nd;
+        if (warp < 4 && with_epi) {
+          uint32_t v[32], hi[16], lo[16];
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(0.001f * (q + lane));
+          const long long t0 = clock64();
+#pragma unroll 1
+          for (int i = 0; i < 64; ++i) {
+            if (mode == 0) {
+              tmem_ld32(tb, v);
+              tc_wait_ld();
+              uint32_t w[32];
+              tmem_ld32(tb + 32, w);
+              tc_wait_ld();
+              v[0] ^= w[0];
+            } else if (mode == 1) {
+              tmem_st16(tb + 64, v); tmem_st16(tb + 80, v + 16); tmem_st16(tb + 96, v); tmem_st16(tb + 112, v + 16);
+              tc_wait_st();
+            } else {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) split2_relu<true>(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]), hi[q], lo[q]);
+#pragma unroll
+              for (int q = 0; q < 16; ++q) { v[2 * q] ^= hi[q] & 0x00010001u; v[2 * q + 1] ^= lo[q] & 0x00010001u; }
+            }
+          }
+          const long long t1 = clock64();
+          if (v[0] == 0xdeadbeefu) out[200] = 1;
+          best_e = min(best_e, t1 - t0);
+        }
+      }
+      if (threadIdx.x == 0 && with_epi) out[64 + 4 * mode + (with_mma ? 1 : 0)] = best_e;
+      if (warp == 4 && lane == 0 && with_mma) out[pass == 0 ? 80 : 66 + 4 * mode] = best_m;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
