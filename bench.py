@@ -547,7 +547,12 @@ def bench_train(ctx, args, c, with_reference_gpu=True):
     for _ in range(max(args.warmup, 3)):
         step(resident)
     sampler.start()
+    prof_range = bool(os.environ.get("UORF_PROFILE_RANGE"))    # ncu --profile-from-start off: list exactly the timed launches
+    if prof_range:
+        torch.cuda.profiler.start()
     ms_total = ctx.timed(lambda: step(resident), args.steps)
+    if prof_range:
+        torch.cuda.profiler.stop()
     keep_busy(lambda: step(resident), ms_total / args.steps)
     clocks = sampler.stop()
 
@@ -689,7 +694,7 @@ def run_b200(args):
         subs = {}
         if args.mode in ("all", "train"):
             subs["train"] = bench_train(ctx, args, TRAIN_CFG)
-        if args.mode in ("all", "train") and args.workload is None:
+        if args.mode == "all":
             subs["train_fine"] = bench_train(ctx, args, TRAIN_FINE_CFG)
         if args.mode in ("all", "strong"):
             subs["strong"] = bench_strong(ctx, args)

@@ -17,7 +17,7 @@ G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
 
-def launches(tag, fname="launches.csv", suffix="launches", cmd="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"):
+def launches(tag, fname="launches.csv", suffix="launches", cmd="python bench.py --mode render --steps 2 --warmup 1 --no-cpu-baseline"):
     if not os.path.exists(os.path.join(G, fname)):
         return
     rows = list(csv.reader(open(os.path.join(G, fname))))

@@ -445,18 +445,21 @@ def test_kernels_stay_inside_their_buffers_and_are_reproducible(monkeypatch):
                 for m_ in (enc, sa, dec):
                     m_.zero_grad(set_to_none=True)
                 res[0].square().mean().backward()
-                outs += [p_.grad for m_ in (enc, sa, dec) for p_ in m_.parameters()]
+                outs += [p_.grad for m_ in (sa, dec) for p_ in m_.parameters()]
+                cudnn_grads = [p_.grad for p_ in enc.parameters()]     # cuDNN's convolution_backward: not this library's kernels
         torch.cuda.synchronize()
-        return outs
+        return outs, (cudnn_grads if train else [])
 
     for train in (False, True):
-        a = run_once(train)
+        a, ca = run_once(train)
         assert ga.check_guards() == 0, "a kernel wrote outside a buffer it was given"
         left = sum(_sentinels_left(t_) for t_ in a)
         assert left == 0, f"{left} output elements were never written (train={train})"
-        b = run_once(train)
+        b, cb = run_once(train)
         assert ga.check_guards() == 0
         assert len(a) == len(b)
         for i, (u, v) in enumerate(zip(a, b)):
             assert torch.equal(u, v), f"output {i} differs between two identical runs (train={train}): a data race or an uninitialised read"
+        for u, v in zip(ca, cb):      # cuDNN's weight-gradient algorithms may use atomics: reproducible to rounding only
+            assert maxerr(u, v) <= 1e-5 * max(1e-12, u.abs().max().item())
         ga.live.clear()
