@@ -412,6 +412,9 @@ constexpr bool kX3Psm = false;
 constexpr bool kX3Psm = true;
 #endif
 constexpr int kPsmChannels = 4;
+// The shipped 3-pass kernel is decoder_fwd_x3.cu (half-tile pipelining, one issuer code path); -DUORF_FWD_X3_V1 (A-B builds) keeps
+// the whole-layer hand-off form of this file.
+int launch_decoder_fwd_x3(const DecFwdParams& p, bool f16, int num_sms, cudaStream_t stream);
 
 // floats of `workspace`: the background sweep's raw outputs [P][4] + (PSM) the per-channel head stash [SMs][4][K][128][4]
 size_t decoder_fwd_workspace_floats(long long P, int K, int num_sms) {
@@ -457,6 +460,9 @@ int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, c
     kern<<<grid, threads, smem, stream>>>(p);
     return UORF_OK;
   };
+#ifndef UORF_FWD_X3_V1
+  if (psm) return launch_decoder_fwd_x3(p, f16, num_sms, stream);
+#endif
   int rc;
   if (psm) rc = f16 ? launch(decoder_fwd_kernel<3, true, kPsmChannels, true>, Cfg<3, kPsmChannels, true>::THREADS)
                     : launch(decoder_fwd_kernel<3, false, kPsmChannels, true>, Cfg<3, kPsmChannels, true>::THREADS);
