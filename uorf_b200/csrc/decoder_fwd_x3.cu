@@ -25,6 +25,28 @@
 #ifndef UORF_X3_WARP_ARRIVE
 #define UORF_X3_WARP_ARRIVE 0
 #endif
+// UORF_X3_RELAY=1 (experiment, off): "accumulator ready" reaches the epilogue warps through hardware named barriers - the issuer
+// warp is the only poller of the d[] mbarriers (tcgen05.commit can only signal an mbarrier) and relays each completion with
+// bar.arrive, the 16 epilogue warps block in bar.sync and spend no issue slots on probing.  Measured: 2.93 ms against 2.77 ms with
+// every waiting warp probing its mbarrier - the relay's extra hop on the dependent chain costs more than the probe loops.
+#ifndef UORF_X3_SETMAXNREG
+#define UORF_X3_SETMAXNREG 1
+#endif
+#ifndef UORF_X3_RELAY
+#define UORF_X3_RELAY 0
+#endif
+
+// -DUORF_TIMELINE_X3 (tuning variant only, scripts/timeline_x3.py): CTA 0 / channel 0 records clock64 stamps of the hand-off
+// points of every stage of the fg sweep into a global buffer read back through uorf_debug_timeline_x3()
+#ifdef UORF_TIMELINE_X3
+__device__ long long g_tlx_epi[16384];
+__device__ long long g_tlx_iss[16384];
+#define TLX_EPI(id) do { if (tl_on && tl_n < 16384) g_tlx_epi[tl_n++] = (clock64() << 8) | (id); } while (0)
+#define TLX_ISS(id) do { if (tl_on && tl_n < 16384) g_tlx_iss[tl_n++] = (clock64() << 8) | (id); } while (0)
+#else
+#define TLX_EPI(id)
+#define TLX_ISS(id)
+#endif
 
 namespace uorf {
 
@@ -38,34 +60,106 @@ struct X3Bars {
   uint64_t d[2];   // N-half n of the current layer's accumulator complete (tcgen05.commit)
 };
 
-__device__ __forceinline__ void x3_arrive(uint64_t* bar) {
+// Lean bounded wait on a shared-memory mbarrier address: ONE probe loop (5 instructions per probe); a protocol bug traps after
+// 2^22 failed probes (~0.1 s) instead of hanging the box.  The general mbar_wait() (two loop levels + clock reads) costs ~250
+// cycles of set-up, branches and instruction fetch per call on the dependent chain of every hand-off.
+__device__ __forceinline__ void x3_wait(uint32_t bar_addr, uint32_t parity, int* err_flag, int site) {
+  if (!mbar_spin(bar_addr, parity, 1u << 22)) {
+    if (err_flag) atomicExch(err_flag, site);
+    __threadfence_system();
+    __trap();
+  }
+}
+__device__ __forceinline__ void x3_arrive_addr(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+// keeps a value in a register: the compiler may not rematerialise it from threadIdx / constants at every use
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T* opaque_ptr(T* q) {
+  asm volatile("" : "+l"(q));
+  return q;
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// epilogue side: wait until N-half n of the channel's accumulator is complete
+// bars_addr: shared address of the channel's X3Bars; bar_id: first named barrier of the channel
+__device__ __forceinline__ void x3_wait_d(uint32_t bars_addr, int bar_id, int n, uint32_t parity, int* err_flag, int site) {
+#if UORF_X3_RELAY
+  named_bar_sync(bar_id + n, kTileM + 32);
+#else
+  x3_wait(bars_addr + 16 + 8 * n, parity, err_flag, site);
+#endif
+  tc_fence_after();
+}
+// issuer side: relay the completions of d[0], d[1] (in this order) to the channel's named barriers
+__device__ __forceinline__ void x3_relay_d(uint32_t bars_addr, int bar_id, uint32_t parity, int* err_flag) {
+#if UORF_X3_RELAY
+#pragma unroll
+  for (int n = 0; n < 2; ++n) {
+    x3_wait(bars_addr + 16 + 8 * n, parity, err_flag, 220 + n);
+    tc_fence_after();
+    tc_fence_before();
+    named_bar_arrive(bar_id + n, kTileM + 32);
+  }
+#endif
+}
+
+__device__ __forceinline__ void x3_arrive(uint32_t bar_addr) {
 #if UORF_X3_WARP_ARRIVE
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+  if ((threadIdx.x & 31) == 0) x3_arrive_addr(bar_addr);
 #else
-  mbar_arrive(bar);
+  x3_arrive_addr(bar_addr);
 #endif
 }
 
 // One half-layer of the epilogue: 32 accumulator columns -> [+ wx * xe] -> next layer's bias into the same columns -> ReLU +
 // hi/lo split -> 16 + 16 operand columns.  `gate` (E(0) only): the barrier the stores of H have to wait for.
 template <bool F16>
-__device__ __forceinline__ void x3_half(uint32_t t_d, uint32_t t_hhi, uint32_t t_hlo, const float* wx, float xe, const float* next_bias,
-                                        uint64_t* gate, uint32_t gate_parity, int* err_flag) {
+__device__ __forceinline__ void x3_half(uint32_t t_d, uint32_t t_hhi, uint32_t t_hlo, bool has_wx, uint32_t wx, float xe, bool has_bias,
+                                        uint32_t next_bias, bool gate, uint32_t bars_addr, int bar_id, uint32_t gate_parity, int* err_flag, bool tl_on, int& tl_n,
+                                        int tl_id) {
   uint32_t r[32];
   tmem_ld32(t_d, r);
-  tc_wait_ld();
-  if (wx != nullptr) {
+  if (has_bias) {
+    // the next layer's bias is fetched while the accumulator load is in flight and stored over the columns just read
+    float4 b[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) b[q] = lds128(next_bias + 16 * q);
+    tc_wait_ld();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t w[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        w[4 * q + 0] = __float_as_uint(b[4 * h + q].x); w[4 * q + 1] = __float_as_uint(b[4 * h + q].y);
+        w[4 * q + 2] = __float_as_uint(b[4 * h + q].z); w[4 * q + 3] = __float_as_uint(b[4 * h + q].w);
+      }
+      tmem_st16(t_d + 16 * h, w);
+    }
+  } else {
+    tc_wait_ld();
+  }
+  if (has_wx) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 w = *reinterpret_cast<const float4*>(wx + 4 * q);
+      const float4 w = lds128(wx + 16 * q);
       r[4 * q + 0] = __float_as_uint(fmaf(w.x, xe, __uint_as_float(r[4 * q + 0])));
       r[4 * q + 1] = __float_as_uint(fmaf(w.y, xe, __uint_as_float(r[4 * q + 1])));
       r[4 * q + 2] = __float_as_uint(fmaf(w.z, xe, __uint_as_float(r[4 * q + 2])));
       r[4 * q + 3] = __float_as_uint(fmaf(w.w, xe, __uint_as_float(r[4 * q + 3])));
     }
   }
-  if (next_bias != nullptr) preload_bias32(t_d, next_bias);
   uint32_t hi[16], lo[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
@@ -75,10 +169,17 @@ __device__ __forceinline__ void x3_half(uint32_t t_d, uint32_t t_hhi, uint32_t t
       split2<F16>(fmaxf(__uint_as_float(r[2 * q]), 0.f), fmaxf(__uint_as_float(r[2 * q + 1]), 0.f), hi[q], lo[q]);
     }
   }
-  if (gate != nullptr) {
-    mbar_wait(gate, gate_parity, err_flag, 310);
-    tc_fence_after();
+  TLX_EPI(0x20 + tl_id);
+  if (gate) {
+    // The conversions have to be complete BEFORE the gate (the point of E(0) is to run under G(.,1)); ptxas otherwise sinks the
+    // pack / FMA instructions below the barrier wait.  So the barrier id is made to depend on every residual word: their sign bits
+    // are zero (cvt.relu), which the assembler cannot know.
+    uint32_t any = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) any |= lo[q];
+    x3_wait_d(bars_addr, bar_id + (int)(any & 0x80008000u), 1, gate_parity, err_flag, 310);
   }
+  TLX_EPI(0x30 + tl_id);
   tmem_st16(t_hhi, hi);
   tmem_st16(t_hlo, lo);
 }
@@ -120,24 +221,29 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
 
   uint32_t n_stage = 0;   // stages completed by this thread's channel (parity of all four barriers = n_stage & 1)
 
-  for (int phase = 0; phase < 2; ++phase) {  // 0: background MLP, 1: foreground MLP + composition
-    const int nslots = phase == 0 ? 1 : K - 1;
-    if (warp == kX3EpiWarps && lane == 0) {
-      fence_proxy_async_smem();
-      const unsigned char* src = p.image + (phase ? blob_fg_offset(3) : 0);
-      const uint32_t bytes = (uint32_t)blob_bytes_one(3, nslots);
-      mbar_arrive_expect_tx(&bar_w, bytes);
-      for (uint32_t off = 0; off < bytes; off += 32768u) {
-        const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
-        bulk_g2s(smem + off, src + off, n, &bar_w);
+  // The two roles never share code after this point (each has its own phase loop), so the issuer warps - one warpgroup - can hand
+  // most of their registers to the epilogue warps: 128 x (96 - 40) = 512 x 14 -> 104 registers per epilogue thread.
+  if (warp >= kX3EpiWarps) {
+#if UORF_X3_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+#endif
+    for (int phase = 0; phase < 2; ++phase) {  // 0: background MLP, 1: foreground MLP + composition
+      const int nslots = phase == 0 ? 1 : K - 1;
+      if (warp == kX3EpiWarps && lane == 0) {
+        fence_proxy_async_smem();
+        const unsigned char* src = p.image + (phase ? blob_fg_offset(3) : 0);
+        const uint32_t bytes = (uint32_t)blob_bytes_one(3, nslots);
+        mbar_arrive_expect_tx(&bar_w, bytes);
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+          const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+          bulk_g2s(smem + off, src + off, n, &bar_w);
+        }
       }
-    }
-    mbar_wait(&bar_w, phase & 1, p.err_flag, 100 + phase);
-
-    if (warp >= kX3EpiWarps) {
+      x3_wait(smem_u32(&bar_w), phase & 1, p.err_flag, 100 + phase);
       // =========================== MMA issuer of channel c ===========================
       const int c = __shfl_sync(0xffffffffu, warp - kX3EpiWarps, 0);   // warp-uniform: operands stay on the uniform datapath
       X3Bars& cb = bars[c];
+      const uint32_t cba = smem_u32(&bars[c]);
       const uint32_t w_smem = smem_u32(smem);
       const uint32_t td = tmem_base + 128 * c;           // accumulator D (64 columns)
       const uint32_t th = td + 64, tl = td + 96;         // operand H: hi / lo (32 columns each)
@@ -145,6 +251,10 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
       const uint32_t id64 = make_idesc_f32acc(128, 64, F16);
       const uint32_t id32 = make_idesc_f32acc(128, 32, F16);
       const uint32_t idh = make_idesc_f32acc(128, phase == 0 ? 16 : 32, F16);
+#ifdef UORF_TIMELINE_X3
+      const bool tl_on = blockIdx.x == 0 && c == 0 && lane == 0 && phase == 1;
+      int tl_n = 0;
+#endif
       for (int it = 0;; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)gridDim.x * ((long long)it * kX3Ch + c);
         if (tile >= p.num_tiles) break;
@@ -156,19 +266,22 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
             // hidden-layer weight tile of MMA stage st: t1 t2 | t4 t5 t6 | head t7; encoding tiles t0 (st 0), t3 (st 3)
             const uint32_t wt = w_smem + (uint32_t)(st < 3 ? st : st + 1) * kTileBytes;
             const uint64_t b_hi = make_sdesc_sw128(wt), b_lo = make_sdesc_sw128(wt + kPlaneBytes);
-            mbar_wait(&cb.a[0], par, p.err_flag, 200 + st);
+            x3_wait(cba, par, p.err_flag, 200 + st);
             tc_fence_after();
+            TLX_ISS(0x60 + st);
             if (st == 0) {
               // layer before.0: encoding operand only (the slot-latent part is the preloaded bias); one N = 64 group
               mma_group_p_ss(td, pdesc, b_hi, b_lo, id64, 1u);
-              mbar_wait(&cb.a[1], par, p.err_flag, 210);
+              if (UORF_X3_KSPLIT) x3_wait(cba + 8, par, p.err_flag, 210);
               tc_commit_elect(&cb.d[0]);
               tc_commit_elect(&cb.d[1]);
             } else if (st == 6) {
               // heads: N = 32 (fg) / 16 (bg), no preloaded bias; K-halves as they arrive
               mma_group_ts<2, 3>(td, th, tl, b_hi, b_lo, idh, 0u);
-              mbar_wait(&cb.a[1], par, p.err_flag, 216);
-              tc_fence_after();
+              if (UORF_X3_KSPLIT) {
+                x3_wait(cba + 8, par, p.err_flag, 216);
+                tc_fence_after();
+              }
               mma_group_ts<2, 3>(td, th + 16, tl + 16, b_hi + 4, b_lo + 4, idh, 1u);
               tc_commit_elect(&cb.d[0]);
               tc_commit_elect(&cb.d[1]);
@@ -176,26 +289,47 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
               const uint64_t p_hi = make_sdesc_sw128(w_smem + 3 * kTileBytes), p_lo = make_sdesc_sw128(w_smem + 3 * kTileBytes + kPlaneBytes);
               if (st == 3) mma_group_p_ss(td, pdesc, p_hi, p_lo, id32, 1u);                      // P(0)
               mma_group_ts<2, 3>(td, th, tl, b_hi, b_lo, id32, 1u);                              // G(0,0)
-              mbar_wait(&cb.a[1], par, p.err_flag, 210 + st);
-              tc_fence_after();
+              if (UORF_X3_KSPLIT) {
+                x3_wait(cba + 8, par, p.err_flag, 210 + st);
+                tc_fence_after();
+              }
+              TLX_ISS(0x70 + st);
               mma_group_ts<2, 3>(td, th + 16, tl + 16, b_hi + 4, b_lo + 4, id32, 1u);            // G(1,0)
               tc_commit_elect(&cb.d[0]);
+              TLX_ISS(0x80 + st);
               if (st == 3) mma_group_p_ss(td + 32, pdesc, p_hi + 256, p_lo + 256, id32, 1u);     // P(1): weight rows 32..63
               mma_group_ts<4, 3>(td + 32, th, tl, b_hi + 256, b_lo + 256, id32, 1u);             // G(0,1) G(1,1)
               tc_commit_elect(&cb.d[1]);
             }
+            TLX_ISS(0x90 + st);
             __syncwarp();
+            x3_relay_d(cba, 1 + 2 * c, par, p.err_flag);
           }
         }
       }
-    } else {
+      // all MMAs of this phase have been consumed; shared memory may be re-used for the next image
+      tc_fence_before();
+      named_bar_sync(0, kX3Threads);
+      tc_fence_after();
+    }
+    if (warp == kX3EpiWarps) tmem_dealloc(tmem_base, kTmemCols);
+  } else {
+#if UORF_X3_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+#endif
+    for (int phase = 0; phase < 2; ++phase) {
+      const int nslots = phase == 0 ? 1 : K - 1;
+      x3_wait(smem_u32(&bar_w), phase & 1, p.err_flag, 102 + phase);
       // =========================== epilogue warps ===========================
       const int ch = warp >> 2;
       const int t = (warp & 3) * 32 + lane;    // point within the tile == TMEM lane
       const uint32_t lane_bits = (uint32_t)((warp & 3) * 32) << 16;
-      const uint32_t td = tmem_base + 128 * ch + lane_bits;
+      const uint32_t td = opaque(tmem_base + 128 * ch + lane_bits);
       const uint32_t th = td + 64, tl = td + 96;
-      X3Bars& cb = bars[ch];
+      const uint32_t cba = opaque(smem_u32(&bars[ch]));   // a[0] +0, a[1] +8, d[0] +16, d[1] +24
+      const int bar_id = (int)opaque((uint32_t)(1 + 2 * ch));
+      const float* s_prm = opaque_ptr(s_params);          // (kept in registers: the compiler otherwise re-derives the shared window per stage)
+      const uint32_t prma = opaque(smem_u32(s_params));
       // per-slot head results of the tile in flight: this channel's slice of a global buffer - each thread only ever reads back
       // what it wrote itself, so no fence is needed, and the 10-40 KB stay L2-resident
       float4* stash = p.stash_g + ((size_t)blockIdx.x * kX3Ch + ch) * K * kTileM;
@@ -208,6 +342,12 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
         for (int cc = 0; cc < 4; ++cc)
           T[r * 4 + cc] = p.fixed_locality ? __ldg(p.fg_transform + r * 4 + cc) : (cc < 3 ? __ldg(p.fg_transform + r * 3 + cc) : 0.f);
       }
+#ifdef UORF_TIMELINE_X3
+      const bool tl_on = blockIdx.x == 0 && warp == 0 && lane == 0 && phase == 1;
+#else
+      const bool tl_on = false;
+#endif
+      int tl_n = 0;
       for (int it = 0;; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)gridDim.x * ((long long)it * kX3Ch + ch);
         if (tile >= p.num_tiles) break;
@@ -225,7 +365,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
         float x_last = 0.f;
         bool outside = false;
         for (int s = 0; s < nslots; ++s) {
-          const float* sb = s_params + kParamFloats + s * kSlotBiasFloats;
+          const float* sb = s_prm + kParamFloats + s * kSlotBiasFloats;
+          const uint32_t sba = prma + 4 * (kParamFloats + s * kSlotBiasFloats);
           // ---- stage 0: coordinates -> object frame -> locality flag -> positional encoding ----
           if (s == 0 || !shared_enc) {
             float x = nx, y = ny, z = nz;
@@ -255,12 +396,22 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
             x_last = v[kPosencMma3];           // cos(16 z): added by FMA in the epilogues of layers before.0 / after.0
           }
           if (phase == 1 && p.outside && valid) p.outside[(long long)s * p.P + pt] = outside ? 1 : 0;
-          preload_bias32(td, sb);
-          preload_bias32(td + 32, sb + 32);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            uint32_t w[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b = lds128(sba + 64 * h + 16 * q);
+              w[4 * q + 0] = __float_as_uint(b.x); w[4 * q + 1] = __float_as_uint(b.y);
+              w[4 * q + 2] = __float_as_uint(b.z); w[4 * q + 3] = __float_as_uint(b.w);
+            }
+            tmem_st16(td + 16 * h, w);
+          }
           tc_wait_st();
           tc_fence_before();
-          x3_arrive(&cb.a[0]);
-          x3_arrive(&cb.a[1]);
+          x3_arrive(cba);
+          if (UORF_X3_KSPLIT) x3_arrive(cba + 8);
+          TLX_EPI(0x01);
 
           // ---- stages 1..6: hidden layers, two halves each ----
 #pragma unroll 1
@@ -268,33 +419,41 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
             const uint32_t par = n_stage & 1;
             ++n_stage;
             // bias of the layer MMA stage `st` computes (preloaded into the accumulator; the head, st == 6, keeps its bias in registers)
-            const float* nb = st == 1 ? s_params + kPB1 : st == 2 ? s_params + kPB2 : st == 3 ? sb + 64
-                            : st == 4 ? s_params + kPA1 : st == 5 ? s_params + kPA2 : nullptr;
-            const float* wx = st == 1 ? s_params + kPW0x : st == 4 ? s_params + kPW3x : nullptr;
-            mbar_wait(&cb.d[0], par, p.err_flag, 300 + st);
-            tc_fence_after();
+            // (plain arithmetic on the stage index: a chain of selects became a jump table, ~200 cycles per stage on the tile's chain)
+            static_assert(kPB1 == 0 && kPB2 == 64 && kPA1 == 128 && kPA2 == 192 && kPW3x == kPW0x + 64, "parameter block layout");
+            const uint32_t nb = st == 3 ? sba + 256 : prma + 256 * (st - 1 - (st > 3 ? 1 : 0));   // shared addresses
+            const uint32_t wx = prma + 4 * kPW0x + (st == 4 ? 256 : 0);
+            const bool has_wx = (opaque(0x12u) >> st) & 1u;   // st == 1 || st == 4 (kept as a bit test: the comparison pair became a jump table)
+            x3_wait_d(cba, bar_id, 0, par, p.err_flag, 300 + st);
+            TLX_EPI(0x10 + st);
+#if UORF_X3_UNROLL_N
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int n = 0; n < 2; ++n) {
-              x3_half<F16>(td + 32 * n, th + 16 * n, tl + 16 * n, wx ? wx + 32 * n : nullptr, x_last, nb ? nb + 32 * n : nullptr,
-                           n == 0 ? &cb.d[1] : nullptr, par, p.err_flag);
-              tc_wait_st();
-              tc_fence_before();
-              x3_arrive(&cb.a[n]);
+              x3_half<F16>(td + 32 * n, th + 16 * n, tl + 16 * n, has_wx, wx + 128 * n, x_last, st != 6, nb + 128 * n, n == 0, cba, bar_id, par, p.err_flag, tl_on, tl_n, 8 * n + st);
+              if (UORF_X3_KSPLIT || n == 1) {
+                tc_wait_st();
+                tc_fence_before();
+                x3_arrive(cba + (UORF_X3_KSPLIT ? 8 * n : 0));
+              }
+              TLX_EPI(0x40 + 8 * n + st);
             }
           }
           // ---- stage 7: heads ----
           {
             const uint32_t par = n_stage & 1;
             ++n_stage;
-            mbar_wait(&cb.d[0], par, p.err_flag, 307);
-            mbar_wait(&cb.d[1], par, p.err_flag, 308);
-            tc_fence_after();
+            x3_wait_d(cba, bar_id, 0, par, p.err_flag, 307);
+            x3_wait_d(cba, bar_id, 1, par, p.err_flag, 308);
+            TLX_EPI(0x17);
           }
           if (phase == 0) {
             uint32_t r[16];
             tmem_ld16(td, r);
             tc_wait_ld();
-            const float* hb = s_params + kPHeadB;
+            const float* hb = s_prm + kPHeadB;
             float4 o;
             o.x = __uint_as_float(r[0]) + hb[0];
             o.y = __uint_as_float(r[1]) + hb[1];
@@ -305,9 +464,9 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
             uint32_t r[32];
             tmem_ld32(td, r);
             tc_wait_ld();
-            const float* hb = s_params + kPHeadB;
-            const float* wc2 = s_params + kPWc2;
-            float c0 = s_params[kPBc2 + 0], c1 = s_params[kPBc2 + 1], c2 = s_params[kPBc2 + 2];
+            const float* hb = s_prm + kPHeadB;
+            const float* wc2 = s_prm + kPWc2;
+            float c0 = s_prm[kPBc2 + 0], c1 = s_prm[kPBc2 + 1], c2 = s_prm[kPBc2 + 2];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float h = fmaxf(__uint_as_float(r[i]) + hb[i], 0.f);
@@ -348,15 +507,14 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
             }
           }
           if (valid && p.raws != nullptr) p.raws[pt] = acc;
+          TLX_EPI(0x02);
         }
       }
+      tc_fence_before();
+      named_bar_sync(0, kX3Threads);
+      tc_fence_after();
     }
-    // all MMAs of this phase have been consumed; shared memory may be re-used for the next image
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
   }
-  if (warp == kX3EpiWarps) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 size_t decoder_fwd_x3_smem_bytes(int K) {
@@ -380,3 +538,13 @@ int launch_decoder_fwd_x3(const DecFwdParams& p, bool f16, int num_sms, cudaStre
 }
 
 }  // namespace uorf
+
+#ifdef UORF_TIMELINE_X3
+extern "C" int uorf_debug_timeline_x3(long long* epi, long long* iss, int n) {
+  if (n > 16384) n = 16384;
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(epi, g_tlx_epi, n * sizeof(long long)) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(iss, g_tlx_iss, n * sizeof(long long)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
