@@ -29,6 +29,14 @@
 // warp is the only poller of the d[] mbarriers (tcgen05.commit can only signal an mbarrier) and relays each completion with
 // bar.arrive, the 16 epilogue warps block in bar.sync and spend no issue slots on probing.  Measured: 2.93 ms against 2.77 ms with
 // every waiting warp probing its mbarrier - the relay's extra hop on the dependent chain costs more than the probe loops.
+// K-split of the operand hand-off (a[0] after E(0), a[1] after E(1)); 0: one hand-off per layer after E(1) (N-split only): 3.10 ms
+#ifndef UORF_X3_KSPLIT
+#define UORF_X3_KSPLIT 1
+#endif
+#ifndef UORF_X3_UNROLL_N
+#define UORF_X3_UNROLL_N 0
+#endif
+// issuer warps hand their registers to the epilogue warps (setmaxnreg): 0 -> 3.10 ms (the epilogue re-derives addresses per stage)
 #ifndef UORF_X3_SETMAXNREG
 #define UORF_X3_SETMAXNREG 1
 #endif
