@@ -84,6 +84,7 @@ struct DecFwdParams {
   int fixed_locality;
   int locality;
   int num_tiles;
+  int zero;             // always 0: run-time zero for scheduling anchors (decoder_fwd_x3.cu)
   int* err_flag;
 };
 

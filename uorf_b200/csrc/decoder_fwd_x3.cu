@@ -33,8 +33,10 @@
 #ifndef UORF_X3_KSPLIT
 #define UORF_X3_KSPLIT 1
 #endif
-#ifndef UORF_X3_UNROLL_N
-#define UORF_X3_UNROLL_N 0
+// next layer's bias fetched before the accumulator / gate waits (1) or under the TMEM load (0, default: measured 2 % faster -
+// the 32 extra live registers cost more than the shared-memory latency they hide)
+#ifndef UORF_X3_PREFETCH
+#define UORF_X3_PREFETCH 0
 #endif
 // issuer warps hand their registers to the epilogue warps (setmaxnreg): 0 -> 3.10 ms (the epilogue re-derives addresses per stage)
 #ifndef UORF_X3_SETMAXNREG
@@ -131,20 +133,21 @@ __device__ __forceinline__ void x3_arrive(uint32_t bar_addr) {
 #endif
 }
 
-// One half-layer of the epilogue: 32 accumulator columns -> [+ wx * xe] -> next layer's bias into the same columns -> ReLU +
-// hi/lo split -> 16 + 16 operand columns.  `gate` (E(0) only): the barrier the stores of H have to wait for.
+// One half-layer of the epilogue, in two steps.
+// x3_convert: 32 accumulator columns -> registers; the next layer's bias (fetched by the caller BEFORE it waited for the accumulator,
+//   so no shared-memory latency sits behind the wait) is stored over the columns just read; [+ wx * xe]; ReLU + hi/lo split.
+// The caller then stores the 16 + 16 operand words (E(0): after the gate on d[1]) and hands them to the issuer.
+__device__ __forceinline__ void x3_load_bias(uint32_t addr, float4 (&b)[8]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) b[q] = lds128(addr + 16 * q);
+}
 template <bool F16>
-__device__ __forceinline__ void x3_half(uint32_t t_d, uint32_t t_hhi, uint32_t t_hlo, bool has_wx, uint32_t wx, float xe, bool has_bias,
-                                        uint32_t next_bias, bool gate, uint32_t bars_addr, int bar_id, uint32_t gate_parity, int* err_flag, bool tl_on, int& tl_n,
-                                        int tl_id) {
+__device__ __forceinline__ void x3_convert(uint32_t t_d, bool has_wx, uint32_t wx, float xe, bool has_bias, const float4 (&b)[8],
+                                           uint32_t (&hi)[16], uint32_t (&lo)[16]) {
   uint32_t r[32];
   tmem_ld32(t_d, r);
+  tc_wait_ld();
   if (has_bias) {
-    // the next layer's bias is fetched while the accumulator load is in flight and stored over the columns just read
-    float4 b[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) b[q] = lds128(next_bias + 16 * q);
-    tc_wait_ld();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       uint32_t w[16];
@@ -155,8 +158,6 @@ __device__ __forceinline__ void x3_half(uint32_t t_d, uint32_t t_hhi, uint32_t t
       }
       tmem_st16(t_d + 16 * h, w);
     }
-  } else {
-    tc_wait_ld();
   }
   if (has_wx) {
 #pragma unroll
@@ -168,7 +169,6 @@ __device__ __forceinline__ void x3_half(uint32_t t_d, uint32_t t_hhi, uint32_t t
       r[4 * q + 3] = __float_as_uint(fmaf(w.w, xe, __uint_as_float(r[4 * q + 3])));
     }
   }
-  uint32_t hi[16], lo[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
     if (F16) {
@@ -177,19 +177,6 @@ __device__ __forceinline__ void x3_half(uint32_t t_d, uint32_t t_hhi, uint32_t t
       split2<F16>(fmaxf(__uint_as_float(r[2 * q]), 0.f), fmaxf(__uint_as_float(r[2 * q + 1]), 0.f), hi[q], lo[q]);
     }
   }
-  TLX_EPI(0x20 + tl_id);
-  if (gate) {
-    // The conversions have to be complete BEFORE the gate (the point of E(0) is to run under G(.,1)); ptxas otherwise sinks the
-    // pack / FMA instructions below the barrier wait.  So the barrier id is made to depend on every residual word: their sign bits
-    // are zero (cvt.relu), which the assembler cannot know.
-    uint32_t any = 0;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) any |= lo[q];
-    x3_wait_d(bars_addr, bar_id + (int)(any & 0x80008000u), 1, gate_parity, err_flag, 310);
-  }
-  TLX_EPI(0x30 + tl_id);
-  tmem_st16(t_hhi, hi);
-  tmem_st16(t_hlo, lo);
 }
 
 template <bool F16>
@@ -233,7 +220,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
   // most of their registers to the epilogue warps: 128 x (96 - 40) = 512 x 14 -> 104 registers per epilogue thread.
   if (warp >= kX3EpiWarps) {
 #if UORF_X3_SETMAXNREG
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
 #endif
     for (int phase = 0; phase < 2; ++phase) {  // 0: background MLP, 1: foreground MLP + composition
       const int nslots = phase == 0 ? 1 : K - 1;
@@ -323,7 +310,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
     if (warp == kX3EpiWarps) tmem_dealloc(tmem_base, kTmemCols);
   } else {
 #if UORF_X3_SETMAXNREG
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
 #endif
     for (int phase = 0; phase < 2; ++phase) {
       const int nslots = phase == 0 ? 1 : K - 1;
@@ -432,21 +419,47 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
             const uint32_t nb = st == 3 ? sba + 256 : prma + 256 * (st - 1 - (st > 3 ? 1 : 0));   // shared addresses
             const uint32_t wx = prma + 4 * kPW0x + (st == 4 ? 256 : 0);
             const bool has_wx = (opaque(0x12u) >> st) & 1u;   // st == 1 || st == 4 (kept as a bit test: the comparison pair became a jump table)
+            const bool has_bias = st != 6;
+            float4 b0[8], b1[8];
+            if (UORF_X3_PREFETCH) x3_load_bias(nb, b0);   // fetched before the wait: no shared-memory latency behind it (st == 6: not used)
             x3_wait_d(cba, bar_id, 0, par, p.err_flag, 300 + st);
             TLX_EPI(0x10 + st);
-#if UORF_X3_UNROLL_N
+            if (!UORF_X3_PREFETCH) x3_load_bias(nb, b0);
+            {
+              uint32_t hi[16], lo[16];
+              x3_convert<F16>(td, has_wx, wx, x_last, has_bias, b0, hi, lo);
+              if (UORF_X3_PREFETCH) x3_load_bias(nb + 128, b1);   // second half's bias: fetched under the gate wait
+              TLX_EPI(0x20 + st);
+              // The conversions have to be complete BEFORE the gate (the point of E(0) is to run under G(.,1)); ptxas otherwise sinks
+              // the pack / FMA instructions below the wait.  So the barrier address is made to depend on every residual word, times
+              // a kernel parameter that is zero at run time (which the assembler cannot know).
+              uint32_t any = 0;
 #pragma unroll
-#else
-#pragma unroll 1
-#endif
-            for (int n = 0; n < 2; ++n) {
-              x3_half<F16>(td + 32 * n, th + 16 * n, tl + 16 * n, has_wx, wx + 128 * n, x_last, st != 6, nb + 128 * n, n == 0, cba, bar_id, par, p.err_flag, tl_on, tl_n, 8 * n + st);
-              if (UORF_X3_KSPLIT || n == 1) {
+              for (int q = 0; q < 16; ++q) any |= lo[q];
+              any *= (uint32_t)p.zero;
+              x3_wait_d(cba + any, bar_id + (int)any, 1, par, p.err_flag, 310);
+              TLX_EPI(0x30 + st);
+              tmem_st16(th, hi);
+              tmem_st16(tl, lo);
+              if (UORF_X3_KSPLIT) {
                 tc_wait_st();
                 tc_fence_before();
-                x3_arrive(cba + (UORF_X3_KSPLIT ? 8 * n : 0));
+                x3_arrive(cba);
               }
-              TLX_EPI(0x40 + 8 * n + st);
+              TLX_EPI(0x40 + st);
+            }
+            {
+              uint32_t hi[16], lo[16];
+              if (!UORF_X3_PREFETCH) x3_load_bias(nb + 128, b1);
+              x3_convert<F16>(td + 32, has_wx, wx + 128, x_last, has_bias, b1, hi, lo);
+              TLX_EPI(0x28 + st);
+              TLX_EPI(0x38 + st);
+              tmem_st16(th + 16, hi);
+              tmem_st16(tl + 16, lo);
+              tc_wait_st();
+              tc_fence_before();
+              x3_arrive(cba + (UORF_X3_KSPLIT ? 8 : 0));
+              TLX_EPI(0x48 + st);
             }
           }
           // ---- stage 7: heads ----
