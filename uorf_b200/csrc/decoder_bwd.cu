@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
     if (warp == kBwdEpiWarps) {
       // =========================== MMA issuer ===========================
       const uint32_t tbu = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t bar_a_addr = smem_u32(&bar_a);
       const uint32_t w_s = smem_u32(smem);
       const uint32_t x_s = smem_u32(s_x);
       const uint32_t dz_s = smem_u32(s_dz);
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
 #endif
       auto wait_a = [&](int site) {
         TLB_ISS(0x20);                       // previous step fully issued (commit + trailing dW group)
-        mbar_wait(&bar_a, n_a & 1, p.err_flag, site);
+        mbar_wait_lean(bar_a_addr, n_a & 1, p.err_flag, site);
         ++n_a;
         tc_fence_after();
         TLB_ISS(0x10);
@@ -306,8 +307,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
       const bool tl_on = blockIdx.x == 0 && warp == 0 && lane == 0 && phase == 1;
       int tl_ne = 0;
 #endif
+      // barrier / parameter addresses as opaque 32-bit shared addresses (the compiler otherwise re-derives the shared window
+      // from special registers at every use) and a single-loop wait: the general mbar_wait() and the select chain that picked
+      // the bias pointer cost ~300 of the ~1100 cycles of every hand-off
+      const uint32_t bar_d_addr = opaque(smem_u32(&bar_d)), bar_a_addr = opaque(smem_u32(&bar_a));
+      const uint32_t prma = opaque(smem_u32(s_params));
       auto wait_d = [&](int site) {
-        mbar_wait(&bar_d, n_d & 1, p.err_flag, site);
+        mbar_wait_lean(bar_d_addr, n_d & 1, p.err_flag, site);
         ++n_d;
         tc_fence_after();
         TLB_EPI(0x30);
@@ -316,7 +322,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
         TLB_EPI(0x50);
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(&bar_a);
+        mbar_arrive_addr(bar_a_addr);
         TLB_EPI(0x40);
       };
       for (int it = 0;; ++it) {
@@ -399,18 +405,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
           }
           publish();
           // ---- stages 1..6: hidden activations ----
-          const float* sb = s_slotb + s * kSlotBiasFloats;
+          const uint32_t sba = prma + 4 * (kParamFloats + s * kSlotBiasFloats);
 #pragma unroll 1
           for (int st = 1; st <= 6; ++st) {
-            const float* bias = (st == 1 ? sb : st == 2 ? s_params + kPB1 : st == 3 ? s_params + kPB2
-                               : st == 4 ? sb + 64 : st == 5 ? s_params + kPA1 : s_params + kPA2) + c0;
+            // bias of layer st - 1: slot biases for the two wide layers (st 1, 4), else b_before.2, .4, b_after.2, .4
+            static_assert(kPB1 == 0 && kPB2 == 64 && kPA1 == 128 && kPA2 == 192, "parameter block layout");
+            const uint32_t bias = (st == 1 ? sba : st == 4 ? sba + 256 : prma + 256 * (st - 2 - (st > 4 ? 1 : 0))) + 4 * c0;
             wait_d(300 + st);
             float v[32];
             load_d32(tb + kBColD + c0, v);
-#pragma unroll
             // rows of padded points need no masking here: their d raw is zero, so every dZ row derived from it is zero and
             // nothing they hold reaches a gradient
-            for (int i = 0; i < 32; ++i) v[i] += bias[i];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b = lds128(bias + 16 * q);
+              v[4 * q + 0] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            }
             store_half16<true, true>(s_x + st * 16384, t, half, v);
             publish();
           }

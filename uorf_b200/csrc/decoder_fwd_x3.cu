@@ -70,29 +70,10 @@ struct X3Bars {
   uint64_t d[2];   // N-half n of the current layer's accumulator complete (tcgen05.commit)
 };
 
-// Lean bounded wait on a shared-memory mbarrier address: ONE probe loop (5 instructions per probe); a protocol bug traps after
-// 2^22 failed probes (~0.1 s) instead of hanging the box.  The general mbar_wait() (two loop levels + clock reads) costs ~250
-// cycles of set-up, branches and instruction fetch per call on the dependent chain of every hand-off.
 __device__ __forceinline__ void x3_wait(uint32_t bar_addr, uint32_t parity, int* err_flag, int site) {
-  if (!mbar_spin(bar_addr, parity, 1u << 22)) {
-    if (err_flag) atomicExch(err_flag, site);
-    __threadfence_system();
-    __trap();
-  }
+  mbar_wait_lean(bar_addr, parity, err_flag, site);
 }
-__device__ __forceinline__ void x3_arrive_addr(uint32_t bar_addr) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
-}
-// keeps a value in a register: the compiler may not rematerialise it from threadIdx / constants at every use
-__device__ __forceinline__ uint32_t opaque(uint32_t v) {
-  asm volatile("" : "+r"(v));
-  return v;
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
+__device__ __forceinline__ void x3_arrive_addr(uint32_t bar_addr) { mbar_arrive_addr(bar_addr); }
 template <typename T>
 __device__ __forceinline__ T* opaque_ptr(T* q) {
   asm volatile("" : "+l"(q));
