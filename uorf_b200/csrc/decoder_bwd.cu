@@ -40,7 +40,20 @@ __device__ long long g_tlb_iss[8192];
 namespace uorf {
 
 constexpr int kTileM128 = 128;
-constexpr int kBwdEpiWarps = 8;    // two warps per TMEM lane quadrant: warp w and w + 4 split the 64 feature columns of a point
+// Epilogue warps per TMEM lane quadrant: warps w, w + 4, ... split the 64 feature columns of a point.  The hand-off chain of a
+// tile is serial (one tile per SM: its activation tiles fill shared memory), and an epilogue step is one warp's dependent
+// instruction stream per point group.  Measured: 4 warps per quadrant (17 warps: 96 registers, the f_color.2 sums spill) 4.17 ms
+// against 3.35 ms with 2 - kept as a switch.
+#ifndef UORF_BWD_NQ
+#define UORF_BWD_NQ 2
+#endif
+// one mbarrier arrival per epilogue WARP (after __syncwarp) instead of one per thread
+#ifndef UORF_BWD_WARP_ARRIVE
+#define UORF_BWD_WARP_ARRIVE 1
+#endif
+constexpr int kBwdNQ = UORF_BWD_NQ;              // 2 or 4
+constexpr int kBwdCols = 64 / kBwdNQ;            // feature columns per thread in the hidden-layer steps
+constexpr int kBwdEpiWarps = 4 * kBwdNQ;
 constexpr int kBwdThreads = (kBwdEpiWarps + 1) * 32;  // + 1 MMA-issuer warp
 constexpr int kAccFloats = 64 * 64;
 // accumulators: 0: before.0 (x P)  1: before.2  2: before.4  3: after.0 (x P)  4: after.0 (x tmp)  5: after.2  6: after.4  7: head
@@ -149,6 +162,59 @@ __device__ __forceinline__ void gate_store_half(const unsigned char* x_tile, uns
   }
 }
 
+// NC-column slices (NC = 16 or 32) of a point's row: chunk = 16-byte chunk index of the first column within the 128-byte row
+template <int NC, bool RELU>
+__device__ __forceinline__ void store_cols16(unsigned char* tile, int t, int chunk0, const float (&v)[NC]) {
+  unsigned char* row = tile + (t >> 3) * 1024 + (t & 7) * 128;
+#pragma unroll
+  for (int c = 0; c < NC / 8; ++c) {
+    uint4 q;
+    if (RELU) {
+      q.x = pack2_relu<true>(v[8 * c + 0], v[8 * c + 1]); q.y = pack2_relu<true>(v[8 * c + 2], v[8 * c + 3]);
+      q.z = pack2_relu<true>(v[8 * c + 4], v[8 * c + 5]); q.w = pack2_relu<true>(v[8 * c + 6], v[8 * c + 7]);
+    } else {
+      q.x = pack2<true>(v[8 * c + 0], v[8 * c + 1]); q.y = pack2<true>(v[8 * c + 2], v[8 * c + 3]);
+      q.z = pack2<true>(v[8 * c + 4], v[8 * c + 5]); q.w = pack2<true>(v[8 * c + 6], v[8 * c + 7]);
+    }
+    *reinterpret_cast<uint4*>(row + ((((chunk0 + c) ^ (t & 7)) & 7) << 4)) = q;
+  }
+}
+template <int NC>
+__device__ __forceinline__ void gate_load_cols(const unsigned char* x_tile, int t, int chunk0, uint4 (&x)[NC / 8]) {
+  const int roff = (t >> 3) * 1024 + (t & 7) * 128;
+#pragma unroll
+  for (int c = 0; c < NC / 8; ++c) {
+    const float4 f = lds128(smem_u32(x_tile + roff + ((((chunk0 + c) ^ (t & 7)) & 7) << 4)));   // asm volatile: stays before the wait
+    x[c] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
+  }
+}
+template <int NC>
+__device__ __forceinline__ void gate_store_cols(const uint4 (&xs)[NC / 8], unsigned char* dz_tile, int t, int chunk0, const float (&g)[NC]) {
+  const int roff = (t >> 3) * 1024 + (t & 7) * 128;
+#pragma unroll
+  for (int c = 0; c < NC / 8; ++c) {
+    const int coff = (((chunk0 + c) ^ (t & 7)) & 7) << 4;
+    const uint4 x = xs[c];
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+    uint32_t q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t m;
+      asm("{\n\t.reg .b32 z;\n\tmov.b32 z, 0;\n\tset.ne.u32.f16x2 %0, %1, z;\n\t}" : "=r"(m) : "r"(xw[i]));   // 0xFFFF per non-zero half
+      q[i] = pack2<true>(g[8 * c + 2 * i], g[8 * c + 2 * i + 1]) & m;
+    }
+    *reinterpret_cast<uint4*>(dz_tile + roff + coff) = make_uint4(q[0], q[1], q[2], q[3]);
+  }
+}
+template <int NC>
+__device__ __forceinline__ void load_dcols(uint32_t taddr, float (&v)[NC]) {
+  uint32_t r[NC];
+  if constexpr (NC == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+  tc_wait_ld();
+#pragma unroll
+  for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void load_d32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   tmem_ld32(taddr, r);
@@ -177,7 +243,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_a, kTileM128 * 2);
+    mbar_init(&bar_a, UORF_BWD_WARP_ARRIVE ? kBwdEpiWarps : kTileM128 * kBwdNQ);
     mbar_init(&bar_d, 1);
     fence_mbar_init();
   }
@@ -300,8 +366,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
     } else {
       // =========================== epilogue warps (two threads <-> point) ===========================
       const int t = (warp & 3) * 32 + lane;   // point within the tile == TMEM lane
-      const int half = warp >> 2;             // this thread owns feature columns 32*half .. 32*half + 31
-      const int c0 = 32 * half;
+      const int quarter = warp >> 2;          // hidden-layer steps: this thread owns feature columns kBwdCols * quarter ...
+      const int c0 = kBwdCols * quarter;
+      const int chunk0 = c0 / 8;
+      // encoding and head steps keep the two-way column split; with four warps per quadrant the last two only take part in the hand-off
+      const int half = quarter;
       const uint32_t tb = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #ifdef UORF_TIMELINE
       const bool tl_on = blockIdx.x == 0 && warp == 0 && lane == 0 && phase == 1;
@@ -322,7 +391,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
         TLB_EPI(0x50);
         fence_proxy_async_smem();
         tc_fence_before();
+#if UORF_BWD_WARP_ARRIVE
+        __syncwarp();
+        if (lane == 0) mbar_arrive_addr(bar_a_addr);
+#else
         mbar_arrive_addr(bar_a_addr);
+#endif
         TLB_EPI(0x40);
       };
       for (int it = 0;; ++it) {
@@ -388,7 +462,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
             }
             store_half16<true>(s_x, t, 0, v);
             }
-          } else {
+          } else if (half == 1) {
             // columns 32..63: cos(16 z), the one-hot slot indicator, zero padding
             float v[32];
             if (fresh) {
@@ -411,17 +485,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
             // bias of layer st - 1: slot biases for the two wide layers (st 1, 4), else b_before.2, .4, b_after.2, .4
             static_assert(kPB1 == 0 && kPB2 == 64 && kPA1 == 128 && kPA2 == 192, "parameter block layout");
             const uint32_t bias = (st == 1 ? sba : st == 4 ? sba + 256 : prma + 256 * (st - 2 - (st > 4 ? 1 : 0))) + 4 * c0;
+            float4 b[kBwdCols / 4];               // fetched before the wait: no shared-memory latency behind it
+#pragma unroll
+            for (int q = 0; q < kBwdCols / 4; ++q) b[q] = lds128(bias + 16 * q);
             wait_d(300 + st);
-            float v[32];
-            load_d32(tb + kBColD + c0, v);
+            float v[kBwdCols];
+            load_dcols<kBwdCols>(tb + kBColD + c0, v);
             // rows of padded points need no masking here: their d raw is zero, so every dZ row derived from it is zero and
             // nothing they hold reaches a gradient
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b = lds128(bias + 16 * q);
-              v[4 * q + 0] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            for (int q = 0; q < kBwdCols / 4; ++q) {
+              v[4 * q + 0] += b[q].x; v[4 * q + 1] += b[q].y; v[4 * q + 2] += b[q].z; v[4 * q + 3] += b[q].w;
             }
-            store_half16<true, true>(s_x + st * 16384, t, half, v);
+            store_cols16<kBwdCols, true>(s_x + st * 16384, t, chunk0, v);
             publish();
           }
           // ---- head forward + backward seed (the 17 head rows live in the first column half) ----
@@ -454,16 +530,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
                 dzh[kHeadShapeRow] = (p.locality && outside) ? 0.f : dr.w;   // model.py:147-148 zeroes sigma outside the box
               }
             }
-            store_half16<true>(s_dz, t, half, dzh);   // the second half writes the zero padding of the head's dZ tile
+            if (half < 2) store_half16<true>(s_dz, t, half, dzh);   // the second half writes the zero padding of the head's dZ tile
           }
           publish();
           // ---- layers 5..0 ----
 #pragma unroll 1
           for (int l = 5; l >= 0; --l) {
+            uint4 xg[kBwdCols / 8];                         // activations that gate this layer: fetched before the wait
+            gate_load_cols<kBwdCols>(s_x + (l + 1) * 16384, t, chunk0, xg);
             wait_d(320 + l);
-            float g[32];
-            load_d32(tb + kBColD + c0, g);                  // dX_{l+1}
-            gate_store_half(s_x + (l + 1) * 16384, s_dz + ((l & 1) ? 16384 : 0), t, half, g);   // dZ_l = dX_{l+1} * [X_{l+1} > 0]
+            float g[kBwdCols];
+            load_dcols<kBwdCols>(tb + kBColD + c0, g);      // dX_{l+1}
+            gate_store_cols<kBwdCols>(xg, s_dz + ((l & 1) ? 16384 : 0), t, chunk0, g);   // dZ_l = dX_{l+1} * [X_{l+1} > 0]
             publish();
           }
         }
