@@ -79,6 +79,18 @@ __device__ __forceinline__ T* opaque_ptr(T* q) {
   asm volatile("" : "+l"(q));
   return q;
 }
+// L2 residency of the background sweep's 16 B / point scratch: it is written in phase 0 and read back in phase 1, with ~700 MB of
+// output stores in between.  The scratch is stored with an evict_last policy and the outputs as streaming (evict-first) stores, so
+// the read-back hits L2 instead of making a 134 MB DRAM round trip.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_global_hint(float4* ptr, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -461,7 +473,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
             o.y = __uint_as_float(r[1]) + hb[1];
             o.z = __uint_as_float(r[2]) + hb[2];
             o.w = __uint_as_float(r[3]) + hb[3];
-            if (valid) p.scratch_bg[pt] = o;
+            if (valid) st_global_hint(p.scratch_bg + pt, o, l2_policy_evict_last());
           } else {
             uint32_t r[32];
             tmem_ld32(td, r);
@@ -483,7 +495,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
         }
         if (phase == 1) {
           // ---- cross-slot composition (model.py:151-159) ----
-          if (valid) stash[t] = p.scratch_bg[pt];
+          if (valid) stash[t] = __ldcs(p.scratch_bg + pt);   // last use: streaming load
           float S = 0.f;
 #pragma unroll 4
           for (int k = 0; k < K; ++k) S += fmaxf(stash[k * kTileM + t].w, 0.f);
@@ -503,12 +515,12 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
             const float4 mk = make_float4(u.x * m, u.y * m, u.z * m, u.w * m);
             acc.x += mk.x; acc.y += mk.y; acc.z += mk.z; acc.w += mk.w;
             if (valid) {
-              if (p.unmasked) p.unmasked[(long long)k * p.P + pt] = u;
-              if (p.masked) p.masked[(long long)k * p.P + pt] = mk;
-              if (p.masks) p.masks[(long long)k * p.P + pt] = m;
+              if (p.unmasked) __stcs(p.unmasked + (long long)k * p.P + pt, u);
+              if (p.masked) __stcs(p.masked + (long long)k * p.P + pt, mk);
+              if (p.masks) __stcs(p.masks + (long long)k * p.P + pt, m);
             }
           }
-          if (valid && p.raws != nullptr) p.raws[pt] = acc;
+          if (valid && p.raws != nullptr) __stcs(p.raws + pt, acc);
           TLX_EPI(0x02);
         }
       }
