@@ -463,3 +463,57 @@ def test_kernels_stay_inside_their_buffers_and_are_reproducible(monkeypatch):
         for u, v in zip(ca, cb):      # cuDNN's weight-gradient algorithms may use atomics: reproducible to rounding only
             assert maxerr(u, v) <= 1e-5 * max(1e-12, u.abs().max().item())
         ga.live.clear()
+
+
+# ------------------------------------------------------------------------------------------------------
+# adversarial driver against the UNMODIFIED reference uorfGanModel (tests/golden/make_golden_gan.py): generator step with the
+# GAN term active (uorf_gan_model.py:137-245) and discriminator step with the R1 penalty (:247-311)
+# ------------------------------------------------------------------------------------------------------
+def test_gan_driver_matches_reference_golden():
+    from uorf_b200.gan_model import uorfGanModel, default_gan_options
+    g = load_golden("gan_driver")
+    cfg = dict(num_slots=3, z_dim=40, n_samp=8, frustum_size=16, frustum_size_fine=16, render_size=16, supervision_size=16,
+               input_size=32, n_img_each_scene=2, stage="coarse", bottom=False, warmup_steps=5, ndf=8, percept_in=100,
+               gan_train_epoch=2, gan_in=1, gpu_ids=[0])
+    torch.manual_seed(3)
+    m = uorfGanModel(default_gan_options(**cfg), precision="fp16x3", with_perceptual=False)
+    init = g["init"]
+    m.load_networks_from_state_dicts(init["enc"], init["sa"], init["dec"])
+    assert set(init["disc"]) == set(m.netDisc.state_dict()), "discriminator state-dict keys differ from the reference"
+    m.netDisc.load_state_dict({k: v.to(dev()) for k, v in init["disc"].items()})
+    epoch = int(g["epoch"])
+    inp = {"img_data": g["img"], "cam2world": g["cam2world"], "azi_rot": g["azi_rot"], "paths": []}
+    # ---- generator step: losses, render and every generator gradient (MSE + weight_gan * softplus(-D(x_recon))) ----
+    m.slot_noise = (g["noise_fg_g"].to(dev()), g["noise_bg_g"].to(dev()))
+    m.set_input(inp)
+    m.forward(epoch=epoch)
+    assert m.weight_gan == float(g["weight_gan"]) > 0
+    assert abs(float(m.loss_recon) - float(g["loss_recon"])) < 1e-5
+    assert maxerr(m.x_recon, g["x_recon"]) < FP32_TOL
+    for o in m.optimizers:
+        o.zero_grad()
+    m.backward()
+    assert abs(float(m.loss_gan) - float(g["loss_gan"])) < 1e-5, (float(m.loss_gan), float(g["loss_gan"]))
+    got, ref = {}, {}
+    for pre, net in (("enc", m.netEncoder), ("sa", m.netSlotAttention), ("dec", m.netDecoder)):
+        for n, p in net.named_parameters():
+            got[f"{pre}.{n}"] = p.grad if p.grad is not None else torch.zeros_like(p)
+            ref[f"{pre}.{n}"] = g["grad"][pre][n]
+    check_grads(got, ref, "generator step of the adversarial driver vs the reference uorfGanModel", 2e-2)
+    # ---- discriminator step: logistic losses and the weights after the logistic + R1 updates (Adam, betas (0, 0.9)) ----
+    m.d_scheduler.step()
+    m.d_scheduler.step()
+    assert abs(m.d_optimizer.param_groups[0]["lr"] - float(g["d_lr"])) < 1e-12
+    m.slot_noise = (g["noise_fg_d"].to(dev()), g["noise_bg_d"].to(dev()))
+    m.forward_disc(it=32)
+    assert abs(float(m.loss_d_real) - float(g["loss_d_real"])) < 1e-5
+    assert abs(float(m.loss_d_fake) - float(g["loss_d_fake"])) < 2e-5
+    lr = float(g["d_lr"])
+    for n, p in m.netDisc.state_dict().items():
+        want = g["final"]["disc"][n].to(dev())
+        moved = (want - init["disc"][n].to(dev())).abs().max().item()
+        # two Adam updates of +-lr each (first steps: update = lr * sign-like g / |g|): an element whose gradient is at rounding
+        # level may take the other sign, so the maximum is bounded by the two full steps and the MEAN has to agree
+        assert maxerr(p, want) <= 2.1 * lr + 1e-6, (n, maxerr(p, want), moved)
+        assert (p.float() - want).abs().mean().item() <= 0.05 * lr + 1e-7, (n, (p.float() - want).abs().mean().item(), moved)
+    assert any((g["final"]["disc"][n] - init["disc"][n]).abs().max() > 0.5 * lr for n in init["disc"])

@@ -46,6 +46,28 @@ def test_reference_eval_driver_reproduces_golden(ref):
     assert torch.equal(model.masked_raws, g["masked_raws"])
 
 
+def test_reference_gan_driver_reproduces_golden(ref):
+    """models.create_model -> uorfGanModel.forward / backward (uorf_gan_model.py:137-245) of the copy == tests/golden/gan_driver.npz
+    (the generator step of make_golden_gan.py, re-run from the recorded initial weights)"""
+    g = load_golden("gan_driver")
+    torch.manual_seed(1)
+    model, opt = ref.create_model("uorf_gan", True, num_slots=3, z_dim=40, n_samp=8, frustum_size=16, frustum_size_fine=16,
+                                  render_size=16, supervision_size=16, input_size=32, n_img_each_scene=2, stage="coarse",
+                                  bottom=False, warmup_steps=5, ndf=8, percept_in=100, gan_train_epoch=2, gan_in=1)
+    assert type(model).__module__ == "models.uorf_gan_model"
+    for net, key in ((model.netEncoder, "enc"), (model.netSlotAttention, "sa"), (model.netDecoder, "dec"), (model.netDisc, "disc")):
+        net.load_state_dict(g["init"][key])
+    model.set_input({"img_data": g["img"], "cam2world": g["cam2world"], "azi_rot": g["azi_rot"], "paths": []})
+    torch.manual_seed(501)
+    model.forward(int(g["epoch"]))
+    for o in model.optimizers:
+        o.zero_grad()
+    model.backward()
+    assert abs(float(model.loss_recon) - float(g["loss_recon"])) < 1e-6 and abs(float(model.loss_gan) - float(g["loss_gan"])) < 1e-6
+    w = model.netDecoder.f_after[0].weight
+    assert torch.allclose(w.grad, g["grad"]["dec"]["f_after.0.weight"], atol=1e-7, rtol=1e-4)
+
+
 def test_swapped_imports_rebinds_and_restores(ref):
     import importlib
     import uorf_b200.modules as B
