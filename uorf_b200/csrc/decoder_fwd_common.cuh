@@ -239,7 +239,7 @@ __device__ __forceinline__ void write_selector(uint32_t t_sel, int bias_id) {
 // colour activation (tanh(x) + 1) / 2 = 1 / (1 + exp(-2x)); FAST uses ex2.approx + fast division (abs error ~1e-6)
 template <bool FAST>
 __device__ __forceinline__ float rgb_act(float x) {
-  if (FAST) return __fdividef(1.f, 1.f + __expf(-2.f * x));
+  if (FAST) return __frcp_rn(1.f + __expf(-2.f * x));
   return (tanhf(x) + 1.f) * 0.5f;
 }
 

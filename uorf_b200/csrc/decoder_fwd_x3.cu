@@ -42,6 +42,15 @@
 #ifndef UORF_X3_SETMAXNREG
 #define UORF_X3_SETMAXNREG 1
 #endif
+// cross-slot composition (experiment, off: no measurable difference): colour activation (tanh + 1) / 2 as 1 / (1 + 2^(-2 x log2 e))
+// with ex2.approx and a correctly rounded reciprocal (abs error < 3e-7), masks as density * rcp(sum) instead of K divisions
+#ifndef UORF_X3_FAST_ACT
+#define UORF_X3_FAST_ACT 0
+#endif
+// E(1) stores its operand words in two batches of eight as they are converted (1) or all sixteen at the end (0)
+#ifndef UORF_X3_EARLY_ST
+#define UORF_X3_EARLY_ST 0
+#endif
 #ifndef UORF_X3_RELAY
 #define UORF_X3_RELAY 0
 #endif
@@ -134,9 +143,9 @@ __device__ __forceinline__ void x3_load_bias(uint32_t addr, float4 (&b)[8]) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) b[q] = lds128(addr + 16 * q);
 }
-template <bool F16>
+template <bool F16, bool STORE = false>
 __device__ __forceinline__ void x3_convert(uint32_t t_d, bool has_wx, uint32_t wx, float xe, bool has_bias, const float4 (&b)[8],
-                                           uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+                                           uint32_t (&hi)[16], uint32_t (&lo)[16], uint32_t t_hhi = 0, uint32_t t_hlo = 0) {
   uint32_t r[32];
   tmem_ld32(t_d, r);
   tc_wait_ld();
@@ -168,6 +177,10 @@ __device__ __forceinline__ void x3_convert(uint32_t t_d, bool has_wx, uint32_t w
       split2_relu<F16>(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]), hi[q], lo[q]);
     } else {   // bf16: keep round-to-nearest on the hi part (truncation would cost one of its 16 bits)
       split2<F16>(fmaxf(__uint_as_float(r[2 * q]), 0.f), fmaxf(__uint_as_float(r[2 * q + 1]), 0.f), hi[q], lo[q]);
+    }
+    if (STORE && (q & 7) == 7) {   // E(1): operand words stored as soon as eight are ready (nothing gates them)
+      tmem_st8(t_hhi + (q - 7), &hi[q - 7]);
+      tmem_st8(t_hlo + (q - 7), &lo[q - 7]);
     }
   }
 }
@@ -336,17 +349,24 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
       const bool tl_on = false;
 #endif
       int tl_n = 0;
+      // the NEXT tile's coordinates (and, in the fg sweep, this tile's bg result) are fetched in the middle of the current tile:
+      // a DRAM round trip at every tile boundary sat on the channel's chain otherwise
+      float pfx = 0.f, pfy = 0.f, pfz = 0.f;
+      {
+        const long long pt0 = ((long long)blockIdx.x + (long long)gridDim.x * ch) * kTileM + t;
+        if (pt0 < p.P) {
+          const float* src = (phase == 0 ? p.coor_bg : p.coor_fg) + pt0 * 3;
+          pfx = __ldg(src); pfy = __ldg(src + 1); pfz = __ldg(src + 2);
+        }
+      }
       for (int it = 0;; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)gridDim.x * ((long long)it * kX3Ch + ch);
         if (tile >= p.num_tiles) break;
         const long long pt = tile * kTileM + t;
         const bool valid = pt < p.P;
         // coordinates are fetched one slot ahead (and once per tile when all fg slots share them, fg_slot_stride == 0)
-        float nx = 0.f, ny = 0.f, nz = 0.f;
-        if (valid) {
-          const float* src = (phase == 0 ? p.coor_bg : p.coor_fg) + pt * 3;
-          nx = __ldg(src); ny = __ldg(src + 1); nz = __ldg(src + 2);
-        }
+        float nx = pfx, ny = pfy, nz = pfz;
+        float4 bgv = make_float4(0.f, 0.f, 0.f, 0.f);
         // When every fg slot sees the same coordinates (the reference's expand() view, no moved object) the encoding operand
         // written for the first slot is still in the strip, and the locality flag is the same: later slots skip the encoding.
         const bool shared_enc = phase == 1 && p.fg_slot_stride == 0 && p.fg_slot_offset == nullptr;
@@ -400,6 +420,14 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
           x3_arrive(cba);
           if (UORF_X3_KSPLIT) x3_arrive(cba + 8);
           TLX_EPI(0x01);
+          if (s == nslots - 1) {   // prefetch for the tile boundary
+            const long long npt = pt + (long long)gridDim.x * kX3Ch * kTileM;
+            if (npt < p.P) {
+              const float* src = (phase == 0 ? p.coor_bg : p.coor_fg) + npt * 3;
+              pfx = __ldg(src); pfy = __ldg(src + 1); pfz = __ldg(src + 2);
+            }
+            if (phase == 1 && valid) bgv = __ldcs(p.scratch_bg + pt);   // last use: streaming load
+          }
 
           // ---- stages 1..6: hidden layers, two halves each ----
 #pragma unroll 1
@@ -444,11 +472,15 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
             {
               uint32_t hi[16], lo[16];
               if (!UORF_X3_PREFETCH) x3_load_bias(nb + 128, b1);
+#if UORF_X3_EARLY_ST
+              x3_convert<F16, true>(td + 32, has_wx, wx + 128, x_last, has_bias, b1, hi, lo, th + 16, tl + 16);
+#else
               x3_convert<F16>(td + 32, has_wx, wx + 128, x_last, has_bias, b1, hi, lo);
               TLX_EPI(0x28 + st);
               TLX_EPI(0x38 + st);
               tmem_st16(th + 16, hi);
               tmem_st16(tl + 16, lo);
+#endif
               tc_wait_st();
               tc_fence_before();
               x3_arrive(cba + (UORF_X3_KSPLIT ? 8 : 0));
@@ -495,21 +527,21 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
         }
         if (phase == 1) {
           // ---- cross-slot composition (model.py:151-159) ----
-          if (valid) stash[t] = __ldcs(p.scratch_bg + pt);   // last use: streaming load
+          if (valid) stash[t] = bgv;
           float S = 0.f;
 #pragma unroll 4
           for (int k = 0; k < K; ++k) S += fmaxf(stash[k * kTileM + t].w, 0.f);
-          const float denom = S + 1e-5f;
+          const float rdenom = UORF_X3_FAST_ACT ? __frcp_rn(S + 1e-5f) : 1.f / (S + 1e-5f);
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
           for (int k = 0; k < K; ++k) {
             const float4 rw = stash[k * kTileM + t];
             const float dens = fmaxf(rw.w, 0.f);
-            const float m = dens / denom;
+            const float m = dens * rdenom;
             float4 u;
-            u.x = rgb_act<false>(rw.x);
-            u.y = rgb_act<false>(rw.y);
-            u.z = rgb_act<false>(rw.z);
+            u.x = rgb_act<UORF_X3_FAST_ACT != 0>(rw.x);
+            u.y = rgb_act<UORF_X3_FAST_ACT != 0>(rw.y);
+            u.z = rgb_act<UORF_X3_FAST_ACT != 0>(rw.z);
             u.w = dens;
             if (p.noise != nullptr && valid) u.w = dens + p.dens_noise * __ldg(p.noise + (long long)k * p.P + pt);
             const float4 mk = make_float4(u.x * m, u.y * m, u.z * m, u.w * m);
