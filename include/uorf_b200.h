@@ -265,6 +265,22 @@ int uorf_slot_attention_backward(const uorf_slot_attention_weights* w, const uor
 int uorf_encoder_conv3x3(const float* src_a, int32_t ca, int32_t upsample_a, const float* src_b, int32_t cb, const float* weight_t,
                          const float* bias, int32_t c_out, int32_t h_in, int32_t w_in, int32_t stride, float* out, void* stream);
 
+/* -----------------------------------------------------------------------------------------------
+ * Kernel 6: 3x3 convolution (stride 1, pad 1) of the perceptual-loss network, fp32-parity on the tensor cores.
+ * Replaces the cuDNN fp32 convolutions behind `get_perceptual_net` (reference models/model.py:316-324: VGG16 features[:23]) as
+ * the training step uses them (models/uorf_nogan_model.py:181-183): forward on both images, data gradient of the rendered branch.
+ *   uorf_conv_split:  x [n] fp32 (times [gate > 0] when gate != NULL) -> 16-bit hi / lo planes [n] (precision: UORF_PREC_FP16X3 /
+ *                     UORF_PREC_BF16X3); n even.
+ *   uorf_conv3x3_x3:  y[p, co] = bias[co] + sum_{tap, ci} x[p + tap, ci] w[co, ci, tap], NHWC, zero padding, optional ReLU.
+ *                     x_hi / x_lo [n*h*w][c_in] from uorf_conv_split; c_in, c_out multiples of 64.
+ *                     w_img: [c_out/64][9 taps][c_in/64][hi | lo] tiles of 64 x 64 16-bit values, rows = output channels, 128 bytes
+ *                     per row, 16-byte chunk c of row r stored at chunk c ^ (r & 7)  (packed on the host side, modules.pack_conv3x3).
+ *                     The data gradient is the same call on (grad_out * [y > 0]) with the flipped / transposed weight image.
+ * ------------------------------------------------------------------------------------------- */
+int uorf_conv_split(const float* x, const float* gate, void* hi, void* lo, int64_t n, int32_t precision, void* stream);
+int uorf_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, const float* bias, float* y, int32_t n, int32_t h, int32_t w,
+                    int32_t c_in, int32_t c_out, int32_t relu, int32_t precision, void* stream);
+
 /* Test hook: site code written by a kernel whose mbarrier wait timed out (0 = none). */
 int uorf_debug_flag(void);
 

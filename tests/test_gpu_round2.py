@@ -517,3 +517,73 @@ def test_gan_driver_matches_reference_golden():
         assert maxerr(p, want) <= 2.1 * lr + 1e-6, (n, maxerr(p, want), moved)
         assert (p.float() - want).abs().mean().item() <= 0.05 * lr + 1e-7, (n, (p.float() - want).abs().mean().item(), moved)
     assert any((g["final"]["disc"][n] - init["disc"][n]).abs().max() > 0.5 * lr for n in init["disc"])
+
+
+# ------------------------------------------------------------------------------------------------------
+# kernel 6: tensor-core 3x3 convolution of the perceptual-loss network (models/model.py:316-324, uorf_nogan_model.py:181-183)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 64), (3, 8, 8, 128, 256), (1, 32, 24, 64, 128), (4, 8, 8, 512, 512), (1, 5, 7, 64, 64)])
+def test_conv3x3_x3_matches_fp32_conv2d(shape):
+    """forward (fp16 pairs) and data gradient (bf16 pairs) against torch's fp32 convolution (TF32 off, as the reference runs it);
+    sizes cover ragged tiles (pixel counts that are not multiples of 128), several K chunks and several output-channel tiles"""
+    from uorf_b200.modules import _Conv3x3ReluFn, pack_conv3x3
+    torch.backends.cudnn.allow_tf32 = False
+    n, h, w, ci, co = shape
+    g = torch.Generator(device="cpu").manual_seed(1234 + ci + co)
+    x = torch.randn(n, ci, h, w, generator=g).to(dev())
+    wt = (torch.randn(co, ci, 3, 3, generator=g) / (3.0 * ci ** 0.5)).to(dev())
+    b = torch.randn(co, generator=g).to(dev()) * 0.1
+    xr = x.clone().requires_grad_(True)
+    ref = torch.relu(torch.nn.functional.conv2d(xr.double(), wt.double(), b.double(), padding=1))
+    gy = torch.randn(ref.shape, generator=g).to(dev()) * 1e-6              # gradients of a weighted loss are tiny
+    ref.backward(gy.double())
+    xn = x.permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+    y = _Conv3x3ReluFn.apply(xn, pack_conv3x3(wt, "fp16x3"), pack_conv3x3(wt, "bf16x3", dgrad=True), b, co, None)
+    assert y.shape == (n, h, w, co)
+    scale = ref.abs().max().item()
+    # fp32-accumulation level: the 3-term split keeps ~22 bits per product; what remains is the rounding of the fp32 accumulator
+    # over 9 * c_in / 16 tensor-core accumulation steps (measured 1.4e-5 of the maximum at c_in = 512, 3e-6 at c_in = 64)
+    assert maxerr(y.permute(0, 3, 1, 2), ref.float()) < 2.5e-5 * max(1.0, scale), (maxerr(y.permute(0, 3, 1, 2), ref.float()), scale)
+    y.backward(gy.permute(0, 2, 3, 1).contiguous())
+    gref = xr.grad.float()
+    err = maxerr(xn.grad.permute(0, 3, 1, 2), gref)
+    assert err < 3e-5 * gref.abs().max().item(), (err, gref.abs().max().item())
+
+
+def test_perceptual_vgg_matches_torch_layers():
+    """PerceptualVGG (tensor-core convolutions) against the nn.Sequential it was built from, evaluated in fp64 (cuDNN's own fp32
+    engines differ from fp64 by 2e-6 in the features and, depending on the algorithm its autotuner picks, 1e-3 .. 2e-2 in the
+    gradient): features, loss and the gradient of the perceptual loss with respect to the rendered image at the training step's
+    shape (4 views, 64 x 64)"""
+    import copy
+    from uorf_b200.modules import PerceptualVGG
+    from uorf_b200.nogan_model import perceptual_net
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(11)
+    net = perceptual_net(None, allow_random_init=True).to(dev())
+    fast = PerceptualVGG(net)
+    net64 = copy.deepcopy(net).double()
+    assert sum(1 for l in fast.layers if l[0] == "x3") == 9
+    img = torch.rand(4, 3, 64, 64, device=dev()) * 2 - 1
+    tgt = torch.rand(4, 3, 64, 64, device=dev()) * 2 - 1
+    res = {}
+    for name, f, dt in (("ref", net64, torch.float64), ("x3", fast, torch.float32)):
+        a = img.to(dt).clone().requires_grad_(True)
+        fa = f(a)
+        with torch.no_grad():
+            fb = f(tgt.to(dt))
+        loss = 0.006 * torch.nn.functional.mse_loss(fa, fb)
+        loss.backward()
+        res[name] = (fa.detach().float(), loss.item(), a.grad.float())
+    fscale = res["ref"][0].abs().max().item()
+    assert maxerr(res["x3"][0], res["ref"][0]) < 2e-5 * max(1.0, fscale)      # measured 5e-6 (cuDNN fp32 vs fp64: 2e-6)
+    assert abs(res["x3"][1] - res["ref"][1]) < 4e-5 * abs(res["ref"][1]) + 1e-9   # measured 1.7e-5 (tensor-core accumulate rounds toward zero)
+    gmax = res["ref"][2].abs().max().item()
+    assert maxerr(res["x3"][2], res["ref"][2]) < 2e-4 * gmax, (maxerr(res["x3"][2], res["ref"][2]), gmax)   # measured 2e-5
+    # both images in one pass, gradient rows restricted to the rendered half: same loss, same gradient
+    a = img.clone().requires_grad_(True)
+    f = fast(torch.cat([a, tgt]), grad_rows=4)
+    loss = 0.006 * torch.nn.functional.mse_loss(f[:4], f[4:].detach())
+    loss.backward()
+    assert abs(loss.item() - res["x3"][1]) < 1e-7 * abs(res["x3"][1]) + 1e-12
+    assert maxerr(a.grad, res["x3"][2]) < 1e-6 * gmax

@@ -35,6 +35,9 @@ int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_s
                               float eps, const float* fwd_workspace, const float* grad_slots, float* workspace, float* grad_feat,
                               cudaStream_t stream);
 size_t decoder_bwd_workspace_floats(long long P, int K, int num_sms);
+int launch_conv_split(const float* x, const float* gate, void* hi, void* lo, long long n, int f16, int num_sms, cudaStream_t stream);
+int launch_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, const float* bias, float* y, int n, int h, int w, int c_in,
+                      int c_out, int relu, int f16, int* err_flag, cudaStream_t stream);
 int launch_decoder_bwd(const uorf_decoder_weights* w, const uorf_decoder_grads* g, const uorf_decoder_bwd_args* a, int num_sms,
                        int* err_flag, cudaStream_t stream);
 }  // namespace uorf
@@ -160,6 +163,30 @@ int uorf_encoder_conv3x3(const float* src_a, int32_t ca, int32_t upsample_a, con
   if (upsample_a && ((h_in | w_in) & 1)) return fail(UORF_ERR_ARG, "uorf_encoder_conv3x3: upsampled source needs even h_in, w_in%s");
   return check_launch(uorf::launch_encoder_conv3x3(src_a, ca, upsample_a, src_b, cb, weight_t, bias, c_out, h_in, w_in, stride, out,
                                                    static_cast<cudaStream_t>(stream)), "uorf_encoder_conv3x3");
+}
+
+int uorf_conv_split(const float* x, const float* gate, void* hi, void* lo, int64_t n, int32_t precision, void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_conv_split");
+  if (!c) return UORF_ERR_DEVICE;
+  if (n < 0 || (n & 1)) return fail(UORF_ERR_ARG, "uorf_conv_split: n must be even and >= 0%s");
+  if (n > 0 && (!x || !hi || !lo)) return fail(UORF_ERR_ARG, "uorf_conv_split: null pointer%s");
+  if (precision != UORF_PREC_FP16X3 && precision != UORF_PREC_BF16X3) return fail(UORF_ERR_ARG, "uorf_conv_split: precision must be a x3 mode%s");
+  return check_launch(uorf::launch_conv_split(x, gate, hi, lo, n, precision == UORF_PREC_FP16X3, c->num_sms, static_cast<cudaStream_t>(stream)),
+                      "uorf_conv_split");
+}
+
+int uorf_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, const float* bias, float* y, int32_t n, int32_t h, int32_t w,
+                    int32_t c_in, int32_t c_out, int32_t relu, int32_t precision, void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_conv3x3_x3");
+  if (!c) return UORF_ERR_DEVICE;
+  if (!x_hi || !x_lo || !w_img || !y) return fail(UORF_ERR_ARG, "uorf_conv3x3_x3: null pointer%s");
+  if (n < 0 || h < 1 || w < 1 || c_in < 64 || c_out < 64 || (c_in & 63) || (c_out & 63))
+    return fail(UORF_ERR_ARG, "uorf_conv3x3_x3: bad sizes (c_in, c_out must be multiples of 64)%s");
+  if (precision != UORF_PREC_FP16X3 && precision != UORF_PREC_BF16X3) return fail(UORF_ERR_ARG, "uorf_conv3x3_x3: precision must be a x3 mode%s");
+  return check_launch(uorf::launch_conv3x3_x3(x_hi, x_lo, w_img, bias, y, n, h, w, c_in, c_out, relu, precision == UORF_PREC_FP16X3,
+                                              c->err_flag_dev, static_cast<cudaStream_t>(stream)), "uorf_conv3x3_x3");
 }
 
 int uorf_debug_flag(void) {

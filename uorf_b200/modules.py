@@ -812,3 +812,127 @@ class _DecoderFn(torch.autograd.Function):
         if ctx.module.grad_sink is not None:
             return (None, None, None, None, None, None, None, gz) + (None,) * len(ctx.names)
         return (None, None, None, None, None, None, None, gz) + tuple(grads[n] for n in ctx.names)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# perceptual-loss network (reference models/model.py:316-324: frozen VGG16 features[:23], used at uorf_nogan_model.py:181-183)
+# ------------------------------------------------------------------------------------------------------------------------
+def pack_conv3x3(weight: torch.Tensor, precision: str = "fp16x3", dgrad: bool = False) -> torch.Tensor:
+    """Conv2d weight [c_out][c_in][3][3] (fp32) -> the tile image uorf_conv3x3_x3 reads (include/uorf_b200.h):
+    [c_out/64][9 taps][c_in/64][hi | lo] tiles of 64 x 64 16-bit values, 128-byte rows, chunk c of row r at chunk c ^ (r & 7).
+    dgrad=True packs the weights of the data-gradient convolution: taps flipped, input / output channels exchanged."""
+    w = weight.detach().float()
+    if dgrad:
+        w = w.flip(2, 3).permute(1, 0, 2, 3)
+    co, ci = int(w.shape[0]), int(w.shape[1])
+    if co % 64 or ci % 64 or tuple(w.shape[2:]) != (3, 3):
+        raise _lib.UorfError("pack_conv3x3: 3x3 kernels with channel counts that are multiples of 64 only")
+    dt = torch.float16 if precision == "fp16x3" else torch.bfloat16
+    hi = w.to(dt)
+    lo = (w - hi.float()).to(dt)
+
+    def tiles(t):   # [co][ci][ky][kx] -> [co/64][tap][ci/64][row][col]
+        return t.permute(2, 3, 0, 1).reshape(9, co // 64, 64, ci // 64, 64).permute(1, 0, 3, 2, 4)
+    img = torch.stack([tiles(hi), tiles(lo)], dim=3).reshape(co // 64, 9, ci // 64, 2, 8, 8, 8, 8)   # [...][row group][row][chunk][elem]
+    r8 = torch.arange(8, device=w.device).view(8, 1)
+    pos = torch.arange(8, device=w.device).view(1, 8)
+    idx = (pos ^ r8).view(1, 1, 1, 1, 1, 8, 8, 1).expand(co // 64, 9, ci // 64, 2, 8, 8, 8, 8)
+    return img.gather(6, idx).contiguous().view(torch.int16).reshape(-1)
+
+
+def _conv_split(x: torch.Tensor, gate: Optional[torch.Tensor], precision: str):
+    hi = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+    with _on(x):
+        check(lib().uorf_conv_split(x.data_ptr(), _ptr(gate), hi.data_ptr(), lo.data_ptr(), x.numel(), _lib.PRECISIONS[precision],
+                                    _stream(x)), "uorf_conv_split")
+    return hi, lo
+
+
+def _conv3x3_x3(x_nhwc: torch.Tensor, gate: Optional[torch.Tensor], w_img: torch.Tensor, bias: Optional[torch.Tensor], c_out: int,
+                relu: bool, precision: str) -> torch.Tensor:
+    n, h, w, c_in = x_nhwc.shape
+    hi, lo = _conv_split(x_nhwc, gate, precision)
+    y = torch.empty((n, h, w, c_out), dtype=torch.float32, device=x_nhwc.device)
+    with _on(x_nhwc):
+        check(lib().uorf_conv3x3_x3(hi.data_ptr(), lo.data_ptr(), w_img.data_ptr(), _ptr(bias), y.data_ptr(), n, h, w, c_in, c_out,
+                                    int(relu), _lib.PRECISIONS[precision], _stream(x_nhwc)), "uorf_conv3x3_x3")
+    return y
+
+
+class _Conv3x3ReluFn(torch.autograd.Function):
+    """y = relu(conv3x3(x) + b) on NHWC tensors, frozen weights: the backward is the data gradient only (bf16 pairs: gradients of
+    a weighted loss sit far below the fp16 range)."""
+
+    @staticmethod
+    def forward(ctx, x, w_fwd, w_bwd, bias, c_out, grad_rows):
+        y = _conv3x3_x3(x, None, w_fwd, bias, c_out, True, "fp16x3")
+        ctx.save_for_backward(y, w_bwd)
+        ctx.c_in, ctx.grad_rows = x.shape[3], grad_rows
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        y, w_bwd = ctx.saved_tensors
+        r = ctx.grad_rows
+        if r is not None and r < g.shape[0]:
+            # only the first `grad_rows` images of the batch carry a gradient (the ground-truth half of the perceptual loss is
+            # constant): the data gradient runs on those rows, the rest of grad_input is zero
+            gx = g.new_zeros((g.shape[0], g.shape[1], g.shape[2], ctx.c_in))
+            gx[:r] = _conv3x3_x3(_f32c(g[:r]), y[:r], w_bwd, None, ctx.c_in, False, "bf16x3")
+        else:
+            gx = _conv3x3_x3(_f32c(g), y, w_bwd, None, ctx.c_in, False, "bf16x3")
+        return gx, None, None, None, None, None
+
+
+class PerceptualVGG(nn.Module):
+    """Drop-in for the nn.Sequential the reference's get_perceptual_net returns (models/model.py:316-324), built FROM it (same
+    frozen weights): every 3x3 convolution + ReLU with at least 64 input channels runs on uorf_conv3x3_x3 (fp32-parity 3-term
+    split on the tensor cores), the 3-channel stem and the max-pools stay torch.  Input N x 3 x H x W, output N x C x H' x W'
+    (a channels-last view; the perceptual loss is a mean over all elements)."""
+
+    def __init__(self, features: nn.Sequential):
+        super().__init__()
+        self.layers = []
+        mods = list(features)
+        i = 0
+        self._bufs = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Conv2d):
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                ok = (m.kernel_size == (3, 3) and m.stride == (1, 1) and m.padding == (1, 1) and m.in_channels % 64 == 0
+                      and m.out_channels % 64 == 0 and relu and m.weight.is_cuda)
+                if ok:
+                    k = self._bufs
+                    self.register_buffer(f"w_fwd{k}", pack_conv3x3(m.weight, "fp16x3"), persistent=False)
+                    self.register_buffer(f"w_bwd{k}", pack_conv3x3(m.weight, "bf16x3", dgrad=True), persistent=False)
+                    self.register_buffer(f"bias{k}", m.bias.detach().float().clone() if m.bias is not None else None, persistent=False)
+                    self.layers.append(("x3", k, m.out_channels))
+                    self._bufs += 1
+                    i += 2
+                    continue
+                self.layers.append(("torch", m))
+            else:
+                self.layers.append(("torch", m))
+            i += 1
+        self._torch = nn.ModuleList([l[1] for l in self.layers if l[0] == "torch"])   # keeps them on the module's device
+        for p_ in self.parameters():
+            p_.requires_grad = False
+
+    def forward(self, x, grad_rows=None):
+        """grad_rows: only the first `grad_rows` images need a gradient (the rest are constants evaluated in the same pass)"""
+        _require_cuda(x)
+        x = _f32c(x).permute(0, 2, 3, 1)                   # NHWC view of ...
+        x = x.contiguous()                                 # ... a channels-last copy (3 channels: tiny)
+        for l in self.layers:
+            if l[0] == "x3":
+                k, c_out = l[1], l[2]
+                x = _Conv3x3ReluFn.apply(x, getattr(self, f"w_fwd{k}"), getattr(self, f"w_bwd{k}"), getattr(self, f"bias{k}"), c_out,
+                                         grad_rows)
+            else:
+                y = l[1](x.permute(0, 3, 1, 2))            # torch layer on the channels-last NCHW view
+                x = y.permute(0, 2, 3, 1)
+                if not x.is_contiguous():
+                    x = x.contiguous()
+        return x.permute(0, 3, 1, 2)

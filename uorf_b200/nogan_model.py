@@ -24,7 +24,7 @@ from torch import nn, optim
 from torch.optim.lr_scheduler import LambdaLR
 
 from .eval_model import init_weights_like_reference
-from .modules import Decoder, Encoder, Projection, SlotAttention, raw2outputs
+from .modules import Decoder, Encoder, PerceptualVGG, Projection, SlotAttention, raw2outputs
 
 
 def default_train_options(**over) -> argparse.Namespace:
@@ -89,6 +89,10 @@ class uorfNoGanModel:
         if with_perceptual:
             self.perceptual_net = perceptual_net(getattr(opt, "vgg_weights", None),
                                                  bool(getattr(opt, "vgg_random_init", False))).to(self.device)
+            if not bool(getattr(opt, "vgg_cudnn", False)):
+                # the same frozen weights behind the tensor-core convolution kernel (uorf_conv3x3_x3); opt.vgg_cudnn keeps the
+                # torch / cuDNN fp32 layers (A-B runs)
+                self.perceptual_net = PerceptualVGG(self.perceptual_net)
             self._vgg_mean = torch.tensor([0.485, 0.456, 0.406], device=self.device).view(1, 3, 1, 1)
             self._vgg_std = torch.tensor([0.229, 0.224, 0.225], device=self.device).view(1, 3, 1, 1)
         render_size = (opt.render_size, opt.render_size)
@@ -194,9 +198,16 @@ class uorfNoGanModel:
             self.loss_perc = torch.zeros((), device=dev)
         elif self.with_perceptual:
             rendered_norm = (rendered - self._vgg_mean) / self._vgg_std
-            rendered_feat = self.perceptual_net(rendered_norm)
-            with torch.no_grad():      # the ground-truth branch carries no gradient (frozen VGG, constant images)
-                x_feat = self.perceptual_net(((x + 1) / 2 - self._vgg_mean) / self._vgg_std)
+            x_norm = (((x + 1) / 2 - self._vgg_mean) / self._vgg_std).detach()
+            if isinstance(self.perceptual_net, PerceptualVGG):
+                # both images in ONE pass (half the launches, twice the tiles per launch); the ground-truth half carries no
+                # gradient: its features are detached and the convolution's backward skips those rows
+                feats = self.perceptual_net(torch.cat([rendered_norm, x_norm], dim=0), grad_rows=N)
+                rendered_feat, x_feat = feats[:N], feats[N:].detach()
+            else:
+                rendered_feat = self.perceptual_net(rendered_norm)
+                with torch.no_grad():      # the ground-truth branch carries no gradient (frozen VGG, constant images)
+                    x_feat = self.perceptual_net(x_norm)
             self.loss_perc = self.weight_percept * self.L2_loss(rendered_feat, x_feat)
         else:
             self.loss_perc = torch.zeros((), device=dev)
