@@ -276,10 +276,14 @@ int uorf_encoder_conv3x3(const float* src_a, int32_t ca, int32_t upsample_a, con
  *                     w_img: [c_out/64][9 taps][c_in/64][hi | lo] tiles of 64 x 64 16-bit values, rows = output channels, 128 bytes
  *                     per row, 16-byte chunk c of row r stored at chunk c ^ (r & 7)  (packed on the host side, modules.pack_conv3x3).
  *                     The data gradient is the same call on (grad_out * [y > 0]) with the flipped / transposed weight image.
+ *                     workspace: uorf_conv3x3_workspace_floats(...) floats (0 for layers with enough pixel tiles), or NULL: layers
+ *                     with few tiles divide their K iterations over several CTAs (split-K) and a second kernel sums the partial
+ *                     results in a fixed order, then adds bias / ReLU.
  * ------------------------------------------------------------------------------------------- */
 int uorf_conv_split(const float* x, const float* gate, void* hi, void* lo, int64_t n, int32_t precision, void* stream);
-int uorf_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, const float* bias, float* y, int32_t n, int32_t h, int32_t w,
-                    int32_t c_in, int32_t c_out, int32_t relu, int32_t precision, void* stream);
+size_t uorf_conv3x3_workspace_floats(int32_t n, int32_t h, int32_t w, int32_t c_in, int32_t c_out);
+int uorf_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, const float* bias, float* y, float* workspace, int32_t n, int32_t h,
+                    int32_t w, int32_t c_in, int32_t c_out, int32_t relu, int32_t precision, void* stream);
 
 /* Test hook: site code written by a kernel whose mbarrier wait timed out (0 = none). */
 int uorf_debug_flag(void);

@@ -585,5 +585,6 @@ def test_perceptual_vgg_matches_torch_layers():
     f = fast(torch.cat([a, tgt]), grad_rows=4)
     loss = 0.006 * torch.nn.functional.mse_loss(f[:4], f[4:].detach())
     loss.backward()
-    assert abs(loss.item() - res["x3"][1]) < 1e-7 * abs(res["x3"][1]) + 1e-12
-    assert maxerr(a.grad, res["x3"][2]) < 1e-6 * gmax
+    # (not bit-equal: the split-K factor of a layer depends on its pixel-tile count, so the summation order differs with the batch)
+    assert abs(loss.item() - res["x3"][1]) < 1e-5 * abs(res["x3"][1]) + 1e-12
+    assert maxerr(a.grad, res["x3"][2]) < 1e-4 * gmax

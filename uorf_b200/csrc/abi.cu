@@ -36,8 +36,9 @@ int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_s
                               cudaStream_t stream);
 size_t decoder_bwd_workspace_floats(long long P, int K, int num_sms);
 int launch_conv_split(const float* x, const float* gate, void* hi, void* lo, long long n, int f16, int num_sms, cudaStream_t stream);
-int launch_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, const float* bias, float* y, int n, int h, int w, int c_in,
-                      int c_out, int relu, int f16, int* err_flag, cudaStream_t stream);
+int launch_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, const float* bias, float* y, float* partials, int splits, int n,
+                      int h, int w, int c_in, int c_out, int relu, int f16, int num_sms, int* err_flag, cudaStream_t stream);
+int conv3x3_splits(int n, int h, int w, int c_in, int c_out, int num_sms);
 int launch_decoder_bwd(const uorf_decoder_weights* w, const uorf_decoder_grads* g, const uorf_decoder_bwd_args* a, int num_sms,
                        int* err_flag, cudaStream_t stream);
 }  // namespace uorf
@@ -176,8 +177,15 @@ int uorf_conv_split(const float* x, const float* gate, void* hi, void* lo, int64
                       "uorf_conv_split");
 }
 
-int uorf_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, const float* bias, float* y, int32_t n, int32_t h, int32_t w,
-                    int32_t c_in, int32_t c_out, int32_t relu, int32_t precision, void* stream) {
+size_t uorf_conv3x3_workspace_floats(int32_t n, int32_t h, int32_t w, int32_t c_in, int32_t c_out) {
+  DeviceCtx* c = ctx();
+  if (!c || n < 1 || h < 1 || w < 1 || c_in < 64 || c_out < 64) return 0;
+  const int s = uorf::conv3x3_splits(n, h, w, c_in, c_out, c->num_sms);
+  return s > 1 ? (size_t)s * n * h * w * c_out : 0;
+}
+
+int uorf_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, const float* bias, float* y, float* workspace, int32_t n, int32_t h,
+                    int32_t w, int32_t c_in, int32_t c_out, int32_t relu, int32_t precision, void* stream) {
   DeviceCtx* c = ctx();
   Range nvtx_range("uorf_conv3x3_x3");
   if (!c) return UORF_ERR_DEVICE;
@@ -185,8 +193,10 @@ int uorf_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, const
   if (n < 0 || h < 1 || w < 1 || c_in < 64 || c_out < 64 || (c_in & 63) || (c_out & 63))
     return fail(UORF_ERR_ARG, "uorf_conv3x3_x3: bad sizes (c_in, c_out must be multiples of 64)%s");
   if (precision != UORF_PREC_FP16X3 && precision != UORF_PREC_BF16X3) return fail(UORF_ERR_ARG, "uorf_conv3x3_x3: precision must be a x3 mode%s");
-  return check_launch(uorf::launch_conv3x3_x3(x_hi, x_lo, w_img, bias, y, n, h, w, c_in, c_out, relu, precision == UORF_PREC_FP16X3,
-                                              c->err_flag_dev, static_cast<cudaStream_t>(stream)), "uorf_conv3x3_x3");
+  const int splits = workspace ? uorf::conv3x3_splits(n, h, w, c_in, c_out, c->num_sms) : 1;
+  return check_launch(uorf::launch_conv3x3_x3(x_hi, x_lo, w_img, bias, y, workspace, splits, n, h, w, c_in, c_out, relu,
+                                              precision == UORF_PREC_FP16X3, c->num_sms, c->err_flag_dev, static_cast<cudaStream_t>(stream)),
+                      "uorf_conv3x3_x3");
 }
 
 int uorf_debug_flag(void) {

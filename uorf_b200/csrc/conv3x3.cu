@@ -36,8 +36,9 @@ struct ConvParams {
   const unsigned short* x_lo;
   const unsigned char* w_img;   // [c_out / 64][9][c_in / 64][hi 8 KB | lo 8 KB], tiles K-major, 128-byte swizzle
   const float* bias;            // [c_out] or null
-  float* y;                     // [pixels][c_out]
+  float* y;                     // [pixels][c_out]  (splits == 1), else partial sums [split][pixels][c_out] without bias / ReLU
   int n, h, w, c_in, c_out, relu;
+  int splits;                   // K iterations divided over gridDim.z CTAs
   int* err_flag;
 };
 
@@ -58,7 +59,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_x3_kernel(const ConvPar
   const uint32_t smem_a = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = p.c_in >> 6;
-  const int iters = 9 * kchunks;
+  const int iters_all = 9 * kchunks;
+  // split-K: this CTA walks K iterations [it0, it0 + iters) (layers with few pixel tiles would otherwise leave most SMs idle)
+  const int it0 = (int)(((long long)iters_all * blockIdx.z) / p.splits);
+  const int iters = (int)(((long long)iters_all * (blockIdx.z + 1)) / p.splits) - it0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kCvStages; ++s) {
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_x3_kernel(const ConvPar
       r_h[i] = (int)((px / p.w) % p.h);
       r_dst[i] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((chunk ^ (row & 7)) & 7) << 4));
     }
-    const unsigned char* w_tiles = p.w_img + (size_t)blockIdx.y * iters * (2 * kCvBBytes);
+    const unsigned char* w_tiles = p.w_img + ((size_t)blockIdx.y * iters_all + it0) * (2 * kCvBBytes);
     auto signal = [&](int it) {            // data of iteration `it` has landed: make it visible to the async proxy and arrive
       fence_proxy_async_smem();
       mbar_arrive(&bar_full[it % kCvStages]);
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_x3_kernel(const ConvPar
     for (int it = 0; it < iters; ++it) {
       const int s = it % kCvStages;
       if (it >= kCvStages) mbar_wait_lean(smem_u32(&bar_empty[s]), ((it / kCvStages) - 1) & 1, p.err_flag, 610);
-      const int tap = it / kchunks, kc = it - tap * kchunks;
+      const int tap = (it0 + it) / kchunks, kc = (it0 + it) - tap * kchunks;
       const int dy = tap / 3 - 1, dx = tap % 3 - 1;
       const long long shift = (long long)dy * p.w + dx;
       const uint32_t st = smem_a + s * kCvStageBytes;
@@ -157,8 +161,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_x3_kernel(const ConvPar
     const long long pix = (long long)blockIdx.x * kCvTileM + t;
     const bool row_ok = pix < npix;
     const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float* dst = p.y + pix * p.c_out + blockIdx.y * kCvTileN;
-    const float* bias = p.bias ? p.bias + blockIdx.y * kCvTileN : nullptr;
+    float* dst = p.y + ((long long)blockIdx.z * npix + pix) * p.c_out + blockIdx.y * kCvTileN;
+    const bool final_out = p.splits == 1;
+    const float* bias = (p.bias && final_out) ? p.bias + blockIdx.y * kCvTileN : nullptr;
     const int nacc = iters < kCvAcc ? iters : kCvAcc;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv3x3_x3_kernel(const ConvPar
             const float4 b = __ldg(reinterpret_cast<const float4*>(bias + 32 * half + 4 * q));
             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
-          if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (p.relu && final_out) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           *reinterpret_cast<float4*>(dst + 32 * half + 4 * q) = o;
         }
       }
@@ -215,6 +220,33 @@ __global__ void __launch_bounds__(256) conv_split_kernel(const float* __restrict
   }
 }
 
+// split-K: y = [relu](bias + sum of the partial sums), fixed order (deterministic)
+__global__ void __launch_bounds__(256) conv_reduce_kernel(const float4* __restrict__ part, int splits, long long n4, const float* __restrict__ bias,
+                                                          int c_out, int relu, float4* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = __ldg(part + i);
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = __ldg(part + (long long)s * n4 + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (i % (c_out / 4)));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    y[i] = a;
+  }
+}
+
+int conv3x3_splits(int n, int h, int w, int c_in, int c_out, int num_sms) {
+  const long long npix = (long long)n * h * w;
+  const long long ctas = ((npix + kCvTileM - 1) / kCvTileM) * (c_out / kCvTileN);
+  const int iters = 9 * (c_in / 64);
+  int s = 1;
+  while (s < 8 && ctas * s * 2 <= num_sms && iters / (s * 2) >= 9) s *= 2;   // keep >= 9 K iterations per CTA
+  return s;
+}
+
 int launch_conv_split(const float* x, const float* gate, void* hi, void* lo, long long n, int f16, int num_sms, cudaStream_t stream) {
   if (n <= 0) return UORF_OK;
   const long long npairs = n / 2;
@@ -225,20 +257,22 @@ int launch_conv_split(const float* x, const float* gate, void* hi, void* lo, lon
   return finish_launch(1);
 }
 
-int launch_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, const float* bias, float* y, int n, int h, int w, int c_in,
-                      int c_out, int relu, int f16, int* err_flag, cudaStream_t stream) {
+int launch_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, const float* bias, float* y, float* partials, int splits, int n,
+                      int h, int w, int c_in, int c_out, int relu, int f16, int num_sms, int* err_flag, cudaStream_t stream) {
   ConvParams p;
   p.x_hi = static_cast<const unsigned short*>(x_hi);
   p.x_lo = static_cast<const unsigned short*>(x_lo);
   p.w_img = static_cast<const unsigned char*>(w_img);
   p.bias = bias;
-  p.y = y;
+  if (splits < 1 || (splits > 1 && partials == nullptr)) splits = 1;
+  p.y = splits > 1 ? partials : y;
+  p.splits = splits;
   p.n = n; p.h = h; p.w = w; p.c_in = c_in; p.c_out = c_out; p.relu = relu;
   p.err_flag = err_flag;
   const long long npix = (long long)n * h * w;
   if (npix <= 0) return UORF_OK;
   const size_t smem = 1024 + (size_t)kCvStages * kCvStageBytes;
-  dim3 grid((unsigned)((npix + kCvTileM - 1) / kCvTileM), (unsigned)(c_out / kCvTileN));
+  dim3 grid((unsigned)((npix + kCvTileM - 1) / kCvTileM), (unsigned)(c_out / kCvTileN), (unsigned)splits);
   auto launch = [&](auto kern) -> int {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return UORF_ERR_DEVICE;
     kern<<<grid, kCvThreads, smem, stream>>>(p);
@@ -246,6 +280,14 @@ int launch_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, con
   };
   const int rc = f16 ? launch(conv3x3_x3_kernel<true>) : launch(conv3x3_x3_kernel<false>);
   if (rc != UORF_OK) return rc;
+  if (splits > 1) {
+    const long long n4 = npix * c_out / 4;
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+    conv_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(partials), splits, n4, bias, c_out, relu,
+                                                            reinterpret_cast<float4*>(y));
+    return finish_launch(2);
+  }
   return finish_launch(1);
 }
 

@@ -855,8 +855,10 @@ def _conv3x3_x3(x_nhwc: torch.Tensor, gate: Optional[torch.Tensor], w_img: torch
     hi, lo = _conv_split(x_nhwc, gate, precision)
     y = torch.empty((n, h, w, c_out), dtype=torch.float32, device=x_nhwc.device)
     with _on(x_nhwc):
-        check(lib().uorf_conv3x3_x3(hi.data_ptr(), lo.data_ptr(), w_img.data_ptr(), _ptr(bias), y.data_ptr(), n, h, w, c_in, c_out,
-                                    int(relu), _lib.PRECISIONS[precision], _stream(x_nhwc)), "uorf_conv3x3_x3")
+        nws = int(lib().uorf_conv3x3_workspace_floats(n, h, w, c_in, c_out))
+        ws = torch.empty(nws, dtype=torch.float32, device=x_nhwc.device) if nws else None
+        check(lib().uorf_conv3x3_x3(hi.data_ptr(), lo.data_ptr(), w_img.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(ws), n, h, w, c_in,
+                                    c_out, int(relu), _lib.PRECISIONS[precision], _stream(x_nhwc)), "uorf_conv3x3_x3")
     return y
 
 
