@@ -583,7 +583,8 @@ def bench_train(ctx, args, c, with_reference_gpu=True):
     ach = 4.0 * fl * pts / (bwd_ms * 1e-3) / 1e12 if bwd_ms else None
     rec = {"metric": "train_scene_steps_per_sec", "workload": c["workload"], "value": world * args.steps / (ms_total * 1e-3),
            "unit": "scene-steps/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms_total / args.steps, "scaling": "weak",
-           "dtype": args.precision + " forward; fp16 tensor-core backward with fp32 accumulation; fp32 elsewhere",
+           "dtype": args.precision + " decoder forward; fp16 tensor-core decoder backward with fp32 accumulation; VGG convolutions fp16x3 forward / "
+                    "bf16x3 data gradient on the tensor cores (fp32 parity); fp32 elsewhere",
            "config": dict(c, step="Encoder+SlotAttention+sampling+decoder+compositing fwd+bwd, MSE + VGG16-relu4_3 perceptual "
                           "(random-init VGG, weight_percept 0.006 active: epoch = percept_in), Adam (reference uorf_nogan_model.py:229-245)",
                           parallelism=f"scene-sharded data parallel x{world}: one scene per rank, ONE flat-bucket gradient all-reduce (NCCL, average)"),

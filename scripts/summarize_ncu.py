@@ -87,6 +87,26 @@ def decoder(tag, precision, repname="prof_decoder.ncu-rep", title=None, outname=
         print("traffic not updated:", e)
 
 
+def conv(tag, repname="prof_conv.ncu-rep"):
+    """one row per captured launch of the tensor-core convolution kernel"""
+    rep = os.path.join(G, repname)
+    if not os.path.exists(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, data = rows[0], rows[2:]
+    cols = ["Kernel Name", "Grid Size", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct"]
+    cols = [c for c in cols if c in hdr]
+    out = [f"# {tag}: `ncu --set full --clock-control none` of conv3x3_x3_kernel launches inside one training step (VGG16 perceptual loss, "
+           "8 images of 64 x 64; launches 15-17 of the step: block-3 / block-4 layers)", "",
+           "| " + " | ".join(cols) + " |", "|" + "---|" * len(cols)]
+    for r in data:
+        out.append("| " + " | ".join(r[hdr.index(c)][:60] for c in cols) + " |")
+    open(os.path.join(P, f"{tag}_conv_ncu.md"), "w").write("\n".join(out) + "\n")
+
+
 def encoder(tag, repname="prof_encoder.ncu-rep"):
     """one row per launch of the six (seven with `bottom`) encoder convolution kernels of one Encoder.forward"""
     rep = os.path.join(G, repname)
@@ -113,7 +133,7 @@ if __name__ == "__main__":
     prec = sys.argv[2] if len(sys.argv) > 2 else "fp16x3"
     os.makedirs(P, exist_ok=True)
     launches(tag)
-    launches(tag, "launches_train.csv", "launches_train", "python bench.py --mode train --steps 2 --warmup 1 --no-graph")
+    launches(tag, "launches_train.csv", "launches_train", "python bench.py --mode train --steps 2 --warmup 1 --no-graph --no-cpu-baseline")
     decoder(tag, prec)
     decoder(tag, "bf16", "prof_decoder_bf16.ncu-rep")
     decoder(tag, "", "prof_composite.ncu-rep", "composite_fwd_kernel launch (scripts/bench_kernels.py 32: 524,288 rays x 64 samples)",
@@ -122,5 +142,6 @@ if __name__ == "__main__":
             f"{tag}_sample_coords_ncu.md")
     decoder(tag, "", "prof_decoder_bwd.ncu-rep", "decoder_bwd_kernel launch (bench.py --mode train: K=8, 64^3 frustum, 4 views)",
             f"{tag}_decoder_bwd_ncu.md")
+    conv(tag)
     encoder(tag)
     print("wrote profiles/%s_*.md" % tag)
