@@ -132,6 +132,9 @@ class uorfNoGanModel:
         self.slot_noise = None        # (noise_fg, noise_bg) overrides the randn draws of SlotAttention
         self.crop_override = None     # (h0, w0) overrides the fine-stage randint draws
         self.process_group = None     # set (with world size > 1) for data-parallel training
+        # every gradient in ONE persistent flat buffer the backward kernels write into (also on one GPU: the autograd path costs
+        # an AccumulateGrad `add` launch per parameter - 83 per step - and per-tensor fills); False: plain autograd accumulation
+        self.flat_grad_bucket = bool(getattr(opt, "flat_grad_bucket", True))
         self._flat_grad = None        # data-parallel mode: the flat gradient bucket every .grad is a view of
 
     def parameters(self):
@@ -301,7 +304,7 @@ class uorfNoGanModel:
             # drop every reference to the previous step's autograd graph (its AccumulateGrad nodes belong to the eager
             # stream and would invalidate the capture) and let the captured backward allocate .grad in the graph's pool
             self.loss_recon = self.loss_perc = None
-            if self.process_group is None:     # (data-parallel mode keeps its persistent flat gradient views)
+            if self.process_group is None and not self.flat_grad_bucket:     # (the flat bucket keeps its persistent gradient views)
                 for p_ in self.parameters():
                     p_.grad = None
             torch.cuda.synchronize(self.device)
@@ -332,12 +335,13 @@ class uorfNoGanModel:
 
     def _step_eager(self, ret_grad=False, epoch=0):
         self.forward(epoch)
-        if self.process_group is not None:
+        if self.process_group is not None or self.flat_grad_bucket:
             flat = self._flat_gradients()
             flat.zero_()               # one fill; the kernels overwrite their slices, anything routed through autograd accumulates
             self.backward()
-            from .sharded import allreduce_flat
-            allreduce_flat(flat, self.process_group)
+            if self.process_group is not None:
+                from .sharded import allreduce_flat
+                allreduce_flat(flat, self.process_group)
         else:
             # optimizer.zero_grad() of the reference (:235-236, zero in place): one multi-tensor launch instead of one fill per tensor
             grads = [p.grad for p in self.parameters() if p.grad is not None]
