@@ -662,6 +662,11 @@ def test_full_size_render_properties():
         msum = masks.sum(0).squeeze(-1)
         assert ((msum - dens_sum / (dens_sum + 1e-5)).abs().max().item()) < 1e-5   # masks = dens / (sum dens + 1e-5)
         assert (unmasked[..., :3].min().item() >= 0) and (unmasked[..., :3].max().item() <= 1)
+        # share of points check_decoder_outputs leaves out of the masks / masked comparison (total density <= 1e-2, where
+        # dens / (sum + 1e-5) amplifies rounding by up to 1e5): reported, and bounded so the comparison keeps its meaning
+        excluded = (dens_sum <= 1e-2).float().mean().item()
+        print(f"full-size render: {100 * excluded:.2f} % of the {P} points have total density <= 1e-2 (masks compared on the rest)")
+        assert excluded < 0.5
         # the kernel's tiling must not matter: a permuted point set yields the permuted outputs, bit for bit
         perm = torch.randperm(P, generator=gen)[:300000].to(dev())
         sub = coords[perm].contiguous()
