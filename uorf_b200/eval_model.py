@@ -132,7 +132,18 @@ class uorfEvalModel:
         if src.is_cuda:
             self.nss2cam0 = src[0:1].inverse()
         else:
-            self.nss2cam0 = src[0:1].inverse().to(self.device, non_blocking=True)
+            # staged through PINNED memory (a small ring, so that a caller may keep several steps in flight): an H2D copy from
+            # pageable memory makes the driver wait for the stream's earlier work before it returns, which serialises the host
+            # with the previous step's render
+            inv = src[0:1].inverse()
+            ring = getattr(self, "_pin_ring", None)
+            if ring is None or ring[0].shape != inv.shape or ring[0].dtype != inv.dtype:
+                ring = self._pin_ring = [torch.empty_like(inv).pin_memory() for _ in range(4)]
+                self._pin_next = 0
+            stage = ring[self._pin_next]
+            self._pin_next = (self._pin_next + 1) % len(ring)
+            stage.copy_(inv)
+            self.nss2cam0 = stage.to(self.device, non_blocking=True)
         self.image_paths = input.get("paths", [])
         for k in ("masks", "mask_idx", "fg_idx", "obj_idxs"):
             if k in input:
