@@ -412,9 +412,15 @@ constexpr bool kX3Psm = false;
 constexpr bool kX3Psm = true;
 #endif
 constexpr int kPsmChannels = 4;
+// The half-tile kernel also runs the one-pass fast modes (-DUORF_FWD_1PASS_HALFTILE=1, parity-green), but there the whole-layer
+// form of this file is faster (bf16: 1.51 ms against 1.75 ms): with a third of the MMAs and a light epilogue the doubled hand-offs
+// cost more than the overlap gains.
+#ifndef UORF_FWD_1PASS_HALFTILE
+#define UORF_FWD_1PASS_HALFTILE 0
+#endif
 // The shipped 3-pass kernel is decoder_fwd_x3.cu (half-tile pipelining, one issuer code path); -DUORF_FWD_X3_V1 (A-B builds) keeps
 // the whole-layer hand-off form of this file.
-int launch_decoder_fwd_x3(const DecFwdParams& p, bool f16, int num_sms, cudaStream_t stream);
+int launch_decoder_fwd_x3(const DecFwdParams& p, int passes, bool f16, int num_sms, cudaStream_t stream);
 
 // floats of `workspace`: the background sweep's raw outputs [P][4] + (PSM) the per-channel head stash [SMs][4][K][128][4]
 size_t decoder_fwd_workspace_floats(long long P, int K, int num_sms) {
@@ -462,7 +468,10 @@ int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, c
     return UORF_OK;
   };
 #ifndef UORF_FWD_X3_V1
-  if (psm) return launch_decoder_fwd_x3(p, f16, num_sms, stream);
+  if (psm) return launch_decoder_fwd_x3(p, 3, f16, num_sms, stream);
+#endif
+#if UORF_FWD_1PASS_HALFTILE
+  if (passes == 1) return launch_decoder_fwd_x3(p, 1, f16, num_sms, stream);   // one-pass fast modes on the half-tile kernel
 #endif
   int rc;
   if (psm) rc = f16 ? launch(decoder_fwd_kernel<3, true, kPsmChannels, true>, Cfg<3, kPsmChannels, true>::THREADS)

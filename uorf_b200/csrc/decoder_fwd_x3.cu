@@ -135,6 +135,35 @@ __device__ __forceinline__ void x3_arrive(uint32_t bar_addr) {
 #endif
 }
 
+// MMA groups of the issuer for PASSES = 3 (hi.hi + lo.hi + hi.lo) and PASSES = 1 (hi.hi only: the one-pass fast modes)
+// NK K-steps of the TMEM operand H (hi at a_hi, lo at a_lo) against the weight tile pair (b_hi, b_lo)
+template <int PASSES, int NK>
+__device__ __forceinline__ void x3_group_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc, uint32_t acc) {
+  if constexpr (PASSES == 3) {
+    mma_group_ts<NK, 3>(d, a_hi, a_lo, b_hi, b_lo, idesc, acc);
+  } else {
+    static_assert(NK == 2 || NK == 4, "unsupported group");
+    if constexpr (NK == 4) {
+      mma_group_ts<4, 1>(d, a_hi, a_lo, b_hi, b_lo, idesc, acc);
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred e, p, t;\n\t.reg .b32 a1;\n\t.reg .b64 h1;\n\t"
+          "elect.sync _|e, 0xffffffff;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, %4, %4;\n\t"
+          "add.u32 a1, %1, 8;\n\tadd.u64 h1, %2, 2;\n\t"
+          "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+          "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], h1, %3, t;\n\t"
+          "}" ::"r"(d), "r"(a_hi), "l"(b_hi), "r"(idesc), "r"(acc) : "memory");
+    }
+  }
+}
+// the two encoding K-steps from the shared-memory strip (SS)
+template <int PASSES>
+__device__ __forceinline__ void x3_group_p(uint32_t d, uint64_t pdesc, uint64_t b_hi, uint64_t b_lo, uint32_t idesc, uint32_t acc) {
+  if constexpr (PASSES == 3) mma_group_p_ss(d, pdesc, b_hi, b_lo, idesc, acc);
+  else mma_group_ss<2, 2, 2>(d, pdesc, b_hi, idesc, acc);
+}
+
 // One half-layer of the epilogue, in two steps.
 // x3_convert: 32 accumulator columns -> registers; the next layer's bias (fetched by the caller BEFORE it waited for the accumulator,
 //   so no shared-memory latency sits behind the wait) is stored over the columns just read; [+ wx * xe]; ReLU + hi/lo split.
@@ -143,7 +172,7 @@ __device__ __forceinline__ void x3_load_bias(uint32_t addr, float4 (&b)[8]) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) b[q] = lds128(addr + 16 * q);
 }
-template <bool F16, bool STORE = false>
+template <int PASSES, bool F16, bool STORE = false>
 __device__ __forceinline__ void x3_convert(uint32_t t_d, bool has_wx, uint32_t wx, float xe, bool has_bias, const float4 (&b)[8],
                                            uint32_t (&hi)[16], uint32_t (&lo)[16], uint32_t t_hhi = 0, uint32_t t_hlo = 0) {
   uint32_t r[32];
@@ -173,20 +202,24 @@ __device__ __forceinline__ void x3_convert(uint32_t t_d, bool has_wx, uint32_t w
   }
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
-    if (F16) {
+    if (PASSES == 1) {
+      hi[q] = pack2_relu<F16>(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]));
+      lo[q] = hi[q];      // (not stored; keeps the ordering anchor of the caller meaningful)
+    } else if (F16) {
       split2_relu<F16>(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]), hi[q], lo[q]);
     } else {   // bf16: keep round-to-nearest on the hi part (truncation would cost one of its 16 bits)
       split2<F16>(fmaxf(__uint_as_float(r[2 * q]), 0.f), fmaxf(__uint_as_float(r[2 * q + 1]), 0.f), hi[q], lo[q]);
     }
     if (STORE && (q & 7) == 7) {   // E(1): operand words stored as soon as eight are ready (nothing gates them)
       tmem_st8(t_hhi + (q - 7), &hi[q - 7]);
-      tmem_st8(t_hlo + (q - 7), &lo[q - 7]);
+      if (PASSES == 3) tmem_st8(t_hlo + (q - 7), &lo[q - 7]);
     }
   }
 }
 
-template <bool F16>
+template <int PASSES, bool F16>
 __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const DecFwdParams p) {
+  constexpr int NPL = PASSES == 3 ? 2 : 1;     // weight planes (hi [+ lo])
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_w;
   __shared__ __align__(8) X3Bars bars[kX3Ch];
@@ -197,8 +230,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int K = p.K;
-  const int w_region = 2 * kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
-  const float* s_params = reinterpret_cast<const float*>(smem + 2 * kPlaneBytes);
+  const int w_region = NPL * kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
+  const float* s_params = reinterpret_cast<const float*>(smem + NPL * kPlaneBytes);
   unsigned char* s_strips = smem + ((w_region + 1023) & ~1023);   // [channel][128 rows x 128 B]
 
   if (threadIdx.x == 0) {
@@ -232,8 +265,8 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
       const int nslots = phase == 0 ? 1 : K - 1;
       if (warp == kX3EpiWarps && lane == 0) {
         fence_proxy_async_smem();
-        const unsigned char* src = p.image + (phase ? blob_fg_offset(3) : 0);
-        const uint32_t bytes = (uint32_t)blob_bytes_one(3, nslots);
+        const unsigned char* src = p.image + (phase ? blob_fg_offset(PASSES) : 0);
+        const uint32_t bytes = (uint32_t)blob_bytes_one(PASSES, nslots);
         mbar_arrive_expect_tx(&bar_w, bytes);
         for (uint32_t off = 0; off < bytes; off += 32768u) {
           const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
@@ -266,40 +299,40 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
             ++n_stage;
             // hidden-layer weight tile of MMA stage st: t1 t2 | t4 t5 t6 | head t7; encoding tiles t0 (st 0), t3 (st 3)
             const uint32_t wt = w_smem + (uint32_t)(st < 3 ? st : st + 1) * kTileBytes;
-            const uint64_t b_hi = make_sdesc_sw128(wt), b_lo = make_sdesc_sw128(wt + kPlaneBytes);
+            const uint64_t b_hi = make_sdesc_sw128(wt), b_lo = make_sdesc_sw128(wt + (NPL - 1) * kPlaneBytes);
             x3_wait(cba, par, p.err_flag, 200 + st);
             tc_fence_after();
             TLX_ISS(0x60 + st);
             if (st == 0) {
               // layer before.0: encoding operand only (the slot-latent part is the preloaded bias); one N = 64 group
-              mma_group_p_ss(td, pdesc, b_hi, b_lo, id64, 1u);
+              x3_group_p<PASSES>(td, pdesc, b_hi, b_lo, id64, 1u);
               if (UORF_X3_KSPLIT) x3_wait(cba + 8, par, p.err_flag, 210);
               tc_commit_elect(&cb.d[0]);
               tc_commit_elect(&cb.d[1]);
             } else if (st == 6) {
               // heads: N = 32 (fg) / 16 (bg), no preloaded bias; K-halves as they arrive
-              mma_group_ts<2, 3>(td, th, tl, b_hi, b_lo, idh, 0u);
+              x3_group_ts<PASSES, 2>(td, th, tl, b_hi, b_lo, idh, 0u);
               if (UORF_X3_KSPLIT) {
                 x3_wait(cba + 8, par, p.err_flag, 216);
                 tc_fence_after();
               }
-              mma_group_ts<2, 3>(td, th + 16, tl + 16, b_hi + 4, b_lo + 4, idh, 1u);
+              x3_group_ts<PASSES, 2>(td, th + 16, tl + 16, b_hi + 4, b_lo + 4, idh, 1u);
               tc_commit_elect(&cb.d[0]);
               tc_commit_elect(&cb.d[1]);
             } else {
-              const uint64_t p_hi = make_sdesc_sw128(w_smem + 3 * kTileBytes), p_lo = make_sdesc_sw128(w_smem + 3 * kTileBytes + kPlaneBytes);
-              if (st == 3) mma_group_p_ss(td, pdesc, p_hi, p_lo, id32, 1u);                      // P(0)
-              mma_group_ts<2, 3>(td, th, tl, b_hi, b_lo, id32, 1u);                              // G(0,0)
+              const uint64_t p_hi = make_sdesc_sw128(w_smem + 3 * kTileBytes), p_lo = make_sdesc_sw128(w_smem + 3 * kTileBytes + (NPL - 1) * kPlaneBytes);
+              if (st == 3) x3_group_p<PASSES>(td, pdesc, p_hi, p_lo, id32, 1u);                      // P(0)
+              x3_group_ts<PASSES, 2>(td, th, tl, b_hi, b_lo, id32, 1u);                              // G(0,0)
               if (UORF_X3_KSPLIT) {
                 x3_wait(cba + 8, par, p.err_flag, 210 + st);
                 tc_fence_after();
               }
               TLX_ISS(0x70 + st);
-              mma_group_ts<2, 3>(td, th + 16, tl + 16, b_hi + 4, b_lo + 4, id32, 1u);            // G(1,0)
+              x3_group_ts<PASSES, 2>(td, th + 16, tl + 16, b_hi + 4, b_lo + 4, id32, 1u);            // G(1,0)
               tc_commit_elect(&cb.d[0]);
               TLX_ISS(0x80 + st);
-              if (st == 3) mma_group_p_ss(td + 32, pdesc, p_hi + 256, p_lo + 256, id32, 1u);     // P(1): weight rows 32..63
-              mma_group_ts<4, 3>(td + 32, th, tl, b_hi + 256, b_lo + 256, id32, 1u);             // G(0,1) G(1,1)
+              if (st == 3) x3_group_p<PASSES>(td + 32, pdesc, p_hi + 256, p_lo + 256, id32, 1u);     // P(1): weight rows 32..63
+              x3_group_ts<PASSES, 4>(td + 32, th, tl, b_hi + 256, b_lo + 256, id32, 1u);             // G(0,1) G(1,1)
               tc_commit_elect(&cb.d[1]);
             }
             TLX_ISS(0x90 + st);
@@ -398,7 +431,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
               if (!p.fixed_locality) outside = fabsf(x) > p.locality_ratio || fabsf(y) > p.locality_ratio || fabsf(z) > p.locality_ratio;
             }
             float v[kPosencK];
-            posenc48<false>(x, y, z, v);
+            posenc48<PASSES == 1>(x, y, z, v);
             posenc_store_smem<F16>(v, strip, t);
             fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
             x_last = v[kPosencMma3];           // cos(16 z): added by FMA in the epilogues of layers before.0 / after.0
@@ -448,7 +481,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
             if (!UORF_X3_PREFETCH) x3_load_bias(nb, b0);
             {
               uint32_t hi[16], lo[16];
-              x3_convert<F16>(td, has_wx, wx, x_last, has_bias, b0, hi, lo);
+              x3_convert<PASSES, F16>(td, has_wx, wx, x_last, has_bias, b0, hi, lo);
               if (UORF_X3_PREFETCH) x3_load_bias(nb + 128, b1);   // second half's bias: fetched under the gate wait
               TLX_EPI(0x20 + st);
               // The conversions have to be complete BEFORE the gate (the point of E(0) is to run under G(.,1)); ptxas otherwise sinks
@@ -461,7 +494,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
               x3_wait_d(cba + any, bar_id + (int)any, 1, par, p.err_flag, 310);
               TLX_EPI(0x30 + st);
               tmem_st16(th, hi);
-              tmem_st16(tl, lo);
+              if (PASSES == 3) tmem_st16(tl, lo);
               if (UORF_X3_KSPLIT) {
                 tc_wait_st();
                 tc_fence_before();
@@ -473,13 +506,13 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
               uint32_t hi[16], lo[16];
               if (!UORF_X3_PREFETCH) x3_load_bias(nb + 128, b1);
 #if UORF_X3_EARLY_ST
-              x3_convert<F16, true>(td + 32, has_wx, wx + 128, x_last, has_bias, b1, hi, lo, th + 16, tl + 16);
+              x3_convert<PASSES, F16, true>(td + 32, has_wx, wx + 128, x_last, has_bias, b1, hi, lo, th + 16, tl + 16);
 #else
-              x3_convert<F16>(td + 32, has_wx, wx + 128, x_last, has_bias, b1, hi, lo);
+              x3_convert<PASSES, F16>(td + 32, has_wx, wx + 128, x_last, has_bias, b1, hi, lo);
               TLX_EPI(0x28 + st);
               TLX_EPI(0x38 + st);
               tmem_st16(th + 16, hi);
-              tmem_st16(tl + 16, lo);
+              if (PASSES == 3) tmem_st16(tl + 16, lo);
 #endif
               tc_wait_st();
               tc_fence_before();
@@ -539,9 +572,9 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
             const float dens = fmaxf(rw.w, 0.f);
             const float m = dens * rdenom;
             float4 u;
-            u.x = rgb_act<UORF_X3_FAST_ACT != 0>(rw.x);
-            u.y = rgb_act<UORF_X3_FAST_ACT != 0>(rw.y);
-            u.z = rgb_act<UORF_X3_FAST_ACT != 0>(rw.z);
+            u.x = rgb_act<(PASSES == 1) || (UORF_X3_FAST_ACT != 0)>(rw.x);
+            u.y = rgb_act<(PASSES == 1) || (UORF_X3_FAST_ACT != 0)>(rw.y);
+            u.z = rgb_act<(PASSES == 1) || (UORF_X3_FAST_ACT != 0)>(rw.z);
             u.w = dens;
             if (p.noise != nullptr && valid) u.w = dens + p.dens_noise * __ldg(p.noise + (long long)k * p.P + pt);
             const float4 mk = make_float4(u.x * m, u.y * m, u.z * m, u.w * m);
@@ -563,13 +596,13 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
   }
 }
 
-size_t decoder_fwd_x3_smem_bytes(int K) {
-  const int w_region = 2 * kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
+size_t decoder_fwd_x3_smem_bytes(int K, int passes) {
+  const int w_region = (passes == 3 ? 2 : 1) * kPlaneBytes + kParamBytes + (K - 1 > 1 ? K - 1 : 1) * kSlotBiasBytes;
   return 1024 + ((w_region + 1023) & ~1023) + (size_t)kX3Ch * kX3StripBytes;
 }
 
-int launch_decoder_fwd_x3(const DecFwdParams& p, bool f16, int num_sms, cudaStream_t stream) {
-  const size_t smem = decoder_fwd_x3_smem_bytes(p.K);
+int launch_decoder_fwd_x3(const DecFwdParams& p, int passes, bool f16, int num_sms, cudaStream_t stream) {
+  const size_t smem = decoder_fwd_x3_smem_bytes(p.K, passes);
   if (smem > 227 * 1024) return UORF_ERR_UNSUPPORTED;
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   if (grid < 1) return UORF_OK;
@@ -578,7 +611,8 @@ int launch_decoder_fwd_x3(const DecFwdParams& p, bool f16, int num_sms, cudaStre
     kern<<<grid, kX3Threads, smem, stream>>>(p);
     return UORF_OK;
   };
-  const int rc = f16 ? launch(decoder_fwd_x3_kernel<true>) : launch(decoder_fwd_x3_kernel<false>);
+  const int rc = passes == 3 ? (f16 ? launch(decoder_fwd_x3_kernel<3, true>) : launch(decoder_fwd_x3_kernel<3, false>))
+                             : (f16 ? launch(decoder_fwd_x3_kernel<1, true>) : launch(decoder_fwd_x3_kernel<1, false>));
   if (rc != UORF_OK) return rc;
   return finish_launch(1);
 }
