@@ -47,6 +47,28 @@ constexpr int kTileM128 = 128;
 #ifndef UORF_BWD_NQ
 #define UORF_BWD_NQ 2
 #endif
+// Forward-recompute steps 1..6 take their A operand (the previous layer's activations) from TMEM (tcgen05.mma TS form: 34.6 instead
+// of 52 cycles per K-step) and hand it over without a proxy fence: the activations are still written to their shared-memory tile
+// for the backward half (dW operand, ReLU gate), but nothing of the recompute half waits for those stores - the proxy fence of the
+// first backward hand-off covers them.
+#ifndef UORF_BWD_TS_FWD
+#define UORF_BWD_TS_FWD 1
+#endif
+constexpr int kBColA = 352;   // TMEM columns 352..383: 16-bit activation operand of the recompute steps (32 columns = 64 features)
+// D (+)= A[tmem, 4 K-steps of 8 columns] . B[smem tile]^T under one elect (A columns + 8 j, B descriptor + 2 j per K-step)
+__device__ __forceinline__ void mma_group_ts4(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred e, p, t;\n\t.reg .b32 a1, a2, a3;\n\t.reg .b64 h1, h2, h3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, %4, %4;\n\t"
+      "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+      "add.u64 h1, %2, 2;\n\tadd.u64 h2, %2, 4;\n\tadd.u64 h3, %2, 6;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], h1, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], h2, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], h3, %3, t;\n\t"
+      "}" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
 // one mbarrier arrival per epilogue WARP (after __syncwarp) instead of one per thread
 #ifndef UORF_BWD_WARP_ARRIVE
 #define UORF_BWD_WARP_ARRIVE 1
@@ -178,6 +200,21 @@ __device__ __forceinline__ void store_cols16(unsigned char* tile, int t, int chu
     }
     *reinterpret_cast<uint4*>(row + ((((chunk0 + c) ^ (t & 7)) & 7) << 4)) = q;
   }
+}
+// store_cols16 + the same packed words into `taddr` (TMEM operand columns of this thread's slice)
+template <int NC>
+__device__ __forceinline__ void store_cols16_tmem(unsigned char* tile, int t, int chunk0, const float (&v)[NC], uint32_t taddr) {
+  unsigned char* row = tile + (t >> 3) * 1024 + (t & 7) * 128;
+  uint32_t w[NC / 2];
+#pragma unroll
+  for (int c = 0; c < NC / 8; ++c) {
+    uint4 q;
+    q.x = pack2_relu<true>(v[8 * c + 0], v[8 * c + 1]); q.y = pack2_relu<true>(v[8 * c + 2], v[8 * c + 3]);
+    q.z = pack2_relu<true>(v[8 * c + 4], v[8 * c + 5]); q.w = pack2_relu<true>(v[8 * c + 6], v[8 * c + 7]);
+    w[4 * c] = q.x; w[4 * c + 1] = q.y; w[4 * c + 2] = q.z; w[4 * c + 3] = q.w;
+    *reinterpret_cast<uint4*>(row + ((((chunk0 + c) ^ (t & 7)) & 7) << 4)) = q;
+  }
+  if constexpr (NC == 32) tmem_st16(taddr, w); else tmem_st8(taddr, w);
 }
 template <int NC>
 __device__ __forceinline__ void gate_load_cols(const unsigned char* x_tile, int t, int chunk0, uint4 (&x)[NC / 8]) {
@@ -315,7 +352,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
       // counts are compile-time, so the issuer's path between wake-up and commit is short straight-line code
       auto fwd = [&](auto XI, auto WI, auto NKS, uint32_t idesc, bool first) {
         constexpr int xi = decltype(XI)::value, wi = decltype(WI)::value, nk = decltype(NKS)::value;
-        mma_group_ss<nk, 2, 2>(tbu + kBColD, make_sdesc_sw128(x_s + xi * 16384), make_sdesc_sw128(w_s + wi * kTileBytes), idesc, first ? 0u : 1u);
+        if constexpr (UORF_BWD_TS_FWD && xi >= 1) {   // activations of the previous layer: TMEM operand
+          static_assert(nk == 4, "hidden layers have four K-steps");
+          mma_group_ts4(tbu + kBColD, tbu + kBColA, make_sdesc_sw128(w_s + wi * kTileBytes), idesc, first ? 0u : 1u);
+        } else {
+          mma_group_ss<nk, 2, 2>(tbu + kBColD, make_sdesc_sw128(x_s + xi * 16384), make_sdesc_sw128(w_s + wi * kTileBytes), idesc, first ? 0u : 1u);
+        }
       };
       // dX = dZ[buf] . W[tile wi] : A K-major (K = out features), B = MN-major view of the weight tile
       auto dx = [&](auto BUF, auto WI, auto NKS) {
@@ -390,6 +432,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
       auto publish = [&]() {  // make this thread's shared-memory tile writes visible to the tensor core, then signal
         TLB_EPI(0x50);
         fence_proxy_async_smem();
+        tc_fence_before();
+#if UORF_BWD_WARP_ARRIVE
+        __syncwarp();
+        if (lane == 0) mbar_arrive_addr(bar_a_addr);
+#else
+        mbar_arrive_addr(bar_a_addr);
+#endif
+        TLB_EPI(0x40);
+      };
+      auto publish_tmem = [&]() {  // hand-off of a TMEM operand: the tcgen05.st has to be complete, no proxy fence
+        TLB_EPI(0x50);
+        tc_wait_st();
         tc_fence_before();
 #if UORF_BWD_WARP_ARRIVE
         __syncwarp();
@@ -497,8 +551,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
             for (int q = 0; q < kBwdCols / 4; ++q) {
               v[4 * q + 0] += b[q].x; v[4 * q + 1] += b[q].y; v[4 * q + 2] += b[q].z; v[4 * q + 3] += b[q].w;
             }
-            store_cols16<kBwdCols, true>(s_x + st * 16384, t, chunk0, v);
-            publish();
+            if (UORF_BWD_TS_FWD) {
+              store_cols16_tmem<kBwdCols>(s_x + st * 16384, t, chunk0, v, tb + kBColA + c0 / 2);
+              publish_tmem();
+            } else {
+              store_cols16<kBwdCols, true>(s_x + st * 16384, t, chunk0, v);
+              publish();
+            }
           }
           // ---- head forward + backward seed (the 17 head rows live in the first column half) ----
           wait_d(307);
