@@ -54,6 +54,12 @@ constexpr int kTileM128 = 128;
 #ifndef UORF_BWD_TS_FWD
 #define UORF_BWD_TS_FWD 1
 #endif
+// The backward steps do the same for dX_l = dZ_l . W_l: dZ goes to TMEM (operand of the TS MMAs, handed over first) AND to its
+// shared-memory tile (operand of the dW / bias-gradient MMAs, which need it contraction-major); the proxy fence for the tile and
+// a second barrier `bar_b` follow the first hand-off, so the fence leaves the dependent chain.
+#ifndef UORF_BWD_TS_BWD
+#define UORF_BWD_TS_BWD 1
+#endif
 constexpr int kBColA = 352;   // TMEM columns 352..383: 16-bit activation operand of the recompute steps (32 columns = 64 features)
 // D (+)= A[tmem, 4 K-steps of 8 columns] . B[smem tile]^T under one elect (A columns + 8 j, B descriptor + 2 j per K-step)
 __device__ __forceinline__ void mma_group_ts4(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
@@ -68,6 +74,30 @@ __device__ __forceinline__ void mma_group_ts4(uint32_t d, uint32_t a, uint64_t b
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], h2, %3, t;\n\t"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], h3, %3, t;\n\t"
       "}" ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// dX groups: A[tmem] . B, B = MN-major view of a weight tile (descriptor + 128 per K-step), D overwritten by the first MMA
+__device__ __forceinline__ void mma_group_ts4_mn(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred e, f, t;\n\t.reg .b32 a1, a2, a3;\n\t.reg .b64 h1, h2, h3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 f, %3, %3;\n\tsetp.eq.b32 t, %3, %3;\n\t"
+      "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+      "add.u64 h1, %2, 128;\n\tadd.u64 h2, %2, 256;\n\tadd.u64 h3, %2, 384;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, f;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], h1, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], h2, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], h3, %3, t;\n\t"
+      "}" ::"r"(d), "r"(a), "l"(b), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void mma_group_ts2_mn(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred e, f, t;\n\t.reg .b32 a1;\n\t.reg .b64 h1;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 f, %3, %3;\n\tsetp.eq.b32 t, %3, %3;\n\t"
+      "add.u32 a1, %1, 8;\n\tadd.u64 h1, %2, 128;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, f;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], h1, %3, t;\n\t"
+      "}" ::"r"(d), "r"(a), "l"(b), "r"(idesc) : "memory");
 }
 // one mbarrier arrival per epilogue WARP (after __syncwarp) instead of one per thread
 #ifndef UORF_BWD_WARP_ARRIVE
@@ -243,6 +273,38 @@ __device__ __forceinline__ void gate_store_cols(const uint4 (&xs)[NC / 8], unsig
     *reinterpret_cast<uint4*>(dz_tile + roff + coff) = make_uint4(q[0], q[1], q[2], q[3]);
   }
 }
+// gate_store_cols + the same packed words into `taddr` (TMEM operand columns of this thread's slice)
+template <int NC>
+__device__ __forceinline__ void gate_store_cols_tmem(const uint4 (&xs)[NC / 8], unsigned char* dz_tile, int t, int chunk0, const float (&g)[NC],
+                                                     uint32_t taddr) {
+  const int roff = (t >> 3) * 1024 + (t & 7) * 128;
+  uint32_t w[NC / 2];
+#pragma unroll
+  for (int c = 0; c < NC / 8; ++c) {
+    const int coff = (((chunk0 + c) ^ (t & 7)) & 7) << 4;
+    const uint32_t xw[4] = {xs[c].x, xs[c].y, xs[c].z, xs[c].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t m;
+      asm("{\n\t.reg .b32 z;\n\tmov.b32 z, 0;\n\tset.ne.u32.f16x2 %0, %1, z;\n\t}" : "=r"(m) : "r"(xw[i]));   // 0xFFFF per non-zero half
+      w[4 * c + i] = pack2<true>(g[8 * c + 2 * i], g[8 * c + 2 * i + 1]) & m;
+    }
+    *reinterpret_cast<uint4*>(dz_tile + roff + coff) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+  }
+  if constexpr (NC == 32) tmem_st16(taddr, w); else tmem_st8(taddr, w);
+}
+// store_half16 (fp16, no ReLU) + the same 16 packed words into TMEM
+__device__ __forceinline__ void store_half16_tmem(unsigned char* tile, int t, int half, const float (&v)[32], uint32_t taddr) {
+  unsigned char* row = tile + (t >> 3) * 1024 + (t & 7) * 128;
+  uint32_t w[16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[4 * c + i] = pack2<true>(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
+    *reinterpret_cast<uint4*>(row + ((((4 * half + c) ^ (t & 7)) & 7) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+  }
+  tmem_st16(taddr, w);
+}
 template <int NC>
 __device__ __forceinline__ void load_dcols(uint32_t taddr, float (&v)[NC]) {
   uint32_t r[NC];
@@ -262,7 +324,7 @@ __device__ __forceinline__ void load_d32(uint32_t taddr, float (&v)[32]) {
 
 __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBwdParams p) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_d;
+  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_d, bar_b;   // bar_b: dZ tile of a backward step fenced for the dW MMAs
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_red[4][64];
 
@@ -282,6 +344,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
     mbar_init(&bar_w, 1);
     mbar_init(&bar_a, UORF_BWD_WARP_ARRIVE ? kBwdEpiWarps : kTileM128 * kBwdNQ);
     mbar_init(&bar_d, 1);
+    mbar_init(&bar_b, UORF_BWD_WARP_ARRIVE ? kBwdEpiWarps : kTileM128 * kBwdNQ);
     fence_mbar_init();
   }
   if (warp == kBwdEpiWarps) {
@@ -302,7 +365,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
   }
 
   const float gscale = grad_scale(__ldg(p.draw_amax));
-  uint32_t n_a = 0, n_d = 0;
+  uint32_t n_a = 0, n_d = 0, n_b = 0;   // completions consumed so far (parity = count & 1); they run on across the two phases
   for (int phase = 0; phase < 2; ++phase) {
     const int nslots = phase == 0 ? 1 : K - 1;
     if (warp == kBwdEpiWarps && lane == 0) {
@@ -360,9 +423,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
         }
       };
       // dX = dZ[buf] . W[tile wi] : A K-major (K = out features), B = MN-major view of the weight tile
+      const uint32_t bar_b_addr = smem_u32(&bar_b);
+      auto wait_b = [&]() {   // the dZ tile of this step is visible to the tensor core (only with UORF_BWD_TS_BWD)
+        if (UORF_BWD_TS_BWD) {
+          mbar_wait_lean(bar_b_addr, n_b & 1, p.err_flag, 230);
+          ++n_b;
+          tc_fence_after();
+        }
+      };
       auto dx = [&](auto BUF, auto WI, auto NKS) {
         constexpr int buf = decltype(BUF)::value, wi = decltype(WI)::value, nk = decltype(NKS)::value;
-        mma_group_ss<nk, 2, 128>(tbu + kBColD, make_sdesc_sw128(dz_s + buf * 16384), sdesc_mn(w_s + wi * kTileBytes), id_dx, 0u);
+        if constexpr (UORF_BWD_TS_BWD) {
+          if constexpr (nk == 4) mma_group_ts4_mn(tbu + kBColD, tbu + kBColA, sdesc_mn(w_s + wi * kTileBytes), id_dx);
+          else mma_group_ts2_mn(tbu + kBColD, tbu + kBColA, sdesc_mn(w_s + wi * kTileBytes), id_dx);
+        } else {
+          mma_group_ss<nk, 2, 128>(tbu + kBColD, make_sdesc_sw128(dz_s + buf * 16384), sdesc_mn(w_s + wi * kTileBytes), id_dx, 0u);
+        }
       };
       // dW[acc] += dZ[buf]^T . X[tile xi] : both MN-major views, contraction over the 128 points (8 K-steps)
       auto dw = [&](auto ACC, auto BUF, auto XI, uint32_t idesc) {
@@ -395,13 +471,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
           wait_a(205); fwd(I_(5), I_(6), I_(4), id_fwd64, true); tc_commit_elect(&bar_d);
           wait_a(206); fwd(I_(6), I_(7), I_(4), id_fwd_head, true); tc_commit_elect(&bar_d);
           // ---- backward ----   (dZ buffers alternate: head -> 0, layer 5 -> 1, 4 -> 0, 3 -> 1, 2 -> 0, 1 -> 1, 0 -> 0)
-          wait_a(207); dx(I_(0), I_(7), I_(2)); tc_commit_elect(&bar_d); dw(I_(7), I_(0), I_(6), id_dw64); dwb(I_(4), I_(0));
-          wait_a(208); dx(I_(1), I_(6), I_(4)); tc_commit_elect(&bar_d); dw(I_(6), I_(1), I_(5), id_dw64); dwb(I_(3), I_(1));
-          wait_a(209); dx(I_(0), I_(5), I_(4)); tc_commit_elect(&bar_d); dw(I_(5), I_(0), I_(4), id_dw64); dwb(I_(2), I_(0));
-          wait_a(210); dx(I_(1), I_(4), I_(4)); tc_commit_elect(&bar_d); dw(I_(4), I_(1), I_(3), id_dw64); dw(I_(3), I_(1), I_(0), id_dw48);
-          wait_a(211); dx(I_(0), I_(2), I_(4)); tc_commit_elect(&bar_d); dw(I_(2), I_(0), I_(2), id_dw64); dwb(I_(1), I_(0));
-          wait_a(212); dx(I_(1), I_(1), I_(4)); tc_commit_elect(&bar_d); dw(I_(1), I_(1), I_(1), id_dw64); dwb(I_(0), I_(1));
-          wait_a(213); dw(I_(0), I_(0), I_(0), id_dw48); tc_commit_elect(&bar_d);   // all tiles free for the next slot once this lands
+          wait_a(207); dx(I_(0), I_(7), I_(2)); tc_commit_elect(&bar_d); wait_b(); dw(I_(7), I_(0), I_(6), id_dw64); dwb(I_(4), I_(0));
+          wait_a(208); dx(I_(1), I_(6), I_(4)); tc_commit_elect(&bar_d); wait_b(); dw(I_(6), I_(1), I_(5), id_dw64); dwb(I_(3), I_(1));
+          wait_a(209); dx(I_(0), I_(5), I_(4)); tc_commit_elect(&bar_d); wait_b(); dw(I_(5), I_(0), I_(4), id_dw64); dwb(I_(2), I_(0));
+          wait_a(210); dx(I_(1), I_(4), I_(4)); tc_commit_elect(&bar_d); wait_b(); dw(I_(4), I_(1), I_(3), id_dw64); dw(I_(3), I_(1), I_(0), id_dw48);
+          wait_a(211); dx(I_(0), I_(2), I_(4)); tc_commit_elect(&bar_d); wait_b(); dw(I_(2), I_(0), I_(2), id_dw64); dwb(I_(1), I_(0));
+          wait_a(212); dx(I_(1), I_(1), I_(4)); tc_commit_elect(&bar_d); wait_b(); dw(I_(1), I_(1), I_(1), id_dw64); dwb(I_(0), I_(1));
+          wait_a(213); wait_b(); dw(I_(0), I_(0), I_(0), id_dw48); tc_commit_elect(&bar_d);   // all tiles free for the next slot once this lands
         }
       }
       __syncwarp();
@@ -452,6 +528,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
         mbar_arrive_addr(bar_a_addr);
 #endif
         TLB_EPI(0x40);
+      };
+      const uint32_t bar_b_addr = opaque(smem_u32(&bar_b));
+      auto publish_tile = [&]() {  // second hand-off of a backward step: the shared-memory dZ tile is visible to the tensor core
+        fence_proxy_async_smem();
+#if UORF_BWD_WARP_ARRIVE
+        __syncwarp();
+        if (lane == 0) mbar_arrive_addr(bar_b_addr);
+#else
+        mbar_arrive_addr(bar_b_addr);
+#endif
       };
       for (int it = 0;; ++it) {
         const long long tile = (long long)blockIdx.x + (long long)gridDim.x * it;
@@ -589,9 +675,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
                 dzh[kHeadShapeRow] = (p.locality && outside) ? 0.f : dr.w;   // model.py:147-148 zeroes sigma outside the box
               }
             }
-            if (half < 2) store_half16<true>(s_dz, t, half, dzh);   // the second half writes the zero padding of the head's dZ tile
+            if (UORF_BWD_TS_BWD) {
+              if (half < 2) store_half16_tmem(s_dz, t, half, dzh, tb + kBColA + 16 * half);
+            } else {
+              if (half < 2) store_half16<true>(s_dz, t, half, dzh);   // the second half writes the zero padding of the head's dZ tile
+            }
           }
-          publish();
+          if (UORF_BWD_TS_BWD) { publish_tmem(); publish_tile(); } else publish();
           // ---- layers 5..0 ----
 #pragma unroll 1
           for (int l = 5; l >= 0; --l) {
@@ -600,8 +690,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
             wait_d(320 + l);
             float g[kBwdCols];
             load_dcols<kBwdCols>(tb + kBColD + c0, g);      // dX_{l+1}
-            gate_store_cols<kBwdCols>(xg, s_dz + ((l & 1) ? 16384 : 0), t, chunk0, g);   // dZ_l = dX_{l+1} * [X_{l+1} > 0]
-            publish();
+            if (UORF_BWD_TS_BWD) {
+              gate_store_cols_tmem<kBwdCols>(xg, s_dz + ((l & 1) ? 16384 : 0), t, chunk0, g, tb + kBColA + c0 / 2);
+              publish_tmem();
+              publish_tile();
+            } else {
+              gate_store_cols<kBwdCols>(xg, s_dz + ((l & 1) ? 16384 : 0), t, chunk0, g);   // dZ_l = dX_{l+1} * [X_{l+1} > 0]
+              publish();
+            }
           }
         }
       }
