@@ -51,6 +51,11 @@
 #ifndef UORF_X3_EARLY_ST
 #define UORF_X3_EARLY_ST 0
 #endif
+// E(0) also reads the second accumulator half (after its gate) and preloads it before the first hand-off: the issuer runs G(0,1)
+// and P(1) under E(1), only G(1,0) and G(1,1) remain behind the second hand-off
+#ifndef UORF_X3_EARLY_D1
+#define UORF_X3_EARLY_D1 0
+#endif
 #ifndef UORF_X3_RELAY
 #define UORF_X3_RELAY 0
 #endif
@@ -171,6 +176,45 @@ __device__ __forceinline__ void x3_group_p(uint32_t d, uint64_t pdesc, uint64_t 
 __device__ __forceinline__ void x3_load_bias(uint32_t addr, float4 (&b)[8]) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) b[q] = lds128(addr + 16 * q);
+}
+// [+ wx * xe]; ReLU + hi/lo split of 32 accumulator values already in registers
+template <int PASSES, bool F16>
+__device__ __forceinline__ void x3_split32(uint32_t (&r)[32], bool has_wx, uint32_t wx, float xe, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+  if (has_wx) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 w = lds128(wx + 16 * q);
+      r[4 * q + 0] = __float_as_uint(fmaf(w.x, xe, __uint_as_float(r[4 * q + 0])));
+      r[4 * q + 1] = __float_as_uint(fmaf(w.y, xe, __uint_as_float(r[4 * q + 1])));
+      r[4 * q + 2] = __float_as_uint(fmaf(w.z, xe, __uint_as_float(r[4 * q + 2])));
+      r[4 * q + 3] = __float_as_uint(fmaf(w.w, xe, __uint_as_float(r[4 * q + 3])));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    if (PASSES == 1) {
+      hi[q] = pack2_relu<F16>(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]));
+      lo[q] = hi[q];
+    } else if (F16) {
+      split2_relu<F16>(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]), hi[q], lo[q]);
+    } else {
+      split2<F16>(fmaxf(__uint_as_float(r[2 * q]), 0.f), fmaxf(__uint_as_float(r[2 * q + 1]), 0.f), hi[q], lo[q]);
+    }
+  }
+}
+// 32 accumulator columns <- bias (32 floats at shared address `addr`)
+__device__ __forceinline__ void x3_preload32(uint32_t t_d, uint32_t addr) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t w[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = lds128(addr + 64 * h + 16 * q);
+      w[4 * q + 0] = __float_as_uint(b.x); w[4 * q + 1] = __float_as_uint(b.y);
+      w[4 * q + 2] = __float_as_uint(b.z); w[4 * q + 3] = __float_as_uint(b.w);
+    }
+    tmem_st16(t_d + 16 * h, w);
+  }
 }
 template <int PASSES, bool F16, bool STORE = false>
 __device__ __forceinline__ void x3_convert(uint32_t t_d, bool has_wx, uint32_t wx, float xe, bool has_bias, const float4 (&b)[8],
@@ -323,6 +367,10 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
               const uint64_t p_hi = make_sdesc_sw128(w_smem + 3 * kTileBytes), p_lo = make_sdesc_sw128(w_smem + 3 * kTileBytes + (NPL - 1) * kPlaneBytes);
               if (st == 3) x3_group_p<PASSES>(td, pdesc, p_hi, p_lo, id32, 1u);                      // P(0)
               x3_group_ts<PASSES, 2>(td, th, tl, b_hi, b_lo, id32, 1u);                              // G(0,0)
+#if UORF_X3_EARLY_D1
+              if (st == 3) x3_group_p<PASSES>(td + 32, pdesc, p_hi + 256, p_lo + 256, id32, 1u);     // P(1): weight rows 32..63
+              x3_group_ts<PASSES, 2>(td + 32, th, tl, b_hi + 256, b_lo + 256, id32, 1u);             // G(0,1)
+#endif
               if (UORF_X3_KSPLIT) {
                 x3_wait(cba + 8, par, p.err_flag, 210 + st);
                 tc_fence_after();
@@ -331,8 +379,12 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
               x3_group_ts<PASSES, 2>(td, th + 16, tl + 16, b_hi + 4, b_lo + 4, id32, 1u);            // G(1,0)
               tc_commit_elect(&cb.d[0]);
               TLX_ISS(0x80 + st);
+#if UORF_X3_EARLY_D1
+              x3_group_ts<PASSES, 2>(td + 32, th + 16, tl + 16, b_hi + 260, b_lo + 260, id32, 1u);   // G(1,1)
+#else
               if (st == 3) x3_group_p<PASSES>(td + 32, pdesc, p_hi + 256, p_lo + 256, id32, 1u);     // P(1): weight rows 32..63
               x3_group_ts<PASSES, 4>(td + 32, th, tl, b_hi + 256, b_lo + 256, id32, 1u);             // G(0,1) G(1,1)
+#endif
               tc_commit_elect(&cb.d[1]);
             }
             TLX_ISS(0x90 + st);
@@ -493,6 +545,30 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
               any *= (uint32_t)p.zero;
               x3_wait_d(cba + any, bar_id + (int)any, 1, par, p.err_flag, 310);
               TLX_EPI(0x30 + st);
+#if UORF_X3_EARLY_D1
+              // d[1] has been waited for: the second accumulator half is read (and the next layer's bias stored over it) BEFORE the
+              // first hand-off, so a[0] also means "D[32:64] is free" and the issuer can run G(0,1) [and P(1)] under E(1) as well
+              uint32_t r1[32];
+              tmem_ld32(td + 32, r1);
+              tmem_st16(th, hi);
+              if (PASSES == 3) tmem_st16(tl, lo);
+              tc_wait_ld();
+              if (has_bias) x3_preload32(td + 32, nb + 128);
+              tc_wait_st();
+              tc_fence_before();
+              x3_arrive(cba);
+              TLX_EPI(0x40 + st);
+              x3_split32<PASSES, F16>(r1, has_wx, wx + 128, x_last, hi, lo);
+              TLX_EPI(0x28 + st);
+              TLX_EPI(0x38 + st);
+              tmem_st16(th + 16, hi);
+              if (PASSES == 3) tmem_st16(tl + 16, lo);
+              tc_wait_st();
+              tc_fence_before();
+              x3_arrive(cba + 8);
+              TLX_EPI(0x48 + st);
+            }
+#else
               tmem_st16(th, hi);
               if (PASSES == 3) tmem_st16(tl, lo);
               if (UORF_X3_KSPLIT) {
@@ -519,6 +595,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
               x3_arrive(cba + (UORF_X3_KSPLIT ? 8 : 0));
               TLX_EPI(0x48 + st);
             }
+#endif
           }
           // ---- stage 7: heads ----
           {
