@@ -452,6 +452,7 @@ int launch_decoder_fwd(const uorf_decoder_args* a, int num_sms, int* err_flag, c
   p.num_tiles = (int)((a->P + kTileM - 1) / kTileM);
   p.err_flag = err_flag;
   p.zero = 0;
+  p.discard_bg = (reinterpret_cast<uintptr_t>(a->workspace) & 127u) == 0;
   const int passes = a->precision >= 3 ? 3 : 1;
   const bool f16 = (a->precision % 2) == 0;
   const bool psm = passes == 3 && kX3Psm;

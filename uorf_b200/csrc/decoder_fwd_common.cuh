@@ -84,6 +84,7 @@ struct DecFwdParams {
   int fixed_locality;
   int locality;
   int num_tiles;
+  int discard_bg;       // scratch_bg is 128-byte aligned: read-back lines may be dropped from L2 (decoder_fwd_x3.cu)
   int zero;             // always 0: run-time zero for scheduling anchors (decoder_fwd_x3.cu)
   int* err_flag;
 };

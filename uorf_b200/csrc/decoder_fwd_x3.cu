@@ -56,6 +56,9 @@
 #ifndef UORF_X3_EARLY_D1
 #define UORF_X3_EARLY_D1 0
 #endif
+#ifndef UORF_X3_DISCARD_BG
+#define UORF_X3_DISCARD_BG 0
+#endif
 #ifndef UORF_X3_RELAY
 #define UORF_X3_RELAY 0
 #endif
@@ -104,6 +107,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
 __device__ __forceinline__ void st_global_hint(float4* ptr, const float4& v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
                : "memory");
+}
+// After its read-back a scratch line is dead: dropping it from L2 (no write-back) also saves the 67 MB the dirty lines would cost
+// when they are finally evicted.  128-byte aligned line wholly inside the scratch.
+__device__ __forceinline__ void l2_discard_line(const void* ptr) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(ptr) : "memory");
 }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -638,6 +646,14 @@ __global__ void __launch_bounds__(kX3Threads, 1) decoder_fwd_x3_kernel(const Dec
         if (phase == 1) {
           // ---- cross-slot composition (model.py:151-159) ----
           if (valid) stash[t] = bgv;
+#if UORF_X3_DISCARD_BG
+          // every lane's read-back value has been consumed: lanes 0..3 drop the warp's four scratch lines (32 points x 16 B)
+          __syncwarp();
+          if (p.discard_bg && lane < 4) {
+            const long long line_pt = pt - lane + 8 * lane;
+            if (line_pt + 8 <= p.P) l2_discard_line(p.scratch_bg + line_pt);
+          }
+#endif
           float S = 0.f;
 #pragma unroll 4
           for (int k = 0; k < K; ++k) S += fmaxf(stash[k * kTileM + t].w, 0.f);
