@@ -260,10 +260,28 @@ int uorf_slot_attention_backward(const uorf_slot_attention_weights* w, const uor
  * [ca][*][*] and src_b [cb][h_in][w_in] (torch.cat, :49,:58,:60); with upsample_a != 0, src_a is stored at half resolution
  * [ca][h_in/2][w_in/2] and read through nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) (:27-32).
  * weight_t is the Conv2d weight transposed to [ca+cb][3][3][c_out]; out [c_out][h_out][w_out], h_out = (h_in-1)/stride + 1.
- * Batch 1 (the drivers encode view 0 only, uorf_eval_model.py:121-123).  Training keeps torch autograd / cuDNN.
+ * Batch 1 (the drivers encode view 0 only, uorf_eval_model.py:121-123).
  * ------------------------------------------------------------------------------------------- */
 int uorf_encoder_conv3x3(const float* src_a, int32_t ca, int32_t upsample_a, const float* src_b, int32_t cb, const float* weight_t,
                          const float* bias, int32_t c_out, int32_t h_in, int32_t w_in, int32_t stride, float* out, void* stream);
+
+/* Backward of the same layer, fp32 - what `loss.backward()` (models/uorf_nogan_model.py:181-183) runs through autograd / cuDNN
+ * for each Conv2d + ReLU of the Encoder (models/model.py:19-34).  kept_out [c_out][h_out][w_out] is the layer's forward output: the
+ * ReLU gate (grad_out counts where kept_out > 0) is applied while reading, no gated copy is made.
+ *   _dgrad: grad_in [c_in][h_in][w_in] (all input channels of the layer: the caller splits the concatenation and takes the
+ *           upsample backward), added to grad_in's contents when accumulate != 0 (second gradient of a skip connection); weight_g = the Conv2d weight as [c_out][3][3][c_in] (permute(0, 2, 3, 1)).
+ *   _wgrad: grad_weight [c_out][ca+cb][3][3] and grad_bias [c_out]; the layer input is described as in the forward call (two
+ *           sources, source A optionally through the upsample); workspace: uorf_encoder_wgrad_workspace_floats(...) floats.
+ * Sums run in a fixed order (bit-reproducible); they differ from cuDNN's by fp32 rounding only. */
+int uorf_encoder_conv3x3_dgrad(const float* grad_out, const float* kept_out, int32_t c_out, const float* weight_g, int32_t c_in,
+                               int32_t h_in, int32_t w_in, int32_t stride, int32_t accumulate, float* grad_in, void* stream);
+/* backward of nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) (models/model.py:27-32): grad_hi [c][2 h_lo][2 w_lo]
+ * -> grad_lo [c][h_lo][w_lo], as a fixed-order gather (the library op scatters with atomics) */
+int uorf_encoder_upsample2x_bwd(const float* grad_hi, int32_t c, int32_t h_lo, int32_t w_lo, float* grad_lo, void* stream);
+int64_t uorf_encoder_wgrad_workspace_floats(int32_t c_in, int32_t c_out, int32_t h_in, int32_t w_in, int32_t stride);
+int uorf_encoder_conv3x3_wgrad(const float* src_a, int32_t ca, int32_t upsample_a, const float* src_b, int32_t cb, const float* grad_out,
+                               const float* kept_out, int32_t c_out, int32_t h_in, int32_t w_in, int32_t stride, float* workspace,
+                               float* grad_weight, float* grad_bias, void* stream);
 
 /* -----------------------------------------------------------------------------------------------
  * Kernel 6: 3x3 convolution (stride 1, pad 1) of the perceptual-loss network, fp32-parity on the tensor cores.

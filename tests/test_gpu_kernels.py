@@ -758,6 +758,47 @@ def test_encoder_inference_kernels_match_cudnn(Z, S, bottom):
     assert maxerr(res[True][1], res[False][1]) < 2e-4 * max(1e-6, res[False][1].abs().max().item())
 
 
+@pytest.mark.parametrize("Z,S,bottom", [(64, 64, False), (40, 32, False), (64, 128, True), (64, 24, False), (64, 256, False)])
+def test_encoder_backward_kernels_match_autograd(Z, S, bottom):
+    """fp32 gradient kernels (weight / bias / data gradient per layer, gates and cat / upsample folded into the loads) against
+    autograd through the torch layers (cuDNN): same sums in another order"""
+    from uorf_b200.modules import Encoder
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(11)
+    enc = Encoder(3, z_dim=Z, bottom=bottom).to(dev())
+    for p_ in enc.parameters():
+        torch.nn.init.normal_(p_, 0.0, 0.05)
+    x = torch.rand(1, 3, S, S, device=dev()) * 2 - 1
+    probe = None
+    res = {}
+    for mode in ("torch", "cudnn", "kernels", "kernels_again", "sink"):
+        enc.use_kernels_in_training = mode != "torch"
+        enc.backward_kernels = mode != "cudnn"
+        enc.grad_sink = None
+        enc.zero_grad()
+        if mode == "sink":
+            enc.grad_sink = {n: torch.full_like(p_, float("nan")) for n, p_ in enc.named_parameters()}
+        y = enc(x)
+        if probe is None:
+            probe = torch.randn_like(y)
+        (y * probe).sum().backward()
+        res[mode] = dict(enc.grad_sink) if mode == "sink" else {n: p_.grad.clone() for n, p_ in enc.named_parameters()}
+        if mode == "sink":
+            assert all(p_.grad is None for p_ in enc.parameters())
+    enc.grad_sink = None
+    for n, ref_g in res["cudnn"].items():
+        # same kept activations, cuDNN's convolution_backward per layer: fp32 rounding only (cuDNN's own weight gradients are
+        # 3e-6 .. 1.2e-5 from a float64 evaluation at these sizes, the kernels 1e-7 .. 5e-7: scripts/enc_bwd_check.py)
+        tol = 5e-5 * max(1e-6, ref_g.abs().max().item())
+        assert maxerr(res["kernels"][n], ref_g) < tol, (n, maxerr(res["kernels"][n], ref_g), ref_g.abs().max().item())
+        # autograd through the torch layers: its forward rounds differently, so a few ReLU gates of near-zero activations flip
+        # (one flipped pixel moves a weight gradient by |g x| ~ 1 of a sum of ~300)
+        t = res["torch"][n]
+        assert maxerr(res["kernels"][n], t) < 2e-2 * max(1e-6, t.abs().max().item()), (n, maxerr(res["kernels"][n], t), t.abs().max().item())
+        assert torch.equal(res["kernels"][n], res["kernels_again"][n]), f"not reproducible: {n}"
+        assert torch.equal(res["kernels"][n], res["sink"][n]), f"sink path differs: {n}"
+
+
 # ------------------------------------------------------------------------------------------------------
 # adversarial driver (uorf_gan_model.py:137-311): generator step with the GAN term, discriminator step with R1
 # ------------------------------------------------------------------------------------------------------

@@ -15,6 +15,13 @@ namespace uorf {
 int launch_sample_coords(const uorf_frustum* f, const float* z_cam, const float* cam2world, int n_views, int scale, int crop_h,
                          int crop_w, const int* crop_origin, int Hc, int Wc, int ray_major, float* coords, float* z_vals, float* ray_dir,
                          int num_sms, cudaStream_t stream);
+int launch_encoder_dgrad3x3(const float* grad_out, const float* kept_out, int c_out, const float* weight_g, int c_in, int h_in, int w_in,
+                            int stride, int accumulate, float* grad_in, cudaStream_t stream);
+int launch_encoder_upsample2x_bwd(const float* grad_hi, int c, int h_lo, int w_lo, float* grad_lo, cudaStream_t stream);
+size_t encoder_wgrad_workspace_floats(int c_in, int c_out, int h_in, int w_in, int stride);
+int launch_encoder_wgrad3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* grad_out, const float* kept_out,
+                            int c_out, int h_in, int w_in, int stride, float* workspace, float* grad_weight, float* grad_bias,
+                            cudaStream_t stream);
 int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* weight_t, const float* bias,
                            int c_out, int h_in, int w_in, int stride, float* out, cudaStream_t stream);
 int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int K, int Z, int passes, int f16, void* image,
@@ -151,6 +158,49 @@ int uorf_init(int device) {
   std::call_once(c->once, init_device, c, device);
   if (c->status != UORF_OK) return fail(c->status, "%s", c->why);
   return UORF_OK;
+}
+
+int uorf_encoder_conv3x3_dgrad(const float* grad_out, const float* kept_out, int32_t c_out, const float* weight_g, int32_t c_in,
+                               int32_t h_in, int32_t w_in, int32_t stride, int32_t accumulate, float* grad_in, void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_encoder_conv3x3_dgrad");
+  if (!c) return UORF_ERR_DEVICE;
+  if (!grad_out || !kept_out || !weight_g || !grad_in) return fail(UORF_ERR_ARG, "uorf_encoder_conv3x3_dgrad: null pointer%s");
+  if (c_out < 1 || c_in < 1 || h_in < 1 || w_in < 1 || (stride != 1 && stride != 2))
+    return fail(UORF_ERR_ARG, "uorf_encoder_conv3x3_dgrad: bad sizes (stride must be 1 or 2)%s");
+  return check_launch(uorf::launch_encoder_dgrad3x3(grad_out, kept_out, c_out, weight_g, c_in, h_in, w_in, stride, accumulate != 0, grad_in,
+                                                    static_cast<cudaStream_t>(stream)), "uorf_encoder_conv3x3_dgrad");
+}
+
+int uorf_encoder_upsample2x_bwd(const float* grad_hi, int32_t c, int32_t h_lo, int32_t w_lo, float* grad_lo, void* stream) {
+  DeviceCtx* dc = ctx();
+  Range nvtx_range("uorf_encoder_upsample2x_bwd");
+  if (!dc) return UORF_ERR_DEVICE;
+  if (!grad_hi || !grad_lo) return fail(UORF_ERR_ARG, "uorf_encoder_upsample2x_bwd: null pointer%s");
+  if (c < 1 || h_lo < 1 || w_lo < 1) return fail(UORF_ERR_ARG, "uorf_encoder_upsample2x_bwd: bad sizes%s");
+  return check_launch(uorf::launch_encoder_upsample2x_bwd(grad_hi, c, h_lo, w_lo, grad_lo, static_cast<cudaStream_t>(stream)),
+                      "uorf_encoder_upsample2x_bwd");
+}
+
+int64_t uorf_encoder_wgrad_workspace_floats(int32_t c_in, int32_t c_out, int32_t h_in, int32_t w_in, int32_t stride) {
+  if (c_in < 1 || c_out < 1 || h_in < 1 || w_in < 1 || (stride != 1 && stride != 2)) return 0;
+  return (int64_t)uorf::encoder_wgrad_workspace_floats(c_in, c_out, h_in, w_in, stride);
+}
+
+int uorf_encoder_conv3x3_wgrad(const float* src_a, int32_t ca, int32_t upsample_a, const float* src_b, int32_t cb, const float* grad_out,
+                               const float* kept_out, int32_t c_out, int32_t h_in, int32_t w_in, int32_t stride, float* workspace,
+                               float* grad_weight, float* grad_bias, void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_encoder_conv3x3_wgrad");
+  if (!c) return UORF_ERR_DEVICE;
+  if (!src_a || !grad_out || !kept_out || !workspace || !grad_weight || !grad_bias || (cb > 0 && !src_b))
+    return fail(UORF_ERR_ARG, "uorf_encoder_conv3x3_wgrad: null pointer%s");
+  if (ca < 1 || cb < 0 || c_out < 1 || h_in < 1 || w_in < 1 || (stride != 1 && stride != 2))
+    return fail(UORF_ERR_ARG, "uorf_encoder_conv3x3_wgrad: bad sizes (stride must be 1 or 2)%s");
+  if (upsample_a && ((h_in | w_in) & 1)) return fail(UORF_ERR_ARG, "uorf_encoder_conv3x3_wgrad: upsampled source needs even h_in, w_in%s");
+  return check_launch(uorf::launch_encoder_wgrad3x3(src_a, ca, upsample_a, src_b, cb, grad_out, kept_out, c_out, h_in, w_in, stride,
+                                                    workspace, grad_weight, grad_bias, static_cast<cudaStream_t>(stream)),
+                      "uorf_encoder_conv3x3_wgrad");
 }
 
 int uorf_encoder_conv3x3(const float* src_a, int32_t ca, int32_t upsample_a, const float* src_b, int32_t cb, const float* weight_t,

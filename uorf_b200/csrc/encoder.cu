@@ -30,14 +30,21 @@ struct EncConvParams {
   int c_out, h_in, w_in, h_out, w_out;
   float* out;                               // [c_out][h_out][w_out]
   int split;                                // CTAs per cluster sharing one output tile (chunk c goes to cluster rank c % split)
+  const float* gate_a;                      // data-gradient modes: src_a is a gradient, taken where gate_a > 0 (the ReLU of the kept output)
+  int h_a, w_a;                             // data-gradient modes: stored size of src_a / gate_a (h_in / 2 when zero-inserted)
+  int accumulate;                           // data-gradient modes: out += result (the skip connection's second gradient)
 };
 
 // One staged input element: the raw global loads (four taps when read through the upsample) stay in registers while the
 // FFMA loop of the previous chunk runs; the interpolation arithmetic happens when the element is written to shared memory,
 // so nothing waits on the loads before the loop.  Everything about an element that does not depend on the chunk (patch
 // position, tap offsets, interpolation weights) is computed once per thread before the channel loop.
-template <bool UP> struct EncSlot;
-template <> struct EncSlot<false> {
+// Slot modes: 0 plain, 1 source A through the bilinear upsample, 2 / 3 data gradient of a stride-1 / stride-2 layer: the "input" is
+// the output gradient behind its ReLU gate, for stride 2 spread over the even positions of a zero-filled image twice the size
+// (a transposed convolution is a stride-1 convolution of that image with the flipped kernel).
+constexpr int kSlotPlain = 0, kSlotUp = 1, kSlotGrad = 2, kSlotGradZi = 3;
+template <int MODE> struct EncSlot;
+template <> struct EncSlot<kSlotPlain> {
   int pk;                                    // (channel within chunk << 16) | y * w_in + x, or -1: padding / beyond the patch
   float v;
   __device__ __forceinline__ void setup(const EncConvParams& p, int i, int y, int x, bool in_patch) {
@@ -50,7 +57,26 @@ template <> struct EncSlot<false> {
   }
   __device__ __forceinline__ float value() const { return v; }
 };
-template <> struct EncSlot<true> {
+template <int MODE> struct EncSlot {      // kSlotGrad / kSlotGradZi
+  int pk;                                    // (channel within chunk << 16) | offset inside one stored channel, or -1
+  float v;
+  __device__ __forceinline__ void setup(const EncConvParams& p, int i, int y, int x, bool in_patch) {
+    bool ok = in_patch && y >= 0 && y < p.h_in && x >= 0 && x < p.w_in;
+    if (MODE == kSlotGradZi) {
+      ok = ok && !((y | x) & 1);
+      y >>= 1; x >>= 1;
+      ok = ok && y < p.h_a && x < p.w_a;
+    }
+    pk = ok ? ((i << 16) | (y * p.w_a + x)) : -1;
+  }
+  __device__ __forceinline__ void load(const EncConvParams& p, int ic0, int cin) {
+    const int ic = ic0 + (pk >> 16), off = ic * (p.h_a * p.w_a) + (pk & 0xffff);
+    v = 0.f;
+    if (pk >= 0 && ic < cin) v = __ldg(p.gate_a + off) > 0.f ? __ldg(p.src_a + off) : 0.f;
+  }
+  __device__ __forceinline__ float value() const { return v; }
+};
+template <> struct EncSlot<kSlotUp> {
   int pk;                                    // as above (full-resolution offset, used for src_b channels)
   unsigned o0, o1;                           // low-resolution tap offsets of src_a: (y0,x0) | (y0,x1) << 16, (y1,x0) | (y1,x1) << 16
   float ly, lx;
@@ -84,8 +110,10 @@ template <> struct EncSlot<true> {
   }
 };
 
-template <int STRIDE, bool UP>
+template <int STRIDE, int MODE>
 __global__ void __launch_bounds__(kEncThreads, 1) encoder_conv3x3_kernel(const EncConvParams p) {
+  constexpr bool UP = MODE == kSlotUp;
+  constexpr bool LINEAR = MODE >= kSlotGrad;            // data gradient: no bias, no ReLU
   constexpr int PH = (kEncTile - 1) * STRIDE + 3;       // input patch side: 10 (stride 1) / 17 (stride 2)
   constexpr int NCOL = 3 * STRIDE + 3;                  // input columns one thread touches per row: 6 / 9
   constexpr int IN_FLOATS = kEncIcb * PH * PH, W_FLOATS = kEncIcb * 9 * kEncOcb;
@@ -113,7 +141,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_conv3x3_kernel(const E
   // loads are in flight at once) are issued before the FFMA loop of chunk c and land in shared memory after it.
   constexpr int N_IN = (IN_FLOATS + kEncThreads - 1) / kEncThreads;
   constexpr int N_W = (W_FLOATS / 4 + kEncThreads - 1) / kEncThreads;
-  EncSlot<UP> vin[N_IN];
+  EncSlot<MODE> vin[N_IN];
   float4 vw[N_W];
   int woff[N_W];                             // (channel within chunk << 24) | offset inside the chunk's [i][9][c_out] weight rows, or -1
 #pragma unroll
@@ -126,7 +154,8 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_conv3x3_kernel(const E
   for (int q = 0; q < N_W; ++q) {
     const int e = tid + q * kEncThreads;                    // float4 index: [i][k][o4]
     const int i = e / (9 * kEncOcb / 4), k = (e / (kEncOcb / 4)) % 9, o = (e % (kEncOcb / 4)) * 4;
-    woff[q] = (e < W_FLOATS / 4 && oc_base + o < p.c_out) ? ((i << 24) | ((i * 9 + k) * p.c_out + oc_base + o)) : -1;   // c_out % 4 == 0
+    const int ks = LINEAR ? 8 - k : k;                      // data gradient: the kernel is flipped in both axes
+    woff[q] = (e < W_FLOATS / 4 && oc_base + o < p.c_out) ? ((i << 24) | ((i * 9 + ks) * p.c_out + oc_base + o)) : -1;   // c_out % 4 == 0
   }
   auto load_chunk = [&](int ic0) {
 #pragma unroll
@@ -232,31 +261,22 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_conv3x3_kernel(const E
   for (int o = 0; o < 4; ++o) {
     const int oc = oc_base + 4 * og + o;
     if (oc >= p.c_out) continue;
-    const float b = __ldg(p.bias + oc);
+    const float b = LINEAR ? 0.f : __ldg(p.bias + oc);
     float* dst = p.out + ((long long)oc * p.h_out + y) * p.w_out + tx0 + px0;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (tx0 + px0 + j < p.w_out) dst[j] = fmaxf(acc[j][o] + b, 0.f);
+      if (tx0 + px0 + j < p.w_out) dst[j] = LINEAR ? (p.accumulate ? dst[j] + acc[j][o] : acc[j][o]) : fmaxf(acc[j][o] + b, 0.f);
   }
 }
 
-int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* weight_t, const float* bias,
-                           int c_out, int h_in, int w_in, int stride, float* out, cudaStream_t stream) {
-  EncConvParams p;
-  p.src_a = src_a; p.ca = ca; p.up_a = up_a;
-  p.src_b = src_b; p.cb = cb;
-  p.weight_t = weight_t; p.bias = bias;
-  p.c_out = c_out; p.h_in = h_in; p.w_in = w_in;
-  p.h_out = (h_in - 1) / stride + 1;
-  p.w_out = (w_in - 1) / stride + 1;
-  p.out = out;
-  if (c_out % 4 != 0 || (long long)h_in * w_in > 65536 || (long long)(ca + cb) * 9 * c_out >= (1 << 24)) return UORF_ERR_UNSUPPORTED;
-  const int base_ctas = ((p.h_out + kEncTile - 1) / kEncTile) * ((p.w_out + kEncTile - 1) / kEncTile) * ((c_out + kEncOcb - 1) / kEncOcb);
-  const int n_chunks = (ca + cb + kEncIcb - 1) / kEncIcb;
+static int launch_enc(EncConvParams& p, int c_in, int mode, int stride, cudaStream_t stream) {
+  if (p.c_out % 4 != 0 || (long long)p.h_in * p.w_in > 65536 || (long long)c_in * 9 * p.c_out >= (1 << 24)) return UORF_ERR_UNSUPPORTED;
+  const int base_ctas = ((p.h_out + kEncTile - 1) / kEncTile) * ((p.w_out + kEncTile - 1) / kEncTile) * ((p.c_out + kEncOcb - 1) / kEncOcb);
+  const int n_chunks = (c_in + kEncIcb - 1) / kEncIcb;
   p.split = 1;
   while (p.split < 8 && base_ctas * p.split * 2 <= 148 && p.split * 2 <= n_chunks) p.split *= 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(((p.h_out + kEncTile - 1) / kEncTile) * ((p.w_out + kEncTile - 1) / kEncTile), (c_out + kEncOcb - 1) / kEncOcb, p.split);
+  cfg.gridDim = dim3(((p.h_out + kEncTile - 1) / kEncTile) * ((p.w_out + kEncTile - 1) / kEncTile), (p.c_out + kEncOcb - 1) / kEncOcb, p.split);
   cfg.blockDim = dim3(kEncThreads);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
@@ -266,12 +286,280 @@ int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* sr
   cfg.attrs = attr;
   cfg.numAttrs = p.split > 1 ? 1 : 0;
   cudaError_t err;
-  if (stride == 1 && up_a) err = cudaLaunchKernelEx(&cfg, encoder_conv3x3_kernel<1, true>, p);
-  else if (stride == 1) err = cudaLaunchKernelEx(&cfg, encoder_conv3x3_kernel<1, false>, p);
-  else if (stride == 2 && !up_a) err = cudaLaunchKernelEx(&cfg, encoder_conv3x3_kernel<2, false>, p);
+  if (mode == kSlotGrad) err = cudaLaunchKernelEx(&cfg, encoder_conv3x3_kernel<1, kSlotGrad>, p);
+  else if (mode == kSlotGradZi) err = cudaLaunchKernelEx(&cfg, encoder_conv3x3_kernel<1, kSlotGradZi>, p);
+  else if (stride == 1 && mode == kSlotUp) err = cudaLaunchKernelEx(&cfg, encoder_conv3x3_kernel<1, kSlotUp>, p);
+  else if (stride == 1) err = cudaLaunchKernelEx(&cfg, encoder_conv3x3_kernel<1, kSlotPlain>, p);
+  else if (stride == 2 && mode == kSlotPlain) err = cudaLaunchKernelEx(&cfg, encoder_conv3x3_kernel<2, kSlotPlain>, p);
   else return UORF_ERR_UNSUPPORTED;
   if (err != cudaSuccess) return UORF_ERR_DEVICE;
   return finish_launch(1);
+}
+
+int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* weight_t, const float* bias,
+                           int c_out, int h_in, int w_in, int stride, float* out, cudaStream_t stream) {
+  EncConvParams p = {};
+  p.src_a = src_a; p.ca = ca; p.up_a = up_a;
+  p.src_b = src_b; p.cb = cb;
+  p.weight_t = weight_t; p.bias = bias;
+  p.c_out = c_out; p.h_in = h_in; p.w_in = w_in;
+  p.h_out = (h_in - 1) / stride + 1;
+  p.w_out = (w_in - 1) / stride + 1;
+  p.out = out;
+  return launch_enc(p, ca + cb, up_a ? kSlotUp : kSlotPlain, stride, stream);
+}
+
+// Data gradient of one layer: grad_in [c_in][h_in][w_in] = transposed convolution of (grad_out where kept_out > 0), both
+// [c_out][h_out][w_out], with the layer's kernel; weight_g = the Conv2d weight as [c_out][3][3][c_in] (the kernel flips the taps).
+int launch_encoder_dgrad3x3(const float* grad_out, const float* kept_out, int c_out, const float* weight_g, int c_in, int h_in, int w_in,
+                            int stride, int accumulate, float* grad_in, cudaStream_t stream) {
+  EncConvParams p = {};
+  p.accumulate = accumulate;
+  p.src_a = grad_out; p.gate_a = kept_out; p.ca = c_out;
+  p.h_a = (h_in - 1) / stride + 1; p.w_a = (w_in - 1) / stride + 1;
+  p.weight_t = weight_g;
+  p.c_out = c_in; p.h_in = h_in; p.w_in = w_in; p.h_out = h_in; p.w_out = w_in;
+  p.out = grad_in;
+  return launch_enc(p, c_out, stride == 1 ? kSlotGrad : kSlotGradZi, 1, stream);
+}
+
+// Backward of nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) (model.py:27-32) as a gather: a low-resolution
+// element collects its (up to) 4 x 4 high-resolution gradients with the separable weights 1/4, 3/4, 3/4, 1/4 (the clamped border
+// rows / columns fold their outer weight into the 3/4).  One thread per element, fixed order: bit-reproducible, unlike the
+// atomic scatter of the library op.
+__global__ void encoder_upsample2x_bwd_kernel(const float* __restrict__ g_hi, int c, int h, int w, float* __restrict__ g_lo) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)c * h * w) return;
+  const int x = (int)(idx % w), y = (int)((idx / w) % h);
+  const float* src = g_hi + (idx / ((long long)h * w)) * (4LL * h * w);
+  const float wy[4] = {y > 0 ? 0.25f : 0.f, y > 0 ? 0.75f : 1.f, y < h - 1 ? 0.75f : 1.f, y < h - 1 ? 0.25f : 0.f};
+  const float wx[4] = {x > 0 ? 0.25f : 0.f, x > 0 ? 0.75f : 1.f, x < w - 1 ? 0.75f : 1.f, x < w - 1 ? 0.25f : 0.f};
+  float s = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int yy = 2 * y - 1 + a;
+    if (yy < 0 || yy >= 2 * h) continue;
+    float r = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int xx = 2 * x - 1 + b;
+      if (xx >= 0 && xx < 2 * w) r = fmaf(wx[b], __ldg(src + (long long)yy * (2 * w) + xx), r);
+    }
+    s = fmaf(wy[a], r, s);
+  }
+  g_lo[idx] = s;
+}
+
+int launch_encoder_upsample2x_bwd(const float* grad_hi, int c, int h_lo, int w_lo, float* grad_lo, cudaStream_t stream) {
+  const long long n = (long long)c * h_lo * w_lo;
+  if (n <= 0) return UORF_OK;
+  encoder_upsample2x_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad_hi, c, h_lo, w_lo, grad_lo);
+  return finish_launch(1);
+}
+
+// ---- weight / bias gradient ---------------------------------------------------------------------------------------
+// dW[o][c][ky][kx] = sum over output pixels of G[o][y][x] * X[c][y*s + ky - 1][x*s + kx - 1], G = grad_out where kept_out > 0, X the
+// layer's input read exactly as the forward reads it (two sources, source A optionally through the upsample; zero padding).
+// CTA = 16 input channels x 32 output channels (4608 weights) over its share of the 8x8 output tiles; the four warp groups take two
+// tile rows each; thread = one input channel x four output channels x nine taps (36 accumulators).  Partial sums of the pixel
+// shares go to a workspace and are added in share order by the reduce kernel (deterministic).
+constexpr int kEwPhp = 12;   // padded patch row (floats): rows start 16-byte aligned for stride 1
+template <int STRIDE, int MODE>
+__global__ void __launch_bounds__(kEncThreads, 1) encoder_wgrad3x3_kernel(const EncConvParams p, const float* __restrict__ grad_out,
+                                                                           const float* __restrict__ kept_out, float* __restrict__ partial) {
+  constexpr bool UP = MODE == kSlotUp;
+  constexpr int PH = (kEncTile - 1) * STRIDE + 3;       // 10 / 17
+  constexpr int PHP = STRIDE == 1 ? kEwPhp : 20;        // padded row length
+  constexpr int NCOL = 7 * STRIDE + 3;                  // input columns of one tile row: 10 / 17
+  constexpr int IN_ELEMS = kEncIcb * PH * PH;
+  constexpr int N_IN = (IN_ELEMS + kEncThreads - 1) / kEncThreads;
+  constexpr int N_G = kEncOcb * 64 / kEncThreads;        // 4
+  constexpr int RED_FLOATS = 36 * kEncGroupThreads;
+  constexpr int STAGE_FLOATS = kEncIcb * PH * PHP + 64 * kEncOcb;
+  constexpr int SMEM_FLOATS = STAGE_FLOATS > RED_FLOATS ? STAGE_FLOATS : RED_FLOATS;
+  __shared__ __align__(16) float smem[SMEM_FLOATS];
+  float* s_in = smem;                                   // [16][PH][PHP]
+  float* s_g = smem + kEncIcb * PH * PHP;               // [64 pixels][32 channels]
+  const int tid = threadIdx.x;
+  const int grp = tid / kEncGroupThreads, t = tid % kEncGroupThreads;
+  const int og = t & 7, ci = t >> 3;
+  const int ic0 = blockIdx.x * kEncIcb, oc_base = blockIdx.y * kEncOcb;
+  const int cin = p.ca + p.cb;
+  const int tiles_x = (p.w_out + kEncTile - 1) / kEncTile;
+  const int n_tiles = tiles_x * ((p.h_out + kEncTile - 1) / kEncTile);
+  float acc[4][9];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[o][k] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+
+  EncSlot<MODE> vin[N_IN];
+  float vg[N_G];
+  auto load_tile = [&](int tile) {
+    const int ty0 = (tile / tiles_x) * kEncTile, tx0 = (tile % tiles_x) * kEncTile;
+#pragma unroll
+    for (int q = 0; q < N_IN; ++q) {
+      const int e = tid + q * kEncThreads;
+      const int i = e / (PH * PH), r = (e / PH) % PH, c = e % PH;
+      vin[q].setup(p, i, ty0 * STRIDE - 1 + r, tx0 * STRIDE - 1 + c, e < IN_ELEMS);
+      vin[q].load(p, ic0, cin);
+    }
+#pragma unroll
+    for (int q = 0; q < N_G; ++q) {
+      const int e = tid + q * kEncThreads;              // [channel][pixel]: a tile row of 8 pixels is contiguous in global memory
+      const int o = e >> 6, y = ty0 + ((e >> 3) & 7), x = tx0 + (e & 7);
+      vg[q] = 0.f;
+      if (oc_base + o < p.c_out && y < p.h_out && x < p.w_out) {
+        const long long off = ((long long)(oc_base + o) * p.h_out + y) * p.w_out + x;
+        vg[q] = __ldg(kept_out + off) > 0.f ? __ldg(grad_out + off) : 0.f;
+      }
+    }
+  };
+  const int share = blockIdx.z, n_share = gridDim.z;
+  if (share < n_tiles) load_tile(share);
+  for (int tile = share; tile < n_tiles; tile += n_share) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < N_IN; ++q) {
+      const int e = tid + q * kEncThreads;
+      if (e < IN_ELEMS) {
+        const int i = e / (PH * PH), r = (e / PH) % PH, c = e % PH;
+        float v;
+        if constexpr (UP) v = vin[q].value(p, ic0);
+        else v = vin[q].value();
+        s_in[(i * PH + r) * PHP + c] = v;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < N_G; ++q) {
+      const int e = tid + q * kEncThreads;
+      s_g[(e & 63) * kEncOcb + (e >> 6)] = vg[q];
+    }
+    __syncthreads();
+    if (tile + n_share < n_tiles) load_tile(tile + n_share);
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = grp * 2 + rr;
+      float4 g[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) g[x] = *reinterpret_cast<const float4*>(&s_g[(row * 8 + x) * kEncOcb + 4 * og]);
+      if (ic0 == 0 && ci == 0) {
+#pragma unroll
+        for (int x = 0; x < 8; ++x) { bsum[0] += g[x].x; bsum[1] += g[x].y; bsum[2] += g[x].z; bsum[3] += g[x].w; }
+      }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        float a[NCOL];
+        const float* src = &s_in[(ci * PH + row * STRIDE + ky) * PHP];
+#pragma unroll
+        for (int c = 0; c < NCOL; ++c) a[c] = src[c];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+          for (int x = 0; x < 8; ++x) {
+            const float v = a[x * STRIDE + kx];
+            acc[0][ky * 3 + kx] = fmaf(g[x].x, v, acc[0][ky * 3 + kx]);
+            acc[1][ky * 3 + kx] = fmaf(g[x].y, v, acc[1][ky * 3 + kx]);
+            acc[2][ky * 3 + kx] = fmaf(g[x].z, v, acc[2][ky * 3 + kx]);
+            acc[3][ky * 3 + kx] = fmaf(g[x].w, v, acc[3][ky * 3 + kx]);
+          }
+        }
+      }
+    }
+  }
+  // fixed-order sum of the four row groups (one group at a time through shared memory), then the CTA's partial:
+  // [share][c_out][cin][9] and the bias sums behind them
+  for (int g = 1; g < kEncGroups; ++g) {
+    __syncthreads();
+    if (grp == g) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) smem[(o * 9 + k) * kEncGroupThreads + t] = acc[o][k];
+    }
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[o][k] += smem[(o * 9 + k) * kEncGroupThreads + t];
+    }
+  }
+  __syncthreads();
+  if (ic0 == 0 && ci == 0 && grp > 0) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) smem[((grp - 1) * 4 + o) * 8 + og] = bsum[o];
+  }
+  __syncthreads();
+  if (grp > 0) return;
+  const long long w_elems = (long long)p.c_out * cin * 9;
+  float* dst = partial + (long long)share * (w_elems + p.c_out);
+  if (ic0 + ci < cin) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int oc = oc_base + 4 * og + o;
+      if (oc >= p.c_out) continue;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) dst[((long long)oc * cin + ic0 + ci) * 9 + k] = acc[o][k];
+    }
+  }
+  if (ic0 == 0 && ci == 0) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int oc = oc_base + 4 * og + o;
+      if (oc >= p.c_out) continue;
+      float b = bsum[o];
+#pragma unroll
+      for (int g = 0; g < kEncGroups - 1; ++g) b += smem[(g * 4 + o) * 8 + og];
+      dst[w_elems + oc] = b;
+    }
+  }
+}
+
+// grad_weight [c_out][cin][3][3] followed by grad_bias [c_out] <- sum of the shares in order
+__global__ void encoder_wgrad_reduce_kernel(const float* __restrict__ partial, int n_share, long long n, long long n_w, float* __restrict__ gw,
+                                            float* __restrict__ gb) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int z = 0; z < n_share; ++z) s += partial[(long long)z * n + i];
+  if (i < n_w) gw[i] = s;
+  else gb[i - n_w] = s;
+}
+
+static int wgrad_shares(int c_in, int c_out, int h_out, int w_out) {
+  const int n_tiles = ((h_out + kEncTile - 1) / kEncTile) * ((w_out + kEncTile - 1) / kEncTile);
+  const int base = ((c_in + kEncIcb - 1) / kEncIcb) * ((c_out + kEncOcb - 1) / kEncOcb);
+  int s = 1;
+  while (s * 2 <= n_tiles && base * s < 2 * 148) s *= 2;
+  return s;
+}
+
+size_t encoder_wgrad_workspace_floats(int c_in, int c_out, int h_in, int w_in, int stride) {
+  const int h_out = (h_in - 1) / stride + 1, w_out = (w_in - 1) / stride + 1;
+  return (size_t)wgrad_shares(c_in, c_out, h_out, w_out) * ((size_t)c_out * c_in * 9 + c_out);
+}
+
+int launch_encoder_wgrad3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* grad_out, const float* kept_out,
+                            int c_out, int h_in, int w_in, int stride, float* workspace, float* grad_weight, float* grad_bias,
+                            cudaStream_t stream) {
+  EncConvParams p = {};
+  p.src_a = src_a; p.ca = ca; p.up_a = up_a;
+  p.src_b = src_b; p.cb = cb;
+  p.c_out = c_out; p.h_in = h_in; p.w_in = w_in;
+  p.h_out = (h_in - 1) / stride + 1;
+  p.w_out = (w_in - 1) / stride + 1;
+  const int cin = ca + cb;
+  if ((long long)h_in * w_in > 65536 || (stride == 2 && up_a)) return UORF_ERR_UNSUPPORTED;
+  const int shares = wgrad_shares(cin, c_out, p.h_out, p.w_out);
+  dim3 grid((cin + kEncIcb - 1) / kEncIcb, (c_out + kEncOcb - 1) / kEncOcb, shares);
+  if (stride == 1 && up_a) encoder_wgrad3x3_kernel<1, kSlotUp><<<grid, kEncThreads, 0, stream>>>(p, grad_out, kept_out, workspace);
+  else if (stride == 1) encoder_wgrad3x3_kernel<1, kSlotPlain><<<grid, kEncThreads, 0, stream>>>(p, grad_out, kept_out, workspace);
+  else encoder_wgrad3x3_kernel<2, kSlotPlain><<<grid, kEncThreads, 0, stream>>>(p, grad_out, kept_out, workspace);
+  const long long n_w = (long long)c_out * cin * 9, n = n_w + c_out;
+  encoder_wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(workspace, shares, n, n_w, grad_weight, grad_bias);
+  return finish_launch(2);
 }
 
 }  // namespace uorf

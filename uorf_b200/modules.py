@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -97,7 +98,9 @@ class Encoder(nn.Module):
         self._planes = {}
         self._wt = {}              # transposed conv weights of the inference path, keyed by weight version
         self.use_kernels = True    # False: always the torch / cuDNN layers
-        self.use_kernels_in_training = True   # forward by the kernels under autograd too; backward = cuDNN per layer (_EncoderFn)
+        self.use_kernels_in_training = True   # forward by the kernels under autograd too (_EncoderFn)
+        # ... and the backward by the fp32 gradient kernels; False (UORF_ENCODER_BACKWARD=cudnn, A-B runs): cuDNN convolution_backward per layer
+        self.backward_kernels = os.environ.get("UORF_ENCODER_BACKWARD", "kernels") != "cudnn"
         self.grad_sink = None                 # {parameter name: tensor}: the training path's backward writes gradients there (see _GradSink)
         self.require_kernels = False          # True: raise instead of running the torch layer stack on a non-kernel shape
         self.last_path = None                 # 'kernels' | 'torch': which path the last forward took
@@ -218,13 +221,91 @@ class _EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out):
-        gx, grads = _encoder_backward(ctx.enc, dict(zip(ctx.names, ctx.saved_tensors)), g_out, ctx.x_needs_grad)
-        names = [n for n, _ in ctx.enc.named_parameters()]
-        sink = ctx.enc.grad_sink
+        enc = ctx.enc
+        a = dict(zip(ctx.names, ctx.saved_tensors))
+        names = [n for n, _ in enc.named_parameters()]
+        sink = enc.grad_sink
+        if enc.backward_kernels and g_out.is_cuda and not ctx.x_needs_grad:
+            grads = _encoder_backward_kernels(enc, a, g_out, sink)     # writes straight into the sink's buffers
+            return (None, None) + ((None,) * len(names) if sink is not None else tuple(grads[n] for n in names))
+        gx, grads = _encoder_backward(enc, a, g_out, ctx.x_needs_grad)
         if sink is not None:       # gradients land in caller-owned buffers (one flat all-reduce bucket); autograd sees None
             torch._foreach_copy_([sink[n] for n in names], [grads[n] for n in names])
             return (None, gx) + (None,) * len(names)
         return (None, gx) + tuple(grads[n] for n in names)
+
+
+def _encoder_backward_kernels(enc, a, g_out, sink=None):
+    """Backward of Encoder.forward (batch 1, no image gradient) on the fp32 kernels of csrc/encoder.cu: per layer one weight / bias
+    gradient launch (+ its fixed-order reduce) that reads the layer input the way the forward did (no cat / upsample tensors) and one
+    data-gradient launch; the ReLU gates are taken from the kept outputs inside the loads.  The two bilinear-upsample backwards are fixed-order gathers, the
+    skip connections' second gradients are added by the data-gradient launch itself: the whole backward is bit-reproducible.  Replaces autograd / cuDNN for models/model.py:36-61 under
+    models/uorf_nogan_model.py:181-183.  -> {parameter name: gradient} (the sink's own tensors when `sink` is given)."""
+    dev = g_out.device
+    grads = {}
+    stream = _stream(g_out)
+
+    def buf(name, like):
+        if sink is not None:
+            t = sink[name]
+            if not (t.is_contiguous() and t.dtype == torch.float32):
+                raise _lib.UorfError("Encoder.grad_sink buffers must be contiguous fp32")
+            return t
+        return torch.empty_like(like, dtype=torch.float32, memory_format=torch.contiguous_format)
+
+    def wgrad(name, src_a, up_a, src_b, g, out, h_in, w_in):
+        conv = getattr(enc, name)[0]
+        ca, cb = src_a.shape[0], (0 if src_b is None else src_b.shape[0])
+        stride = conv.stride[0]
+        gw, gb = buf(name + ".0.weight", conv.weight), buf(name + ".0.bias", conv.bias)
+        ws = torch.empty(lib().uorf_encoder_wgrad_workspace_floats(ca + cb, conv.out_channels, h_in, w_in, stride), device=dev, dtype=torch.float32)
+        check(lib().uorf_encoder_conv3x3_wgrad(src_a.data_ptr(), ca, int(up_a), _ptr(src_b), cb, g.data_ptr(), out.data_ptr(), conv.out_channels,
+                                               h_in, w_in, stride, ws.data_ptr(), gw.data_ptr(), gb.data_ptr(), stream), "uorf_encoder_conv3x3_wgrad")
+        grads[name + ".0.weight"], grads[name + ".0.bias"] = gw, gb
+
+    def dgrad(name, g, out, h_in, w_in, into=None):
+        """-> gradient of the layer input [c_in][h_in][w_in]; `into`: added to that tensor instead (skip connection)"""
+        conv = getattr(enc, name)[0]
+        wg = conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()       # [c_out][3][3][c_in]
+        gi = torch.empty(conv.in_channels, h_in, w_in, device=dev, dtype=torch.float32) if into is None else into
+        check(lib().uorf_encoder_conv3x3_dgrad(g.data_ptr(), out.data_ptr(), conv.out_channels, wg.data_ptr(), conv.in_channels, h_in, w_in,
+                                               conv.stride[0], int(into is not None), gi.data_ptr(), stream), "uorf_encoder_conv3x3_dgrad")
+        return gi
+
+    def up_bwd(g, low):     # backward of nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False), model.py:27-32
+        out = torch.empty_like(low)
+        check(lib().uorf_encoder_upsample2x_bwd(g.data_ptr(), low.shape[0], low.shape[1], low.shape[2], out.data_ptr(), stream),
+              "uorf_encoder_upsample2x_bwd")
+        return out
+
+    z = a["out"].shape[0]
+    h1, w1 = a["d1"].shape[1], a["d1"].shape[2]
+    h2, w2 = a["d2"].shape[1], a["d2"].shape[2]
+    h3, w3 = a["d3"].shape[1], a["d3"].shape[2]
+    with _on(g_out):
+        g = _f32c(g_out[0])
+        wgrad("enc_up_1", a["u2"], True, a["d1"], g, a["out"], h1, w1)
+        gi = dgrad("enc_up_1", g, a["out"], h1, w1)
+        g_d1 = gi[z:]
+        g = up_bwd(gi[:z], a["u2"])
+        wgrad("enc_up_2", a["u3"], True, a["d2"], g, a["u2"], h2, w2)
+        gi = dgrad("enc_up_2", g, a["u2"], h2, w2)
+        g_d2 = gi[z:]
+        g = up_bwd(gi[:z], a["u3"])
+        wgrad("enc_up_3", a["d3"], False, None, g, a["u3"], h3, w3)
+        g_d3 = dgrad("enc_up_3", g, a["u3"], h3, w3)
+        wgrad("enc_down_3", a["d2"], False, None, g_d3, a["d3"], h2, w2)
+        dgrad("enc_down_3", g_d3, a["d3"], h2, w2, into=g_d2)
+        wgrad("enc_down_2", a["d1"], False, None, g_d2, a["d2"], h1, w1)
+        dgrad("enc_down_2", g_d2, a["d2"], h1, w1, into=g_d1)
+        H, W = a["img"].shape[1], a["img"].shape[2]
+        if enc.bottom:
+            wgrad("enc_down_1", a["d0"], False, None, g_d1, a["d1"], H, W)
+            g_d0 = dgrad("enc_down_1", g_d1, a["d1"], H, W)
+            wgrad("enc_down_0", a["img"], False, a["planes"], g_d0, a["d0"], H, W)
+        else:
+            wgrad("enc_down_1", a["img"], False, a["planes"], g_d1, a["d1"], H, W)
+    return grads
 
 
 def _encoder_backward(enc, a, g_out, x_needs_grad):
