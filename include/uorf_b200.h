@@ -284,6 +284,27 @@ int uorf_encoder_conv3x3_wgrad(const float* src_a, int32_t ca, int32_t upsample_
                                float* grad_weight, float* grad_bias, void* stream);
 
 /* -----------------------------------------------------------------------------------------------
+ * Adam update of many small fp32 tensors in one launch - the `optimizer.step()` of the training drivers
+ * (reference models/uorf_nogan_model.py:59-61 torch.optim.Adam over encoder + slot attention + decoder, :229-245 the step).
+ * `chunks` is a DEVICE array: every entry is at most UORF_ADAM_CHUNK consecutive elements of one parameter with the matching
+ * slices of its gradient and both moment buffers, and the parameter's step counter (a device float, already incremented for
+ * this update - torch's capturable / fused state layout).  lr_dev != NULL: the learning rate is read from that device float
+ * (graph replays with a scheduler), else lr_host.  Update rule of torch.optim.Adam (amsgrad off, maximize off).
+ * --------------------------------------------------------------------------------------------- */
+#define UORF_ADAM_CHUNK 1024
+typedef struct uorf_adam_chunk {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  const float* step;
+  int32_t n;
+  int32_t reserved;
+} uorf_adam_chunk;
+int uorf_adam_step(const uorf_adam_chunk* chunks, int32_t n_chunks, const float* lr_dev, float lr_host, float beta1, float beta2, float eps,
+                   float weight_decay, void* stream);
+
+/* -----------------------------------------------------------------------------------------------
  * Kernel 6: 3x3 convolution (stride 1, pad 1) of the perceptual-loss network, fp32-parity on the tensor cores.
  * Replaces the cuDNN fp32 convolutions behind `get_perceptual_net` (reference models/model.py:316-324: VGG16 features[:23]) as
  * the training step uses them (models/uorf_nogan_model.py:181-183): forward on both images, data gradient of the rendered branch.

@@ -588,3 +588,47 @@ def test_perceptual_vgg_matches_torch_layers():
     # (not bit-equal: the split-K factor of a layer depends on its pixel-tile count, so the summation order differs with the batch)
     assert abs(loss.item() - res["x3"][1]) < 1e-5 * abs(res["x3"][1]) + 1e-12
     assert maxerr(a.grad, res["x3"][2]) < 1e-4 * gmax
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("capturable,weight_decay", [(True, 0.0), (False, 0.0), (True, 1e-2)])
+def test_adam_kernel_matches_torch_adam(capturable, weight_decay):
+    """uorf_b200.optim.Adam (one launch of uorf_adam_step over 1,024-element chunks) against torch.optim.Adam(fused=True) on the same
+    tensors and gradients: same state layout, same update rule; 25 steps with a learning-rate schedule"""
+    import torch
+    from uorf_b200.optim import Adam
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    shapes = [(64, 7, 3, 3), (64,), (64, 128, 3, 3), (3, 64), (1, 1, 64), (1025,), (5000,)]
+    ours = [torch.nn.Parameter(torch.randn(s, device=dev)) for s in shapes]
+    ref = [torch.nn.Parameter(p_.detach().clone()) for p_ in ours]
+    mk_lr = lambda: torch.tensor(3e-4, device=dev) if capturable else 3e-4
+    o_ours = Adam(ours, lr=mk_lr(), capturable=capturable, fused=True, weight_decay=weight_decay)
+    o_ref = torch.optim.Adam(ref, lr=mk_lr(), capturable=capturable, fused=True, weight_decay=weight_decay)
+    for step in range(25):
+        for a, b in zip(ours, ref):
+            g = torch.randn_like(a) * (10.0 ** ((step % 5) - 3))
+            if a.grad is None:
+                a.grad, b.grad = g.clone(), g.clone()
+            else:
+                a.grad.copy_(g); b.grad.copy_(g)          # addresses stay: the chunk table is reused
+        for o in (o_ours, o_ref):
+            for grp in o.param_groups:
+                if torch.is_tensor(grp["lr"]):
+                    grp["lr"].fill_(3e-4 * (step + 1) / 25)
+                else:
+                    grp["lr"] = 3e-4 * (step + 1) / 25
+        o_ours.step()
+        o_ref.step()
+    assert o_ours.kernel_steps == 25
+    for a, b in zip(ours, ref):
+        assert torch.isfinite(a).all()
+        scale = b.detach().abs().max().item()
+        assert (a.detach() - b.detach()).abs().max().item() <= 2e-6 * scale, (a.shape, (a.detach() - b.detach()).abs().max().item())
+        sa, sb = o_ours.state[a], o_ref.state[b]
+        assert float(sa["step"]) == float(sb["step"]) == 25.0
+        for k in ("exp_avg", "exp_avg_sq"):
+            assert (sa[k] - sb[k]).abs().max().item() <= 2e-6 * max(sb[k].abs().max().item(), 1e-30), k
+    # the state dict is torch's: it loads into a plain torch.optim.Adam
+    o_plain = torch.optim.Adam(ref, lr=mk_lr(), capturable=capturable, fused=True, weight_decay=weight_decay)
+    o_plain.load_state_dict(o_ours.state_dict())

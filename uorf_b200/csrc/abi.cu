@@ -22,6 +22,8 @@ size_t encoder_wgrad_workspace_floats(int c_in, int c_out, int h_in, int w_in, i
 int launch_encoder_wgrad3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* grad_out, const float* kept_out,
                             int c_out, int h_in, int w_in, int stride, float* workspace, float* grad_weight, float* grad_bias,
                             cudaStream_t stream);
+int launch_adam_step(const uorf_adam_chunk* chunks, int n_chunks, const float* lr_dev, float lr_host, float beta1, float beta2, float eps,
+                     float weight_decay, cudaStream_t stream);
 int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* weight_t, const float* bias,
                            int c_out, int h_in, int w_in, int stride, float* out, cudaStream_t stream);
 int launch_decoder_prep(const uorf_decoder_weights* w, const float* z_slots, int K, int Z, int passes, int f16, void* image,
@@ -158,6 +160,17 @@ int uorf_init(int device) {
   std::call_once(c->once, init_device, c, device);
   if (c->status != UORF_OK) return fail(c->status, "%s", c->why);
   return UORF_OK;
+}
+
+int uorf_adam_step(const uorf_adam_chunk* chunks, int32_t n_chunks, const float* lr_dev, float lr_host, float beta1, float beta2, float eps,
+                   float weight_decay, void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_adam_step");
+  if (!c) return UORF_ERR_DEVICE;
+  if (n_chunks < 0 || (n_chunks > 0 && !chunks)) return fail(UORF_ERR_ARG, "uorf_adam_step: bad chunk table%s");
+  if (!(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f)) return fail(UORF_ERR_ARG, "uorf_adam_step: bad hyper-parameters%s");
+  return check_launch(uorf::launch_adam_step(chunks, n_chunks, lr_dev, lr_host, beta1, beta2, eps, weight_decay, static_cast<cudaStream_t>(stream)),
+                      "uorf_adam_step");
 }
 
 int uorf_encoder_conv3x3_dgrad(const float* grad_out, const float* kept_out, int32_t c_out, const float* weight_g, int32_t c_in,

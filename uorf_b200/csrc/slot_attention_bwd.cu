@@ -474,17 +474,32 @@ __global__ void sa_bwd_reduce_kernel(const SabParams p) {
     p.g.slots_mu[e] = dmu; p.g.slots_logsigma[e] = dls;
     p.g.slots_mu_bg[e] = p.dS[e];
     p.g.slots_logsigma_bg[e] = p.dS[e] * expf(p.w.slots_logsigma_bg[e]) * p.noise_bg[e];
-    float gw = 0.f, gb = 0.f;
-#pragma unroll 8
-    for (int b = 0; b < p.nblk; ++b) { const float* part = p.tok_part + (long long)b * (2 * C * C + 2 * C); gw += part[2 * C * C + e]; gb += part[2 * C * C + C + e]; }
-    p.g.norm_feat_w[e] = gw; p.g.norm_feat_b[e] = gb;
   }
-  for (int e = gid; e < C * C; e += gn) {
-    float ak = 0.f, av = 0.f;
-#pragma unroll 8
-    for (int b = 0; b < p.nblk; ++b) {      // fixed order; the unrolled loads are in flight together
- const float* part = p.tok_part + (long long)b * (2 * C * C + 2 * C); ak += part[e]; av += part[C * C + e]; }
-    p.g.to_k_w[e] = ak; p.g.to_v_w[e] = av;
+  // token-pass partials [nblk][2 C C + 2 C] -> to_k_w | to_v_w | norm_feat_w | norm_feat_b (the same order).  A block takes 32
+  // consecutive elements; warp j adds blocks j, j + 8, ... in order (coalesced rows), warp 0 then adds the eight sums in order:
+  // bit-reproducible.  (One thread per element walked all 128 partial blocks alone: 4096 busy threads, 128 dependent round trips.)
+  __shared__ float s_part[8][32];
+  const int row = 2 * C * C + 2 * C;
+  const int lane = threadIdx.x & 31, wsub = threadIdx.x >> 5;       // launched with 256 threads
+  for (int e0 = blockIdx.x * 32; e0 < row; e0 += gridDim.x * 32) {
+    const int e = e0 + lane;
+    float a = 0.f;
+    if (e < row) {
+#pragma unroll 4
+      for (int b = wsub; b < p.nblk; b += 8) a += p.tok_part[(long long)b * row + e];
+    }
+    s_part[wsub][lane] = a;
+    __syncthreads();
+    if (wsub == 0 && e < row) {
+      float t = s_part[0][lane];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) t += s_part[j][lane];
+      if (e < C * C) p.g.to_k_w[e] = t;
+      else if (e < 2 * C * C) p.g.to_v_w[e - C * C] = t;
+      else if (e < 2 * C * C + C) p.g.norm_feat_w[e - 2 * C * C] = t;
+      else p.g.norm_feat_b[e - 2 * C * C - C] = t;
+    }
+    __syncthreads();
   }
 }
 

@@ -883,11 +883,15 @@ class _DecoderFn(torch.autograd.Function):
         dummy = lambda t, *shape: t if t is not None else raws.new_empty(0)
         outs = (raws, dummy(masked), unmasked, dummy(masks))
         ctx.mark_non_differentiable(outs[1], outs[2], outs[3])
+        # autograd would hand the backward a zero tensor per non-differentiable output otherwise: two K x P x 4 fills per step
+        ctx.set_materialize_grads(False)
         return outs
 
     @staticmethod
     def backward(ctx, g_raws, *unused):
         coor_bg, coor_fg, fg_transform, z_slots, unmasked = ctx.saved_tensors
+        if g_raws is None:
+            g_raws = torch.zeros(coor_bg.shape[0], 4, device=coor_bg.device, dtype=torch.float32)
         gz, grads = ctx.module._launch_backward(coor_bg, coor_fg, z_slots, fg_transform, ctx.dens_noise, ctx.noise, unmasked,
                                                 g_raws)
         if ctx.module.grad_sink is not None:

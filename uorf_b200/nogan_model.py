@@ -23,6 +23,7 @@ import torch.nn.functional as F
 from torch import nn, optim
 from torch.optim.lr_scheduler import LambdaLR
 
+from . import optim as _optim
 from .eval_model import init_weights_like_reference
 from .modules import Decoder, Encoder, PerceptualVGG, Projection, SlotAttention, raw2outputs
 
@@ -123,9 +124,12 @@ class uorfNoGanModel:
             # per step: 9.24 -> 8.94 ms).  opt.fused_adam=False / UORF_FUSED_ADAM=0 selects torch's default (foreach) - passed as
             # fused=None, never as an explicit False, which would select the slow single-tensor loop.
             fused = bool(getattr(opt, "fused_adam", os.environ.get("UORF_FUSED_ADAM", "1") == "1"))
-            self.optimizer = optim.Adam(chain(self.netEncoder.parameters(), self.netSlotAttention.parameters(),
-                                              self.netDecoder.parameters()), lr=lr, capturable=self._capturable,
-                                        fused=True if fused else None)
+            # ... and over it uorf_b200.optim.Adam: the same optimizer (state, state_dict) whose update is ONE launch of
+            # uorf_adam_step with 1,024-element blocks (torch's fused kernel: 38 blocks of 65,536 elements, ~70 us); UORF_ADAM_KERNEL=0: torch's
+            adam_cls = _optim.Adam if fused and os.environ.get("UORF_ADAM_KERNEL", "1") == "1" else optim.Adam
+            self.optimizer = adam_cls(chain(self.netEncoder.parameters(), self.netSlotAttention.parameters(),
+                                            self.netDecoder.parameters()), lr=lr, capturable=self._capturable,
+                                      fused=True if fused else None)
             self.optimizers = [self.optimizer]
             self.schedulers = [exp_decay_schedule_with_warmup(self.optimizer, opt.warmup_steps, opt.attn_decay_steps)]
         self.L2_loss = nn.MSELoss()
