@@ -283,6 +283,15 @@ int uorf_encoder_conv3x3_wgrad(const float* src_a, int32_t ca, int32_t upsample_
                                const float* kept_out, int32_t c_out, int32_t h_in, int32_t w_in, int32_t stride, float* workspace,
                                float* grad_weight, float* grad_bias, void* stream);
 
+/* 3-channel stem of the same network (VGG16 conv1_1 + ReLU, models/model.py:316-324), fp32 FFMA:
+ *   uorf_conv3x3_stem:        x NCHW [n][3][h][w], weight [c_out][3][3][3] (the Conv2d tensor), bias [c_out]
+ *                             -> y NHWC [n][h][w][c_out] = relu(conv + bias): the layout uorf_conv_split / uorf_conv3x3_x3 read;
+ *   uorf_conv3x3_stem_dgrad:  grad_y NHWC taken where y > 0 -> grad_x NCHW [n][3][h][w] (fixed summation order). */
+int uorf_conv3x3_stem(const float* x, const float* weight, const float* bias, int32_t n, int32_t h, int32_t w, int32_t c_out, float* y,
+                      void* stream);
+int uorf_conv3x3_stem_dgrad(const float* grad_y, const float* y, const float* weight, int32_t n, int32_t h, int32_t w, int32_t c_out,
+                            float* grad_x, void* stream);
+
 /* -----------------------------------------------------------------------------------------------
  * Adam update of many small fp32 tensors in one launch - the `optimizer.step()` of the training drivers
  * (reference models/uorf_nogan_model.py:59-61 torch.optim.Adam over encoder + slot attention + decoder, :229-245 the step).

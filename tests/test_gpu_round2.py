@@ -588,6 +588,21 @@ def test_perceptual_vgg_matches_torch_layers():
     # (not bit-equal: the split-K factor of a layer depends on its pixel-tile count, so the summation order differs with the batch)
     assert abs(loss.item() - res["x3"][1]) < 1e-5 * abs(res["x3"][1]) + 1e-12
     assert maxerr(a.grad, res["x3"][2]) < 1e-4 * gmax
+    # the constant images handed over separately (the training driver's call): the same launches, bit-equal
+    a2 = img.clone().requires_grad_(True)
+    f2 = fast(a2, x_const=tgt)
+    loss2 = 0.006 * torch.nn.functional.mse_loss(f2[:4], f2[4:].detach())
+    loss2.backward()
+    assert loss2.item() == loss.item() and torch.equal(a2.grad, a.grad)
+    # layer-by-layer autograd nodes (torch stem, per-layer zero rows) instead of the single node: same arithmetic in the x3 layers
+    assert fast.use_stack and fast._stack_plan() is not None
+    fast.use_stack = False
+    a3 = img.clone().requires_grad_(True)
+    f3 = fast(a3, x_const=tgt)
+    loss3 = 0.006 * torch.nn.functional.mse_loss(f3[:4], f3[4:].detach())
+    loss3.backward()
+    assert abs(loss3.item() - loss.item()) < 1e-5 * abs(loss.item()) + 1e-12
+    assert maxerr(a3.grad, a.grad) < 1e-4 * gmax
 
 
 @pytest.mark.gpu

@@ -22,6 +22,8 @@ size_t encoder_wgrad_workspace_floats(int c_in, int c_out, int h_in, int w_in, i
 int launch_encoder_wgrad3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* grad_out, const float* kept_out,
                             int c_out, int h_in, int w_in, int stride, float* workspace, float* grad_weight, float* grad_bias,
                             cudaStream_t stream);
+int launch_vgg_stem_fwd(const float* x, const float* weight, const float* bias, int n, int h, int w, int c_out, float* y, cudaStream_t stream);
+int launch_vgg_stem_dgrad(const float* g, const float* y, const float* weight, int n, int h, int w, int c_out, float* gx, cudaStream_t stream);
 int launch_adam_step(const uorf_adam_chunk* chunks, int n_chunks, const float* lr_dev, float lr_host, float beta1, float beta2, float eps,
                      float weight_decay, cudaStream_t stream);
 int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* weight_t, const float* bias,
@@ -160,6 +162,27 @@ int uorf_init(int device) {
   std::call_once(c->once, init_device, c, device);
   if (c->status != UORF_OK) return fail(c->status, "%s", c->why);
   return UORF_OK;
+}
+
+int uorf_conv3x3_stem(const float* x, const float* weight, const float* bias, int32_t n, int32_t h, int32_t w, int32_t c_out, float* y,
+                      void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_conv3x3_stem");
+  if (!c) return UORF_ERR_DEVICE;
+  if (!x || !weight || !bias || !y) return fail(UORF_ERR_ARG, "uorf_conv3x3_stem: null pointer%s");
+  if (n < 0 || h < 1 || w < 1 || c_out < 4 || c_out > 64 || (c_out & 3)) return fail(UORF_ERR_ARG, "uorf_conv3x3_stem: bad sizes (c_out: multiple of 4, <= 64)%s");
+  return check_launch(uorf::launch_vgg_stem_fwd(x, weight, bias, n, h, w, c_out, y, static_cast<cudaStream_t>(stream)), "uorf_conv3x3_stem");
+}
+
+int uorf_conv3x3_stem_dgrad(const float* grad_y, const float* y, const float* weight, int32_t n, int32_t h, int32_t w, int32_t c_out,
+                            float* grad_x, void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_conv3x3_stem_dgrad");
+  if (!c) return UORF_ERR_DEVICE;
+  if (!grad_y || !y || !weight || !grad_x) return fail(UORF_ERR_ARG, "uorf_conv3x3_stem_dgrad: null pointer%s");
+  if (n < 0 || h < 1 || w < 1 || c_out < 1 || c_out > 64) return fail(UORF_ERR_ARG, "uorf_conv3x3_stem_dgrad: bad sizes (c_out <= 64)%s");
+  return check_launch(uorf::launch_vgg_stem_dgrad(grad_y, y, weight, n, h, w, c_out, grad_x, static_cast<cudaStream_t>(stream)),
+                      "uorf_conv3x3_stem_dgrad");
 }
 
 int uorf_adam_step(const uorf_adam_chunk* chunks, int32_t n_chunks, const float* lr_dev, float lr_host, float beta1, float beta2, float eps,

@@ -291,4 +291,93 @@ int launch_conv3x3_x3(const void* x_hi, const void* x_lo, const void* w_img, con
   return finish_launch(1);
 }
 
+// ---- 3-channel stem of the perceptual network (conv1_1 of VGG16: 3 -> c_out channels, 3x3, pad 1) in fp32 FFMA --------------
+// Forward: x NCHW [n][3][h][w] -> y NHWC [n][h][w][c_out] = relu(conv + bias) (the layout the tensor-core layers read).
+// 27 inputs per pixel: a thread owns one pixel and four output channels; the 16 threads of a pixel share its loads through L1.
+// weight [c_out][3][3][3] (the Conv2d tensor as it is), c_out a multiple of 4 and <= 64.
+__global__ void __launch_bounds__(256) vgg_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ weight, const float* __restrict__ bias,
+                                                            int n, int h, int w, int c_out, float* __restrict__ y) {
+  __shared__ float s_w[27][64];
+  for (int e = threadIdx.x; e < 27 * c_out; e += blockDim.x) s_w[e % 27][e / 27] = weight[e];     // [o][c][ky][kx] -> [c ky kx][o]
+  __syncthreads();
+  const int groups = c_out >> 2;
+  const long long npix = (long long)n * h * w;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix = gid / groups;
+  const int o4 = (int)(gid % groups) * 4;
+  if (pix >= npix) return;
+  const int px = (int)(pix % w), py = (int)((pix / w) % h);
+  const float* src = x + (pix / ((long long)h * w)) * 3LL * h * w;
+  float a0 = bias[o4], a1 = bias[o4 + 1], a2 = bias[o4 + 2], a3 = bias[o4 + 3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yy = py + ky - 1, xx = px + kx - 1;
+        const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(src + ((long long)c * h + yy) * w + xx) : 0.f;
+        const float4 wv = *reinterpret_cast<const float4*>(&s_w[(c * 3 + ky) * 3 + kx][o4]);
+        a0 = fmaf(v, wv.x, a0); a1 = fmaf(v, wv.y, a1); a2 = fmaf(v, wv.z, a2); a3 = fmaf(v, wv.w, a3);
+      }
+  *reinterpret_cast<float4*>(y + pix * c_out + o4) = make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
+}
+
+// Data gradient: g NHWC [n][h][w][c_out] taken where the kept output y > 0 -> gx NCHW [n][3][h][w].  One warp per pixel: a lane owns
+// output channels lane, lane + 32 and three partial sums (one per input channel), folded over the taps in registers and over the
+// lanes by a fixed shuffle tree (bit-reproducible).
+__global__ void __launch_bounds__(256) vgg_stem_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ weight,
+                                                              int n, int h, int w, int c_out, float* __restrict__ gx) {
+  __shared__ float s_w[27][64];
+  for (int e = threadIdx.x; e < 27 * 64; e += blockDim.x) s_w[e % 27][e / 27] = (e / 27) < c_out ? weight[e] : 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long npix = (long long)n * h * w;
+  const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const int px = (int)(pix % w), py = (int)((pix / w) % h);
+  const long long img = pix / ((long long)h * w);
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = py + 1 - ky, xx = px + 1 - kx;          // the output pixel whose tap (ky, kx) read this input pixel
+      if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+      const long long off = ((img * h + yy) * w + xx) * c_out;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int o = lane + 32 * half;
+        if (o < c_out) {
+          const float gv = __ldg(y + off + o) > 0.f ? __ldg(g + off + o) : 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[c] = fmaf(gv, s_w[(c * 3 + ky) * 3 + kx][o], acc[c]);
+        }
+      }
+    }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = acc[c];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0) gx[((img * 3 + c) * h + py) * w + px] = v;
+  }
+}
+
+int launch_vgg_stem_fwd(const float* x, const float* weight, const float* bias, int n, int h, int w, int c_out, float* y, cudaStream_t stream) {
+  if (c_out % 4 != 0 || c_out > 64 || c_out < 4) return UORF_ERR_UNSUPPORTED;
+  const long long threads = (long long)n * h * w * (c_out / 4);
+  if (threads <= 0) return UORF_OK;
+  vgg_stem_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(x, weight, bias, n, h, w, c_out, y);
+  return finish_launch(1);
+}
+
+int launch_vgg_stem_dgrad(const float* g, const float* y, const float* weight, int n, int h, int w, int c_out, float* gx, cudaStream_t stream) {
+  if (c_out > 64 || c_out < 1) return UORF_ERR_UNSUPPORTED;
+  const long long npix = (long long)n * h * w;
+  if (npix <= 0) return UORF_OK;
+  vgg_stem_dgrad_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, stream>>>(g, y, weight, n, h, w, c_out, gx);
+  return finish_launch(1);
+}
+
 }  // namespace uorf

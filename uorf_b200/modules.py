@@ -947,6 +947,10 @@ def _conv3x3_x3(x_nhwc: torch.Tensor, gate: Optional[torch.Tensor], w_img: torch
     return y
 
 
+def _pair(v):
+    return [int(v), int(v)] if isinstance(v, int) else [int(t) for t in v]
+
+
 class _Conv3x3ReluFn(torch.autograd.Function):
     """y = relu(conv3x3(x) + b) on NHWC tensors, frozen weights: the backward is the data gradient only (bf16 pairs: gradients of
     a weighted loss sit far below the fp16 range)."""
@@ -1004,12 +1008,42 @@ class PerceptualVGG(nn.Module):
                 self.layers.append(("torch", m))
             i += 1
         self._torch = nn.ModuleList([l[1] for l in self.layers if l[0] == "torch"])   # keeps them on the module's device
+        self.use_stack = os.environ.get("UORF_VGG_STACK", "1") == "1"   # one autograd node for the whole network (_VggStackFn)
         for p_ in self.parameters():
             p_.requires_grad = False
 
-    def forward(self, x, grad_rows=None):
-        """grad_rows: only the first `grad_rows` images need a gradient (the rest are constants evaluated in the same pass)"""
+    def _stack_plan(self):
+        """[("stem", conv) | ("x3", k, c_out) | ("pool", module)] when the network is stem conv + ReLU followed by tensor-core
+        convolutions and max-pools only (VGG16 features[:23] is): the whole stack then runs under ONE autograd node"""
+        L = self.layers
+        if len(L) < 2 or L[0][0] != "torch" or L[1][0] != "torch" or not isinstance(L[0][1], nn.Conv2d) or not isinstance(L[1][1], nn.ReLU):
+            return None
+        c = L[0][1]
+        if not (c.in_channels == 3 and c.kernel_size == (3, 3) and c.stride == (1, 1) and c.padding == (1, 1) and c.dilation == (1, 1)
+                and c.groups == 1 and c.bias is not None and c.out_channels % 4 == 0 and c.out_channels <= 64 and c.weight.is_cuda
+                and c.weight.dtype == torch.float32):
+            return None
+        ops = [("stem", c)]
+        for l in L[2:]:
+            if l[0] == "x3":
+                ops.append(l)
+            elif isinstance(l[1], nn.MaxPool2d) and not l[1].return_indices:
+                ops.append(("pool", l[1]))
+            else:
+                return None
+        return ops
+
+    def forward(self, x, grad_rows=None, x_const=None):
+        """grad_rows: only the first `grad_rows` images need a gradient (the rest are constants evaluated in the same pass);
+        x_const: further constant images appended to the batch (no torch.cat node, no zero gradient rows for them)"""
         _require_cuda(x)
+        plan = self._stack_plan() if self.use_stack else None
+        if plan is not None:
+            r = x.shape[0] if grad_rows is None else int(grad_rows)
+            return _VggStackFn.apply(self, plan, r, x, x_const).permute(0, 3, 1, 2)
+        if x_const is not None:
+            grad_rows = x.shape[0] if grad_rows is None else grad_rows
+            x = torch.cat([x, x_const], dim=0)
         x = _f32c(x).permute(0, 2, 3, 1)                   # NHWC view of ...
         x = x.contiguous()                                 # ... a channels-last copy (3 channels: tiny)
         for l in self.layers:
@@ -1023,3 +1057,75 @@ class PerceptualVGG(nn.Module):
                 if not x.is_contiguous():
                     x = x.contiguous()
         return x.permute(0, 3, 1, 2)
+
+
+class _VggStackFn(torch.autograd.Function):
+    """The whole perceptual network under one autograd node: forward over the full batch (stem kernel, tensor-core layers, torch's
+    channels-last max-pool with indices), backward over the first `rows` images only - the constant images of the batch never get
+    gradient rows, so there are no per-layer zero fills / copies, and the 3-channel stem and its data gradient are two small FFMA
+    launches instead of cuDNN's NHWC <-> NCHW conversions around a generic engine.  -> features NHWC."""
+
+    @staticmethod
+    def forward(ctx, vgg, plan, rows, x, x_const):
+        xin = _f32c(x if x_const is None else torch.cat([x, x_const.to(x.dtype)], dim=0))
+        n, _, h, w = xin.shape
+        stream = _stream(xin)
+        saved, meta = [], []
+        cur = None
+        with _on(xin):
+            for op in plan:
+                if op[0] == "stem":
+                    conv = op[1]
+                    cur = torch.empty(n, h, w, conv.out_channels, device=xin.device, dtype=torch.float32)
+                    check(lib().uorf_conv3x3_stem(xin.data_ptr(), conv.weight.data_ptr(), conv.bias.data_ptr(), n, h, w, conv.out_channels,
+                                                  cur.data_ptr(), stream), "uorf_conv3x3_stem")
+                    saved.append(cur)
+                    meta.append(("stem", conv))
+                elif op[0] == "x3":
+                    k, c_out = op[1], op[2]
+                    c_in = cur.shape[3]
+                    cur = _conv3x3_x3(cur, None, getattr(vgg, f"w_fwd{k}"), getattr(vgg, f"bias{k}"), c_out, True, "fp16x3")
+                    saved.append(cur)
+                    meta.append(("x3", k, c_in))
+                else:
+                    m = op[1]
+                    ks, st, pd, dl = _pair(m.kernel_size), _pair(m.stride if m.stride is not None else m.kernel_size), _pair(m.padding), _pair(m.dilation)
+                    out, idx = torch.ops.aten.max_pool2d_with_indices(cur.permute(0, 3, 1, 2), ks, st, pd, dl, m.ceil_mode)
+                    meta.append(("pool", (ks, st, pd, dl, m.ceil_mode), tuple(cur.shape)))
+                    saved.append(idx)
+                    cur = out.permute(0, 2, 3, 1)
+                    if not cur.is_contiguous():
+                        cur = cur.contiguous()
+        ctx.vgg, ctx.meta, ctx.rows = vgg, meta, min(int(rows), n)
+        ctx.x_shape = tuple(x.shape)
+        ctx.save_for_backward(*saved)
+        return cur
+
+    @staticmethod
+    def backward(ctx, g):
+        vgg, r = ctx.vgg, ctx.rows
+        saved = ctx.saved_tensors
+        if not ctx.needs_input_grad[3] or r == 0:
+            return None, None, None, None, None
+        g = _f32c(g[:r])
+        # activations walk: saved[i] is the output of op i (its ReLU gate) or the indices of pool i; a pool's input is saved[i - 1]
+        for i in range(len(ctx.meta) - 1, -1, -1):
+            m = ctx.meta[i]
+            if m[0] == "x3":
+                g = _conv3x3_x3(g, saved[i][:r], getattr(vgg, f"w_bwd{m[1]}"), None, m[2], False, "bf16x3")
+            elif m[0] == "pool":
+                ks, st, pd, dl, ceil = m[1]
+                inp = saved[i - 1][:r].permute(0, 3, 1, 2)
+                gi = torch.ops.aten.max_pool2d_with_indices_backward(g.permute(0, 3, 1, 2), inp, ks, st, pd, dl, ceil, saved[i][:r])
+                g = _f32c(gi.permute(0, 2, 3, 1))
+            else:
+                conv = m[1]
+                n_, h, w, c = g.shape
+                gx = torch.empty(ctx.x_shape[0], 3, h, w, device=g.device, dtype=torch.float32)
+                if r < ctx.x_shape[0]:
+                    gx[r:].zero_()
+                with _on(g):
+                    check(lib().uorf_conv3x3_stem_dgrad(g.data_ptr(), saved[i].data_ptr(), conv.weight.data_ptr(), r, h, w, c, gx.data_ptr(),
+                                                        _stream(g)), "uorf_conv3x3_stem_dgrad")
+                g = gx
+        return None, None, None, g, None

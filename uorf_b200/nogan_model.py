@@ -209,7 +209,7 @@ class uorfNoGanModel:
             if isinstance(self.perceptual_net, PerceptualVGG):
                 # both images in ONE pass (half the launches, twice the tiles per launch); the ground-truth half carries no
                 # gradient: its features are detached and the convolution's backward skips those rows
-                feats = self.perceptual_net(torch.cat([rendered_norm, x_norm], dim=0), grad_rows=N)
+                feats = self.perceptual_net(rendered_norm, x_const=x_norm)
                 rendered_feat, x_feat = feats[:N], feats[N:].detach()
             else:
                 rendered_feat = self.perceptual_net(rendered_norm)
