@@ -273,6 +273,17 @@ int uorf_encoder_conv3x3(const float* src_a, int32_t ca, int32_t upsample_a, con
  *   _wgrad: grad_weight [c_out][ca+cb][3][3] and grad_bias [c_out]; the layer input is described as in the forward call (two
  *           sources, source A optionally through the upsample); workspace: uorf_encoder_wgrad_workspace_floats(...) floats.
  * Sums run in a fixed order (bit-reproducible); they differ from cuDNN's by fp32 rounding only. */
+/* weight layouts of the layer calls above for up to 8 layers in one launch (`layers` is a HOST array; the training step refreshes
+ * them once per step): weight [c_out][c_in][3][3] -> fwd_t [c_in][3][3][c_out] (uorf_encoder_conv3x3's weight_t) and
+ * dgrad_t [c_out][3][3][c_in] (uorf_encoder_conv3x3_dgrad's weight_g); either output may be NULL. */
+typedef struct uorf_encoder_prep_layer {
+  const float* weight;
+  float* fwd_t;
+  float* dgrad_t;
+  int32_t c_out;
+  int32_t c_in;
+} uorf_encoder_prep_layer;
+int uorf_encoder_weight_prep(const uorf_encoder_prep_layer* layers, int32_t n_layers, void* stream);
 int uorf_encoder_conv3x3_dgrad(const float* grad_out, const float* kept_out, int32_t c_out, const float* weight_g, int32_t c_in,
                                int32_t h_in, int32_t w_in, int32_t stride, int32_t accumulate, float* grad_in, void* stream);
 /* backward of nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) (models/model.py:27-32): grad_hi [c][2 h_lo][2 w_lo]
@@ -282,6 +293,17 @@ int64_t uorf_encoder_wgrad_workspace_floats(int32_t c_in, int32_t c_out, int32_t
 int uorf_encoder_conv3x3_wgrad(const float* src_a, int32_t ca, int32_t upsample_a, const float* src_b, int32_t cb, const float* grad_out,
                                const float* kept_out, int32_t c_out, int32_t h_in, int32_t w_in, int32_t stride, float* workspace,
                                float* grad_weight, float* grad_bias, void* stream);
+
+/* nn.MaxPool2d(2, 2) of the same network (models/model.py:316-324, VGG16 pools 1-3) folded into the operand split of its reader:
+ *   uorf_conv_split_pool2x2:    x NHWC [n][h][w][c] fp32 -> hi / lo planes [n][h/2][w/2][c] of maxpool(x); the pooled tensor is not
+ *                               materialised (the next convolution is its only reader);
+ *   uorf_conv_split_unpool2x2:  backward: grad_pooled [n][h/2][w/2][c], x the pool's input (the ReLU output of the layer before it)
+ *                               -> hi / lo planes [n][h][w][c] of the gradient routed to the first maximum of every window (torch's
+ *                               choice) where x > 0: the input of that layer's data-gradient convolution.
+ * h, w, c even. */
+int uorf_conv_split_pool2x2(const float* x, void* hi, void* lo, int32_t n, int32_t h, int32_t w, int32_t c, int32_t precision, void* stream);
+int uorf_conv_split_unpool2x2(const float* grad_pooled, const float* x, void* hi, void* lo, int32_t n, int32_t h, int32_t w, int32_t c,
+                              int32_t precision, void* stream);
 
 /* 3-channel stem of the same network (VGG16 conv1_1 + ReLU, models/model.py:316-324), fp32 FFMA:
  *   uorf_conv3x3_stem:        x NCHW [n][3][h][w], weight [c_out][3][3][3] (the Conv2d tensor), bias [c_out]

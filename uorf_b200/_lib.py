@@ -89,6 +89,10 @@ SA_STATE_KEYS = {
     "to_res_bg_b1": "to_res_bg.1.bias", "to_res_bg_w2": "to_res_bg.3.weight", "to_res_bg_b2": "to_res_bg.3.bias",
 }
 
+class EncoderPrepLayer(C.Structure):      # struct uorf_encoder_prep_layer
+    _fields_ = [("weight", C.c_void_p), ("fwd_t", C.c_void_p), ("dgrad_t", C.c_void_p), ("c_out", C.c_int32), ("c_in", C.c_int32)]
+
+
 _SIGNATURES = {
     "uorf_abi_version": (C.c_int, []),
     "uorf_last_error": (C.c_char_p, []),
@@ -106,6 +110,10 @@ _SIGNATURES = {
     "uorf_conv3x3_stem": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "uorf_conv3x3_stem_dgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                           C.c_void_p]),
+    "uorf_encoder_weight_prep": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "uorf_conv_split_pool2x2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "uorf_conv_split_unpool2x2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_void_p]),
     "uorf_adam_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "uorf_conv_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "uorf_conv3x3_workspace_floats": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

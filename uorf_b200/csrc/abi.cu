@@ -24,6 +24,8 @@ int launch_encoder_wgrad3x3(const float* src_a, int ca, int up_a, const float* s
                             cudaStream_t stream);
 int launch_vgg_stem_fwd(const float* x, const float* weight, const float* bias, int n, int h, int w, int c_out, float* y, cudaStream_t stream);
 int launch_vgg_stem_dgrad(const float* g, const float* y, const float* weight, int n, int h, int w, int c_out, float* gx, cudaStream_t stream);
+int launch_encoder_weight_prep(const uorf_encoder_prep_layer* layers, int n_layers, cudaStream_t stream);
+int launch_conv_split_pool(const float* x, const float* g, void* hi, void* lo, int n, int h, int w, int c, int f16, int num_sms, cudaStream_t stream);
 int launch_adam_step(const uorf_adam_chunk* chunks, int n_chunks, const float* lr_dev, float lr_host, float beta1, float beta2, float eps,
                      float weight_decay, cudaStream_t stream);
 int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* weight_t, const float* bias,
@@ -164,6 +166,29 @@ int uorf_init(int device) {
   return UORF_OK;
 }
 
+static int split_pool_common(const char* what, const float* x, const float* g, void* hi, void* lo, int32_t n, int32_t h, int32_t w, int32_t c,
+                             int32_t precision, void* stream) {
+  DeviceCtx* dc = ctx();
+  Range nvtx_range(what);
+  if (!dc) return UORF_ERR_DEVICE;
+  if (!x || !hi || !lo) return fail(UORF_ERR_ARG, "uorf_conv_split_pool2x2 / _unpool2x2: null pointer%s");
+  if (n < 0 || h < 2 || w < 2 || c < 2 || ((h | w | c) & 1)) return fail(UORF_ERR_ARG, "uorf_conv_split_pool2x2 / _unpool2x2: h, w, c must be even%s");
+  if (precision != UORF_PREC_FP16X3 && precision != UORF_PREC_BF16X3)
+    return fail(UORF_ERR_ARG, "uorf_conv_split_pool2x2 / _unpool2x2: precision must be a x3 mode%s");
+  return check_launch(uorf::launch_conv_split_pool(x, g, hi, lo, n, h, w, c, precision == UORF_PREC_FP16X3, dc->num_sms,
+                                                   static_cast<cudaStream_t>(stream)), what);
+}
+
+int uorf_conv_split_pool2x2(const float* x, void* hi, void* lo, int32_t n, int32_t h, int32_t w, int32_t c, int32_t precision, void* stream) {
+  return split_pool_common("uorf_conv_split_pool2x2", x, nullptr, hi, lo, n, h, w, c, precision, stream);
+}
+
+int uorf_conv_split_unpool2x2(const float* grad_pooled, const float* x, void* hi, void* lo, int32_t n, int32_t h, int32_t w, int32_t c,
+                              int32_t precision, void* stream) {
+  if (!grad_pooled) return fail(UORF_ERR_ARG, "uorf_conv_split_unpool2x2: null pointer%s");
+  return split_pool_common("uorf_conv_split_unpool2x2", x, grad_pooled, hi, lo, n, h, w, c, precision, stream);
+}
+
 int uorf_conv3x3_stem(const float* x, const float* weight, const float* bias, int32_t n, int32_t h, int32_t w, int32_t c_out, float* y,
                       void* stream) {
   DeviceCtx* c = ctx();
@@ -194,6 +219,16 @@ int uorf_adam_step(const uorf_adam_chunk* chunks, int32_t n_chunks, const float*
   if (!(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f)) return fail(UORF_ERR_ARG, "uorf_adam_step: bad hyper-parameters%s");
   return check_launch(uorf::launch_adam_step(chunks, n_chunks, lr_dev, lr_host, beta1, beta2, eps, weight_decay, static_cast<cudaStream_t>(stream)),
                       "uorf_adam_step");
+}
+
+int uorf_encoder_weight_prep(const uorf_encoder_prep_layer* layers, int32_t n_layers, void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_encoder_weight_prep");
+  if (!c) return UORF_ERR_DEVICE;
+  if (n_layers < 0 || n_layers > 8 || (n_layers > 0 && !layers)) return fail(UORF_ERR_ARG, "uorf_encoder_weight_prep: 0..8 layers%s");
+  for (int i = 0; i < n_layers; ++i)
+    if (!layers[i].weight || layers[i].c_out < 1 || layers[i].c_in < 1) return fail(UORF_ERR_ARG, "uorf_encoder_weight_prep: bad layer%s");
+  return check_launch(uorf::launch_encoder_weight_prep(layers, n_layers, static_cast<cudaStream_t>(stream)), "uorf_encoder_weight_prep");
 }
 
 int uorf_encoder_conv3x3_dgrad(const float* grad_out, const float* kept_out, int32_t c_out, const float* weight_g, int32_t c_in,

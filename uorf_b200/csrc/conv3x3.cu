@@ -220,6 +220,63 @@ __global__ void __launch_bounds__(256) conv_split_kernel(const float* __restrict
   }
 }
 
+// nn.MaxPool2d(2, 2) folded into the operand split of the NEXT layer: x NHWC [n][h][w][c] -> hi / lo planes [n][h/2][w/2][c] of the
+// pooled tensor, which itself never reaches memory (its only reader is that layer).  One thread per window and channel pair.
+template <bool F16>
+__global__ void __launch_bounds__(256) conv_split_pool_kernel(const float* __restrict__ x, unsigned int* __restrict__ hi, unsigned int* __restrict__ lo,
+                                                              int n, int h, int w, int c) {
+  const int cp = c >> 1, wo = w >> 1, ho = h >> 1;
+  const long long total = (long long)n * ho * wo * cp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % cp);
+    const long long win = i / cp;
+    const int ox = (int)(win % wo), oy = (int)((win / wo) % ho);
+    const long long img = win / ((long long)wo * ho);
+    const float2* src = reinterpret_cast<const float2*>(x + ((img * h + 2 * oy) * w + 2 * ox) * c) + ch;
+    const float2 a = __ldg(src), b = __ldg(src + cp), d = __ldg(src + (long long)w * cp), e = __ldg(src + (long long)w * cp + cp);
+    uint32_t vh, vl;
+    split2<F16>(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)), vh, vl);
+    hi[i] = vh;
+    lo[i] = vl;
+  }
+}
+
+// ... and its backward folded into the split that feeds the data gradient of the layer BEFORE the pool: g [n][h/2][w/2][c] (gradient
+// of the pooled tensor), x [n][h][w][c] (the pool's input = that layer's ReLU output) -> hi / lo planes [n][h][w][c] of
+// (g routed to the first maximum of each window, where x > 0).  First maximum in row-major window order, as torch's max-pool picks.
+template <bool F16>
+__global__ void __launch_bounds__(256) conv_split_unpool_kernel(const float* __restrict__ g, const float* __restrict__ x, unsigned int* __restrict__ hi,
+                                                                unsigned int* __restrict__ lo, int n, int h, int w, int c) {
+  const int cp = c >> 1, wo = w >> 1, ho = h >> 1;
+  const long long total = (long long)n * ho * wo * cp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % cp);
+    const long long win = i / cp;
+    const int ox = (int)(win % wo), oy = (int)((win / wo) % ho);
+    const long long img = win / ((long long)wo * ho);
+    const long long base = ((img * h + 2 * oy) * w + 2 * ox) * (long long)cp + ch;      // float2 / word index of the window's first pixel
+    const float2* src = reinterpret_cast<const float2*>(x) + base;
+    const float2 v[4] = {__ldg(src), __ldg(src + cp), __ldg(src + (long long)w * cp), __ldg(src + (long long)w * cp + cp)};
+    const float2 gv = __ldg(reinterpret_cast<const float2*>(g) + i);
+    int ax = 0, ay = 0;
+    float mx = v[0].x, my = v[0].y;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      if (v[q].x > mx) { mx = v[q].x; ax = q; }
+      if (v[q].y > my) { my = v[q].y; ay = q; }
+    }
+    const float ox_ = mx > 0.f ? gv.x : 0.f, oy_ = my > 0.f ? gv.y : 0.f;      // ReLU gate of the layer that produced x
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t vh, vl;
+      split2<F16>(q == ax ? ox_ : 0.f, q == ay ? oy_ : 0.f, vh, vl);
+      const long long dst = base + (q & 1) * cp + (q >> 1) * (long long)w * cp;
+      hi[dst] = vh;
+      lo[dst] = vl;
+    }
+  }
+}
+
 // split-K: y = [relu](bias + sum of the partial sums), fixed order (deterministic)
 __global__ void __launch_bounds__(256) conv_reduce_kernel(const float4* __restrict__ part, int splits, long long n4, const float* __restrict__ bias,
                                                           int c_out, int relu, float4* __restrict__ y) {
@@ -254,6 +311,23 @@ int launch_conv_split(const float* x, const float* gate, void* hi, void* lo, lon
   if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
   if (f16) conv_split_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(x, gate, static_cast<unsigned int*>(hi), static_cast<unsigned int*>(lo), npairs);
   else conv_split_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(x, gate, static_cast<unsigned int*>(hi), static_cast<unsigned int*>(lo), npairs);
+  return finish_launch(1);
+}
+
+int launch_conv_split_pool(const float* x, const float* g, void* hi, void* lo, int n, int h, int w, int c, int f16, int num_sms, cudaStream_t stream) {
+  const long long total = (long long)n * (h / 2) * (w / 2) * (c / 2);
+  if (total <= 0) return UORF_OK;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+  unsigned int* ph = static_cast<unsigned int*>(hi);
+  unsigned int* pl = static_cast<unsigned int*>(lo);
+  if (g == nullptr) {
+    if (f16) conv_split_pool_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(x, ph, pl, n, h, w, c);
+    else conv_split_pool_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(x, ph, pl, n, h, w, c);
+  } else {
+    if (f16) conv_split_unpool_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(g, x, ph, pl, n, h, w, c);
+    else conv_split_unpool_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(g, x, ph, pl, n, h, w, c);
+  }
   return finish_launch(1);
 }
 
@@ -302,25 +376,26 @@ __global__ void __launch_bounds__(256) vgg_stem_fwd_kernel(const float* __restri
   __syncthreads();
   const int groups = c_out >> 2;
   const long long npix = (long long)n * h * w;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long pix = gid / groups;
-  const int o4 = (int)(gid % groups) * 4;
-  if (pix >= npix) return;
-  const int px = (int)(pix % w), py = (int)((pix / w) % h);
-  const float* src = x + (pix / ((long long)h * w)) * 3LL * h * w;
-  float a0 = bias[o4], a1 = bias[o4 + 1], a2 = bias[o4 + 2], a3 = bias[o4 + 3];
+  // grid-stride: the weight tile is staged once per block, not once per 16 pixels
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < npix * groups; gid += (long long)gridDim.x * blockDim.x) {
+    const long long pix = gid / groups;
+    const int o4 = (int)(gid % groups) * 4;
+    const int px = (int)(pix % w), py = (int)((pix / w) % h);
+    const float* src = x + (pix / ((long long)h * w)) * 3LL * h * w;
+    float a0 = bias[o4], a1 = bias[o4 + 1], a2 = bias[o4 + 2], a3 = bias[o4 + 3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int yy = py + ky - 1, xx = px + kx - 1;
-        const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(src + ((long long)c * h + yy) * w + xx) : 0.f;
-        const float4 wv = *reinterpret_cast<const float4*>(&s_w[(c * 3 + ky) * 3 + kx][o4]);
-        a0 = fmaf(v, wv.x, a0); a1 = fmaf(v, wv.y, a1); a2 = fmaf(v, wv.z, a2); a3 = fmaf(v, wv.w, a3);
-      }
-  *reinterpret_cast<float4*>(y + pix * c_out + o4) = make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = py + ky - 1, xx = px + kx - 1;
+          const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(src + ((long long)c * h + yy) * w + xx) : 0.f;
+          const float4 wv = *reinterpret_cast<const float4*>(&s_w[(c * 3 + ky) * 3 + kx][o4]);
+          a0 = fmaf(v, wv.x, a0); a1 = fmaf(v, wv.y, a1); a2 = fmaf(v, wv.z, a2); a3 = fmaf(v, wv.w, a3);
+        }
+    *reinterpret_cast<float4*>(y + pix * c_out + o4) = make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
+  }
 }
 
 // Data gradient: g NHWC [n][h][w][c_out] taken where the kept output y > 0 -> gx NCHW [n][3][h][w].  One warp per pixel: a lane owns
@@ -333,34 +408,35 @@ __global__ void __launch_bounds__(256) vgg_stem_dgrad_kernel(const float* __rest
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long npix = (long long)n * h * w;
-  const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (pix >= npix) return;
-  const int px = (int)(pix % w), py = (int)((pix / w) % h);
-  const long long img = pix / ((long long)h * w);
-  float acc[3] = {0.f, 0.f, 0.f};
+  const int wpb = blockDim.x >> 5;
+  for (long long pix = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); pix < npix; pix += (long long)gridDim.x * wpb) {   // warp-uniform
+    const int px = (int)(pix % w), py = (int)((pix / w) % h);
+    const long long img = pix / ((long long)h * w);
+    float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int yy = py + 1 - ky, xx = px + 1 - kx;          // the output pixel whose tap (ky, kx) read this input pixel
-      if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
-      const long long off = ((img * h + yy) * w + xx) * c_out;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yy = py + 1 - ky, xx = px + 1 - kx;          // the output pixel whose tap (ky, kx) read this input pixel
+        if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+        const long long off = ((img * h + yy) * w + xx) * c_out;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int o = lane + 32 * half;
-        if (o < c_out) {
-          const float gv = __ldg(y + off + o) > 0.f ? __ldg(g + off + o) : 0.f;
+        for (int half = 0; half < 2; ++half) {
+          const int o = lane + 32 * half;
+          if (o < c_out) {
+            const float gv = __ldg(y + off + o) > 0.f ? __ldg(g + off + o) : 0.f;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) acc[c] = fmaf(gv, s_w[(c * 3 + ky) * 3 + kx][o], acc[c]);
+            for (int c = 0; c < 3; ++c) acc[c] = fmaf(gv, s_w[(c * 3 + ky) * 3 + kx][o], acc[c]);
+          }
         }
       }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = acc[c];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if (lane == 0) gx[((img * 3 + c) * h + py) * w + px] = v;
     }
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float v = acc[c];
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    if (lane == 0) gx[((img * 3 + c) * h + py) * w + px] = v;
   }
 }
 
@@ -368,7 +444,9 @@ int launch_vgg_stem_fwd(const float* x, const float* weight, const float* bias, 
   if (c_out % 4 != 0 || c_out > 64 || c_out < 4) return UORF_ERR_UNSUPPORTED;
   const long long threads = (long long)n * h * w * (c_out / 4);
   if (threads <= 0) return UORF_OK;
-  vgg_stem_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(x, weight, bias, n, h, w, c_out, y);
+  long long blocks = (threads + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  vgg_stem_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, weight, bias, n, h, w, c_out, y);
   return finish_launch(1);
 }
 
@@ -376,7 +454,9 @@ int launch_vgg_stem_dgrad(const float* g, const float* y, const float* weight, i
   if (c_out > 64 || c_out < 1) return UORF_ERR_UNSUPPORTED;
   const long long npix = (long long)n * h * w;
   if (npix <= 0) return UORF_OK;
-  vgg_stem_dgrad_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, stream>>>(g, y, weight, n, h, w, c_out, gx);
+  long long blocks = (npix + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  vgg_stem_dgrad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, y, weight, n, h, w, c_out, gx);
   return finish_launch(1);
 }
 

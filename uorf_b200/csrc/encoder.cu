@@ -357,6 +357,29 @@ int launch_encoder_upsample2x_bwd(const float* grad_hi, int c, int h_lo, int w_l
   return finish_launch(1);
 }
 
+// Both weight layouts the layer kernels read, for every layer of the U-Net in one launch (the weights move every training step):
+// Conv2d weight [c_out][c_in][3][3] -> forward [c_in][3][3][c_out] and data-gradient [c_out][3][3][c_in] (either may be null).
+struct EncPrepTable { uorf_encoder_prep_layer l[8]; };
+__global__ void encoder_weight_prep_kernel(const EncPrepTable t) {
+  const uorf_encoder_prep_layer L = t.l[blockIdx.y];
+  const int n = L.c_out * L.c_in * 9;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int k = e % 9, ci = (e / 9) % L.c_in, co = e / (9 * L.c_in);
+    const float v = __ldg(L.weight + e);
+    if (L.fwd_t) L.fwd_t[(ci * 9 + k) * L.c_out + co] = v;
+    if (L.dgrad_t) L.dgrad_t[(co * 9 + k) * L.c_in + ci] = v;
+  }
+}
+
+int launch_encoder_weight_prep(const uorf_encoder_prep_layer* layers, int n_layers, cudaStream_t stream) {
+  if (n_layers < 1) return UORF_OK;
+  if (n_layers > 8) return UORF_ERR_UNSUPPORTED;
+  EncPrepTable t = {};
+  for (int i = 0; i < n_layers; ++i) t.l[i] = layers[i];
+  encoder_weight_prep_kernel<<<dim3(16, n_layers), 256, 0, stream>>>(t);
+  return finish_launch(1);
+}
+
 // ---- weight / bias gradient ---------------------------------------------------------------------------------------
 // dW[o][c][ky][kx] = sum over output pixels of G[o][y][x] * X[c][y*s + ky - 1][x*s + kx - 1], G = grad_out where kept_out > 0, X the
 // layer's input read exactly as the forward reads it (two sources, source A optionally through the upsample; zero padding).
@@ -532,7 +555,7 @@ static int wgrad_shares(int c_in, int c_out, int h_out, int w_out) {
   const int n_tiles = ((h_out + kEncTile - 1) / kEncTile) * ((w_out + kEncTile - 1) / kEncTile);
   const int base = ((c_in + kEncIcb - 1) / kEncIcb) * ((c_out + kEncOcb - 1) / kEncOcb);
   int s = 1;
-  while (s * 2 <= n_tiles && base * s < 2 * 148) s *= 2;
+  while (s * 2 <= n_tiles && base * s * 2 <= 148) s *= 2;   // at most one wave of CTAs: more tiles per CTA amortise staging, reduction and partial traffic
   return s;
 }
 

@@ -97,6 +97,7 @@ class Encoder(nn.Module):
         self.enc_up_1 = nn.Sequential(nn.Conv2d(z_dim * 2, z_dim, 3, stride=1, padding=1), nn.ReLU(True))
         self._planes = {}
         self._wt = {}              # transposed conv weights of the inference path, keyed by weight version
+        self._train_wt = None      # (weight addresses, {layer: (forward layout, data-gradient layout)}, launch table) of the training path
         self.use_kernels = True    # False: always the torch / cuDNN layers
         self.use_kernels_in_training = True   # forward by the kernels under autograd too (_EncoderFn)
         # ... and the backward by the fp32 gradient kernels; False (UORF_ENCODER_BACKWARD=cudnn, A-B runs): cuDNN convolution_backward per layer
@@ -121,8 +122,34 @@ class Encoder(nn.Module):
         counters - torch's fused Adam (`torch._fused_adam_`) and CUDA-graph replays of an optimizer step both do"""
         self._wt.clear()
 
-    def _conv(self, layer, src_a, up_a, src_b, h_in, w_in, use_cache=True):
+    def _training_weights(self):
+        """{layer name: (forward layout [in][3][3][out], data-gradient layout [out][3][3][in])} of the CURRENT weights, written by one
+        launch into buffers that stay (graph-capturable; the training step calls this once, before its forward)"""
+        names = (["enc_down_0"] if self.bottom else []) + ["enc_down_1", "enc_down_2", "enc_down_3", "enc_up_3", "enc_up_2", "enc_up_1"]
+        convs = [getattr(self, n)[0] for n in names]
+        dev = convs[0].weight.device
+        if any(c.weight.dtype != torch.float32 or not c.weight.is_contiguous() for c in convs):
+            raise _lib.UorfError("Encoder kernels need contiguous fp32 weights")
+        key = tuple(c.weight.data_ptr() for c in convs)
+        if self._train_wt is None or self._train_wt[0] != key:
+            bufs = {n: (torch.empty(c.in_channels, 3, 3, c.out_channels, device=dev, dtype=torch.float32),
+                        torch.empty(c.out_channels, 3, 3, c.in_channels, device=dev, dtype=torch.float32) if i > 0 else None)
+                    for i, (n, c) in enumerate(zip(names, convs))}       # the first layer's input needs no gradient
+            table = (_lib.EncoderPrepLayer * len(names))()
+            for i, (n, c) in enumerate(zip(names, convs)):
+                table[i].weight, table[i].fwd_t, table[i].dgrad_t = c.weight.data_ptr(), bufs[n][0].data_ptr(), _ptr(bufs[n][1])
+                table[i].c_out, table[i].c_in = c.out_channels, c.in_channels
+            self._train_wt = (key, bufs, table)
+        _, bufs, table = self._train_wt
+        w0 = convs[0].weight
+        with _on(w0):
+            check(lib().uorf_encoder_weight_prep(table, len(table), _stream(w0)), "uorf_encoder_weight_prep")
+        return bufs
+
+    def _conv(self, layer, src_a, up_a, src_b, h_in, w_in, use_cache=True, wt=None):
         conv = layer[0]
+        if wt is not None:
+            return self._conv_launch(conv, wt, src_a, up_a, src_b, h_in, w_in)
         key = (conv.weight.data_ptr(), conv.weight._version)
         cache = self._wt.get(id(conv)) if use_cache else None
         if cache is None or cache[0] != key:       # [out][in][3][3] -> [in][3][3][out], once per weight version
@@ -132,11 +159,14 @@ class Encoder(nn.Module):
             # Adam / graph replays move them without bumping `_version` (invalidate_weight_cache covers inference after those).
             if use_cache and not torch.cuda.is_current_stream_capturing():
                 self._wt[id(conv)] = cache
+        return self._conv_launch(conv, cache[1], src_a, up_a, src_b, h_in, w_in)
+
+    def _conv_launch(self, conv, weight_t, src_a, up_a, src_b, h_in, w_in):
         stride = conv.stride[0]
         ca, cb = src_a.shape[0], (0 if src_b is None else src_b.shape[0])
         out = torch.empty(conv.out_channels, (h_in - 1) // stride + 1, (w_in - 1) // stride + 1, device=src_a.device, dtype=torch.float32)
         with _on(src_a):
-            check(lib().uorf_encoder_conv3x3(src_a.data_ptr(), ca, int(up_a), _ptr(src_b), cb, cache[1].data_ptr(),
+            check(lib().uorf_encoder_conv3x3(src_a.data_ptr(), ca, int(up_a), _ptr(src_b), cb, weight_t.data_ptr(),
                                              _f32c(conv.bias.detach()).data_ptr(), conv.out_channels, h_in, w_in, stride, out.data_ptr(),
                                              _stream(src_a)), "uorf_encoder_conv3x3")
         return out
@@ -147,21 +177,23 @@ class Encoder(nn.Module):
         img = _f32c(x[0])
         planes = self._pixel_planes(H, W, x.device)[0]
         d0 = None
-        uc = keep is None      # training forward: always the current weights
+        uc = keep is None      # training forward: always the current weights ...
+        wts = self._training_weights() if keep is not None else None      # ... both layouts of all layers from one launch
+        wt_of = lambda name: None if wts is None else wts[name][0]
         if self.bottom:
-            d0 = self._conv(self.enc_down_0, img, False, planes, H, W, uc)
-            d1 = self._conv(self.enc_down_1, d0, False, None, H, W, uc)
+            d0 = self._conv(self.enc_down_0, img, False, planes, H, W, uc, wt_of("enc_down_0"))
+            d1 = self._conv(self.enc_down_1, d0, False, None, H, W, uc, wt_of("enc_down_1"))
         else:
-            d1 = self._conv(self.enc_down_1, img, False, planes, H, W, uc)
+            d1 = self._conv(self.enc_down_1, img, False, planes, H, W, uc, wt_of("enc_down_1"))
         h1, w1 = d1.shape[1], d1.shape[2]
-        d2 = self._conv(self.enc_down_2, d1, False, None, h1, w1, uc)
+        d2 = self._conv(self.enc_down_2, d1, False, None, h1, w1, uc, wt_of("enc_down_2"))
         h2, w2 = d2.shape[1], d2.shape[2]
-        d3 = self._conv(self.enc_down_3, d2, False, None, h2, w2, uc)
-        u3 = self._conv(self.enc_up_3, d3, False, None, d3.shape[1], d3.shape[2], uc)      # kept at low resolution
-        u2 = self._conv(self.enc_up_2, u3, True, d2, h2, w2, uc)                           # cat[upsample(u3), d2]
-        out = self._conv(self.enc_up_1, u2, True, d1, h1, w1, uc)                          # cat[upsample(u2), d1]
+        d3 = self._conv(self.enc_down_3, d2, False, None, h2, w2, uc, wt_of("enc_down_3"))
+        u3 = self._conv(self.enc_up_3, d3, False, None, d3.shape[1], d3.shape[2], uc, wt_of("enc_up_3"))      # kept at low resolution
+        u2 = self._conv(self.enc_up_2, u3, True, d2, h2, w2, uc, wt_of("enc_up_2"))                           # cat[upsample(u3), d2]
+        out = self._conv(self.enc_up_1, u2, True, d1, h1, w1, uc, wt_of("enc_up_1"))                          # cat[upsample(u2), d1]
         if keep is not None:
-            keep.update(img=img, planes=planes, d0=d0, d1=d1, d2=d2, d3=d3, u3=u3, u2=u2, out=out)
+            keep.update(wts=wts, img=img, planes=planes, d0=d0, d1=d1, d2=d2, d3=d3, u3=u3, u2=u2, out=out)
         return out[None]
 
     def _kernels_apply(self, x):
@@ -215,6 +247,7 @@ class _EncoderFn(torch.autograd.Function):
             out = enc._forward_inference(x, keep)
         ctx.enc = enc
         ctx.x_needs_grad = x.requires_grad
+        ctx.wts = keep["wts"]      # the step's weight layouts (the weights do not move between this forward and its backward)
         ctx.names = [n for n in ("img", "planes", "d0", "d1", "d2", "d3", "u3", "u2", "out") if keep[n] is not None]
         ctx.save_for_backward(*[keep[n] for n in ctx.names])
         return out
@@ -226,7 +259,7 @@ class _EncoderFn(torch.autograd.Function):
         names = [n for n, _ in enc.named_parameters()]
         sink = enc.grad_sink
         if enc.backward_kernels and g_out.is_cuda and not ctx.x_needs_grad:
-            grads = _encoder_backward_kernels(enc, a, g_out, sink)     # writes straight into the sink's buffers
+            grads = _encoder_backward_kernels(enc, a, g_out, sink, ctx.wts)     # writes straight into the sink's buffers
             return (None, None) + ((None,) * len(names) if sink is not None else tuple(grads[n] for n in names))
         gx, grads = _encoder_backward(enc, a, g_out, ctx.x_needs_grad)
         if sink is not None:       # gradients land in caller-owned buffers (one flat all-reduce bucket); autograd sees None
@@ -235,7 +268,7 @@ class _EncoderFn(torch.autograd.Function):
         return (None, gx) + tuple(grads[n] for n in names)
 
 
-def _encoder_backward_kernels(enc, a, g_out, sink=None):
+def _encoder_backward_kernels(enc, a, g_out, sink=None, wts=None):
     """Backward of Encoder.forward (batch 1, no image gradient) on the fp32 kernels of csrc/encoder.cu: per layer one weight / bias
     gradient launch (+ its fixed-order reduce) that reads the layer input the way the forward did (no cat / upsample tensors) and one
     data-gradient launch; the ReLU gates are taken from the kept outputs inside the loads.  The two bilinear-upsample backwards are fixed-order gathers, the
@@ -266,7 +299,7 @@ def _encoder_backward_kernels(enc, a, g_out, sink=None):
     def dgrad(name, g, out, h_in, w_in, into=None):
         """-> gradient of the layer input [c_in][h_in][w_in]; `into`: added to that tensor instead (skip connection)"""
         conv = getattr(enc, name)[0]
-        wg = conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()       # [c_out][3][3][c_in]
+        wg = wts[name][1] if wts is not None else conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()   # [c_out][3][3][c_in]
         gi = torch.empty(conv.in_channels, h_in, w_in, device=dev, dtype=torch.float32) if into is None else into
         check(lib().uorf_encoder_conv3x3_dgrad(g.data_ptr(), out.data_ptr(), conv.out_channels, wg.data_ptr(), conv.in_channels, h_in, w_in,
                                                conv.stride[0], int(into is not None), gi.data_ptr(), stream), "uorf_encoder_conv3x3_dgrad")
@@ -934,17 +967,39 @@ def _conv_split(x: torch.Tensor, gate: Optional[torch.Tensor], precision: str):
     return hi, lo
 
 
+def _conv3x3_run(hi: torch.Tensor, lo: torch.Tensor, shape, w_img: torch.Tensor, bias: Optional[torch.Tensor], c_out: int, relu: bool,
+                 precision: str) -> torch.Tensor:
+    """the convolution on operand planes that are already split (hi / lo of an n x h x w x c_in tensor) -> n x h x w x c_out fp32"""
+    n, h, w, c_in = shape
+    y = torch.empty((n, h, w, c_out), dtype=torch.float32, device=hi.device)
+    with _on(hi):
+        nws = int(lib().uorf_conv3x3_workspace_floats(n, h, w, c_in, c_out))
+        ws = torch.empty(nws, dtype=torch.float32, device=hi.device) if nws else None
+        check(lib().uorf_conv3x3_x3(hi.data_ptr(), lo.data_ptr(), w_img.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(ws), n, h, w, c_in,
+                                    c_out, int(relu), _lib.PRECISIONS[precision], _stream(hi)), "uorf_conv3x3_x3")
+    return y
+
+
 def _conv3x3_x3(x_nhwc: torch.Tensor, gate: Optional[torch.Tensor], w_img: torch.Tensor, bias: Optional[torch.Tensor], c_out: int,
                 relu: bool, precision: str) -> torch.Tensor:
-    n, h, w, c_in = x_nhwc.shape
     hi, lo = _conv_split(x_nhwc, gate, precision)
-    y = torch.empty((n, h, w, c_out), dtype=torch.float32, device=x_nhwc.device)
+    return _conv3x3_run(hi, lo, tuple(x_nhwc.shape), w_img, bias, c_out, relu, precision)
+
+
+def _conv_split_pool(x_nhwc: torch.Tensor, grad_pooled: Optional[torch.Tensor], precision: str):
+    """grad_pooled None: planes of maxpool2x2(x) (n x h/2 x w/2 x c); else planes of the pool's backward behind x's ReLU gate (n x h x w x c)"""
+    n, h, w, c = x_nhwc.shape
+    shape = (n, h // 2, w // 2, c) if grad_pooled is None else (n, h, w, c)
+    hi = torch.empty(shape, dtype=torch.int16, device=x_nhwc.device)
+    lo = torch.empty(shape, dtype=torch.int16, device=x_nhwc.device)
     with _on(x_nhwc):
-        nws = int(lib().uorf_conv3x3_workspace_floats(n, h, w, c_in, c_out))
-        ws = torch.empty(nws, dtype=torch.float32, device=x_nhwc.device) if nws else None
-        check(lib().uorf_conv3x3_x3(hi.data_ptr(), lo.data_ptr(), w_img.data_ptr(), _ptr(bias), y.data_ptr(), _ptr(ws), n, h, w, c_in,
-                                    c_out, int(relu), _lib.PRECISIONS[precision], _stream(x_nhwc)), "uorf_conv3x3_x3")
-    return y
+        if grad_pooled is None:
+            check(lib().uorf_conv_split_pool2x2(x_nhwc.data_ptr(), hi.data_ptr(), lo.data_ptr(), n, h, w, c, _lib.PRECISIONS[precision],
+                                                _stream(x_nhwc)), "uorf_conv_split_pool2x2")
+        else:
+            check(lib().uorf_conv_split_unpool2x2(grad_pooled.data_ptr(), x_nhwc.data_ptr(), hi.data_ptr(), lo.data_ptr(), n, h, w, c,
+                                                  _lib.PRECISIONS[precision], _stream(x_nhwc)), "uorf_conv_split_unpool2x2")
+    return hi, lo, shape
 
 
 def _pair(v):
@@ -1009,6 +1064,7 @@ class PerceptualVGG(nn.Module):
             i += 1
         self._torch = nn.ModuleList([l[1] for l in self.layers if l[0] == "torch"])   # keeps them on the module's device
         self.use_stack = os.environ.get("UORF_VGG_STACK", "1") == "1"   # one autograd node for the whole network (_VggStackFn)
+        self.fuse_pool = os.environ.get("UORF_VGG_FUSE_POOL", "1") == "1"   # ... with the 2x2 max-pools folded into the operand splits
         for p_ in self.parameters():
             p_.requires_grad = False
 
@@ -1073,25 +1129,40 @@ class _VggStackFn(torch.autograd.Function):
         saved, meta = [], []
         cur = None
         with _on(xin):
-            for op in plan:
+            pending = None           # (hi, lo, shape): the next convolution's operand planes, produced by a fused pool + split
+            for j, op in enumerate(plan):
                 if op[0] == "stem":
                     conv = op[1]
                     cur = torch.empty(n, h, w, conv.out_channels, device=xin.device, dtype=torch.float32)
                     check(lib().uorf_conv3x3_stem(xin.data_ptr(), conv.weight.data_ptr(), conv.bias.data_ptr(), n, h, w, conv.out_channels,
                                                   cur.data_ptr(), stream), "uorf_conv3x3_stem")
+                    meta.append(("stem", conv, len(saved)))
                     saved.append(cur)
-                    meta.append(("stem", conv))
                 elif op[0] == "x3":
                     k, c_out = op[1], op[2]
-                    c_in = cur.shape[3]
-                    cur = _conv3x3_x3(cur, None, getattr(vgg, f"w_fwd{k}"), getattr(vgg, f"bias{k}"), c_out, True, "fp16x3")
+                    if pending is not None:
+                        c_in = pending[2][3]
+                        cur = _conv3x3_run(pending[0], pending[1], pending[2], getattr(vgg, f"w_fwd{k}"), getattr(vgg, f"bias{k}"), c_out, True,
+                                           "fp16x3")
+                        pending = None
+                    else:
+                        c_in = cur.shape[3]
+                        cur = _conv3x3_x3(cur, None, getattr(vgg, f"w_fwd{k}"), getattr(vgg, f"bias{k}"), c_out, True, "fp16x3")
+                    meta.append(("x3", k, c_in, len(saved)))
                     saved.append(cur)
-                    meta.append(("x3", k, c_in))
                 else:
                     m = op[1]
                     ks, st, pd, dl = _pair(m.kernel_size), _pair(m.stride if m.stride is not None else m.kernel_size), _pair(m.padding), _pair(m.dilation)
+                    fuse = (vgg.fuse_pool and ks == [2, 2] and st == [2, 2] and pd == [0, 0] and dl == [1, 1] and not m.ceil_mode
+                            and j > 0 and plan[j - 1][0] == "x3" and j + 1 < len(plan) and plan[j + 1][0] == "x3"
+                            and cur.shape[1] % 2 == 0 and cur.shape[2] % 2 == 0)
+                    if fuse:         # the pooled tensor is never materialised: pool + split forward, unpool + gate + split backward
+                        pending = _conv_split_pool(cur, None, "fp16x3")
+                        meta.append(("pool_fused", None, len(saved) - 1))     # its input: the previous layer's output
+                        cur = None
+                        continue
                     out, idx = torch.ops.aten.max_pool2d_with_indices(cur.permute(0, 3, 1, 2), ks, st, pd, dl, m.ceil_mode)
-                    meta.append(("pool", (ks, st, pd, dl, m.ceil_mode), tuple(cur.shape)))
+                    meta.append(("pool", (ks, st, pd, dl, m.ceil_mode), len(saved)))
                     saved.append(idx)
                     cur = out.permute(0, 2, 3, 1)
                     if not cur.is_contiguous():
@@ -1108,15 +1179,21 @@ class _VggStackFn(torch.autograd.Function):
         if not ctx.needs_input_grad[3] or r == 0:
             return None, None, None, None, None
         g = _f32c(g[:r])
-        # activations walk: saved[i] is the output of op i (its ReLU gate) or the indices of pool i; a pool's input is saved[i - 1]
+        gs = None                    # (hi, lo, shape): operand planes of the next data-gradient convolution (fused unpool + gate + split)
         for i in range(len(ctx.meta) - 1, -1, -1):
             m = ctx.meta[i]
             if m[0] == "x3":
-                g = _conv3x3_x3(g, saved[i][:r], getattr(vgg, f"w_bwd{m[1]}"), None, m[2], False, "bf16x3")
+                if gs is not None:
+                    g = _conv3x3_run(gs[0], gs[1], gs[2], getattr(vgg, f"w_bwd{m[1]}"), None, m[2], False, "bf16x3")
+                    gs = None
+                else:
+                    g = _conv3x3_x3(g, saved[m[3]][:r], getattr(vgg, f"w_bwd{m[1]}"), None, m[2], False, "bf16x3")
+            elif m[0] == "pool_fused":
+                gs = _conv_split_pool(saved[m[2]][:r], g, "bf16x3")
             elif m[0] == "pool":
                 ks, st, pd, dl, ceil = m[1]
-                inp = saved[i - 1][:r].permute(0, 3, 1, 2)
-                gi = torch.ops.aten.max_pool2d_with_indices_backward(g.permute(0, 3, 1, 2), inp, ks, st, pd, dl, ceil, saved[i][:r])
+                inp = saved[m[2] - 1][:r].permute(0, 3, 1, 2)          # a pool's input is the activation saved just before its indices
+                gi = torch.ops.aten.max_pool2d_with_indices_backward(g.permute(0, 3, 1, 2), inp, ks, st, pd, dl, ceil, saved[m[2]][:r])
                 g = _f32c(gi.permute(0, 2, 3, 1))
             else:
                 conv = m[1]
@@ -1125,7 +1202,7 @@ class _VggStackFn(torch.autograd.Function):
                 if r < ctx.x_shape[0]:
                     gx[r:].zero_()
                 with _on(g):
-                    check(lib().uorf_conv3x3_stem_dgrad(g.data_ptr(), saved[i].data_ptr(), conv.weight.data_ptr(), r, h, w, c, gx.data_ptr(),
+                    check(lib().uorf_conv3x3_stem_dgrad(g.data_ptr(), saved[m[2]].data_ptr(), conv.weight.data_ptr(), r, h, w, c, gx.data_ptr(),
                                                         _stream(g)), "uorf_conv3x3_stem_dgrad")
                 g = gx
         return None, None, None, g, None
