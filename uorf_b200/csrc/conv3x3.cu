@@ -225,15 +225,14 @@ __global__ void __launch_bounds__(256) conv_split_kernel(const float* __restrict
 template <bool F16>
 __global__ void __launch_bounds__(256) conv_split_pool_kernel(const float* __restrict__ x, unsigned int* __restrict__ hi, unsigned int* __restrict__ lo,
                                                               int n, int h, int w, int c) {
-  const int cp = c >> 1, wo = w >> 1, ho = h >> 1;
-  const long long total = (long long)n * ho * wo * cp;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % cp);
-    const long long win = i / cp;
-    const int ox = (int)(win % wo), oy = (int)((win / wo) % ho);
-    const long long img = win / ((long long)wo * ho);
-    const float2* src = reinterpret_cast<const float2*>(x + ((img * h + 2 * oy) * w + 2 * ox) * c) + ch;
-    const float2 a = __ldg(src), b = __ldg(src + cp), d = __ldg(src + (long long)w * cp), e = __ldg(src + (long long)w * cp + cp);
+  const unsigned cp = c >> 1, wo = w >> 1, ho = h >> 1;
+  const unsigned total = (unsigned)n * ho * wo * cp;                    // the launcher keeps n h w c below 2^31: 32-bit index arithmetic
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned win = i / cp, ch = i - win * cp;
+    const unsigned row = win / wo, ox = win - row * wo;
+    const unsigned img = row / ho, oy = row - img * ho;
+    const float2* src = reinterpret_cast<const float2*>(x) + ((size_t)(img * h + 2 * oy) * w + 2 * ox) * cp + ch;
+    const float2 a = __ldg(src), b = __ldg(src + cp), d = __ldg(src + (size_t)w * cp), e = __ldg(src + (size_t)w * cp + cp);
     uint32_t vh, vl;
     split2<F16>(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)), vh, vl);
     hi[i] = vh;
@@ -247,16 +246,15 @@ __global__ void __launch_bounds__(256) conv_split_pool_kernel(const float* __res
 template <bool F16>
 __global__ void __launch_bounds__(256) conv_split_unpool_kernel(const float* __restrict__ g, const float* __restrict__ x, unsigned int* __restrict__ hi,
                                                                 unsigned int* __restrict__ lo, int n, int h, int w, int c) {
-  const int cp = c >> 1, wo = w >> 1, ho = h >> 1;
-  const long long total = (long long)n * ho * wo * cp;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % cp);
-    const long long win = i / cp;
-    const int ox = (int)(win % wo), oy = (int)((win / wo) % ho);
-    const long long img = win / ((long long)wo * ho);
-    const long long base = ((img * h + 2 * oy) * w + 2 * ox) * (long long)cp + ch;      // float2 / word index of the window's first pixel
+  const unsigned cp = c >> 1, wo = w >> 1, ho = h >> 1;
+  const unsigned total = (unsigned)n * ho * wo * cp;                    // the launcher keeps n h w c below 2^31: 32-bit index arithmetic
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned win = i / cp, ch = i - win * cp;
+    const unsigned row = win / wo, ox = win - row * wo;
+    const unsigned img = row / ho, oy = row - img * ho;
+    const size_t base = ((size_t)(img * h + 2 * oy) * w + 2 * ox) * cp + ch;      // float2 / word index of the window's first pixel
     const float2* src = reinterpret_cast<const float2*>(x) + base;
-    const float2 v[4] = {__ldg(src), __ldg(src + cp), __ldg(src + (long long)w * cp), __ldg(src + (long long)w * cp + cp)};
+    const float2 v[4] = {__ldg(src), __ldg(src + cp), __ldg(src + (size_t)w * cp), __ldg(src + (size_t)w * cp + cp)};
     const float2 gv = __ldg(reinterpret_cast<const float2*>(g) + i);
     int ax = 0, ay = 0;
     float mx = v[0].x, my = v[0].y;
@@ -270,7 +268,7 @@ __global__ void __launch_bounds__(256) conv_split_unpool_kernel(const float* __r
     for (int q = 0; q < 4; ++q) {
       uint32_t vh, vl;
       split2<F16>(q == ax ? ox_ : 0.f, q == ay ? oy_ : 0.f, vh, vl);
-      const long long dst = base + (q & 1) * cp + (q >> 1) * (long long)w * cp;
+      const size_t dst = base + (q & 1) * cp + (q >> 1) * (size_t)w * cp;
       hi[dst] = vh;
       lo[dst] = vl;
     }
@@ -317,6 +315,7 @@ int launch_conv_split(const float* x, const float* gate, void* hi, void* lo, lon
 int launch_conv_split_pool(const float* x, const float* g, void* hi, void* lo, int n, int h, int w, int c, int f16, int num_sms, cudaStream_t stream) {
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 2);
   if (total <= 0) return UORF_OK;
+  if ((long long)n * h * w * c >= (1LL << 31)) return UORF_ERR_UNSUPPORTED;
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
   unsigned int* ph = static_cast<unsigned int*>(hi);
@@ -375,13 +374,14 @@ __global__ void __launch_bounds__(256) vgg_stem_fwd_kernel(const float* __restri
   for (int e = threadIdx.x; e < 27 * c_out; e += blockDim.x) s_w[e % 27][e / 27] = weight[e];     // [o][c][ky][kx] -> [c ky kx][o]
   __syncthreads();
   const int groups = c_out >> 2;
-  const long long npix = (long long)n * h * w;
+  const unsigned npix = (unsigned)n * h * w, hw = (unsigned)h * w;      // the launcher keeps n h w c_out below 2^31: 32-bit index arithmetic
   // grid-stride: the weight tile is staged once per block, not once per 16 pixels
-  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < npix * groups; gid += (long long)gridDim.x * blockDim.x) {
-    const long long pix = gid / groups;
+  for (unsigned gid = blockIdx.x * blockDim.x + threadIdx.x; gid < npix * groups; gid += gridDim.x * blockDim.x) {
+    const unsigned pix = gid / groups;
     const int o4 = (int)(gid % groups) * 4;
-    const int px = (int)(pix % w), py = (int)((pix / w) % h);
-    const float* src = x + (pix / ((long long)h * w)) * 3LL * h * w;
+    const unsigned img = pix / hw, rem = pix - img * hw;
+    const int py = (int)(rem / w), px = (int)(rem - (rem / w) * w);
+    const float* src = x + (size_t)img * 3 * hw;
     float a0 = bias[o4], a1 = bias[o4 + 1], a2 = bias[o4 + 2], a3 = bias[o4 + 3];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -390,11 +390,11 @@ __global__ void __launch_bounds__(256) vgg_stem_fwd_kernel(const float* __restri
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int yy = py + ky - 1, xx = px + kx - 1;
-          const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(src + ((long long)c * h + yy) * w + xx) : 0.f;
+          const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(src + (c * h + yy) * w + xx) : 0.f;
           const float4 wv = *reinterpret_cast<const float4*>(&s_w[(c * 3 + ky) * 3 + kx][o4]);
           a0 = fmaf(v, wv.x, a0); a1 = fmaf(v, wv.y, a1); a2 = fmaf(v, wv.z, a2); a3 = fmaf(v, wv.w, a3);
         }
-    *reinterpret_cast<float4*>(y + pix * c_out + o4) = make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
+    *reinterpret_cast<float4*>(y + (size_t)pix * c_out + o4) = make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
   }
 }
 
@@ -407,35 +407,39 @@ __global__ void __launch_bounds__(256) vgg_stem_dgrad_kernel(const float* __rest
   for (int e = threadIdx.x; e < 27 * 64; e += blockDim.x) s_w[e % 27][e / 27] = (e / 27) < c_out ? weight[e] : 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long long npix = (long long)n * h * w;
-  const int wpb = blockDim.x >> 5;
-  for (long long pix = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); pix < npix; pix += (long long)gridDim.x * wpb) {   // warp-uniform
-    const int px = (int)(pix % w), py = (int)((pix / w) % h);
-    const long long img = pix / ((long long)h * w);
+  const unsigned npix = (unsigned)n * h * w, hw = (unsigned)h * w;      // below 2^31 / c_out (launcher): 32-bit index arithmetic
+  const unsigned wpb = blockDim.x >> 5;
+  const bool second = lane + 32 < c_out;
+  for (unsigned pix = blockIdx.x * wpb + (threadIdx.x >> 5); pix < npix; pix += gridDim.x * wpb) {   // warp-uniform
+    const unsigned img = pix / hw, rem = pix - img * hw;
+    const int py = (int)(rem / w), px = (int)(rem - (rem / w) * w);
+    // all 36 loads of the pixel are issued before the first use (one round trip instead of eighteen)
+    float yv[9][2], gv[9][2];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = py + 1 - t / 3, xx = px + 1 - t % 3;          // the output pixel whose tap t read this input pixel
+      const bool in = yy >= 0 && yy < h && xx >= 0 && xx < w;
+      const size_t off = ((size_t)img * hw + (unsigned)(yy * w + xx)) * c_out + lane;
+      yv[t][0] = in && lane < c_out ? __ldg(y + off) : 0.f;
+      gv[t][0] = in && lane < c_out ? __ldg(g + off) : 0.f;
+      yv[t][1] = in && second ? __ldg(y + off + 32) : 0.f;
+      gv[t][1] = in && second ? __ldg(g + off + 32) : 0.f;
+    }
     float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+    for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int yy = py + 1 - ky, xx = px + 1 - kx;          // the output pixel whose tap (ky, kx) read this input pixel
-        if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
-        const long long off = ((img * h + yy) * w + xx) * c_out;
+      for (int half = 0; half < 2; ++half) {
+        const float v = yv[t][half] > 0.f ? gv[t][half] : 0.f;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int o = lane + 32 * half;
-          if (o < c_out) {
-            const float gv = __ldg(y + off + o) > 0.f ? __ldg(g + off + o) : 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) acc[c] = fmaf(gv, s_w[(c * 3 + ky) * 3 + kx][o], acc[c]);
-          }
-        }
+        for (int c = 0; c < 3; ++c) acc[c] = fmaf(v, s_w[c * 9 + t][lane + 32 * half], acc[c]);
       }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float v = acc[c];
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-      if (lane == 0) gx[((img * 3 + c) * h + py) * w + px] = v;
+      if (lane == 0) gx[((size_t)img * 3 + c) * hw + rem] = v;
     }
   }
 }
@@ -444,6 +448,7 @@ int launch_vgg_stem_fwd(const float* x, const float* weight, const float* bias, 
   if (c_out % 4 != 0 || c_out > 64 || c_out < 4) return UORF_ERR_UNSUPPORTED;
   const long long threads = (long long)n * h * w * (c_out / 4);
   if (threads <= 0) return UORF_OK;
+  if ((long long)n * h * w * c_out >= (1LL << 31)) return UORF_ERR_UNSUPPORTED;
   long long blocks = (threads + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   vgg_stem_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, weight, bias, n, h, w, c_out, y);
@@ -454,6 +459,7 @@ int launch_vgg_stem_dgrad(const float* g, const float* y, const float* weight, i
   if (c_out > 64 || c_out < 1) return UORF_ERR_UNSUPPORTED;
   const long long npix = (long long)n * h * w;
   if (npix <= 0) return UORF_OK;
+  if (npix * c_out >= (1LL << 31)) return UORF_ERR_UNSUPPORTED;
   long long blocks = (npix + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   vgg_stem_dgrad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, y, weight, n, h, w, c_out, gx);

@@ -29,6 +29,26 @@ constexpr int kBMaxHid = 128;
 __host__ __device__ inline int sab_saved_stride(int K, int C) { return 3 * K * C + ((K + 3) & ~3); }
 
 // per-slot gradient region (floats)
+// The weight gradients of the per-slot matrices are sums of outer products a (x) b over iterations and slots.  The per-slot kernel
+// only STORES the factor vectors (12 C + 2 hidden floats per iteration and slot); the reduce kernel forms every weight element as
+// a short sum of products.  (Accumulating the outer products into a per-slot global region cost five dependent read-modify-write
+// sweeps of up to 12,288 elements per launch - two thirds of the per-slot kernel's time.)
+struct SabVec {
+  int q_a, q_b;        // d q [C], LN_q(slot) [C]                   -> to_q weight
+  int ds, m;           // d slot_out [C], relu hidden [hidden]      -> residual MLP second weight
+  int dm, ln;          // d hidden (gated) [hidden], LN_res(h') [C] -> residual MLP first weight
+  int dg;              // d gates: input part [3C], hidden part [3C]
+  int upd, h;          // GRU input [C], GRU state [C]              -> gru_w_ih = dg[0:3C] (x) upd, gru_w_hh = dg[3C:6C] (x) h
+  int total;
+};
+__host__ __device__ inline SabVec sab_vec(int C, int Hd) {
+  SabVec v;
+  v.q_a = 0; v.q_b = C; v.ds = 2 * C; v.m = 3 * C; v.dm = 3 * C + Hd; v.ln = 3 * C + 2 * Hd; v.dg = 4 * C + 2 * Hd;
+  v.upd = 10 * C + 2 * Hd; v.h = 11 * C + 2 * Hd; v.total = 12 * C + 2 * Hd;
+  return v;
+}
+constexpr int kBMaxIters = 8;
+
 struct SlotRegion {
   int wih, whh, bih, bhh, lnr_w, lnr_b, w1, b1, w2, b2, lnq_w, lnq_b, wq, total;
 };
@@ -68,6 +88,7 @@ struct SabParams {
   float* dq_part;   // [nblk][K][C]
   float* slot_reg;  // [K][region]
   float* tok_part;  // [nblk][2*C*C + 2*C]   d to_k | d to_v | d norm_feat w | b
+  float* vec_store; // [iters][K][12 C + 2 hidden]: the factor pairs of every weight-gradient outer product (see SabVec)
   float* grad_feat; // [ntok][C]
   int nblk;
 };
@@ -91,10 +112,6 @@ __device__ __forceinline__ void b_matvec_t(const float* W, const float* x, float
     for (int o = 0; o < n_out; ++o) acc = fmaf(W[(long long)o * n_in + c], x[o], acc);
     y[c] = acc;
   }
-}
-// G[o][c] += a[o] * b[c]
-__device__ __forceinline__ void b_outer_acc(float* G, const float* a, const float* b, int n_out, int n_in) {
-  for (int e = threadIdx.x; e < n_out * n_in; e += blockDim.x) G[e] += a[e / n_in] * b[e % n_in];
 }
 __device__ __forceinline__ void b_vec_acc(float* G, const float* a, int n) {
   for (int e = threadIdx.x; e < n; e += blockDim.x) G[e] += a[e];
@@ -147,6 +164,7 @@ __global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabPar
   const int C = p.C, K = p.K, Hd = p.hidden, k = blockIdx.x;
   const SlotRegion R = slot_region(C, Hd);
   float* G = p.slot_reg + (long long)k * R.total;
+  const SabVec VO = sab_vec(C, Hd);
   const bool bg = k == 0;
   // The kernel is a chain of ~10 dependent matvec phases over the slot's weights: with `staged` they are pulled into shared
   // memory once, by TMA bulk copies that run while the first phases read their inputs (as in the forward update kernel).
@@ -195,7 +213,10 @@ __global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabPar
     __syncthreads();
     b_ln_fwd(s_b, bg ? p.w.to_q_bg_ln_w : p.w.to_q_ln_w, bg ? p.w.to_q_bg_ln_b : p.w.to_q_ln_b, s_xh, s_c, s_stat, C);   // s_c = LN_q(slot)
     __syncthreads();
-    b_outer_acc(G + R.wq, s_a, s_c, C, C);                                   // d to_q.1.weight
+    {                                                                        // factors of d to_q.1.weight
+      float* V = p.vec_store + ((long long)it_q * K + k) * VO.total;
+      for (int c = threadIdx.x; c < C; c += blockDim.x) { V[VO.q_a + c] = s_a[c]; V[VO.q_b + c] = s_c[c]; }
+    }
     if (!landed) { mbar_wait(&s_bar, 0); landed = true; }
     b_matvec_t(w_q, s_a, s_d, C, C);                                         // s_d = d LN_q output
     __syncthreads();
@@ -238,13 +259,15 @@ __global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabPar
     for (int j = threadIdx.x; j < Hd; j += blockDim.x) s_m[j] = fmaxf(s_m[j], 0.f);
     __syncthreads();
     // ---- residual MLP backward: slot_out = h' + W2 relu(W1 LN(h') + b1) + b2 ----
-    b_outer_acc(G + R.w2, s_ds, s_m, C, Hd);
+    float* V = p.vec_store + ((long long)it_a * K + k) * VO.total;           // factors of this iteration's weight gradients
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { V[VO.ds + c] = s_ds[c]; V[VO.ln + c] = s_ln[c]; V[VO.upd + c] = s_b[c]; V[VO.h + c] = s_a[c]; }
+    for (int j = threadIdx.x; j < Hd; j += blockDim.x) V[VO.m + j] = s_m[j];
     b_vec_acc(G + R.b2, s_ds, C);
     b_matvec_t(w_2, s_ds, s_dm, C, Hd);                                      // d relu output
     __syncthreads();
     for (int j = threadIdx.x; j < Hd; j += blockDim.x) s_dm[j] = s_m[j] > 0.f ? s_dm[j] : 0.f;
     __syncthreads();
-    b_outer_acc(G + R.w1, s_dm, s_ln, Hd, C);
+    for (int j = threadIdx.x; j < Hd; j += blockDim.x) V[VO.dm + j] = s_dm[j];
     b_vec_acc(G + R.b1, s_dm, Hd);
     float* s_dln = s_g;   // reuse s_g[0..C): the gate pre-activations are no longer needed (r, z, n are in s_c/s_d/s_e)
     // keep h_n = W_hn h + b_hn, needed for d r: copy before s_g is overwritten
@@ -275,9 +298,8 @@ __global__ void __launch_bounds__(kBSlotThreads) sa_bwd_slot_kernel(const SabPar
       s_f[c] = dh2 * z;                                // direct path to h
     }
     __syncthreads();
-    b_outer_acc(G + R.wih, s_dg, s_b, 3 * C, C);
+    for (int j = threadIdx.x; j < 6 * C; j += blockDim.x) V[VO.dg + j] = s_dg[j];
     b_vec_acc(G + R.bih, s_dg, 3 * C);
-    b_outer_acc(G + R.whh, s_dg + 3 * C, s_a, 3 * C, C);
     b_vec_acc(G + R.bhh, s_dg + 3 * C, 3 * C);
     b_matvec_t(w_ih, s_dg, s_xh, 3 * C, C);             // s_xh = d upd
     b_matvec_t(w_hh, s_dg + 3 * C, s_hn, 3 * C, C);     // s_hn = W_hh^T d gh
@@ -454,14 +476,39 @@ __global__ void sa_bwd_reduce_kernel(const SabParams p) {
     return a;
   };
   auto bg_val = [&](int off) { return p.slot_reg[off]; };
-  for (int e = gid; e < 3 * C * C; e += gn) { p.g.gru_w_ih[e] = fg_sum(R.wih + e); p.g.gru_w_hh[e] = fg_sum(R.whh + e);
-                                                p.g.gru_bg_w_ih[e] = bg_val(R.wih + e); p.g.gru_bg_w_hh[e] = bg_val(R.whh + e); }
+  // weight element (o, c) of slot k: sum over the iterations (last first, the order the backward runs) of a[o] * b[c]
+  const SabVec VO = sab_vec(C, Hd);
+  auto outer = [&](int off_a, int off_b, int o, int c, int k) {
+    float acc = 0.f;
+    for (int it = p.iters - 1; it >= 0; --it) {
+      const float* V = p.vec_store + ((long long)it * K + k) * VO.total;
+      acc = fmaf(V[off_a + o], V[off_b + c], acc);
+    }
+    return acc;
+  };
+  auto outer_fg = [&](int off_a, int off_b, int o, int c) {
+    float a = 0.f;
+    for (int k = 1; k < K; ++k) a += outer(off_a, off_b, o, c, k);
+    return a;
+  };
+  for (int e = gid; e < 3 * C * C; e += gn) {
+    const int o = e / C, c = e - o * C;
+    p.g.gru_w_ih[e] = outer_fg(VO.dg, VO.upd, o, c); p.g.gru_w_hh[e] = outer_fg(VO.dg + 3 * C, VO.h, o, c);
+    p.g.gru_bg_w_ih[e] = outer(VO.dg, VO.upd, o, c, 0); p.g.gru_bg_w_hh[e] = outer(VO.dg + 3 * C, VO.h, o, c, 0);
+  }
   for (int e = gid; e < 3 * C; e += gn) { p.g.gru_b_ih[e] = fg_sum(R.bih + e); p.g.gru_b_hh[e] = fg_sum(R.bhh + e);
                                             p.g.gru_bg_b_ih[e] = bg_val(R.bih + e); p.g.gru_bg_b_hh[e] = bg_val(R.bhh + e); }
-  for (int e = gid; e < Hd * C; e += gn) { p.g.to_res_w1[e] = fg_sum(R.w1 + e); p.g.to_res_w2[e] = fg_sum(R.w2 + e);
-                                             p.g.to_res_bg_w1[e] = bg_val(R.w1 + e); p.g.to_res_bg_w2[e] = bg_val(R.w2 + e); }
+  for (int e = gid; e < Hd * C; e += gn) {
+    const int j = e / C, c = e - j * C;          // first weight [hidden][C]
+    p.g.to_res_w1[e] = outer_fg(VO.dm, VO.ln, j, c); p.g.to_res_bg_w1[e] = outer(VO.dm, VO.ln, j, c, 0);
+    const int o = e / Hd, jj = e - o * Hd;       // second weight [C][hidden]
+    p.g.to_res_w2[e] = outer_fg(VO.ds, VO.m, o, jj); p.g.to_res_bg_w2[e] = outer(VO.ds, VO.m, o, jj, 0);
+  }
   for (int e = gid; e < Hd; e += gn) { p.g.to_res_b1[e] = fg_sum(R.b1 + e); p.g.to_res_bg_b1[e] = bg_val(R.b1 + e); }
-  for (int e = gid; e < C * C; e += gn) { p.g.to_q_w[e] = fg_sum(R.wq + e); p.g.to_q_bg_w[e] = bg_val(R.wq + e); }
+  for (int e = gid; e < C * C; e += gn) {
+    const int o = e / C, c = e - o * C;
+    p.g.to_q_w[e] = outer_fg(VO.q_a, VO.q_b, o, c); p.g.to_q_bg_w[e] = outer(VO.q_a, VO.q_b, o, c, 0);
+  }
   for (int e = gid; e < C; e += gn) {
     p.g.to_res_b2[e] = fg_sum(R.b2 + e); p.g.to_res_bg_b2[e] = bg_val(R.b2 + e);
     p.g.to_res_ln_w[e] = fg_sum(R.lnr_w + e); p.g.to_res_ln_b[e] = fg_sum(R.lnr_b + e);
@@ -506,14 +553,15 @@ __global__ void sa_bwd_reduce_kernel(const SabParams p) {
 size_t slot_attention_bwd_ws_floats(int ntok, int C, int K, int hidden) {
   const size_t nblk = (ntok + kBTok - 1) / kBTok;
   const SlotRegion R = slot_region(C, hidden);
-  return (size_t)2 * K * C + (size_t)2 * ntok * C + nblk * K * C + (size_t)K * R.total + nblk * (2 * C * C + 2 * C) + 64;
+  return (size_t)2 * K * C + (size_t)2 * ntok * C + nblk * K * C + (size_t)K * R.total + nblk * (2 * C * C + 2 * C) +
+         (size_t)kBMaxIters * K * sab_vec(C, hidden).total + 64;
 }
 
 int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_slot_attention_grads* g, const float* feat, long long feat_ts,
                               long long feat_cs, const float* noise_fg, const float* noise_bg, int ntok, int C, int K, int hidden, int iters,
                               float eps, const float* fwd_workspace, const float* grad_slots, float* workspace, float* grad_feat,
                               cudaStream_t stream) {
-  if (C > kBMaxC || K > kBMaxK || hidden > kBMaxHid || K < 2 || iters > 8 || iters < 1) return UORF_ERR_UNSUPPORTED;
+  if (C > kBMaxC || K > kBMaxK || hidden > kBMaxHid || K < 2 || iters > kBMaxIters || iters < 1) return UORF_ERR_UNSUPPORTED;
   SabParams p;
   p.w = *w; p.g = *g;
   p.feat = feat; p.feat_ts = feat_ts; p.feat_cs = feat_cs;
@@ -534,7 +582,8 @@ int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_s
   p.dV = ws; ws += (size_t)ntok * C;
   p.dq_part = ws; ws += (size_t)nblk * K * C;
   p.slot_reg = ws; ws += (size_t)K * R.total;
-  p.tok_part = ws;
+  p.tok_part = ws; ws += (size_t)nblk * (2 * C * C + 2 * C);
+  p.vec_store = ws;
   p.grad_feat = grad_feat;
   // weight staging of the per-slot kernel (TMA bulk copies: 16-byte aligned tensors, sizes multiples of 16 bytes)
   const size_t stage_bytes = (size_t)(C * C + 2 * 3 * C * C + 2 * hidden * C) * sizeof(float);
