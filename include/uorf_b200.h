@@ -314,6 +314,11 @@ int uorf_conv3x3_stem(const float* x, const float* weight, const float* bias, in
 int uorf_conv3x3_stem_dgrad(const float* grad_y, const float* y, const float* weight, int32_t n, int32_t h, int32_t w, int32_t c_out,
                             float* grad_x, void* stream);
 
+/* Inverse of `batch` row-major dim x dim matrices (dim 3 or 4), device to device, one launch: the `.inverse()` of the scene pose in
+ * the drivers' set_input (models/uorf_nogan_model.py:117-126, uorf_eval_model.py:98-107) when the pose already lives on the device.
+ * Gauss-Jordan with partial pivoting in fp32; a singular matrix gives inf / nan entries as the library does. */
+int uorf_invert_small(const float* src, float* dst, int32_t batch, int32_t dim, void* stream);
+
 /* -----------------------------------------------------------------------------------------------
  * Adam update of many small fp32 tensors in one launch - the `optimizer.step()` of the training drivers
  * (reference models/uorf_nogan_model.py:59-61 torch.optim.Adam over encoder + slot attention + decoder, :229-245 the step).

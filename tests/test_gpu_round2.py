@@ -647,3 +647,24 @@ def test_adam_kernel_matches_torch_adam(capturable, weight_decay):
     # the state dict is torch's: it loads into a plain torch.optim.Adam
     o_plain = torch.optim.Adam(ref, lr=mk_lr(), capturable=capturable, fused=True, weight_decay=weight_decay)
     o_plain.load_state_dict(o_ours.state_dict())
+
+
+@pytest.mark.gpu
+def test_invert_pose_matches_torch_inverse():
+    """uorf_invert_small (one launch, Gauss-Jordan with partial pivoting) against torch's LU-based `.inverse()` on camera poses,
+    azimuth rotations and badly scaled / permuted matrices"""
+    from uorf_b200.modules import invert_pose
+    d = torch.device("cuda:0")
+    g = load_golden("train_driver_coarse")
+    poses = g["cam2world"].to(d).float()
+    mats4 = [poses, torch.randn(64, 4, 4, device=d), torch.eye(4, device=d)[[2, 0, 3, 1]][None] * torch.tensor([1e-3, 5.0, 200.0, 1.0], device=d)]
+    mats3 = [g["azi_rot"].to(d).float(), torch.randn(64, 3, 3, device=d)]
+    for m in mats4 + mats3:
+        got, want = invert_pose(m), m.double().inverse()
+        n = m.shape[-1]
+        eye = torch.eye(n, device=d, dtype=torch.float64)
+        res_got = (got.double() @ m.double() - eye).abs().amax(dim=(-2, -1))
+        res_ref = (m.inverse().double() @ m.double() - eye).abs().amax(dim=(-2, -1))
+        assert torch.all(res_got <= 4 * res_ref + 1e-6), (res_got.max().item(), res_ref.max().item())
+        assert ((got.double() - want).abs().amax(dim=(-2, -1)) <= 1e-5 * want.abs().amax(dim=(-2, -1)) * (1 + res_ref * 1e5)).all()
+    assert invert_pose(poses[0:1]).shape == (1, 4, 4)

@@ -26,6 +26,7 @@ int launch_vgg_stem_fwd(const float* x, const float* weight, const float* bias, 
 int launch_vgg_stem_dgrad(const float* g, const float* y, const float* weight, int n, int h, int w, int c_out, float* gx, cudaStream_t stream);
 int launch_encoder_weight_prep(const uorf_encoder_prep_layer* layers, int n_layers, cudaStream_t stream);
 int launch_conv_split_pool(const float* x, const float* g, void* hi, void* lo, int n, int h, int w, int c, int f16, int num_sms, cudaStream_t stream);
+int launch_invert_small(const float* src, float* dst, int batch, int dim, cudaStream_t stream);
 int launch_adam_step(const uorf_adam_chunk* chunks, int n_chunks, const float* lr_dev, float lr_host, float beta1, float beta2, float eps,
                      float weight_decay, cudaStream_t stream);
 int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* weight_t, const float* bias,
@@ -208,6 +209,15 @@ int uorf_conv3x3_stem_dgrad(const float* grad_y, const float* y, const float* we
   if (n < 0 || h < 1 || w < 1 || c_out < 1 || c_out > 64) return fail(UORF_ERR_ARG, "uorf_conv3x3_stem_dgrad: bad sizes (c_out <= 64)%s");
   return check_launch(uorf::launch_vgg_stem_dgrad(grad_y, y, weight, n, h, w, c_out, grad_x, static_cast<cudaStream_t>(stream)),
                       "uorf_conv3x3_stem_dgrad");
+}
+
+int uorf_invert_small(const float* src, float* dst, int32_t batch, int32_t dim, void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_invert_small");
+  if (!c) return UORF_ERR_DEVICE;
+  if (batch < 0 || (batch > 0 && (!src || !dst))) return fail(UORF_ERR_ARG, "uorf_invert_small: null pointer%s");
+  if (dim != 3 && dim != 4) return fail(UORF_ERR_ARG, "uorf_invert_small: dim must be 3 or 4%s");
+  return check_launch(uorf::launch_invert_small(src, dst, batch, dim, static_cast<cudaStream_t>(stream)), "uorf_invert_small");
 }
 
 int uorf_adam_step(const uorf_adam_chunk* chunks, int32_t n_chunks, const float* lr_dev, float lr_host, float beta1, float beta2, float eps,

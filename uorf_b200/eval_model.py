@@ -22,7 +22,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .modules import Decoder, Encoder, Projection, SlotAttention, raw2outputs
+from .modules import Decoder, Encoder, Projection, SlotAttention, invert_pose, raw2outputs
 
 
 def default_eval_options(**over) -> argparse.Namespace:
@@ -130,7 +130,7 @@ class uorfEvalModel:
         if not self.opt.fixed_locality:
             self.cam2world_azi = input["azi_rot"].to(self.device, non_blocking=True)
         if src.is_cuda:
-            self.nss2cam0 = src[0:1].inverse()
+            self.nss2cam0 = invert_pose(src[0:1])
         else:
             # staged through PINNED memory (a small ring, so that a caller may keep several steps in flight): an H2D copy from
             # pageable memory makes the driver wait for the stream's earlier work before it returns, which serialises the host

@@ -378,6 +378,20 @@ def _encoder_backward(enc, a, g_out, x_needs_grad):
     return (gx[:, :a["img"].shape[0]] if x_needs_grad else None), grads
 
 
+def invert_pose(m: torch.Tensor) -> torch.Tensor:
+    """`m.inverse()` for the drivers' pose matrices (... x 3 x 3 or ... x 4 x 4): one launch of uorf_invert_small for fp32 CUDA
+    tensors (torch's route is an LU factorisation + triangular solves: 13 launches for 16 numbers), torch's own inverse otherwise"""
+    if not (m.is_cuda and m.dtype == torch.float32 and m.dim() >= 2 and m.shape[-1] == m.shape[-2] and m.shape[-1] in (3, 4)
+            and not m.requires_grad):
+        return m.inverse()
+    src = m.contiguous()
+    dst = torch.empty_like(src)
+    with _on(src):
+        check(lib().uorf_invert_small(src.data_ptr(), dst.data_ptr(), src.numel() // (src.shape[-1] ** 2), src.shape[-1], _stream(src)),
+              "uorf_invert_small")
+    return dst
+
+
 # ======================================================================================================
 # sin_emb (standalone; the decoder kernel computes it on chip)
 # ======================================================================================================

@@ -25,7 +25,7 @@ from torch.optim.lr_scheduler import LambdaLR
 
 from . import optim as _optim
 from .eval_model import init_weights_like_reference
-from .modules import Decoder, Encoder, PerceptualVGG, Projection, SlotAttention, raw2outputs
+from .modules import Decoder, Encoder, PerceptualVGG, Projection, SlotAttention, invert_pose, raw2outputs
 
 
 def default_train_options(**over) -> argparse.Namespace:
@@ -157,7 +157,7 @@ class uorfNoGanModel:
         src = c2w if self.opt.fixed_locality else input["azi_rot"]
         if not self.opt.fixed_locality:
             self.cam2world_azi = input["azi_rot"].to(self.device, non_blocking=True)
-        self.nss2cam0 = src[0:1].inverse() if src.is_cuda else src[0:1].inverse().to(self.device, non_blocking=True)
+        self.nss2cam0 = invert_pose(src[0:1]) if src.is_cuda else src[0:1].inverse().to(self.device, non_blocking=True)
 
     def forward(self, epoch=0):
         opt = self.opt
