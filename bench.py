@@ -786,7 +786,17 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_b200(args)
+        try:
+            run_b200(args)
+        except Exception:
+            # a kernel's bounded wait records its site in pinned host memory before it traps (csrc/common.cuh mbar_wait*): readable
+            # after the launch failure that follows
+            try:
+                from uorf_b200._lib import lib
+                print(f"[bench] uorf_debug_flag (failing wait site, 0 = none) = {lib().uorf_debug_flag()}", file=sys.stderr, flush=True)
+            except Exception:
+                pass
+            raise
 
 
 if __name__ == "__main__":

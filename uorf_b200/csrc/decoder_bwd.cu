@@ -324,7 +324,13 @@ __device__ __forceinline__ void load_d32(uint32_t taddr, float (&v)[32]) {
 
 __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBwdParams p) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_d, bar_b;   // bar_b: dZ tile of a backward step fenced for the dW MMAs
+  // bar_b[2]: dZ tile of a backward step fenced for the dW MMAs, ALTERNATING between two barriers (step j of a slot uses j & 1).
+  // The epilogue's arrival for step j + 1 only needs the commit of step j, which the issuer makes BEFORE it waits on bar_b for step
+  // j: with one barrier a stalled issuer could find two phases completed (parity back where it started) and wait for a third that
+  // depends on itself - seen as a bounded-wait trap about once in 2,000 launches.  Step j + 2 needs the commit of step j + 1, which
+  // follows that wait in program order, and between the last step of a slot and the first of the next (both barrier 0) lie the
+  // seven hand-offs of the forward recompute: with two barriers no phase can be skipped.
+  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_d, bar_b[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_red[4][64];
 
@@ -344,7 +350,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
     mbar_init(&bar_w, 1);
     mbar_init(&bar_a, UORF_BWD_WARP_ARRIVE ? kBwdEpiWarps : kTileM128 * kBwdNQ);
     mbar_init(&bar_d, 1);
-    mbar_init(&bar_b, UORF_BWD_WARP_ARRIVE ? kBwdEpiWarps : kTileM128 * kBwdNQ);
+    mbar_init(&bar_b[0], UORF_BWD_WARP_ARRIVE ? kBwdEpiWarps : kTileM128 * kBwdNQ);
+    mbar_init(&bar_b[1], UORF_BWD_WARP_ARRIVE ? kBwdEpiWarps : kTileM128 * kBwdNQ);
     fence_mbar_init();
   }
   if (warp == kBwdEpiWarps) {
@@ -365,7 +372,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
   }
 
   const float gscale = grad_scale(__ldg(p.draw_amax));
-  uint32_t n_a = 0, n_d = 0, n_b = 0;   // completions consumed so far (parity = count & 1); they run on across the two phases
+  uint32_t n_a = 0, n_d = 0;   // completions consumed so far (parity = count & 1); they run on across the two phases
+  uint32_t n_b = 0;            // issuer: slots finished (bar_b[1] completes three phases per slot)
   for (int phase = 0; phase < 2; ++phase) {
     const int nslots = phase == 0 ? 1 : K - 1;
     if (warp == kBwdEpiWarps && lane == 0) {
@@ -423,11 +431,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
         }
       };
       // dX = dZ[buf] . W[tile wi] : A K-major (K = out features), B = MN-major view of the weight tile
-      const uint32_t bar_b_addr = smem_u32(&bar_b);
-      auto wait_b = [&]() {   // the dZ tile of this step is visible to the tensor core (only with UORF_BWD_TS_BWD)
+      const uint32_t bar_b_addr = smem_u32(&bar_b[0]);
+      // the dZ tile of backward step J (0..6 within the slot) is visible to the tensor core (only with UORF_BWD_TS_BWD).  Step J uses
+      // barrier J & 1: barrier 0 completes four phases per slot (parity known at compile time), barrier 1 three (parity follows the
+      // slot count) - static addresses, so the issuer's code stays on the uniform datapath
+      auto wait_b = [&](auto J) {
         if (UORF_BWD_TS_BWD) {
-          mbar_wait_lean(bar_b_addr, n_b & 1, p.err_flag, 230);
-          ++n_b;
+          constexpr int j = decltype(J)::value;
+          const uint32_t par = (j & 1) ? (((j >> 1) + n_b) & 1u) : (uint32_t)((j >> 1) & 1);
+          mbar_wait_lean(bar_b_addr + 8 * (j & 1), par, p.err_flag, 230 + j);
           tc_fence_after();
         }
       };
@@ -471,13 +483,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
           wait_a(205); fwd(I_(5), I_(6), I_(4), id_fwd64, true); tc_commit_elect(&bar_d);
           wait_a(206); fwd(I_(6), I_(7), I_(4), id_fwd_head, true); tc_commit_elect(&bar_d);
           // ---- backward ----   (dZ buffers alternate: head -> 0, layer 5 -> 1, 4 -> 0, 3 -> 1, 2 -> 0, 1 -> 1, 0 -> 0)
-          wait_a(207); dx(I_(0), I_(7), I_(2)); tc_commit_elect(&bar_d); wait_b(); dw(I_(7), I_(0), I_(6), id_dw64); dwb(I_(4), I_(0));
-          wait_a(208); dx(I_(1), I_(6), I_(4)); tc_commit_elect(&bar_d); wait_b(); dw(I_(6), I_(1), I_(5), id_dw64); dwb(I_(3), I_(1));
-          wait_a(209); dx(I_(0), I_(5), I_(4)); tc_commit_elect(&bar_d); wait_b(); dw(I_(5), I_(0), I_(4), id_dw64); dwb(I_(2), I_(0));
-          wait_a(210); dx(I_(1), I_(4), I_(4)); tc_commit_elect(&bar_d); wait_b(); dw(I_(4), I_(1), I_(3), id_dw64); dw(I_(3), I_(1), I_(0), id_dw48);
-          wait_a(211); dx(I_(0), I_(2), I_(4)); tc_commit_elect(&bar_d); wait_b(); dw(I_(2), I_(0), I_(2), id_dw64); dwb(I_(1), I_(0));
-          wait_a(212); dx(I_(1), I_(1), I_(4)); tc_commit_elect(&bar_d); wait_b(); dw(I_(1), I_(1), I_(1), id_dw64); dwb(I_(0), I_(1));
-          wait_a(213); wait_b(); dw(I_(0), I_(0), I_(0), id_dw48); tc_commit_elect(&bar_d);   // all tiles free for the next slot once this lands
+          wait_a(207); dx(I_(0), I_(7), I_(2)); tc_commit_elect(&bar_d); wait_b(I_(0)); dw(I_(7), I_(0), I_(6), id_dw64); dwb(I_(4), I_(0));
+          wait_a(208); dx(I_(1), I_(6), I_(4)); tc_commit_elect(&bar_d); wait_b(I_(1)); dw(I_(6), I_(1), I_(5), id_dw64); dwb(I_(3), I_(1));
+          wait_a(209); dx(I_(0), I_(5), I_(4)); tc_commit_elect(&bar_d); wait_b(I_(2)); dw(I_(5), I_(0), I_(4), id_dw64); dwb(I_(2), I_(0));
+          wait_a(210); dx(I_(1), I_(4), I_(4)); tc_commit_elect(&bar_d); wait_b(I_(3)); dw(I_(4), I_(1), I_(3), id_dw64); dw(I_(3), I_(1), I_(0), id_dw48);
+          wait_a(211); dx(I_(0), I_(2), I_(4)); tc_commit_elect(&bar_d); wait_b(I_(4)); dw(I_(2), I_(0), I_(2), id_dw64); dwb(I_(1), I_(0));
+          wait_a(212); dx(I_(1), I_(1), I_(4)); tc_commit_elect(&bar_d); wait_b(I_(5)); dw(I_(1), I_(1), I_(1), id_dw64); dwb(I_(0), I_(1));
+          wait_a(213); wait_b(I_(6)); dw(I_(0), I_(0), I_(0), id_dw48); tc_commit_elect(&bar_d);   // all tiles free for the next slot once this lands
+          ++n_b;                                                              // slots done (parity of barrier 1)
         }
       }
       __syncwarp();
@@ -529,14 +542,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
 #endif
         TLB_EPI(0x40);
       };
-      const uint32_t bar_b_addr = opaque(smem_u32(&bar_b));
-      auto publish_tile = [&]() {  // second hand-off of a backward step: the shared-memory dZ tile is visible to the tensor core
+      const uint32_t bar_b_addr = opaque(smem_u32(&bar_b[0]));
+      auto publish_tile = [&](int j) {  // second hand-off of backward step j (0..6): the shared-memory dZ tile is visible to the tensor core
         fence_proxy_async_smem();
 #if UORF_BWD_WARP_ARRIVE
         __syncwarp();
-        if (lane == 0) mbar_arrive_addr(bar_b_addr);
+        if (lane == 0) mbar_arrive_addr(bar_b_addr + 8 * (j & 1));
 #else
-        mbar_arrive_addr(bar_b_addr);
+        mbar_arrive_addr(bar_b_addr + 8 * (j & 1));
 #endif
       };
       for (int it = 0;; ++it) {
@@ -681,7 +694,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
               if (half < 2) store_half16<true>(s_dz, t, half, dzh);   // the second half writes the zero padding of the head's dZ tile
             }
           }
-          if (UORF_BWD_TS_BWD) { publish_tmem(); publish_tile(); } else publish();
+          if (UORF_BWD_TS_BWD) { publish_tmem(); publish_tile(0); } else publish();
           // ---- layers 5..0 ----
 #pragma unroll 1
           for (int l = 5; l >= 0; --l) {
@@ -693,7 +706,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) decoder_bwd_kernel(const DecBw
             if (UORF_BWD_TS_BWD) {
               gate_store_cols_tmem<kBwdCols>(xg, s_dz + ((l & 1) ? 16384 : 0), t, chunk0, g, tb + kBColA + c0 / 2);
               publish_tmem();
-              publish_tile();
+              publish_tile(6 - l);
             } else {
               gate_store_cols<kBwdCols>(xg, s_dz + ((l & 1) ? 16384 : 0), t, chunk0, g);   // dZ_l = dX_{l+1} * [X_{l+1} > 0]
               publish();
