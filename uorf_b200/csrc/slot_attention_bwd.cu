@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kBThreads) sa_bwd_feat_kernel(const SabParams 
 }
 
 // ---- fixed-order reductions into the parameter-gradient tensors ----------------------------------------------
-__global__ void sa_bwd_reduce_kernel(const SabParams p) {
+__global__ void sa_bwd_reduce_kernel(const SabParams p, int staged) {
   const int C = p.C, K = p.K, Hd = p.hidden;
   const SlotRegion R = slot_region(C, Hd);
   const int gid = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
@@ -478,10 +478,20 @@ __global__ void sa_bwd_reduce_kernel(const SabParams p) {
   auto bg_val = [&](int off) { return p.slot_reg[off]; };
   // weight element (o, c) of slot k: sum over the iterations (last first, the order the backward runs) of a[o] * b[c]
   const SabVec VO = sab_vec(C, Hd);
+  // the factor vectors (iters x K x (12 C + 2 hidden) floats: 96 KB at the reference sizes) are read ~40 times per weight element:
+  // staged in shared memory when they fit (staged != 0)
+  extern __shared__ __align__(16) float s_vec[];
+  const float* vec = p.vec_store;
+  if (staged) {
+    const int n4 = p.iters * K * VO.total / 4;              // C, hidden multiples of 4 (checked by the launcher)
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) reinterpret_cast<float4*>(s_vec)[i] = reinterpret_cast<const float4*>(p.vec_store)[i];
+    __syncthreads();
+    vec = s_vec;
+  }
   auto outer = [&](int off_a, int off_b, int o, int c, int k) {
     float acc = 0.f;
     for (int it = p.iters - 1; it >= 0; --it) {
-      const float* V = p.vec_store + ((long long)it * K + k) * VO.total;
+      const float* V = vec + (it * K + k) * VO.total;
       acc = fmaf(V[off_a + o], V[off_b + c], acc);
     }
     return acc;
@@ -603,7 +613,10 @@ int launch_slot_attention_bwd(const uorf_slot_attention_weights* w, const uorf_s
   }
   sa_bwd_slot_kernel<<<K, kBSlotThreads, dyn, stream>>>(p, 1, 0, 0, 0, 0, staged);   // query path of iteration 0 -> d slot_0
   sa_bwd_feat_kernel<<<nblk, kBThreads, 0, stream>>>(p);
-  sa_bwd_reduce_kernel<<<148, 256, 0, stream>>>(p);
+  const size_t vec_bytes = (size_t)iters * K * sab_vec(C, hidden).total * sizeof(float);
+  const int red_staged = (vec_bytes <= 160 * 1024 && C % 4 == 0 && hidden % 4 == 0 && (reinterpret_cast<uintptr_t>(p.vec_store) & 15) == 0) ? 1 : 0;
+  if (red_staged && cudaFuncSetAttribute(sa_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess) return UORF_ERR_DEVICE;
+  sa_bwd_reduce_kernel<<<148, 256, red_staged ? vec_bytes : 0, stream>>>(p, red_staged);
   return finish_launch(2 * iters + 3);
 }
 
