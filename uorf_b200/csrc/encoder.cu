@@ -376,7 +376,7 @@ int launch_encoder_weight_prep(const uorf_encoder_prep_layer* layers, int n_laye
   if (n_layers > 8) return UORF_ERR_UNSUPPORTED;
   EncPrepTable t = {};
   for (int i = 0; i < n_layers; ++i) t.l[i] = layers[i];
-  encoder_weight_prep_kernel<<<dim3(16, n_layers), 256, 0, stream>>>(t);
+  encoder_weight_prep_kernel<<<dim3(96, n_layers), 256, 0, stream>>>(t);
   return finish_launch(1);
 }
 
