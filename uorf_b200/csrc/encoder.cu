@@ -129,7 +129,13 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_conv3x3_kernel(const E
   const int grp = tid / kEncGroupThreads, t = tid % kEncGroupThreads;
   const int og = t & 7;                    // output-channel group: channels oc_base + 4*og .. +3
   const int pg = t >> 3;                   // pixel group 0..15: row pg >> 1, columns 4*(pg & 1) .. +3
-  const int py = pg >> 1, px0 = (pg & 1) * 4;
+  // zero-inserted gradient (stride-2 data gradient): three quarters of the patch are structural zeros.  Rows are dealt so that a warp
+  // owns two rows of the SAME parity (0,2 | 1,3 | 4,6 | 5,7): the tap rows that meet only zero rows are skipped warp-uniformly, and
+  // within a row the (pixel, tap column) pairs that meet zero columns are skipped at compile time - a quarter of the FMAs remain
+  constexpr bool ZI = MODE == kSlotGradZi;
+  const int wq = t >> 5, q4 = pg & 3;
+  const int py = ZI ? 4 * (wq >> 1) + (wq & 1) + 2 * (q4 >> 1) : pg >> 1;
+  const int px0 = (pg & 1) * 4;
   const int cin = p.ca + p.cb;
   float acc[4][4];
 #pragma unroll
@@ -193,6 +199,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_conv3x3_kernel(const E
         const int i = grp * kEncIcPerGroup + ii;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
+          if (ZI && ((py + ky + 1) & 1)) continue;            // image row ty0 + py + ky - 1 is odd: a zero row (ty0 is a multiple of 8)
           float a[NCOL];
           const float* row = &s_in[i][py * STRIDE + ky][px0 * STRIDE];
 #pragma unroll
@@ -202,6 +209,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encoder_conv3x3_kernel(const E
             const float4 w = *reinterpret_cast<const float4*>(&s_w[i][ky * 3 + kx][4 * og]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+              if (ZI && !((j + kx) & 1)) continue;            // image column tx0 + px0 + j + kx - 1 is odd: a zero column
               const float v = a[j * STRIDE + kx];
               acc[j][0] = fmaf(v, w.x, acc[j][0]);
               acc[j][1] = fmaf(v, w.y, acc[j][1]);
