@@ -314,6 +314,23 @@ int uorf_conv3x3_stem(const float* x, const float* weight, const float* bias, in
 int uorf_conv3x3_stem_dgrad(const float* grad_y, const float* y, const float* weight, int32_t n, int32_t h, int32_t w, int32_t c_out,
                             float* grad_x, void* stream);
 
+/* Image-side losses of the training step (models/uorf_nogan_model.py:168-183: `x_recon = rendered * 2 - 1`, `L2_loss(x_recon, x)`,
+ * `vgg_normalizer` of both images, `L2_loss` of the two feature maps), each direction one launch; means are block partial sums
+ * added in a fixed order (bit-reproducible).  `scratch`: UORF_LOSS_SCRATCH_FLOATS floats, ZERO-INITIALISED ONCE by the caller and
+ * then left alone (it holds the partial sums and a self-resetting ticket); one scratch per call site.
+ *   uorf_image_loss_forward:   rgb_map [n*hw][3] (uorf_composite_forward's rgb), x [n][3][hw], mean / stdv [3] ->
+ *                              x_recon, rendered, rendered_norm, x_norm [n][3][hw], *loss_recon = mean((x_recon - x)^2)
+ *   uorf_image_loss_backward:  grad_rgb_map [n*hw][3] from grad_x_recon / grad_rendered_norm [n][3][hw] and *grad_loss (each may be NULL)
+ *   uorf_feature_mse_forward:  features = [rendered half | ground-truth half], m floats each, same layout -> *loss = mean((a - b)^2)
+ *   uorf_feature_mse_backward: grad_features [2 m]: first half *grad_loss * 2 (a - b) / m, second half zero (constants) */
+#define UORF_LOSS_SCRATCH_FLOATS 72
+int uorf_image_loss_forward(const float* rgb_map, const float* x, const float* mean, const float* stdv, int32_t n, int32_t hw, float* x_recon,
+                            float* rendered, float* rendered_norm, float* x_norm, float* scratch, float* loss_recon, void* stream);
+int uorf_image_loss_backward(const float* x_recon, const float* x, const float* stdv, const float* grad_x_recon, const float* grad_rendered_norm,
+                             const float* grad_loss, int32_t n, int32_t hw, float* grad_rgb_map, void* stream);
+int uorf_feature_mse_forward(const float* features, int64_t m, float* scratch, float* loss, void* stream);
+int uorf_feature_mse_backward(const float* features, const float* grad_loss, int64_t m, float* grad_features, void* stream);
+
 /* Inverse of `batch` row-major dim x dim matrices (dim 3 or 4), device to device, one launch: the `.inverse()` of the scene pose in
  * the drivers' set_input (models/uorf_nogan_model.py:117-126, uorf_eval_model.py:98-107) when the pose already lives on the device.
  * Gauss-Jordan with partial pivoting in fp32; a singular matrix gives inf / nan entries as the library does. */

@@ -668,3 +668,34 @@ def test_invert_pose_matches_torch_inverse():
         assert torch.all(res_got <= 4 * res_ref + 1e-6), (res_got.max().item(), res_ref.max().item())
         assert ((got.double() - want).abs().amax(dim=(-2, -1)) <= 1e-5 * want.abs().amax(dim=(-2, -1)) * (1 + res_ref * 1e5)).all()
     assert invert_pose(poses[0:1]).shape == (1, 4, 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stage", ["coarse", "fine"])
+def test_fused_losses_match_torch_expressions(stage):
+    """opt.fused_losses (uorf_image_loss_* / uorf_feature_mse_*: x_recon, both MSEs, vgg_normalizer of both images in one launch each
+    way) against the reference's torch expressions (models/uorf_nogan_model.py:168-183) in the same driver: losses and every gradient"""
+    from uorf_b200.nogan_model import uorfNoGanModel, default_train_options
+    g = load_golden("train_driver_" + stage)
+    size = dict(frustum_size=16, frustum_size_fine=32, render_size=16, supervision_size=16) if stage == "coarse" else \
+        dict(frustum_size=8, frustum_size_fine=16, render_size=8, supervision_size=8)          # the golden scene's image is 16 x 16
+    kw = dict(num_slots=3, z_dim=40, n_samp=8, input_size=32, n_img_each_scene=2, stage=stage, bottom=stage == "fine", gpu_ids=[0],
+              vgg_random_init=True, percept_in=0, **size)
+    inp = {"img_data": g["img"], "cam2world": g["cam2world"], "azi_rot": g["azi_rot"], "paths": []}
+    res = {}
+    for fused in (False, True):
+        torch.manual_seed(4)                                             # the same randomly initialised VGG16 for both models
+        m = uorfNoGanModel(default_train_options(fused_losses=fused, **kw), precision="fp16x3", with_perceptual=True)
+        m.load_networks_from_state_dicts(g["enc"], g["sa"], g["dec"])
+        m.slot_noise = (g["noise_fg"].to(dev()), g["noise_bg"].to(dev()))
+        m.crop_override = (3, 5)
+        m.set_input(inp)
+        m.forward(epoch=1)
+        assert m.fused_losses == fused and m.weight_percept > 0
+        m.backward()
+        res[fused] = (float(m.loss_recon), float(m.loss_perc), m.x_recon.clone(), {n: p_.grad.detach().clone() for n, p_ in m.named_parameters()})
+    a, b = res[False], res[True]
+    assert abs(a[0] - b[0]) <= 2e-6 * abs(a[0]) and abs(a[1] - b[1]) <= 2e-6 * abs(a[1]) + 1e-12, (a[:2], b[:2])
+    assert torch.equal(a[2], b[2])                                   # x_recon: the same two roundings
+    for n in a[3]:
+        assert maxerr(a[3][n], b[3][n]) <= 2e-5 * max(a[3][n].abs().max().item(), 1e-12), n

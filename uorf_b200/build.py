@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libuorf_b200.so")
-SOURCES = ["abi.cu", "encoder.cu", "sample_coords.cu", "decoder_prep.cu", "decoder_fwd.cu", "decoder_fwd_x3.cu", "decoder_bwd.cu", "composite.cu", "conv3x3.cu", "adam.cu",
+SOURCES = ["abi.cu", "encoder.cu", "sample_coords.cu", "decoder_prep.cu", "decoder_fwd.cu", "decoder_fwd_x3.cu", "decoder_bwd.cu", "composite.cu", "conv3x3.cu", "adam.cu", "losses.cu",
            "slot_attention.cu", "slot_attention_bwd.cu"]
 # test / diagnostic hooks (tcgen05 layout probes, hand-off timing): their own library, never linked into the product .so
 PROBE_LIB = os.path.join(OUT, "libuorf_b200_probe.so")

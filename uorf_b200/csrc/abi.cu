@@ -27,6 +27,12 @@ int launch_vgg_stem_dgrad(const float* g, const float* y, const float* weight, i
 int launch_encoder_weight_prep(const uorf_encoder_prep_layer* layers, int n_layers, cudaStream_t stream);
 int launch_conv_split_pool(const float* x, const float* g, void* hi, void* lo, int n, int h, int w, int c, int f16, int num_sms, cudaStream_t stream);
 int launch_invert_small(const float* src, float* dst, int batch, int dim, cudaStream_t stream);
+int launch_image_loss_fwd(const float* rgb, const float* x, const float* mean, const float* stdv, int n, int hw, float* x_recon, float* rendered,
+                          float* rendered_norm, float* x_norm, float* scratch, float* loss, cudaStream_t stream);
+int launch_image_loss_bwd(const float* x_recon, const float* x, const float* stdv, const float* g_x_recon, const float* g_rendered_norm,
+                          const float* g_loss, int n, int hw, float* grad_rgb, cudaStream_t stream);
+int launch_feat_mse_fwd(const float* f, long long m, float* scratch, float* loss, cudaStream_t stream);
+int launch_feat_mse_bwd(const float* f, const float* g_loss, long long m, float* grad, cudaStream_t stream);
 int launch_adam_step(const uorf_adam_chunk* chunks, int n_chunks, const float* lr_dev, float lr_host, float beta1, float beta2, float eps,
                      float weight_decay, cudaStream_t stream);
 int launch_encoder_conv3x3(const float* src_a, int ca, int up_a, const float* src_b, int cb, const float* weight_t, const float* bias,
@@ -218,6 +224,46 @@ int uorf_invert_small(const float* src, float* dst, int32_t batch, int32_t dim, 
   if (batch < 0 || (batch > 0 && (!src || !dst))) return fail(UORF_ERR_ARG, "uorf_invert_small: null pointer%s");
   if (dim != 3 && dim != 4) return fail(UORF_ERR_ARG, "uorf_invert_small: dim must be 3 or 4%s");
   return check_launch(uorf::launch_invert_small(src, dst, batch, dim, static_cast<cudaStream_t>(stream)), "uorf_invert_small");
+}
+
+int uorf_image_loss_forward(const float* rgb_map, const float* x, const float* mean, const float* stdv, int32_t n, int32_t hw, float* x_recon,
+                            float* rendered, float* rendered_norm, float* x_norm, float* scratch, float* loss_recon, void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_image_loss_forward");
+  if (!c) return UORF_ERR_DEVICE;
+  if (!rgb_map || !x || !mean || !stdv || !x_recon || !rendered || !rendered_norm || !x_norm || !scratch || !loss_recon)
+    return fail(UORF_ERR_ARG, "uorf_image_loss_forward: null pointer%s");
+  if (n < 1 || hw < 1) return fail(UORF_ERR_ARG, "uorf_image_loss_forward: bad sizes%s");
+  return check_launch(uorf::launch_image_loss_fwd(rgb_map, x, mean, stdv, n, hw, x_recon, rendered, rendered_norm, x_norm, scratch, loss_recon,
+                                                  static_cast<cudaStream_t>(stream)), "uorf_image_loss_forward");
+}
+
+int uorf_image_loss_backward(const float* x_recon, const float* x, const float* stdv, const float* grad_x_recon, const float* grad_rendered_norm,
+                             const float* grad_loss, int32_t n, int32_t hw, float* grad_rgb_map, void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_image_loss_backward");
+  if (!c) return UORF_ERR_DEVICE;
+  if (!x_recon || !x || !stdv || !grad_rgb_map) return fail(UORF_ERR_ARG, "uorf_image_loss_backward: null pointer%s");
+  if (n < 1 || hw < 1) return fail(UORF_ERR_ARG, "uorf_image_loss_backward: bad sizes%s");
+  return check_launch(uorf::launch_image_loss_bwd(x_recon, x, stdv, grad_x_recon, grad_rendered_norm, grad_loss, n, hw, grad_rgb_map,
+                                                  static_cast<cudaStream_t>(stream)), "uorf_image_loss_backward");
+}
+
+int uorf_feature_mse_forward(const float* features, int64_t m, float* scratch, float* loss, void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_feature_mse_forward");
+  if (!c) return UORF_ERR_DEVICE;
+  if (!features || !scratch || !loss || m < 1) return fail(UORF_ERR_ARG, "uorf_feature_mse_forward: bad arguments%s");
+  return check_launch(uorf::launch_feat_mse_fwd(features, m, scratch, loss, static_cast<cudaStream_t>(stream)), "uorf_feature_mse_forward");
+}
+
+int uorf_feature_mse_backward(const float* features, const float* grad_loss, int64_t m, float* grad_features, void* stream) {
+  DeviceCtx* c = ctx();
+  Range nvtx_range("uorf_feature_mse_backward");
+  if (!c) return UORF_ERR_DEVICE;
+  if (!features || !grad_loss || !grad_features || m < 1) return fail(UORF_ERR_ARG, "uorf_feature_mse_backward: bad arguments%s");
+  return check_launch(uorf::launch_feat_mse_bwd(features, grad_loss, m, grad_features, static_cast<cudaStream_t>(stream)),
+                      "uorf_feature_mse_backward");
 }
 
 int uorf_adam_step(const uorf_adam_chunk* chunks, int32_t n_chunks, const float* lr_dev, float lr_host, float beta1, float beta2, float eps,

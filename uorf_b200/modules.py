@@ -378,6 +378,79 @@ def _encoder_backward(enc, a, g_out, x_needs_grad):
     return (gx[:, :a["img"].shape[0]] if x_needs_grad else None), grads
 
 
+_LOSS_SCRATCH_FLOATS = 72        # UORF_LOSS_SCRATCH_FLOATS (include/uorf_b200.h)
+
+
+def loss_scratch(device) -> torch.Tensor:
+    """the zero-initialised scratch a fused-loss call site keeps for its whole life (partial sums + a self-resetting ticket)"""
+    return torch.zeros(_LOSS_SCRATCH_FLOATS, device=device, dtype=torch.float32)
+
+
+class _ImageLossFn(torch.autograd.Function):
+    """rgb_map (N*H*W) x 3 from raw2outputs, x N x 3 x H x W -> x_recon, rendered, rendered_norm, x_norm (N x 3 x H x W) and loss_recon =
+    mse(x_recon, x): `uorf_image_loss_forward / _backward` (reference models/uorf_nogan_model.py:168-183, ~17 torch launches)."""
+
+    @staticmethod
+    def forward(ctx, rgb_map, x, mean, std, scratch):
+        n, _, h, w = x.shape
+        rgb_c, x_c = _f32c(rgb_map), _f32c(x)
+        outs = [torch.empty(n, 3, h, w, device=x.device, dtype=torch.float32) for _ in range(4)]
+        loss = torch.empty((), device=x.device, dtype=torch.float32)
+        with _on(x_c):
+            check(lib().uorf_image_loss_forward(rgb_c.data_ptr(), x_c.data_ptr(), mean.data_ptr(), std.data_ptr(), n, h * w, outs[0].data_ptr(),
+                                                outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), scratch.data_ptr(), loss.data_ptr(),
+                                                _stream(x_c)), "uorf_image_loss_forward")
+        ctx.save_for_backward(outs[0], x_c, std)
+        ctx.shape = (n, h, w)
+        ctx.mark_non_differentiable(outs[1], outs[3])
+        ctx.set_materialize_grads(False)
+        return outs[0], outs[1], outs[2], outs[3], loss
+
+    @staticmethod
+    def backward(ctx, g_x_recon, g_rendered, g_rn, g_x_norm, g_loss):
+        x_recon, x_c, std = ctx.saved_tensors
+        n, h, w = ctx.shape
+        if g_x_recon is None and g_rn is None and g_loss is None:
+            return None, None, None, None, None
+        gxr = _f32c(g_x_recon) if g_x_recon is not None else None
+        grn = _f32c(g_rn) if g_rn is not None else None
+        gl = _f32c(g_loss) if g_loss is not None else None
+        g_rgb = torch.empty(n * h * w, 3, device=x_c.device, dtype=torch.float32)
+        with _on(x_c):
+            check(lib().uorf_image_loss_backward(x_recon.data_ptr(), x_c.data_ptr(), std.data_ptr(), _ptr(gxr), _ptr(grn), _ptr(gl), n, h * w,
+                                                 g_rgb.data_ptr(), _stream(x_c)), "uorf_image_loss_backward")
+        return g_rgb, None, None, None, None
+
+
+class _FeatureMseFn(torch.autograd.Function):
+    """features of [rendered images | ground-truth images] in one batch (any layout, the same for both halves) -> mse of the two halves;
+    the gradient reaches the rendered half only (the reference detaches nothing but its ground-truth branch is constant)."""
+
+    @staticmethod
+    def forward(ctx, feats, scratch):
+        base = feats if feats.is_contiguous() else (feats.permute(0, 2, 3, 1) if feats.dim() == 4 and feats.permute(0, 2, 3, 1).is_contiguous()
+                                                    else feats.contiguous())
+        if base.dtype != torch.float32 or base.shape[0] % 2:
+            raise _lib.UorfError("feature mse: fp32 features of an even batch (rendered half, ground-truth half)")
+        m = base.numel() // 2
+        loss = torch.empty((), device=feats.device, dtype=torch.float32)
+        with _on(base):
+            check(lib().uorf_feature_mse_forward(base.data_ptr(), m, scratch.data_ptr(), loss.data_ptr(), _stream(base)), "uorf_feature_mse_forward")
+        ctx.save_for_backward(base)
+        ctx.perm = base.data_ptr() == feats.data_ptr() and not feats.is_contiguous()      # feats is the NCHW view of an NHWC buffer
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (base,) = ctx.saved_tensors
+        m = base.numel() // 2
+        g = torch.empty_like(base)
+        gl = _f32c(g_loss)
+        with _on(base):
+            check(lib().uorf_feature_mse_backward(base.data_ptr(), gl.data_ptr(), m, g.data_ptr(), _stream(base)), "uorf_feature_mse_backward")
+        return (g.permute(0, 3, 1, 2) if ctx.perm else g), None
+
+
 def invert_pose(m: torch.Tensor) -> torch.Tensor:
     """`m.inverse()` for the drivers' pose matrices (... x 3 x 3 or ... x 4 x 4): one launch of uorf_invert_small for fp32 CUDA
     tensors (torch's route is an LU factorisation + triangular solves: 13 launches for 16 numbers), torch's own inverse otherwise"""

@@ -25,7 +25,8 @@ from torch.optim.lr_scheduler import LambdaLR
 
 from . import optim as _optim
 from .eval_model import init_weights_like_reference
-from .modules import Decoder, Encoder, PerceptualVGG, Projection, SlotAttention, invert_pose, raw2outputs
+from .modules import (Decoder, Encoder, PerceptualVGG, Projection, SlotAttention, _FeatureMseFn, _ImageLossFn, invert_pose, loss_scratch,
+                      raw2outputs)
 
 
 def default_train_options(**over) -> argparse.Namespace:
@@ -139,6 +140,8 @@ class uorfNoGanModel:
         # every gradient in ONE persistent flat buffer the backward kernels write into (also on one GPU: the autograd path costs
         # an AccumulateGrad `add` launch per parameter - 83 per step - and per-tensor fills); False: plain autograd accumulation
         self.flat_grad_bucket = bool(getattr(opt, "flat_grad_bucket", True))
+        self.fused_losses = bool(getattr(opt, "fused_losses", os.environ.get("UORF_FUSED_LOSSES", "1") == "1"))
+        self._loss_scratch = None
         self._flat_grad = None        # data-parallel mode: the flat gradient bucket every .grad is a view of
 
     def parameters(self):
@@ -196,17 +199,33 @@ class uorfNoGanModel:
         raws, masked_raws, unmasked_raws, _ = self.netDecoder(coords, coords[None, ...].expand(K - 1, -1, -1), z_slots, self.nss2cam0,
                                                               dens_noise=dens_noise)
         rgb_map, _, _ = raw2outputs(raws.view(N * H * W, D, 4), z_vals, ray_dir)
-        rendered = rgb_map.view(N, H, W, 3).permute([0, 3, 1, 2])
-        x_recon = rendered * 2 - 1
-        self.loss_recon = self.L2_loss(x_recon, x)
+        # image-side glue (x_recon, MSE, vgg_normalizer of both images) as one launch each way; opt.fused_losses=False /
+        # UORF_FUSED_LOSSES=0: the reference's torch expressions (~25 tiny launches per step)
+        fused = self.fused_losses and x.dtype == torch.float32 and rgb_map.dtype == torch.float32
+        rendered_norm = x_norm = None
+        if fused:
+            if self._loss_scratch is None:
+                self._loss_scratch = (loss_scratch(dev), loss_scratch(dev))
+                self._vgg_mean3 = (self._vgg_mean if self.with_perceptual else torch.zeros(3, device=dev)).reshape(3).contiguous()
+                self._vgg_std3 = (self._vgg_std if self.with_perceptual else torch.ones(3, device=dev)).reshape(3).contiguous()
+            x_recon, rendered, rendered_norm, x_norm, self.loss_recon = _ImageLossFn.apply(rgb_map, x, self._vgg_mean3, self._vgg_std3,
+                                                                                           self._loss_scratch[0])
+        else:
+            rendered = rgb_map.view(N, H, W, 3).permute([0, 3, 1, 2])
+            x_recon = rendered * 2 - 1
+            self.loss_recon = self.L2_loss(x_recon, x)
         self.loss_extra = self._extra_generator_loss(x_recon, x, epoch)   # None here; the adversarial term of the GAN driver
         if self.with_perceptual and self.weight_percept == 0:
             # the reference evaluates both VGG passes and multiplies by zero (:181-183): skipped, the loss is exactly 0
             self.loss_perc = torch.zeros((), device=dev)
         elif self.with_perceptual:
-            rendered_norm = (rendered - self._vgg_mean) / self._vgg_std
-            x_norm = (((x + 1) / 2 - self._vgg_mean) / self._vgg_std).detach()
-            if isinstance(self.perceptual_net, PerceptualVGG):
+            if rendered_norm is None:
+                rendered_norm = (rendered - self._vgg_mean) / self._vgg_std
+                x_norm = (((x + 1) / 2 - self._vgg_mean) / self._vgg_std).detach()
+            if isinstance(self.perceptual_net, PerceptualVGG) and fused:
+                feats = self.perceptual_net(rendered_norm, x_const=x_norm)
+                self.loss_perc = self.weight_percept * _FeatureMseFn.apply(feats, self._loss_scratch[1])
+            elif isinstance(self.perceptual_net, PerceptualVGG):
                 # both images in ONE pass (half the launches, twice the tiles per launch); the ground-truth half carries no
                 # gradient: its features are detached and the convolution's backward skips those rows
                 feats = self.perceptual_net(rendered_norm, x_const=x_norm)
@@ -215,7 +234,8 @@ class uorfNoGanModel:
                 rendered_feat = self.perceptual_net(rendered_norm)
                 with torch.no_grad():      # the ground-truth branch carries no gradient (frozen VGG, constant images)
                     x_feat = self.perceptual_net(x_norm)
-            self.loss_perc = self.weight_percept * self.L2_loss(rendered_feat, x_feat)
+            if not (isinstance(self.perceptual_net, PerceptualVGG) and fused):
+                self.loss_perc = self.weight_percept * self.L2_loss(rendered_feat, x_feat)
         else:
             self.loss_perc = torch.zeros((), device=dev)
         with torch.no_grad():
