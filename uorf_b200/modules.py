@@ -1164,7 +1164,7 @@ class PerceptualVGG(nn.Module):
         c = L[0][1]
         if not (c.in_channels == 3 and c.kernel_size == (3, 3) and c.stride == (1, 1) and c.padding == (1, 1) and c.dilation == (1, 1)
                 and c.groups == 1 and c.bias is not None and c.out_channels % 4 == 0 and c.out_channels <= 64 and c.weight.is_cuda
-                and c.weight.dtype == torch.float32):
+                and c.weight.dtype == torch.float32 and c.weight.is_contiguous() and c.bias.is_contiguous()):
             return None
         ops = [("stem", c)]
         for l in L[2:]:

@@ -64,6 +64,9 @@ class Adam(optim.Adam):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        if getattr(self, "grad_scale", None) is not None or getattr(self, "found_inf", None) is not None:
+            super().step()           # a GradScaler drives this step (unscale / skip logic lives in torch's implementation)
+            return loss
         plan = []
         for gi, group in enumerate(self.param_groups):
             params, grads, exp_avgs, exp_avg_sqs, max_sqs, steps = [], [], [], [], [], []
